@@ -1,0 +1,180 @@
+/*
+ * prl.h — C ABI of libprl.so, the B200 (sm_100a) hot-path library behind the
+ * PipelineRL plugin / stream API.
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every device buffer is owned by the caller; the library owns only opaque
+ *     handles it hands out from *_create and frees in *_destroy;
+ *   - no allocation inside hot calls; every call takes an explicit stream
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - functions return 0 on success, <0 on error; prl_last_error() gives the
+ *     message for the calling thread. Nothing throws across the ABI;
+ *   - the library is not internally threaded: one host thread per GPU drives it.
+ *
+ * Each entry point cites the reference interface it replaces
+ * (paths relative to the ServiceNow/PipelineRL tree).
+ */
+#ifndef PRL_H_
+#define PRL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRL_OK 0
+#define PRL_ERR_INVALID (-1)   /* bad argument */
+#define PRL_ERR_CUDA (-2)      /* CUDA runtime / driver error */
+#define PRL_ERR_UNSUPPORTED (-3)
+#define PRL_ERR_NONFINITE (-4) /* reproduces the reference's isfinite asserts */
+
+typedef void* prl_stream_t; /* cudaStream_t */
+
+/* ---- library ---------------------------------------------------------- */
+const char* prl_last_error(void);
+int prl_version(void);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+uint64_t prl_launch_count(void);
+
+/* ======================================================================= *
+ * Hot path (2a): policy-gradient loss tail
+ *   replaces pipelinerl/finetune/rl/__init__.py:237-439 (rl_step after the
+ *   logprob tail) and rl/utils.py:71-92 (sum_sum) — one launch instead of
+ *   ~25 per-segment Python loops and ~30 .item() syncs.
+ * ======================================================================= */
+
+enum { PRL_LOSS_PPO = 0, PRL_LOSS_REINFORCE = 1, PRL_LOSS_GSPO = 2 };
+
+/* index of each statistic in the stats[] output (order of rl/__init__.py:398-439) */
+enum {
+  PRL_STAT_LOSS = 0, PRL_STAT_MAX_LOSS, PRL_STAT_MIN_LOSS,
+  PRL_STAT_REWARD, PRL_STAT_MAX_REWARD, PRL_STAT_MIN_REWARD,
+  PRL_STAT_ENTROPY, PRL_STAT_OLD_LOGPROBS, PRL_STAT_NEW_LOGPROBS, PRL_STAT_REF_LOGPROBS,
+  PRL_STAT_ADVANTAGE, PRL_STAT_MAX_ADVANTAGE, PRL_STAT_MIN_ADVANTAGE,
+  PRL_STAT_KL, PRL_STAT_KL_NEW_OLD, PRL_STAT_MEAN_ABS_LOG_RATIO_NEW_OLD,
+  PRL_STAT_MAX_KL, PRL_STAT_MIN_KL,
+  PRL_STAT_RATIO_NEW_OLD, PRL_STAT_RATIO_NEW_OLD_SUM, PRL_STAT_RATIO_NEW_OLD_SQUARED_SUM,
+  PRL_STAT_RATIO_REF_NEW, PRL_STAT_RATIO_REF_OLD,
+  PRL_STAT_CLAMP_LOG_RATIO_REF_NEW_INDICATOR, PRL_STAT_CLAMP_LOG_RATIO_NEW_OLD_INDICATOR,
+  PRL_STAT_TOKEN_WEIGHT, PRL_STAT_MAX_TOKEN_WEIGHT, PRL_STAT_MIN_TOKEN_WEIGHT,
+  PRL_STAT_KL_COEF, PRL_STAT_ENTROPY_BONUS_COEF,
+  PRL_STAT_NUM_OUTPUT_TOKENS_SUM, PRL_STAT_INPUT_SIZE,
+  PRL_NUM_STATS /* = 32 */
+};
+
+/* RLConfig fields the loss tail reads (rl/__init__.py:43-105), with the decayed
+ * coefficients already evaluated by the caller (linear_decay_coef, :119-133). */
+typedef struct {
+  int32_t policy_loss;          /* PRL_LOSS_* */
+  int32_t use_advantages;       /* bool */
+  int32_t relu_log_p_weights;   /* bool */
+  int32_t group_normalization;  /* bool */
+  int32_t overlong_filtering;   /* bool */
+  int32_t use_entropy_loss;     /* bool: entropy_bonus != 0 or final_entropy_bonus != 0 */
+  float epsilon_low, epsilon_high;
+  float clamp_log_ratio_ref_new_value;
+  float kl_coef;                /* already decayed for current_step */
+  float entropy_bonus_coef;     /* already decayed */
+  float batch_size;             /* config.batch_size (token weight = 1/batch_size) */
+} prl_pg_config;
+
+/* One packed row [1, T] (PipelineBatchEncoding, finetune/types.py:46-75). All
+ * pointers are device pointers. Token-aligned columns are UNSHIFTED, length T;
+ * the kernel applies the reference's [:, 1:] shift itself. new_logprobs and
+ * entropy are the outputs of the logprob tail, length T-1 (position t holds the
+ * log-probability of token t+1). */
+typedef struct {
+  int64_t T;                   /* tokens in the packed row (input_ids.numel()) */
+  const float* new_logprobs;   /* [T-1] */
+  const float* entropy;        /* [T-1] or NULL (treated as 0) */
+  const int64_t* labels;       /* [T]  mask = labels[t+1] != -100 */
+  const float* rewards;        /* [T] */
+  const float* advantages;     /* [T] */
+  const float* ref_logprobs;   /* [T] */
+  const float* old_logprobs;   /* [T] */
+  const float* group_tokens;   /* [T] */
+  const float* num_labels;     /* [T] */
+  const float* overflow;       /* [T] */
+  const int64_t* segment_ids;  /* [T] or NULL; required for PRL_LOSS_GSPO */
+  const int64_t* position_ids; /* [T] or NULL. When given, num_sequences is counted on the device as
+                                  1 + #{t >= 1 : position_ids[t] == 0} (rl/__init__.py:166-178) */
+  int32_t n_segments;          /* GSPO: any upper bound on max(segment_ids[1:]) + 1 (empty segments
+                                  contribute nothing, as in the reference); else ignored */
+  int32_t num_sequences;       /* used when position_ids is NULL (unpacked batch: number of rows) */
+  int32_t sentinel;            /* batch.sentinel */
+} prl_pg_batch;
+
+/* Scratch the caller allocates once: prl_pg_workspace_bytes(max n_segments) bytes. */
+size_t prl_pg_workspace_bytes(int32_t max_segments);
+
+/* Forward + backward of the loss tail in one pass.
+ *   loss          [1]  device, = final_loss (policy_loss_total)
+ *   dloss_dlogprob[T-1] device, d final_loss / d new_logprobs (may be NULL)
+ *   dloss_dentropy[T-1] device or NULL, d final_loss / d entropy (only non-zero
+ *                       when use_entropy_loss)
+ *   stats         [PRL_NUM_STATS] device doubles, the reference's stats dict;
+ *                 when no token is labelled only PRL_STAT_INPUT_SIZE is meaningful
+ *                 (rl/__init__.py:388-392) and PRL_STAT_NUM_OUTPUT_TOKENS_SUM is 0.
+ *   nonfinite     [1] device int32: bitmask, bit0 new_logprobs, bit1 log_ratio_ref_new,
+ *                 bit2 approx_kl, bit3 loss (the reference's asserts :213,263,291,386)
+ */
+int prl_pg_loss_fwd_bwd(const prl_pg_batch* batch, const prl_pg_config* cfg,
+                        float* loss, float* dloss_dlogprob, float* dloss_dentropy,
+                        double* stats, int32_t* nonfinite,
+                        void* workspace, size_t workspace_bytes, prl_stream_t stream);
+
+/* ======================================================================= *
+ * Hot path (2b, generic-model variant): logprob tail from materialised logits
+ *   replaces pipelinerl/finetune/rl/__init__.py:207-233 (logits/T, gather,
+ *   logsumexp, 38-chunk entropy) with one read of the logits; backward reads
+ *   once, writes once.  logits [T, V] fp32 with row stride `row_stride`
+ *   elements; outputs have T-1 entries (position t scores token t+1).
+ * ======================================================================= */
+int prl_logprob_tail_fwd(const float* logits, int64_t T, int64_t V, int64_t row_stride,
+                         const int64_t* input_ids, float temperature,
+                         float* new_logprobs /*[T-1]*/, float* entropy /*[T-1] or NULL*/,
+                         float* lse /*[T-1] or NULL, saved for backward*/, prl_stream_t stream);
+/* dlogits [T, V] (row T-1 is zero-filled).  g_entropy may be NULL. */
+int prl_logprob_tail_bwd(const float* logits, int64_t T, int64_t V, int64_t row_stride,
+                         const int64_t* input_ids, float temperature,
+                         const float* lse, const float* entropy,
+                         const float* g_logprobs, const float* g_entropy,
+                         float* dlogits, int64_t dlogits_stride, prl_stream_t stream);
+
+/* ======================================================================= *
+ * Hot path (2c): fused AdamW over a flat parameter arena
+ *   replaces torch.optim.AdamW as built by pipelinerl/finetune/optim.py:25-29
+ *   + clip_grad_norm_ (finetune_loop.py:739) + the bf16 re-cast of the
+ *   DeepSpeed bf16 optimizer (finetune_loop.py:727-736).
+ * ======================================================================= */
+typedef struct {
+  int64_t n;                 /* elements in the arena */
+  float* master;             /* [n] fp32 master weights (in/out) */
+  float* exp_avg;            /* [n] (in/out) */
+  float* exp_avg_sq;         /* [n] (in/out) */
+  const void* grad;          /* [n] bf16 or fp32 gradient */
+  int32_t grad_is_bf16;
+  void* param_bf16;          /* [n] bf16 copy consumed by fwd/bwd and the weight push (out), or NULL */
+  void* param_bf16_lo;       /* [n] bf16 residual master - bf16(master) (out) or NULL: fp32-equivalent head */
+  /* weight-decay groups (optim.py:8-22): tensor t covers [tensor_offsets[t], tensor_offsets[t+1]) */
+  const int64_t* tensor_offsets; /* device [n_tensors+1], ascending, [0]=0, [n_tensors]=n */
+  const uint8_t* tensor_no_decay;/* device [n_tensors] 1 = weight_decay 0 (bias / LayerNorm.weight) */
+  int32_t n_tensors;
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t step;              /* 1-based optimizer step (bias correction) */
+  float max_grad_norm;       /* <=0: no clipping */
+  float grad_scale;          /* gradients are multiplied by this before use (1/accum etc.); 1.0 default */
+} prl_adamw_args;
+
+size_t prl_adamw_workspace_bytes(void);
+/* grad_norm_out: device float[1], the pre-clip global L2 norm (as clip_grad_norm_ returns). */
+int prl_adamw_step(const prl_adamw_args* args, float* grad_norm_out,
+                   void* workspace, size_t workspace_bytes, prl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRL_H_ */

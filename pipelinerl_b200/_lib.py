@@ -1,0 +1,128 @@
+"""ctypes binding of libprl.so (include/prl.h).
+
+The product path has no CPU fallback: if the library is missing this module
+raises on first use.  Nothing under oracle/ is imported here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libprl.so"
+_lib = None
+
+
+class PrlError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libprl error {code}: {msg}")
+        self.code = code
+
+
+class NonFiniteError(AssertionError):
+    """Mirrors the reference's `assert torch.isfinite(...)` (rl/__init__.py:213,263,291,386)."""
+
+
+# ---- structs (field order = include/prl.h) -------------------------------------
+class PgConfig(C.Structure):
+    _fields_ = [
+        ("policy_loss", C.c_int32), ("use_advantages", C.c_int32), ("relu_log_p_weights", C.c_int32),
+        ("group_normalization", C.c_int32), ("overlong_filtering", C.c_int32), ("use_entropy_loss", C.c_int32),
+        ("epsilon_low", C.c_float), ("epsilon_high", C.c_float), ("clamp_log_ratio_ref_new_value", C.c_float),
+        ("kl_coef", C.c_float), ("entropy_bonus_coef", C.c_float), ("batch_size", C.c_float),
+    ]
+
+
+class PgBatch(C.Structure):
+    _fields_ = [
+        ("T", C.c_int64),
+        ("new_logprobs", C.c_void_p), ("entropy", C.c_void_p), ("labels", C.c_void_p),
+        ("rewards", C.c_void_p), ("advantages", C.c_void_p), ("ref_logprobs", C.c_void_p),
+        ("old_logprobs", C.c_void_p), ("group_tokens", C.c_void_p), ("num_labels", C.c_void_p),
+        ("overflow", C.c_void_p), ("segment_ids", C.c_void_p), ("position_ids", C.c_void_p),
+        ("n_segments", C.c_int32), ("num_sequences", C.c_int32), ("sentinel", C.c_int32),
+    ]
+
+
+class AdamwArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64),
+        ("master", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+        ("grad", C.c_void_p), ("grad_is_bf16", C.c_int32),
+        ("param_bf16", C.c_void_p), ("param_bf16_lo", C.c_void_p),
+        ("tensor_offsets", C.c_void_p), ("tensor_no_decay", C.c_void_p), ("n_tensors", C.c_int32),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("weight_decay", C.c_float), ("step", C.c_int32), ("max_grad_norm", C.c_float),
+        ("grad_scale", C.c_float),
+    ]
+
+
+PRL_NUM_STATS = 32
+LOSS_IDS = {"ppo": 0, "reinforce": 1, "gspo": 2}
+STAT_NAMES = [
+    "loss", "max_loss", "min_loss", "reward", "max_reward", "min_reward", "entropy", "old_logprobs",
+    "new_logprobs", "ref_logprobs", "advantage", "max_advantage", "min_advantage", "kl", "kl_new_old",
+    "mean_abs_log_ratio_new_old", "max_kl", "min_kl", "ratio_new_old", "ratio_new_old_sum",
+    "ratio_new_old_squared_sum", "ratio_ref_new", "ratio_ref_old", "clamp_log_ratio_ref_new_indicator",
+    "clamp_log_ratio_new_old_indicator", "token_weight", "max_token_weight", "min_token_weight", "kl_coef",
+    "entropy_bonus_coef", "num_output_tokens_sum", "input_size",
+]
+assert len(STAT_NAMES) == PRL_NUM_STATS
+
+# symbol -> (restype, argtypes); every symbol include/prl.h declares must be listed here
+_SIGNATURES = {
+    "prl_last_error": (C.c_char_p, []),
+    "prl_version": (C.c_int, []),
+    "prl_launch_count": (C.c_uint64, []),
+    "prl_pg_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "prl_pg_loss_fwd_bwd": (C.c_int, [C.POINTER(PgBatch), C.POINTER(PgConfig), C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "prl_logprob_tail_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_float,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "prl_logprob_tail_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_float,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_void_p]),
+    "prl_adamw_workspace_bytes": (C.c_size_t, []),
+    "prl_adamw_step": (C.c_int, [C.POINTER(AdamwArgs), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load libprl.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise RuntimeError(
+                f"{_LIB_PATH} is missing: build it with `python -m pipelinerl_b200._build` "
+                "(the CUDA extension is the product; there is no CPU fallback)")
+        lib = C.CDLL(str(_LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def declared_symbols() -> list[str]:
+    return sorted(_SIGNATURES)
+
+
+def check(code: int) -> None:
+    if code != 0:
+        msg = load().prl_last_error().decode(errors="replace")
+        raise PrlError(code, msg)
+
+
+def launch_count() -> int:
+    return int(load().prl_launch_count())
+
+
+def stream_ptr(stream=None) -> int:
+    """cudaStream_t of a torch stream (current stream by default) as an integer."""
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return int(s.cuda_stream)

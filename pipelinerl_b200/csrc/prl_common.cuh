@@ -1,0 +1,113 @@
+// Shared host/device helpers for libprl.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/prl.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libprl is written for sm_100a only"
+#endif
+
+namespace prl {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define PRL_CHECK_ARG(cond, ...)            \
+  do {                                      \
+    if (!(cond)) {                          \
+      prl::set_error(__VA_ARGS__);          \
+      return PRL_ERR_INVALID;               \
+    }                                       \
+  } while (0)
+
+#define PRL_CUDA(expr)                                                            \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      prl::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,               \
+                     cudaGetErrorString(_e));                                     \
+      return PRL_ERR_CUDA;                                                        \
+    }                                                                             \
+  } while (0)
+
+#define PRL_LAUNCH_CHECK()                                                        \
+  do {                                                                            \
+    prl::count_launch();                                                          \
+    cudaError_t _e = cudaGetLastError();                                          \
+    if (_e != cudaSuccess) {                                                      \
+      prl::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__,           \
+                     cudaGetErrorString(_e));                                     \
+      return PRL_ERR_CUDA;                                                        \
+    }                                                                             \
+  } while (0)
+
+int num_sms();  // SM count of the current device (cached per device)
+
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// streaming 128-bit loads/stores that do not pollute L1
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ld_stream_u2(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
+               : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_f4(float4* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream_u4(uint4* p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream_u2(uint2* p, uint2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};"
+               :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t hi16) {
+  return __uint_as_float(hi16 << 16);
+}
+// round-to-nearest-even fp32 -> bf16 bits (NaN preserved as quiet NaN)
+__device__ __forceinline__ uint32_t float_to_bf16_bits(float f) {
+  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f));
+}
+
+}  // namespace prl

@@ -1,0 +1,140 @@
+"""Optimizer of the trainer: fused AdamW over a flat parameter arena (csrc/adamw.cu).
+
+Interface of the reference (pipelinerl/finetune/optim.py): `get_grouped_params` decides which
+tensors are exempt from weight decay (names containing "bias" or "LayerNorm.weight", :8-22) and
+`get_optimizer("adamw_torch", model, lr, wd)` returns the optimizer (:25-29).  Here the returned
+object owns ONE contiguous arena per state (fp32 master, exp_avg, exp_avg_sq, gradient, bf16
+shadow), re-points every parameter's .data/.grad at views of it, and performs
+
+    global grad-norm -> clip -> AdamW -> bf16 re-cast
+
+in two kernel launches without a host sync.  The bf16 shadow arena is exactly what the weight push
+(hot path 3) copies to the samplers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable
+
+import torch
+
+from .. import _lib
+
+NO_DECAY_DEFAULT = ("bias", "LayerNorm.weight")
+
+
+def get_grouped_params(model, weight_decay: float, no_decay: Iterable[str] = NO_DECAY_DEFAULT):
+    """Two torch-style param groups; kept for callers that build a stock optimizer themselves."""
+    with_wd, without_wd = [], []
+    for name, p in model.named_parameters():
+        (without_wd if any(tag in name for tag in no_decay) else with_wd).append(p)
+    return [{"params": with_wd, "weight_decay": weight_decay}, {"params": without_wd, "weight_decay": 0.0}]
+
+
+def _align(n: int, a: int = 64) -> int:
+    return (n + a - 1) // a * a
+
+
+class FusedAdamW:
+    """AdamW(lr, betas=(0.9, 0.999), eps=1e-8, weight_decay) == torch.optim.AdamW numerics, one arena.
+
+    named_params: iterable of (name, Parameter) all on one CUDA device.  Parameters may be fp32
+    (then they ARE the master weights and `shadow_bf16` is an extra output) or bf16 (then a fp32
+    master arena is created from them, the DeepSpeed-bf16 arrangement of the reference).
+    """
+
+    def __init__(self, named_params, lr: float, weight_decay: float = 0.01, betas=(0.9, 0.999), eps: float = 1e-8,
+                 max_grad_norm: float | None = None, no_decay: Iterable[str] = NO_DECAY_DEFAULT,
+                 grad_dtype: torch.dtype | None = None, keep_lo_residual: bool = False):
+        named = [(n, p) for n, p in named_params if p.requires_grad]
+        if not named:
+            raise ValueError("FusedAdamW: no trainable parameters")
+        dev = named[0][1].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedAdamW needs CUDA parameters: pipelinerl_b200 has no CPU fallback")
+        self.lib = _lib.load()
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.max_grad_norm = max_grad_norm
+        self.step_count = 0
+        pdt = self.params[0].dtype
+        if any(p.dtype != pdt for p in self.params):
+            raise ValueError("FusedAdamW: mixed parameter dtypes")
+        if pdt not in (torch.float32, torch.bfloat16):
+            raise ValueError(f"FusedAdamW: unsupported parameter dtype {pdt}")
+        gdt = grad_dtype or pdt
+        # tensors start on 64-element boundaries so that 16-byte vector accesses never straddle two tensors
+        offsets, at = [], 0
+        for p in self.params:
+            offsets.append(at)
+            at = _align(at + p.numel())
+        self.n = at
+        self.offsets = offsets
+        self.master = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.master)
+        self.exp_avg_sq = torch.zeros_like(self.master)
+        self.grad = torch.zeros(self.n, dtype=gdt, device=dev)
+        self.shadow_bf16 = torch.zeros(self.n, dtype=torch.bfloat16, device=dev)
+        self.shadow_lo = torch.zeros(self.n, dtype=torch.bfloat16, device=dev) if keep_lo_residual else None
+        with torch.no_grad():
+            for p, off in zip(self.params, offsets):
+                k = p.numel()
+                self.master[off:off + k].copy_(p.detach().reshape(-1).float())
+                self.shadow_bf16[off:off + k].copy_(p.detach().reshape(-1))
+                home = self.master if pdt == torch.float32 else self.shadow_bf16
+                p.data = home[off:off + k].view(p.shape)
+                p.grad = self.grad[off:off + k].view(p.shape)
+        table = offsets + [self.n]
+        self.tensor_offsets = torch.tensor(table, dtype=torch.int64, device=dev)
+        flags = [1 if any(tag in n for tag in no_decay) else 0 for n in self.names]
+        self.tensor_no_decay = torch.tensor(flags, dtype=torch.uint8, device=dev)
+        self.workspace = torch.zeros(int(self.lib.prl_adamw_workspace_bytes()), dtype=torch.uint8, device=dev)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.param_groups = [{"lr": lr, "weight_decay": weight_decay, "params": self.params}]
+
+    # torch.optim-like surface used by the trainer loop
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        self.grad.zero_()
+
+    def step(self, grad_scale: float = 1.0) -> torch.Tensor:
+        """One optimizer step.  Returns the (device) pre-clip gradient norm, as clip_grad_norm_ does."""
+        self.step_count += 1
+        lr = self.param_groups[0]["lr"]
+        a = _lib.AdamwArgs()
+        a.n = self.n
+        a.master = self.master.data_ptr()
+        a.exp_avg = self.exp_avg.data_ptr()
+        a.exp_avg_sq = self.exp_avg_sq.data_ptr()
+        a.grad = self.grad.data_ptr()
+        a.grad_is_bf16 = int(self.grad.dtype == torch.bfloat16)
+        a.param_bf16 = self.shadow_bf16.data_ptr()
+        a.param_bf16_lo = self.shadow_lo.data_ptr() if self.shadow_lo is not None else None
+        a.tensor_offsets = self.tensor_offsets.data_ptr()
+        a.tensor_no_decay = self.tensor_no_decay.data_ptr()
+        a.n_tensors = len(self.params)
+        a.lr, a.beta1, a.beta2, a.eps = lr, self.betas[0], self.betas[1], self.eps
+        a.weight_decay = self.weight_decay
+        a.step = self.step_count
+        a.max_grad_norm = float(self.max_grad_norm) if self.max_grad_norm else 0.0
+        a.grad_scale = grad_scale
+        _lib.check(self.lib.prl_adamw_step(C.byref(a), self.grad_norm.data_ptr(), self.workspace.data_ptr(),
+                                           self.workspace.numel(), _lib.stream_ptr()))
+        return self.grad_norm
+
+    def state_dict(self) -> dict:
+        return {"step": self.step_count, "master": self.master, "exp_avg": self.exp_avg,
+                "exp_avg_sq": self.exp_avg_sq, "names": self.names, "offsets": self.offsets}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.step_count = int(sd["step"])
+        self.master.copy_(sd["master"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.shadow_bf16.copy_(self.master)
+
+
+def get_optimizer(name: str, model, learning_rate: float, weight_decay: float, **kw) -> FusedAdamW:
+    if name != "adamw_torch":
+        raise ValueError(f"Unknown optimizer: {name} (only the reference default adamw_torch is on the hot path)")
+    return FusedAdamW(model.named_parameters(), lr=learning_rate, weight_decay=weight_decay, **kw)

@@ -1,0 +1,67 @@
+"""The drop-in boundary: libprl.so loads, exports every symbol include/prl.h declares, and the product
+package never touches oracle/.  No compute calls here (CPU box)."""
+import ast
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from pipelinerl_b200 import _build, _lib
+    _build.build(verbose=False)
+    return _lib.load()
+
+
+def _header_symbols():
+    text = (ROOT / "include" / "prl.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(prl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from pipelinerl_b200 import _lib
+    syms = _header_symbols()
+    assert syms, "no symbols parsed from include/prl.h"
+    for s in syms:
+        assert hasattr(built_lib, s), f"libprl.so does not export {s}"
+    assert sorted(_lib.declared_symbols()) == syms, "ctypes binding and header disagree"
+
+
+def test_version_and_error_string(built_lib):
+    assert built_lib.prl_version() >= 100
+    assert isinstance(built_lib.prl_last_error(), bytes)
+    assert built_lib.prl_pg_workspace_bytes(16) > 0 and built_lib.prl_adamw_workspace_bytes() > 0
+
+
+def test_sm100a_cubin_present():
+    import subprocess
+    from pipelinerl_b200 import _lib
+    out = subprocess.run(["cuobjdump", "--list-elf", str(_lib.lib_path())], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_product_never_imports_oracle():
+    for py in (ROOT / "pipelinerl_b200").rglob("*.py"):
+        tree = ast.parse(py.read_text())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom) and node.module:
+                names = [node.module]
+            assert not any(n == "oracle" or n.startswith("oracle.") for n in names), f"{py} imports oracle"
+
+
+def test_ops_fail_loudly_without_cuda():
+    import torch
+    from pipelinerl_b200.finetune.optim import FusedAdamW
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    p = torch.nn.Parameter(torch.zeros(4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FusedAdamW([("w", p)], lr=1e-3)

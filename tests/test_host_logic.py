@@ -1,0 +1,121 @@
+"""Product host code (no GPU needed) against the reference's own outputs: bit-exact layout contract."""
+import copy
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from pipelinerl_b200.finetune.data import collate, collate_packed, preprocess_fn
+from pipelinerl_b200.finetune.rl import RLConfig, populate_rl_data, prepare_rl_fields
+from pipelinerl_b200.finetune.types import PipelineBatchEncoding
+from pipelinerl_b200.finetune.utils import create_sentinel_batch
+from tests.helpers import GOLDEN, load_rl_case
+
+
+class Tok:
+    eos_token_id = 7
+    padding_side = "right"
+
+
+@pytest.fixture(scope="module")
+def cases():
+    return json.loads((GOLDEN / "preprocess_cases.json").read_text())
+
+
+def _entries(case):
+    cfg = RLConfig(**case["config"])
+    entries = []
+    for s in copy.deepcopy(case["raw_samples"]):
+        enc = preprocess_fn(s, Tok(), seq_length=10_000, is_rl=True)
+        for k in ("group_id", "rollout_index", "step_index", "finished"):
+            enc[k] = s[k]
+        if "finish_reason" in s:
+            enc["finish_reason"] = s["finish_reason"]
+        enc["model_version"] = s["metadata"]["model_version"]
+        entries.append(enc)
+    return populate_rl_data(entries, Tok.eos_token_id, cfg), cfg
+
+
+@pytest.mark.parametrize("name", ["loo_std", "loo_nostd", "loo_std_sp4"])
+def test_populate_and_pack_match_reference(cases, name):
+    case = cases[name]
+    entries, _ = _entries(case)
+    for got, want in zip(entries, case["entries"]):
+        for k, w in want.items():
+            if isinstance(w, list) and w and isinstance(w[0], float):
+                np.testing.assert_allclose(got[k], w, rtol=1e-12, atol=0, err_msg=k)
+            else:
+                assert got[k] == w, k
+    batch = collate_packed(entries, Tok(), seq_parallel=case["seq_parallel"])
+    for k, w in case["batch"].items():
+        g = getattr(batch, k)
+        if isinstance(g, torch.Tensor):
+            want_t = torch.tensor(w, dtype=g.dtype)
+            assert g.shape == want_t.shape, k
+            assert torch.equal(g, want_t), f"{k} differs"
+        else:
+            assert g == w, k
+    assert batch.seq_boundaries.dtype == torch.int32 and batch.input_ids.dtype == torch.int64
+    assert batch.rewards.dtype == torch.float32
+
+
+def test_prepare_rl_fields_alignment_and_assert():
+    enc = {"input_ids": [1, 2, 3, 4], "labels": [-100, -100, 3, 4]}
+    out = prepare_rl_fields(enc, 0.5, [-1.0, -2.0], [-1.5, -2.5])
+    assert out["old_logprobs"] == [0, 0, -1.0, -2.0] and out["ref_logprobs"] == [0, 0, -1.5, -2.5]
+    assert out["rewards"] == [0.5] * 4 and out["num_labels"] == [0, 0, 1, 1]
+    with pytest.raises(AssertionError):
+        prepare_rl_fields({"input_ids": [1, 2], "labels": [-100, 2]}, 1.0, [-1.0, -1.0], [-1.0, -1.0])
+
+
+def test_sentinel_batch_matches_reference():
+    arrs, _ = load_rl_case("sentinel")
+    sb = create_sentinel_batch("cpu", tokenizer=Tok(), model_version=5)
+    for k in ("input_ids", "attention_mask", "labels", "position_ids", "segment_ids", "rewards", "advantages",
+              "ref_logprobs", "old_logprobs", "group_tokens", "num_labels", "overflow", "seq_boundaries"):
+        assert torch.equal(getattr(sb, k), torch.from_numpy(arrs[k])), k
+    assert sb.sentinel and sb.is_packed and sb.model_version == 5
+
+
+def test_collate_unpacked_matches_reference(cases):
+    arrs, _ = load_rl_case("unpacked")
+    # rebuild the same entries the generator used (seed 77 samples are stored only via the batch), so
+    # check structural properties + padding rules on a fresh case instead
+    case = cases["loo_nostd"]
+    entries, _ = _entries(case)
+    keep = ["input_ids", "labels", "attention_mask", "rewards", "advantages", "old_logprobs", "ref_logprobs",
+            "overflow", "group_tokens", "num_labels", "model_version"]
+    b = collate([{k: e[k] for k in keep} for e in entries[:3]], Tok())
+    L = b.input_ids.shape[1]
+    assert L % 16 == 0 and b.input_ids.shape[0] == 3 and not b.is_packed
+    n0 = len(entries[0]["input_ids"])
+    assert b.labels[0, n0:].eq(-100).all() and b.input_ids[0, n0:].eq(0).all() and b.rewards[0, n0:].eq(0).all()
+    assert b.attention_mask[0, :n0].eq(1).all() and b.attention_mask[0, n0:].eq(0).all()
+    assert arrs["input_ids"].shape[1] % 16 == 0  # same rule in the reference fixture
+
+
+def test_make_slices_and_errors(cases):
+    case = cases["loo_std_sp4"]
+    entries, _ = _entries(case)
+    batch = collate_packed(entries, Tok(), seq_parallel=4)
+    T = batch.input_ids.shape[1]
+    assert T % 4 == 0
+    parts = batch.make_slices(4)
+    assert torch.equal(torch.cat([p.input_ids for p in parts], dim=1), batch.input_ids)
+    assert torch.equal(torch.cat([p.advantages for p in parts], dim=1), batch.advantages)
+    assert all(p.model_version == batch.model_version and p.padding == batch.padding for p in parts)
+    with pytest.raises(ValueError):
+        batch.make_slices(T + 1)
+    with pytest.raises(ValueError):
+        batch.make_slices(7 if T % 7 else 9)
+
+
+def test_empty_and_single_sample_groups():
+    cfg = RLConfig(divide_advantage_by_std=True)
+    assert populate_rl_data([], 7, cfg) == []
+    e = prepare_rl_fields({"input_ids": [9, 9, 7], "labels": [-100, 9, 7]}, 1.0, [-0.1, -0.2], [-0.1, -0.2])
+    e.update(group_id="g", rollout_index=0, step_index=0, finished=True)
+    out = populate_rl_data([e], 7, cfg)[0]
+    assert out["advantages"] == [0.0, 0.0, 0.0]  # single member: baseline = own reward, std NaN -> 0
+    assert out["group_tokens"] == [3.0] * 3 and out["num_labels"] == [2] * 3 and out["overflow"] == [0.0] * 3
