@@ -163,7 +163,7 @@ typedef struct {
   const int64_t* tensor_offsets; /* device [n_tensors+1], ascending, [0]=0, [n_tensors]=n */
   const uint8_t* tensor_no_decay;/* device [n_tensors] 1 = weight_decay 0 (bias / LayerNorm.weight) */
   int32_t n_tensors;
-  float lr, beta1, beta2, eps, weight_decay;
+  double lr, beta1, beta2, eps, weight_decay; /* doubles: torch derives 1-beta, lr*wd, bias corrections in double */
   int32_t step;              /* 1-based optimizer step (bias correction) */
   float max_grad_norm;       /* <=0: no clipping */
   float grad_scale;          /* gradients are multiplied by this before use (1/accum etc.); 1.0 default */
@@ -173,6 +173,85 @@ size_t prl_adamw_workspace_bytes(void);
 /* grad_norm_out: device float[1], the pre-clip global L2 norm (as clip_grad_norm_ returns). */
 int prl_adamw_step(const prl_adamw_args* args, float* grad_norm_out,
                    void* workspace, size_t workspace_bytes, prl_stream_t stream);
+
+/* ======================================================================= *
+ * Hot path (1): tcgen05 weight-streaming GEMM of the token step
+ *   Y[M, N] = X[M, K] * W[N, K]^T, bf16 operands (row-major, K contiguous),
+ *   fp32 accumulation in TMEM.  Replaces the cuBLAS GEMMs the vLLM engine runs
+ *   per decode step for the reference (pipelinerl/async_llm.py:134 ->
+ *   /v1/chat/completions; flags conf/base.yaml:59-73) and, with W_lo, the fp32
+ *   lm_head matmul of pipelinerl/vllm_quantization.py:266-278
+ *   (W_fp32 = W + W_lo with both parts bf16).
+ *   Output: fp32 partial sums partials[split_k][M][N]; the consumer adds the
+ *   splits in index order (deterministic).  K %% 8 == 0; pointers 16-B aligned.
+ * ======================================================================= */
+int prl_gemm_auto_split_k(int64_t M, int64_t N, int64_t K);
+int prl_gemm_bf16_splitk(const void* W, const void* W_lo /*or NULL*/, const void* X,
+                         int64_t M, int64_t N, int64_t K, int32_t split_k /*0 = auto*/,
+                         float* partials, prl_stream_t stream);
+
+/* ======================================================================= *
+ * Hot path (1): fused epilogue kernels of one token step and paged attention.
+ *   Together with prl_gemm_bf16_splitk these are the decode step the
+ *   reference delegates to the vLLM engine (client: pipelinerl/async_llm.py:86-212;
+ *   server flags conf/base.yaml:59-73; fp32 head vllm_quantization.py:128-278):
+ *   fused_add_rms_norm, rotary_embedding, reshape_and_cache, paged attention,
+ *   silu_and_mul, sampler + processed_logprobs.
+ *   All activations: one row per token; `partials` are GEMM split-K partials
+ *   [n_split][B][cols] fp32.  KV cache (bf16), page_size 64, head_dim 128:
+ *     row(layer, kv, page, kvh, slot) = (((layer*2+kv)*n_pages + page)*n_kv + kvh)*64 + slot
+ * ======================================================================= */
+int prl_embed_rmsnorm(const int32_t* tokens, const void* embed_bf16, const void* gamma_bf16, float eps,
+                      int32_t B, int32_t H, int32_t vocab, float* h /*[B,H] residual, out*/,
+                      void* x_bf16 /*[B,H] out*/, prl_stream_t stream);
+int prl_residual_rmsnorm(const float* partials, int32_t n_split, int32_t B, int32_t H, const void* gamma_bf16,
+                         float eps, float* h /*in/out*/, void* x_bf16 /*out*/, prl_stream_t stream);
+int prl_qkv_rope_cache(const float* partials, int32_t n_split, int32_t B, const void* bias_bf16 /*or NULL*/,
+                       int32_t n_q, int32_t n_kv, int32_t head_dim, const int32_t* positions /*[B]*/,
+                       const int32_t* block_table /*[B,max_blocks]*/, int32_t max_blocks,
+                       const float* inv_freq /*[head_dim/2]*/, void* q_out_bf16 /*[B,n_q,128]*/,
+                       void* kv_cache_bf16, int64_t n_pages, int32_t layer, int32_t page_size,
+                       prl_stream_t stream);
+int prl_silu_mul(const float* partials, int32_t n_split, int32_t B, int32_t I, void* act_bf16 /*[B,I]*/,
+                 prl_stream_t stream);
+int prl_paged_attn_splits(int32_t B, int32_t n_kv, int32_t max_seq_len);
+size_t prl_paged_attn_workspace_bytes(int32_t B, int32_t n_q, int32_t n_splits);
+int prl_paged_attn_decode(const void* q_bf16, const void* kv_cache_bf16, int64_t n_pages, int32_t n_layers,
+                          int32_t layer, const int32_t* block_table, int32_t max_blocks,
+                          const int32_t* seq_lens /*[B] tokens in cache incl. the current one*/,
+                          int32_t B, int32_t n_q, int32_t n_kv, int32_t head_dim, int32_t page_size,
+                          int32_t n_splits, float sm_scale, void* out_bf16 /*[B, n_q*128]*/,
+                          void* workspace, size_t workspace_bytes, prl_stream_t stream);
+/* Sampling with in-kernel logprob capture: id ~ softmax(logits/T) (Gumbel-max, counter-based RNG on
+ * (seed, step, row, vocab id)) or argmax when greedy; logprob = log_softmax(logits/T)[id]. */
+int prl_sample_logprob(const float* logits /*[B,V]*/, int32_t B, int32_t V, float temperature, int32_t greedy,
+                       uint64_t seed, uint32_t step, int32_t* out_ids, float* out_logprobs, prl_stream_t stream);
+/* Device-resident scheduler state of one sampler (all pointers device, one entry per slot).
+ * prl_advance_state moves every active slot one token forward without a host round trip:
+ * feeds the next prompt token while inside the prompt, else appends (sampled id, logprob) to the
+ * slot's output ring, and retires the slot on EOS (finished=1, "stop") or max_new (finished=2, "length")
+ * — the finish_reason values pipelinerl/async_llm.py:202-212 reports. */
+typedef struct {
+  int32_t B;
+  const int32_t* sampled;          /* [B] ids drawn by prl_sample_logprob this step */
+  const float* sampled_logprobs;   /* [B] */
+  int32_t* tokens;                 /* [B] next input token (in/out) */
+  int32_t* positions;              /* [B] position of `tokens` */
+  int32_t* seq_lens;               /* [B] tokens in the KV cache incl. the current one; 0 = slot idle */
+  uint8_t* active;                 /* [B] */
+  const int32_t* prompt_buf;       /* [B, prompt_stride] */
+  int32_t prompt_stride;
+  const int32_t* prompt_len;       /* [B] */
+  int32_t* out_ids;                /* [B, out_stride] */
+  float* out_logprobs;             /* [B, out_stride] */
+  int32_t out_stride;
+  int32_t* gen_count;              /* [B] */
+  const int32_t* max_new;          /* [B] */
+  uint8_t* finished;               /* [B] 0 running, 1 stop, 2 length */
+  int32_t eos_id;
+  int32_t ignore_eos;
+} prl_engine_state;
+int prl_advance_state(const prl_engine_state* state, prl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -50,9 +50,19 @@ class AdamwArgs(C.Structure):
         ("grad", C.c_void_p), ("grad_is_bf16", C.c_int32),
         ("param_bf16", C.c_void_p), ("param_bf16_lo", C.c_void_p),
         ("tensor_offsets", C.c_void_p), ("tensor_no_decay", C.c_void_p), ("n_tensors", C.c_int32),
-        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-        ("weight_decay", C.c_float), ("step", C.c_int32), ("max_grad_norm", C.c_float),
+        ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+        ("weight_decay", C.c_double), ("step", C.c_int32), ("max_grad_norm", C.c_float),
         ("grad_scale", C.c_float),
+    ]
+
+
+class EngineState(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("sampled", C.c_void_p), ("sampled_logprobs", C.c_void_p), ("tokens", C.c_void_p),
+        ("positions", C.c_void_p), ("seq_lens", C.c_void_p), ("active", C.c_void_p), ("prompt_buf", C.c_void_p),
+        ("prompt_stride", C.c_int32), ("prompt_len", C.c_void_p), ("out_ids", C.c_void_p),
+        ("out_logprobs", C.c_void_p), ("out_stride", C.c_int32), ("gen_count", C.c_void_p), ("max_new", C.c_void_p),
+        ("finished", C.c_void_p), ("eos_id", C.c_int32), ("ignore_eos", C.c_int32),
     ]
 
 
@@ -81,6 +91,26 @@ _SIGNATURES = {
     "prl_logprob_tail_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_void_p]),
+    "prl_gemm_auto_split_k": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
+    "prl_gemm_bf16_splitk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                       C.c_void_p, C.c_void_p]),
+    "prl_embed_rmsnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "prl_residual_rmsnorm": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_float,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "prl_qkv_rope_cache": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "prl_silu_mul": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "prl_paged_attn_splits": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    "prl_paged_attn_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "prl_paged_attn_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.c_void_p]),
+    "prl_sample_logprob": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_uint64,
+                                     C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "prl_advance_state": (C.c_int, [C.POINTER(EngineState), C.c_void_p]),
     "prl_adamw_workspace_bytes": (C.c_size_t, []),
     "prl_adamw_step": (C.c_int, [C.POINTER(AdamwArgs), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }

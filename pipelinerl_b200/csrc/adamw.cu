@@ -79,18 +79,22 @@ __global__ void __launch_bounds__(kThreads) grad_sumsq_kernel(const void* __rest
 }
 
 struct UpdateConsts {
-  float lr, beta1, beta2, eps, weight_decay;
+  float lr, beta1, beta2, eps;
+  float weight_decay;     // decay FACTOR 1 - lr*wd (1 for no-decay tensors)
   float step_size;        // lr / (1 - beta1^t)
-  float inv_sqrt_bc2;     // 1 / sqrt(1 - beta2^t)
+  float bc2_sqrt;         // sqrt(1 - beta2^t)
+  // torch evaluates these scalars in double precision before the fp32 tensor op; 1.f - 0.999f would be
+  // off by 4.7e-5 relative
+  float one_minus_beta1, one_minus_beta2;
   float max_grad_norm, grad_scale;
 };
 
-__device__ __forceinline__ void adam_elem(float g, float& p, float& m, float& v, const UpdateConsts& k, float wd) {
+__device__ __forceinline__ void adam_elem(float g, float& p, float& m, float& v, const UpdateConsts& k, float wd /* decay factor */) {
   // same operation order as torch.optim.adamw (_single_tensor_adam)
-  p = p * (1.f - k.lr * wd);
-  m = m + (g - m) * (1.f - k.beta1);          // lerp_(grad, 1 - beta1)
-  v = v * k.beta2 + (1.f - k.beta2) * g * g;  // mul_(beta2).addcmul_(g, g, 1 - beta2)
-  const float denom = sqrtf(v) * k.inv_sqrt_bc2 + k.eps;
+  p = p * wd;                                  // wd = 1 - lr * weight_decay, evaluated in double on the host
+  m = m + (g - m) * k.one_minus_beta1;         // lerp_(grad, 1 - beta1)
+  v = v * k.beta2 + k.one_minus_beta2 * g * g; // mul_(beta2).addcmul_(g, g, 1 - beta2)
+  const float denom = sqrtf(v) / k.bc2_sqrt + k.eps;
   p = p - k.step_size * (m / denom);
 }
 
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(kThreads) adamw_kernel(prl_adamw_args a, Updat
         float4 p = *reinterpret_cast<const float4*>(a.master + i);
         float4 m = *reinterpret_cast<const float4*>(a.exp_avg + i);
         float4 v = *reinterpret_cast<const float4*>(a.exp_avg_sq + i);
-        const float wd = a.tensor_no_decay[tix] ? 0.f : k.weight_decay;
+        const float wd = a.tensor_no_decay[tix] ? 1.f : k.weight_decay;
         adam_elem(g[0], p.x, m.x, v.x, k, wd);
         adam_elem(g[1], p.y, m.y, v.y, k, wd);
         adam_elem(g[2], p.z, m.z, v.z, k, wd);
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(kThreads) adamw_kernel(prl_adamw_args a, Updat
           while (j >= tj_end) { ++tj; tj_end = a.tensor_offsets[tj + 1]; }
           const float g = load_grad1<kBf16>(a.grad, j, gscale);
           float p = a.master[j], m = a.exp_avg[j], v = a.exp_avg_sq[j];
-          adam_elem(g, p, m, v, k, a.tensor_no_decay[tj] ? 0.f : k.weight_decay);
+          adam_elem(g, p, m, v, k, a.tensor_no_decay[tj] ? 1.f : k.weight_decay);
           a.master[j] = p; a.exp_avg[j] = m; a.exp_avg_sq[j] = v;
           if (a.param_bf16) {
             const __nv_bfloat16 hi = __float2bfloat16_rn(p);
@@ -230,11 +234,14 @@ extern "C" int prl_adamw_step(const prl_adamw_args* a, float* grad_norm_out, voi
   PRL_LAUNCH_CHECK();
 
   UpdateConsts k;
-  k.lr = a->lr; k.beta1 = a->beta1; k.beta2 = a->beta2; k.eps = a->eps; k.weight_decay = a->weight_decay;
-  const double bc1 = 1.0 - pow((double)a->beta1, (double)a->step);
-  const double bc2 = 1.0 - pow((double)a->beta2, (double)a->step);
-  k.step_size = (float)((double)a->lr / bc1);
-  k.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  k.lr = (float)a->lr; k.beta1 = (float)a->beta1; k.beta2 = (float)a->beta2; k.eps = (float)a->eps;
+  k.weight_decay = (float)(1.0 - a->lr * a->weight_decay);  // decay FACTOR
+  k.one_minus_beta1 = (float)(1.0 - a->beta1);
+  k.one_minus_beta2 = (float)(1.0 - a->beta2);
+  const double bc1 = 1.0 - pow(a->beta1, (double)a->step);
+  const double bc2 = 1.0 - pow(a->beta2, (double)a->step);
+  k.step_size = (float)(a->lr / bc1);
+  k.bc2_sqrt = (float)sqrt(bc2);
   k.max_grad_norm = a->max_grad_norm;
   k.grad_scale = gs;
 

@@ -1,0 +1,327 @@
+// Hot path (1): the small fused kernels around the tcgen05 GEMMs of one token step.
+//
+// They replace, for the reference's sampler (vLLM behind pipelinerl/async_llm.py:134),
+// vLLM's fused_add_rms_norm / rotary_embedding / reshape_and_cache_flash / silu_and_mul
+// custom ops and the sampler + processed_logprobs path (conf/base.yaml:65).  Each one
+// consumes the fp32 split-K partials of the preceding GEMM (summed in split order, so
+// results are deterministic) and emits the bf16 operand of the next GEMM, i.e. the
+// split-K reduction, bias, RoPE, KV-page write, residual add, RMSNorm and SiLU*mul are
+// all "epilogue" work on L2-resident activations, never a separate pass over weights.
+//
+// Numerics contract (restated by oracle/decode_oracle.py): residual stream fp32,
+// GEMM operands bf16, accumulation fp32, RoPE angles fp32, KV cache bf16.
+#include "prl_common.cuh"
+#include <math.h>
+
+namespace prl {
+namespace {
+
+__device__ __forceinline__ float block_sum(float v, float* s_red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  const int nw = (blockDim.x + 31) >> 5;
+  for (int i = 0; i < nw; ++i) t += s_red[i];
+  __syncthreads();
+  return t;
+}
+
+// ---- embedding gather + RMSNorm ------------------------------------------------------
+// h[b,:] = embed[token[b],:] ; x[b,:] = bf16(h * rsqrt(mean(h^2) + eps) * g)
+__global__ void __launch_bounds__(256) embed_rmsnorm_kernel(const int32_t* __restrict__ tokens,
+                                                           const __nv_bfloat16* __restrict__ embed,
+                                                           const __nv_bfloat16* __restrict__ gamma, float eps, int H,
+                                                           int vocab, float* __restrict__ h,
+                                                           __nv_bfloat16* __restrict__ x) {
+  __shared__ float s_red[8];
+  const int b = blockIdx.x;
+  int tok = tokens[b];
+  if (tok < 0 || tok >= vocab) tok = 0;
+  const __nv_bfloat16* row = embed + (int64_t)tok * H;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    const float v = __bfloat162float(row[i]);
+    h[(int64_t)b * H + i] = v;
+    ss += v * v;
+  }
+  const float tot = block_sum(ss, s_red);
+  const float r = rsqrtf(tot / (float)H + eps);
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    const float v = __bfloat162float(row[i]);
+    x[(int64_t)b * H + i] = __float2bfloat16_rn(v * r * __bfloat162float(gamma[i]));
+  }
+}
+
+// ---- split-K reduce + residual add + RMSNorm --------------------------------------------
+// h[b,:] += sum_s part[s,b,:] ; x[b,:] = bf16(rmsnorm(h) * g)
+__global__ void __launch_bounds__(256) residual_rmsnorm_kernel(const float* __restrict__ part, int n_split, int B,
+                                                              int H, const __nv_bfloat16* __restrict__ gamma,
+                                                              float eps, float* __restrict__ h,
+                                                              __nv_bfloat16* __restrict__ x) {
+  extern __shared__ float s_row[];  // H floats
+  __shared__ float s_red[8];
+  const int b = blockIdx.x;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    float v = h[(int64_t)b * H + i];
+    for (int s = 0; s < n_split; ++s) v += part[((int64_t)s * B + b) * H + i];
+    s_row[i] = v;
+    h[(int64_t)b * H + i] = v;
+    ss += v * v;
+  }
+  const float tot = block_sum(ss, s_red);
+  const float r = rsqrtf(tot / (float)H + eps);
+  for (int i = threadIdx.x; i < H; i += blockDim.x)
+    x[(int64_t)b * H + i] = __float2bfloat16_rn(s_row[i] * r * __bfloat162float(gamma[i]));
+}
+
+// ---- split-K reduce + bias + RoPE + KV-page write ---------------------------------------
+// part [n_split, B, (n_q + 2 n_kv) * 128]; one block per (token, head), 64 threads = 64 rotation pairs.
+// q -> q_out [B, n_q, 128] bf16 ; k, v -> cache rows ((layer*2 + kv) * n_pages + page) * n_kv * PAGE + kvh*PAGE + slot
+__global__ void __launch_bounds__(64) qkv_rope_cache_kernel(const float* __restrict__ part, int n_split, int B,
+                                                           const __nv_bfloat16* __restrict__ bias, int n_q, int n_kv,
+                                                           const int32_t* __restrict__ positions,
+                                                           const int32_t* __restrict__ block_table, int max_blocks,
+                                                           const float* __restrict__ inv_freq_tab,
+                                                           __nv_bfloat16* __restrict__ q_out,
+                                                           __nv_bfloat16* __restrict__ kv_cache, int64_t n_pages,
+                                                           int layer, int page_size) {
+  constexpr int D = 128;
+  const int b = blockIdx.x, head = blockIdx.y, i = threadIdx.x;  // i in [0, 64)
+  const int n_heads = n_q + 2 * n_kv;
+  const int64_t ncol = (int64_t)n_heads * D;
+  const int col = head * D + i;
+  float x1 = 0.f, x2 = 0.f;
+  for (int s = 0; s < n_split; ++s) {
+    const float* p = part + ((int64_t)s * B + b) * ncol;
+    x1 += p[col];
+    x2 += p[col + 64];
+  }
+  if (bias) {
+    x1 += __bfloat162float(bias[col]);
+    x2 += __bfloat162float(bias[col + 64]);
+  }
+  const int pos = positions[b];
+  const bool is_v = head >= n_q + n_kv;
+  float o1 = x1, o2 = x2;
+  if (!is_v) {
+    // NeoX-style rotation of the pair (i, i + 64); inv_freq[i] = 1 / theta^(2i/128) is tabulated by the host
+    // with the exact fp32 expression HF's rotary embedding uses, the angle is an fp32 product as there
+    const float inv_freq = inv_freq_tab[i];
+    float sn, cs;
+    sincosf((float)pos * inv_freq, &sn, &cs);
+    o1 = x1 * cs - x2 * sn;
+    o2 = x2 * cs + x1 * sn;
+  }
+  if (head < n_q) {
+    __nv_bfloat16* q = q_out + ((int64_t)b * n_q + head) * D;
+    q[i] = __float2bfloat16_rn(o1);
+    q[i + 64] = __float2bfloat16_rn(o2);
+  } else {
+    const int kv = is_v ? 1 : 0;
+    const int kvh = is_v ? head - n_q - n_kv : head - n_q;
+    const int page = block_table[(int64_t)b * max_blocks + pos / page_size];
+    const int slot = pos % page_size;
+    const int64_t row = (((int64_t)(layer * 2 + kv) * n_pages + page) * n_kv + kvh) * page_size + slot;
+    __nv_bfloat16* dst = kv_cache + row * D;
+    dst[i] = __float2bfloat16_rn(o1);
+    dst[i + 64] = __float2bfloat16_rn(o2);
+  }
+}
+
+// ---- split-K reduce + SiLU(gate) * up ------------------------------------------------------
+// part [n_split, B, 2I] (gate columns first, as in the fused gate_up weight) -> act [B, I] bf16
+__global__ void __launch_bounds__(256) silu_mul_kernel(const float* __restrict__ part, int n_split, int B, int I,
+                                                      __nv_bfloat16* __restrict__ act) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= I) return;
+  float g = 0.f, u = 0.f;
+  for (int s = 0; s < n_split; ++s) {
+    const float* p = part + ((int64_t)s * B + b) * 2 * I;
+    g += p[i];
+    u += p[I + i];
+  }
+  const float silu = g / (1.f + __expf(-g));
+  act[(int64_t)b * I + i] = __float2bfloat16_rn(silu * u);
+}
+
+// ---- sampler + in-kernel logprob capture ----------------------------------------------------
+// logits [B, V] fp32 (split-K already 1 for the head).  Per token: z = logits / T;
+// id = argmax(z + Gumbel noise) (== a sample from softmax(z)), or argmax(z) when greedy;
+// logprob = z[id] - logsumexp(z)  (vLLM's processed_logprobs at top_p = 1, top_k = -1).
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ float gumbel(uint64_t seed, uint32_t step, uint32_t b, uint32_t v) {
+  uint32_t x = mix32((uint32_t)seed ^ (v * 0x9E3779B9u));
+  x = mix32(x ^ (uint32_t)(seed >> 32) ^ (step * 0x85EBCA6Bu) ^ (b * 0xC2B2AE35u));
+  const float u = ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+  return -__logf(-__logf(u));
+}
+
+struct ArgMax { float v; int i; };
+__device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
+  // ties -> lowest index, like torch.argmax
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+
+__global__ void __launch_bounds__(1024) sample_logprob_kernel(const float* __restrict__ logits, int V, float inv_temp,
+                                                             int greedy, uint64_t seed, uint32_t step,
+                                                             int32_t* __restrict__ out_ids,
+                                                             float* __restrict__ out_logprobs) {
+  const int b = blockIdx.x;
+  const float* z = logits + (int64_t)b * V;
+  float m = -INFINITY, s = 0.f;
+  ArgMax best{-INFINITY, 0x7fffffff};
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float zi = z[i] * inv_temp;
+    if (zi > m) { s = s * __expf(m - zi) + 1.f; m = zi; } else { s += __expf(zi - m); }
+    const float key = greedy ? zi : zi + gumbel(seed, step, (uint32_t)b, (uint32_t)i);
+    best = better(best, ArgMax{key, i});
+  }
+  // warp then block reduction of (m, s) and the arg-max
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const float mm = fmaxf(m, m2);
+    s = (m == -INFINITY ? 0.f : s * __expf(m - mm)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mm));
+    m = mm;
+    ArgMax o2{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
+    best = better(best, o2);
+  }
+  __shared__ float s_m[32], s_s[32], s_v[32];
+  __shared__ int s_i[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_m[warp] = m; s_s[warp] = s; s_v[warp] = best.v; s_i[warp] = best.i; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = blockDim.x >> 5;
+    float M = -INFINITY, S = 0.f;
+    ArgMax bb{-INFINITY, 0x7fffffff};
+    for (int w = 0; w < nw; ++w) {
+      const float mm = fmaxf(M, s_m[w]);
+      S = (M == -INFINITY ? 0.f : S * __expf(M - mm)) + (s_m[w] == -INFINITY ? 0.f : s_s[w] * __expf(s_m[w] - mm));
+      M = mm;
+      bb = better(bb, ArgMax{s_v[w], s_i[w]});
+    }
+    const float lse = M + logf(S);
+    out_ids[b] = bb.i;
+    out_logprobs[b] = z[bb.i] * inv_temp - lse;
+  }
+}
+
+// ---- advance the per-sequence state after a step (device-side, no host round trip) -------------
+// Slot b just processed the token at position pos.  While the next position is still inside the
+// prompt the sample is discarded and the next prompt token is fed (prefill-by-decode); afterwards
+// the sampled id / logprob are appended to the slot's output ring and become the next input.
+__global__ void advance_kernel(prl_engine_state st) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= st.B) return;
+  if (!st.active[b]) return;
+  const int pos = st.positions[b];
+  const int next = pos + 1;
+  if (next < st.prompt_len[b]) {
+    st.tokens[b] = st.prompt_buf[(int64_t)b * st.prompt_stride + next];
+  } else {
+    const int n = st.gen_count[b];
+    const int id = st.sampled[b];
+    st.out_ids[(int64_t)b * st.out_stride + n] = id;
+    st.out_logprobs[(int64_t)b * st.out_stride + n] = st.sampled_logprobs[b];
+    st.gen_count[b] = n + 1;
+    st.tokens[b] = id;
+    const bool eos = (id == st.eos_id) && !st.ignore_eos;
+    if (eos || n + 1 >= st.max_new[b]) {
+      st.finished[b] = eos ? 1 : 2;  // 1 = stop, 2 = length
+      st.active[b] = 0;
+      st.seq_lens[b] = 0;            // the slot stops reading its KV
+      st.positions[b] = 0;
+      return;
+    }
+  }
+  st.positions[b] = next;
+  st.seq_lens[b] = next + 1;
+}
+
+}  // namespace
+}  // namespace prl
+
+using namespace prl;
+
+extern "C" int prl_embed_rmsnorm(const int32_t* tokens, const void* embed, const void* gamma, float eps, int32_t B,
+                                 int32_t H, int32_t vocab, float* h, void* x_bf16, prl_stream_t st) {
+  PRL_CHECK_ARG(tokens && embed && gamma && h && x_bf16 && B >= 1 && H >= 1, "prl_embed_rmsnorm: bad argument");
+  embed_rmsnorm_kernel<<<B, 256, 0, (cudaStream_t)st>>>(tokens, (const __nv_bfloat16*)embed,
+                                                       (const __nv_bfloat16*)gamma, eps, H, vocab, h,
+                                                       (__nv_bfloat16*)x_bf16);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
+extern "C" int prl_residual_rmsnorm(const float* partials, int32_t n_split, int32_t B, int32_t H, const void* gamma,
+                                    float eps, float* h, void* x_bf16, prl_stream_t st) {
+  PRL_CHECK_ARG(partials && gamma && h && x_bf16 && B >= 1 && H >= 1 && n_split >= 0, "prl_residual_rmsnorm: bad argument");
+  PRL_CHECK_ARG(H * 4 <= 96 * 1024, "prl_residual_rmsnorm: hidden size too large for the row buffer");
+  static bool configured = false;
+  if (!configured) {
+    PRL_CUDA(cudaFuncSetAttribute(residual_rmsnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
+  residual_rmsnorm_kernel<<<B, 256, (size_t)H * 4, (cudaStream_t)st>>>(partials, n_split, B, H,
+                                                                       (const __nv_bfloat16*)gamma, eps, h,
+                                                                       (__nv_bfloat16*)x_bf16);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
+extern "C" int prl_qkv_rope_cache(const float* partials, int32_t n_split, int32_t B, const void* bias, int32_t n_q,
+                                  int32_t n_kv, int32_t head_dim, const int32_t* positions,
+                                  const int32_t* block_table, int32_t max_blocks, const float* inv_freq, void* q_out,
+                                  void* kv_cache, int64_t n_pages, int32_t layer, int32_t page_size,
+                                  prl_stream_t st) {
+  PRL_CHECK_ARG(partials && positions && block_table && q_out && kv_cache && inv_freq, "prl_qkv_rope_cache: NULL argument");
+  PRL_CHECK_ARG(head_dim == 128, "prl_qkv_rope_cache: head_dim must be 128 (got %d)", head_dim);
+  PRL_CHECK_ARG(B >= 1 && n_q >= 1 && n_kv >= 1 && page_size >= 1 && max_blocks >= 1, "prl_qkv_rope_cache: bad shape");
+  dim3 grid((unsigned)B, (unsigned)(n_q + 2 * n_kv));
+  qkv_rope_cache_kernel<<<grid, 64, 0, (cudaStream_t)st>>>(partials, n_split, B, (const __nv_bfloat16*)bias, n_q, n_kv,
+                                                          positions, block_table, max_blocks, inv_freq,
+                                                          (__nv_bfloat16*)q_out, (__nv_bfloat16*)kv_cache, n_pages,
+                                                          layer, page_size);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
+extern "C" int prl_silu_mul(const float* partials, int32_t n_split, int32_t B, int32_t I, void* act_bf16,
+                            prl_stream_t st) {
+  PRL_CHECK_ARG(partials && act_bf16 && B >= 1 && I >= 1 && n_split >= 1, "prl_silu_mul: bad argument");
+  dim3 grid((unsigned)((I + 255) / 256), (unsigned)B);
+  silu_mul_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(partials, n_split, B, I, (__nv_bfloat16*)act_bf16);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
+extern "C" int prl_sample_logprob(const float* logits, int32_t B, int32_t V, float temperature, int32_t greedy,
+                                  uint64_t seed, uint32_t step, int32_t* out_ids, float* out_logprobs,
+                                  prl_stream_t st) {
+  PRL_CHECK_ARG(logits && out_ids && out_logprobs && B >= 1 && V >= 1, "prl_sample_logprob: bad argument");
+  PRL_CHECK_ARG(temperature > 0.f, "prl_sample_logprob: temperature must be > 0 (use greedy=1 for argmax)");
+  sample_logprob_kernel<<<B, 1024, 0, (cudaStream_t)st>>>(logits, V, 1.f / temperature, greedy, seed, step, out_ids,
+                                                         out_logprobs);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
+extern "C" int prl_advance_state(const prl_engine_state* state, prl_stream_t st) {
+  PRL_CHECK_ARG(state && state->B >= 1, "prl_advance_state: bad argument");
+  PRL_CHECK_ARG(state->sampled && state->sampled_logprobs && state->tokens && state->positions && state->seq_lens &&
+                    state->active && state->prompt_buf && state->prompt_len && state->out_ids &&
+                    state->out_logprobs && state->gen_count && state->max_new && state->finished,
+                "prl_advance_state: NULL field");
+  advance_kernel<<<(state->B + 127) / 128, 128, 0, (cudaStream_t)st>>>(*state);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}

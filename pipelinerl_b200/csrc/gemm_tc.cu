@@ -1,0 +1,312 @@
+// tcgen05 weight-streaming GEMM for the token step (hot path 1) and the output head.
+//
+//   Y[M_tok, N_out] = X[M_tok, K] * W[N_out, K]^T      (bf16 in, fp32 accumulate)
+//
+// replaces the cuBLAS GEMMs vLLM issues per decode step for Qwen2's qkv / o / gate_up /
+// down projections (reached from pipelinerl/async_llm.py:134 through the vLLM engine) and
+// the fp32 lm_head matmul of pipelinerl/vllm_quantization.py:266-278.
+//
+// Decode shapes are skinny (M_tok <= 64..256), so the kernel is laid out "swap-AB":
+// the WEIGHT tile is the UMMA M operand (128 output features per CTA), the tokens are
+// the UMMA N operand (16..256), and D^T = W_tile * X^T accumulates in TMEM
+// (lane = output feature, column = token).  Every weight byte is read from HBM exactly
+// once per step by TMA (EVICT_FIRST), the small activation tile is re-read from L2
+// (EVICT_LAST); split-K fills the 148 SMs when N_out/128 < #SMs, with fp32 partials
+// reduced by the consumer epilogue kernel (decode_ops.cu) in a fixed order.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
+// (one elected lane), warps 2..5 = epilogue (TMEM -> registers -> global).
+// An optional second weight operand W_lo (bf16 residual of an fp32 master) is
+// accumulated into the same TMEM tile: fp32-equivalent head at the cost of a second
+// bf16 stream (same bytes as an fp32 weight).
+//
+// HBM-bound: algorithmic bytes = 2*N*K (+2*N*K with W_lo) + 2*M*K + 4*split_k*M*N.
+#include "prl_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace prl {
+
+// ------------------------------------------------------------------------------------
+// host: tensor maps
+// ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess || !p) {
+      set_error("cuTensorMapEncodeTiled not available from the driver");
+      return nullptr;
+    }
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t outer_rows,
+                      uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return PRL_ERR_CUDA;
+  if ((uintptr_t)base % 16 != 0 || row_stride_bytes % 16 != 0) {
+    set_error("TMA operand must be 16-byte aligned (base %p, row stride %llu B)", base,
+              (unsigned long long)row_stride_bytes);
+    return PRL_ERR_INVALID;
+  }
+  cuuint64_t dims[2] = {inner_elems, outer_rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t elem_strides[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, elem_strides,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner %llu rows %llu stride %llu box %u x %u)", (int)r,
+              (unsigned long long)inner_elems, (unsigned long long)outer_rows, (unsigned long long)row_stride_bytes,
+              box_inner, box_rows);
+    return PRL_ERR_CUDA;
+  }
+  return PRL_OK;
+}
+
+namespace {
+
+constexpr int kBlockM = 128;  // output features per CTA (UMMA M)
+constexpr int kBlockK = 64;   // bf16 elements per stage row = 128 B = one swizzle atom
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct GemmParams {
+  int64_t M, N, K;
+  int kblocks;        // ceil(K / 64)
+  int split_k;
+  int has_lo;
+  float* partials;    // [split_k, M, N]
+};
+
+template <int kNTile>
+struct SmemLayout {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;       // 16 KB
+  static constexpr int kBBytes = kNTile * kBlockK * 2;
+  static constexpr int stage_bytes(bool lo) { return kABytes * (lo ? 2 : 1) + kBBytes; }
+  static constexpr int stages(bool lo) {
+    int s = kSmemBudget / stage_bytes(lo);
+    return s > 8 ? 8 : s;
+  }
+};
+
+template <int kNTile>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wlo,
+                   const __grid_constant__ CUtensorMap tm_x, GemmParams p, int n_stages) {
+  using L = SmemLayout<kNTile>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const bool lo = p.has_lo != 0;
+  const int stage_bytes = L::stage_bytes(lo);
+  // barriers live after the tile ring
+  const uint32_t bar_base = smem_base + (uint32_t)(n_stages * stage_bytes);
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(n_stages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (uint32_t)(2 * n_stages);
+  const uint32_t tmem_slot = tmem_full_bar + 8u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * kBlockM;        // first output feature of this CTA
+  const int split = blockIdx.y;
+  const int m0 = blockIdx.z * kNTile;         // first token of this CTA
+  const int kb_begin = (int)(((int64_t)p.kblocks * split) / p.split_k);
+  const int kb_end = (int)(((int64_t)p.kblocks * (split + 1)) / p.split_k);
+  const int n_kb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_w);
+    ptx::prefetch_tensormap(&tm_x);
+    if (lo) ptx::prefetch_tensormap(&tm_wlo);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, kNTile < 32 ? 32 : kNTile);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)stage_bytes;
+      for (int i = 0; i < n_kb; ++i) {
+        const int s = i % n_stages;
+        const uint32_t ph = (uint32_t)((i / n_stages) & 1);
+        ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(full_bar(s), tx);
+        const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes);
+        const int kcoord = (kb_begin + i) * kBlockK;
+        ptx::tma_load_2d(a_dst, &tm_w, kcoord, n0, full_bar(s), ptx::kEvictFirst);
+        uint32_t b_dst = a_dst + L::kABytes;
+        if (lo) {
+          ptx::tma_load_2d(a_dst + L::kABytes, &tm_wlo, kcoord, n0, full_bar(s), ptx::kEvictFirst);
+          b_dst += L::kABytes;
+        }
+        ptx::tma_load_2d(b_dst, &tm_x, kcoord, m0, full_bar(s), ptx::kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, kNTile);
+      for (int i = 0; i < n_kb; ++i) {
+        const int s = i % n_stages;
+        const uint32_t ph = (uint32_t)((i / n_stages) & 1);
+        ptx::mbar_wait(full_bar(s), ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t a_addr = smem_base + (uint32_t)(s * stage_bytes);
+        const uint32_t b_addr = a_addr + L::kABytes * (lo ? 2 : 1);
+        const uint64_t a_desc = ptx::make_kmajor_sw128_desc(a_addr);
+        const uint64_t b_desc = ptx::make_kmajor_sw128_desc(b_addr);
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+          // advancing K by 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
+          ptx::mma_bf16_ss(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                           (i > 0 || k > 0) ? 1u : 0u);
+        }
+        if (lo) {
+          const uint64_t al_desc = ptx::make_kmajor_sw128_desc(a_addr + L::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            ptx::mma_bf16_ss(tmem_base, al_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, 1u);
+        }
+        ptx::tc_commit(empty_bar(s));  // frees the smem slot when these MMAs have read it
+      }
+      ptx::tc_commit(tmem_full_bar);   // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: TMEM -> registers -> fp32 partial tile =====
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after_sync();
+    const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    const int feat = n0 + q * 32 + lane;       // output feature owned by this thread
+    float* out = p.partials + ((int64_t)split * p.M + m0) * p.N + feat;
+    const int m_valid = (int)((p.M - m0) < kNTile ? (p.M - m0) : kNTile);
+    const bool feat_ok = feat < p.N;
+    constexpr int kChunk = kNTile < 32 ? 16 : 32;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kNTile; c0 += kChunk) {
+      uint32_t r[kChunk];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      if constexpr (kChunk == 32) ptx::tmem_ld_32x32b_x32(taddr, r);
+      else ptx::tmem_ld_32x32b_x16(taddr, r);
+      ptx::tmem_ld_wait();
+      if (n_kb == 0) {
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) r[j] = 0u;
+      }
+      if (feat_ok) {
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j)
+          if (c0 + j < m_valid) out[(int64_t)(c0 + j) * p.N] = __uint_as_float(r[j]);  // 32 lanes -> 128 B row segment
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, kNTile < 32 ? 32 : kNTile);
+  }
+}
+
+template <int kNTile>
+int launch_gemm(const CUtensorMap& tw, const CUtensorMap& twl, const CUtensorMap& tx, const GemmParams& p,
+                cudaStream_t stream) {
+  using L = SmemLayout<kNTile>;
+  const bool lo = p.has_lo != 0;
+  const int n_stages = L::stages(lo);
+  const int smem = n_stages * L::stage_bytes(lo) + 1024 /*align slack*/ + 8 * (2 * n_stages + 2) + 16;
+  static int configured = 0;
+  if (configured < smem) {
+    PRL_CUDA(cudaFuncSetAttribute(gemm_swapab_kernel<kNTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  dim3 grid((unsigned)((p.N + kBlockM - 1) / kBlockM), (unsigned)p.split_k, (unsigned)((p.M + kNTile - 1) / kNTile));
+  gemm_swapab_kernel<kNTile><<<grid, kThreads, smem, stream>>>(tw, twl, tx, p, n_stages);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
+int pick_ntile(int64_t M) {
+  if (M <= 16) return 16;
+  if (M <= 32) return 32;
+  if (M <= 64) return 64;
+  if (M <= 128) return 128;
+  return 256;
+}
+
+}  // namespace
+}  // namespace prl
+
+using namespace prl;
+
+extern "C" int prl_gemm_auto_split_k(int64_t M, int64_t N, int64_t K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 1;
+  const int sms = num_sms();
+  const int64_t tiles = ((N + kBlockM - 1) / kBlockM) * ((M + pick_ntile(M) - 1) / pick_ntile(M));
+  const int kblocks = (int)((K + kBlockK - 1) / kBlockK);
+  if (tiles >= sms) return 1;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 16 && s <= kblocks; ++s) {
+    if (kblocks / s < 4) break;  // keep at least 4 k-blocks per CTA so the pipeline fills
+    const int64_t ctas = tiles * s;
+    const int64_t waves = (ctas + sms - 1) / sms;
+    const double eff = (double)ctas / (double)(waves * sms);
+    if (eff > best_eff + 0.03) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
+extern "C" int prl_gemm_bf16_splitk(const void* W, const void* W_lo, const void* X, int64_t M, int64_t N, int64_t K,
+                                    int32_t split_k, float* partials, prl_stream_t stream_) {
+  PRL_CHECK_ARG(W && X && partials, "prl_gemm_bf16_splitk: NULL argument");
+  PRL_CHECK_ARG(M >= 1 && N >= 1 && K >= 8 && K % 8 == 0, "prl_gemm_bf16_splitk: need M,N >= 1 and K %% 8 == 0 (M=%lld N=%lld K=%lld)",
+                (long long)M, (long long)N, (long long)K);
+  const int kblocks = (int)((K + kBlockK - 1) / kBlockK);
+  if (split_k <= 0) split_k = prl_gemm_auto_split_k(M, N, K);
+  PRL_CHECK_ARG(split_k <= kblocks, "prl_gemm_bf16_splitk: split_k %d > k-blocks %d", split_k, kblocks);
+  const int nt = pick_ntile(M);
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.kblocks = kblocks; p.split_k = split_k; p.has_lo = W_lo ? 1 : 0; p.partials = partials;
+  CUtensorMap tw, twl, tx;
+  int rc = make_tmap_2d_bf16(&tw, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, kBlockK, kBlockM);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&twl, W_lo ? W_lo : W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, kBlockK, kBlockM);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tx, X, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kBlockK, (uint32_t)nt);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  switch (nt) {
+    case 16: return launch_gemm<16>(tw, twl, tx, p, stream);
+    case 32: return launch_gemm<32>(tw, twl, tx, p, stream);
+    case 64: return launch_gemm<64>(tw, twl, tx, p, stream);
+    case 128: return launch_gemm<128>(tw, twl, tx, p, stream);
+    default: return launch_gemm<256>(tw, twl, tx, p, stream);
+  }
+}

@@ -1,0 +1,276 @@
+"""Sampler engine: continuous-batching token-step loop on one GPU, over libprl.so.
+
+This is what replaces the vLLM server of the reference for hot path 1 (launch:
+pipelinerl/launch.py:191-247; per-request client: pipelinerl/async_llm.py:86-212).  One engine
+owns one GPU: a parameter arena (model.ParamArena), a paged KV pool, device-resident per-slot
+scheduler state, and a CUDA graph of the whole token step (all ~290 kernel launches of a 28-layer
+model replayed with one call).  The host only admits requests into free slots and harvests
+finished ones; token feeding, sampling, logprob capture and retirement happen on the device
+(prl_advance_state), so there is no per-token host round trip.
+
+Requests carry token ids in and (token ids, logprobs, finish_reason) out — the fields
+`make_training_text` needs (async_llm.py:215-346).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _lib
+from .model import ModelConfig, ParamArena
+
+PAGE_SIZE = 64
+
+
+@dataclass
+class SamplingParams:
+    max_tokens: int = 16
+    temperature: float = 1.0
+    greedy: bool = False
+    ignore_eos: bool = False
+
+
+@dataclass
+class Request:
+    req_id: int
+    prompt_ids: list[int]
+    params: SamplingParams
+    slot: int = -1
+    pages: list[int] = field(default_factory=list)
+    output_ids: list[int] = field(default_factory=list)
+    output_logprobs: list[float] = field(default_factory=list)
+    finish_reason: str | None = None
+    model_version: int = 0
+
+
+class DecodeEngine:
+    def __init__(self, cfg: ModelConfig, arena: ParamArena, max_batch: int = 64, max_seq_len: int = 16384,
+                 n_pages: int | None = None, max_new_tokens: int = 8192, eos_id: int = -1, seed: int = 42,
+                 device: torch.device | str = "cuda:0", use_cuda_graph: bool = True):
+        if cfg.head_dim != 128:
+            raise ValueError("the sm_100a attention kernel is built for head_dim 128")
+        self.cfg, self.arena = cfg, arena
+        self.lib = _lib.load()
+        self.dev = torch.device(device)
+        if self.dev.type != "cuda":
+            raise RuntimeError("DecodeEngine needs a CUDA device: pipelinerl_b200 has no CPU fallback")
+        self.B = max_batch
+        self.max_seq_len = max_seq_len
+        self.max_blocks = (max_seq_len + PAGE_SIZE - 1) // PAGE_SIZE
+        # page 0 is a scratch page: idle slots point at it, so their (discarded) KV writes are harmless
+        self.n_pages = n_pages if n_pages is not None else 1 + self.B * self.max_blocks
+        self.max_new = max_new_tokens
+        self.eos_id, self.seed = eos_id, seed
+        self.use_graph = use_cuda_graph
+        d, B, H, I = self.dev, self.B, cfg.hidden_size, cfg.intermediate_size
+        kv_elems = cfg.num_layers * 2 * self.n_pages * cfg.num_kv_heads * PAGE_SIZE * cfg.head_dim
+        self.kv_cache = torch.zeros(kv_elems, dtype=torch.bfloat16, device=d)
+        i32 = dict(dtype=torch.int32, device=d)
+        self.block_table = torch.zeros(B, self.max_blocks, **i32)
+        self.tokens = torch.zeros(B, **i32)
+        self.positions = torch.zeros(B, **i32)
+        self.seq_lens = torch.zeros(B, **i32)
+        self.active = torch.zeros(B, dtype=torch.uint8, device=d)
+        self.finished = torch.zeros(B, dtype=torch.uint8, device=d)
+        self.prompt_stride = max_seq_len
+        self.prompt_buf = torch.zeros(B, self.prompt_stride, **i32)
+        self.prompt_len = torch.zeros(B, **i32)
+        self.out_ids = torch.zeros(B, self.max_new, **i32)
+        self.out_logprobs = torch.zeros(B, self.max_new, dtype=torch.float32, device=d)
+        self.gen_count = torch.zeros(B, **i32)
+        self.max_new_t = torch.zeros(B, **i32)
+        self.sampled = torch.zeros(B, **i32)
+        self.sampled_lp = torch.zeros(B, dtype=torch.float32, device=d)
+        # activations
+        self.h = torch.zeros(B, H, dtype=torch.float32, device=d)
+        self.x = torch.zeros(B, H, dtype=torch.bfloat16, device=d)
+        self.q = torch.zeros(B, cfg.q_size, dtype=torch.bfloat16, device=d)
+        self.attn_out = torch.zeros(B, cfg.q_size, dtype=torch.bfloat16, device=d)
+        self.act = torch.zeros(B, I, dtype=torch.bfloat16, device=d)
+        self.logits = torch.zeros(B, cfg.vocab_size, dtype=torch.float32, device=d)
+        # HF rotary: inv_freq = 1 / theta^(arange(0, d, 2) / d) in fp32
+        self.inv_freq = (1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, dtype=torch.int64).float()
+                                                   / cfg.head_dim))).to(d)
+        self._plan_gemms()
+        self.attn_splits = int(self.lib.prl_paged_attn_splits(B, cfg.num_kv_heads, max_seq_len))
+        self.attn_ws = torch.zeros(int(self.lib.prl_paged_attn_workspace_bytes(B, cfg.num_q_heads, self.attn_splits)),
+                                   dtype=torch.uint8, device=d)
+        self.free_pages = list(range(self.n_pages - 1, 0, -1))
+        self.free_slots = list(range(B - 1, -1, -1))
+        self.slot_req: dict[int, Request] = {}
+        self.step_count = 0
+        self.temperature = 1.0
+        self.greedy = False
+        self.ignore_eos = False
+        self._graph: torch.cuda.CUDAGraph | None = None
+        self._graph_key = None
+        self._next_id = 0
+        self._state = self._make_state()
+
+    # ------------------------------------------------------------------------------------------
+    def _plan_gemms(self) -> None:
+        cfg, B = self.cfg, self.B
+        shapes = {"qkv": (cfg.qkv_size, cfg.hidden_size), "o": (cfg.hidden_size, cfg.q_size),
+                  "gate_up": (2 * cfg.intermediate_size, cfg.hidden_size),
+                  "down": (cfg.hidden_size, cfg.intermediate_size), "head": (cfg.vocab_size, cfg.hidden_size)}
+        self.split_k = {k: int(self.lib.prl_gemm_auto_split_k(B, n, kk)) for k, (n, kk) in shapes.items()}
+        self.split_k["head"] = 1  # the sampler reads plain logits
+        need = max(self.split_k[k] * B * shapes[k][0] for k in ("qkv", "o", "gate_up", "down"))
+        self.partials = torch.zeros(need, dtype=torch.float32, device=self.dev)
+
+    def _make_state(self) -> _lib.EngineState:
+        s = _lib.EngineState()
+        s.B = self.B
+        s.sampled, s.sampled_logprobs = self.sampled.data_ptr(), self.sampled_lp.data_ptr()
+        s.tokens, s.positions, s.seq_lens = self.tokens.data_ptr(), self.positions.data_ptr(), self.seq_lens.data_ptr()
+        s.active = self.active.data_ptr()
+        s.prompt_buf, s.prompt_stride, s.prompt_len = self.prompt_buf.data_ptr(), self.prompt_stride, self.prompt_len.data_ptr()
+        s.out_ids, s.out_logprobs, s.out_stride = self.out_ids.data_ptr(), self.out_logprobs.data_ptr(), self.max_new
+        s.gen_count, s.max_new, s.finished = self.gen_count.data_ptr(), self.max_new_t.data_ptr(), self.finished.data_ptr()
+        s.eos_id, s.ignore_eos = self.eos_id, 0
+        return s
+
+    # ------------------------------------------------------------------------------------------
+    def _gemm(self, w_name: str, x: torch.Tensor, n: int, k: int, split: int, out: torch.Tensor, lo: str | None = None):
+        _lib.check(self.lib.prl_gemm_bf16_splitk(self.arena.ptr(w_name), self.arena.ptr(lo) if lo else None,
+                                                 x.data_ptr(), self.B, n, k, split, out.data_ptr(), self._st))
+
+    def _step_kernels(self) -> None:
+        """Enqueue one token step for all B slots on the current stream (graph-capturable)."""
+        cfg, lib, B, a = self.cfg, self.lib, self.B, self.arena
+        self._st = _lib.stream_ptr()
+        st = self._st
+        H, I = cfg.hidden_size, cfg.intermediate_size
+        part = self.partials
+        _lib.check(lib.prl_embed_rmsnorm(self.tokens.data_ptr(), a.ptr("embed_tokens.weight"),
+                                         a.ptr("layers.0.input_layernorm.weight"), cfg.rms_eps, B, H, cfg.vocab_size,
+                                         self.h.data_ptr(), self.x.data_ptr(), st))
+        sm_scale = 1.0 / math.sqrt(cfg.head_dim)
+        for l in range(cfg.num_layers):
+            p = f"layers.{l}."
+            self._gemm(p + "qkv_proj.weight", self.x, cfg.qkv_size, H, self.split_k["qkv"], part)
+            _lib.check(lib.prl_qkv_rope_cache(part.data_ptr(), self.split_k["qkv"], B,
+                                              a.ptr(p + "qkv_proj.bias") if cfg.qkv_bias else None, cfg.num_q_heads,
+                                              cfg.num_kv_heads, cfg.head_dim, self.positions.data_ptr(),
+                                              self.block_table.data_ptr(), self.max_blocks, self.inv_freq.data_ptr(),
+                                              self.q.data_ptr(), self.kv_cache.data_ptr(), self.n_pages, l, PAGE_SIZE,
+                                              st))
+            _lib.check(lib.prl_paged_attn_decode(self.q.data_ptr(), self.kv_cache.data_ptr(), self.n_pages,
+                                                 cfg.num_layers, l, self.block_table.data_ptr(), self.max_blocks,
+                                                 self.seq_lens.data_ptr(), B, cfg.num_q_heads, cfg.num_kv_heads,
+                                                 cfg.head_dim, PAGE_SIZE, self.attn_splits, sm_scale,
+                                                 self.attn_out.data_ptr(), self.attn_ws.data_ptr(),
+                                                 self.attn_ws.numel(), st))
+            self._gemm(p + "o_proj.weight", self.attn_out, H, cfg.q_size, self.split_k["o"], part)
+            _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), self.split_k["o"], B, H,
+                                                a.ptr(p + "post_attention_layernorm.weight"), cfg.rms_eps,
+                                                self.h.data_ptr(), self.x.data_ptr(), st))
+            self._gemm(p + "gate_up_proj.weight", self.x, 2 * I, H, self.split_k["gate_up"], part)
+            _lib.check(lib.prl_silu_mul(part.data_ptr(), self.split_k["gate_up"], B, I, self.act.data_ptr(), st))
+            self._gemm(p + "down_proj.weight", self.act, H, I, self.split_k["down"], part)
+            nxt = f"layers.{l + 1}.input_layernorm.weight" if l + 1 < cfg.num_layers else "norm.weight"
+            _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), self.split_k["down"], B, H, a.ptr(nxt), cfg.rms_eps,
+                                                self.h.data_ptr(), self.x.data_ptr(), st))
+        self._gemm("lm_head.weight", self.x, cfg.vocab_size, H, 1, self.logits,
+                   lo="lm_head.weight_lo" if cfg.fp32_head else None)
+
+    def _sample_and_advance(self) -> None:
+        lib, st = self.lib, _lib.stream_ptr()
+        _lib.check(lib.prl_sample_logprob(self.logits.data_ptr(), self.B, self.cfg.vocab_size, float(self.temperature),
+                                          int(self.greedy), self.seed, self.step_count, self.sampled.data_ptr(),
+                                          self.sampled_lp.data_ptr(), st))
+        self._state.ignore_eos = int(self.ignore_eos)
+        _lib.check(lib.prl_advance_state(C.byref(self._state), st))
+
+    def step(self) -> None:
+        """One token for every active slot.  The model part is replayed from a CUDA graph; sampling and
+        state advance are launched per step (they take the step counter as an RNG argument)."""
+        if self.use_graph:
+            key = (self.arena.data.data_ptr(),)
+            if self._graph is None or self._graph_key != key:
+                self._step_kernels()  # warm-up outside capture (sets kernel attributes)
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_kernels()
+                self._graph, self._graph_key = g, key
+            self._graph.replay()
+        else:
+            self._step_kernels()
+        self._sample_and_advance()
+        self.step_count += 1
+
+    # ---- host-side admission / harvest --------------------------------------------------------
+    def can_admit(self, prompt_len: int, max_tokens: int) -> bool:
+        need = (prompt_len + max_tokens + PAGE_SIZE - 1) // PAGE_SIZE
+        return bool(self.free_slots) and len(self.free_pages) >= need
+
+    def add_request(self, prompt_ids: list[int], params: SamplingParams, model_version: int = 0) -> Request:
+        n = len(prompt_ids)
+        if n < 1:
+            raise ValueError("empty prompt")
+        if n + params.max_tokens > self.max_seq_len or params.max_tokens > self.max_new:
+            raise ValueError(f"request of {n}+{params.max_tokens} tokens exceeds the engine limits")
+        if not self.can_admit(n, params.max_tokens):
+            raise RuntimeError("engine full")
+        req = Request(self._next_id, list(prompt_ids), params, model_version=model_version)
+        self._next_id += 1
+        slot = self.free_slots.pop()
+        n_pages = (n + params.max_tokens + PAGE_SIZE - 1) // PAGE_SIZE
+        req.slot, req.pages = slot, [self.free_pages.pop() for _ in range(n_pages)]
+        row = torch.zeros(self.max_blocks, dtype=torch.int32)
+        row[:n_pages] = torch.tensor(req.pages, dtype=torch.int32)
+        self.block_table[slot].copy_(row, non_blocking=True)
+        self.prompt_buf[slot, :n].copy_(torch.tensor(prompt_ids, dtype=torch.int32), non_blocking=True)
+        self.prompt_len[slot] = n
+        self.max_new_t[slot] = params.max_tokens
+        self.tokens[slot] = prompt_ids[0]
+        self.positions[slot] = 0
+        self.seq_lens[slot] = 1
+        self.gen_count[slot] = 0
+        self.finished[slot] = 0
+        self.active[slot] = 1
+        self.slot_req[slot] = req
+        return req
+
+    def harvest(self) -> list[Request]:
+        """Collect finished requests (one small D2H copy of the flags, then the finished rows)."""
+        if not self.slot_req:
+            return []
+        fin = self.finished.cpu()
+        done = []
+        for slot, req in list(self.slot_req.items()):
+            code = int(fin[slot])
+            if code == 0:
+                continue
+            n = int(self.gen_count[slot].item())
+            req.output_ids = self.out_ids[slot, :n].cpu().tolist()
+            req.output_logprobs = self.out_logprobs[slot, :n].cpu().tolist()
+            req.finish_reason = "stop" if code == 1 else "length"
+            self.block_table[slot].zero_()
+            self.finished[slot] = 0
+            self.free_pages.extend(req.pages)
+            self.free_slots.append(slot)
+            del self.slot_req[slot]
+            done.append(req)
+        return done
+
+    def generate(self, prompts: list[list[int]], params: SamplingParams) -> list[Request]:
+        """Convenience driver: run the given prompts to completion (used by tests and the bench)."""
+        self.temperature, self.greedy, self.ignore_eos = params.temperature, params.greedy, params.ignore_eos
+        pending = list(enumerate(prompts))
+        results: dict[int, Request] = {}
+        index_of: dict[int, int] = {}
+        while pending or self.slot_req:
+            while pending and self.can_admit(len(pending[0][1]), params.max_tokens):
+                i, pr = pending.pop(0)
+                r = self.add_request(pr, params)
+                index_of[r.req_id] = i
+            for _ in range(8):
+                self.step()
+            for r in self.harvest():
+                results[index_of[r.req_id]] = r
+        return [results[i] for i in range(len(prompts))]
