@@ -253,6 +253,27 @@ typedef struct {
 } prl_engine_state;
 int prl_advance_state(const prl_engine_state* state, prl_stream_t stream);
 
+/* ======================================================================= *
+ * Hot path (3): in-flight weight update as a one-shot NVLink P2P copy
+ *   replaces WeightUpdateManager.send_weight_update (pipelinerl/finetune_loop.py:205-292),
+ *   WorkerExtension.receive_weight_update (pipelinerl/vllm1.py:110-127) and the PyNccl group of
+ *   pipelinerl/torch_utils.py:70-94.  Sampler side (once): allocate the two arena buffers and a
+ *   16-byte control block with prl_ipc_alloc, export their handles.  Learner side: open the handles,
+ *   then per update prl_weights_push (its byte slice -> every sampler's inactive buffer) followed by
+ *   prl_weights_signal on the same stream.  Control block: u64 version (max of pushed versions),
+ *   u64 arrivals (monotonic count of signals); the sampler flips buffers at a token-step boundary
+ *   when arrivals has advanced by the number of pushing learner ranks.
+ * ======================================================================= */
+int prl_ipc_alloc(size_t bytes, void** dptr);
+int prl_ipc_free(void* dptr);
+int prl_ipc_export(const void* dptr, uint8_t handle[64]);
+int prl_ipc_open(const uint8_t handle[64], void** dptr);
+int prl_ipc_close(void* dptr);
+int prl_enable_peer_access(int32_t peer_device);
+int prl_weights_push(const void* src_arena, void* const* dst_arenas, int32_t n_dst, size_t offset_bytes,
+                     size_t bytes, int32_t max_ctas /*0 = 2 per SM*/, prl_stream_t stream);
+int prl_weights_signal(void* const* ctrl_blocks, int32_t n_dst, uint64_t version, prl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

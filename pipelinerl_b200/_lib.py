@@ -111,6 +111,15 @@ _SIGNATURES = {
     "prl_sample_logprob": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_uint64,
                                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "prl_advance_state": (C.c_int, [C.POINTER(EngineState), C.c_void_p]),
+    "prl_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "prl_ipc_free": (C.c_int, [C.c_void_p]),
+    "prl_ipc_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "prl_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "prl_ipc_close": (C.c_int, [C.c_void_p]),
+    "prl_enable_peer_access": (C.c_int, [C.c_int32]),
+    "prl_weights_push": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_size_t, C.c_size_t, C.c_int32,
+                                   C.c_void_p]),
+    "prl_weights_signal": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_uint64, C.c_void_p]),
     "prl_adamw_workspace_bytes": (C.c_size_t, []),
     "prl_adamw_step": (C.c_int, [C.POINTER(AdamwArgs), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }
