@@ -186,6 +186,8 @@ int prl_adamw_step(const prl_adamw_args* args, float* grad_norm_out,
  *   splits in index order (deterministic).  K %% 8 == 0; pointers 16-B aligned.
  * ======================================================================= */
 int prl_gemm_auto_split_k(int64_t M, int64_t N, int64_t K);
+/* Tuning knob: shared-memory tile ring per CTA in KB (<= 100 lets two CTAs share an SM). */
+int prl_gemm_set_smem_budget_kb(int32_t kb);
 int prl_gemm_bf16_splitk(const void* W, const void* W_lo /*or NULL*/, const void* X,
                          int64_t M, int64_t N, int64_t K, int32_t split_k /*0 = auto*/,
                          float* partials, prl_stream_t stream);
@@ -224,8 +226,10 @@ int prl_paged_attn_decode(const void* q_bf16, const void* kv_cache_bf16, int64_t
                           void* workspace, size_t workspace_bytes, prl_stream_t stream);
 /* Sampling with in-kernel logprob capture: id ~ softmax(logits/T) (Gumbel-max, counter-based RNG on
  * (seed, step, row, vocab id)) or argmax when greedy; logprob = log_softmax(logits/T)[id]. */
+size_t prl_sample_workspace_bytes(int32_t B);
 int prl_sample_logprob(const float* logits /*[B,V]*/, int32_t B, int32_t V, float temperature, int32_t greedy,
-                       uint64_t seed, uint32_t step, int32_t* out_ids, float* out_logprobs, prl_stream_t stream);
+                       uint64_t seed, uint32_t step, int32_t* out_ids, float* out_logprobs,
+                       void* workspace, size_t workspace_bytes, prl_stream_t stream);
 /* Device-resident scheduler state of one sampler (all pointers device, one entry per slot).
  * prl_advance_state moves every active slot one token forward without a host round trip:
  * feeds the next prompt token while inside the prompt, else appends (sampled id, logprob) to the

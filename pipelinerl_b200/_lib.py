@@ -92,6 +92,7 @@ _SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_void_p]),
     "prl_gemm_auto_split_k": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
+    "prl_gemm_set_smem_budget_kb": (C.c_int, [C.c_int32]),
     "prl_gemm_bf16_splitk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                        C.c_void_p, C.c_void_p]),
     "prl_embed_rmsnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_int32,
@@ -108,8 +109,9 @@ _SIGNATURES = {
                                         C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t,
                                         C.c_void_p]),
+    "prl_sample_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "prl_sample_logprob": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_uint64,
-                                     C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                     C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "prl_advance_state": (C.c_int, [C.POINTER(EngineState), C.c_void_p]),
     "prl_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "prl_ipc_free": (C.c_int, [C.c_void_p]),

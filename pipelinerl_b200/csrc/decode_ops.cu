@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) embed_rmsnorm_kernel(const int32_t* __res
                                                            const __nv_bfloat16* __restrict__ gamma, float eps, int H,
                                                            int vocab, float* __restrict__ h,
                                                            __nv_bfloat16* __restrict__ x) {
-  __shared__ float s_red[8];
+  __shared__ float s_red[32];
   const int b = blockIdx.x;
   int tok = tokens[b];
   if (tok < 0 || tok >= vocab) tok = 0;
@@ -56,25 +56,48 @@ __global__ void __launch_bounds__(256) embed_rmsnorm_kernel(const int32_t* __res
 
 // ---- split-K reduce + residual add + RMSNorm --------------------------------------------
 // h[b,:] += sum_s part[s,b,:] ; x[b,:] = bf16(rmsnorm(h) * g)
-__global__ void __launch_bounds__(256) residual_rmsnorm_kernel(const float* __restrict__ part, int n_split, int B,
-                                                              int H, const __nv_bfloat16* __restrict__ gamma,
-                                                              float eps, float* __restrict__ h,
-                                                              __nv_bfloat16* __restrict__ x) {
-  extern __shared__ float s_row[];  // H floats
-  __shared__ float s_red[8];
+// One block per token; each thread owns float4 column groups, issues the residual load and all
+// n_split partial loads back to back (independent, L2-resident), so the kernel costs about one
+// L2 round trip + one block reduction instead of a serial chain per element.
+constexpr int kMaxSplitUnroll = 8;
+__global__ void __launch_bounds__(1024) residual_rmsnorm_kernel(const float* __restrict__ part, int n_split, int B,
+                                                               int H, const __nv_bfloat16* __restrict__ gamma,
+                                                               float eps, float* __restrict__ h,
+                                                               __nv_bfloat16* __restrict__ x) {
+  extern __shared__ float s_row[];  // H floats (only used when a thread owns more than one group)
+  __shared__ float s_red[32];
   const int b = blockIdx.x;
+  const int H4 = H >> 2;
+  float4* hrow = reinterpret_cast<float4*>(h + (int64_t)b * H);
   float ss = 0.f;
-  for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    float v = h[(int64_t)b * H + i];
-    for (int s = 0; s < n_split; ++s) v += part[((int64_t)s * B + b) * H + i];
-    s_row[i] = v;
-    h[(int64_t)b * H + i] = v;
-    ss += v * v;
+  float4 keep = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool single = H4 <= (int)blockDim.x;
+  for (int i = threadIdx.x; i < H4; i += blockDim.x) {
+    float4 v = hrow[i];
+    for (int s = 0; s < n_split; s += kMaxSplitUnroll) {
+      float4 p[kMaxSplitUnroll];
+#pragma unroll
+      for (int u = 0; u < kMaxSplitUnroll; ++u)
+        if (s + u < n_split) p[u] = reinterpret_cast<const float4*>(part + ((int64_t)(s + u) * B + b) * H)[i];
+#pragma unroll
+      for (int u = 0; u < kMaxSplitUnroll; ++u)
+        if (s + u < n_split) { v.x += p[u].x; v.y += p[u].y; v.z += p[u].z; v.w += p[u].w; }
+    }
+    hrow[i] = v;
+    if (single) keep = v; else reinterpret_cast<float4*>(s_row)[i] = v;
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
   const float tot = block_sum(ss, s_red);
   const float r = rsqrtf(tot / (float)H + eps);
-  for (int i = threadIdx.x; i < H; i += blockDim.x)
-    x[(int64_t)b * H + i] = __float2bfloat16_rn(s_row[i] * r * __bfloat162float(gamma[i]));
+  for (int i = threadIdx.x; i < H4; i += blockDim.x) {
+    const float4 v = single ? keep : reinterpret_cast<const float4*>(s_row)[i];
+    const uint2 gw = reinterpret_cast<const uint2*>(gamma)[i];
+    const float g0 = bf16_bits_to_float(gw.x & 0xffffu), g1 = bf16_bits_to_float(gw.x >> 16);
+    const float g2 = bf16_bits_to_float(gw.y & 0xffffu), g3 = bf16_bits_to_float(gw.y >> 16);
+    const uint32_t o0 = float_to_bf16_bits(v.x * r * g0), o1 = float_to_bf16_bits(v.y * r * g1);
+    const uint32_t o2 = float_to_bf16_bits(v.z * r * g2), o3 = float_to_bf16_bits(v.w * r * g3);
+    reinterpret_cast<uint2*>(x + (int64_t)b * H)[i] = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
+  }
 }
 
 // ---- split-K reduce + bias + RoPE + KV-page write ---------------------------------------
@@ -132,20 +155,24 @@ __global__ void __launch_bounds__(64) qkv_rope_cache_kernel(const float* __restr
 }
 
 // ---- split-K reduce + SiLU(gate) * up ------------------------------------------------------
-// part [n_split, B, 2I] (gate columns first, as in the fused gate_up weight) -> act [B, I] bf16
+// part [n_split, B, 2I] (gate columns first, as in the fused gate_up weight) -> act [B, I] bf16; 4 columns/thread
 __global__ void __launch_bounds__(256) silu_mul_kernel(const float* __restrict__ part, int n_split, int B, int I,
                                                       __nv_bfloat16* __restrict__ act) {
   const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= I) return;
-  float g = 0.f, u = 0.f;
+  const int i4 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= I) return;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f), u = g;
   for (int s = 0; s < n_split; ++s) {
     const float* p = part + ((int64_t)s * B + b) * 2 * I;
-    g += p[i];
-    u += p[I + i];
+    const float4 a = reinterpret_cast<const float4*>(p)[i4];
+    const float4 c = reinterpret_cast<const float4*>(p + I)[i4];
+    g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+    u.x += c.x; u.y += c.y; u.z += c.z; u.w += c.w;
   }
-  const float silu = g / (1.f + __expf(-g));
-  act[(int64_t)b * I + i] = __float2bfloat16_rn(silu * u);
+  auto f = [](float gg, float uu) { return (gg / (1.f + __expf(-gg))) * uu; };
+  const uint32_t o0 = float_to_bf16_bits(f(g.x, u.x)), o1 = float_to_bf16_bits(f(g.y, u.y));
+  const uint32_t o2 = float_to_bf16_bits(f(g.z, u.z)), o3 = float_to_bf16_bits(f(g.w, u.w));
+  reinterpret_cast<uint2*>(act + (int64_t)b * I)[i4] = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
 }
 
 // ---- sampler + in-kernel logprob capture ----------------------------------------------------
@@ -170,21 +197,26 @@ __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
   return a;
 }
 
-__global__ void __launch_bounds__(1024) sample_logprob_kernel(const float* __restrict__ logits, int V, float inv_temp,
-                                                             int greedy, uint64_t seed, uint32_t step,
-                                                             int32_t* __restrict__ out_ids,
-                                                             float* __restrict__ out_logprobs) {
-  const int b = blockIdx.x;
+constexpr int kSampleParts = 16;   // CTAs per row: 64 rows x 16 = 1024 CTAs keep every SM busy
+constexpr int kSampleThreads = 256;
+struct SamplePartial { float m, s, v; int i; };
+
+// phase 1: each CTA scans a contiguous 1/16 of the vocabulary of one row
+__global__ void __launch_bounds__(kSampleThreads) sample_partial_kernel(const float* __restrict__ logits, int V,
+                                                                       float inv_temp, int greedy, uint64_t seed,
+                                                                       uint32_t step, SamplePartial* __restrict__ part) {
+  const int b = blockIdx.x, pi = blockIdx.y;
   const float* z = logits + (int64_t)b * V;
+  const int per = (V + kSampleParts - 1) / kSampleParts;
+  const int lo = pi * per, hi = (lo + per < V) ? lo + per : V;
   float m = -INFINITY, s = 0.f;
   ArgMax best{-INFINITY, 0x7fffffff};
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+  for (int i = lo + threadIdx.x; i < hi; i += kSampleThreads) {
     const float zi = z[i] * inv_temp;
     if (zi > m) { s = s * __expf(m - zi) + 1.f; m = zi; } else { s += __expf(zi - m); }
     const float key = greedy ? zi : zi + gumbel(seed, step, (uint32_t)b, (uint32_t)i);
     best = better(best, ArgMax{key, i});
   }
-  // warp then block reduction of (m, s) and the arg-max
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
@@ -194,25 +226,42 @@ __global__ void __launch_bounds__(1024) sample_logprob_kernel(const float* __res
     ArgMax o2{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
     best = better(best, o2);
   }
-  __shared__ float s_m[32], s_s[32], s_v[32];
-  __shared__ int s_i[32];
+  __shared__ float s_m[8], s_s[8], s_v[8];
+  __shared__ int s_i[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) { s_m[warp] = m; s_s[warp] = s; s_v[warp] = best.v; s_i[warp] = best.i; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const int nw = blockDim.x >> 5;
     float M = -INFINITY, S = 0.f;
     ArgMax bb{-INFINITY, 0x7fffffff};
-    for (int w = 0; w < nw; ++w) {
+    for (int w = 0; w < kSampleThreads / 32; ++w) {
       const float mm = fmaxf(M, s_m[w]);
       S = (M == -INFINITY ? 0.f : S * __expf(M - mm)) + (s_m[w] == -INFINITY ? 0.f : s_s[w] * __expf(s_m[w] - mm));
       M = mm;
       bb = better(bb, ArgMax{s_v[w], s_i[w]});
     }
-    const float lse = M + logf(S);
-    out_ids[b] = bb.i;
-    out_logprobs[b] = z[bb.i] * inv_temp - lse;
+    part[b * kSampleParts + pi] = SamplePartial{M, S, bb.v, bb.i};
   }
+}
+
+// phase 2: merge the 16 partials of a row (fixed order), emit id and log-probability
+__global__ void sample_finalize_kernel(const float* __restrict__ logits, int V, float inv_temp, int B,
+                                       const SamplePartial* __restrict__ part, int32_t* __restrict__ out_ids,
+                                       float* __restrict__ out_logprobs) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float M = -INFINITY, S = 0.f;
+  ArgMax bb{-INFINITY, 0x7fffffff};
+  for (int k = 0; k < kSampleParts; ++k) {
+    const SamplePartial q = part[b * kSampleParts + k];
+    const float mm = fmaxf(M, q.m);
+    S = (M == -INFINITY ? 0.f : S * __expf(M - mm)) + (q.m == -INFINITY ? 0.f : q.s * __expf(q.m - mm));
+    M = mm;
+    bb = better(bb, ArgMax{q.v, q.i});
+  }
+  const float lse = M + logf(S);
+  out_ids[b] = bb.i;
+  out_logprobs[b] = logits[(int64_t)b * V + bb.i] * inv_temp - lse;
 }
 
 // ---- advance the per-sequence state after a step (device-side, no host round trip) -------------
@@ -264,16 +313,20 @@ extern "C" int prl_embed_rmsnorm(const int32_t* tokens, const void* embed, const
 
 extern "C" int prl_residual_rmsnorm(const float* partials, int32_t n_split, int32_t B, int32_t H, const void* gamma,
                                     float eps, float* h, void* x_bf16, prl_stream_t st) {
-  PRL_CHECK_ARG(partials && gamma && h && x_bf16 && B >= 1 && H >= 1 && n_split >= 0, "prl_residual_rmsnorm: bad argument");
+  PRL_CHECK_ARG(partials && gamma && h && x_bf16 && B >= 1 && H >= 4 && n_split >= 0, "prl_residual_rmsnorm: bad argument");
+  PRL_CHECK_ARG(H % 4 == 0, "prl_residual_rmsnorm: hidden size must be a multiple of 4 (got %d)", H);
   PRL_CHECK_ARG(H * 4 <= 96 * 1024, "prl_residual_rmsnorm: hidden size too large for the row buffer");
   static bool configured = false;
   if (!configured) {
     PRL_CUDA(cudaFuncSetAttribute(residual_rmsnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     configured = true;
   }
-  residual_rmsnorm_kernel<<<B, 256, (size_t)H * 4, (cudaStream_t)st>>>(partials, n_split, B, H,
-                                                                       (const __nv_bfloat16*)gamma, eps, h,
-                                                                       (__nv_bfloat16*)x_bf16);
+  int threads = ((H / 4 + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  const size_t smem = (H / 4 > threads) ? (size_t)H * 4 : 0;
+  residual_rmsnorm_kernel<<<B, threads, smem, (cudaStream_t)st>>>(partials, n_split, B, H,
+                                                                 (const __nv_bfloat16*)gamma, eps, h,
+                                                                 (__nv_bfloat16*)x_bf16);
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }
@@ -297,20 +350,31 @@ extern "C" int prl_qkv_rope_cache(const float* partials, int32_t n_split, int32_
 
 extern "C" int prl_silu_mul(const float* partials, int32_t n_split, int32_t B, int32_t I, void* act_bf16,
                             prl_stream_t st) {
-  PRL_CHECK_ARG(partials && act_bf16 && B >= 1 && I >= 1 && n_split >= 1, "prl_silu_mul: bad argument");
-  dim3 grid((unsigned)((I + 255) / 256), (unsigned)B);
+  PRL_CHECK_ARG(partials && act_bf16 && B >= 1 && I >= 4 && n_split >= 1, "prl_silu_mul: bad argument");
+  PRL_CHECK_ARG(I % 4 == 0, "prl_silu_mul: intermediate size must be a multiple of 4 (got %d)", I);
+  dim3 grid((unsigned)((I / 4 + 255) / 256), (unsigned)B);
   silu_mul_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(partials, n_split, B, I, (__nv_bfloat16*)act_bf16);
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }
 
+extern "C" size_t prl_sample_workspace_bytes(int32_t B) {
+  return (size_t)(B < 1 ? 1 : B) * kSampleParts * sizeof(SamplePartial);
+}
+
 extern "C" int prl_sample_logprob(const float* logits, int32_t B, int32_t V, float temperature, int32_t greedy,
                                   uint64_t seed, uint32_t step, int32_t* out_ids, float* out_logprobs,
-                                  prl_stream_t st) {
-  PRL_CHECK_ARG(logits && out_ids && out_logprobs && B >= 1 && V >= 1, "prl_sample_logprob: bad argument");
+                                  void* workspace, size_t workspace_bytes, prl_stream_t st) {
+  PRL_CHECK_ARG(logits && out_ids && out_logprobs && workspace && B >= 1 && V >= 1, "prl_sample_logprob: bad argument");
   PRL_CHECK_ARG(temperature > 0.f, "prl_sample_logprob: temperature must be > 0 (use greedy=1 for argmax)");
-  sample_logprob_kernel<<<B, 1024, 0, (cudaStream_t)st>>>(logits, V, 1.f / temperature, greedy, seed, step, out_ids,
-                                                         out_logprobs);
+  PRL_CHECK_ARG(workspace_bytes >= prl_sample_workspace_bytes(B), "prl_sample_logprob: workspace too small");
+  dim3 grid((unsigned)B, kSampleParts);
+  sample_partial_kernel<<<grid, kSampleThreads, 0, (cudaStream_t)st>>>(logits, V, 1.f / temperature, greedy, seed, step,
+                                                                      (SamplePartial*)workspace);
+  PRL_LAUNCH_CHECK();
+  sample_finalize_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)st>>>(logits, V, 1.f / temperature, B,
+                                                                    (const SamplePartial*)workspace, out_ids,
+                                                                    out_logprobs);
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }

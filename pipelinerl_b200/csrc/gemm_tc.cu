@@ -79,7 +79,7 @@ constexpr int kBlockM = 128;  // output features per CTA (UMMA M)
 constexpr int kBlockK = 64;   // bf16 elements per stage row = 128 B = one swizzle atom
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 192;
-constexpr int kSmemBudget = 200 * 1024;
+static int g_smem_budget = 200 * 1024;  // per-CTA tile ring; <= 100 KB lets two CTAs share an SM
 
 struct GemmParams {
   int64_t M, N, K;
@@ -94,14 +94,14 @@ struct SmemLayout {
   static constexpr int kABytes = kBlockM * kBlockK * 2;       // 16 KB
   static constexpr int kBBytes = kNTile * kBlockK * 2;
   static constexpr int stage_bytes(bool lo) { return kABytes * (lo ? 2 : 1) + kBBytes; }
-  static constexpr int stages(bool lo) {
-    int s = kSmemBudget / stage_bytes(lo);
-    return s > 8 ? 8 : s;
+  static int stages(bool lo) {
+    int s = g_smem_budget / stage_bytes(lo);
+    return s > 8 ? 8 : (s < 2 ? 2 : s);
   }
 };
 
 template <int kNTile>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wlo,
                    const __grid_constant__ CUtensorMap tm_x, GemmParams p, int n_stages) {
   using L = SmemLayout<kNTile>;
@@ -264,6 +264,12 @@ int pick_ntile(int64_t M) {
 }  // namespace prl
 
 using namespace prl;
+
+extern "C" int prl_gemm_set_smem_budget_kb(int32_t kb) {
+  PRL_CHECK_ARG(kb >= 48 && kb <= 220, "prl_gemm_set_smem_budget_kb: 48..220 KB");
+  g_smem_budget = kb * 1024;
+  return PRL_OK;
+}
 
 extern "C" int prl_gemm_auto_split_k(int64_t M, int64_t N, int64_t K) {
   if (M <= 0 || N <= 0 || K <= 0) return 1;

@@ -98,6 +98,7 @@ class DecodeEngine:
         self.attn_splits = int(self.lib.prl_paged_attn_splits(B, cfg.num_kv_heads, max_seq_len))
         self.attn_ws = torch.zeros(int(self.lib.prl_paged_attn_workspace_bytes(B, cfg.num_q_heads, self.attn_splits)),
                                    dtype=torch.uint8, device=d)
+        self.sample_ws = torch.zeros(int(self.lib.prl_sample_workspace_bytes(B)), dtype=torch.uint8, device=d)
         self.free_pages = list(range(self.n_pages - 1, 0, -1))
         self.free_slots = list(range(B - 1, -1, -1))
         self.slot_req: dict[int, Request] = {}
@@ -105,8 +106,7 @@ class DecodeEngine:
         self.temperature = 1.0
         self.greedy = False
         self.ignore_eos = False
-        self._graph: torch.cuda.CUDAGraph | None = None
-        self._graph_key = None
+        self._graphs: dict[int, torch.cuda.CUDAGraph] = {}
         self._next_id = 0
         self._state = self._make_state()
 
@@ -181,7 +181,8 @@ class DecodeEngine:
         lib, st = self.lib, _lib.stream_ptr()
         _lib.check(lib.prl_sample_logprob(self.logits.data_ptr(), self.B, self.cfg.vocab_size, float(self.temperature),
                                           int(self.greedy), self.seed, self.step_count, self.sampled.data_ptr(),
-                                          self.sampled_lp.data_ptr(), st))
+                                          self.sampled_lp.data_ptr(), self.sample_ws.data_ptr(),
+                                          self.sample_ws.numel(), st))
         self._state.ignore_eos = int(self.ignore_eos)
         _lib.check(lib.prl_advance_state(C.byref(self._state), st))
 
@@ -189,19 +190,25 @@ class DecodeEngine:
         """One token for every active slot.  The model part is replayed from a CUDA graph; sampling and
         state advance are launched per step (they take the step counter as an RNG argument)."""
         if self.use_graph:
-            key = (self.arena.data.data_ptr(),)
-            if self._graph is None or self._graph_key != key:
+            key = self.arena.data.data_ptr()
+            g = self._graphs.get(key)
+            if g is None:
                 self._step_kernels()  # warm-up outside capture (sets kernel attributes)
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._step_kernels()
-                self._graph, self._graph_key = g, key
-            self._graph.replay()
+                self._graphs[key] = g
+            g.replay()
         else:
             self._step_kernels()
         self._sample_and_advance()
         self.step_count += 1
+
+    def set_arena(self, arena: ParamArena) -> None:
+        """Switch the parameter buffer between two token steps (weight update flip).  Graphs are cached per
+        buffer, so after the first use of each of the two buffers a flip costs one dictionary lookup."""
+        self.arena = arena
 
     # ---- host-side admission / harvest --------------------------------------------------------
     def can_admit(self, prompt_len: int, max_tokens: int) -> bool:

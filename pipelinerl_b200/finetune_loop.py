@@ -1,0 +1,83 @@
+"""Trainer stage: micro-batches -> rl_step -> backward -> (boundary) fused AdamW -> weight update.
+
+Mirrors the control flow of pipelinerl/finetune_loop.py::rl_finetuning_worker (:562-1097) for one learner
+rank with the pieces that matter to the hot path:
+  * micro-batches accumulate until `samples_per_step` samples were seen (:674-713); sentinel batches
+    contribute loss*0 (:784-786);
+  * at the boundary: optimizer step with gradient clipping (:727-744), then `send_weight_update(version)`
+    every `weight_update_interval` steps with version = samples trained on (:936-949);
+  * `SamplesProcessed` / `WeightUpdateSuccess` / `TrainingDone` messages on topic `weight_update_request`.
+The model is any torch module (rl_step's contract); the optimizer is FusedAdamW; no Accelerate/DeepSpeed.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+from typing import Iterable
+
+import torch
+
+from .finetune.optim import FusedAdamW
+from .finetune.rl import RLConfig, rl_step
+from .finetune.types import PipelineBatchEncoding, TrainingMetrics
+from .weights import SamplesProcessed, TrainingDone, WeightUpdateManager
+
+
+@dataclass
+class TrainerConfig:
+    samples_per_step: int = 8              # train_batch_size * gradient_accumulation_passes (finetune_loop.py:629-631)
+    learning_rate: float = 1e-6
+    weight_decay: float = 0.01
+    gradient_clipping_threshold: float | None = 0.3
+    max_train_steps: int = 10
+    weight_update_interval: int = 1
+    rl: RLConfig = field(default_factory=RLConfig)
+
+
+def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding], cfg: TrainerConfig,
+                 weight_manager: WeightUpdateManager | None = None, message_writer=None,
+                 device: torch.device | str = "cuda:0") -> tuple[TrainingMetrics, list[dict]]:
+    dev = torch.device(device)
+    opt = FusedAdamW(model.named_parameters(), lr=cfg.learning_rate, weight_decay=cfg.weight_decay,
+                     max_grad_norm=cfg.gradient_clipping_threshold)
+    if weight_manager is not None:
+        weight_manager.src = opt.shadow_bf16
+    rl_cfg = cfg.rl.model_copy(update={"batch_size": cfg.samples_per_step})
+    tm = TrainingMetrics()
+    history: list[dict] = []
+    samples_in_step, step_stats, t_step = 0, [], time.time()
+    opt.zero_grad()
+    for batch in batches:
+        batch = batch.to_device(dev)
+        loss, stats = rl_step(model, batch, tm.completed_steps, cfg.max_train_steps, rl_cfg)
+        if batch.sentinel:
+            loss = loss * 0.0
+        loss.backward()
+        n_samples = 0 if batch.sentinel else (int(batch.seq_boundaries.numel()) - 1 - (1 if batch.padding else 0)
+                                               if batch.is_packed else batch.input_ids.shape[0])
+        samples_in_step += n_samples
+        tm.samples += n_samples
+        tm.tokens += int(batch.input_ids.numel())
+        tm.passes += 1
+        step_stats.append(stats)
+        if message_writer is not None:
+            message_writer.write(SamplesProcessed(samples_processed=tm.samples, timestamp=time.time()))
+        if samples_in_step < cfg.samples_per_step:
+            continue
+        grad_norm = opt.step()
+        opt.zero_grad()
+        tm.completed_steps += 1
+        tm.grad_norm = float(grad_norm.item())
+        tm.train_loss = sum(s.get("loss", 0.0) for s in step_stats)
+        pushed_ms = None
+        if weight_manager is not None and tm.completed_steps % cfg.weight_update_interval == 0:
+            pushed_ms = weight_manager.send_weight_update(tm.samples)
+            tm.last_broadcasted_version = tm.samples
+        history.append({"step": tm.completed_steps, "loss": tm.train_loss, "grad_norm": tm.grad_norm,
+                        "samples": tm.samples, "sec_per_step": time.time() - t_step, "push_ms": pushed_ms})
+        samples_in_step, step_stats, t_step = 0, [], time.time()
+        if tm.completed_steps >= cfg.max_train_steps:
+            break
+    if message_writer is not None:
+        message_writer.write(TrainingDone(timestamp=time.time()))
+    return tm, history

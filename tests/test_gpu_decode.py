@@ -87,11 +87,12 @@ def test_sampling_distribution_and_logprob_capture(cuda_device):
     logits = (torch.randn(1, V, generator=g) * 2).repeat(B, 1).to(cuda_device)
     ids = torch.zeros(B, dtype=torch.int32, device=cuda_device)
     lps = torch.zeros(B, device=cuda_device)
+    ws = torch.zeros(int(lib.prl_sample_workspace_bytes(B)), dtype=torch.uint8, device=cuda_device)
     counts = torch.zeros(V)
     T = 0.8
     ref = torch.log_softmax(logits[0].cpu() / T, -1)
     for step in range(400):
-        _lib.check(lib.prl_sample_logprob(logits.data_ptr(), B, V, T, 0, 1234, step, ids.data_ptr(), lps.data_ptr(), None))
+        _lib.check(lib.prl_sample_logprob(logits.data_ptr(), B, V, T, 0, 1234, step, ids.data_ptr(), lps.data_ptr(), ws.data_ptr(), ws.numel(), None))
         i = ids.cpu().long()
         assert torch.allclose(lps.cpu(), ref[i], atol=1e-4)
         counts += torch.bincount(i, minlength=V).float()
@@ -102,7 +103,7 @@ def test_sampling_distribution_and_logprob_capture(cuda_device):
     sigma = torch.sqrt(n * p[top] * (1 - p[top]))
     assert ((counts[top] - n * p[top]).abs() < 5 * sigma + 1).all()
     # greedy == argmax, ties to the lowest index
-    _lib.check(lib.prl_sample_logprob(logits.data_ptr(), B, V, 1.0, 1, 0, 0, ids.data_ptr(), lps.data_ptr(), None))
+    _lib.check(lib.prl_sample_logprob(logits.data_ptr(), B, V, 1.0, 1, 0, 0, ids.data_ptr(), lps.data_ptr(), ws.data_ptr(), ws.numel(), None))
     assert (ids.cpu() == int(torch.argmax(logits[0].cpu()))).all()
 
 

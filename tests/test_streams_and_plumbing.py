@@ -1,0 +1,110 @@
+"""Host plumbing (CPU): stream topics, trainer messages, push-slice partitioning incl. a world_size-2 gloo run."""
+import json
+import os
+import subprocess
+import sys
+import threading
+from pathlib import Path
+
+import pytest
+
+from pipelinerl_b200 import streams
+from pipelinerl_b200.weights import WeightUpdateSuccess, push_slice
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(autouse=True)
+def files_backend():
+    streams.reset_streams_backend()
+    streams.set_streams_backend("files")
+    yield
+    streams.reset_streams_backend()
+
+
+def test_stream_roundtrip_and_layout(tmp_path):
+    spec = streams.SingleStreamSpec(exp_path=tmp_path, topic="actor")
+    with streams.write_to_streams(spec) as w:
+        w.write({"a": 1})
+        w.write(WeightUpdateSuccess(version=7))
+    assert (tmp_path / "streams" / "actor" / "0" / "0" / "0.jsonl").exists()
+    with streams.read_stream(spec) as r:
+        got = r.read_available()
+    assert got[0] == {"a": 1} and got[1]["kind"] == "weight_update_success" and got[1]["version"] == 7
+
+
+def test_blocking_tail_sees_later_writes(tmp_path):
+    spec = streams.SingleStreamSpec(exp_path=tmp_path, topic="training_data", partition=1)
+    seen = []
+
+    def reader():
+        with streams.read_stream(spec) as r:
+            for x in r.read():
+                seen.append(x)
+                if len(seen) == 3:
+                    return
+    with streams.write_to_streams(spec) as w:
+        w.write({"i": 0})
+        t = threading.Thread(target=reader)
+        t.start()
+        w.write({"i": 1})
+        w.write({"i": 2})
+        t.join(timeout=10)
+    assert [x["i"] for x in seen] == [0, 1, 2]
+
+
+def test_round_robin_partitions(tmp_path):
+    spec = streams.StreamRangeSpec(exp_path=tmp_path, topic="training_data", partition_range=(0, 3))
+    with streams.write_to_streams(spec) as w:
+        for i in range(7):
+            w.write({"i": i})
+        w.write({"i": 99}, partition=2)
+    counts = []
+    for p in range(3):
+        with streams.read_stream(streams.SingleStreamSpec(exp_path=tmp_path, topic="training_data", partition=p)) as r:
+            counts.append([x["i"] for x in r.read_available()])
+    assert counts == [[0, 3, 6], [1, 4], [2, 5, 99]]
+
+
+def test_backend_must_be_set(tmp_path):
+    streams.reset_streams_backend()
+    with pytest.raises(ValueError):
+        streams.read_stream(streams.SingleStreamSpec(exp_path=tmp_path, topic="x"))
+    with pytest.raises(ValueError):
+        streams.set_streams_backend("kafka")
+
+
+@pytest.mark.parametrize("nbytes,n", [(16, 1), (15_230_000_000 // 16 * 16, 2), (4096, 3), (1600, 7), (32, 4)])
+def test_push_slices_cover_arena_exactly(nbytes, n):
+    at = 0
+    for r in range(n):
+        off, ln = push_slice(nbytes, r, n)
+        assert off == at and off % 16 == 0 and ln % 16 == 0
+        at += ln
+    assert at == nbytes
+
+
+def test_world_size_2_gloo_slices_and_max_reduce(tmp_path):
+    """The N>1 host logic (slice ownership, max-over-ranks timing) under torch.distributed gloo, world_size 2."""
+    script = tmp_path / "w2.py"
+    script.write_text(
+        "import os, sys, json, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {str(ROOT)!r})\n"
+        "from pipelinerl_b200.weights import push_slice\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "off, ln = push_slice(1 << 20, r, w)\n"
+        "t = torch.tensor([off, ln, 10.0 + r], dtype=torch.float64)\n"
+        "allt = [torch.zeros(3, dtype=torch.float64) for _ in range(w)]\n"
+        "dist.all_gather(allt, t)\n"
+        "mx = torch.tensor([10.0 + r], dtype=torch.float64); dist.all_reduce(mx, op=dist.ReduceOp.MAX)\n"
+        "if r == 0: print(json.dumps({'slices': [a.tolist() for a in allt], 'max': mx.item()}))\n"
+        "dist.destroy_process_group()\n")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29571")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29571", str(script)],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    (o0, l0, _), (o1, l1, _) = out["slices"]
+    assert o0 == 0 and o1 == l0 and l0 + l1 == (1 << 20) and out["max"] == 11.0
