@@ -210,7 +210,8 @@ int prl_residual_rmsnorm(const float* partials, int32_t n_split, int32_t B, int3
                          float eps, float* h /*in/out*/, void* x_bf16 /*out*/, prl_stream_t stream);
 int prl_qkv_rope_cache(const float* partials, int32_t n_split, int32_t B, const void* bias_bf16 /*or NULL*/,
                        int32_t n_q, int32_t n_kv, int32_t head_dim, const int32_t* positions /*[B]*/,
-                       const int32_t* block_table /*[B,max_blocks]*/, int32_t max_blocks,
+                       const int32_t* block_table /*[slots,max_blocks]*/, int32_t max_blocks,
+                       const int32_t* row_slot /*[B] block-table row of each token row, or NULL = identity*/,
                        const float* inv_freq /*[head_dim/2]*/, void* q_out_bf16 /*[B,n_q,128]*/,
                        void* kv_cache_bf16, int64_t n_pages, int32_t layer, int32_t page_size,
                        prl_stream_t stream);
@@ -224,6 +225,16 @@ int prl_paged_attn_decode(const void* q_bf16, const void* kv_cache_bf16, int64_t
                           int32_t B, int32_t n_q, int32_t n_kv, int32_t head_dim, int32_t page_size,
                           int32_t n_splits, float sm_scale, void* out_bf16 /*[B, n_q*128]*/,
                           void* workspace, size_t workspace_bytes, prl_stream_t stream);
+/* Chunked prefill: causal attention of seq_q_len[z] query rows (starting at row seq_q_start[z], first
+ * position seq_pos0[z]) against the paged KV of block-table row seq_slot[z]; the chunk's own K/V must
+ * already be in the cache (prl_qkv_rope_cache).  Replaces vLLM's chunked-prefill attention
+ * (conf/base.yaml:64,72). */
+int prl_paged_attn_prefill(const void* q_bf16 /*[rows,n_q,128]*/, const void* kv_cache_bf16, int64_t n_pages,
+                           int32_t n_layers, int32_t layer, const int32_t* block_table, int32_t max_blocks,
+                           const int32_t* seq_q_start, const int32_t* seq_q_len, const int32_t* seq_pos0,
+                           const int32_t* seq_slot, int32_t n_seqs, int32_t max_q_len, int32_t n_q, int32_t n_kv,
+                           int32_t head_dim, int32_t page_size, float sm_scale, void* out_bf16 /*[rows,n_q*128]*/,
+                           prl_stream_t stream);
 /* Sampling with in-kernel logprob capture: id ~ softmax(logits/T) (Gumbel-max, counter-based RNG on
  * (seed, step, row, vocab id)) or argmax when greedy; logprob = log_softmax(logits/T)[id]. */
 size_t prl_sample_workspace_bytes(int32_t B);

@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(256) embed_rmsnorm_kernel(const int32_t* __res
                                                            const __nv_bfloat16* __restrict__ gamma, float eps, int H,
                                                            int vocab, float* __restrict__ h,
                                                            __nv_bfloat16* __restrict__ x) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_red[32];
   const int b = blockIdx.x;
   int tok = tokens[b];
@@ -64,6 +66,8 @@ __global__ void __launch_bounds__(1024) residual_rmsnorm_kernel(const float* __r
                                                                int H, const __nv_bfloat16* __restrict__ gamma,
                                                                float eps, float* __restrict__ h,
                                                                __nv_bfloat16* __restrict__ x) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_row[];  // H floats (only used when a thread owns more than one group)
   __shared__ float s_red[32];
   const int b = blockIdx.x;
@@ -107,10 +111,13 @@ __global__ void __launch_bounds__(64) qkv_rope_cache_kernel(const float* __restr
                                                            const __nv_bfloat16* __restrict__ bias, int n_q, int n_kv,
                                                            const int32_t* __restrict__ positions,
                                                            const int32_t* __restrict__ block_table, int max_blocks,
+                                                           const int32_t* __restrict__ row_slot,
                                                            const float* __restrict__ inv_freq_tab,
                                                            __nv_bfloat16* __restrict__ q_out,
                                                            __nv_bfloat16* __restrict__ kv_cache, int64_t n_pages,
                                                            int layer, int page_size) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int D = 128;
   const int b = blockIdx.x, head = blockIdx.y, i = threadIdx.x;  // i in [0, 64)
   const int n_heads = n_q + 2 * n_kv;
@@ -145,7 +152,8 @@ __global__ void __launch_bounds__(64) qkv_rope_cache_kernel(const float* __restr
   } else {
     const int kv = is_v ? 1 : 0;
     const int kvh = is_v ? head - n_q - n_kv : head - n_q;
-    const int page = block_table[(int64_t)b * max_blocks + pos / page_size];
+    const int slot_row = row_slot ? row_slot[b] : b;
+    const int page = block_table[(int64_t)slot_row * max_blocks + pos / page_size];
     const int slot = pos % page_size;
     const int64_t row = (((int64_t)(layer * 2 + kv) * n_pages + page) * n_kv + kvh) * page_size + slot;
     __nv_bfloat16* dst = kv_cache + row * D;
@@ -158,6 +166,8 @@ __global__ void __launch_bounds__(64) qkv_rope_cache_kernel(const float* __restr
 // part [n_split, B, 2I] (gate columns first, as in the fused gate_up weight) -> act [B, I] bf16; 4 columns/thread
 __global__ void __launch_bounds__(256) silu_mul_kernel(const float* __restrict__ part, int n_split, int B, int I,
                                                       __nv_bfloat16* __restrict__ act) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const int i4 = blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 * 4 >= I) return;
@@ -205,6 +215,8 @@ struct SamplePartial { float m, s, v; int i; };
 __global__ void __launch_bounds__(kSampleThreads) sample_partial_kernel(const float* __restrict__ logits, int V,
                                                                        float inv_temp, int greedy, uint64_t seed,
                                                                        uint32_t step, SamplePartial* __restrict__ part) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, pi = blockIdx.y;
   const float* z = logits + (int64_t)b * V;
   const int per = (V + kSampleParts - 1) / kSampleParts;
@@ -248,6 +260,8 @@ __global__ void __launch_bounds__(kSampleThreads) sample_partial_kernel(const fl
 __global__ void sample_finalize_kernel(const float* __restrict__ logits, int V, float inv_temp, int B,
                                        const SamplePartial* __restrict__ part, int32_t* __restrict__ out_ids,
                                        float* __restrict__ out_logprobs) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float M = -INFINITY, S = 0.f;
@@ -269,6 +283,8 @@ __global__ void sample_finalize_kernel(const float* __restrict__ logits, int V, 
 // prompt the sample is discarded and the next prompt token is fed (prefill-by-decode); afterwards
 // the sampled id / logprob are appended to the slot's output ring and become the next input.
 __global__ void advance_kernel(prl_engine_state st) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= st.B) return;
   if (!st.active[b]) return;
@@ -304,9 +320,8 @@ using namespace prl;
 extern "C" int prl_embed_rmsnorm(const int32_t* tokens, const void* embed, const void* gamma, float eps, int32_t B,
                                  int32_t H, int32_t vocab, float* h, void* x_bf16, prl_stream_t st) {
   PRL_CHECK_ARG(tokens && embed && gamma && h && x_bf16 && B >= 1 && H >= 1, "prl_embed_rmsnorm: bad argument");
-  embed_rmsnorm_kernel<<<B, 256, 0, (cudaStream_t)st>>>(tokens, (const __nv_bfloat16*)embed,
-                                                       (const __nv_bfloat16*)gamma, eps, H, vocab, h,
-                                                       (__nv_bfloat16*)x_bf16);
+  PRL_CUDA(launch_pdl(embed_rmsnorm_kernel, dim3(B), dim3(256), 0, (cudaStream_t)st, tokens, (const __nv_bfloat16*)embed,
+                      (const __nv_bfloat16*)gamma, eps, (int)H, (int)vocab, h, (__nv_bfloat16*)x_bf16));
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }
@@ -324,26 +339,25 @@ extern "C" int prl_residual_rmsnorm(const float* partials, int32_t n_split, int3
   int threads = ((H / 4 + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
   const size_t smem = (H / 4 > threads) ? (size_t)H * 4 : 0;
-  residual_rmsnorm_kernel<<<B, threads, smem, (cudaStream_t)st>>>(partials, n_split, B, H,
-                                                                 (const __nv_bfloat16*)gamma, eps, h,
-                                                                 (__nv_bfloat16*)x_bf16);
+  PRL_CUDA(launch_pdl(residual_rmsnorm_kernel, dim3(B), dim3(threads), smem, (cudaStream_t)st, partials, (int)n_split,
+                      (int)B, (int)H, (const __nv_bfloat16*)gamma, eps, h, (__nv_bfloat16*)x_bf16));
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }
 
 extern "C" int prl_qkv_rope_cache(const float* partials, int32_t n_split, int32_t B, const void* bias, int32_t n_q,
                                   int32_t n_kv, int32_t head_dim, const int32_t* positions,
-                                  const int32_t* block_table, int32_t max_blocks, const float* inv_freq, void* q_out,
+                                  const int32_t* block_table, int32_t max_blocks, const int32_t* row_slot,
+                                  const float* inv_freq, void* q_out,
                                   void* kv_cache, int64_t n_pages, int32_t layer, int32_t page_size,
                                   prl_stream_t st) {
   PRL_CHECK_ARG(partials && positions && block_table && q_out && kv_cache && inv_freq, "prl_qkv_rope_cache: NULL argument");
   PRL_CHECK_ARG(head_dim == 128, "prl_qkv_rope_cache: head_dim must be 128 (got %d)", head_dim);
   PRL_CHECK_ARG(B >= 1 && n_q >= 1 && n_kv >= 1 && page_size >= 1 && max_blocks >= 1, "prl_qkv_rope_cache: bad shape");
   dim3 grid((unsigned)B, (unsigned)(n_q + 2 * n_kv));
-  qkv_rope_cache_kernel<<<grid, 64, 0, (cudaStream_t)st>>>(partials, n_split, B, (const __nv_bfloat16*)bias, n_q, n_kv,
-                                                          positions, block_table, max_blocks, inv_freq,
-                                                          (__nv_bfloat16*)q_out, (__nv_bfloat16*)kv_cache, n_pages,
-                                                          layer, page_size);
+  PRL_CUDA(launch_pdl(qkv_rope_cache_kernel, grid, dim3(64), 0, (cudaStream_t)st, partials, (int)n_split, (int)B,
+                      (const __nv_bfloat16*)bias, (int)n_q, (int)n_kv, positions, block_table, (int)max_blocks, row_slot,
+                      inv_freq, (__nv_bfloat16*)q_out, (__nv_bfloat16*)kv_cache, n_pages, (int)layer, (int)page_size));
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }
@@ -353,7 +367,8 @@ extern "C" int prl_silu_mul(const float* partials, int32_t n_split, int32_t B, i
   PRL_CHECK_ARG(partials && act_bf16 && B >= 1 && I >= 4 && n_split >= 1, "prl_silu_mul: bad argument");
   PRL_CHECK_ARG(I % 4 == 0, "prl_silu_mul: intermediate size must be a multiple of 4 (got %d)", I);
   dim3 grid((unsigned)((I / 4 + 255) / 256), (unsigned)B);
-  silu_mul_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(partials, n_split, B, I, (__nv_bfloat16*)act_bf16);
+  PRL_CUDA(launch_pdl(silu_mul_kernel, grid, dim3(256), 0, (cudaStream_t)st, partials, (int)n_split, (int)B, (int)I,
+                      (__nv_bfloat16*)act_bf16));
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }
@@ -369,12 +384,11 @@ extern "C" int prl_sample_logprob(const float* logits, int32_t B, int32_t V, flo
   PRL_CHECK_ARG(temperature > 0.f, "prl_sample_logprob: temperature must be > 0 (use greedy=1 for argmax)");
   PRL_CHECK_ARG(workspace_bytes >= prl_sample_workspace_bytes(B), "prl_sample_logprob: workspace too small");
   dim3 grid((unsigned)B, kSampleParts);
-  sample_partial_kernel<<<grid, kSampleThreads, 0, (cudaStream_t)st>>>(logits, V, 1.f / temperature, greedy, seed, step,
-                                                                      (SamplePartial*)workspace);
+  PRL_CUDA(launch_pdl(sample_partial_kernel, grid, dim3(kSampleThreads), 0, (cudaStream_t)st, logits, (int)V,
+                      1.f / temperature, (int)greedy, seed, step, (SamplePartial*)workspace));
   PRL_LAUNCH_CHECK();
-  sample_finalize_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)st>>>(logits, V, 1.f / temperature, B,
-                                                                    (const SamplePartial*)workspace, out_ids,
-                                                                    out_logprobs);
+  PRL_CUDA(launch_pdl(sample_finalize_kernel, dim3((B + 63) / 64), dim3(64), 0, (cudaStream_t)st, logits, (int)V,
+                      1.f / temperature, (int)B, (const SamplePartial*)workspace, out_ids, out_logprobs));
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }
@@ -385,7 +399,7 @@ extern "C" int prl_advance_state(const prl_engine_state* state, prl_stream_t st)
                     state->active && state->prompt_buf && state->prompt_len && state->out_ids &&
                     state->out_logprobs && state->gen_count && state->max_new && state->finished,
                 "prl_advance_state: NULL field");
-  advance_kernel<<<(state->B + 127) / 128, 128, 0, (cudaStream_t)st>>>(*state);
+  PRL_CUDA(launch_pdl(advance_kernel, dim3((state->B + 127) / 128), dim3(128), 0, (cudaStream_t)st, *state));
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }

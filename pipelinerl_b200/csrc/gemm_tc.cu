@@ -79,7 +79,7 @@ constexpr int kBlockM = 128;  // output features per CTA (UMMA M)
 constexpr int kBlockK = 64;   // bf16 elements per stage row = 128 B = one swizzle atom
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 192;
-static int g_smem_budget = 200 * 1024;  // per-CTA tile ring; <= 100 KB lets two CTAs share an SM
+static int g_smem_budget = 100 * 1024;  // per-CTA tile ring; <= 100 KB lets two CTAs share an SM
 
 struct GemmParams {
   int64_t M, N, K;
@@ -146,12 +146,29 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   ptx::tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===== TMA producer =====
+    // Weights do not depend on the preceding kernel: fill the first ring pass with WEIGHT tiles right away
+    // (programmatic dependent launch lets this run under the predecessor's tail), then wait for the
+    // dependency and add the activation tiles.
     if (lane == 0) {
       const uint32_t tx = (uint32_t)stage_bytes;
-      for (int i = 0; i < n_kb; ++i) {
+      const int pre = n_kb < n_stages ? n_kb : n_stages;
+      for (int i = 0; i < pre; ++i) {
+        ptx::mbar_arrive_expect_tx(full_bar(i), tx);
+        const uint32_t a_dst = smem_base + (uint32_t)(i * stage_bytes);
+        const int kcoord = (kb_begin + i) * kBlockK;
+        ptx::tma_load_2d(a_dst, &tm_w, kcoord, n0, full_bar(i), ptx::kEvictFirst);
+        if (lo) ptx::tma_load_2d(a_dst + L::kABytes, &tm_wlo, kcoord, n0, full_bar(i), ptx::kEvictFirst);
+      }
+      pdl_wait();
+      for (int i = 0; i < pre; ++i) {
+        const uint32_t b_dst = smem_base + (uint32_t)(i * stage_bytes) + L::kABytes * (lo ? 2 : 1);
+        ptx::tma_load_2d(b_dst, &tm_x, (kb_begin + i) * kBlockK, m0, full_bar(i), ptx::kEvictLast);
+      }
+      for (int i = pre; i < n_kb; ++i) {
         const int s = i % n_stages;
         const uint32_t ph = (uint32_t)((i / n_stages) & 1);
         ptx::mbar_wait(empty_bar(s), ph ^ 1u);
@@ -199,6 +216,7 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
     __syncwarp();
   } else {
     // ===== epilogue: TMEM -> registers -> fp32 partial tile =====
+    pdl_wait();  // the partial buffer may still be read by the predecessor's consumer
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after_sync();
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
@@ -247,7 +265,7 @@ int launch_gemm(const CUtensorMap& tw, const CUtensorMap& twl, const CUtensorMap
     configured = smem;
   }
   dim3 grid((unsigned)((p.N + kBlockM - 1) / kBlockM), (unsigned)p.split_k, (unsigned)((p.M + kNTile - 1) / kNTile));
-  gemm_swapab_kernel<kNTile><<<grid, kThreads, smem, stream>>>(tw, twl, tx, p, n_stages);
+  PRL_CUDA(launch_pdl(gemm_swapab_kernel<kNTile>, grid, dim3(kThreads), (size_t)smem, stream, tw, twl, tx, p, n_stages));
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }

@@ -46,8 +46,33 @@ void count_launch(int n = 1);
   } while (0)
 
 int num_sms();  // SM count of the current device (cached per device)
+bool use_pdl();  // programmatic dependent launch for the token-step kernels (PRL_PDL=0 disables)
+
+// Launch with the programmatic-stream-serialization attribute: the kernel may start while its
+// predecessor on the stream is still draining; it must execute pdl_wait() before touching anything
+// the predecessor wrote (or still reads).  Works under stream capture (programmatic graph edges).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = use_pdl() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 constexpr int kWarp = 32;
+
+// PDL device side: let the next kernel of the stream start its prologue / weight prefetch now ...
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// ... and block until every prerequisite grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

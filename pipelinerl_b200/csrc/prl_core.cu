@@ -2,6 +2,7 @@
 #include "prl_common.cuh"
 #include <atomic>
 #include <string.h>
+#include <stdlib.h>
 
 namespace prl {
 
@@ -16,6 +17,15 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+bool use_pdl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PRL_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 int num_sms() {
   static int cached[64];

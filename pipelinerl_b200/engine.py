@@ -44,12 +44,14 @@ class Request:
     output_logprobs: list[float] = field(default_factory=list)
     finish_reason: str | None = None
     model_version: int = 0
+    prefix_key: int | None = None
 
 
 class DecodeEngine:
     def __init__(self, cfg: ModelConfig, arena: ParamArena, max_batch: int = 64, max_seq_len: int = 16384,
                  n_pages: int | None = None, max_new_tokens: int = 8192, eos_id: int = -1, seed: int = 42,
-                 device: torch.device | str = "cuda:0", use_cuda_graph: bool = True):
+                 device: torch.device | str = "cuda:0", use_cuda_graph: bool = True, prefill_chunk: int = 1024,
+                 prefix_sharing: bool = True):
         if cfg.head_dim != 128:
             raise ValueError("the sm_100a attention kernel is built for head_dim 128")
         self.cfg, self.arena = cfg, arena
@@ -107,6 +109,15 @@ class DecodeEngine:
         self.greedy = False
         self.ignore_eos = False
         self._graphs: dict[int, torch.cuda.CUDAGraph] = {}
+        # ---- chunked prefill + prefix sharing (GRPO attempts share their prompt) ----
+        self.prefill_chunk = int(prefill_chunk)
+        self.prefix_sharing = prefix_sharing
+        self.page_ref = [0] * self.n_pages
+        self._prefill_queue: list[Request] = []
+        self._prefix_cache: dict[int, dict] = {}      # hash(prompt prefix) -> entry
+        self._pending_share: list[tuple[Request, dict]] = []
+        self._pf = None                                # lazily allocated prefill buffers
+        self.stats = {"prefill_tokens": 0, "prefix_hits": 0, "prefix_hit_tokens": 0}
         self._next_id = 0
         self._state = self._make_state()
 
@@ -134,9 +145,11 @@ class DecodeEngine:
         return s
 
     # ------------------------------------------------------------------------------------------
-    def _gemm(self, w_name: str, x: torch.Tensor, n: int, k: int, split: int, out: torch.Tensor, lo: str | None = None):
+    def _gemm(self, w_name: str, x: torch.Tensor, n: int, k: int, split: int, out: torch.Tensor, lo: str | None = None,
+              m: int | None = None):
         _lib.check(self.lib.prl_gemm_bf16_splitk(self.arena.ptr(w_name), self.arena.ptr(lo) if lo else None,
-                                                 x.data_ptr(), self.B, n, k, split, out.data_ptr(), self._st))
+                                                 x.data_ptr(), self.B if m is None else m, n, k, split,
+                                                 out.data_ptr(), self._st))
 
     def _step_kernels(self) -> None:
         """Enqueue one token step for all B slots on the current stream (graph-capturable)."""
@@ -155,7 +168,8 @@ class DecodeEngine:
             _lib.check(lib.prl_qkv_rope_cache(part.data_ptr(), self.split_k["qkv"], B,
                                               a.ptr(p + "qkv_proj.bias") if cfg.qkv_bias else None, cfg.num_q_heads,
                                               cfg.num_kv_heads, cfg.head_dim, self.positions.data_ptr(),
-                                              self.block_table.data_ptr(), self.max_blocks, self.inv_freq.data_ptr(),
+                                              self.block_table.data_ptr(), self.max_blocks, None,
+                                              self.inv_freq.data_ptr(),
                                               self.q.data_ptr(), self.kv_cache.data_ptr(), self.n_pages, l, PAGE_SIZE,
                                               st))
             _lib.check(lib.prl_paged_attn_decode(self.q.data_ptr(), self.kv_cache.data_ptr(), self.n_pages,
@@ -189,6 +203,8 @@ class DecodeEngine:
     def step(self) -> None:
         """One token for every active slot.  The model part is replayed from a CUDA graph; sampling and
         state advance are launched per step (they take the step counter as an RNG argument)."""
+        if self._prefill_queue or self._pending_share:
+            self.run_prefill()
         if self.use_graph:
             key = self.arena.data.data_ptr()
             g = self._graphs.get(key)
@@ -210,10 +226,155 @@ class DecodeEngine:
         buffer, so after the first use of each of the two buffers a flip costs one dictionary lookup."""
         self.arena = arena
 
+    # ---- chunked prefill ------------------------------------------------------------------------
+    def _prefill_buffers(self):
+        if self._pf is None:
+            cfg, C, d = self.cfg, self.prefill_chunk, self.dev
+            H, I = cfg.hidden_size, cfg.intermediate_size
+            widest = max(cfg.qkv_size, 2 * I, H)
+            i32 = dict(dtype=torch.int32, device=d)
+            self._pf = dict(
+                tokens=torch.zeros(C, **i32), pos=torch.zeros(C, **i32), slot=torch.zeros(C, **i32),
+                seq=torch.zeros(4, C, **i32),  # q_start, q_len, pos0, slot per packed sequence
+                h=torch.zeros(C, H, dtype=torch.float32, device=d), x=torch.zeros(C, H, dtype=torch.bfloat16, device=d),
+                q=torch.zeros(C, cfg.q_size, dtype=torch.bfloat16, device=d),
+                attn=torch.zeros(C, cfg.q_size, dtype=torch.bfloat16, device=d),
+                act=torch.zeros(C, I, dtype=torch.bfloat16, device=d),
+                part=torch.zeros(C * widest, dtype=torch.float32, device=d))
+        return self._pf
+
+    def _prefill_rows(self, segs: list[tuple[Request, int, int]]) -> None:
+        """One packed chunk: segs = [(request, first prompt index, n tokens)], total rows <= prefill_chunk."""
+        cfg, lib, a, pf = self.cfg, self.lib, self.arena, self._prefill_buffers()
+        n = sum(k for _, _, k in segs)
+        toks, pos, slot, meta = [], [], [], [[], [], [], []]
+        at = 0
+        for req, s0, k in segs:
+            toks += req.prompt_ids[s0:s0 + k]
+            pos += range(s0, s0 + k)
+            slot += [req.slot] * k
+            meta[0].append(at); meta[1].append(k); meta[2].append(s0); meta[3].append(req.slot)
+            at += k
+        pf["tokens"][:n].copy_(torch.tensor(toks, dtype=torch.int32), non_blocking=True)
+        pf["pos"][:n].copy_(torch.tensor(pos, dtype=torch.int32), non_blocking=True)
+        pf["slot"][:n].copy_(torch.tensor(slot, dtype=torch.int32), non_blocking=True)
+        ns = len(segs)
+        pf["seq"][:, :ns].copy_(torch.tensor(meta, dtype=torch.int32), non_blocking=True)
+        self._st = _lib.stream_ptr()
+        st, H, I = self._st, cfg.hidden_size, cfg.intermediate_size
+        part, h, x = pf["part"], pf["h"], pf["x"]
+        sm_scale = 1.0 / math.sqrt(cfg.head_dim)
+        _lib.check(lib.prl_embed_rmsnorm(pf["tokens"].data_ptr(), a.ptr("embed_tokens.weight"),
+                                         a.ptr("layers.0.input_layernorm.weight"), cfg.rms_eps, n, H, cfg.vocab_size,
+                                         h.data_ptr(), x.data_ptr(), st))
+        max_q = max(k for _, _, k in segs)
+        for l in range(cfg.num_layers):
+            p = f"layers.{l}."
+            self._gemm(p + "qkv_proj.weight", x, cfg.qkv_size, H, 1, part, m=n)
+            _lib.check(lib.prl_qkv_rope_cache(part.data_ptr(), 1, n, a.ptr(p + "qkv_proj.bias") if cfg.qkv_bias else None,
+                                              cfg.num_q_heads, cfg.num_kv_heads, cfg.head_dim, pf["pos"].data_ptr(),
+                                              self.block_table.data_ptr(), self.max_blocks, pf["slot"].data_ptr(),
+                                              self.inv_freq.data_ptr(), pf["q"].data_ptr(), self.kv_cache.data_ptr(),
+                                              self.n_pages, l, PAGE_SIZE, st))
+            seq = pf["seq"]
+            _lib.check(lib.prl_paged_attn_prefill(pf["q"].data_ptr(), self.kv_cache.data_ptr(), self.n_pages,
+                                                  cfg.num_layers, l, self.block_table.data_ptr(), self.max_blocks,
+                                                  seq[0].data_ptr(), seq[1].data_ptr(), seq[2].data_ptr(),
+                                                  seq[3].data_ptr(), ns, max_q, cfg.num_q_heads, cfg.num_kv_heads,
+                                                  cfg.head_dim, PAGE_SIZE, sm_scale, pf["attn"].data_ptr(), st))
+            self._gemm(p + "o_proj.weight", pf["attn"], H, cfg.q_size, 1, part, m=n)
+            _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), 1, n, H, a.ptr(p + "post_attention_layernorm.weight"),
+                                                cfg.rms_eps, h.data_ptr(), x.data_ptr(), st))
+            self._gemm(p + "gate_up_proj.weight", x, 2 * I, H, 1, part, m=n)
+            _lib.check(lib.prl_silu_mul(part.data_ptr(), 1, n, I, pf["act"].data_ptr(), st))
+            self._gemm(p + "down_proj.weight", pf["act"], H, I, 1, part, m=n)
+            nxt = f"layers.{l + 1}.input_layernorm.weight" if l + 1 < cfg.num_layers else "norm.weight"
+            _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), 1, n, H, a.ptr(nxt), cfg.rms_eps, h.data_ptr(),
+                                                x.data_ptr(), st))
+        self.stats["prefill_tokens"] += n
+
+    def run_prefill(self) -> int:
+        """Prefill the first P-1 prompt tokens of every queued request in packed chunks of <= prefill_chunk rows
+        (the last prompt token goes through the decode step, which yields the first sample), then attach the
+        requests that were waiting to share one of those prefixes.  Returns the number of prefilled tokens."""
+        done = 0
+        work = [[r, 0] for r in self._prefill_queue]   # [request, next prompt index]
+        self._prefill_queue = []
+        C = self.prefill_chunk
+        while work:
+            segs, room = [], C
+            for item in work:
+                r, at = item
+                k = min(room, len(r.prompt_ids) - 1 - at)
+                if k <= 0:
+                    continue
+                segs.append((r, at, k))
+                item[1] += k
+                room -= k
+                if room == 0:
+                    break
+            work = [it for it in work if it[1] < len(it[0].prompt_ids) - 1]
+            if segs:
+                self._prefill_rows(segs)
+                done += sum(k for _, _, k in segs)
+        for req, entry in self._pending_share:
+            self._attach_shared(req, entry)
+        self._pending_share = []
+        return done
+
+    # ---- pages and prefix sharing -----------------------------------------------------------------
+    def _alloc_pages(self, n: int) -> list[int]:
+        if len(self.free_pages) < n:
+            self._evict_prefixes(n - len(self.free_pages))
+        if len(self.free_pages) < n:
+            raise RuntimeError("engine out of KV pages")
+        pages = [self.free_pages.pop() for _ in range(n)]
+        for pg in pages:
+            self.page_ref[pg] = 1
+        return pages
+
+    def _release_pages(self, pages: list[int]) -> None:
+        for pg in pages:
+            self.page_ref[pg] -= 1
+            if self.page_ref[pg] == 0:
+                self.free_pages.append(pg)
+
+    def _evict_prefixes(self, need: int) -> None:
+        for key in list(self._prefix_cache):
+            if need <= 0:
+                break
+            e = self._prefix_cache[key]
+            if e["users"] == 0 and e["ready"]:
+                before = len(self.free_pages)
+                self._release_pages(e["pages"])
+                need -= len(self.free_pages) - before
+                del self._prefix_cache[key]
+
+    def _attach_shared(self, req: Request, entry: dict) -> None:
+        """Point req's block table at the shared full pages of a prefilled prefix; copy the partial page."""
+        n_full, rem = entry["n_full"], entry["rem"]
+        shared = entry["pages"][:n_full]
+        own = req.pages
+        for pg in shared:
+            self.page_ref[pg] += 1
+        # req.pages currently holds freshly allocated pages for the WHOLE request; give the first n_full back
+        self._release_pages(own[:n_full])
+        req.pages = shared + own[n_full:]
+        row = torch.zeros(self.max_blocks, dtype=torch.int32)
+        row[:len(req.pages)] = torch.tensor(req.pages, dtype=torch.int32)
+        self.block_table[req.slot].copy_(row, non_blocking=True)
+        if rem:
+            c = self.cfg
+            kv = self.kv_cache.view(c.num_layers, 2, self.n_pages, c.num_kv_heads, PAGE_SIZE, c.head_dim)
+            kv[:, :, req.pages[n_full], :, :rem] = kv[:, :, entry["pages"][n_full], :, :rem]
+        self.stats["prefix_hits"] += 1
+        self.stats["prefix_hit_tokens"] += n_full * PAGE_SIZE + rem
+
     # ---- host-side admission / harvest --------------------------------------------------------
     def can_admit(self, prompt_len: int, max_tokens: int) -> bool:
         need = (prompt_len + max_tokens + PAGE_SIZE - 1) // PAGE_SIZE
-        return bool(self.free_slots) and len(self.free_pages) >= need
+        evictable = sum(len(e["pages"]) for e in self._prefix_cache.values() if e["users"] == 0)
+        return bool(self.free_slots) and len(self.free_pages) + evictable >= need
 
     def add_request(self, prompt_ids: list[int], params: SamplingParams, model_version: int = 0) -> Request:
         n = len(prompt_ids)
@@ -227,16 +388,39 @@ class DecodeEngine:
         self._next_id += 1
         slot = self.free_slots.pop()
         n_pages = (n + params.max_tokens + PAGE_SIZE - 1) // PAGE_SIZE
-        req.slot, req.pages = slot, [self.free_pages.pop() for _ in range(n_pages)]
+        req.slot, req.pages = slot, self._alloc_pages(n_pages)
         row = torch.zeros(self.max_blocks, dtype=torch.int32)
         row[:n_pages] = torch.tensor(req.pages, dtype=torch.int32)
         self.block_table[slot].copy_(row, non_blocking=True)
         self.prompt_buf[slot, :n].copy_(torch.tensor(prompt_ids, dtype=torch.int32), non_blocking=True)
+        start = 0  # index of the prompt token the decode loop processes first
+        if self.prefill_chunk > 0 and n > 1:
+            start = n - 1
+            entry = None
+            if self.prefix_sharing and n - 1 >= PAGE_SIZE:
+                key = hash(tuple(prompt_ids[:n - 1]))
+                entry = self._prefix_cache.get(key)
+                if entry is None:
+                    # this request prefills; the entry keeps one reference on the prefix pages so later attempts of
+                    # the same problem can share them after this request has finished
+                    n_full, rem = (n - 1) // PAGE_SIZE, (n - 1) % PAGE_SIZE
+                    keep = req.pages[:n_full + (1 if rem else 0)]
+                    for pg in keep:
+                        self.page_ref[pg] += 1
+                    self._prefix_cache[key] = {"pages": keep, "n_full": n_full, "rem": rem, "users": 1, "ready": True}
+                    req.prefix_key = key
+                    self._prefill_queue.append(req)
+                else:
+                    entry["users"] += 1
+                    req.prefix_key = key
+                    self._pending_share.append((req, entry))
+            else:
+                self._prefill_queue.append(req)
         self.prompt_len[slot] = n
         self.max_new_t[slot] = params.max_tokens
-        self.tokens[slot] = prompt_ids[0]
-        self.positions[slot] = 0
-        self.seq_lens[slot] = 1
+        self.tokens[slot] = prompt_ids[start]
+        self.positions[slot] = start
+        self.seq_lens[slot] = start + 1
         self.gen_count[slot] = 0
         self.finished[slot] = 0
         self.active[slot] = 1
@@ -259,7 +443,9 @@ class DecodeEngine:
             req.finish_reason = "stop" if code == 1 else "length"
             self.block_table[slot].zero_()
             self.finished[slot] = 0
-            self.free_pages.extend(req.pages)
+            self._release_pages(req.pages)
+            if req.prefix_key is not None and req.prefix_key in self._prefix_cache:
+                self._prefix_cache[req.prefix_key]["users"] -= 1
             self.free_slots.append(slot)
             del self.slot_req[slot]
             done.append(req)

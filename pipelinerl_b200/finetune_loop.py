@@ -34,9 +34,19 @@ class TrainerConfig:
     rl: RLConfig = field(default_factory=RLConfig)
 
 
+def allreduce_gradients(flat_grad: torch.Tensor, group=None) -> None:
+    """Learner data parallelism: ONE sum all-reduce of the flat gradient arena per optimizer step — the only
+    collective on the hot path (the reference's DDP/ZeRO traffic at finetune_loop.py:716-755).
+    A plain SUM is exact because every rank's loss is already normalised by the GLOBAL samples-per-step
+    (rl/__init__.py:250, finetune_loop.py:644-646).  NCCL over NVLink on GPUs, gloo in the CPU tests."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+
+
 def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding], cfg: TrainerConfig,
                  weight_manager: WeightUpdateManager | None = None, message_writer=None,
-                 device: torch.device | str = "cuda:0") -> tuple[TrainingMetrics, list[dict]]:
+                 device: torch.device | str = "cuda:0", dp_group=None) -> tuple[TrainingMetrics, list[dict]]:
     dev = torch.device(device)
     opt = FusedAdamW(model.named_parameters(), lr=cfg.learning_rate, weight_decay=cfg.weight_decay,
                      max_grad_norm=cfg.gradient_clipping_threshold)
@@ -64,6 +74,7 @@ def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding
             message_writer.write(SamplesProcessed(samples_processed=tm.samples, timestamp=time.time()))
         if samples_in_step < cfg.samples_per_step:
             continue
+        allreduce_gradients(opt.grad, dp_group)
         grad_norm = opt.step()
         opt.zero_grad()
         tm.completed_steps += 1

@@ -38,8 +38,8 @@ class TorchQwen2(torch.nn.Module):
             self.register_parameter(key, torch.nn.Parameter(t.to(device)))
             self.names.append(name)
         d = cfg.head_dim
-        self.register_buffer("inv_freq", 1.0 / (cfg.rope_theta ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d)),
-                             persistent=False)
+        self.register_buffer("inv_freq", (1.0 / (cfg.rope_theta ** (torch.arange(0, d, 2, dtype=torch.int64).float()
+                                                                     / d))).to(device), persistent=False)
         self.layout = ArenaLayout.build(cfg)
 
     def p(self, name: str) -> torch.Tensor:

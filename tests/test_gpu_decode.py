@@ -32,7 +32,8 @@ def test_teacher_forced_logprobs_match_oracle_and_hf(cuda_device, kind):
     """Feed a 150-token sequence as the prompt (prefill-by-decode), read the logits of every step."""
     cfg = tiny_cfg(kind)
     w = tiny_weights(cfg)
-    eng = make_engine(cfg, w, cuda_device, max_batch=4, max_seq_len=256, max_new_tokens=8, use_cuda_graph=False)
+    eng = make_engine(cfg, w, cuda_device, max_batch=4, max_seq_len=256, max_new_tokens=8, use_cuda_graph=False,
+                      prefill_chunk=0)  # prefill-by-decode: every prompt position goes through the decode kernels
     gold = np.load(GOLDEN / f"qwen2_tiny_{kind}_T0.7.npz")
     tokens = gold["tokens"].tolist()
     from pipelinerl_b200.engine import SamplingParams
@@ -146,3 +147,85 @@ def test_paged_attention_long_context_vs_fp32(cuda_device):
             ref = torch.einsum("grs,gsd->grd", torch.softmax(s, -1), V).reshape(-1)
             err = (out[b].float() - ref).abs().max().item()
             assert err <= 4e-3 * max(1.0, ref.abs().max().item()), (splits, b, err)
+
+
+def test_prefix_sharing_and_chunked_prefill(cuda_device):
+    """8 attempts of one 150-token prompt (a GRPO group): one prefill, 7 prefix hits; results identical to an engine
+    without sharing and to the oracle.  prefill_chunk=64 forces multi-chunk prefill with a ragged tail."""
+    from pipelinerl_b200.engine import SamplingParams
+    cfg = tiny_cfg("gqa7")
+    w = tiny_weights(cfg)
+    g = torch.Generator().manual_seed(21)
+    prompt = torch.randint(0, cfg.vocab_size, (150,), generator=g).tolist()
+    other = torch.randint(0, cfg.vocab_size, (70,), generator=g).tolist()
+    prompts = [prompt] * 8 + [other]
+    outs = {}
+    for share in (True, False):
+        eng = make_engine(cfg, w, cuda_device, max_batch=12, max_seq_len=256, max_new_tokens=16, prefill_chunk=64,
+                          prefix_sharing=share)
+        res = eng.generate(prompts, SamplingParams(max_tokens=12, greedy=True))
+        outs[share] = [(r.output_ids, r.output_logprobs) for r in res]
+        if share:
+            assert eng.stats["prefix_hits"] == 7 and eng.stats["prefix_hit_tokens"] == 7 * 149
+            assert eng.stats["prefill_tokens"] == 149 + 69
+        else:
+            assert eng.stats["prefix_hits"] == 0 and eng.stats["prefill_tokens"] == 8 * 149 + 69
+        # all pages come back (prefix cache entries are evictable)
+        eng._evict_prefixes(10 ** 9)
+        assert len(eng.free_pages) == eng.n_pages - 1 and not any(eng.page_ref[1:])
+    for (ids_a, lp_a), (ids_b, lp_b) in zip(outs[True], outs[False]):
+        assert ids_a == ids_b and np.allclose(lp_a, lp_b, atol=1e-5)
+    assert all(o[0] == outs[True][0][0] for o in outs[True][:8])
+    orc = OracleQwen2(cfg, w)
+    logits = orc.forward(torch.tensor(prompt))[-1]
+    for tok, lp in zip(*outs[True][0]):
+        ref = torch.log_softmax(logits, -1)
+        assert abs(lp - float(ref[tok])) <= 3e-2
+        logits = orc.forward(torch.tensor([tok]))[-1]
+
+
+def test_prefill_attention_long_context_vs_fp32(cuda_device):
+    """Prefill attention alone: a 1000-row chunk at position 7000 of an 8000-token sequence (causal), plus a short
+    sequence packed in the same launch."""
+    from pipelinerl_b200 import _lib
+    lib = _lib.load()
+    dev = cuda_device
+    n_q, n_kv, D, P = 28, 4, 128, 64
+    seqs = [(7000, 1000), (0, 37)]           # (pos0, q_len)
+    max_blocks = 128
+    n_pages = 1 + sum((p0 + ql + P - 1) // P for p0, ql in seqs) + 3
+    g = torch.Generator().manual_seed(9)
+    L, layer = 1, 0
+    kv = (torch.randn(L * 2 * n_pages * n_kv * P * D, generator=g) * 0.5).to(torch.bfloat16).to(dev)
+    kv5 = kv.view(L, 2, n_pages, n_kv, P, D)
+    perm = torch.randperm(n_pages - 1, generator=g) + 1
+    bt = torch.zeros(len(seqs), max_blocks, dtype=torch.int32)
+    at = 0
+    for z, (p0, ql) in enumerate(seqs):
+        k = (p0 + ql + P - 1) // P
+        bt[z, :k] = perm[at:at + k].int()
+        at += k
+    rows = sum(ql for _, ql in seqs)
+    q = torch.randn(rows, n_q, D, generator=g).to(torch.bfloat16).to(dev)
+    out = torch.zeros(rows, n_q * D, dtype=torch.bfloat16, device=dev)
+    starts = [0, seqs[0][1]]
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+    qs, ql_t, p0_t, sl = i32(starts), i32([s[1] for s in seqs]), i32([s[0] for s in seqs]), i32([0, 1])
+    bt_d = bt.to(dev)
+    _lib.check(lib.prl_paged_attn_prefill(q.data_ptr(), kv.data_ptr(), n_pages, L, layer, bt_d.data_ptr(), max_blocks,
+                                          qs.data_ptr(), ql_t.data_ptr(), p0_t.data_ptr(), sl.data_ptr(), len(seqs),
+                                          max(s[1] for s in seqs), n_q, n_kv, D, P, 1.0 / D ** 0.5, out.data_ptr(), None))
+    torch.cuda.synchronize()
+    for z, (p0, ql) in enumerate(seqs):
+        S = p0 + ql
+        k = (S + P - 1) // P
+        pages = bt[z, :k].long().to(dev)
+        K = kv5[layer, 0, pages].permute(1, 0, 2, 3).reshape(n_kv, k * P, D)[:, :S].float()
+        V = kv5[layer, 1, pages].permute(1, 0, 2, 3).reshape(n_kv, k * P, D)[:, :S].float()
+        qz = q[starts[z]:starts[z] + ql].float().view(ql, n_kv, n_q // n_kv, D)
+        s = torch.einsum("tgrd,gsd->gtrs", qz, K) / D ** 0.5
+        mask = torch.arange(S, device=dev)[None, :] > (p0 + torch.arange(ql, device=dev))[:, None]
+        s = s.masked_fill(mask[None, :, None, :], float("-inf"))
+        ref = torch.einsum("gtrs,gsd->tgrd", torch.softmax(s, -1), V).reshape(ql, -1)
+        err = (out[starts[z]:starts[z] + ql].float() - ref).abs().max().item()
+        assert err <= 4e-3 * max(1.0, ref.abs().max().item()), (z, err)

@@ -1,0 +1,26 @@
+"""Cross-process, cross-GPU weight update (CUDA IPC + NVLink P2P).  Needs >= 2 GPUs: skipped on the
+single-GPU test box, run with `gpurun --gpus 2`."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_push_is_byte_exact_and_sampler_never_pauses():
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29583")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29583", str(ROOT / "tools" / "push_bench.py"),
+                          "--learners", "1", "--model", "tiny", "--updates", "3", "--context", "128", "--batch", "8"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["bytes_identical_on_all_ranks"]
+    assert out["ours"]["stall_ms_max"] is not None and out["ours"]["stall_ms_max"] < 50

@@ -108,3 +108,24 @@ def test_world_size_2_gloo_slices_and_max_reduce(tmp_path):
     out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
     (o0, l0, _), (o1, l1, _) = out["slices"]
     assert o0 == 0 and o1 == l0 and l0 + l1 == (1 << 20) and out["max"] == 11.0
+
+
+def test_dp_gradient_allreduce_gloo_world2(tmp_path):
+    """Learner DP exchange step: SUM all-reduce of the flat gradient arena (gloo, world_size 2)."""
+    script = tmp_path / "dp.py"
+    script.write_text(
+        "import sys, json, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {str(ROOT)!r})\n"
+        "from pipelinerl_b200.finetune_loop import allreduce_gradients\n"
+        "dist.init_process_group('gloo')\n"
+        "r = dist.get_rank()\n"
+        "g = torch.arange(10, dtype=torch.float32) * (r + 1)\n"
+        "allreduce_gradients(g)\n"
+        "if r == 0: print(json.dumps(g.tolist()))\n"
+        "dist.destroy_process_group()\n")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29577", str(script)],
+                         capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stderr[-2000:]
+    got = json.loads([l for l in res.stdout.splitlines() if l.startswith("[")][-1])
+    assert got == [3.0 * i for i in range(10)]
