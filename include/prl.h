@@ -192,6 +192,20 @@ int prl_gemm_bf16_splitk(const void* W, const void* W_lo /*or NULL*/, const void
                          int64_t M, int64_t N, int64_t K, int32_t split_k /*0 = auto*/,
                          float* partials, prl_stream_t stream);
 
+/* Fused output head with IN-KERNEL logprob capture: logits = X W^T (+ W_lo) are produced tile by tile in
+ * TMEM and reduced on the spot — per token logsumexp, exact entropy, the log-probability of a given target
+ * (teacher forcing: the trainer's new_logprobs, rl/__init__.py:207-233, and the reference-logprob scoring of
+ * llm.py:606-648) and/or a sample from softmax(logits/T) with its log-probability (the sampler +
+ * processed_logprobs path, conf/base.yaml:65).  Full-vocabulary logits (608 KB/token in fp32 for Qwen2.5)
+ * never reach HBM.  Any output pointer may be NULL.  Sampling uses the same counter-based RNG as
+ * prl_sample_logprob (row = token index). */
+size_t prl_head_workspace_bytes(int64_t M, int64_t V);
+int prl_head_logprob(const void* W /*[V,K] bf16*/, const void* W_lo /*or NULL*/, const void* X /*[M,K] bf16*/,
+                     int64_t M, int64_t V, int64_t K, float temperature, const int64_t* targets /*[M] or NULL*/,
+                     int32_t greedy, uint64_t seed, uint32_t step, float* logprob_target, float* entropy, float* lse,
+                     int32_t* sampled_ids, float* sampled_logprobs, void* workspace, size_t workspace_bytes,
+                     prl_stream_t stream);
+
 /* ======================================================================= *
  * Hot path (1): fused epilogue kernels of one token step and paged attention.
  *   Together with prl_gemm_bf16_splitk these are the decode step the

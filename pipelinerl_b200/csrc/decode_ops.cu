@@ -189,17 +189,6 @@ __global__ void __launch_bounds__(256) silu_mul_kernel(const float* __restrict__
 // logits [B, V] fp32 (split-K already 1 for the head).  Per token: z = logits / T;
 // id = argmax(z + Gumbel noise) (== a sample from softmax(z)), or argmax(z) when greedy;
 // logprob = z[id] - logsumexp(z)  (vLLM's processed_logprobs at top_p = 1, top_k = -1).
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {
-  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-  return x;
-}
-__device__ __forceinline__ float gumbel(uint64_t seed, uint32_t step, uint32_t b, uint32_t v) {
-  uint32_t x = mix32((uint32_t)seed ^ (v * 0x9E3779B9u));
-  x = mix32(x ^ (uint32_t)(seed >> 32) ^ (step * 0x85EBCA6Bu) ^ (b * 0xC2B2AE35u));
-  const float u = ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
-  return -__logf(-__logf(u));
-}
-
 struct ArgMax { float v; int i; };
 __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
   // ties -> lowest index, like torch.argmax

@@ -81,12 +81,23 @@ constexpr int kUmmaK = 16;
 constexpr int kThreads = 192;
 static int g_smem_budget = 100 * 1024;  // per-CTA tile ring; <= 100 KB lets two CTAs share an SM
 
+struct HeadPart { float m, s, u, key, z; int idx; };  // per (vocab tile, token): online-softmax state + best sample
+
 struct GemmParams {
   int64_t M, N, K;
   int kblocks;        // ceil(K / 64)
   int split_k;
   int has_lo;
   float* partials;    // [split_k, M, N]
+  // fused head epilogue (logits never reach HBM): temperature, teacher-forcing targets, sampling
+  int head;
+  float inv_temp;
+  const int64_t* targets;   // [M] or NULL
+  float* picked;            // [M] z of the target id (written by the CTA whose tile holds it)
+  int greedy;
+  unsigned long long seed;
+  unsigned int step;
+  HeadPart* head_part;      // [n_tiles, M]
 };
 
 template <int kNTile>
@@ -100,7 +111,7 @@ struct SmemLayout {
   }
 };
 
-template <int kNTile>
+template <int kNTile, bool kHead>
 __global__ void __launch_bounds__(kThreads, 2)
 gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wlo,
                    const __grid_constant__ CUtensorMap tm_x, GemmParams p, int n_stages) {
@@ -215,31 +226,85 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
     }
     __syncwarp();
   } else {
-    // ===== epilogue: TMEM -> registers -> fp32 partial tile =====
-    pdl_wait();  // the partial buffer may still be read by the predecessor's consumer
+    // ===== epilogue =====
+    pdl_wait();  // the output buffers may still be read by the predecessor's consumer
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after_sync();
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
-    const int feat = n0 + q * 32 + lane;       // output feature owned by this thread
-    float* out = p.partials + ((int64_t)split * p.M + m0) * p.N + feat;
+    const int feat = n0 + q * 32 + lane;       // output feature (vocab id) owned by this thread
     const int m_valid = (int)((p.M - m0) < kNTile ? (p.M - m0) : kNTile);
     const bool feat_ok = feat < p.N;
     constexpr int kChunk = kNTile < 32 ? 16 : 32;
+    if constexpr (!kHead) {
+      // ---- TMEM -> registers -> fp32 partial tile ----
+      float* out = p.partials + ((int64_t)split * p.M + m0) * p.N + feat;
 #pragma unroll 1
-    for (int c0 = 0; c0 < kNTile; c0 += kChunk) {
-      uint32_t r[kChunk];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      if constexpr (kChunk == 32) ptx::tmem_ld_32x32b_x32(taddr, r);
-      else ptx::tmem_ld_32x32b_x16(taddr, r);
-      ptx::tmem_ld_wait();
-      if (n_kb == 0) {
+      for (int c0 = 0; c0 < kNTile; c0 += kChunk) {
+        uint32_t r[kChunk];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        if constexpr (kChunk == 32) ptx::tmem_ld_32x32b_x32(taddr, r);
+        else ptx::tmem_ld_32x32b_x16(taddr, r);
+        ptx::tmem_ld_wait();
+        if (n_kb == 0) {
 #pragma unroll
-        for (int j = 0; j < kChunk; ++j) r[j] = 0u;
+          for (int j = 0; j < kChunk; ++j) r[j] = 0u;
+        }
+        if (feat_ok) {
+#pragma unroll
+          for (int j = 0; j < kChunk; ++j)
+            if (c0 + j < m_valid) out[(int64_t)(c0 + j) * p.N] = __uint_as_float(r[j]);  // 32 lanes -> 128 B row segment
+        }
       }
-      if (feat_ok) {
+    } else {
+      // ---- fused output head: per token, online-softmax statistics over this tile's 128 vocabulary rows,
+      //      the target logit and the best Gumbel-perturbed logit; the logits themselves are never stored ----
+      HeadPart* s_hp = reinterpret_cast<HeadPart*>(smem_raw + (smem_base - ptx::smem_u32(smem_raw)));  // [4][kNTile], ring is drained
+#pragma unroll 1
+      for (int c0 = 0; c0 < kNTile; c0 += kChunk) {
+        uint32_t r[kChunk];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        if constexpr (kChunk == 32) ptx::tmem_ld_32x32b_x32(taddr, r);
+        else ptx::tmem_ld_32x32b_x16(taddr, r);
+        ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < kChunk; ++j)
-          if (c0 + j < m_valid) out[(int64_t)(c0 + j) * p.N] = __uint_as_float(r[j]);  // 32 lanes -> 128 B row segment
+        for (int j = 0; j < kChunk; ++j) {
+          const int tok = m0 + c0 + j;
+          const bool tok_ok = c0 + j < m_valid;
+          const float z = feat_ok ? __uint_as_float(r[j]) * p.inv_temp : -INFINITY;
+          const float m = warp_max(z);
+          const float e = (z == -INFINITY) ? 0.f : __expf(z - m);
+          const float ssum = warp_sum(e);
+          const float usum = warp_sum(e > 0.f ? e * z : 0.f);
+          float key = -INFINITY;
+          if (feat_ok) key = p.greedy ? z : z + gumbel(p.seed, p.step, (uint32_t)tok, (uint32_t)feat);
+          float bkey = key, bz = z;
+          int bidx = feat_ok ? feat : 0x7fffffff;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float k2 = __shfl_xor_sync(0xffffffffu, bkey, o);
+            const float z2 = __shfl_xor_sync(0xffffffffu, bz, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, bidx, o);
+            if (k2 > bkey || (k2 == bkey && i2 < bidx)) { bkey = k2; bz = z2; bidx = i2; }
+          }
+          if (p.targets && tok_ok && feat_ok && p.targets[tok] == (int64_t)feat) p.picked[tok] = z;
+          if (lane == 0) s_hp[q * kNTile + c0 + j] = HeadPart{m, ssum, usum, bkey, bz, bidx};
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      const int et = threadIdx.x - 64;                // 0..127
+      for (int tkn = et; tkn < m_valid; tkn += 128) {
+        HeadPart a = s_hp[tkn];
+#pragma unroll
+        for (int qq = 1; qq < 4; ++qq) {
+          const HeadPart b = s_hp[qq * kNTile + tkn];
+          const float mm = fmaxf(a.m, b.m);
+          const float fa = (a.m == -INFINITY) ? 0.f : __expf(a.m - mm), fb = (b.m == -INFINITY) ? 0.f : __expf(b.m - mm);
+          a.s = a.s * fa + b.s * fb;
+          a.u = a.u * fa + b.u * fb;
+          a.m = mm;
+          if (b.key > a.key || (b.key == a.key && b.idx < a.idx)) { a.key = b.key; a.z = b.z; a.idx = b.idx; }
+        }
+        p.head_part[(int64_t)blockIdx.x * p.M + m0 + tkn] = a;
       }
     }
   }
@@ -252,6 +317,40 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   }
 }
 
+// merge the per-tile head statistics of one token (fixed order -> deterministic)
+__global__ void __launch_bounds__(128) head_combine_kernel(const HeadPart* __restrict__ part, int n_tiles, int64_t M,
+                                                          const float* __restrict__ picked, int has_targets,
+                                                          float* __restrict__ lp_target, float* __restrict__ entropy,
+                                                          float* __restrict__ lse_out, int32_t* __restrict__ ids,
+                                                          float* __restrict__ lp_sampled) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t tok = blockIdx.x;
+  HeadPart a{-INFINITY, 0.f, 0.f, -INFINITY, 0.f, 0x7fffffff};
+  auto merge = [](HeadPart& x, const HeadPart& y) {
+    const float mm = fmaxf(x.m, y.m);
+    const float fx = (x.m == -INFINITY) ? 0.f : __expf(x.m - mm), fy = (y.m == -INFINITY) ? 0.f : __expf(y.m - mm);
+    x.s = x.s * fx + y.s * fy;
+    x.u = x.u * fx + y.u * fy;
+    x.m = mm;
+    if (y.key > x.key || (y.key == x.key && y.idx < x.idx)) { x.key = y.key; x.z = y.z; x.idx = y.idx; }
+  };
+  for (int t = threadIdx.x; t < n_tiles; t += 128) merge(a, part[(int64_t)t * M + tok]);
+  __shared__ HeadPart s_a[128];
+  s_a[threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    HeadPart r = s_a[0];
+    for (int i = 1; i < 128; ++i) merge(r, s_a[i]);
+    const float lse = r.m + logf(r.s);
+    if (lse_out) lse_out[tok] = lse;
+    if (entropy) entropy[tok] = lse - r.u / r.s;
+    if (lp_target && has_targets) lp_target[tok] = picked[tok] - lse;
+    if (ids) ids[tok] = r.idx;
+    if (lp_sampled) lp_sampled[tok] = r.z - lse;
+  }
+}
+
 template <int kNTile>
 int launch_gemm(const CUtensorMap& tw, const CUtensorMap& twl, const CUtensorMap& tx, const GemmParams& p,
                 cudaStream_t stream) {
@@ -259,13 +358,14 @@ int launch_gemm(const CUtensorMap& tw, const CUtensorMap& twl, const CUtensorMap
   const bool lo = p.has_lo != 0;
   const int n_stages = L::stages(lo);
   const int smem = n_stages * L::stage_bytes(lo) + 1024 /*align slack*/ + 8 * (2 * n_stages + 2) + 16;
-  static int configured = 0;
-  if (configured < smem) {
-    PRL_CUDA(cudaFuncSetAttribute(gemm_swapab_kernel<kNTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
+  static int configured[2] = {0, 0};
+  auto kernel = p.head ? gemm_swapab_kernel<kNTile, true> : gemm_swapab_kernel<kNTile, false>;
+  if (configured[p.head ? 1 : 0] < smem) {
+    PRL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[p.head ? 1 : 0] = smem;
   }
   dim3 grid((unsigned)((p.N + kBlockM - 1) / kBlockM), (unsigned)p.split_k, (unsigned)((p.M + kNTile - 1) / kNTile));
-  PRL_CUDA(launch_pdl(gemm_swapab_kernel<kNTile>, grid, dim3(kThreads), (size_t)smem, stream, tw, twl, tx, p, n_stages));
+  PRL_CUDA(launch_pdl(kernel, grid, dim3(kThreads), (size_t)smem, stream, tw, twl, tx, p, n_stages));
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }
@@ -316,7 +416,7 @@ extern "C" int prl_gemm_bf16_splitk(const void* W, const void* W_lo, const void*
   if (split_k <= 0) split_k = prl_gemm_auto_split_k(M, N, K);
   PRL_CHECK_ARG(split_k <= kblocks, "prl_gemm_bf16_splitk: split_k %d > k-blocks %d", split_k, kblocks);
   const int nt = pick_ntile(M);
-  GemmParams p;
+  GemmParams p = {};
   p.M = M; p.N = N; p.K = K; p.kblocks = kblocks; p.split_k = split_k; p.has_lo = W_lo ? 1 : 0; p.partials = partials;
   CUtensorMap tw, twl, tx;
   int rc = make_tmap_2d_bf16(&tw, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, kBlockK, kBlockM);
@@ -333,4 +433,49 @@ extern "C" int prl_gemm_bf16_splitk(const void* W, const void* W_lo, const void*
     case 128: return launch_gemm<128>(tw, twl, tx, p, stream);
     default: return launch_gemm<256>(tw, twl, tx, p, stream);
   }
+}
+
+extern "C" size_t prl_head_workspace_bytes(int64_t M, int64_t V) {
+  const int64_t tiles = (V + kBlockM - 1) / kBlockM;
+  return (size_t)(tiles * M) * sizeof(HeadPart) + (size_t)M * sizeof(float) + 64;
+}
+
+extern "C" int prl_head_logprob(const void* W, const void* W_lo, const void* X, int64_t M, int64_t V, int64_t K,
+                                float temperature, const int64_t* targets, int32_t greedy, uint64_t seed, uint32_t step,
+                                float* logprob_target, float* entropy, float* lse, int32_t* sampled_ids,
+                                float* sampled_logprobs, void* workspace, size_t workspace_bytes,
+                                prl_stream_t stream_) {
+  PRL_CHECK_ARG(W && X && workspace, "prl_head_logprob: NULL argument");
+  PRL_CHECK_ARG(M >= 1 && V >= 1 && K >= 8 && K % 8 == 0, "prl_head_logprob: need M,V >= 1 and K %% 8 == 0");
+  PRL_CHECK_ARG(temperature > 0.f, "prl_head_logprob: temperature must be > 0");
+  PRL_CHECK_ARG(!logprob_target || targets, "prl_head_logprob: logprob_target needs targets");
+  PRL_CHECK_ARG(workspace_bytes >= prl_head_workspace_bytes(M, V), "prl_head_logprob: workspace too small");
+  const int nt = pick_ntile(M);
+  const int64_t tiles = (V + kBlockM - 1) / kBlockM;
+  GemmParams p = {};
+  p.M = M; p.N = V; p.K = K; p.kblocks = (int)((K + kBlockK - 1) / kBlockK); p.split_k = 1; p.has_lo = W_lo ? 1 : 0;
+  p.head = 1; p.inv_temp = 1.f / temperature; p.targets = targets; p.greedy = greedy; p.seed = seed; p.step = step;
+  p.head_part = (HeadPart*)workspace;
+  p.picked = (float*)((char*)workspace + (size_t)(tiles * M) * sizeof(HeadPart));
+  CUtensorMap tw, twl, tx;
+  int rc = make_tmap_2d_bf16(&tw, W, (uint64_t)K, (uint64_t)V, (uint64_t)K * 2, kBlockK, kBlockM);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&twl, W_lo ? W_lo : W, (uint64_t)K, (uint64_t)V, (uint64_t)K * 2, kBlockK, kBlockM);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tx, X, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kBlockK, (uint32_t)nt);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  switch (nt) {
+    case 16: rc = launch_gemm<16>(tw, twl, tx, p, stream); break;
+    case 32: rc = launch_gemm<32>(tw, twl, tx, p, stream); break;
+    case 64: rc = launch_gemm<64>(tw, twl, tx, p, stream); break;
+    case 128: rc = launch_gemm<128>(tw, twl, tx, p, stream); break;
+    default: rc = launch_gemm<256>(tw, twl, tx, p, stream); break;
+  }
+  if (rc) return rc;
+  PRL_CUDA(launch_pdl(head_combine_kernel, dim3((unsigned)M), dim3(128), 0, stream, (const HeadPart*)p.head_part,
+                      (int)tiles, M, (const float*)p.picked, targets ? 1 : 0, logprob_target, entropy, lse, sampled_ids,
+                      sampled_logprobs));
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
 }

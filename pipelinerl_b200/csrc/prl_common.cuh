@@ -135,4 +135,18 @@ __device__ __forceinline__ uint32_t float_to_bf16_bits(float f) {
   return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f));
 }
 
+// counter-based RNG for Gumbel-max sampling: noise depends only on (seed, step, row, vocab id), so the fused
+// head epilogue (gemm_tc.cu) and the stand-alone sampler (decode_ops.cu) draw identical samples
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ float gumbel(uint64_t seed, uint32_t step, uint32_t b, uint32_t v) {
+  uint32_t x = mix32((uint32_t)seed ^ (v * 0x9E3779B9u));
+  x = mix32(x ^ (uint32_t)(seed >> 32) ^ (step * 0x85EBCA6Bu) ^ (b * 0xC2B2AE35u));
+  const float u = ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+  return -__logf(-__logf(u));
+}
+
+
 }  // namespace prl

@@ -51,7 +51,7 @@ class DecodeEngine:
     def __init__(self, cfg: ModelConfig, arena: ParamArena, max_batch: int = 64, max_seq_len: int = 16384,
                  n_pages: int | None = None, max_new_tokens: int = 8192, eos_id: int = -1, seed: int = 42,
                  device: torch.device | str = "cuda:0", use_cuda_graph: bool = True, prefill_chunk: int = 1024,
-                 prefix_sharing: bool = True):
+                 prefix_sharing: bool = True, fused_head: bool = True):
         if cfg.head_dim != 128:
             raise ValueError("the sm_100a attention kernel is built for head_dim 128")
         self.cfg, self.arena = cfg, arena
@@ -67,6 +67,7 @@ class DecodeEngine:
         self.max_new = max_new_tokens
         self.eos_id, self.seed = eos_id, seed
         self.use_graph = use_cuda_graph
+        self.fused_head = fused_head  # lm_head + sampling + logprob capture in one GEMM epilogue (no logits in HBM)
         d, B, H, I = self.dev, self.B, cfg.hidden_size, cfg.intermediate_size
         kv_elems = cfg.num_layers * 2 * self.n_pages * cfg.num_kv_heads * PAGE_SIZE * cfg.head_dim
         self.kv_cache = torch.zeros(kv_elems, dtype=torch.bfloat16, device=d)
@@ -101,6 +102,7 @@ class DecodeEngine:
         self.attn_ws = torch.zeros(int(self.lib.prl_paged_attn_workspace_bytes(B, cfg.num_q_heads, self.attn_splits)),
                                    dtype=torch.uint8, device=d)
         self.sample_ws = torch.zeros(int(self.lib.prl_sample_workspace_bytes(B)), dtype=torch.uint8, device=d)
+        self.head_ws = torch.zeros(int(self.lib.prl_head_workspace_bytes(B, cfg.vocab_size)), dtype=torch.uint8, device=d)
         self.free_pages = list(range(self.n_pages - 1, 0, -1))
         self.free_slots = list(range(B - 1, -1, -1))
         self.slot_req: dict[int, Request] = {}
@@ -188,11 +190,22 @@ class DecodeEngine:
             nxt = f"layers.{l + 1}.input_layernorm.weight" if l + 1 < cfg.num_layers else "norm.weight"
             _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), self.split_k["down"], B, H, a.ptr(nxt), cfg.rms_eps,
                                                 self.h.data_ptr(), self.x.data_ptr(), st))
-        self._gemm("lm_head.weight", self.x, cfg.vocab_size, H, 1, self.logits,
-                   lo="lm_head.weight_lo" if cfg.fp32_head else None)
+        if not self.fused_head:
+            self._gemm("lm_head.weight", self.x, cfg.vocab_size, H, 1, self.logits,
+                       lo="lm_head.weight_lo" if cfg.fp32_head else None)
 
     def _sample_and_advance(self) -> None:
         lib, st = self.lib, _lib.stream_ptr()
+        if self.fused_head:
+            cfg, a = self.cfg, self.arena
+            _lib.check(lib.prl_head_logprob(a.ptr("lm_head.weight"), a.ptr("lm_head.weight_lo") if cfg.fp32_head else None,
+                                            self.x.data_ptr(), self.B, cfg.vocab_size, cfg.hidden_size,
+                                            float(self.temperature), None, int(self.greedy), self.seed, self.step_count,
+                                            None, None, None, self.sampled.data_ptr(), self.sampled_lp.data_ptr(),
+                                            self.head_ws.data_ptr(), self.head_ws.numel(), st))
+            self._state.ignore_eos = int(self.ignore_eos)
+            _lib.check(lib.prl_advance_state(C.byref(self._state), st))
+            return
         _lib.check(lib.prl_sample_logprob(self.logits.data_ptr(), self.B, self.cfg.vocab_size, float(self.temperature),
                                           int(self.greedy), self.seed, self.step_count, self.sampled.data_ptr(),
                                           self.sampled_lp.data_ptr(), self.sample_ws.data_ptr(),

@@ -125,10 +125,10 @@ class WeightReceiver:
         total = ArenaLayout.build(cfg).total
         self.nbytes = total * 2
         self._bufs = [ipc_alloc(self.nbytes), ipc_alloc(self.nbytes)]
-        self._ctrl_buf = ipc_alloc(16)
+        self._ctrl_buf = ipc_alloc(32)
         self.arenas = [ParamArena(cfg, self.dev, data=b.tensor(torch.bfloat16, self.dev)) for b in self._bufs]
-        self.ctrl = self._ctrl_buf.tensor(torch.int64, self.dev)  # [version, arrivals]
-        self._ctrl_host = torch.zeros(2, dtype=torch.int64).pin_memory()
+        self.ctrl = self._ctrl_buf.tensor(torch.int64, self.dev)  # [version, arrivals, acked flips, -]
+        self._ctrl_host = torch.zeros(4, dtype=torch.int64).pin_memory()
         self._poll_stream = torch.cuda.Stream(device=self.dev)
         self._poll_event: torch.cuda.Event | None = None
         self.active = 0
@@ -174,6 +174,9 @@ class WeightReceiver:
         if engine is not None:
             engine.set_arena(self.arenas[self.active])
         self.flips += 1
+        # acknowledge: the learner may now overwrite the buffer this sampler just stopped reading ... but only
+        # after the token step that is possibly still in flight on it has finished (stream order)
+        self.ctrl[2] = self.flips
         self.last_flip_wall_s = time.perf_counter() - t0
         return True
 
@@ -206,18 +209,23 @@ class WeightUpdateManager:
                 assert s.nbytes == nbytes
             else:
                 assert s.nbytes == nbytes, "learner and sampler arenas must share one layout"
-                a0, a1, c = ipc_open(s.arena[0], nbytes), ipc_open(s.arena[1], nbytes), ipc_open(s.ctrl, 16)
+                a0, a1, c = ipc_open(s.arena[0], nbytes), ipc_open(s.arena[1], nbytes), ipc_open(s.ctrl, 32)
                 self._opened += [a0, a1, c]
                 self.peer_bufs.append((a0.ptr, a1.ptr))
                 self.peer_ctrl.append(c.ptr)
         self.n = len(self.peer_bufs)
         self.target = [1] * self.n  # samplers start on buffer 0, so the first update lands in buffer 1
+        self.sent = 0
+        dev = learner_arena.device
+        self._ctrl_views = [_RawCudaBuffer(p, 32, owner=False).tensor(torch.int64, dev) for p in self.peer_ctrl]
         self.offset, self.bytes = push_slice(nbytes, rank, n_learners)
         self.last_push_ms = 0.0
 
-    def send_weight_update(self, version: int, stream: torch.cuda.Stream | None = None, wait: bool = True) -> float:
+    def send_weight_update(self, version: int, stream: torch.cuda.Stream | None = None, wait: bool = True,
+                           ack_timeout_s: float = 120.0) -> float:
         """Push this rank's slice to every sampler's inactive buffer and signal.  Returns device ms of the push."""
         st = stream or torch.cuda.current_stream()
+        self.wait_for_acks(ack_timeout_s)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ms = 0.0
         with torch.cuda.stream(st):
@@ -231,6 +239,7 @@ class WeightUpdateManager:
                 _lib.check(self.lib.prl_weights_signal(ctrl, len(idx), version, int(st.cuda_stream)))
             e1.record()
         self.target = [1 - t for t in self.target]
+        self.sent += 1
         if wait:
             e1.synchronize()
             ms = e0.elapsed_time(e1)
@@ -238,6 +247,20 @@ class WeightUpdateManager:
         if self.update_stream is not None and self.rank == 0:
             self.update_stream.write(WeightUpdateSuccess(version=version, timestamp=time.time()))
         return ms
+
+    def wait_for_acks(self, timeout_s: float = 120.0) -> None:
+        """Update j overwrites the buffer the sampler was reading before its (j-1)-th flip: wait until every
+        sampler has acknowledged j-1 flips (a P2P read of one word per sampler; normally already true because
+        updates are an optimizer step apart)."""
+        need = self.sent  # update j = sent + 1 needs flips 1 .. j-1 acknowledged
+        if need <= 0:
+            return
+        t0 = time.time()
+        for view in self._ctrl_views:
+            while int(view[2].item()) < need:
+                if time.time() - t0 > timeout_s:
+                    raise TimeoutError(f"sampler did not acknowledge weight version flip {need}")
+                time.sleep(0.001)
 
     def close(self) -> None:
         for b in self._opened:

@@ -33,7 +33,7 @@ def test_teacher_forced_logprobs_match_oracle_and_hf(cuda_device, kind):
     cfg = tiny_cfg(kind)
     w = tiny_weights(cfg)
     eng = make_engine(cfg, w, cuda_device, max_batch=4, max_seq_len=256, max_new_tokens=8, use_cuda_graph=False,
-                      prefill_chunk=0)  # prefill-by-decode: every prompt position goes through the decode kernels
+                      prefill_chunk=0, fused_head=False)  # prefill-by-decode; materialised logits are inspected below
     gold = np.load(GOLDEN / f"qwen2_tiny_{kind}_T0.7.npz")
     tokens = gold["tokens"].tolist()
     from pipelinerl_b200.engine import SamplingParams
@@ -54,11 +54,12 @@ def test_teacher_forced_logprobs_match_oracle_and_hf(cuda_device, kind):
     assert err_hf.max() <= 3e-2 and err_hf.mean() <= 6e-3, (err_hf.max(), err_hf.mean())
 
 
-@pytest.mark.parametrize("kind,use_graph", [("gqa2", True), ("gqa7", False)])
-def test_greedy_generation_matches_oracle(cuda_device, kind, use_graph):
+@pytest.mark.parametrize("kind,use_graph,fused", [("gqa2", True, True), ("gqa7", False, True), ("gqa2", True, False)])
+def test_greedy_generation_matches_oracle(cuda_device, kind, use_graph, fused):
     cfg = tiny_cfg(kind)
     w = tiny_weights(cfg)
-    eng = make_engine(cfg, w, cuda_device, max_batch=8, max_seq_len=320, max_new_tokens=40, use_cuda_graph=use_graph)
+    eng = make_engine(cfg, w, cuda_device, max_batch=8, max_seq_len=320, max_new_tokens=40, use_cuda_graph=use_graph,
+                      fused_head=fused)
     from pipelinerl_b200.engine import SamplingParams
     g = torch.Generator().manual_seed(11)
     prompts = [torch.randint(0, cfg.vocab_size, (n,), generator=g).tolist() for n in (5, 64, 65, 130, 1, 17, 200, 33, 90)]

@@ -31,12 +31,37 @@ def test_push_is_byte_exact_and_targets_inactive_buffer(cuda_device):
     # HF-name views of the pushed arena equal the learner's (fused-name mapping q/k/v -> qkv etc.)
     a, b = recv.arena.hf_state_dict(), learner.hf_state_dict()
     assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
-    # the next update goes to buffer 0
+    # the next update goes to buffer 0 (allowed only after the sampler acknowledged the first flip)
+    torch.cuda.synchronize()
+    assert int(recv.ctrl[2].item()) == 1
     learner.data.add_(1)
     for m in mgrs:
         m.send_weight_update(version=6)
     torch.cuda.synchronize()
     assert torch.equal(recv.arenas[0].data, learner.data) and not torch.equal(recv.arenas[1].data, learner.data)
+    recv.close()
+
+
+def test_second_update_waits_for_flip_ack(cuda_device):
+    """Update 2 would overwrite the buffer the sampler is still reading until it has flipped to update 1."""
+    from pipelinerl_b200.model import ParamArena
+    from pipelinerl_b200.weights import WeightReceiver, WeightUpdateManager
+    cfg = tiny_cfg("gqa2")
+    recv = WeightReceiver(cfg, cuda_device, n_pushers=1)
+    learner = ParamArena(cfg, cuda_device).init_random(seed=3)
+    mgr = WeightUpdateManager([recv], learner.data)
+    mgr.send_weight_update(1)
+    with pytest.raises(TimeoutError):
+        mgr.send_weight_update(2, ack_timeout_s=0.2)     # sampler has not flipped yet
+    assert torch.count_nonzero(recv.arenas[0].data) == 0  # live buffer untouched
+    for _ in range(50):
+        if recv.maybe_flip():
+            break
+        torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    mgr.send_weight_update(2, ack_timeout_s=5.0)         # now allowed
+    torch.cuda.synchronize()
+    assert torch.equal(recv.arenas[0].data, learner.data)
     recv.close()
 
 
@@ -76,7 +101,7 @@ def test_in_flight_update_changes_logprobs_without_draining(cuda_device):
     prompt = list(range(10, 30))
     req = eng.add_request(prompt, SamplingParams(max_tokens=16, greedy=True))
     mgr = WeightUpdateManager([recv], learner.data)
-    n_before = len(prompt) - 1 + 6     # prompt feed + 6 generated tokens under weights A
+    n_before = 6     # the prompt is prefilled inside the first step; 6 generated tokens under weights A
     for _ in range(n_before):
         eng.step()
     mgr.send_weight_update(version=1)
