@@ -38,6 +38,10 @@ const char* prl_last_error(void);
 int prl_version(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t prl_launch_count(void);
+/* Tuning switches (A/B measurements): programmatic dependent launch on the token-step kernels (default on,
+ * env PRL_PDL=0 disables) and in-kernel merge of the attention context splits (default off). */
+int prl_set_pdl(int32_t on);
+int prl_attn_set_fused_combine(int32_t on);
 
 /* ======================================================================= *
  * Hot path (2a): policy-gradient loss tail
@@ -188,6 +192,9 @@ int prl_adamw_step(const prl_adamw_args* args, float* grad_norm_out,
 int prl_gemm_auto_split_k(int64_t M, int64_t N, int64_t K);
 /* Tuning knob: shared-memory tile ring per CTA in KB (<= 100 lets two CTAs share an SM). */
 int prl_gemm_set_smem_budget_kb(int32_t kb);
+/* Weight layout switch: 0 = row-major [N,K]; 1 = contiguous 16 KB tiles [N/128][K/64][128][64] (one sequential
+ * TMA box per tile; needs N % 128 == 0, K % 64 == 0). */
+int prl_gemm_set_tiled_weights(int32_t on);
 int prl_gemm_bf16_splitk(const void* W, const void* W_lo /*or NULL*/, const void* X,
                          int64_t M, int64_t N, int64_t K, int32_t split_k /*0 = auto*/,
                          float* partials, prl_stream_t stream);
@@ -220,18 +227,22 @@ int prl_head_logprob(const void* W /*[V,K] bf16*/, const void* W_lo /*or NULL*/,
 int prl_embed_rmsnorm(const int32_t* tokens, const void* embed_bf16, const void* gamma_bf16, float eps,
                       int32_t B, int32_t H, int32_t vocab, float* h /*[B,H] residual, out*/,
                       void* x_bf16 /*[B,H] out*/, prl_stream_t stream);
+/* `l2_prefetch` (nullable) on the three epilogue kernels below: a weight range of an UPCOMING GEMM to pull into
+ * the 126 MB L2 (evict_last) while the long HBM-bound kernel that runs in between hides the DRAM latency. */
 int prl_residual_rmsnorm(const float* partials, int32_t n_split, int32_t B, int32_t H, const void* gamma_bf16,
-                         float eps, float* h /*in/out*/, void* x_bf16 /*out*/, prl_stream_t stream);
+                         float eps, float* h /*in/out*/, void* x_bf16 /*out*/, const void* l2_prefetch,
+                         size_t l2_prefetch_bytes, prl_stream_t stream);
 int prl_qkv_rope_cache(const float* partials, int32_t n_split, int32_t B, const void* bias_bf16 /*or NULL*/,
                        int32_t n_q, int32_t n_kv, int32_t head_dim, const int32_t* positions /*[B]*/,
                        const int32_t* block_table /*[slots,max_blocks]*/, int32_t max_blocks,
                        const int32_t* row_slot /*[B] block-table row of each token row, or NULL = identity*/,
                        const float* inv_freq /*[head_dim/2]*/, void* q_out_bf16 /*[B,n_q,128]*/,
                        void* kv_cache_bf16, int64_t n_pages, int32_t layer, int32_t page_size,
-                       prl_stream_t stream);
+                       const void* l2_prefetch, size_t l2_prefetch_bytes, prl_stream_t stream);
 int prl_silu_mul(const float* partials, int32_t n_split, int32_t B, int32_t I, void* act_bf16 /*[B,I]*/,
-                 prl_stream_t stream);
+                 const void* l2_prefetch, size_t l2_prefetch_bytes, prl_stream_t stream);
 int prl_paged_attn_splits(int32_t B, int32_t n_kv, int32_t max_seq_len);
+/* The workspace must be zero-filled once before its first use (arrival counters; they re-arm themselves). */
 size_t prl_paged_attn_workspace_bytes(int32_t B, int32_t n_q, int32_t n_splits);
 int prl_paged_attn_decode(const void* q_bf16, const void* kv_cache_bf16, int64_t n_pages, int32_t n_layers,
                           int32_t layer, const int32_t* block_table, int32_t max_blocks,

@@ -83,6 +83,8 @@ _SIGNATURES = {
     "prl_last_error": (C.c_char_p, []),
     "prl_version": (C.c_int, []),
     "prl_launch_count": (C.c_uint64, []),
+    "prl_set_pdl": (C.c_int, [C.c_int32]),
+    "prl_attn_set_fused_combine": (C.c_int, [C.c_int32]),
     "prl_pg_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "prl_pg_loss_fwd_bwd": (C.c_int, [C.POINTER(PgBatch), C.POINTER(PgConfig), C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -93,6 +95,7 @@ _SIGNATURES = {
                                        C.c_void_p]),
     "prl_gemm_auto_split_k": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
     "prl_gemm_set_smem_budget_kb": (C.c_int, [C.c_int32]),
+    "prl_gemm_set_tiled_weights": (C.c_int, [C.c_int32]),
     "prl_gemm_bf16_splitk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                        C.c_void_p, C.c_void_p]),
     "prl_head_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
@@ -102,15 +105,16 @@ _SIGNATURES = {
     "prl_embed_rmsnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "prl_residual_rmsnorm": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_float,
-                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "prl_qkv_rope_cache": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                     C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+                                     C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "prl_paged_attn_prefill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                          C.c_void_p, C.c_void_p]),
-    "prl_silu_mul": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "prl_silu_mul": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t,
+                               C.c_void_p]),
     "prl_paged_attn_splits": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     "prl_paged_attn_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "prl_paged_attn_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,

@@ -16,6 +16,18 @@
 namespace prl {
 namespace {
 
+// Software prefetch ACROSS kernels through the 126 MB L2: a small epilogue kernel asks L2 to fetch the weights
+// of an upcoming latency-bound GEMM (qkv / o_proj: 26-33 MB) while the long HBM-bound kernel in between
+// (attention, gate_up, down) runs, so that GEMM then streams from L2 instead of paying DRAM latency cold.
+// Lines are requested evict_last so the evict_first streams of the kernels in between do not displace them.
+__device__ __forceinline__ void l2_prefetch_range(const void* ptr, size_t bytes, size_t tid, size_t nthreads) {
+  if (!ptr) return;
+  const char* base = static_cast<const char*>(ptr);
+  const size_t n_lines = bytes >> 7;
+  for (size_t i = tid; i < n_lines; i += nthreads)
+    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + (i << 7)));
+}
+
 __device__ __forceinline__ float block_sum(float v, float* s_red) {
   v = warp_sum(v);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -65,8 +77,10 @@ constexpr int kMaxSplitUnroll = 8;
 __global__ void __launch_bounds__(1024) residual_rmsnorm_kernel(const float* __restrict__ part, int n_split, int B,
                                                                int H, const __nv_bfloat16* __restrict__ gamma,
                                                                float eps, float* __restrict__ h,
-                                                               __nv_bfloat16* __restrict__ x) {
+                                                               __nv_bfloat16* __restrict__ x, const void* pf_ptr,
+                                                               size_t pf_bytes) {
   pdl_launch_dependents();
+  l2_prefetch_range(pf_ptr, pf_bytes, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
   pdl_wait();
   extern __shared__ float s_row[];  // H floats (only used when a thread owns more than one group)
   __shared__ float s_red[32];
@@ -115,8 +129,11 @@ __global__ void __launch_bounds__(64) qkv_rope_cache_kernel(const float* __restr
                                                            const float* __restrict__ inv_freq_tab,
                                                            __nv_bfloat16* __restrict__ q_out,
                                                            __nv_bfloat16* __restrict__ kv_cache, int64_t n_pages,
-                                                           int layer, int page_size) {
+                                                           int layer, int page_size, const void* pf_ptr,
+                                                           size_t pf_bytes) {
   pdl_launch_dependents();
+  l2_prefetch_range(pf_ptr, pf_bytes, ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x,
+                    (size_t)gridDim.x * gridDim.y * blockDim.x);
   pdl_wait();
   constexpr int D = 128;
   const int b = blockIdx.x, head = blockIdx.y, i = threadIdx.x;  // i in [0, 64)
@@ -165,8 +182,11 @@ __global__ void __launch_bounds__(64) qkv_rope_cache_kernel(const float* __restr
 // ---- split-K reduce + SiLU(gate) * up ------------------------------------------------------
 // part [n_split, B, 2I] (gate columns first, as in the fused gate_up weight) -> act [B, I] bf16; 4 columns/thread
 __global__ void __launch_bounds__(256) silu_mul_kernel(const float* __restrict__ part, int n_split, int B, int I,
-                                                      __nv_bfloat16* __restrict__ act) {
+                                                      __nv_bfloat16* __restrict__ act, const void* pf_ptr,
+                                                      size_t pf_bytes) {
   pdl_launch_dependents();
+  l2_prefetch_range(pf_ptr, pf_bytes, ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x,
+                    (size_t)gridDim.x * gridDim.y * blockDim.x);
   pdl_wait();
   const int b = blockIdx.y;
   const int i4 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -316,7 +336,8 @@ extern "C" int prl_embed_rmsnorm(const int32_t* tokens, const void* embed, const
 }
 
 extern "C" int prl_residual_rmsnorm(const float* partials, int32_t n_split, int32_t B, int32_t H, const void* gamma,
-                                    float eps, float* h, void* x_bf16, prl_stream_t st) {
+                                    float eps, float* h, void* x_bf16, const void* l2_prefetch, size_t l2_prefetch_bytes,
+                                    prl_stream_t st) {
   PRL_CHECK_ARG(partials && gamma && h && x_bf16 && B >= 1 && H >= 4 && n_split >= 0, "prl_residual_rmsnorm: bad argument");
   PRL_CHECK_ARG(H % 4 == 0, "prl_residual_rmsnorm: hidden size must be a multiple of 4 (got %d)", H);
   PRL_CHECK_ARG(H * 4 <= 96 * 1024, "prl_residual_rmsnorm: hidden size too large for the row buffer");
@@ -329,7 +350,8 @@ extern "C" int prl_residual_rmsnorm(const float* partials, int32_t n_split, int3
   if (threads > 1024) threads = 1024;
   const size_t smem = (H / 4 > threads) ? (size_t)H * 4 : 0;
   PRL_CUDA(launch_pdl(residual_rmsnorm_kernel, dim3(B), dim3(threads), smem, (cudaStream_t)st, partials, (int)n_split,
-                      (int)B, (int)H, (const __nv_bfloat16*)gamma, eps, h, (__nv_bfloat16*)x_bf16));
+                      (int)B, (int)H, (const __nv_bfloat16*)gamma, eps, h, (__nv_bfloat16*)x_bf16, l2_prefetch,
+                      l2_prefetch_bytes));
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }
@@ -339,25 +361,26 @@ extern "C" int prl_qkv_rope_cache(const float* partials, int32_t n_split, int32_
                                   const int32_t* block_table, int32_t max_blocks, const int32_t* row_slot,
                                   const float* inv_freq, void* q_out,
                                   void* kv_cache, int64_t n_pages, int32_t layer, int32_t page_size,
-                                  prl_stream_t st) {
+                                  const void* l2_prefetch, size_t l2_prefetch_bytes, prl_stream_t st) {
   PRL_CHECK_ARG(partials && positions && block_table && q_out && kv_cache && inv_freq, "prl_qkv_rope_cache: NULL argument");
   PRL_CHECK_ARG(head_dim == 128, "prl_qkv_rope_cache: head_dim must be 128 (got %d)", head_dim);
   PRL_CHECK_ARG(B >= 1 && n_q >= 1 && n_kv >= 1 && page_size >= 1 && max_blocks >= 1, "prl_qkv_rope_cache: bad shape");
   dim3 grid((unsigned)B, (unsigned)(n_q + 2 * n_kv));
   PRL_CUDA(launch_pdl(qkv_rope_cache_kernel, grid, dim3(64), 0, (cudaStream_t)st, partials, (int)n_split, (int)B,
                       (const __nv_bfloat16*)bias, (int)n_q, (int)n_kv, positions, block_table, (int)max_blocks, row_slot,
-                      inv_freq, (__nv_bfloat16*)q_out, (__nv_bfloat16*)kv_cache, n_pages, (int)layer, (int)page_size));
+                      inv_freq, (__nv_bfloat16*)q_out, (__nv_bfloat16*)kv_cache, n_pages, (int)layer, (int)page_size,
+                      l2_prefetch, l2_prefetch_bytes));
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }
 
 extern "C" int prl_silu_mul(const float* partials, int32_t n_split, int32_t B, int32_t I, void* act_bf16,
-                            prl_stream_t st) {
+                            const void* l2_prefetch, size_t l2_prefetch_bytes, prl_stream_t st) {
   PRL_CHECK_ARG(partials && act_bf16 && B >= 1 && I >= 4 && n_split >= 1, "prl_silu_mul: bad argument");
   PRL_CHECK_ARG(I % 4 == 0, "prl_silu_mul: intermediate size must be a multiple of 4 (got %d)", I);
   dim3 grid((unsigned)((I / 4 + 255) / 256), (unsigned)B);
   PRL_CUDA(launch_pdl(silu_mul_kernel, grid, dim3(256), 0, (cudaStream_t)st, partials, (int)n_split, (int)B, (int)I,
-                      (__nv_bfloat16*)act_bf16));
+                      (__nv_bfloat16*)act_bf16, l2_prefetch, l2_prefetch_bytes));
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }

@@ -79,7 +79,8 @@ constexpr int kBlockM = 128;  // output features per CTA (UMMA M)
 constexpr int kBlockK = 64;   // bf16 elements per stage row = 128 B = one swizzle atom
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 192;
-static int g_smem_budget = 100 * 1024;  // per-CTA tile ring; <= 100 KB lets two CTAs share an SM
+static int g_smem_budget = 100 * 1024;
+static int g_tiled_weights = 0;  // weights stored as contiguous [N/128][K/64][128][64] tiles  // per-CTA tile ring; <= 100 KB lets two CTAs share an SM
 
 struct HeadPart { float m, s, u, key, z; int idx; };  // per (vocab tile, token): online-softmax state + best sample
 
@@ -90,6 +91,7 @@ struct GemmParams {
   int has_lo;
   float* partials;    // [split_k, M, N]
   // fused head epilogue (logits never reach HBM): temperature, teacher-forcing targets, sampling
+  int tiled;          // weight tile (n_tile, kb) is the contiguous 16 KB block number n_tile*kblocks + kb
   int head;
   float inv_temp;
   const int64_t* targets;   // [M] or NULL
@@ -171,8 +173,10 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
         ptx::mbar_arrive_expect_tx(full_bar(i), tx);
         const uint32_t a_dst = smem_base + (uint32_t)(i * stage_bytes);
         const int kcoord = (kb_begin + i) * kBlockK;
-        ptx::tma_load_2d(a_dst, &tm_w, kcoord, n0, full_bar(i), ptx::kEvictFirst);
-        if (lo) ptx::tma_load_2d(a_dst + L::kABytes, &tm_wlo, kcoord, n0, full_bar(i), ptx::kEvictFirst);
+        const int wc0 = p.tiled ? 0 : kcoord;
+        const int wc1 = p.tiled ? (blockIdx.x * p.kblocks + kb_begin + i) * kBlockM : n0;
+        ptx::tma_load_2d(a_dst, &tm_w, wc0, wc1, full_bar(i), ptx::kEvictFirst);
+        if (lo) ptx::tma_load_2d(a_dst + L::kABytes, &tm_wlo, wc0, wc1, full_bar(i), ptx::kEvictFirst);
       }
       pdl_wait();
       for (int i = 0; i < pre; ++i) {
@@ -186,10 +190,12 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
         ptx::mbar_arrive_expect_tx(full_bar(s), tx);
         const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes);
         const int kcoord = (kb_begin + i) * kBlockK;
-        ptx::tma_load_2d(a_dst, &tm_w, kcoord, n0, full_bar(s), ptx::kEvictFirst);
+        const int wc0 = p.tiled ? 0 : kcoord;
+        const int wc1 = p.tiled ? (blockIdx.x * p.kblocks + kb_begin + i) * kBlockM : n0;
+        ptx::tma_load_2d(a_dst, &tm_w, wc0, wc1, full_bar(s), ptx::kEvictFirst);
         uint32_t b_dst = a_dst + L::kABytes;
         if (lo) {
-          ptx::tma_load_2d(a_dst + L::kABytes, &tm_wlo, kcoord, n0, full_bar(s), ptx::kEvictFirst);
+          ptx::tma_load_2d(a_dst + L::kABytes, &tm_wlo, wc0, wc1, full_bar(s), ptx::kEvictFirst);
           b_dst += L::kABytes;
         }
         ptx::tma_load_2d(b_dst, &tm_x, kcoord, m0, full_bar(s), ptx::kEvictLast);
@@ -370,6 +376,18 @@ int launch_gemm(const CUtensorMap& tw, const CUtensorMap& twl, const CUtensorMap
   return PRL_OK;
 }
 
+// Weight tensor map.  Row-major: [N rows, K cols].  Tiled: the same bytes seen as [(N/128)*(K/64)*128 rows, 64 cols]
+// — tile (n_tile, kb) is one contiguous 16 KB block, fetched by a single sequential TMA box.
+int make_weight_tmap(CUtensorMap* out, const void* W, int64_t N, int64_t K, int tiled) {
+  if (!tiled) return make_tmap_2d_bf16(out, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, kBlockK, kBlockM);
+  if (N % kBlockM != 0 || K % kBlockK != 0) {
+    set_error("tiled weights need N %% 128 == 0 and K %% 64 == 0 (N=%lld K=%lld)", (long long)N, (long long)K);
+    return PRL_ERR_INVALID;
+  }
+  return make_tmap_2d_bf16(out, W, kBlockK, (uint64_t)(N / kBlockM) * (uint64_t)(K / kBlockK) * kBlockM, kBlockK * 2,
+                           kBlockK, kBlockM);
+}
+
 int pick_ntile(int64_t M) {
   if (M <= 16) return 16;
   if (M <= 32) return 32;
@@ -386,6 +404,11 @@ using namespace prl;
 extern "C" int prl_gemm_set_smem_budget_kb(int32_t kb) {
   PRL_CHECK_ARG(kb >= 48 && kb <= 220, "prl_gemm_set_smem_budget_kb: 48..220 KB");
   g_smem_budget = kb * 1024;
+  return PRL_OK;
+}
+
+extern "C" int prl_gemm_set_tiled_weights(int32_t on) {
+  g_tiled_weights = on ? 1 : 0;
   return PRL_OK;
 }
 
@@ -418,10 +441,11 @@ extern "C" int prl_gemm_bf16_splitk(const void* W, const void* W_lo, const void*
   const int nt = pick_ntile(M);
   GemmParams p = {};
   p.M = M; p.N = N; p.K = K; p.kblocks = kblocks; p.split_k = split_k; p.has_lo = W_lo ? 1 : 0; p.partials = partials;
+  p.tiled = g_tiled_weights;
   CUtensorMap tw, twl, tx;
-  int rc = make_tmap_2d_bf16(&tw, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, kBlockK, kBlockM);
+  int rc = make_weight_tmap(&tw, W, N, K, p.tiled);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&twl, W_lo ? W_lo : W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, kBlockK, kBlockM);
+  rc = make_weight_tmap(&twl, W_lo ? W_lo : W, N, K, p.tiled);
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tx, X, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kBlockK, (uint32_t)nt);
   if (rc) return rc;
@@ -457,10 +481,11 @@ extern "C" int prl_head_logprob(const void* W, const void* W_lo, const void* X, 
   p.head = 1; p.inv_temp = 1.f / temperature; p.targets = targets; p.greedy = greedy; p.seed = seed; p.step = step;
   p.head_part = (HeadPart*)workspace;
   p.picked = (float*)((char*)workspace + (size_t)(tiles * M) * sizeof(HeadPart));
+  p.tiled = g_tiled_weights;
   CUtensorMap tw, twl, tx;
-  int rc = make_tmap_2d_bf16(&tw, W, (uint64_t)K, (uint64_t)V, (uint64_t)K * 2, kBlockK, kBlockM);
+  int rc = make_weight_tmap(&tw, W, V, K, p.tiled);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&twl, W_lo ? W_lo : W, (uint64_t)K, (uint64_t)V, (uint64_t)K * 2, kBlockK, kBlockM);
+  rc = make_weight_tmap(&twl, W_lo ? W_lo : W, V, K, p.tiled);
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tx, X, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kBlockK, (uint32_t)nt);
   if (rc) return rc;

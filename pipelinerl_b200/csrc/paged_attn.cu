@@ -13,7 +13,9 @@
 //     mma.sync m16n8k16 (the work is ~7 FLOP per KV byte, far below any tensor roof:
 //     tensor cores are used for issue efficiency, not throughput), online softmax in
 //     fp32 (exp2 domain), ldmatrix with the matching XOR swizzle (conflict-free);
-//   * per-split (m, l, O) partials are merged by a small combine kernel.
+//   * per-split (m, l, O) partials are merged either by a small combine kernel (default) or by whichever split
+//     CTA of the (sequence, kv head) finishes last (arrival ticket; prl_attn_set_fused_combine) — A/B measured in
+//     profiles/r1_ablation*.jsonl.
 // KV cache layout (bf16): row = (((layer*2 + kv) * n_pages + page) * n_kv + kvh) * 64 + slot,
 // 128 contiguous d per row — written by qkv_rope_cache_kernel (decode_ops.cu).
 #include "prl_common.cuh"
@@ -41,6 +43,8 @@ struct AttnParams {
   float scale_log2;
   float* o_part;               // [B, n_q, n_splits, 128]
   float* ml_part;              // [B, n_q, n_splits, 2]
+  unsigned int* tickets;       // [B, n_kv] arrival counters (zero on entry, self-resetting); NULL = separate combine kernel
+  __nv_bfloat16* out;          // [B, n_q*128]
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -89,6 +93,33 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap tm_kv, AttnParams p
   const int n_it = p_end > p_begin ? p_end - p_begin : 0;
   const int R = p.R;
 
+  // last-arriving split of a (sequence, kv head) merges all splits and writes the bf16 output: no combine launch
+  auto finish = [&]() {
+    if (p.tickets == nullptr) return;   // the stand-alone combine kernel merges the splits
+    __shared__ unsigned int s_ticket;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&p.tickets[b * p.n_kv + kvh], 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)(p.n_splits - 1)) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < R * kD; i += kThreads) {
+      const int r = i / kD, d = i % kD;
+      const int64_t head = (int64_t)b * p.n_q + kvh * R + r;
+      float M = -INFINITY;
+      for (int sp = 0; sp < p.n_splits; ++sp) M = fmaxf(M, __ldcg(&p.ml_part[(head * p.n_splits + sp) * 2]));
+      float L = 0.f, O = 0.f;
+      for (int sp = 0; sp < p.n_splits; ++sp) {
+        const float ms = __ldcg(&p.ml_part[(head * p.n_splits + sp) * 2]);
+        const float f = (ms == -INFINITY) ? 0.f : fast_exp2(ms - M);
+        L += __ldcg(&p.ml_part[(head * p.n_splits + sp) * 2 + 1]) * f;
+        O += __ldcg(&p.o_part[(head * p.n_splits + sp) * kD + d]) * f;
+      }
+      p.out[head * kD + d] = __float2bfloat16_rn(L > 0.f ? O / L : 0.f);
+    }
+    if (threadIdx.x == 0) p.tickets[b * p.n_kv + kvh] = 0u;  // re-arm for the next launch
+  };
+
   if (n_it == 0) {  // empty split (short sequence): neutral partial
     for (int i = threadIdx.x; i < R * kD; i += kThreads) {
       const int r = i / kD, d = i % kD;
@@ -99,6 +130,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap tm_kv, AttnParams p
         p.ml_part[(head * p.n_splits + split) * 2 + 1] = 0.f;
       }
     }
+    finish();
     return;
   }
 
@@ -268,6 +300,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap tm_kv, AttnParams p
       p.ml_part[(head * p.n_splits + split) * 2 + 1] = L;
     }
   }
+  finish();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -466,7 +499,7 @@ paged_attn_prefill_kernel(const __grid_constant__ CUtensorMap tm_kv, PrefillPara
   }
 }
 
-// merge the context splits: out[b, head, :] = sum_s O_s 2^(m_s - M) / sum_s l_s 2^(m_s - M)
+// stand-alone merge of the context splits (alternative to the in-kernel ticket merge; chosen at run time)
 __global__ void __launch_bounds__(kD) attn_combine_kernel(const float* __restrict__ o_part,
                                                          const float* __restrict__ ml_part, int n_splits,
                                                          __nv_bfloat16* __restrict__ out) {
@@ -486,10 +519,17 @@ __global__ void __launch_bounds__(kD) attn_combine_kernel(const float* __restric
   out[head * kD + d] = __float2bfloat16_rn(L > 0.f ? O / L : 0.f);
 }
 
+static int g_fused_combine = 0;
+
 }  // namespace
 }  // namespace prl
 
 using namespace prl;
+
+extern "C" int prl_attn_set_fused_combine(int32_t on) {
+  g_fused_combine = on ? 1 : 0;
+  return PRL_OK;
+}
 
 extern "C" int prl_paged_attn_splits(int32_t B, int32_t n_kv, int32_t max_seq_len) {
   const int pages = (max_seq_len + kPage - 1) / kPage;
@@ -502,7 +542,8 @@ extern "C" int prl_paged_attn_splits(int32_t B, int32_t n_kv, int32_t max_seq_le
 }
 
 extern "C" size_t prl_paged_attn_workspace_bytes(int32_t B, int32_t n_q, int32_t n_splits) {
-  return (size_t)B * n_q * n_splits * (kD + 2) * sizeof(float);
+  // partial O, (m, l) per split + one arrival counter per (sequence, kv head) (<= n_q of them)
+  return (size_t)B * n_q * n_splits * (kD + 2) * sizeof(float) + (size_t)B * n_q * sizeof(unsigned int);
 }
 
 extern "C" int prl_paged_attn_decode(const void* q, const void* kv_cache, int64_t n_pages, int32_t n_layers,
@@ -532,6 +573,8 @@ extern "C" int prl_paged_attn_decode(const void* q, const void* kv_cache, int64_
   p.scale_log2 = sm_scale * 1.4426950408889634f;
   p.o_part = (float*)workspace;
   p.ml_part = p.o_part + (size_t)B * n_q * n_splits * kD;
+  p.tickets = g_fused_combine ? reinterpret_cast<unsigned int*>(p.ml_part + (size_t)B * n_q * n_splits * 2) : nullptr;
+  p.out = (__nv_bfloat16*)out_bf16;
   const int smem = kStages * kStageBytes + 1024 + 8 * 2 * kStages + 4 * kMaxPagesPerSplit + 16;
   static bool configured = false;
   if (!configured) {
@@ -542,9 +585,11 @@ extern "C" int prl_paged_attn_decode(const void* q, const void* kv_cache, int64_
   dim3 grid((unsigned)n_splits, (unsigned)n_kv, (unsigned)B);
   PRL_CUDA(launch_pdl(paged_attn_decode_kernel, grid, dim3(kThreads), (size_t)smem, stream, tm, p));
   PRL_LAUNCH_CHECK();
-  PRL_CUDA(launch_pdl(attn_combine_kernel, dim3((unsigned)(B * n_q)), dim3(kD), 0, stream, (const float*)p.o_part,
-                      (const float*)p.ml_part, (int)n_splits, (__nv_bfloat16*)out_bf16));
-  PRL_LAUNCH_CHECK();
+  if (!g_fused_combine) {
+    PRL_CUDA(launch_pdl(attn_combine_kernel, dim3((unsigned)(B * n_q)), dim3(kD), 0, stream, (const float*)p.o_part,
+                        (const float*)p.ml_part, (int)n_splits, (__nv_bfloat16*)out_bf16));
+    PRL_LAUNCH_CHECK();
+  }
   return PRL_OK;
 }
 

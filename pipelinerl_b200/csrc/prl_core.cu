@@ -18,13 +18,13 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+static int g_pdl = -1;
 bool use_pdl() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_pdl < 0) {
     const char* e = getenv("PRL_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
   }
-  return v == 1;
+  return g_pdl == 1;
 }
 
 int num_sms() {
@@ -42,6 +42,7 @@ int num_sms() {
 }  // namespace prl
 
 extern "C" {
+int prl_set_pdl(int32_t on) { prl::g_pdl = on ? 1 : 0; return PRL_OK; }
 const char* prl_last_error(void) { return prl::g_err; }
 int prl_version(void) { return 100; }
 uint64_t prl_launch_count(void) { return prl::g_launches.load(std::memory_order_relaxed); }

@@ -44,14 +44,15 @@ class Request:
     output_logprobs: list[float] = field(default_factory=list)
     finish_reason: str | None = None
     model_version: int = 0
-    prefix_key: int | None = None
+    prefilled: int = 0                                   # prompt tokens whose KV is in the cache
+    waits_for: list = field(default_factory=list)        # [(request filling a shared page, tokens it must reach)]
 
 
 class DecodeEngine:
     def __init__(self, cfg: ModelConfig, arena: ParamArena, max_batch: int = 64, max_seq_len: int = 16384,
                  n_pages: int | None = None, max_new_tokens: int = 8192, eos_id: int = -1, seed: int = 42,
                  device: torch.device | str = "cuda:0", use_cuda_graph: bool = True, prefill_chunk: int = 1024,
-                 prefix_sharing: bool = True, fused_head: bool = True):
+                 prefix_sharing: bool = True, fused_head: bool = False):
         if cfg.head_dim != 128:
             raise ValueError("the sm_100a attention kernel is built for head_dim 128")
         self.cfg, self.arena = cfg, arena
@@ -67,7 +68,14 @@ class DecodeEngine:
         self.max_new = max_new_tokens
         self.eos_id, self.seed = eos_id, seed
         self.use_graph = use_cuda_graph
-        self.fused_head = fused_head  # lm_head + sampling + logprob capture in one GEMM epilogue (no logits in HBM)
+        # fused_head: lm_head + sampling + logprob capture in one GEMM epilogue (no logits in HBM).  For the 64-row
+        # decode step the logits round trip is only 78 MB and the fused epilogue cannot live in the step's CUDA graph
+        # (its RNG arguments change per step), so the unfused path measured 1.5 % faster (profiles/r1_ablation_b.jsonl);
+        # the fused kernel is what scoring / the trainer's forward use, where the logits would be 608 KB per token.
+        self.fused_head = fused_head
+        self.l2_prefetch_bytes = 0          # cross-kernel L2 prefetch budget per site; measured to HURT (+0.19 ms/step,
+                                            # profiles/r1_ablation.jsonl: HBM is already saturated), so off
+        self._skip: set[str] = set()        # timing ablations only (tools/step_ablation.py)
         d, B, H, I = self.dev, self.B, cfg.hidden_size, cfg.intermediate_size
         kv_elems = cfg.num_layers * 2 * self.n_pages * cfg.num_kv_heads * PAGE_SIZE * cfg.head_dim
         self.kv_cache = torch.zeros(kv_elems, dtype=torch.bfloat16, device=d)
@@ -116,8 +124,10 @@ class DecodeEngine:
         self.prefix_sharing = prefix_sharing
         self.page_ref = [0] * self.n_pages
         self._prefill_queue: list[Request] = []
-        self._prefix_cache: dict[int, dict] = {}      # hash(prompt prefix) -> entry
-        self._pending_share: list[tuple[Request, dict]] = []
+        from collections import OrderedDict
+        self._page_of_hash: "OrderedDict[int, int]" = OrderedDict()   # chained hash of a full 64-token page -> page id (LRU)
+        self._hash_of_page: dict[int, int] = {}
+        self._page_pending: dict[int, tuple[Request, int]] = {}       # page -> (request that fills it, tokens needed)
         self._pf = None                                # lazily allocated prefill buffers
         self.stats = {"prefill_tokens": 0, "prefix_hits": 0, "prefix_hit_tokens": 0}
         self._next_id = 0
@@ -160,36 +170,59 @@ class DecodeEngine:
         st = self._st
         H, I = cfg.hidden_size, cfg.intermediate_size
         part = self.partials
+        skip = self._skip
+        pf = self.l2_prefetch_bytes  # cross-kernel L2 prefetch budget per site (0 disables)
+
+        def wbytes(name):  # whole weight tensor, capped by the budget
+            shape = a.layout.shapes[name]
+            return min(pf, shape[0] * shape[1] * 2) if pf else 0
         _lib.check(lib.prl_embed_rmsnorm(self.tokens.data_ptr(), a.ptr("embed_tokens.weight"),
                                          a.ptr("layers.0.input_layernorm.weight"), cfg.rms_eps, B, H, cfg.vocab_size,
                                          self.h.data_ptr(), self.x.data_ptr(), st))
         sm_scale = 1.0 / math.sqrt(cfg.head_dim)
         for l in range(cfg.num_layers):
             p = f"layers.{l}."
-            self._gemm(p + "qkv_proj.weight", self.x, cfg.qkv_size, H, self.split_k["qkv"], part)
-            _lib.check(lib.prl_qkv_rope_cache(part.data_ptr(), self.split_k["qkv"], B,
-                                              a.ptr(p + "qkv_proj.bias") if cfg.qkv_bias else None, cfg.num_q_heads,
-                                              cfg.num_kv_heads, cfg.head_dim, self.positions.data_ptr(),
-                                              self.block_table.data_ptr(), self.max_blocks, None,
-                                              self.inv_freq.data_ptr(),
-                                              self.q.data_ptr(), self.kv_cache.data_ptr(), self.n_pages, l, PAGE_SIZE,
-                                              st))
-            _lib.check(lib.prl_paged_attn_decode(self.q.data_ptr(), self.kv_cache.data_ptr(), self.n_pages,
-                                                 cfg.num_layers, l, self.block_table.data_ptr(), self.max_blocks,
-                                                 self.seq_lens.data_ptr(), B, cfg.num_q_heads, cfg.num_kv_heads,
-                                                 cfg.head_dim, PAGE_SIZE, self.attn_splits, sm_scale,
-                                                 self.attn_out.data_ptr(), self.attn_ws.data_ptr(),
-                                                 self.attn_ws.numel(), st))
-            self._gemm(p + "o_proj.weight", self.attn_out, H, cfg.q_size, self.split_k["o"], part)
-            _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), self.split_k["o"], B, H,
-                                                a.ptr(p + "post_attention_layernorm.weight"), cfg.rms_eps,
-                                                self.h.data_ptr(), self.x.data_ptr(), st))
-            self._gemm(p + "gate_up_proj.weight", self.x, 2 * I, H, self.split_k["gate_up"], part)
-            _lib.check(lib.prl_silu_mul(part.data_ptr(), self.split_k["gate_up"], B, I, self.act.data_ptr(), st))
-            self._gemm(p + "down_proj.weight", self.act, H, I, self.split_k["down"], part)
+            if "gemm" not in skip:
+                self._gemm(p + "qkv_proj.weight", self.x, cfg.qkv_size, H, self.split_k["qkv"], part)
+            if "small" not in skip:
+                # while attention streams the KV cache, L2 fetches o_proj's weights
+                _lib.check(lib.prl_qkv_rope_cache(part.data_ptr(), self.split_k["qkv"], B,
+                                                  a.ptr(p + "qkv_proj.bias") if cfg.qkv_bias else None, cfg.num_q_heads,
+                                                  cfg.num_kv_heads, cfg.head_dim, self.positions.data_ptr(),
+                                                  self.block_table.data_ptr(), self.max_blocks, None,
+                                                  self.inv_freq.data_ptr(), self.q.data_ptr(), self.kv_cache.data_ptr(),
+                                                  self.n_pages, l, PAGE_SIZE,
+                                                  a.ptr(p + "o_proj.weight") if pf else None, wbytes(p + "o_proj.weight"), st))
+            if "attn" not in skip:
+                _lib.check(lib.prl_paged_attn_decode(self.q.data_ptr(), self.kv_cache.data_ptr(), self.n_pages,
+                                                     cfg.num_layers, l, self.block_table.data_ptr(), self.max_blocks,
+                                                     self.seq_lens.data_ptr(), B, cfg.num_q_heads, cfg.num_kv_heads,
+                                                     cfg.head_dim, PAGE_SIZE, self.attn_splits, sm_scale,
+                                                     self.attn_out.data_ptr(), self.attn_ws.data_ptr(),
+                                                     self.attn_ws.numel(), st))
+            if "gemm" not in skip:
+                self._gemm(p + "o_proj.weight", self.attn_out, H, cfg.q_size, self.split_k["o"], part)
+            if "small" not in skip:
+                # while gate_up streams, L2 fetches the head of down_proj
+                _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), self.split_k["o"], B, H,
+                                                    a.ptr(p + "post_attention_layernorm.weight"), cfg.rms_eps,
+                                                    self.h.data_ptr(), self.x.data_ptr(),
+                                                    a.ptr(p + "down_proj.weight") if pf else None,
+                                                    wbytes(p + "down_proj.weight"), st))
+            if "gemm" not in skip:
+                self._gemm(p + "gate_up_proj.weight", self.x, 2 * I, H, self.split_k["gate_up"], part)
+            nxt_qkv = f"layers.{l + 1}.qkv_proj.weight" if l + 1 < cfg.num_layers else None
+            if "small" not in skip:
+                # while down streams, L2 fetches the next layer's qkv_proj
+                _lib.check(lib.prl_silu_mul(part.data_ptr(), self.split_k["gate_up"], B, I, self.act.data_ptr(),
+                                            a.ptr(nxt_qkv) if (pf and nxt_qkv) else None,
+                                            wbytes(nxt_qkv) if nxt_qkv else 0, st))
+            if "gemm" not in skip:
+                self._gemm(p + "down_proj.weight", self.act, H, I, self.split_k["down"], part)
             nxt = f"layers.{l + 1}.input_layernorm.weight" if l + 1 < cfg.num_layers else "norm.weight"
-            _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), self.split_k["down"], B, H, a.ptr(nxt), cfg.rms_eps,
-                                                self.h.data_ptr(), self.x.data_ptr(), st))
+            if "small" not in skip:
+                _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), self.split_k["down"], B, H, a.ptr(nxt), cfg.rms_eps,
+                                                    self.h.data_ptr(), self.x.data_ptr(), None, 0, st))
         if not self.fused_head:
             self._gemm("lm_head.weight", self.x, cfg.vocab_size, H, 1, self.logits,
                        lo="lm_head.weight_lo" if cfg.fp32_head else None)
@@ -216,7 +249,7 @@ class DecodeEngine:
     def step(self) -> None:
         """One token for every active slot.  The model part is replayed from a CUDA graph; sampling and
         state advance are launched per step (they take the step counter as an RNG argument)."""
-        if self._prefill_queue or self._pending_share:
+        if self._prefill_queue:
             self.run_prefill()
         if self.use_graph:
             key = self.arena.data.data_ptr()
@@ -288,7 +321,7 @@ class DecodeEngine:
                                               cfg.num_q_heads, cfg.num_kv_heads, cfg.head_dim, pf["pos"].data_ptr(),
                                               self.block_table.data_ptr(), self.max_blocks, pf["slot"].data_ptr(),
                                               self.inv_freq.data_ptr(), pf["q"].data_ptr(), self.kv_cache.data_ptr(),
-                                              self.n_pages, l, PAGE_SIZE, st))
+                                              self.n_pages, l, PAGE_SIZE, None, 0, st))
             seq = pf["seq"]
             _lib.check(lib.prl_paged_attn_prefill(pf["q"].data_ptr(), self.kv_cache.data_ptr(), self.n_pages,
                                                   cfg.num_layers, l, self.block_table.data_ptr(), self.max_blocks,
@@ -297,48 +330,51 @@ class DecodeEngine:
                                                   cfg.head_dim, PAGE_SIZE, sm_scale, pf["attn"].data_ptr(), st))
             self._gemm(p + "o_proj.weight", pf["attn"], H, cfg.q_size, 1, part, m=n)
             _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), 1, n, H, a.ptr(p + "post_attention_layernorm.weight"),
-                                                cfg.rms_eps, h.data_ptr(), x.data_ptr(), st))
+                                                cfg.rms_eps, h.data_ptr(), x.data_ptr(), None, 0, st))
             self._gemm(p + "gate_up_proj.weight", x, 2 * I, H, 1, part, m=n)
-            _lib.check(lib.prl_silu_mul(part.data_ptr(), 1, n, I, pf["act"].data_ptr(), st))
+            _lib.check(lib.prl_silu_mul(part.data_ptr(), 1, n, I, pf["act"].data_ptr(), None, 0, st))
             self._gemm(p + "down_proj.weight", pf["act"], H, I, 1, part, m=n)
             nxt = f"layers.{l + 1}.input_layernorm.weight" if l + 1 < cfg.num_layers else "norm.weight"
             _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), 1, n, H, a.ptr(nxt), cfg.rms_eps, h.data_ptr(),
-                                                x.data_ptr(), st))
+                                                x.data_ptr(), None, 0, st))
         self.stats["prefill_tokens"] += n
 
     def run_prefill(self) -> int:
-        """Prefill the first P-1 prompt tokens of every queued request in packed chunks of <= prefill_chunk rows
-        (the last prompt token goes through the decode step, which yields the first sample), then attach the
-        requests that were waiting to share one of those prefixes.  Returns the number of prefilled tokens."""
+        """Prefill the not-yet-cached prompt tokens [start, P-1) of every queued request in packed chunks of
+        <= prefill_chunk rows (the last prompt token goes through the decode step, which yields the first
+        sample).  A request that shares prefix pages another queued request is still filling waits for them."""
         done = 0
-        work = [[r, 0] for r in self._prefill_queue]   # [request, next prompt index]
+        work = list(self._prefill_queue)
         self._prefill_queue = []
         C = self.prefill_chunk
         while work:
             segs, room = [], C
-            for item in work:
-                r, at = item
-                k = min(room, len(r.prompt_ids) - 1 - at)
-                if k <= 0:
-                    continue
-                segs.append((r, at, k))
-                item[1] += k
-                room -= k
+            progress_at_launch = {id(r): r.prefilled for r in work}
+            for r in work:
                 if room == 0:
                     break
-            work = [it for it in work if it[1] < len(it[0].prompt_ids) - 1]
-            if segs:
-                self._prefill_rows(segs)
-                done += sum(k for _, _, k in segs)
-        for req, entry in self._pending_share:
-            self._attach_shared(req, entry)
-        self._pending_share = []
+                if any(progress_at_launch.get(id(o), o.prefilled) < need for o, need in r.waits_for):
+                    continue
+                k = min(room, len(r.prompt_ids) - 1 - r.prefilled)
+                if k <= 0:
+                    continue
+                segs.append((r, r.prefilled, k))
+                room -= k
+            if not segs:
+                raise RuntimeError("prefill scheduling deadlock (prefix dependency cycle)")
+            self._prefill_rows(segs)
+            for r, at, k in segs:
+                r.prefilled = at + k
+            done += sum(k for _, _, k in segs)
+            work = [r for r in work if r.prefilled < len(r.prompt_ids) - 1]
+        self._page_pending = {pg: (r, need) for pg, (r, need) in self._page_pending.items() if r.prefilled < need}
         return done
 
-    # ---- pages and prefix sharing -----------------------------------------------------------------
+    # ---- pages and prefix sharing (page-granular, chained hashes: GRPO attempts AND later turns of a
+    #      conversation reuse every full 64-token page of their common prefix) ------------------------------
     def _alloc_pages(self, n: int) -> list[int]:
         if len(self.free_pages) < n:
-            self._evict_prefixes(n - len(self.free_pages))
+            self._evict_cached_pages(n - len(self.free_pages))
         if len(self.free_pages) < n:
             raise RuntimeError("engine out of KV pages")
         pages = [self.free_pages.pop() for _ in range(n)]
@@ -352,41 +388,33 @@ class DecodeEngine:
             if self.page_ref[pg] == 0:
                 self.free_pages.append(pg)
 
-    def _evict_prefixes(self, need: int) -> None:
-        for key in list(self._prefix_cache):
+    def _evict_cached_pages(self, need: int) -> None:
+        """Drop least-recently-used cached prefix pages that no live request references."""
+        for h in list(self._page_of_hash):
             if need <= 0:
                 break
-            e = self._prefix_cache[key]
-            if e["users"] == 0 and e["ready"]:
-                before = len(self.free_pages)
-                self._release_pages(e["pages"])
-                need -= len(self.free_pages) - before
-                del self._prefix_cache[key]
+            pg = self._page_of_hash[h]
+            if self.page_ref[pg] == 1 and pg not in self._page_pending:
+                del self._page_of_hash[h]
+                del self._hash_of_page[pg]
+                self._release_pages([pg])
+                need -= 1
 
-    def _attach_shared(self, req: Request, entry: dict) -> None:
-        """Point req's block table at the shared full pages of a prefilled prefix; copy the partial page."""
-        n_full, rem = entry["n_full"], entry["rem"]
-        shared = entry["pages"][:n_full]
-        own = req.pages
-        for pg in shared:
-            self.page_ref[pg] += 1
-        # req.pages currently holds freshly allocated pages for the WHOLE request; give the first n_full back
-        self._release_pages(own[:n_full])
-        req.pages = shared + own[n_full:]
-        row = torch.zeros(self.max_blocks, dtype=torch.int32)
-        row[:len(req.pages)] = torch.tensor(req.pages, dtype=torch.int32)
-        self.block_table[req.slot].copy_(row, non_blocking=True)
-        if rem:
-            c = self.cfg
-            kv = self.kv_cache.view(c.num_layers, 2, self.n_pages, c.num_kv_heads, PAGE_SIZE, c.head_dim)
-            kv[:, :, req.pages[n_full], :, :rem] = kv[:, :, entry["pages"][n_full], :, :rem]
-        self.stats["prefix_hits"] += 1
-        self.stats["prefix_hit_tokens"] += n_full * PAGE_SIZE + rem
+    def _evict_prefixes(self, need: int) -> None:  # kept name: tests / callers free the whole cache with a big `need`
+        self._evict_cached_pages(need)
+
+    @staticmethod
+    def _page_hashes(prompt_ids: list[int], n_full: int) -> list[int]:
+        out, h = [], 0
+        for k in range(n_full):
+            h = hash((h, tuple(prompt_ids[k * PAGE_SIZE:(k + 1) * PAGE_SIZE])))
+            out.append(h)
+        return out
 
     # ---- host-side admission / harvest --------------------------------------------------------
     def can_admit(self, prompt_len: int, max_tokens: int) -> bool:
         need = (prompt_len + max_tokens + PAGE_SIZE - 1) // PAGE_SIZE
-        evictable = sum(len(e["pages"]) for e in self._prefix_cache.values() if e["users"] == 0)
+        evictable = sum(1 for pg in self._hash_of_page if self.page_ref[pg] == 1 and pg not in self._page_pending)
         return bool(self.free_slots) and len(self.free_pages) + evictable >= need
 
     def add_request(self, prompt_ids: list[int], params: SamplingParams, model_version: int = 0) -> Request:
@@ -401,34 +429,45 @@ class DecodeEngine:
         self._next_id += 1
         slot = self.free_slots.pop()
         n_pages = (n + params.max_tokens + PAGE_SIZE - 1) // PAGE_SIZE
-        req.slot, req.pages = slot, self._alloc_pages(n_pages)
+        req.slot = slot
+        start = 0  # index of the prompt token the decode loop processes first
+        shared: list[int] = []
+        if self.prefill_chunk > 0 and n > 1:
+            start = n - 1
+            n_full = (n - 1) // PAGE_SIZE
+            hashes = self._page_hashes(prompt_ids, n_full) if self.prefix_sharing else []
+            for h in hashes:                       # longest cached chain of full pages
+                pg = self._page_of_hash.get(h)
+                if pg is None:
+                    break
+                shared.append(pg)
+                self._page_of_hash.move_to_end(h)
+            for pg in shared:
+                self.page_ref[pg] += 1
+                if pg in self._page_pending:
+                    owner, need = self._page_pending[pg]
+                    req.waits_for.append((owner, need))
+            own = self._alloc_pages(n_pages - len(shared))
+            req.pages = shared + own
+            req.prefilled = len(shared) * PAGE_SIZE
+            for k in range(len(shared), len(hashes)):   # publish this request's own full prompt pages
+                pg, h = req.pages[k], hashes[k]
+                if h not in self._page_of_hash:
+                    self._page_of_hash[h] = pg
+                    self._hash_of_page[pg] = h
+                    self.page_ref[pg] += 1               # the cache's own reference
+                    self._page_pending[pg] = (req, (k + 1) * PAGE_SIZE)
+            if shared:
+                self.stats["prefix_hits"] += 1
+                self.stats["prefix_hit_tokens"] += len(shared) * PAGE_SIZE
+            if req.prefilled < n - 1:
+                self._prefill_queue.append(req)
+        else:
+            req.pages = self._alloc_pages(n_pages)
         row = torch.zeros(self.max_blocks, dtype=torch.int32)
         row[:n_pages] = torch.tensor(req.pages, dtype=torch.int32)
         self.block_table[slot].copy_(row, non_blocking=True)
         self.prompt_buf[slot, :n].copy_(torch.tensor(prompt_ids, dtype=torch.int32), non_blocking=True)
-        start = 0  # index of the prompt token the decode loop processes first
-        if self.prefill_chunk > 0 and n > 1:
-            start = n - 1
-            entry = None
-            if self.prefix_sharing and n - 1 >= PAGE_SIZE:
-                key = hash(tuple(prompt_ids[:n - 1]))
-                entry = self._prefix_cache.get(key)
-                if entry is None:
-                    # this request prefills; the entry keeps one reference on the prefix pages so later attempts of
-                    # the same problem can share them after this request has finished
-                    n_full, rem = (n - 1) // PAGE_SIZE, (n - 1) % PAGE_SIZE
-                    keep = req.pages[:n_full + (1 if rem else 0)]
-                    for pg in keep:
-                        self.page_ref[pg] += 1
-                    self._prefix_cache[key] = {"pages": keep, "n_full": n_full, "rem": rem, "users": 1, "ready": True}
-                    req.prefix_key = key
-                    self._prefill_queue.append(req)
-                else:
-                    entry["users"] += 1
-                    req.prefix_key = key
-                    self._pending_share.append((req, entry))
-            else:
-                self._prefill_queue.append(req)
         self.prompt_len[slot] = n
         self.max_new_t[slot] = params.max_tokens
         self.tokens[slot] = prompt_ids[start]
@@ -457,8 +496,6 @@ class DecodeEngine:
             self.block_table[slot].zero_()
             self.finished[slot] = 0
             self._release_pages(req.pages)
-            if req.prefix_key is not None and req.prefix_key in self._prefix_cache:
-                self._prefix_cache[req.prefix_key]["users"] -= 1
             self.free_slots.append(slot)
             del self.slot_req[slot]
             done.append(req)

@@ -167,8 +167,10 @@ def test_prefix_sharing_and_chunked_prefill(cuda_device):
         res = eng.generate(prompts, SamplingParams(max_tokens=12, greedy=True))
         outs[share] = [(r.output_ids, r.output_logprobs) for r in res]
         if share:
-            assert eng.stats["prefix_hits"] == 7 and eng.stats["prefix_hit_tokens"] == 7 * 149
-            assert eng.stats["prefill_tokens"] == 149 + 69
+            # page-granular sharing: the 2 full pages (128 tokens) of the 149-token prefix are reused, the 21-token
+            # tail of each attempt is re-prefilled
+            assert eng.stats["prefix_hits"] == 7 and eng.stats["prefix_hit_tokens"] == 7 * 128
+            assert eng.stats["prefill_tokens"] == 149 + 7 * 21 + 69
         else:
             assert eng.stats["prefix_hits"] == 0 and eng.stats["prefill_tokens"] == 8 * 149 + 69
         # all pages come back (prefix cache entries are evictable)
@@ -230,3 +232,25 @@ def test_prefill_attention_long_context_vs_fp32(cuda_device):
         ref = torch.einsum("gtrs,gsd->tgrd", torch.softmax(s, -1), V).reshape(ql, -1)
         err = (out[starts[z]:starts[z] + ql].float() - ref).abs().max().item()
         assert err <= 4e-3 * max(1.0, ref.abs().max().item()), (z, err)
+
+
+def test_kv_reuse_across_turns(cuda_device):
+    """Multi-turn rollouts (BASELINE config 5): turn 2's prompt = turn 1's prompt + answer + new message; every
+    full page of the common prefix is reused from the cache even after turn 1 finished."""
+    from pipelinerl_b200.engine import SamplingParams
+    cfg = tiny_cfg("gqa2")
+    w = tiny_weights(cfg)
+    eng = make_engine(cfg, w, cuda_device, max_batch=4, max_seq_len=512, max_new_tokens=16, prefill_chunk=128)
+    g = torch.Generator().manual_seed(33)
+    turn1 = torch.randint(0, cfg.vocab_size, (200,), generator=g).tolist()
+    r1 = eng.generate([turn1], SamplingParams(max_tokens=8, greedy=True))[0]
+    turn2 = turn1 + r1.output_ids + torch.randint(0, cfg.vocab_size, (90,), generator=g).tolist()
+    before = dict(eng.stats)
+    r2 = eng.generate([turn2], SamplingParams(max_tokens=8, greedy=True))[0]
+    assert eng.stats["prefix_hit_tokens"] - before["prefix_hit_tokens"] == (199 // 64) * 64   # 3 pages of turn 1's prompt
+    assert eng.stats["prefill_tokens"] - before["prefill_tokens"] == len(turn2) - 1 - 192
+    orc = OracleQwen2(cfg, w)
+    logits = orc.forward(torch.tensor(turn2))[-1]
+    for tok, lp in zip(r2.output_ids, r2.output_logprobs):
+        assert abs(lp - float(torch.log_softmax(logits, -1)[tok])) <= 3e-2
+        logits = orc.forward(torch.tensor([tok]))[-1]

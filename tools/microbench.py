@@ -39,20 +39,22 @@ def main():
         W = (torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16)
         X = torch.randn(B, K, device=dev).to(torch.bfloat16)
         auto = lib.prl_gemm_auto_split_k(B, N, K)
-        for budget in (200, 100, 72):
+        for budget, tiled in ((100, 0), (100, 1), (200, 1)):
             lib.prl_gemm_set_smem_budget_kb(budget)
-            for split in sorted(set([1, auto, max(1, auto // 2), auto * 2, 4, 8])):
+            lib.prl_gemm_set_tiled_weights(tiled)   # timing experiment: tiled addressing of the same buffer
+            for split in sorted(set([auto, auto * 2])):
                 if split > (K + 63) // 64 // 2 or (name in ("gate_up", "head") and split > 2):
                     continue
                 part = torch.empty(split, B, N, device=dev)
                 us = timeit(lambda: _lib.check(lib.prl_gemm_bf16_splitk(W.data_ptr(), None, X.data_ptr(), B, N, K, split,
                                                                         part.data_ptr(), st)))
                 gbs = N * K * 2 / us / 1e3
-                out.append({"kernel": "gemm", "name": name, "N": N, "K": K, "smem_kb": budget, "split_k": split,
+                out.append({"kernel": "gemm", "name": name, "N": N, "K": K, "smem_kb": budget, "tiled": tiled, "split_k": split,
                             "auto": auto, "us": round(us, 2), "weight_GBs": round(gbs, 1)})
                 print(json.dumps(out[-1]), flush=True)
         del W
-    lib.prl_gemm_set_smem_budget_kb(200)
+    lib.prl_gemm_set_smem_budget_kb(100)
+    lib.prl_gemm_set_tiled_weights(0)
     # epilogue kernels
     h = torch.randn(B, H, device=dev)
     x = torch.empty(B, H, dtype=torch.bfloat16, device=dev)
@@ -60,11 +62,11 @@ def main():
     for split in (1, 4, 5, 8):
         part = torch.randn(split, B, H, device=dev)
         us = timeit(lambda: _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), split, B, H, gamma.data_ptr(), 1e-6,
-                                                                h.data_ptr(), x.data_ptr(), st)))
+                                                                h.data_ptr(), x.data_ptr(), None, 0, st)))
         print(json.dumps({"kernel": "residual_rmsnorm", "split": split, "us": round(us, 2)}), flush=True)
     part = torch.randn(1, B, 2 * I, device=dev)
     act = torch.empty(B, I, dtype=torch.bfloat16, device=dev)
-    us = timeit(lambda: _lib.check(lib.prl_silu_mul(part.data_ptr(), 1, B, I, act.data_ptr(), st)))
+    us = timeit(lambda: _lib.check(lib.prl_silu_mul(part.data_ptr(), 1, B, I, act.data_ptr(), None, 0, st)))
     print(json.dumps({"kernel": "silu_mul", "us": round(us, 2)}), flush=True)
     logits = torch.randn(B, V, device=dev)
     ids = torch.zeros(B, dtype=torch.int32, device=dev)
