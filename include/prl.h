@@ -148,6 +148,12 @@ int prl_logprob_tail_bwd(const float* logits, int64_t T, int64_t V, int64_t row_
                          const float* g_logprobs, const float* g_entropy,
                          float* dlogits, int64_t dlogits_stride, prl_stream_t stream);
 
+/* Same backward for an explicit list of rows with their targets (logits [n_rows, V] of a recomputed chunk). */
+int prl_logprob_rows_bwd(const float* logits, int64_t n_rows, int64_t V, int64_t row_stride,
+                         const int64_t* targets /*[n_rows]*/, float temperature, const float* lse,
+                         const float* entropy, const float* g_logprobs, const float* g_entropy,
+                         float* dlogits, int64_t dlogits_stride, prl_stream_t stream);
+
 /* ======================================================================= *
  * Hot path (2c): fused AdamW over a flat parameter arena
  *   replaces torch.optim.AdamW as built by pipelinerl/finetune/optim.py:25-29

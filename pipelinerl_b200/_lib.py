@@ -134,6 +134,9 @@ _SIGNATURES = {
     "prl_weights_push": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_size_t, C.c_size_t, C.c_int32,
                                    C.c_void_p]),
     "prl_weights_signal": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_uint64, C.c_void_p]),
+    "prl_logprob_rows_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_float,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_void_p]),
     "prl_adamw_workspace_bytes": (C.c_size_t, []),
     "prl_adamw_step": (C.c_int, [C.POINTER(AdamwArgs), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }

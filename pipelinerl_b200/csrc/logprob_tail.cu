@@ -156,3 +156,21 @@ extern "C" int prl_logprob_tail_bwd(const float* logits, int64_t T, int64_t V, i
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }
+
+// Backward over an explicit (row, target) list: rows of a recomputed logits CHUNK (the fused head's backward
+// recomputes logits chunk by chunk instead of keeping 608 KB/token alive between forward and backward).
+extern "C" int prl_logprob_rows_bwd(const float* logits, int64_t n_rows, int64_t V, int64_t row_stride,
+                                    const int64_t* targets, float temperature, const float* lse, const float* entropy,
+                                    const float* g_logprobs, const float* g_entropy, float* dlogits,
+                                    int64_t dlogits_stride, prl_stream_t stream_) {
+  PRL_CHECK_ARG(n_rows >= 1 && V >= 1 && row_stride >= V && dlogits_stride >= V, "prl_logprob_rows_bwd: bad shape");
+  PRL_CHECK_ARG(temperature > 0.f, "prl_logprob_rows_bwd: temperature must be > 0");
+  PRL_CHECK_ARG(logits && targets && lse && dlogits, "prl_logprob_rows_bwd: NULL argument");
+  PRL_CHECK_ARG(!g_entropy || entropy, "prl_logprob_rows_bwd: g_entropy needs the forward entropy");
+  // the kernel reads ids[row + 1]: bias the pointer by one element so that it sees targets[row]
+  tail_bwd_kernel<<<(unsigned)n_rows, kThreads, 0, (cudaStream_t)stream_>>>(
+      logits, V, row_stride, n_rows, targets - 1, 1.f / temperature, lse, entropy, g_logprobs, g_entropy, dlogits,
+      dlogits_stride);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}

@@ -289,8 +289,9 @@ class DecodeEngine:
                 part=torch.zeros(C * widest, dtype=torch.float32, device=d))
         return self._pf
 
-    def _prefill_rows(self, segs: list[tuple[Request, int, int]]) -> None:
-        """One packed chunk: segs = [(request, first prompt index, n tokens)], total rows <= prefill_chunk."""
+    def _prefill_rows(self, segs: list[tuple[Request, int, int]], score_temperature: float | None = None):
+        """One packed chunk: segs = [(request, first prompt index, n tokens)], total rows <= prefill_chunk.
+        With score_temperature, the fused head also returns log p(prompt[i+1] | prompt[:i+1]) for every row."""
         cfg, lib, a, pf = self.cfg, self.lib, self.arena, self._prefill_buffers()
         n = sum(k for _, _, k in segs)
         toks, pos, slot, meta = [], [], [], [[], [], [], []]
@@ -338,6 +339,53 @@ class DecodeEngine:
             _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), 1, n, H, a.ptr(nxt), cfg.rms_eps, h.data_ptr(),
                                                 x.data_ptr(), None, 0, st))
         self.stats["prefill_tokens"] += n
+        if score_temperature is None:
+            return None
+        # teacher-forced scoring: targets = the next prompt token of every row; logits never reach HBM
+        tg = []
+        for req, s0, k in segs:
+            tg += req.prompt_ids[s0 + 1:s0 + k + 1]
+        if "targets" not in pf:
+            pf["targets"] = torch.zeros(self.prefill_chunk, dtype=torch.int64, device=self.dev)
+            pf["lp"] = torch.zeros(self.prefill_chunk, dtype=torch.float32, device=self.dev)
+            pf["head_ws"] = torch.zeros(int(lib.prl_head_workspace_bytes(self.prefill_chunk, cfg.vocab_size)),
+                                        dtype=torch.uint8, device=self.dev)
+        pf["targets"][:n].copy_(torch.tensor(tg, dtype=torch.int64), non_blocking=True)
+        _lib.check(lib.prl_head_logprob(a.ptr("lm_head.weight"), a.ptr("lm_head.weight_lo") if cfg.fp32_head else None,
+                                        x.data_ptr(), n, cfg.vocab_size, H, float(score_temperature),
+                                        pf["targets"].data_ptr(), 1, 0, 0, pf["lp"].data_ptr(), None, None, None, None,
+                                        pf["head_ws"].data_ptr(), pf["head_ws"].numel(), st))
+        return pf["lp"][:n].cpu().tolist()
+
+    def score(self, sequences: list[list[int]], temperature: float = 1.0) -> list[list[float]]:
+        """Teacher-forced log-probabilities log p(seq[i+1] | seq[:i+1]) — the reference-logprob path the
+        preprocessor uses when kl_coef > 0 (`/v1/completions` with echo, pipelinerl/llm.py:606-648,
+        preprocess.py:86-104) — through the chunked-prefill kernels and the fused head."""
+        out: list[list[float]] = []
+        for seq in sequences:
+            n = len(seq)
+            if n < 2:
+                out.append([])
+                continue
+            if n > self.max_seq_len or not self.free_slots:
+                raise RuntimeError("engine cannot score this sequence now (too long or no free slot)")
+            req = Request(-1, list(seq), SamplingParams(max_tokens=0))
+            req.slot = self.free_slots.pop()
+            req.pages = self._alloc_pages((n + PAGE_SIZE - 1) // PAGE_SIZE)
+            row = torch.zeros(self.max_blocks, dtype=torch.int32)
+            row[:len(req.pages)] = torch.tensor(req.pages, dtype=torch.int32)
+            self.block_table[req.slot].copy_(row, non_blocking=True)
+            lps: list[float] = []
+            at = 0
+            while at < n - 1:
+                k = min(self.prefill_chunk, n - 1 - at)
+                lps += self._prefill_rows([(req, at, k)], score_temperature=temperature)
+                at += k
+            self.block_table[req.slot].zero_()
+            self._release_pages(req.pages)
+            self.free_slots.append(req.slot)
+            out.append(lps)
+        return out
 
     def run_prefill(self) -> int:
         """Prefill the not-yet-cached prompt tokens [start, P-1) of every queued request in packed chunks of

@@ -216,7 +216,7 @@ def rl_step(model, batch: PipelineBatchEncoding, current_step: int, max_step: in
     cfg_struct, kl_coef, ent_coef = _cfg_struct(config, current_step, max_step)
     B, L = batch.input_ids.shape
 
-    if hasattr(model, "forward_logprobs"):
+    if hasattr(model, "forward_logprobs") and getattr(model, "use_fused_head", True):
         new_lp_all, ent_all = model.forward_logprobs(batch, config.temperature)
         logits = None
     else:

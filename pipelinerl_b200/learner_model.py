@@ -55,9 +55,26 @@ class TorchQwen2(torch.nn.Module):
         x1, x2 = x[..., :64], x[..., 64:]
         return torch.cat([x1 * cs - x2 * sn, x2 * cs + x1 * sn], dim=-1)
 
+    def forward_logprobs(self, batch, temperature: float):
+        """rl_step's fast path: (new_logprobs [B, L-1], entropy [B, L-1]) through the fused tcgen05 head — the
+        [L, V] logits are never materialised (finetune/fused_head.py)."""
+        from .finetune.fused_head import fused_head_logprobs
+        hidden = self.hidden_states(batch.input_ids, batch.position_ids if batch.is_packed else None)
+        lps, ents = [], []
+        for b in range(hidden.shape[0]):
+            lp, ent = fused_head_logprobs(hidden[b, :-1], self.p("lm_head.weight"), batch.input_ids[b, 1:], temperature)
+            lps.append(lp)
+            ents.append(ent)
+        return torch.stack(lps), torch.stack(ents)
+
     def forward(self, input_ids, attention_mask=None, labels=None, position_ids=None, **kw):
         """Packed rows [1, T] with position_ids restarting per sample (block-diagonal causal attention), or
         padded [B, L] batches."""
+        x = self.hidden_states(input_ids, position_ids)
+        return types.SimpleNamespace(logits=F.linear(x.float(), self.p("lm_head.weight").float()))
+
+    def hidden_states(self, input_ids, position_ids=None):
+        """Final-norm hidden states [B, T, H]."""
         c = self.cfg
         B, T = input_ids.shape
         if position_ids is None:
@@ -86,9 +103,8 @@ class TorchQwen2(torch.nn.Module):
                 gu = F.linear(x, self.p(q_ + "gate_up_proj.weight"))
                 h = h + F.linear(F.silu(gu[:, :c.intermediate_size]) * gu[:, c.intermediate_size:],
                                  self.p(q_ + "down_proj.weight"))
-            x = self._norm(h, self.p("norm.weight"))
-            outs.append(F.linear(x.float(), self.p("lm_head.weight").float()))
-        return types.SimpleNamespace(logits=torch.stack(outs))
+            outs.append(self._norm(h, self.p("norm.weight")))
+        return torch.stack(outs)
 
     def _norm(self, h, g):
         hf = h.float()

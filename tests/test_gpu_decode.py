@@ -254,3 +254,21 @@ def test_kv_reuse_across_turns(cuda_device):
     for tok, lp in zip(r2.output_ids, r2.output_logprobs):
         assert abs(lp - float(torch.log_softmax(logits, -1)[tok])) <= 3e-2
         logits = orc.forward(torch.tensor([tok]))[-1]
+
+
+@pytest.mark.parametrize("kind", ["gqa2", "gqa7"])
+def test_score_reference_logprobs(cuda_device, kind):
+    """engine.score() (chunked prefill + fused head with targets) == oracle / HF teacher-forced logprobs."""
+    cfg = tiny_cfg(kind)
+    w = tiny_weights(cfg)
+    eng = make_engine(cfg, w, cuda_device, max_batch=4, max_seq_len=256, max_new_tokens=8, prefill_chunk=64)
+    gold = np.load(GOLDEN / f"qwen2_tiny_{kind}_T0.7.npz")
+    tokens = gold["tokens"].tolist()
+    got = np.array(eng.score([tokens, tokens[:3], [5]], temperature=0.7)[0])
+    orc = OracleQwen2(cfg, w)
+    want = orc.score(tokens, 0.7).numpy()
+    assert got.shape == want.shape
+    err = np.abs(got - want)
+    assert err.max() <= 3e-2 and err.mean() <= 6e-3, (err.max(), err.mean())
+    assert np.abs(got - gold["logprobs"]).max() <= 3e-2
+    assert len(eng.free_pages) == eng.n_pages - 1 and len(eng.free_slots) == eng.B

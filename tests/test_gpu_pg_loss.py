@@ -176,3 +176,35 @@ def test_large_row_properties(cuda_device):
     assert s[_lib.STAT_NAMES.index("num_output_tokens_sum")] == float(m.sum())
     assert abs(s[_lib.STAT_NAMES.index("ratio_new_old_sum")] - float(m.sum())) < 1e-3
     assert s[_lib.STAT_NAMES.index("kl")] == 0.0 and flags.item() == 0
+
+
+def test_rl_step_fused_head_matches_logits_path(cuda_device):
+    """rl_step through a model exposing forward_logprobs (tcgen05 fused head, no [T, V] logits) == rl_step through
+    the same model's materialised logits: loss, stats and every parameter gradient."""
+    from pipelinerl_b200.finetune.rl import RLConfig, rl_step
+    from pipelinerl_b200.learner_model import TorchQwen2
+    from tests.helpers import tiny_cfg, tiny_weights
+    arrs, meta = load_rl_case("ppo_kl_entropy")
+    cfg_m = tiny_cfg("gqa2")
+    w = tiny_weights(cfg_m, std=0.02, bias_std=0.0)
+    arrs = dict(arrs)
+    arrs["input_ids"] = arrs["input_ids"] % cfg_m.vocab_size
+    arrs["labels"] = np.where(arrs["labels"] == -100, -100, arrs["labels"] % cfg_m.vocab_size)
+    rl = RLConfig(**meta["config"])
+    results = []
+    for fused in (True, False):
+        model = TorchQwen2(cfg_m, cuda_device, dtype=torch.float32, init=w)
+        model.use_fused_head = fused
+        batch = batch_from_arrays(arrs, cuda_device)
+        loss, stats = rl_step(model, batch, meta["current_step"], meta["max_step"], rl)
+        loss.backward()
+        grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+        results.append((loss.item(), stats, grads))
+    (l1, s1, g1), (l0, s0, g0) = results
+    assert abs(l1 - l0) <= 2e-3 * max(1.0, abs(l0))        # bf16 rounding of the head input in the fused path
+    for k in s0:
+        assert abs(s1[k] - s0[k]) <= 5e-3 + 5e-3 * abs(s0[k]), k
+    assert set(g1) == set(g0)
+    for n in g0:
+        scale = g0[n].abs().max().item() + 1e-12
+        assert (g1[n] - g0[n]).abs().max().item() <= 3e-2 * scale, n
