@@ -130,9 +130,13 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   const uint32_t tmem_slot = tmem_full_bar + 8u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * kBlockM;        // first output feature of this CTA
+  // blockIdx.x enumerates (weight tile, token tile) with the token tile fastest, so the CTAs that share a
+  // weight tile are co-scheduled and the tile is fetched from HBM once (prefill / training shapes, M > 256)
+  const int m_tiles = (int)((p.M + kNTile - 1) / kNTile);
+  const int n_tile = (int)blockIdx.x / m_tiles;
+  const int n0 = n_tile * kBlockM;            // first output feature of this CTA
   const int split = blockIdx.y;
-  const int m0 = blockIdx.z * kNTile;         // first token of this CTA
+  const int m0 = ((int)blockIdx.x % m_tiles) * kNTile;  // first token of this CTA
   const int kb_begin = (int)(((int64_t)p.kblocks * split) / p.split_k);
   const int kb_end = (int)(((int64_t)p.kblocks * (split + 1)) / p.split_k);
   const int n_kb = kb_end - kb_begin;
@@ -174,7 +178,7 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
         const uint32_t a_dst = smem_base + (uint32_t)(i * stage_bytes);
         const int kcoord = (kb_begin + i) * kBlockK;
         const int wc0 = p.tiled ? 0 : kcoord;
-        const int wc1 = p.tiled ? (blockIdx.x * p.kblocks + kb_begin + i) * kBlockM : n0;
+        const int wc1 = p.tiled ? (n_tile * p.kblocks + kb_begin + i) * kBlockM : n0;
         ptx::tma_load_2d(a_dst, &tm_w, wc0, wc1, full_bar(i), ptx::kEvictFirst);
         if (lo) ptx::tma_load_2d(a_dst + L::kABytes, &tm_wlo, wc0, wc1, full_bar(i), ptx::kEvictFirst);
       }
@@ -191,7 +195,7 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
         const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes);
         const int kcoord = (kb_begin + i) * kBlockK;
         const int wc0 = p.tiled ? 0 : kcoord;
-        const int wc1 = p.tiled ? (blockIdx.x * p.kblocks + kb_begin + i) * kBlockM : n0;
+        const int wc1 = p.tiled ? (n_tile * p.kblocks + kb_begin + i) * kBlockM : n0;
         ptx::tma_load_2d(a_dst, &tm_w, wc0, wc1, full_bar(s), ptx::kEvictFirst);
         uint32_t b_dst = a_dst + L::kABytes;
         if (lo) {
@@ -310,7 +314,7 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
           a.m = mm;
           if (b.key > a.key || (b.key == a.key && b.idx < a.idx)) { a.key = b.key; a.z = b.z; a.idx = b.idx; }
         }
-        p.head_part[(int64_t)blockIdx.x * p.M + m0 + tkn] = a;
+        p.head_part[(int64_t)n_tile * p.M + m0 + tkn] = a;
       }
     }
   }
@@ -370,7 +374,7 @@ int launch_gemm(const CUtensorMap& tw, const CUtensorMap& twl, const CUtensorMap
     PRL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured[p.head ? 1 : 0] = smem;
   }
-  dim3 grid((unsigned)((p.N + kBlockM - 1) / kBlockM), (unsigned)p.split_k, (unsigned)((p.M + kNTile - 1) / kNTile));
+  dim3 grid((unsigned)(((p.N + kBlockM - 1) / kBlockM) * ((p.M + kNTile - 1) / kNTile)), (unsigned)p.split_k, 1);
   PRL_CUDA(launch_pdl(kernel, grid, dim3(kThreads), (size_t)smem, stream, tw, twl, tx, p, n_stages));
   PRL_LAUNCH_CHECK();
   return PRL_OK;
