@@ -119,6 +119,7 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
                    const __grid_constant__ CUtensorMap tm_x, GemmParams p, int n_stages) {
   using L = SmemLayout<kNTile>;
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();  // let the next kernel start its own prologue / weight prefetch as early as possible
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const bool lo = p.has_lo != 0;
   const int stage_bytes = L::stage_bytes(lo);
@@ -141,6 +142,10 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   const int kb_end = (int)(((int64_t)p.kblocks * (split + 1)) / p.split_k);
   const int n_kb = kb_end - kb_begin;
 
+  // Thread 0 arms the barriers and IMMEDIATELY fills the first ring pass with WEIGHT tiles: weights do not depend on
+  // the preceding kernel (PDL lets this run under the predecessor's tail) nor on the rest of this CTA's prologue
+  // (TMEM allocation, descriptor prefetch), so the first HBM round trip overlaps both.
+  const int pre = n_kb < n_stages ? n_kb : n_stages;
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) {
       ptx::mbar_init(full_bar(s), 1);
@@ -148,11 +153,17 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
     }
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::fence_barrier_init();
-  }
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&tm_w);
+    ptx::fence_proxy_async();
+    for (int i = 0; i < pre; ++i) {
+      ptx::mbar_arrive_expect_tx(full_bar(i), (uint32_t)stage_bytes);
+      const uint32_t a_dst = smem_base + (uint32_t)(i * stage_bytes);
+      const int kcoord = (kb_begin + i) * kBlockK;
+      const int wc0 = p.tiled ? 0 : kcoord;
+      const int wc1 = p.tiled ? (n_tile * p.kblocks + kb_begin + i) * kBlockM : n0;
+      ptx::tma_load_2d(a_dst, &tm_w, wc0, wc1, full_bar(i), ptx::kEvictFirst);
+      if (lo) ptx::tma_load_2d(a_dst + L::kABytes, &tm_wlo, wc0, wc1, full_bar(i), ptx::kEvictFirst);
+    }
     ptx::prefetch_tensormap(&tm_x);
-    if (lo) ptx::prefetch_tensormap(&tm_wlo);
   }
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, kNTile < 32 ? 32 : kNTile);
@@ -163,25 +174,11 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
   ptx::tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  pdl_launch_dependents();
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    // Weights do not depend on the preceding kernel: fill the first ring pass with WEIGHT tiles right away
-    // (programmatic dependent launch lets this run under the predecessor's tail), then wait for the
-    // dependency and add the activation tiles.
+    // ===== TMA producer =====  (first-pass weight tiles were issued by thread 0 before the CTA-wide sync)
     if (lane == 0) {
       const uint32_t tx = (uint32_t)stage_bytes;
-      const int pre = n_kb < n_stages ? n_kb : n_stages;
-      for (int i = 0; i < pre; ++i) {
-        ptx::mbar_arrive_expect_tx(full_bar(i), tx);
-        const uint32_t a_dst = smem_base + (uint32_t)(i * stage_bytes);
-        const int kcoord = (kb_begin + i) * kBlockK;
-        const int wc0 = p.tiled ? 0 : kcoord;
-        const int wc1 = p.tiled ? (n_tile * p.kblocks + kb_begin + i) * kBlockM : n0;
-        ptx::tma_load_2d(a_dst, &tm_w, wc0, wc1, full_bar(i), ptx::kEvictFirst);
-        if (lo) ptx::tma_load_2d(a_dst + L::kABytes, &tm_wlo, wc0, wc1, full_bar(i), ptx::kEvictFirst);
-      }
       pdl_wait();
       for (int i = 0; i < pre; ++i) {
         const uint32_t b_dst = smem_base + (uint32_t)(i * stage_bytes) + L::kABytes * (lo ? 2 : 1);
