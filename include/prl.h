@@ -184,6 +184,34 @@ size_t prl_adamw_workspace_bytes(void);
 int prl_adamw_step(const prl_adamw_args* args, float* grad_norm_out,
                    void* workspace, size_t workspace_bytes, prl_stream_t stream);
 
+/* Learner data parallelism as one fused exchange step over NVLink peer memory (replaces the gradient all-reduce
+ * + per-rank full optimizer of finetune_loop.py:716-755): rank r owns elements [shard_begin, shard_end) of the
+ * arena and ONLY that shard of fp32 master / exp_avg / exp_avg_sq (optimizer state sharded n_peers ways).
+ *   prl_adamw_sharded_reduce : gsum = sum_p grads[p][shard] (P2P loads, fixed order), partial sum of squares
+ *                              published into every rank's norm table (slot = rank).
+ *   -- host barrier (all ranks reduced) --
+ *   prl_adamw_sharded_update : clip by the global norm, AdamW on the shard, bf16 re-cast stored into EVERY rank's
+ *                              parameter arena shadows[p][shard] (P2P stores).
+ *   -- host barrier (all shards written) --
+ * grads[]/shadows[]/norm_tables[] are the n_peers ranks' buffers in rank order (own and peers', mapped with
+ * prl_ipc_open); norm_tables[p] is a double[n_peers] in rank p's memory. */
+typedef struct {
+  int64_t n, shard_begin, shard_end;
+  float* master; float* exp_avg; float* exp_avg_sq;   /* [shard_end - shard_begin] */
+  const void* grads[8];
+  void* shadows[8];
+  double* norm_tables[8];
+  int32_t n_peers, rank, grad_is_bf16;
+  float* gsum_scratch;                                /* [shard_end - shard_begin] fp32 */
+  const int64_t* tensor_offsets; const uint8_t* tensor_no_decay; int32_t n_tensors;
+  double lr, beta1, beta2, eps, weight_decay;
+  int32_t step;
+  float max_grad_norm, grad_scale;
+} prl_adamw_shard_args;
+int prl_adamw_sharded_reduce(const prl_adamw_shard_args* args, void* workspace, size_t workspace_bytes,
+                             prl_stream_t stream);
+int prl_adamw_sharded_update(const prl_adamw_shard_args* args, float* grad_norm_out, prl_stream_t stream);
+
 /* ======================================================================= *
  * Hot path (1): tcgen05 weight-streaming GEMM of the token step
  *   Y[M, N] = X[M, K] * W[N, K]^T, bf16 operands (row-major, K contiguous),

@@ -56,6 +56,19 @@ class AdamwArgs(C.Structure):
     ]
 
 
+class AdamwShardArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64), ("shard_begin", C.c_int64), ("shard_end", C.c_int64),
+        ("master", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+        ("grads", C.c_void_p * 8), ("shadows", C.c_void_p * 8), ("norm_tables", C.c_void_p * 8),
+        ("n_peers", C.c_int32), ("rank", C.c_int32), ("grad_is_bf16", C.c_int32),
+        ("gsum_scratch", C.c_void_p), ("tensor_offsets", C.c_void_p), ("tensor_no_decay", C.c_void_p),
+        ("n_tensors", C.c_int32),
+        ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double),
+        ("step", C.c_int32), ("max_grad_norm", C.c_float), ("grad_scale", C.c_float),
+    ]
+
+
 class EngineState(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("sampled", C.c_void_p), ("sampled_logprobs", C.c_void_p), ("tokens", C.c_void_p),
@@ -137,6 +150,8 @@ _SIGNATURES = {
     "prl_logprob_rows_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_void_p]),
+    "prl_adamw_sharded_reduce": (C.c_int, [C.POINTER(AdamwShardArgs), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "prl_adamw_sharded_update": (C.c_int, [C.POINTER(AdamwShardArgs), C.c_void_p, C.c_void_p]),
     "prl_adamw_workspace_bytes": (C.c_size_t, []),
     "prl_adamw_step": (C.c_int, [C.POINTER(AdamwArgs), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }

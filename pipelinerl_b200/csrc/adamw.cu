@@ -200,6 +200,130 @@ __global__ void __launch_bounds__(kThreads) adamw_kernel(prl_adamw_args a, Updat
   }
 }
 
+
+// =====================================================================================================
+// Learner data parallelism as ONE fused exchange step over NVLink peer memory:
+//   reduce-scatter(grad) -> clip -> AdamW on this rank's 1/Ng shard -> all-gather(bf16 params)
+// Every rank maps every other rank's full gradient arena and bf16 parameter arena (CUDA IPC).  Kernel A
+// (shard_reduce) sums the Ng gradients of this rank's shard straight out of peer memory (P2P loads) into an
+// fp32 scratch and leaves its partial sum of squares in every rank's norm table; kernel B (shard_update)
+// applies clip + AdamW to the shard (fp32 master / m / v exist ONLY for the shard: optimizer state is sharded
+// Ng ways) and stores the re-cast bf16 parameters into every rank's parameter arena (P2P stores).
+// Replaces the DDP/ZeRO gradient all-reduce + per-rank full AdamW of the reference
+// (finetune_loop.py:716-755, conf/deepspeed/*.json); no NCCL on the data path, host barriers only between phases.
+// =====================================================================================================
+constexpr int kMaxPeers = 8;
+
+struct ShardParams {
+  int64_t n, lo, hi;
+  float* master; float* exp_avg; float* exp_avg_sq;     // shard-local, index i - lo
+  const void* grads[kMaxPeers];
+  void* shadows[kMaxPeers];
+  int n_peers, rank, grad_is_bf16;
+  float* gsum;                                          // [hi - lo]
+  double* norm_tables[kMaxPeers];                       // norm_tables[p][r] = rank r's partial, stored in rank p's memory
+  const int64_t* tensor_offsets; const uint8_t* tensor_no_decay; int n_tensors;
+  float grad_scale;
+};
+
+template <bool kBf16>
+__global__ void __launch_bounds__(kThreads) shard_reduce_kernel(ShardParams a, AdamWorkspace* ws) {
+  double acc = 0.0;
+  const int64_t n4 = (a.hi - a.lo) / 4;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = a.lo + v * 4;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int p = 0; p < a.n_peers; ++p) {   // fixed peer order on every rank -> bitwise identical sums everywhere
+      float g[4];
+      load_grad4<kBf16>(a.grads[p], i, a.grad_scale, g);
+      s[0] += g[0]; s[1] += g[1]; s[2] += g[2]; s[3] += g[3];
+    }
+    *reinterpret_cast<float4*>(a.gsum + v * 4) = make_float4(s[0], s[1], s[2], s[3]);
+    acc += (double)(s[0] * s[0] + s[1] * s[1] + s[2] * s[2] + s[3] * s[3]);
+  }
+  __shared__ double s_w[kThreads / kWarp];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < kThreads / kWarp; ++i) t += s_w[i];
+    ws->partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void shard_norm_publish_kernel(ShardParams a, const AdamWorkspace* ws, int n_blocks) {
+  __shared__ double s_red[kThreads / kWarp];
+  double t = 0;
+  for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) t += ws->partial[i];
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0;
+    for (int i = 0; i < kThreads / kWarp; ++i) tot += s_red[i];
+    for (int p = 0; p < a.n_peers; ++p) a.norm_tables[p][a.rank] = tot;   // P2P store into every rank's table
+    __threadfence_system();
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) shard_update_kernel(ShardParams a, UpdateConsts k, const double* norm_table,
+                                                                float* __restrict__ grad_norm_out) {
+  __shared__ float s_clip;
+  __shared__ int s_tensor;
+  if (threadIdx.x == 0) {
+    double tot = 0;
+    for (int r = 0; r < a.n_peers; ++r) tot += norm_table[r];
+    const float norm = (float)sqrt(tot);
+    s_clip = (k.max_grad_norm > 0.f) ? fminf(k.max_grad_norm / (norm + 1e-6f), 1.f) : 1.f;
+    if (blockIdx.x == 0 && grad_norm_out) *grad_norm_out = norm;
+  }
+  __syncthreads();
+  const float clip = s_clip;
+  const int64_t n_chunks = (a.hi - a.lo + kChunk - 1) / kChunk;
+  for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const int64_t base = a.lo + c * kChunk;
+    const int64_t end = (base + kChunk < a.hi) ? base + kChunk : a.hi;
+    if (threadIdx.x == 0) {
+      int lo = 0, hi = a.n_tensors;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (a.tensor_offsets[mid] <= base) lo = mid; else hi = mid;
+      }
+      s_tensor = lo;
+    }
+    __syncthreads();
+    int tix = s_tensor;
+    int64_t t_end = a.tensor_offsets[tix + 1];
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int64_t i = base + ((int64_t)it * kThreads + threadIdx.x) * kVec;
+      if (i >= end) break;
+      // shard bounds and tensor starts are multiples of 64 elements (arena alignment), so a 4-vector never straddles
+      while (i >= t_end) { ++tix; t_end = a.tensor_offsets[tix + 1]; }
+      const int64_t j = i - a.lo;
+      const float4 g = *reinterpret_cast<const float4*>(a.gsum + j);
+      float4 p = *reinterpret_cast<const float4*>(a.master + j);
+      float4 m = *reinterpret_cast<const float4*>(a.exp_avg + j);
+      float4 v = *reinterpret_cast<const float4*>(a.exp_avg_sq + j);
+      const float wd = a.tensor_no_decay[tix] ? 1.f : k.weight_decay;
+      adam_elem(g.x * clip, p.x, m.x, v.x, k, wd);
+      adam_elem(g.y * clip, p.y, m.y, v.y, k, wd);
+      adam_elem(g.z * clip, p.z, m.z, v.z, k, wd);
+      adam_elem(g.w * clip, p.w, m.w, v.w, k, wd);
+      *reinterpret_cast<float4*>(a.master + j) = p;
+      *reinterpret_cast<float4*>(a.exp_avg + j) = m;
+      *reinterpret_cast<float4*>(a.exp_avg_sq + j) = v;
+      const uint32_t b0 = float_to_bf16_bits(p.x), b1 = float_to_bf16_bits(p.y);
+      const uint32_t b2 = float_to_bf16_bits(p.z), b3 = float_to_bf16_bits(p.w);
+      const uint2 packed = make_uint2(b0 | (b1 << 16), b2 | (b3 << 16));
+      for (int q = 0; q < a.n_peers; ++q)   // all-gather: every rank's bf16 parameter arena receives this shard
+        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(a.shadows[q]) + i) = packed;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace prl
 
@@ -249,6 +373,74 @@ extern "C" int prl_adamw_step(const prl_adamw_args* a, float* grad_norm_out, voi
   int blocks = (int)(n_chunks < (int64_t)num_sms() * 8 ? n_chunks : (int64_t)num_sms() * 8);
   if (a->grad_is_bf16) adamw_kernel<true><<<blocks, kThreads, 0, stream>>>(*a, k, ws, grad_norm_out, norm_blocks);
   else adamw_kernel<false><<<blocks, kThreads, 0, stream>>>(*a, k, ws, grad_norm_out, norm_blocks);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
+// ---- sharded exchange step (see the block comment above shard_reduce_kernel) -----------------------------------
+static int fill_shard_params(const prl_adamw_shard_args* a, ShardParams* sp) {
+  PRL_CHECK_ARG(a, "prl_adamw_sharded: NULL args");
+  PRL_CHECK_ARG(a->n_peers >= 1 && a->n_peers <= kMaxPeers && a->rank >= 0 && a->rank < a->n_peers,
+                "prl_adamw_sharded: need 1..8 peers and a valid rank");
+  PRL_CHECK_ARG(a->shard_begin >= 0 && a->shard_end >= a->shard_begin && a->shard_end <= a->n &&
+                    a->shard_begin % 64 == 0 && (a->shard_end % 64 == 0 || a->shard_end == a->n),
+                "prl_adamw_sharded: shard bounds must be 64-element aligned");
+  PRL_CHECK_ARG(a->master && a->exp_avg && a->exp_avg_sq && a->gsum_scratch && a->tensor_offsets && a->tensor_no_decay,
+                "prl_adamw_sharded: NULL state pointer");
+  sp->n = a->n; sp->lo = a->shard_begin; sp->hi = a->shard_end;
+  sp->master = a->master; sp->exp_avg = a->exp_avg; sp->exp_avg_sq = a->exp_avg_sq;
+  sp->n_peers = a->n_peers; sp->rank = a->rank; sp->grad_is_bf16 = a->grad_is_bf16;
+  sp->gsum = a->gsum_scratch;
+  for (int p = 0; p < a->n_peers; ++p) {
+    PRL_CHECK_ARG(a->grads[p] && a->shadows[p] && a->norm_tables[p], "prl_adamw_sharded: NULL peer pointer %d", p);
+    sp->grads[p] = a->grads[p]; sp->shadows[p] = a->shadows[p]; sp->norm_tables[p] = a->norm_tables[p];
+  }
+  sp->tensor_offsets = a->tensor_offsets; sp->tensor_no_decay = a->tensor_no_decay; sp->n_tensors = a->n_tensors;
+  sp->grad_scale = a->grad_scale == 0.f ? 1.f : a->grad_scale;
+  return PRL_OK;
+}
+
+extern "C" int prl_adamw_sharded_reduce(const prl_adamw_shard_args* a, void* workspace, size_t workspace_bytes,
+                                        prl_stream_t stream_) {
+  ShardParams sp;
+  int rc = fill_shard_params(a, &sp);
+  if (rc) return rc;
+  PRL_CHECK_ARG(workspace && workspace_bytes >= sizeof(AdamWorkspace), "prl_adamw_sharded_reduce: workspace too small");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  AdamWorkspace* ws = (AdamWorkspace*)workspace;
+  const int64_t n4 = (sp.hi - sp.lo) / 4;
+  int blocks = (int)((n4 + kThreads - 1) / kThreads);
+  if (blocks < 1) blocks = 1;
+  const int cap = num_sms() * 8 < kMaxNormBlocks ? num_sms() * 8 : kMaxNormBlocks;
+  if (blocks > cap) blocks = cap;
+  if (sp.grad_is_bf16) shard_reduce_kernel<true><<<blocks, kThreads, 0, stream>>>(sp, ws);
+  else shard_reduce_kernel<false><<<blocks, kThreads, 0, stream>>>(sp, ws);
+  PRL_LAUNCH_CHECK();
+  shard_norm_publish_kernel<<<1, kThreads, 0, stream>>>(sp, ws, blocks);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
+extern "C" int prl_adamw_sharded_update(const prl_adamw_shard_args* a, float* grad_norm_out, prl_stream_t stream_) {
+  ShardParams sp;
+  int rc = fill_shard_params(a, &sp);
+  if (rc) return rc;
+  PRL_CHECK_ARG(a->step >= 1, "prl_adamw_sharded_update: step is 1-based");
+  UpdateConsts k;
+  k.lr = (float)a->lr; k.beta1 = (float)a->beta1; k.beta2 = (float)a->beta2; k.eps = (float)a->eps;
+  k.weight_decay = (float)(1.0 - a->lr * a->weight_decay);
+  k.one_minus_beta1 = (float)(1.0 - a->beta1);
+  k.one_minus_beta2 = (float)(1.0 - a->beta2);
+  const double bc1 = 1.0 - pow(a->beta1, (double)a->step);
+  const double bc2 = 1.0 - pow(a->beta2, (double)a->step);
+  k.step_size = (float)(a->lr / bc1);
+  k.bc2_sqrt = (float)sqrt(bc2);
+  k.max_grad_norm = a->max_grad_norm;
+  k.grad_scale = 1.f;
+  const int64_t n_chunks = (sp.hi - sp.lo + kChunk - 1) / kChunk;
+  if (n_chunks == 0) return PRL_OK;
+  int blocks = (int)(n_chunks < (int64_t)num_sms() * 8 ? n_chunks : (int64_t)num_sms() * 8);
+  shard_update_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream_>>>(sp, k, a->norm_tables[a->rank], grad_norm_out);
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }

@@ -363,7 +363,12 @@ int launch_gemm(const CUtensorMap& tw, const CUtensorMap& twl, const CUtensorMap
                 cudaStream_t stream) {
   using L = SmemLayout<kNTile>;
   const bool lo = p.has_lo != 0;
-  const int n_stages = L::stages(lo);
+  int n_stages = L::stages(lo);
+  if (kNTile >= 128) {  // compute-bound shapes (prefill / training): one CTA per SM with the deepest ring that fits
+    n_stages = (200 * 1024) / L::stage_bytes(lo);
+    if (n_stages > 8) n_stages = 8;
+    if (n_stages < 2) n_stages = 2;
+  }
   const int smem = n_stages * L::stage_bytes(lo) + 1024 /*align slack*/ + 8 * (2 * n_stages + 2) + 16;
   static int configured[2] = {0, 0};
   auto kernel = p.head ? gemm_swapab_kernel<kNTile, true> : gemm_swapab_kernel<kNTile, false>;

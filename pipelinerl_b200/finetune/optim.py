@@ -138,3 +138,126 @@ def get_optimizer(name: str, model, learning_rate: float, weight_decay: float, *
     if name != "adamw_torch":
         raise ValueError(f"Unknown optimizer: {name} (only the reference default adamw_torch is on the hot path)")
     return FusedAdamW(model.named_parameters(), lr=learning_rate, weight_decay=weight_decay, **kw)
+
+
+class ShardedFusedAdamW:
+    """Data-parallel learners: gradient reduce-scatter + AdamW on a 1/Ng shard + bf16 parameter all-gather as one
+    exchange step over NVLink peer memory (csrc/adamw.cu: shard_reduce / shard_update), with the fp32 optimizer
+    state sharded Ng ways.  One process per GPU; `torch.distributed` is used for the one-off exchange of CUDA-IPC
+    handles and for the host barriers between the two phases — there is no NCCL collective on the data path.
+
+    Parameters must be bf16 (the reference's `load_as_bf16: True` + DeepSpeed-bf16 arrangement): their .data are
+    views of this rank's bf16 parameter arena, their .grad views of its bf16 gradient arena.
+    """
+
+    def __init__(self, named_params, lr: float, weight_decay: float = 0.01, betas=(0.9, 0.999), eps: float = 1e-8,
+                 max_grad_norm: float | None = None, no_decay: Iterable[str] = NO_DECAY_DEFAULT, group=None):
+        import torch.distributed as dist
+        from ..weights import ipc_alloc, ipc_export, ipc_open
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("ShardedFusedAdamW needs an initialised torch.distributed process group")
+        named = [(n, p) for n, p in named_params if p.requires_grad]
+        dev = named[0][1].device
+        if dev.type != "cuda":
+            raise RuntimeError("ShardedFusedAdamW needs CUDA parameters: pipelinerl_b200 has no CPU fallback")
+        if any(p.dtype != torch.bfloat16 for _, p in named):
+            raise ValueError("ShardedFusedAdamW: parameters must be bf16")
+        self.lib, self.dist, self.group = _lib.load(), dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError("ShardedFusedAdamW: at most 8 learner ranks (one box)")
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        self.lr, self.weight_decay, self.betas, self.eps, self.max_grad_norm = lr, weight_decay, betas, eps, max_grad_norm
+        self.step_count = 0
+        offsets, at = [], 0
+        for p in self.params:
+            offsets.append(at)
+            at = _align(at + p.numel())
+        self.n, self.offsets = at, offsets
+        per = _align((self.n + self.world - 1) // self.world)
+        self.lo, self.hi = min(self.n, per * self.rank), min(self.n, per * (self.rank + 1))
+        # IPC-shareable arenas of this rank
+        self._grad_buf, self._shadow_buf = ipc_alloc(self.n * 2), ipc_alloc(self.n * 2)
+        self._norm_buf = ipc_alloc(8 * 8)
+        self.grad = self._grad_buf.tensor(torch.bfloat16, dev)
+        self.shadow_bf16 = self._shadow_buf.tensor(torch.bfloat16, dev)
+        shard = max(self.hi - self.lo, 1)
+        self.master = torch.zeros(shard, dtype=torch.float32, device=dev)
+        self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.master), torch.zeros_like(self.master)
+        self.gsum = torch.zeros_like(self.master)
+        with torch.no_grad():
+            for p, off in zip(self.params, offsets):
+                k = p.numel()
+                self.shadow_bf16[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.shadow_bf16[off:off + k].view(p.shape)
+                p.grad = self.grad[off:off + k].view(p.shape)
+            self.master[: self.hi - self.lo].copy_(self.shadow_bf16[self.lo:self.hi].float())
+        self.tensor_offsets = torch.tensor(offsets + [self.n], dtype=torch.int64, device=dev)
+        self.tensor_no_decay = torch.tensor([1 if any(t in n for t in no_decay) else 0 for n in self.names],
+                                            dtype=torch.uint8, device=dev)
+        self.workspace = torch.zeros(int(self.lib.prl_adamw_workspace_bytes()), dtype=torch.uint8, device=dev)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        # exchange handles (once) and map the peers' arenas
+        mine = (ipc_export(self._grad_buf), ipc_export(self._shadow_buf), ipc_export(self._norm_buf), self.n)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, mine, group=group)
+        self._peer_bufs = []
+        self._grads, self._shadows, self._norms = [], [], []
+        for r, (hg, hs, hn, n_r) in enumerate(gathered):
+            if n_r != self.n:
+                raise RuntimeError("ShardedFusedAdamW: ranks disagree on the arena size")
+            if r == self.rank:
+                self._grads.append(self._grad_buf.ptr); self._shadows.append(self._shadow_buf.ptr); self._norms.append(self._norm_buf.ptr)
+            else:
+                g, s, nn = ipc_open(hg, self.n * 2), ipc_open(hs, self.n * 2), ipc_open(hn, 64)
+                self._peer_bufs += [g, s, nn]
+                self._grads.append(g.ptr); self._shadows.append(s.ptr); self._norms.append(nn.ptr)
+        self.param_groups = [{"lr": lr, "weight_decay": weight_decay, "params": self.params}]
+        self.last_phase_ms = (0.0, 0.0)
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        self.grad.zero_()
+
+    def _args(self) -> _lib.AdamwShardArgs:
+        a = _lib.AdamwShardArgs()
+        a.n, a.shard_begin, a.shard_end = self.n, self.lo, self.hi
+        a.master, a.exp_avg, a.exp_avg_sq = self.master.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+        for r in range(self.world):
+            a.grads[r], a.shadows[r], a.norm_tables[r] = self._grads[r], self._shadows[r], self._norms[r]
+        a.n_peers, a.rank, a.grad_is_bf16 = self.world, self.rank, 1
+        a.gsum_scratch = self.gsum.data_ptr()
+        a.tensor_offsets, a.tensor_no_decay, a.n_tensors = self.tensor_offsets.data_ptr(), self.tensor_no_decay.data_ptr(), len(self.params)
+        a.lr, a.beta1, a.beta2, a.eps = self.param_groups[0]["lr"], self.betas[0], self.betas[1], self.eps
+        a.weight_decay, a.step = self.weight_decay, self.step_count
+        a.max_grad_norm = float(self.max_grad_norm) if self.max_grad_norm else 0.0
+        a.grad_scale = 1.0
+        return a
+
+    def _barrier(self) -> None:
+        torch.cuda.current_stream().synchronize()
+        self.dist.barrier(group=self.group)
+
+    def step(self, grad_scale: float = 1.0) -> torch.Tensor:
+        self.step_count += 1
+        a = self._args()
+        a.grad_scale = grad_scale
+        st = _lib.stream_ptr()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        self._barrier()                                   # every rank's backward has written its gradient arena
+        e[0].record()
+        _lib.check(self.lib.prl_adamw_sharded_reduce(C.byref(a), self.workspace.data_ptr(), self.workspace.numel(), st))
+        e[1].record()
+        self._barrier()                                   # every rank's norm partial is in every norm table
+        e[2].record()
+        _lib.check(self.lib.prl_adamw_sharded_update(C.byref(a), self.grad_norm.data_ptr(), st))
+        e[3].record()
+        self._barrier()                                   # every shard of every parameter arena is written
+        self.last_phase_ms = (e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3]))
+        return self.grad_norm
+
+    def close(self) -> None:
+        for b in self._peer_bufs:
+            b.release()
+        for b in (self._grad_buf, self._shadow_buf, self._norm_buf):
+            b.release()

@@ -48,8 +48,17 @@ def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding
                  weight_manager: WeightUpdateManager | None = None, message_writer=None,
                  device: torch.device | str = "cuda:0", dp_group=None) -> tuple[TrainingMetrics, list[dict]]:
     dev = torch.device(device)
-    opt = FusedAdamW(model.named_parameters(), lr=cfg.learning_rate, weight_decay=cfg.weight_decay,
-                     max_grad_norm=cfg.gradient_clipping_threshold)
+    import torch.distributed as dist
+    sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size(dp_group) > 1 and \
+        all(p.dtype == torch.bfloat16 for _, p in model.named_parameters())
+    if sharded:
+        # learner DP: P2P reduce-scatter + AdamW shard + P2P all-gather in one exchange step (optimizer state / Ng)
+        from .finetune.optim import ShardedFusedAdamW
+        opt = ShardedFusedAdamW(model.named_parameters(), lr=cfg.learning_rate, weight_decay=cfg.weight_decay,
+                                max_grad_norm=cfg.gradient_clipping_threshold, group=dp_group)
+    else:
+        opt = FusedAdamW(model.named_parameters(), lr=cfg.learning_rate, weight_decay=cfg.weight_decay,
+                         max_grad_norm=cfg.gradient_clipping_threshold)
     if weight_manager is not None:
         weight_manager.src = opt.shadow_bf16
     rl_cfg = cfg.rl.model_copy(update={"batch_size": cfg.samples_per_step})
@@ -74,7 +83,8 @@ def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding
             message_writer.write(SamplesProcessed(samples_processed=tm.samples, timestamp=time.time()))
         if samples_in_step < cfg.samples_per_step:
             continue
-        allreduce_gradients(opt.grad, dp_group)
+        if not sharded:
+            allreduce_gradients(opt.grad, dp_group)   # fp32-parameter path: plain SUM all-reduce, full AdamW per rank
         grad_norm = opt.step()
         opt.zero_grad()
         tm.completed_steps += 1

@@ -24,3 +24,16 @@ def test_two_gpu_push_is_byte_exact_and_sampler_never_pauses():
     out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
     assert out["bytes_identical_on_all_ranks"]
     assert out["ours"]["stall_ms_max"] is not None and out["ours"]["stall_ms_max"] < 50
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_adamw_exchange_matches_oracle():
+    """P2P reduce-scatter + AdamW shard + P2P all-gather == AdamW on the summed gradients (oracle), and every rank
+    ends with bit-identical bf16 parameters."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29584")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29584", str(ROOT / "tools" / "dp_adamw_bench.py"),
+                          "--check"], capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["ok"] and out["world"] == 2
