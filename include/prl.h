@@ -327,6 +327,27 @@ typedef struct {
 } prl_engine_state;
 int prl_advance_state(const prl_engine_state* state, prl_stream_t stream);
 
+/* ---- tensor parallelism inside one engine (BASELINE config 4: Qwen2.5-32B, TP=2; the reference passes
+ * tensor-parallel-size to vLLM, world.py:56-59, which all-reduces twice per layer with NCCL/custom all-reduce).
+ * Here the row-parallel GEMMs (o_proj, down_proj) store their fp32 partial tiles into the local AND the peer GPU's
+ * reduction buffer in their epilogue (prl_gemm_bf16_splitk_peer: the all-reduce is fused into the GEMM over NVLink
+ * peer memory); the consumer (prl_residual_rmsnorm) then reduces tp x split slots in a fixed order, so both ranks
+ * compute bit-identical residual streams.  Ordering between the GPUs uses counters in peer memory:
+ *   prl_tp_signal(peer counter)        after this rank's P2P stores (stream order + system fence)
+ *   prl_tp_wait(local counter, epoch, signals_per_step, k)   before consuming the peer's k-th delivery of the step
+ *   prl_tp_epoch(epoch)                once per token step.
+ * The vocab-parallel head exchanges 16 sampler partials per row instead of logits (prl_sample_partials with a
+ * vocabulary offset, prl_weights_push of the partials, prl_sample_finalize over both groups). */
+int prl_gemm_bf16_splitk_peer(const void* W, const void* X, int64_t M, int64_t N, int64_t K, int32_t split_k,
+                              float* partials, float* peer_partials, prl_stream_t stream);
+int prl_tp_signal(void* peer_flag, prl_stream_t stream);
+int prl_tp_wait(const void* flag, const void* epoch, int32_t signals_per_step, int32_t k, prl_stream_t stream);
+int prl_tp_epoch(void* epoch, prl_stream_t stream);
+int prl_sample_partials(const float* logits, int32_t B, int32_t V, float temperature, int32_t greedy, uint64_t seed,
+                        uint32_t step, int32_t vocab_offset, void* partials /*[B][16] x 32 B*/, prl_stream_t stream);
+int prl_sample_finalize(const void* partials /*[n_groups][B][16]*/, int32_t B, int32_t n_groups, int32_t* out_ids,
+                        float* out_logprobs, prl_stream_t stream);
+
 /* ======================================================================= *
  * Hot path (3): in-flight weight update as a one-shot NVLink P2P copy
  *   replaces WeightUpdateManager.send_weight_update (pipelinerl/finetune_loop.py:205-292),

@@ -138,6 +138,14 @@ _SIGNATURES = {
     "prl_sample_logprob": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_uint64,
                                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "prl_advance_state": (C.c_int, [C.POINTER(EngineState), C.c_void_p]),
+    "prl_gemm_bf16_splitk_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    "prl_tp_signal": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "prl_tp_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "prl_tp_epoch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "prl_sample_partials": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_uint64, C.c_uint32,
+                                      C.c_int32, C.c_void_p, C.c_void_p]),
+    "prl_sample_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "prl_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "prl_ipc_free": (C.c_int, [C.c_void_p]),
     "prl_ipc_export": (C.c_int, [C.c_void_p, C.c_char_p]),

@@ -218,12 +218,13 @@ __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
 
 constexpr int kSampleParts = 16;   // CTAs per row: 64 rows x 16 = 1024 CTAs keep every SM busy
 constexpr int kSampleThreads = 256;
-struct SamplePartial { float m, s, v; int i; };
+struct SamplePartial { float m, s, v, z; int i; int pad[3]; };  // z = logit/T of the best key (logprob without re-reading logits)
 
 // phase 1: each CTA scans a contiguous 1/16 of the vocabulary of one row
 __global__ void __launch_bounds__(kSampleThreads) sample_partial_kernel(const float* __restrict__ logits, int V,
                                                                        float inv_temp, int greedy, uint64_t seed,
-                                                                       uint32_t step, SamplePartial* __restrict__ part) {
+                                                                       uint32_t step, int vocab_offset,
+                                                                       SamplePartial* __restrict__ part) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x, pi = blockIdx.y;
@@ -232,11 +233,16 @@ __global__ void __launch_bounds__(kSampleThreads) sample_partial_kernel(const fl
   const int lo = pi * per, hi = (lo + per < V) ? lo + per : V;
   float m = -INFINITY, s = 0.f;
   ArgMax best{-INFINITY, 0x7fffffff};
+  float best_z = 0.f;
   for (int i = lo + threadIdx.x; i < hi; i += kSampleThreads) {
     const float zi = z[i] * inv_temp;
     if (zi > m) { s = s * __expf(m - zi) + 1.f; m = zi; } else { s += __expf(zi - m); }
-    const float key = greedy ? zi : zi + gumbel(seed, step, (uint32_t)b, (uint32_t)i);
-    best = better(best, ArgMax{key, i});
+    const int gid = vocab_offset + i;   // global vocabulary id (vocab-parallel head: this rank owns a slice)
+    const float key = greedy ? zi : zi + gumbel(seed, step, (uint32_t)b, (uint32_t)gid);
+    const ArgMax cand{key, gid};
+    const ArgMax nb = better(best, cand);
+    if (nb.i != best.i) best_z = zi;
+    best = nb;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -245,46 +251,87 @@ __global__ void __launch_bounds__(kSampleThreads) sample_partial_kernel(const fl
     s = (m == -INFINITY ? 0.f : s * __expf(m - mm)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mm));
     m = mm;
     ArgMax o2{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
-    best = better(best, o2);
+    const float z2 = __shfl_xor_sync(0xffffffffu, best_z, o);
+    const ArgMax nb = better(best, o2);
+    if (nb.i != best.i) best_z = z2;
+    best = nb;
   }
-  __shared__ float s_m[8], s_s[8], s_v[8];
+  __shared__ float s_m[8], s_s[8], s_v[8], s_z[8];
   __shared__ int s_i[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { s_m[warp] = m; s_s[warp] = s; s_v[warp] = best.v; s_i[warp] = best.i; }
+  if (lane == 0) { s_m[warp] = m; s_s[warp] = s; s_v[warp] = best.v; s_i[warp] = best.i; s_z[warp] = best_z; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float M = -INFINITY, S = 0.f;
+    float M = -INFINITY, S = 0.f, bz = 0.f;
     ArgMax bb{-INFINITY, 0x7fffffff};
     for (int w = 0; w < kSampleThreads / 32; ++w) {
       const float mm = fmaxf(M, s_m[w]);
       S = (M == -INFINITY ? 0.f : S * __expf(M - mm)) + (s_m[w] == -INFINITY ? 0.f : s_s[w] * __expf(s_m[w] - mm));
       M = mm;
-      bb = better(bb, ArgMax{s_v[w], s_i[w]});
+      const ArgMax nb = better(bb, ArgMax{s_v[w], s_i[w]});
+      if (nb.i != bb.i) bz = s_z[w];
+      bb = nb;
     }
-    part[b * kSampleParts + pi] = SamplePartial{M, S, bb.v, bb.i};
+    SamplePartial out;
+    out.m = M; out.s = S; out.v = bb.v; out.z = bz; out.i = bb.i; out.pad[0] = out.pad[1] = out.pad[2] = 0;
+    part[b * kSampleParts + pi] = out;
   }
 }
 
-// phase 2: merge the 16 partials of a row (fixed order), emit id and log-probability
-__global__ void sample_finalize_kernel(const float* __restrict__ logits, int V, float inv_temp, int B,
-                                       const SamplePartial* __restrict__ part, int32_t* __restrict__ out_ids,
-                                       float* __restrict__ out_logprobs) {
+// phase 2: merge the partials of a row — 16 per vocabulary slice, `n_groups` slices ([group][B][16]; one group
+// unless the head is vocab-parallel over tensor-parallel ranks) — in a fixed order; emit id and log-probability
+__global__ void sample_finalize_kernel(int B, int n_groups, const SamplePartial* __restrict__ part,
+                                       int32_t* __restrict__ out_ids, float* __restrict__ out_logprobs) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  float M = -INFINITY, S = 0.f;
+  float M = -INFINITY, S = 0.f, bz = 0.f;
   ArgMax bb{-INFINITY, 0x7fffffff};
-  for (int k = 0; k < kSampleParts; ++k) {
-    const SamplePartial q = part[b * kSampleParts + k];
-    const float mm = fmaxf(M, q.m);
-    S = (M == -INFINITY ? 0.f : S * __expf(M - mm)) + (q.m == -INFINITY ? 0.f : q.s * __expf(q.m - mm));
-    M = mm;
-    bb = better(bb, ArgMax{q.v, q.i});
-  }
-  const float lse = M + logf(S);
+  for (int g = 0; g < n_groups; ++g)
+    for (int k = 0; k < kSampleParts; ++k) {
+      const SamplePartial q = part[((int64_t)g * B + b) * kSampleParts + k];
+      const float mm = fmaxf(M, q.m);
+      S = (M == -INFINITY ? 0.f : S * __expf(M - mm)) + (q.m == -INFINITY ? 0.f : q.s * __expf(q.m - mm));
+      M = mm;
+      const ArgMax nb = better(bb, ArgMax{q.v, q.i});
+      if (nb.i != bb.i) bz = q.z;
+      bb = nb;
+    }
   out_ids[b] = bb.i;
-  out_logprobs[b] = logits[(int64_t)b * V + bb.i] * inv_temp - lse;
+  out_logprobs[b] = bz - (M + logf(S));
+}
+
+// ---- tensor-parallel synchronisation through peer memory (no NCCL on the token path) -----------------------------
+// signal: after this rank's P2P stores (previous kernels of the stream) bump a counter in the PEER's memory.
+__global__ void tp_signal_kernel(unsigned long long* peer_flag) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    atomicAdd_system(peer_flag, 1ull);
+  }
+}
+// wait: spin until the local counter (bumped by the peer) reaches epoch * per_step + k, i.e. the peer has issued
+// its k-th signal of this token step.  `epoch` counts completed steps on this rank (tp_epoch_kernel).
+__global__ void tp_wait_kernel(const unsigned long long* flag, const unsigned long long* epoch, int per_step, int k) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) {
+    const unsigned long long want = (*epoch) * (unsigned long long)per_step + (unsigned long long)k;
+    const long long t0 = clock64();
+    while (true) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+      if (v >= want) break;
+      if (clock64() - t0 > 20000000000LL) asm volatile("trap;");  // ~10 s: the peer died
+    }
+  }
+}
+__global__ void tp_epoch_kernel(unsigned long long* epoch) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) *epoch += 1ull;
 }
 
 // ---- advance the per-sequence state after a step (device-side, no host round trip) -------------
@@ -389,18 +436,54 @@ extern "C" size_t prl_sample_workspace_bytes(int32_t B) {
   return (size_t)(B < 1 ? 1 : B) * kSampleParts * sizeof(SamplePartial);
 }
 
+// phase 1 only: per-row partials of logits[:, vocab slice] into `partials` ([B][16]); ids are global (offset added)
+extern "C" int prl_sample_partials(const float* logits, int32_t B, int32_t V, float temperature, int32_t greedy,
+                                   uint64_t seed, uint32_t step, int32_t vocab_offset, void* partials,
+                                   prl_stream_t st) {
+  PRL_CHECK_ARG(logits && partials && B >= 1 && V >= 1, "prl_sample_partials: bad argument");
+  PRL_CHECK_ARG(temperature > 0.f, "prl_sample_partials: temperature must be > 0 (use greedy=1 for argmax)");
+  dim3 grid((unsigned)B, kSampleParts);
+  PRL_CUDA(launch_pdl(sample_partial_kernel, grid, dim3(kSampleThreads), 0, (cudaStream_t)st, logits, (int)V,
+                      1.f / temperature, (int)greedy, seed, step, (int)vocab_offset, (SamplePartial*)partials));
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
+// phase 2 only: merge n_groups x 16 partials per row ([group][B][16]) -> ids, logprobs
+extern "C" int prl_sample_finalize(const void* partials, int32_t B, int32_t n_groups, int32_t* out_ids,
+                                   float* out_logprobs, prl_stream_t st) {
+  PRL_CHECK_ARG(partials && out_ids && out_logprobs && B >= 1 && n_groups >= 1, "prl_sample_finalize: bad argument");
+  PRL_CUDA(launch_pdl(sample_finalize_kernel, dim3((B + 63) / 64), dim3(64), 0, (cudaStream_t)st, (int)B, (int)n_groups,
+                      (const SamplePartial*)partials, out_ids, out_logprobs));
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
 extern "C" int prl_sample_logprob(const float* logits, int32_t B, int32_t V, float temperature, int32_t greedy,
                                   uint64_t seed, uint32_t step, int32_t* out_ids, float* out_logprobs,
                                   void* workspace, size_t workspace_bytes, prl_stream_t st) {
-  PRL_CHECK_ARG(logits && out_ids && out_logprobs && workspace && B >= 1 && V >= 1, "prl_sample_logprob: bad argument");
-  PRL_CHECK_ARG(temperature > 0.f, "prl_sample_logprob: temperature must be > 0 (use greedy=1 for argmax)");
-  PRL_CHECK_ARG(workspace_bytes >= prl_sample_workspace_bytes(B), "prl_sample_logprob: workspace too small");
-  dim3 grid((unsigned)B, kSampleParts);
-  PRL_CUDA(launch_pdl(sample_partial_kernel, grid, dim3(kSampleThreads), 0, (cudaStream_t)st, logits, (int)V,
-                      1.f / temperature, (int)greedy, seed, step, (SamplePartial*)workspace));
+  PRL_CHECK_ARG(workspace && workspace_bytes >= prl_sample_workspace_bytes(B), "prl_sample_logprob: workspace too small");
+  int rc = prl_sample_partials(logits, B, V, temperature, greedy, seed, step, 0, workspace, st);
+  if (rc) return rc;
+  return prl_sample_finalize(workspace, B, 1, out_ids, out_logprobs, st);
+}
+
+extern "C" int prl_tp_signal(void* peer_flag, prl_stream_t st) {
+  PRL_CHECK_ARG(peer_flag, "prl_tp_signal: NULL flag");
+  PRL_CUDA(launch_pdl(tp_signal_kernel, dim3(1), dim3(32), 0, (cudaStream_t)st, (unsigned long long*)peer_flag));
   PRL_LAUNCH_CHECK();
-  PRL_CUDA(launch_pdl(sample_finalize_kernel, dim3((B + 63) / 64), dim3(64), 0, (cudaStream_t)st, logits, (int)V,
-                      1.f / temperature, (int)B, (const SamplePartial*)workspace, out_ids, out_logprobs));
+  return PRL_OK;
+}
+extern "C" int prl_tp_wait(const void* flag, const void* epoch, int32_t signals_per_step, int32_t k, prl_stream_t st) {
+  PRL_CHECK_ARG(flag && epoch && signals_per_step >= 1 && k >= 1 && k <= signals_per_step, "prl_tp_wait: bad argument");
+  PRL_CUDA(launch_pdl(tp_wait_kernel, dim3(1), dim3(32), 0, (cudaStream_t)st, (const unsigned long long*)flag,
+                      (const unsigned long long*)epoch, (int)signals_per_step, (int)k));
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+extern "C" int prl_tp_epoch(void* epoch, prl_stream_t st) {
+  PRL_CHECK_ARG(epoch, "prl_tp_epoch: NULL counter");
+  PRL_CUDA(launch_pdl(tp_epoch_kernel, dim3(1), dim3(32), 0, (cudaStream_t)st, (unsigned long long*)epoch));
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }

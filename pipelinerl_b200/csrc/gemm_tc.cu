@@ -90,6 +90,7 @@ struct GemmParams {
   int split_k;
   int has_lo;
   float* partials;    // [split_k, M, N]
+  float* peer_partials;  // same layout in a tensor-parallel peer's memory (P2P stores), or NULL
   // fused head epilogue (logits never reach HBM): temperature, teacher-forcing targets, sampling
   int tiled;          // weight tile (n_tile, kb) is the contiguous 16 KB block number n_tile*kblocks + kb
   int head;
@@ -245,6 +246,9 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
     if constexpr (!kHead) {
       // ---- TMEM -> registers -> fp32 partial tile ----
       float* out = p.partials + ((int64_t)split * p.M + m0) * p.N + feat;
+      // tensor-parallel row-parallel GEMM: the partial sums are ALSO stored straight into the peer GPU's reduction
+      // buffer over NVLink, so the "all-reduce" is this epilogue plus the consumer's ordinary split reduction
+      float* out_peer = p.peer_partials ? p.peer_partials + ((int64_t)split * p.M + m0) * p.N + feat : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < kNTile; c0 += kChunk) {
         uint32_t r[kChunk];
@@ -260,6 +264,11 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
 #pragma unroll
           for (int j = 0; j < kChunk; ++j)
             if (c0 + j < m_valid) out[(int64_t)(c0 + j) * p.N] = __uint_as_float(r[j]);  // 32 lanes -> 128 B row segment
+          if (out_peer) {
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j)
+              if (c0 + j < m_valid) out_peer[(int64_t)(c0 + j) * p.N] = __uint_as_float(r[j]);
+          }
         }
       }
     } else {
@@ -436,8 +445,22 @@ extern "C" int prl_gemm_auto_split_k(int64_t M, int64_t N, int64_t K) {
   return best;
 }
 
+static int gemm_splitk_impl(const void* W, const void* W_lo, const void* X, int64_t M, int64_t N, int64_t K,
+                            int32_t split_k, float* partials, float* peer_partials, prl_stream_t stream_);
+
 extern "C" int prl_gemm_bf16_splitk(const void* W, const void* W_lo, const void* X, int64_t M, int64_t N, int64_t K,
                                     int32_t split_k, float* partials, prl_stream_t stream_) {
+  return gemm_splitk_impl(W, W_lo, X, M, N, K, split_k, partials, nullptr, stream_);
+}
+
+extern "C" int prl_gemm_bf16_splitk_peer(const void* W, const void* X, int64_t M, int64_t N, int64_t K, int32_t split_k,
+                                         float* partials, float* peer_partials, prl_stream_t stream_) {
+  PRL_CHECK_ARG(peer_partials, "prl_gemm_bf16_splitk_peer: NULL peer buffer");
+  return gemm_splitk_impl(W, nullptr, X, M, N, K, split_k, partials, peer_partials, stream_);
+}
+
+static int gemm_splitk_impl(const void* W, const void* W_lo, const void* X, int64_t M, int64_t N, int64_t K,
+                            int32_t split_k, float* partials, float* peer_partials, prl_stream_t stream_) {
   PRL_CHECK_ARG(W && X && partials, "prl_gemm_bf16_splitk: NULL argument");
   PRL_CHECK_ARG(M >= 1 && N >= 1 && K >= 8 && K % 8 == 0, "prl_gemm_bf16_splitk: need M,N >= 1 and K %% 8 == 0 (M=%lld N=%lld K=%lld)",
                 (long long)M, (long long)N, (long long)K);
@@ -447,6 +470,7 @@ extern "C" int prl_gemm_bf16_splitk(const void* W, const void* W_lo, const void*
   const int nt = pick_ntile(M);
   GemmParams p = {};
   p.M = M; p.N = N; p.K = K; p.kblocks = kblocks; p.split_k = split_k; p.has_lo = W_lo ? 1 : 0; p.partials = partials;
+  p.peer_partials = peer_partials;
   p.tiled = g_tiled_weights;
   CUtensorMap tw, twl, tx;
   int rc = make_weight_tmap(&tw, W, N, K, p.tiled);

@@ -101,7 +101,7 @@ class DecodeEngine:
         self.q = torch.zeros(B, cfg.q_size, dtype=torch.bfloat16, device=d)
         self.attn_out = torch.zeros(B, cfg.q_size, dtype=torch.bfloat16, device=d)
         self.act = torch.zeros(B, I, dtype=torch.bfloat16, device=d)
-        self.logits = torch.zeros(B, cfg.vocab_size, dtype=torch.float32, device=d)
+        self.logits = torch.zeros(B, cfg.head_rows, dtype=torch.float32, device=d)
         # HF rotary: inv_freq = 1 / theta^(arange(0, d, 2) / d) in fp32
         self.inv_freq = (1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, dtype=torch.int64).float()
                                                    / cfg.head_dim))).to(d)
@@ -138,7 +138,7 @@ class DecodeEngine:
         cfg, B = self.cfg, self.B
         shapes = {"qkv": (cfg.qkv_size, cfg.hidden_size), "o": (cfg.hidden_size, cfg.q_size),
                   "gate_up": (2 * cfg.intermediate_size, cfg.hidden_size),
-                  "down": (cfg.hidden_size, cfg.intermediate_size), "head": (cfg.vocab_size, cfg.hidden_size)}
+                  "down": (cfg.hidden_size, cfg.intermediate_size), "head": (cfg.head_rows, cfg.hidden_size)}
         self.split_k = {k: int(self.lib.prl_gemm_auto_split_k(B, n, kk)) for k, (n, kk) in shapes.items()}
         self.split_k["head"] = 1  # the sampler reads plain logits
         need = max(self.split_k[k] * B * shapes[k][0] for k in ("qkv", "o", "gate_up", "down"))
@@ -224,7 +224,7 @@ class DecodeEngine:
                 _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), self.split_k["down"], B, H, a.ptr(nxt), cfg.rms_eps,
                                                     self.h.data_ptr(), self.x.data_ptr(), None, 0, st))
         if not self.fused_head:
-            self._gemm("lm_head.weight", self.x, cfg.vocab_size, H, 1, self.logits,
+            self._gemm("lm_head.weight", self.x, cfg.head_rows, H, 1, self.logits,
                        lo="lm_head.weight_lo" if cfg.fp32_head else None)
 
     def _sample_and_advance(self) -> None:
@@ -239,7 +239,7 @@ class DecodeEngine:
             self._state.ignore_eos = int(self.ignore_eos)
             _lib.check(lib.prl_advance_state(C.byref(self._state), st))
             return
-        _lib.check(lib.prl_sample_logprob(self.logits.data_ptr(), self.B, self.cfg.vocab_size, float(self.temperature),
+        _lib.check(lib.prl_sample_logprob(self.logits.data_ptr(), self.B, self.cfg.head_rows, float(self.temperature),
                                           int(self.greedy), self.seed, self.step_count, self.sampled.data_ptr(),
                                           self.sampled_lp.data_ptr(), self.sample_ws.data_ptr(),
                                           self.sample_ws.numel(), st))

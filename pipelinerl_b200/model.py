@@ -28,6 +28,7 @@ class ModelConfig:
     rms_eps: float = 1e-6
     qkv_bias: bool = True
     fp32_head: bool = False  # keep a bf16 residual of the head (W = hi + lo): fp32-equivalent lm_head
+    lm_head_rows: int | None = None  # vocabulary rows of THIS shard's lm_head (vocab-parallel head under TP)
 
     @property
     def q_size(self) -> int:
@@ -40,6 +41,23 @@ class ModelConfig:
     @property
     def qkv_size(self) -> int:
         return self.q_size + 2 * self.kv_size
+
+    @property
+    def head_rows(self) -> int:
+        return self.lm_head_rows if self.lm_head_rows is not None else self.vocab_size
+
+    def shard(self, tp: int) -> "ModelConfig":
+        """Per-rank configuration under tensor parallelism: heads, MLP width and lm_head rows divided by tp
+        (column-parallel qkv / gate_up / head, row-parallel o_proj / down_proj); embeddings and norms replicated."""
+        from dataclasses import replace
+        if tp == 1:
+            return self
+        for what, v in (("q heads", self.num_q_heads), ("kv heads", self.num_kv_heads),
+                        ("intermediate", self.intermediate_size), ("vocab", self.vocab_size)):
+            if v % tp:
+                raise ValueError(f"{what} ({v}) not divisible by tp={tp}")
+        return replace(self, num_q_heads=self.num_q_heads // tp, num_kv_heads=self.num_kv_heads // tp,
+                       intermediate_size=self.intermediate_size // tp, lm_head_rows=self.vocab_size // tp)
 
     @staticmethod
     def qwen2_5_7b(**kw) -> "ModelConfig":
@@ -86,9 +104,9 @@ def fused_shapes(cfg: ModelConfig) -> list[tuple[str, tuple[int, ...]]]:
         out.append((p + "down_proj.weight", (H, I)))
     out.append(("embed_tokens.weight", (cfg.vocab_size, H)))
     out.append(("norm.weight", (H,)))
-    out.append(("lm_head.weight", (cfg.vocab_size, H)))
+    out.append(("lm_head.weight", (cfg.head_rows, H)))
     if cfg.fp32_head:
-        out.append(("lm_head.weight_lo", (cfg.vocab_size, H)))
+        out.append(("lm_head.weight_lo", (cfg.head_rows, H)))
     return out
 
 
@@ -199,3 +217,25 @@ class ParamArena:
 
     def hf_state_dict(self) -> dict[str, torch.Tensor]:
         return {hf: self.view(fused)[r0:r0 + rn] for hf, (fused, r0, rn) in self.layout.hf_slices().items()}
+
+
+def shard_fused_weights(cfg: ModelConfig, full: dict[str, torch.Tensor], rank: int, tp: int) -> dict[str, torch.Tensor]:
+    """Slice full fused tensors (names of fused_shapes(cfg)) into rank `rank`'s tensor-parallel shard."""
+    loc = cfg.shard(tp)
+    d, out = cfg.head_dim, {}
+    ql, kl, I, Il = loc.q_size, loc.kv_size, cfg.intermediate_size, loc.intermediate_size
+    for name, t in full.items():
+        if name.endswith("qkv_proj.weight") or name.endswith("qkv_proj.bias"):
+            q, k, v = t[:cfg.q_size], t[cfg.q_size:cfg.q_size + cfg.kv_size], t[cfg.q_size + cfg.kv_size:]
+            out[name] = torch.cat([q[rank * ql:(rank + 1) * ql], k[rank * kl:(rank + 1) * kl], v[rank * kl:(rank + 1) * kl]])
+        elif name.endswith("o_proj.weight"):
+            out[name] = t[:, rank * ql:(rank + 1) * ql].contiguous()
+        elif name.endswith("gate_up_proj.weight"):
+            out[name] = torch.cat([t[rank * Il:(rank + 1) * Il], t[I + rank * Il:I + (rank + 1) * Il]])
+        elif name.endswith("down_proj.weight"):
+            out[name] = t[:, rank * Il:(rank + 1) * Il].contiguous()
+        elif name.startswith("lm_head.weight"):
+            out[name] = t[rank * loc.head_rows:(rank + 1) * loc.head_rows]
+        else:
+            out[name] = t
+    return out

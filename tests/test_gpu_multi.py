@@ -37,3 +37,16 @@ def test_two_gpu_sharded_adamw_exchange_matches_oracle():
     assert res.returncode == 0, res.stderr[-3000:]
     out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
     assert out["ok"] and out["world"] == 2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_tensor_parallel_engine_matches_oracle():
+    """TP=2 engine (GEMM epilogue stores partials into the peer's reduction buffer, counters in peer memory, sampler
+    partial exchange) == single-model oracle; both ranks sample identical tokens."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29585")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29585", str(ROOT / "tools" / "tp_bench.py"),
+                          "--check"], capture_output=True, text=True, env=env, timeout=900)
+    assert res.returncode == 0, res.stderr[-3000:]
+    out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["ok"]
