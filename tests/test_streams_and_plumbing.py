@@ -129,3 +129,19 @@ def test_dp_gradient_allreduce_gloo_world2(tmp_path):
     assert res.returncode == 0, res.stderr[-2000:]
     got = json.loads([l for l in res.stdout.splitlines() if l.startswith("[")][-1])
     assert got == [3.0 * i for i in range(10)]
+
+
+def test_trainer_state_follows_topic(tmp_path):
+    from pipelinerl_b200.state import TrainerState
+    from pipelinerl_b200.weights import SamplesProcessed, TrainingDone, TRAINER_TOPIC
+    spec = streams.SingleStreamSpec(exp_path=tmp_path, topic=TRAINER_TOPIC)
+    with streams.write_to_streams(spec) as w:
+        w.write(SamplesProcessed(samples_processed=5))
+        st = TrainerState(tmp_path)
+        st.start_listening()
+        assert st.wait_for_processed_samples() == 5
+        w.write(WeightUpdateSuccess(version=16))
+        assert st.wait_for_model_version() == 16
+        w.write(TrainingDone())
+        assert st.wait_for_training_done(timeout=5) and st.training_done
+        st.stop()
