@@ -229,6 +229,9 @@ int prl_gemm_set_smem_budget_kb(int32_t kb);
 /* Weight layout switch: 0 = row-major [N,K]; 1 = contiguous 16 KB tiles [N/128][K/64][128][64] (one sequential
  * TMA box per tile; needs N % 128 == 0, K % 64 == 0). */
 int prl_gemm_set_tiled_weights(int32_t on);
+/* M_tok > 128 (chunked prefill / scoring / learner shapes): 1 (default) = CTA-pair kernel, one
+ * tcgen05.mma.cta_group::2 256x256 tile per (2,1,1) cluster; 0 = the single-CTA 128x256 kernel. */
+int prl_gemm_set_cta_pair(int32_t on);
 int prl_gemm_bf16_splitk(const void* W, const void* W_lo /*or NULL*/, const void* X,
                          int64_t M, int64_t N, int64_t K, int32_t split_k /*0 = auto*/,
                          float* partials, prl_stream_t stream);

@@ -391,6 +391,152 @@ int launch_gemm(const CUtensorMap& tw, const CUtensorMap& twl, const CUtensorMap
   return PRL_OK;
 }
 
+// ------------------------------------------------------------------------------------
+// CTA-pair variant for compute-bound shapes (chunked prefill, scoring, learner forward: M_tok > 128).
+// A (2,1,1) cluster owns a 256-feature x 256-token output tile: each CTA stages its own 128 weight rows and
+// 128 of the 256 token rows per k-block (32 KB/stage/CTA instead of 48 KB for the same math), the leader issues
+// ONE tcgen05.mma.cta_group::2 (UMMA 256x256x16) per K=16 slice, and each CTA's TMEM receives the 128 features
+// it staged x all 256 tokens.  Per-SM shared-memory operand traffic per flop is halved relative to cta_group::1.
+// ------------------------------------------------------------------------------------
+constexpr int k2TokTile = 256;                       // tokens per CTA pair (UMMA N)
+constexpr int k2StageBytes = 2 * kBlockM * kBlockK * 2;  // 16 KB weights + 16 KB tokens per CTA
+static int g_use_2cta = 1;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x, GemmParams p,
+                 int n_stages) {
+  extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + (uint32_t)(n_stages * k2StageBytes);
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(n_stages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (uint32_t)(2 * n_stages);
+  const uint32_t tmem_slot = tmem_full_bar + 8u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int pair = (int)blockIdx.x >> 1;
+  const int m_tiles = (int)((p.M + k2TokTile - 1) / k2TokTile);
+  const int n0 = (pair / m_tiles) * (2 * kBlockM) + (int)rank * kBlockM;  // first output feature of THIS CTA
+  const int m0 = (pair % m_tiles) * k2TokTile;                            // first token of the pair
+  const int split = blockIdx.y;
+  const int kb_begin = (int)(((int64_t)p.kblocks * split) / p.split_k);
+  const int kb_end = (int)(((int64_t)p.kblocks * (split + 1)) / p.split_k);
+  const int n_kb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      ptx::mbar_init(full_bar(s), 2);   // leader's arrive.expect_tx + the peer's remote arrive (only rank 0's copy is used)
+      ptx::mbar_init(empty_bar(s), 1);  // multicast tcgen05.commit
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+    ptx::prefetch_tensormap(&tm_w);
+    ptx::prefetch_tensormap(&tm_x);
+  }
+  ptx::cluster_sync();  // both CTAs' barriers exist before any remote arrive / TMA completion / multicast commit
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(tmem_slot, k2TokTile);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync();
+  ptx::tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      pdl_wait();
+      const uint64_t w_hint = m_tiles > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;  // token tiles re-read the weights via L2
+      for (int i = 0; i < n_kb; ++i) {
+        const int s = i % n_stages;
+        const uint32_t ph = (uint32_t)((i / n_stages) & 1);
+        ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+        if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(s), 2u * (uint32_t)k2StageBytes);
+        else ptx::mbar_arrive_remote(full_bar(s), 0);
+        const uint32_t a_dst = smem_base + (uint32_t)(s * k2StageBytes);
+        const int kcoord = (kb_begin + i) * kBlockK;
+        ptx::tma_load_2d_2sm(a_dst, &tm_w, kcoord, n0, full_bar(s), w_hint);
+        ptx::tma_load_2d_2sm(a_dst + kBlockM * kBlockK * 2, &tm_x, kcoord, m0 + (int)rank * kBlockM, full_bar(s),
+                             ptx::kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(2 * kBlockM, k2TokTile);
+      for (int i = 0; i < n_kb; ++i) {
+        const int s = i % n_stages;
+        const uint32_t ph = (uint32_t)((i / n_stages) & 1);
+        ptx::mbar_wait(full_bar(s), ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t a_addr = smem_base + (uint32_t)(s * k2StageBytes);
+        const uint64_t a_desc = ptx::make_kmajor_sw128_desc(a_addr);
+        const uint64_t b_desc = ptx::make_kmajor_sw128_desc(a_addr + kBlockM * kBlockK * 2);
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          ptx::mma_bf16_ss_2sm(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                               (i > 0 || k > 0) ? 1u : 0u);
+        ptx::tc_commit_2sm(empty_bar(s), 3);  // both CTAs' slots
+      }
+      ptx::tc_commit_2sm(tmem_full_bar, 3);
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue (both CTAs: 128 features x 256 tokens each) =====
+    pdl_wait();
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after_sync();
+    const int q = warp & 3;
+    const int feat = n0 + q * 32 + lane;
+    const int m_valid = (int)((p.M - m0) < k2TokTile ? (p.M - m0) : k2TokTile);
+    const bool feat_ok = feat < p.N;
+    float* out = p.partials + ((int64_t)split * p.M + m0) * p.N + feat;
+#pragma unroll 1
+    for (int c0 = 0; c0 < k2TokTile; c0 += 32) {
+      if (c0 >= m_valid) break;
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      ptx::tmem_ld_wait();
+      if (n_kb == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (feat_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < m_valid) out[(int64_t)(c0 + j) * p.N] = __uint_as_float(r[j]);
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync();  // neither CTA may release TMEM (or exit) while the pair's MMAs / the peer's reads are in flight
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc_2sm(tmem_base, k2TokTile);
+  }
+}
+
+int launch_gemm_pair(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, cudaStream_t stream) {
+  int n_stages = 6;
+  const int smem = n_stages * k2StageBytes + 1024 + 8 * (2 * n_stages + 2) + 16;
+  static int configured = 0;
+  if (!configured) {
+    PRL_CUDA(cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = 1;
+  }
+  const int64_t pairs = ((p.N + 2 * kBlockM - 1) / (2 * kBlockM)) * ((p.M + k2TokTile - 1) / k2TokTile);
+  dim3 grid((unsigned)(2 * pairs), (unsigned)p.split_k, 1);
+  PRL_CUDA(launch_pdl(gemm_pair_kernel, grid, dim3(kThreads), (size_t)smem, stream, tw, tx, p, n_stages));
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
 // Weight tensor map.  Row-major: [N rows, K cols].  Tiled: the same bytes seen as [(N/128)*(K/64)*128 rows, 64 cols]
 // — tile (n_tile, kb) is one contiguous 16 KB block, fetched by a single sequential TMA box.
 int make_weight_tmap(CUtensorMap* out, const void* W, int64_t N, int64_t K, int tiled) {
@@ -419,6 +565,11 @@ using namespace prl;
 extern "C" int prl_gemm_set_smem_budget_kb(int32_t kb) {
   PRL_CHECK_ARG(kb >= 48 && kb <= 220, "prl_gemm_set_smem_budget_kb: 48..220 KB");
   g_smem_budget = kb * 1024;
+  return PRL_OK;
+}
+
+extern "C" int prl_gemm_set_cta_pair(int32_t on) {
+  g_use_2cta = on ? 1 : 0;
   return PRL_OK;
 }
 
@@ -480,6 +631,12 @@ static int gemm_splitk_impl(const void* W, const void* W_lo, const void* X, int6
   rc = make_tmap_2d_bf16(&tx, X, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kBlockK, (uint32_t)nt);
   if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (nt == 256 && g_use_2cta && !W_lo && !peer_partials && !p.tiled) {
+    // token box of 128 rows: each CTA of the pair stages half of the 256-token tile
+    rc = make_tmap_2d_bf16(&tx, X, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kBlockK, kBlockM);
+    if (rc) return rc;
+    return launch_gemm_pair(tw, tx, p, stream);
+  }
   switch (nt) {
     case 16: return launch_gemm<16>(tw, twl, tx, p, stream);
     case 32: return launch_gemm<32>(tw, twl, tx, p, stream);

@@ -23,6 +23,8 @@ def run_gemm(W, X, W_lo=None, split_k=0):
 SHAPES = [
     (1, 128, 64, 1), (16, 256, 128, 2), (37, 300, 200, 1), (64, 4608, 3584, 0), (64, 3584, 18944, 0),
     (33, 1152, 512, 3), (128, 640, 1024, 2), (200, 384, 256, 1), (300, 256, 192, 1), (64, 37888, 3584, 0),
+    # M > 128 runs the CTA-pair (tcgen05 cta_group::2) kernel: ragged token / feature / k tails, split-K, many k-blocks
+    (129, 128, 64, 1), (513, 777, 200, 1), (256, 512, 4096, 2), (1024, 4608, 3584, 1), (700, 1000, 1288, 3),
 ]
 
 
@@ -37,6 +39,23 @@ def test_gemm_matches_fp32_matmul(cuda_device, M, N, K, split_k):
     want = X.float() @ W.float().t()
     scale = want.abs().max().item()
     assert (got - want).abs().max().item() <= 2e-4 * scale + 1e-6
+
+
+def test_cta_pair_kernel_agrees_with_single_cta(cuda_device):
+    """Same operands through both M>128 kernels: fp32 accumulation order per element is identical (k ascending),
+    so the two tiles must agree BITWISE."""
+    from pipelinerl_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11)
+    X = torch.randn(600, 1536, generator=g).to(torch.bfloat16).to(cuda_device)
+    W = (torch.randn(1000, 1536, generator=g) * 0.05).to(torch.bfloat16).to(cuda_device)
+    try:
+        _lib.check(lib.prl_gemm_set_cta_pair(0))
+        single = run_gemm(W, X, split_k=2)
+    finally:
+        _lib.check(lib.prl_gemm_set_cta_pair(1))
+    pair = run_gemm(W, X, split_k=2)
+    assert torch.equal(single, pair)
 
 
 def test_gemm_hi_lo_is_fp32_equivalent(cuda_device):
