@@ -232,6 +232,18 @@ int prl_gemm_set_tiled_weights(int32_t on);
 /* M_tok > 128 (chunked prefill / scoring / learner shapes): 1 (default) = CTA-pair kernel, one
  * tcgen05.mma.cta_group::2 256x256 tile per (2,1,1) cluster; 0 = the single-CTA 128x256 kernel. */
 int prl_gemm_set_cta_pair(int32_t on);
+/* Compute-bound GEMM of the learner body / prefill (csrc/gemm_tn.cu), replaces the cuBLAS GEMMs under the HF
+ * Qwen2 forward+backward that rl_step drives (pipelinerl/finetune/rl/__init__.py:190-207, finetune_loop.py:716-725):
+ *     C[M,N] (=|+=) alpha * A[M,K] * B[N,K]^T (+ bias[N]) (+ residual[M,N])
+ * A, B bf16 row-major with row strides lda / ldb (elements, multiples of 8, base 16-byte aligned); C bf16 or fp32
+ * (c_is_f32), `accumulate` (fp32 only) adds into C; bias / residual bf16 or NULL.  Persistent CTA-pair kernel
+ * (tcgen05.mma.cta_group::2, 256x256 tiles, double-buffered TMEM accumulators). */
+int prl_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                void* C, int64_t ldc, int32_t c_is_f32, int32_t accumulate, const void* bias,
+                const void* residual, int64_t ldr, float alpha, prl_stream_t stream);
+/* bf16 [rows, cols] (row stride ld_in) -> [cols, rows] (row stride ld_out): stages the K-major operands of wgrad. */
+int prl_transpose_bf16(const void* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
+                       prl_stream_t stream);
 int prl_gemm_bf16_splitk(const void* W, const void* W_lo /*or NULL*/, const void* X,
                          int64_t M, int64_t N, int64_t K, int32_t split_k /*0 = auto*/,
                          float* partials, prl_stream_t stream);

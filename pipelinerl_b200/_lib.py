@@ -110,6 +110,10 @@ _SIGNATURES = {
     "prl_gemm_set_smem_budget_kb": (C.c_int, [C.c_int32]),
     "prl_gemm_set_tiled_weights": (C.c_int, [C.c_int32]),
     "prl_gemm_set_cta_pair": (C.c_int, [C.c_int32]),
+    "prl_gemm_tn": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                              C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                              C.c_float, C.c_void_p]),
+    "prl_transpose_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "prl_gemm_bf16_splitk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                        C.c_void_p, C.c_void_p]),
     "prl_head_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),

@@ -1,0 +1,354 @@
+// CTA-pair tcgen05 GEMM for the compute-bound shapes of the learner (hot path 2) and of prefill / scoring:
+//
+//   C[M, N] (=|+=) A[M, K] * B[N, K]^T  (+ bias[N]) (+ residual[M, N])     bf16 operands, fp32 accumulation in TMEM
+//
+// replaces the cuBLAS GEMMs behind the HF Qwen2 forward/backward that rl_step drives
+// (pipelinerl/finetune/rl/__init__.py:190-207 forward; finetune_loop.py:716-725 backward): with K-major ("TN")
+// operands the same kernel serves
+//   forward   Y  = X  * W^T            A = X [T, in],        B = W [out, in]
+//   dgrad     dX = dY * W              A = dY [T, out],      B = W^T [in, out]     (transposed weight copy)
+//   wgrad     dW += dY^T * X           A = dY^T [out, T],    B = X^T [in, T]       (fp32 accumulate epilogue)
+//
+// One (2,1,1) cluster owns a 256 x 256 output tile: CTA r stages A rows [128 r, 128 r + 128) and B rows
+// [128 r, 128 r + 128) of the tile per 64-wide k-block (TMA, SWIZZLE_128B, 6-stage ring, 32 KB/stage/CTA), the
+// leader issues tcgen05.mma.cta_group::2 (UMMA 256x256x16), and CTA r's TMEM receives its 128 A-rows x all 256
+// columns, so every epilogue thread owns ONE output row and writes contiguous row segments (16-byte stores).
+// The kernel is persistent: each cluster walks tiles in an L2-friendly order (8 row-tiles x all column tiles per
+// super-group), and the 512 TMEM columns hold TWO accumulators so that the epilogue of tile i overlaps the
+// mainloop of tile i + 1.
+//
+// Tensor-core bound: flops = 2 M N K; algorithmic bytes = 2 (M K + N K) + out bytes.
+#include "prl_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace prl {
+namespace {
+
+constexpr int kTile = 256;      // output tile edge per cluster
+constexpr int kHalf = 128;      // operand rows staged per CTA
+constexpr int kBK = 64;         // bf16 per k-block row = one 128-B swizzle atom
+constexpr int kStages = 6;
+constexpr int kStageBytes = 2 * kHalf * kBK * 2;  // 32 KB
+constexpr int kThreadsTN = 192;
+constexpr int kGroupM = 8;      // row tiles per raster super-group
+
+struct TnParams {
+  int64_t M, N, K;
+  int kblocks;
+  int m_tiles, n_tiles;
+  void* C;
+  int64_t ldc;
+  int c_f32;         // 1: fp32 output, 0: bf16 output
+  int accumulate;    // C += (fp32 only)
+  const __nv_bfloat16* bias;      // [N] or NULL
+  const __nv_bfloat16* residual;  // [M, ldr] or NULL
+  int64_t ldr;
+  float alpha;
+};
+
+__device__ __forceinline__ void tile_coords(int t, const TnParams& p, int& tm, int& tn) {
+  const int per_group = kGroupM * p.n_tiles;
+  const int g = t / per_group;
+  const int first_m = g * kGroupM;
+  const int rows = (p.m_tiles - first_m) < kGroupM ? (p.m_tiles - first_m) : kGroupM;
+  const int r = t - g * per_group;
+  tm = first_m + r % rows;
+  tn = r / rows;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTN, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, TnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + (uint32_t)(kStages * kStageBytes);
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(kStages + s); };
+  auto acc_full_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * kStages + a); };       // MMA -> epilogue
+  auto acc_empty_bar = [&](int a) { return bar_base + 8u * (uint32_t)(2 * kStages + 2 + a); };  // epilogue -> MMA
+  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int n_clusters = (int)gridDim.x >> 1;
+  const int cluster = (int)blockIdx.x >> 1;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(full_bar(s), 2);   // leader expect_tx + peer's remote arrive (rank 0's copy is the one used)
+      ptx::mbar_init(empty_bar(s), 1);  // multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(acc_full_bar(a), 1);   // multicast tcgen05.commit
+      ptx::mbar_init(acc_empty_bar(a), 2);  // one elected epilogue thread of EACH CTA (rank 0's copy is the one used)
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+    ptx::prefetch_tensormap(&tm_a);
+    ptx::prefetch_tensormap(&tm_b);
+  }
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(tmem_slot, 512);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync();
+  ptx::tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      int it = 0;
+      for (int t = cluster; t < total_tiles; t += n_clusters) {
+        int tm, tn;
+        tile_coords(t, p, tm, tn);
+        const int a_row = tm * kTile + (int)rank * kHalf;
+        const int b_row = tn * kTile + (int)rank * kHalf;
+        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (uint32_t)((it / kStages) & 1);
+          ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(s), 2u * (uint32_t)kStageBytes);
+          else ptx::mbar_arrive_remote(full_bar(s), 0);
+          const uint32_t a_dst = smem_base + (uint32_t)(s * kStageBytes);
+          ptx::tma_load_2d_2sm(a_dst, &tm_a, kb * kBK, a_row, full_bar(s), ptx::kEvictNormal);
+          ptx::tma_load_2d_2sm(a_dst + kHalf * kBK * 2, &tm_b, kb * kBK, b_row, full_bar(s), ptx::kEvictNormal);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(kTile, kTile);
+      int it = 0, local = 0;
+      for (int t = cluster; t < total_tiles; t += n_clusters, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_ph = (uint32_t)((local >> 1) & 1);
+        ptx::mbar_wait(acc_empty_bar(acc), acc_ph ^ 1u);  // both CTAs' epilogues have drained this accumulator
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTile);
+        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (uint32_t)((it / kStages) & 1);
+          ptx::mbar_wait(full_bar(s), ph);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_addr = smem_base + (uint32_t)(s * kStageBytes);
+          const uint64_t a_desc = ptx::make_kmajor_sw128_desc(a_addr);
+          const uint64_t b_desc = ptx::make_kmajor_sw128_desc(a_addr + kHalf * kBK * 2);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            ptx::mma_bf16_ss_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                                 (kb > 0 || k > 0) ? 1u : 0u);
+          ptx::tc_commit_2sm(empty_bar(s), 3);
+        }
+        ptx::tc_commit_2sm(acc_full_bar(acc), 3);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue (both CTAs): thread = one output row, 256 columns in 32-column chunks =====
+    const int q = warp & 3;
+    int local = 0;
+    for (int t = cluster; t < total_tiles; t += n_clusters, ++local) {
+      int tm, tn;
+      tile_coords(t, p, tm, tn);
+      const int acc = local & 1;
+      const uint32_t acc_ph = (uint32_t)((local >> 1) & 1);
+      ptx::mbar_wait(acc_full_bar(acc), acc_ph);
+      ptx::tc_fence_after_sync();
+      const int64_t row = (int64_t)tm * kTile + (int64_t)rank * kHalf + q * 32 + lane;
+      const int64_t col0 = (int64_t)tn * kTile;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kTile; c0 += 32) {
+        if (col0 + c0 >= p.N) break;  // uniform across the CTA
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTile + c0), r);
+        ptx::tmem_ld_wait();
+        if (!row_ok) continue;
+        const int64_t col = col0 + c0;
+        const bool full = (col + 32 <= p.N);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || col + j < p.N) v[j] += __bfloat162float(p.bias[col + j]);
+        }
+        if (p.residual) {
+          const __nv_bfloat16* rp = p.residual + row * p.ldr + col;
+          if (full && ((p.ldr & 7) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rp + j);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h[e]);
+                v[j + 2 * e] += f.x;
+                v[j + 2 * e + 1] += f.y;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col + j < p.N) v[j] += __bfloat162float(rp[j]);
+          }
+        }
+        if (p.c_f32) {
+          float* cp = reinterpret_cast<float*>(p.C) + row * p.ldc + col;
+          if (full && ((p.ldc & 3) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (p.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(cp + j);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              *reinterpret_cast<float4*>(cp + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col + j < p.N) cp[j] = p.accumulate ? cp[j] + v[j] : v[j];
+          }
+        } else {
+          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col;
+          if (full && ((p.ldc & 7) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(cp + j) = u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col + j < p.N) cp[j] = __float2bfloat16(v[j]);
+          }
+        }
+      }
+      // this CTA's four epilogue warps are done with the accumulator -> tell the leader's MMA warp
+      ptx::tc_fence_before_sync();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        if (rank == 0) ptx::mbar_arrive(acc_empty_bar(acc));
+        else ptx::mbar_arrive_remote(acc_empty_bar(acc), 0);
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+// bf16 [R, C] -> [C, R]; 64 x 64 tiles through shared memory, 16-byte global accesses on both sides
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t R, int64_t C,
+                                                             int64_t ldi, __nv_bfloat16* __restrict__ out, int64_t ldo) {
+  __shared__ __nv_bfloat16 tile[64][64 + 8];
+  const int64_t r0 = (int64_t)blockIdx.y * 64, c0 = (int64_t)blockIdx.x * 64;
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;  // 8 x 32: each thread moves 8 bf16
+  const bool vec_in = ((ldi & 7) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  const bool vec_out = ((ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll
+  for (int rr = 0; rr < 64; rr += 32) {
+    const int64_t r = r0 + rr + ty, c = c0 + tx * 8;
+    if (r < R) {
+      if (vec_in && c + 8 <= C) {
+        const uint4 u = *reinterpret_cast<const uint4*>(in + r * ldi + c);
+        const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) tile[rr + ty][tx * 8 + e] = h[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (c + e < C) tile[rr + ty][tx * 8 + e] = in[r * ldi + c + e];
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int cc = 0; cc < 64; cc += 32) {
+    const int64_t c = c0 + cc + ty, r = r0 + tx * 8;  // output row = input column
+    if (c < C) {
+      __nv_bfloat16 h[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) h[e] = tile[tx * 8 + e][cc + ty];
+      if (vec_out && r + 8 <= R) {
+        *reinterpret_cast<uint4*>(out + c * ldo + r) = *reinterpret_cast<const uint4*>(h);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (r + e < R) out[c * ldo + r + e] = h[e];
+      }
+    }
+  }
+}
+
+}  // namespace
+}  // namespace prl
+
+using namespace prl;
+
+extern "C" int prl_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                           void* C, int64_t ldc, int32_t c_is_f32, int32_t accumulate, const void* bias,
+                           const void* residual, int64_t ldr, float alpha, prl_stream_t stream_) {
+  PRL_CHECK_ARG(A && B && C, "prl_gemm_tn: NULL argument");
+  PRL_CHECK_ARG(M >= 1 && N >= 1 && K >= 8, "prl_gemm_tn: need M, N >= 1 and K >= 8 (M=%lld N=%lld K=%lld)", (long long)M,
+                (long long)N, (long long)K);
+  PRL_CHECK_ARG(lda >= K && ldb >= K && lda % 8 == 0 && ldb % 8 == 0,
+                "prl_gemm_tn: operand row strides must be >= K and multiples of 8 elements (lda=%lld ldb=%lld K=%lld)",
+                (long long)lda, (long long)ldb, (long long)K);
+  PRL_CHECK_ARG(ldc >= N, "prl_gemm_tn: ldc %lld < N %lld", (long long)ldc, (long long)N);
+  PRL_CHECK_ARG(!accumulate || c_is_f32, "prl_gemm_tn: accumulate needs an fp32 output");
+  PRL_CHECK_ARG(!residual || ldr >= N, "prl_gemm_tn: ldr %lld < N %lld", (long long)ldr, (long long)N);
+  TnParams p = {};
+  p.M = M; p.N = N; p.K = K;
+  p.kblocks = (int)((K + kBK - 1) / kBK);
+  p.m_tiles = (int)((M + kTile - 1) / kTile);
+  p.n_tiles = (int)((N + kTile - 1) / kTile);
+  p.C = C; p.ldc = ldc; p.c_f32 = c_is_f32; p.accumulate = accumulate;
+  p.bias = (const __nv_bfloat16*)bias;
+  p.residual = (const __nv_bfloat16*)residual;
+  p.ldr = ldr;
+  p.alpha = alpha;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d_bf16(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBK, kHalf);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBK, kHalf);
+  if (rc) return rc;
+  const int smem = kStages * kStageBytes + 1024 + 8 * (2 * kStages + 4) + 16;
+  static bool configured = false;
+  if (!configured) {
+    PRL_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
+  int clusters = num_sms() / 2;
+  if (tiles < clusters) clusters = (int)tiles;
+  gemm_tn_kernel<<<dim3((unsigned)(2 * clusters)), dim3(kThreadsTN), (size_t)smem, (cudaStream_t)stream_>>>(ta, tb, p);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
+extern "C" int prl_transpose_bf16(const void* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
+                                  prl_stream_t stream_) {
+  PRL_CHECK_ARG(in && out, "prl_transpose_bf16: NULL argument");
+  PRL_CHECK_ARG(rows >= 1 && cols >= 1 && ld_in >= cols && ld_out >= rows, "prl_transpose_bf16: bad shape / strides");
+  dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64));
+  PRL_CHECK_ARG(grid.y <= 65535, "prl_transpose_bf16: too many row tiles (%u)", grid.y);
+  transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)in, rows, cols, ld_in,
+                                                                 (__nv_bfloat16*)out, ld_out);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}

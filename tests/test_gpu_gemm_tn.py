@@ -1,0 +1,99 @@
+"""CTA-pair persistent tcgen05 GEMM of the learner body (csrc/gemm_tn.cu) against fp32 torch matmuls of the
+same bf16 operands.  Tolerance: fp32 accumulation of bf16 products (1e-4 of the output scale) plus one bf16
+rounding (2^-8 relative) where the output is bf16."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def gemm_tn(A, B, out_dtype=torch.bfloat16, bias=None, residual=None, acc_into=None, alpha=1.0):
+    from pipelinerl_b200 import _lib
+    lib = _lib.load()
+    M, K = A.shape
+    N = B.shape[0]
+    if acc_into is not None:
+        C = acc_into
+    else:
+        C = torch.full((M, N), float("nan"), dtype=out_dtype, device=A.device)
+    _lib.check(lib.prl_gemm_tn(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, C.data_ptr(), C.stride(0),
+                               int(C.dtype == torch.float32), int(acc_into is not None),
+                               bias.data_ptr() if bias is not None else None,
+                               residual.data_ptr() if residual is not None else None,
+                               residual.stride(0) if residual is not None else 0, alpha, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    return C
+
+
+SHAPES = [(1, 8, 8), (256, 256, 64), (129, 130, 72), (300, 777, 200), (1024, 4608, 3584), (2048, 3584, 18944),
+          (4608, 3584, 4096), (5000, 1000, 1288), (16, 37888, 512), (777, 24, 136)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_tn_f32_out(cuda_device, M, N, K):
+    g = torch.Generator().manual_seed(M * 31 + N * 7 + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
+    B = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).to(cuda_device)
+    got = gemm_tn(A, B, out_dtype=torch.float32)
+    want = A.float() @ B.float().t()
+    assert torch.isfinite(got).all(), "unwritten output"
+    assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item() + 1e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 776, 200), (1024, 4608, 3584), (513, 100, 64)])
+def test_gemm_tn_bf16_bias_residual(cuda_device, M, N, K):
+    g = torch.Generator().manual_seed(5)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
+    B = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).to(cuda_device)
+    bias = torch.randn(N, generator=g).to(torch.bfloat16).to(cuda_device)
+    res = torch.randn(M, N, generator=g).to(torch.bfloat16).to(cuda_device)
+    got = gemm_tn(A, B, bias=bias, residual=res)
+    want = A.float() @ B.float().t() + bias.float() + res.float()
+    scale = want.abs().max().item()
+    assert (got.float() - want).abs().max().item() <= (2e-4 + 2 ** -8) * scale
+    plain = gemm_tn(A, B)
+    assert torch.equal(plain, (A.float() @ B.float().t()).to(torch.bfloat16)) or \
+        (plain.float() - A.float() @ B.float().t()).abs().max().item() <= (2e-4 + 2 ** -8) * scale
+
+
+def test_gemm_tn_accumulates_and_strided_operands(cuda_device):
+    """wgrad form: fp32 C += A * B^T with operands that are column slices of wider buffers."""
+    g = torch.Generator().manual_seed(9)
+    big_a = torch.randn(640, 1024, generator=g).to(torch.bfloat16).to(cuda_device)
+    big_b = torch.randn(384, 1024, generator=g).to(torch.bfloat16).to(cuda_device)
+    A, B = big_a[:, 128:128 + 520], big_b[:, 256:256 + 520]
+    C = torch.randn(640, 384, generator=g).to(cuda_device)
+    want = C + 0.5 * (A.float() @ B.float().t())
+    got = gemm_tn(A, B, acc_into=C, alpha=0.5)
+    assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()
+
+
+def test_gemm_tn_is_deterministic(cuda_device):
+    g = torch.Generator().manual_seed(1)
+    A = torch.randn(3000, 2048, generator=g).to(torch.bfloat16).to(cuda_device)
+    B = torch.randn(1500, 2048, generator=g).to(torch.bfloat16).to(cuda_device)
+    assert torch.equal(gemm_tn(A, B), gemm_tn(A, B))
+
+
+@pytest.mark.parametrize("R,C", [(1, 1), (64, 64), (100, 37), (4096, 3584), (777, 1288)])
+def test_transpose_bf16(cuda_device, R, C):
+    from pipelinerl_b200 import _lib
+    lib = _lib.load()
+    x = torch.randn(R, C, device=cuda_device).to(torch.bfloat16)
+    out = torch.empty(C, R, dtype=torch.bfloat16, device=cuda_device)
+    _lib.check(lib.prl_transpose_bf16(x.data_ptr(), R, C, x.stride(0), out.data_ptr(), out.stride(0), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(out, x.t().contiguous())
+
+
+def test_gemm_tn_rejects_bad_arguments(cuda_device):
+    from pipelinerl_b200 import _lib
+    lib = _lib.load()
+    A = torch.zeros(16, 20, dtype=torch.bfloat16, device=cuda_device)
+    C = torch.zeros(16, 16, dtype=torch.bfloat16, device=cuda_device)
+    rc = lib.prl_gemm_tn(A.data_ptr(), 20, A.data_ptr(), 20, 16, 16, 20, C.data_ptr(), 16, 0, 0, None, None, 0, 1.0,
+                         _lib.stream_ptr())
+    assert rc != 0 and b"multiples of 8" in lib.prl_last_error()
+    rc = lib.prl_gemm_tn(A.data_ptr(), 24, A.data_ptr(), 24, 16, 16, 16, C.data_ptr(), 16, 0, 1, None, None, 0, 1.0,
+                         _lib.stream_ptr())
+    assert rc != 0 and b"accumulate" in lib.prl_last_error()
