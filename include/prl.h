@@ -241,6 +241,34 @@ int prl_gemm_set_cta_pair(int32_t on);
 int prl_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
                 void* C, int64_t ldc, int32_t c_is_f32, int32_t accumulate, const void* bias,
                 const void* residual, int64_t ldr, float alpha, prl_stream_t stream);
+/* =======================================================================
+ * Row-wise kernels of the learner body (csrc/learner_ops.cu): what HF's Qwen2RMSNorm / apply_rotary_pos_emb /
+ * Qwen2MLP activation / embedding and their autograd backward do between the GEMMs of rl_step's model call
+ * (pipelinerl/finetune/rl/__init__.py:190-207; backward finetune_loop.py:716-725).  bf16 activations [T, H]
+ * contiguous unless a row stride is given; fp32 statistics; gradient reductions over tokens ACCUMULATE into fp32
+ * outputs in a fixed order (workspace: prl_rowops_workspace_bytes(row length)).
+ * ======================================================================= */
+size_t prl_rowops_workspace_bytes(int64_t cols);
+int prl_rmsnorm_fwd(const void* x, const void* gamma, int64_t T, int64_t H, float eps, void* y, float* rstd /*[T]*/,
+                    prl_stream_t stream);
+/* dx = (dres or 0) + dRMSNorm(x; gamma, rstd)(dy);  dgamma[H] += sum_t dy * x * rstd */
+int prl_rmsnorm_bwd(const void* x, const void* gamma, const float* rstd, const void* dy, const void* dres /*or NULL*/,
+                    int64_t T, int64_t H, void* dx, float* dgamma, void* workspace, size_t workspace_bytes,
+                    prl_stream_t stream);
+/* out[cols] += column sums of x [T, cols] (row stride ld): bias gradient */
+int prl_colsum_bf16(const void* x, int64_t ld, int64_t T, int64_t cols, float* out, void* workspace,
+                    size_t workspace_bytes, prl_stream_t stream);
+/* rotate heads [0, n_heads) of every row of x [T, ld] in place by sign * pos[t] * inv_freq[i] (pairs (i, i + d/2));
+ * sign = +1 forward, -1 backward (the transpose of a rotation) */
+int prl_rope_inplace(void* x, int64_t ld, int64_t T, int32_t n_heads, int32_t head_dim, const int32_t* pos,
+                     const float* inv_freq /*[head_dim/2]*/, float sign, prl_stream_t stream);
+/* gate_up [T, 2I] = [gate | up] -> act [T, I] = silu(gate) * up, and its backward */
+int prl_silu_mul_fwd(const void* gate_up, int64_t T, int64_t I, void* act, prl_stream_t stream);
+int prl_silu_mul_bwd(const void* gate_up, const void* dact, int64_t T, int64_t I, void* dgate_up, prl_stream_t stream);
+int prl_embed_gather(const void* table, const int64_t* ids, int64_t T, int64_t H, void* out, prl_stream_t stream);
+/* dtable[ids[t]] += dh[t] (fp32 atomics: the one reduction here whose order is not fixed, as in torch) */
+int prl_embed_scatter_add(float* dtable, const int64_t* ids, const void* dh, int64_t T, int64_t H, prl_stream_t stream);
+
 /* bf16 [rows, cols] (row stride ld_in) -> [cols, rows] (row stride ld_out): stages the K-major operands of wgrad. */
 int prl_transpose_bf16(const void* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
                        prl_stream_t stream);

@@ -84,7 +84,10 @@ class FusedAdamW:
                 self.shadow_bf16[off:off + k].copy_(p.detach().reshape(-1))
                 home = self.master if pdt == torch.float32 else self.shadow_bf16
                 p.data = home[off:off + k].view(p.shape)
-                p.grad = self.grad[off:off + k].view(p.shape)
+                if gdt == pdt:
+                    p.grad = self.grad[off:off + k].view(p.shape)
+                # else (bf16 parameters, fp32 gradient arena): torch forbids a .grad of another dtype; producers
+                # that accumulate in fp32 (learner_body.NativeBody) write through grad_view(name) instead
         table = offsets + [self.n]
         self.tensor_offsets = torch.tensor(table, dtype=torch.int64, device=dev)
         flags = [1 if any(tag in n for tag in no_decay) else 0 for n in self.names]
@@ -92,6 +95,14 @@ class FusedAdamW:
         self.workspace = torch.zeros(int(self.lib.prl_adamw_workspace_bytes()), dtype=torch.uint8, device=dev)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.param_groups = [{"lr": lr, "weight_decay": weight_decay, "params": self.params}]
+
+    def grad_view(self, name: str) -> torch.Tensor:
+        i = self.names.index(name)
+        p = self.params[i]
+        return self.grad[self.offsets[i]:self.offsets[i] + p.numel()].view(p.shape)
+
+    def grad_views(self) -> dict[str, torch.Tensor]:
+        return {n: self.grad[o:o + p.numel()].view(p.shape) for n, p, o in zip(self.names, self.params, self.offsets)}
 
     # torch.optim-like surface used by the trainer loop
     def zero_grad(self, set_to_none: bool = False) -> None:

@@ -57,8 +57,12 @@ def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding
         opt = ShardedFusedAdamW(model.named_parameters(), lr=cfg.learning_rate, weight_decay=cfg.weight_decay,
                                 max_grad_norm=cfg.gradient_clipping_threshold, group=dp_group)
     else:
+        native = hasattr(model, "bind")   # learner_model.NativeQwen2: fp32 gradient accumulation in the arena
         opt = FusedAdamW(model.named_parameters(), lr=cfg.learning_rate, weight_decay=cfg.weight_decay,
-                         max_grad_norm=cfg.gradient_clipping_threshold)
+                         max_grad_norm=cfg.gradient_clipping_threshold,
+                         grad_dtype=torch.float32 if native else None)
+        if native:
+            model.bind(opt)
     if weight_manager is not None:
         weight_manager.src = opt.shadow_bf16
     rl_cfg = cfg.rl.model_copy(update={"batch_size": cfg.samples_per_step})
@@ -87,6 +91,8 @@ def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding
             allreduce_gradients(opt.grad, dp_group)   # fp32-parameter path: plain SUM all-reduce, full AdamW per rank
         grad_norm = opt.step()
         opt.zero_grad()
+        if hasattr(model, "after_optimizer_step"):
+            model.after_optimizer_step()
         tm.completed_steps += 1
         tm.grad_norm = float(grad_norm.item())
         tm.train_loss = sum(s.get("loss", 0.0) for s in step_stats)

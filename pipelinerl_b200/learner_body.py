@@ -1,0 +1,289 @@
+"""Native learner body: hand-scheduled forward / backward of the Qwen2 transformer over ONE packed row.
+
+This is the part of hot path 2 that the reference runs as HF eager blocks under autograd with non-reentrant
+gradient checkpointing (pipelinerl/finetune/rl/__init__.py:190-207 forward, finetune_loop.py:716-725 backward,
+conf/finetune/base.yaml:47-50 checkpointing).  Here there is no autograd inside the body:
+
+  forward   per layer: RMSNorm -> qkv GEMM(+bias) -> RoPE -> causal block-diagonal attention -> o GEMM(+residual)
+            -> RMSNorm -> gate_up GEMM -> SiLU*up -> down GEMM(+residual); only each layer's INPUT is kept
+  backward  per layer (reverse): recompute the layer, then dgrad GEMMs against transposed weight copies and wgrad
+            GEMMs that ACCUMULATE IN FP32 straight into the optimizer's gradient arena (no .grad tensors, no
+            autograd accumulation kernels, no per-parameter allocation)
+
+Every GEMM is `prl_gemm_tn` (csrc/gemm_tn.cu, persistent CTA-pair tcgen05 kernel); the K-major operands of wgrad
+are staged by `prl_transpose_bf16`.  The row-wise pieces (RMSNorm, RoPE, SiLU*up, bias / gain reductions, embedding
+scatter) are the kernels of csrc/learner_ops.cu.  Attention inside the learner is the one library call left
+(torch SDPA = a flash-attention library kernel): its sm_100a replacement is the next kernel on this path.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .model import ModelConfig
+
+
+def _ru(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class Ops:
+    """Thin typed front of the C ABI for the learner body (bf16 activations, fp32 statistics / gradients)."""
+
+    def __init__(self):
+        self.lib = _lib.load()
+
+    # C[M,N] (=|+=) A[M,K] B[N,K]^T (+bias) (+residual)
+    def gemm(self, A, B, out=None, out_dtype=torch.bfloat16, bias=None, residual=None, accumulate=False, alpha=1.0):
+        M, K = A.shape
+        N = B.shape[0]
+        assert B.shape[1] == K and A.stride(1) == 1 and B.stride(1) == 1
+        if out is None:
+            out = torch.empty(M, N, dtype=out_dtype, device=A.device)
+        assert out.shape == (M, N) and out.stride(1) == 1
+        _lib.check(self.lib.prl_gemm_tn(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, out.data_ptr(),
+                                        out.stride(0), int(out.dtype == torch.float32), int(accumulate),
+                                        bias.data_ptr() if bias is not None else None,
+                                        residual.data_ptr() if residual is not None else None,
+                                        residual.stride(0) if residual is not None else 0, float(alpha),
+                                        _lib.stream_ptr()))
+        return out
+
+    def transpose(self, x, out=None):
+        R, Cc = x.shape
+        assert x.stride(1) == 1
+        if out is None:
+            buf = torch.empty(Cc, _ru(R, 8), dtype=torch.bfloat16, device=x.device)  # row stride multiple of 8 (TMA)
+            out = buf[:, :R]
+        _lib.check(self.lib.prl_transpose_bf16(x.data_ptr(), R, Cc, x.stride(0), out.data_ptr(), out.stride(0),
+                                               _lib.stream_ptr()))
+        return out
+
+    def wgrad(self, G, dY, X):
+        """G[out, in] (fp32) += dY[T, out]^T X[T, in]"""
+        self.gemm(self.transpose(dY), self.transpose(X), out=G, accumulate=True)
+
+    def rmsnorm(self, x, gamma, eps):
+        T, H = x.shape
+        y = torch.empty_like(x)
+        rstd = torch.empty(T, dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.prl_rmsnorm_fwd(x.data_ptr(), gamma.data_ptr(), T, H, float(eps), y.data_ptr(),
+                                            rstd.data_ptr(), _lib.stream_ptr()))
+        return y, rstd
+
+    def rmsnorm_bwd(self, x, gamma, rstd, dy, dres, dgamma):
+        """returns dres + d/dx RMSNorm (bf16); dgamma (fp32 [H]) += column sums"""
+        T, H = x.shape
+        dx = torch.empty_like(x)
+        ws = torch.empty(int(self.lib.prl_rowops_workspace_bytes(H)), dtype=torch.uint8, device=x.device)
+        _lib.check(self.lib.prl_rmsnorm_bwd(x.data_ptr(), gamma.data_ptr(), rstd.data_ptr(), dy.data_ptr(),
+                                            dres.data_ptr() if dres is not None else None, T, H, dx.data_ptr(),
+                                            dgamma.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+        return dx
+
+    def rope_(self, qkv, pos, inv_freq, n_heads, head_dim, sign):
+        """rotate the first n_heads heads of every row of qkv [T, *] in place by sign * pos * inv_freq"""
+        T = qkv.shape[0]
+        _lib.check(self.lib.prl_rope_inplace(qkv.data_ptr(), qkv.stride(0), T, n_heads, head_dim, pos.data_ptr(),
+                                             inv_freq.data_ptr(), float(sign), _lib.stream_ptr()))
+
+    def silu_mul(self, gu):
+        T, two_i = gu.shape
+        act = torch.empty(T, two_i // 2, dtype=torch.bfloat16, device=gu.device)
+        _lib.check(self.lib.prl_silu_mul_fwd(gu.data_ptr(), T, two_i // 2, act.data_ptr(), _lib.stream_ptr()))
+        return act
+
+    def silu_mul_bwd(self, gu, dact):
+        T, two_i = gu.shape
+        dgu = torch.empty_like(gu)
+        _lib.check(self.lib.prl_silu_mul_bwd(gu.data_ptr(), dact.data_ptr(), T, two_i // 2, dgu.data_ptr(),
+                                             _lib.stream_ptr()))
+        return dgu
+
+    def colsum_acc(self, x, out_f32):
+        """out[C] (fp32) += sum over rows of x [T, C] (bf16), fixed reduction order"""
+        T, Cc = x.shape
+        ws = torch.empty(int(self.lib.prl_rowops_workspace_bytes(Cc)), dtype=torch.uint8, device=x.device)
+        _lib.check(self.lib.prl_colsum_bf16(x.data_ptr(), x.stride(0), T, Cc, out_f32.data_ptr(), ws.data_ptr(),
+                                            ws.numel(), _lib.stream_ptr()))
+
+    def embed(self, table, ids):
+        T, H = ids.numel(), table.shape[1]
+        out = torch.empty(T, H, dtype=torch.bfloat16, device=table.device)
+        _lib.check(self.lib.prl_embed_gather(table.data_ptr(), ids.data_ptr(), T, H, out.data_ptr(), _lib.stream_ptr()))
+        return out
+
+    def embed_bwd(self, dtable_f32, ids, dh):
+        T, H = dh.shape
+        _lib.check(self.lib.prl_embed_scatter_add(dtable_f32.data_ptr(), ids.data_ptr(), dh.data_ptr(), T, H,
+                                                  _lib.stream_ptr()))
+
+
+class NativeBody:
+    """weights: fused name -> bf16 tensor (views of the parameter arena); grads: fused name -> fp32 tensor
+    (views of the optimizer's gradient arena).  `refresh()` must be called after every optimizer step: it rebuilds
+    the transposed weight copies the dgrad GEMMs read."""
+
+    def __init__(self, cfg: ModelConfig, weights: dict[str, torch.Tensor], grads: dict[str, torch.Tensor]):
+        self.cfg, self.w, self.g = cfg, weights, grads
+        self.ops = Ops()
+        dev = next(iter(weights.values())).device
+        d = cfg.head_dim
+        self.inv_freq = (1.0 / (cfg.rope_theta ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))).to(dev)
+        self.wt: dict[str, torch.Tensor] = {}
+        self.refresh()
+        self._saved = None
+
+    def _gemm_names(self):
+        for l in range(self.cfg.num_layers):
+            for k in ("qkv_proj", "o_proj", "gate_up_proj", "down_proj"):
+                yield f"layers.{l}.{k}.weight"
+        if "lm_head.weight" in self.w:
+            yield "lm_head.weight"
+
+    def head_t(self) -> torch.Tensor:
+        return self.wt["lm_head.weight"]
+
+    def refresh(self) -> None:
+        for name in self._gemm_names():
+            w = self.w[name]
+            if name not in self.wt:
+                buf = torch.empty(w.shape[1], _ru(w.shape[0], 8), dtype=torch.bfloat16, device=w.device)
+                self.wt[name] = buf[:, : w.shape[0]]
+            self.ops.transpose(w, out=self.wt[name])
+
+    # ---- attention (library call for now): q, k roped; block-diagonal causal over the packed segments ----
+    def _attention(self, qkv, bounds, need_grad):
+        c = self.cfg
+        T = qkv.shape[0]
+        q = qkv[:, :c.q_size].view(T, c.num_q_heads, c.head_dim)
+        k = qkv[:, c.q_size:c.q_size + c.kv_size].view(T, c.num_kv_heads, c.head_dim)
+        v = qkv[:, c.q_size + c.kv_size:].view(T, c.num_kv_heads, c.head_dim)
+        leaves = []
+        out = torch.empty(T, c.q_size, dtype=torch.bfloat16, device=qkv.device)
+        graph = []
+        for s, e in bounds:
+            qs, ks, vs = (t[s:e].transpose(0, 1)[None] for t in (q, k, v))
+            if need_grad:
+                qs, ks, vs = (t.detach().requires_grad_(True) for t in (qs, ks, vs))
+            with torch.set_grad_enabled(need_grad):
+                o = F.scaled_dot_product_attention(qs, ks, vs, is_causal=True, enable_gqa=True,
+                                                   scale=1.0 / math.sqrt(c.head_dim))
+            out[s:e] = o[0].transpose(0, 1).reshape(e - s, c.q_size).detach()
+            if need_grad:
+                graph.append((o, qs, ks, vs))
+        return out, graph
+
+    def _attention_bwd(self, graph, bounds, d_attn, T):
+        c = self.cfg
+        dqkv = torch.empty(T, c.qkv_size, dtype=torch.bfloat16, device=d_attn.device)
+        for (o, qs, ks, vs), (s, e) in zip(graph, bounds):
+            do = d_attn[s:e].view(e - s, c.num_q_heads, c.head_dim).transpose(0, 1)[None]
+            dq, dk, dv = torch.autograd.grad(o, (qs, ks, vs), do)
+            dqkv[s:e, :c.q_size] = dq[0].transpose(0, 1).reshape(e - s, c.q_size)
+            dqkv[s:e, c.q_size:c.q_size + c.kv_size] = dk[0].transpose(0, 1).reshape(e - s, c.kv_size)
+            dqkv[s:e, c.q_size + c.kv_size:] = dv[0].transpose(0, 1).reshape(e - s, c.kv_size)
+        return dqkv
+
+    # ---- one layer ----
+    def _layer(self, l, h, pos, bounds, keep):
+        c, o, w = self.cfg, self.ops, self.w
+        p = f"layers.{l}."
+        x1, rstd1 = o.rmsnorm(h, w[p + "input_layernorm.weight"], c.rms_eps)
+        qkv = o.gemm(x1, w[p + "qkv_proj.weight"], bias=w.get(p + "qkv_proj.bias"))
+        o.rope_(qkv, pos, self.inv_freq, c.num_q_heads + c.num_kv_heads, c.head_dim, +1.0)
+        attn, graph = self._attention(qkv, bounds, need_grad=keep)
+        h2 = o.gemm(attn, w[p + "o_proj.weight"], residual=h)
+        x2, rstd2 = o.rmsnorm(h2, w[p + "post_attention_layernorm.weight"], c.rms_eps)
+        gu = o.gemm(x2, w[p + "gate_up_proj.weight"])
+        act = o.silu_mul(gu)
+        h3 = o.gemm(act, w[p + "down_proj.weight"], residual=h2)
+        if keep:
+            return h3, (x1, rstd1, attn, graph, h2, x2, rstd2, gu, act)
+        return h3, None
+
+    def _layer_bwd(self, l, h, pos, bounds, dh3):
+        c, o, w, g, wt = self.cfg, self.ops, self.w, self.g, self.wt
+        p = f"layers.{l}."
+        _, (x1, rstd1, attn, graph, h2, x2, rstd2, gu, act) = self._layer(l, h, pos, bounds, keep=True)
+        T = h.shape[0]
+        d_act = o.gemm(dh3, wt[p + "down_proj.weight"])
+        o.wgrad(g[p + "down_proj.weight"], dh3, act)
+        del act
+        d_gu = o.silu_mul_bwd(gu, d_act)
+        del gu, d_act
+        dx2 = o.gemm(d_gu, wt[p + "gate_up_proj.weight"])
+        o.wgrad(g[p + "gate_up_proj.weight"], d_gu, x2)
+        del d_gu, x2
+        dh2 = o.rmsnorm_bwd(h2, w[p + "post_attention_layernorm.weight"], rstd2, dx2, dh3,
+                            g[p + "post_attention_layernorm.weight"])
+        del dx2, h2
+        d_attn = o.gemm(dh2, wt[p + "o_proj.weight"])
+        o.wgrad(g[p + "o_proj.weight"], dh2, attn)
+        dqkv = self._attention_bwd(graph, bounds, d_attn, T)
+        del graph, attn, d_attn
+        o.rope_(dqkv, pos, self.inv_freq, c.num_q_heads + c.num_kv_heads, c.head_dim, -1.0)
+        if c.qkv_bias:
+            o.colsum_acc(dqkv, g[p + "qkv_proj.bias"])
+        dx1 = o.gemm(dqkv, wt[p + "qkv_proj.weight"])
+        o.wgrad(g[p + "qkv_proj.weight"], dqkv, x1)
+        del dqkv, x1
+        return o.rmsnorm_bwd(h, w[p + "input_layernorm.weight"], rstd1, dx1, dh2, g[p + "input_layernorm.weight"])
+
+    # ---- whole body ----
+    @staticmethod
+    def segment_bounds(position_ids: torch.Tensor) -> list[tuple[int, int]]:
+        starts = torch.nonzero(position_ids == 0).flatten().tolist()
+        T = position_ids.numel()
+        if not starts or starts[0] != 0:
+            starts = [0] + starts
+        return [(s, e) for s, e in zip(starts, starts[1:] + [T])]
+
+    def forward(self, input_ids: torch.Tensor, position_ids: torch.Tensor, keep: bool = True) -> torch.Tensor:
+        """input_ids / position_ids: [T] (position ids restart at 0 for every packed sample).  Returns the final-norm
+        hidden states [T, H] (bf16)."""
+        c, o = self.cfg, self.ops
+        ids = input_ids.to(torch.int64).contiguous()
+        pos = position_ids.to(torch.int32).contiguous()
+        bounds = self.segment_bounds(position_ids)
+        h = o.embed(self.w["embed_tokens.weight"], ids)
+        inputs = []
+        for l in range(c.num_layers):
+            if keep:
+                inputs.append(h)
+            h, _ = self._layer(l, h, pos, bounds, keep=False)
+        y, rstd = o.rmsnorm(h, self.w["norm.weight"], c.rms_eps)
+        if keep:
+            self._saved = (ids, pos, bounds, inputs, h, rstd)
+        return y
+
+    def backward(self, d_hidden: torch.Tensor) -> None:
+        """d_hidden: dL/d(final-norm hidden) [T, H].  Accumulates every parameter gradient of the body."""
+        assert self._saved is not None, "backward() without a kept forward()"
+        c, o, g = self.cfg, self.ops, self.g
+        ids, pos, bounds, inputs, h_last, rstd = self._saved
+        self._saved = None
+        dh = o.rmsnorm_bwd(h_last, self.w["norm.weight"], rstd, d_hidden.to(torch.bfloat16).contiguous(), None,
+                           g["norm.weight"])
+        del h_last
+        for l in range(c.num_layers - 1, -1, -1):
+            dh = self._layer_bwd(l, inputs.pop(), pos, bounds, dh)
+        o.embed_bwd(g["embed_tokens.weight"], ids, dh)
+
+
+class _BodyFn(torch.autograd.Function):
+    """Autograd adapter: makes `hidden = body(ids)` a node whose backward runs NativeBody.backward (parameter
+    gradients go straight into the arena, so the node has no tensor inputs that need grad besides the hook)."""
+
+    @staticmethod
+    def forward(ctx, hook, body, input_ids, position_ids):
+        ctx.body = body
+        return body.forward(input_ids, position_ids, keep=True)
+
+    @staticmethod
+    def backward(ctx, d_hidden):
+        ctx.body.backward(d_hidden)
+        return torch.zeros((), device=d_hidden.device), None, None, None

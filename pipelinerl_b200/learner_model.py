@@ -15,6 +15,7 @@ import types
 import torch
 import torch.nn.functional as F
 
+from . import _lib
 from .model import ArenaLayout, ModelConfig, fused_shapes
 
 
@@ -109,3 +110,128 @@ class TorchQwen2(torch.nn.Module):
     def _norm(self, h, g):
         hf = h.float()
         return (hf * torch.rsqrt((hf * hf).mean(-1, keepdim=True) + self.cfg.rms_eps)).to(h.dtype) * g
+
+
+class _NativeHead(torch.autograd.Function):
+    """Final projection + log-softmax statistics of the native learner.  Forward: one tcgen05 GEMM whose epilogue
+    reduces logits in TMEM (prl_head_logprob).  Backward: per chunk of rows, logits recomputed by the same kernel,
+    d logits formed in one pass (prl_logprob_rows_bwd), then dX = dZ W (prl_gemm_tn against the transposed head) and
+    dW += dZ^T X accumulated in fp32 in the optimizer's gradient arena."""
+
+    @staticmethod
+    def forward(ctx, hidden, model, targets, temperature: float, chunk_rows: int):
+        lib = _lib.load()
+        x = hidden.to(torch.bfloat16).contiguous()
+        W = model.p("lm_head.weight").data
+        M, K = x.shape
+        V = W.shape[0]
+        tg = targets.to(torch.int64).contiguous()
+        lp = torch.empty(M, dtype=torch.float32, device=x.device)
+        ent, lse = torch.empty_like(lp), torch.empty_like(lp)
+        ws = torch.empty(int(lib.prl_head_workspace_bytes(M, V)), dtype=torch.uint8, device=x.device)
+        _lib.check(lib.prl_head_logprob(W.data_ptr(), None, x.data_ptr(), M, V, K, float(temperature), tg.data_ptr(), 1, 0,
+                                        0, lp.data_ptr(), ent.data_ptr(), lse.data_ptr(), None, None, ws.data_ptr(),
+                                        ws.numel(), _lib.stream_ptr()))
+        ctx.save_for_backward(x, tg, lse, ent)
+        ctx.model, ctx.temperature, ctx.chunk_rows = model, float(temperature), int(chunk_rows)
+        return lp, ent
+
+    @staticmethod
+    def backward(ctx, g_lp, g_ent):
+        x, tg, lse, ent = ctx.saved_tensors
+        model, lib = ctx.model, _lib.load()
+        body = model.body
+        ops = body.ops
+        W, Wt, gW = model.p("lm_head.weight").data, body.head_t(), body.g["lm_head.weight"]
+        M, K = x.shape
+        V = W.shape[0]
+        dev = x.device
+        g_lp = g_lp.contiguous() if g_lp is not None else torch.zeros(M, device=dev)
+        use_ent = g_ent is not None
+        g_ent = g_ent.contiguous() if use_ent else None
+        dx = torch.empty(M, K, dtype=torch.bfloat16, device=dev)
+        Cn = min(ctx.chunk_rows, M)
+        logits_buf = torch.empty(Cn, V, dtype=torch.float32, device=dev)
+        dlogits_buf = torch.empty(Cn, V, dtype=torch.float32, device=dev)
+        st = _lib.stream_ptr()
+        for r0 in range(0, M, Cn):
+            n = min(Cn, M - r0)
+            xs, logits, dlogits = x[r0:r0 + n], logits_buf[:n], dlogits_buf[:n]
+            ops.gemm(xs, W, out=logits)
+            _lib.check(lib.prl_logprob_rows_bwd(logits.data_ptr(), n, V, V, tg[r0:r0 + n].data_ptr(), ctx.temperature,
+                                                lse[r0:r0 + n].data_ptr(), ent[r0:r0 + n].data_ptr(),
+                                                g_lp[r0:r0 + n].data_ptr(),
+                                                g_ent[r0:r0 + n].data_ptr() if use_ent else None,
+                                                dlogits.data_ptr(), V, st))
+            dz = dlogits.to(torch.bfloat16)
+            ops.gemm(dz, Wt, out=dx[r0:r0 + n])
+            ops.wgrad(gW, dz, xs)
+        return dx, None, None, None, None
+
+
+class NativeQwen2(torch.nn.Module):
+    """Learner model whose body is learner_body.NativeBody (hand-scheduled tcgen05 GEMMs + row kernels, fp32
+    gradient accumulation in the optimizer arena).  bf16 parameters in the fused arena order; must be bound to a
+    FusedAdamW(grad_dtype=torch.float32) with `bind(optimizer)` before the first step, and
+    `after_optimizer_step()` must follow every optimizer step (refreshes the transposed weight copies)."""
+
+    use_fused_head = True
+
+    def __init__(self, cfg: ModelConfig, device, init: dict[str, torch.Tensor] | None = None, seed: int = 42):
+        super().__init__()
+        self.cfg = cfg
+        self.names = []
+        g = torch.Generator(device=device).manual_seed(seed)
+        for name, shape in fused_shapes(cfg):
+            if init is not None:
+                t = init[name].to(device=device, dtype=torch.bfloat16)
+            elif name.endswith("layernorm.weight") or name == "norm.weight":
+                t = torch.ones(shape, dtype=torch.bfloat16, device=device)
+            elif name.endswith(".bias") or name.endswith("_lo"):
+                t = torch.zeros(shape, dtype=torch.bfloat16, device=device)
+            else:
+                t = (torch.randn(shape, generator=g, device=device, dtype=torch.float32) * 0.02).to(torch.bfloat16)
+            self.register_parameter(name.replace(".", "__"), torch.nn.Parameter(t))
+            self.names.append(name)
+        self.layout = ArenaLayout.build(cfg)
+        self.body = None
+        self._hook = torch.zeros((), device=device, requires_grad=True)
+
+    def p(self, name: str) -> torch.Tensor:
+        return getattr(self, name.replace(".", "__"))
+
+    def named_parameters(self, *a, **k):
+        for name in self.names:
+            yield name, self.p(name)
+
+    def bind(self, optimizer) -> None:
+        from .learner_body import NativeBody
+        if optimizer.grad.dtype != torch.float32:
+            raise ValueError("NativeQwen2 accumulates gradients in fp32: build FusedAdamW(grad_dtype=torch.float32)")
+        weights = {n: self.p(n).data for n in self.names}
+        self.body = NativeBody(self.cfg, weights, optimizer.grad_views())
+
+    def after_optimizer_step(self) -> None:
+        self.body.refresh()
+
+    def hidden_states(self, input_ids, position_ids=None):
+        if self.body is None:
+            raise RuntimeError("NativeQwen2.bind(optimizer) must be called first")
+        from .learner_body import _BodyFn
+        B, T = input_ids.shape
+        if position_ids is None:
+            position_ids = torch.arange(T, device=input_ids.device)[None].expand(B, T)
+        return torch.stack([_BodyFn.apply(self._hook, self.body, input_ids[b], position_ids[b]) for b in range(B)])
+
+    def forward_logprobs(self, batch, temperature: float):
+        hidden = self.hidden_states(batch.input_ids, batch.position_ids if batch.is_packed else None)
+        lps, ents = [], []
+        for b in range(hidden.shape[0]):
+            lp, ent = _NativeHead.apply(hidden[b, :-1], self, batch.input_ids[b, 1:], temperature, 2048)
+            lps.append(lp)
+            ents.append(ent)
+        return torch.stack(lps), torch.stack(ents)
+
+    def forward(self, input_ids, attention_mask=None, labels=None, position_ids=None, **kw):
+        x = self.hidden_states(input_ids, position_ids)
+        return types.SimpleNamespace(logits=F.linear(x.float(), self.p("lm_head.weight").float()))
