@@ -44,6 +44,9 @@ struct TnParams {
   const __nv_bfloat16* residual;  // [M, ldr] or NULL
   int64_t ldr;
   float alpha;
+  // head epilogue (kHead): logits never leave TMEM/registers
+  const int64_t* targets;  // [M] or NULL
+  float4* head_part;       // [n_tiles, M]: (max, sum exp, sum exp*z, target logit or -inf) of one 256-column vocabulary tile
 };
 
 __device__ __forceinline__ void tile_coords(int t, const TnParams& p, int& tm, int& tn) {
@@ -56,6 +59,7 @@ __device__ __forceinline__ void tile_coords(int t, const TnParams& p, int& tm, i
   tn = r / rows;
 }
 
+template <bool kHead>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTN, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, TnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -162,6 +166,47 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int64_t row = (int64_t)tm * kTile + (int64_t)rank * kHalf + q * 32 + lane;
       const int64_t col0 = (int64_t)tn * kTile;
       const bool row_ok = row < p.M;
+      if constexpr (kHead) {
+        // thread = one token; online softmax statistics over this tile's 256 vocabulary columns, all thread-local
+        constexpr float kLog2e = 1.4426950408889634f;
+        const int64_t tgt = (p.targets && row_ok) ? p.targets[row] : -1;
+        float m = -INFINITY, ssum = 0.f, usum = 0.f, zt = -INFINITY;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTile; c0 += 32) {
+          if (col0 + c0 >= p.N) break;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTile + c0), r);
+          ptx::tmem_ld_wait();
+          const int64_t col = col0 + c0;
+          const int n_ok = (int)((p.N - col) < 32 ? (p.N - col) : 32);
+          float z[32];
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            z[j] = (j < n_ok) ? __uint_as_float(r[j]) * p.alpha : -INFINITY;
+            cm = fmaxf(cm, z[j]);
+          }
+          const float m2 = fmaxf(m, cm);
+          const float sc = (m == -INFINITY) ? 0.f : exp2f((m - m2) * kLog2e);
+          ssum *= sc;
+          usum *= sc;
+          m = m2;
+          const float mb = m * kLog2e;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float e = exp2f(fmaf(z[j], kLog2e, -mb));  // exp2(-inf) = 0 for the masked tail
+            ssum += e;
+            usum = fmaf(e, (j < n_ok) ? z[j] : 0.f, usum);
+          }
+          const uint64_t rel = (uint64_t)(tgt - col);
+          if (rel < 32u) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (rel == (uint64_t)j) zt = z[j];
+          }
+        }
+        if (row_ok) p.head_part[(int64_t)tn * p.M + row] = make_float4(m, ssum, usum, zt);
+      } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < kTile; c0 += 32) {
         if (col0 + c0 >= p.N) break;  // uniform across the CTA
@@ -234,6 +279,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           }
         }
       }
+      }  // !kHead
       // this CTA's four epilogue warps are done with the accumulator -> tell the leader's MMA warp
       ptx::tc_fence_before_sync();
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -249,6 +295,40 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (warp == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+// one warp per token: merge the per-tile statistics in a fixed order (lane-strided tiles, then a shuffle tree)
+__global__ void __launch_bounds__(128) head_tn_combine_kernel(const float4* __restrict__ part, int n_tiles, int64_t M,
+                                                             int has_targets, float* __restrict__ lp_target,
+                                                             float* __restrict__ entropy, float* __restrict__ lse_out) {
+  const int64_t tok = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (tok >= M) return;
+  float m = -INFINITY, s = 0.f, u = 0.f, zt = -INFINITY;
+  auto merge = [&](float m2, float s2, float u2, float zt2) {
+    const float mm = fmaxf(m, m2);
+    const float f1 = (m == -INFINITY) ? 0.f : __expf(m - mm), f2 = (m2 == -INFINITY) ? 0.f : __expf(m2 - mm);
+    s = s * f1 + s2 * f2;
+    u = u * f1 + u2 * f2;
+    m = mm;
+    zt = fmaxf(zt, zt2);  // exactly one tile holds the target, the others carry -inf
+  };
+  for (int t = lane; t < n_tiles; t += 32) {
+    const float4 v = part[(int64_t)t * M + tok];
+    merge(v.x, v.y, v.z, v.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const float u2 = __shfl_xor_sync(0xffffffffu, u, o), z2 = __shfl_xor_sync(0xffffffffu, zt, o);
+    merge(m2, s2, u2, z2);
+  }
+  if (lane == 0) {
+    const float lse = m + logf(s);
+    if (lse_out) lse_out[tok] = lse;
+    if (entropy) entropy[tok] = lse - u / s;
+    if (lp_target && has_targets) lp_target[tok] = zt - lse;
   }
 }
 
@@ -330,16 +410,53 @@ extern "C" int prl_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ld
   const int smem = kStages * kStageBytes + 1024 + 8 * (2 * kStages + 4) + 16;
   static bool configured = false;
   if (!configured) {
-    PRL_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PRL_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = (int)tiles;
-  gemm_tn_kernel<<<dim3((unsigned)(2 * clusters)), dim3(kThreadsTN), (size_t)smem, (cudaStream_t)stream_>>>(ta, tb, p);
+  gemm_tn_kernel<false><<<dim3((unsigned)(2 * clusters)), dim3(kThreadsTN), (size_t)smem, (cudaStream_t)stream_>>>(ta, tb, p);
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }
+
+namespace prl {
+// fused output head for many tokens (M > 128): logprob of the target, entropy and logsumexp of softmax(X W^T / T)
+// without storing logits.  Called by prl_head_logprob (gemm_tc.cu).  workspace: ceil(V/256) * M float4.
+int head_logprob_tn(const void* W, const void* X, int64_t M, int64_t V, int64_t K, float temperature,
+                    const int64_t* targets, float* logprob_target, float* entropy, float* lse, void* workspace,
+                    cudaStream_t stream) {
+  TnParams p = {};
+  p.M = M; p.N = V; p.K = K;
+  p.kblocks = (int)((K + kBK - 1) / kBK);
+  p.m_tiles = (int)((M + kTile - 1) / kTile);
+  p.n_tiles = (int)((V + kTile - 1) / kTile);
+  p.alpha = 1.f / temperature;
+  p.targets = targets;
+  p.head_part = (float4*)workspace;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d_bf16(&ta, X, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kBK, kHalf);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tb, W, (uint64_t)K, (uint64_t)V, (uint64_t)K * 2, kBK, kHalf);
+  if (rc) return rc;
+  const int smem = kStages * kStageBytes + 1024 + 8 * (2 * kStages + 4) + 16;
+  static bool configured = false;
+  if (!configured) {
+    PRL_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
+  int clusters = num_sms() / 2;
+  if (tiles < clusters) clusters = (int)tiles;
+  gemm_tn_kernel<true><<<dim3((unsigned)(2 * clusters)), dim3(kThreadsTN), (size_t)smem, stream>>>(ta, tb, p);
+  PRL_LAUNCH_CHECK();
+  head_tn_combine_kernel<<<(unsigned)((M + 3) / 4), 128, 0, stream>>>((const float4*)workspace, p.n_tiles, M,
+                                                                      targets ? 1 : 0, logprob_target, entropy, lse);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+}  // namespace prl
 
 extern "C" int prl_transpose_bf16(const void* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
                                   prl_stream_t stream_) {

@@ -136,6 +136,7 @@ class NativeBody:
         self.wt: dict[str, torch.Tensor] = {}
         self.refresh()
         self._saved = None
+        self.keep_attention_layers = cfg.num_layers   # lower it when activation memory is short (0 = full recompute)
 
     def _gemm_names(self):
         for l in range(self.cfg.num_layers):
@@ -162,8 +163,7 @@ class NativeBody:
         q = qkv[:, :c.q_size].view(T, c.num_q_heads, c.head_dim)
         k = qkv[:, c.q_size:c.q_size + c.kv_size].view(T, c.num_kv_heads, c.head_dim)
         v = qkv[:, c.q_size + c.kv_size:].view(T, c.num_kv_heads, c.head_dim)
-        leaves = []
-        out = torch.empty(T, c.q_size, dtype=torch.bfloat16, device=qkv.device)
+        out = None
         graph = []
         for s, e in bounds:
             qs, ks, vs = (t[s:e].transpose(0, 1)[None] for t in (q, k, v))
@@ -172,7 +172,13 @@ class NativeBody:
             with torch.set_grad_enabled(need_grad):
                 o = F.scaled_dot_product_attention(qs, ks, vs, is_causal=True, enable_gqa=True,
                                                    scale=1.0 / math.sqrt(c.head_dim))
-            out[s:e] = o[0].transpose(0, 1).reshape(e - s, c.q_size).detach()
+            flat = o.detach()[0].transpose(0, 1)
+            if len(bounds) == 1 and flat.is_contiguous():
+                out = flat.reshape(T, c.q_size)      # the library already wrote [T, heads, d]: no copy
+            else:
+                if out is None:
+                    out = torch.empty(T, c.q_size, dtype=torch.bfloat16, device=qkv.device)
+                out[s:e] = flat.reshape(e - s, c.q_size)
             if need_grad:
                 graph.append((o, qs, ks, vs))
         return out, graph
@@ -188,27 +194,35 @@ class NativeBody:
             dqkv[s:e, c.q_size + c.kv_size:] = dv[0].transpose(0, 1).reshape(e - s, c.kv_size)
         return dqkv
 
-    # ---- one layer ----
-    def _layer(self, l, h, pos, bounds, keep):
+    # ---- one layer, in two halves ----
+    def _attn_half(self, l, h, pos, bounds, need_grad):
         c, o, w = self.cfg, self.ops, self.w
         p = f"layers.{l}."
         x1, rstd1 = o.rmsnorm(h, w[p + "input_layernorm.weight"], c.rms_eps)
         qkv = o.gemm(x1, w[p + "qkv_proj.weight"], bias=w.get(p + "qkv_proj.bias"))
         o.rope_(qkv, pos, self.inv_freq, c.num_q_heads + c.num_kv_heads, c.head_dim, +1.0)
-        attn, graph = self._attention(qkv, bounds, need_grad=keep)
+        attn, graph = self._attention(qkv, bounds, need_grad=need_grad)
         h2 = o.gemm(attn, w[p + "o_proj.weight"], residual=h)
+        return x1, rstd1, attn, graph, h2
+
+    def _mlp_half(self, l, h2):
+        c, o, w = self.cfg, self.ops, self.w
+        p = f"layers.{l}."
         x2, rstd2 = o.rmsnorm(h2, w[p + "post_attention_layernorm.weight"], c.rms_eps)
         gu = o.gemm(x2, w[p + "gate_up_proj.weight"])
         act = o.silu_mul(gu)
         h3 = o.gemm(act, w[p + "down_proj.weight"], residual=h2)
-        if keep:
-            return h3, (x1, rstd1, attn, graph, h2, x2, rstd2, gu, act)
-        return h3, None
+        return x2, rstd2, gu, act, h3
 
-    def _layer_bwd(self, l, h, pos, bounds, dh3):
+    def _layer_bwd(self, l, h, saved, pos, bounds, dh3):
         c, o, w, g, wt = self.cfg, self.ops, self.w, self.g, self.wt
         p = f"layers.{l}."
-        _, (x1, rstd1, attn, graph, h2, x2, rstd2, gu, act) = self._layer(l, h, pos, bounds, keep=True)
+        if saved is None:   # full recompute of the layer from its input
+            x1, rstd1, attn, graph, h2 = self._attn_half(l, h, pos, bounds, need_grad=True)
+        else:               # attention half was kept by the forward: only the (cheap) norm is redone
+            attn, graph, h2 = saved
+            x1, rstd1 = o.rmsnorm(h, w[p + "input_layernorm.weight"], c.rms_eps)
+        x2, rstd2, gu, act, _ = self._mlp_half(l, h2)
         T = h.shape[0]
         d_act = o.gemm(dh3, wt[p + "down_proj.weight"])
         o.wgrad(g[p + "down_proj.weight"], dh3, act)
@@ -244,33 +258,39 @@ class NativeBody:
 
     def forward(self, input_ids: torch.Tensor, position_ids: torch.Tensor, keep: bool = True) -> torch.Tensor:
         """input_ids / position_ids: [T] (position ids restart at 0 for every packed sample).  Returns the final-norm
-        hidden states [T, H] (bf16)."""
+        hidden states [T, H] (bf16).  With keep, each layer's input is saved for the backward; the first
+        `keep_attention_layers` layers also keep their attention half (attention output + its softmax statistics +
+        post-attention residual, ~0.4 GB per layer at 16 K tokens of Qwen2.5-7B) so the backward does not redo the
+        qkv GEMM, RoPE, attention forward and o_proj."""
         c, o = self.cfg, self.ops
         ids = input_ids.to(torch.int64).contiguous()
         pos = position_ids.to(torch.int32).contiguous()
         bounds = self.segment_bounds(position_ids)
         h = o.embed(self.w["embed_tokens.weight"], ids)
-        inputs = []
+        inputs, kept = [], []
         for l in range(c.num_layers):
+            keep_attn = keep and l < self.keep_attention_layers
+            _, _, attn, graph, h2 = self._attn_half(l, h, pos, bounds, need_grad=keep_attn)
             if keep:
                 inputs.append(h)
-            h, _ = self._layer(l, h, pos, bounds, keep=False)
+                kept.append((attn, graph, h2) if keep_attn else None)
+            h = self._mlp_half(l, h2)[-1]
         y, rstd = o.rmsnorm(h, self.w["norm.weight"], c.rms_eps)
         if keep:
-            self._saved = (ids, pos, bounds, inputs, h, rstd)
+            self._saved = (ids, pos, bounds, inputs, kept, h, rstd)
         return y
 
     def backward(self, d_hidden: torch.Tensor) -> None:
         """d_hidden: dL/d(final-norm hidden) [T, H].  Accumulates every parameter gradient of the body."""
         assert self._saved is not None, "backward() without a kept forward()"
         c, o, g = self.cfg, self.ops, self.g
-        ids, pos, bounds, inputs, h_last, rstd = self._saved
+        ids, pos, bounds, inputs, kept, h_last, rstd = self._saved
         self._saved = None
         dh = o.rmsnorm_bwd(h_last, self.w["norm.weight"], rstd, d_hidden.to(torch.bfloat16).contiguous(), None,
                            g["norm.weight"])
         del h_last
         for l in range(c.num_layers - 1, -1, -1):
-            dh = self._layer_bwd(l, inputs.pop(), pos, bounds, dh)
+            dh = self._layer_bwd(l, inputs.pop(), kept.pop(), pos, bounds, dh)
         o.embed_bwd(g["embed_tokens.weight"], ids, dh)
 
 

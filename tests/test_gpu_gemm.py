@@ -127,3 +127,30 @@ def test_fused_head_logprob_capture(cuda_device, M, V, K):
     same = (ids == ids2)
     assert same.float().mean() > 0.97   # tie-breaks can differ at fp32 noise level between the two logits paths
     assert torch.allclose(lp_s[same], lp2[same], atol=3e-4)
+
+
+@pytest.mark.parametrize("M,V,K,with_targets", [(129, 640, 256, True), (1000, 4096 + 77, 512, True),
+                                                (2048, 152064, 128, True), (300, 1000, 264, False)])
+def test_fused_head_many_tokens_statistics_only(cuda_device, M, V, K, with_targets):
+    """M > 128 without sampling outputs runs the CTA-pair kernel with the token-per-thread epilogue (gemm_tn.cu)."""
+    from pipelinerl_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(V + M)
+    X = torch.randn(M, K, generator=g).to(torch.bfloat16).to(cuda_device)
+    W = (torch.randn(V, K, generator=g) * 0.08).to(torch.bfloat16).to(cuda_device)
+    targets = torch.randint(0, V, (M,), generator=g).to(cuda_device)
+    targets[0], targets[-1] = V - 1, 0
+    T = 1.3
+    ws = torch.zeros(int(lib.prl_head_workspace_bytes(M, V)), dtype=torch.uint8, device=cuda_device)
+    lp_t, ent, lse = (torch.full((M,), float("nan"), device=cuda_device) for _ in range(3))
+    _lib.check(lib.prl_head_logprob(W.data_ptr(), None, X.data_ptr(), M, V, K, T,
+                                    targets.data_ptr() if with_targets else None, 1, 0, 0,
+                                    lp_t.data_ptr() if with_targets else None, ent.data_ptr(), lse.data_ptr(), None, None,
+                                    ws.data_ptr(), ws.numel(), None))
+    torch.cuda.synchronize()
+    logits = (X.float() @ W.float().t())
+    ref = torch.log_softmax(logits / T, -1)
+    assert torch.allclose(lse, torch.logsumexp(logits / T, -1), atol=2e-4, rtol=1e-5)
+    assert torch.allclose(ent, -(ref.exp() * ref).sum(-1), atol=3e-4, rtol=1e-4)
+    if with_targets:
+        assert torch.allclose(lp_t, ref.gather(1, targets[:, None])[:, 0], atol=3e-4, rtol=1e-4)
