@@ -10,8 +10,9 @@ A "step" = one token for each of the 64 sequences (one pass of hot path 1).  N >
 GPU (the token step shards as replicas only, no data-path collective) -> weak scaling.
 
 ONE JSON line on stdout (rank 0).  Extra keys: roofline (dominant kernel = paged decode attention),
-cpu_baseline (oracle port on the host cores, bounded sample), components (trainer-side kernels: fused AdamW
-and PG-loss tail on 7B-sized inputs).
+cpu_baseline (oracle port on the host cores, bounded sample), components (trainer side: fused AdamW and PG-loss
+tail on 7B-sized inputs, and `trainer_step` = hot path 2 end to end on Qwen2.5-7B: 2 x 16 384-token micro-batches
+through rl_step -> native backward -> fused AdamW; tools/train_bench.py).
 """
 from __future__ import annotations
 
@@ -255,6 +256,17 @@ def run_ours(args):
 
     if rank == 0 and not args.no_components:
         out["components"] = bench_components(dev, peak)
+        # hot path 2 end to end (rl_step -> backward -> fused AdamW) on the same model: needs the whole GPU
+        import gc
+        del eng, attn_all_layers
+        gc.collect()
+        torch.cuda.empty_cache()
+        try:
+            sys.path.insert(0, str(ROOT / "tools"))
+            import train_bench
+            out["components"]["trainer_step"] = train_bench.measure(steps=2, warmup=1, dev=dev, log=False)
+        except Exception as e:  # noqa: BLE001  (informational component: the headline line must still print)
+            out["components"]["trainer_step"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, budget_s=25.0)
     if rank == 0:

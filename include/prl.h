@@ -269,6 +269,12 @@ int prl_embed_gather(const void* table, const int64_t* ids, int64_t T, int64_t H
 /* dtable[ids[t]] += dh[t] (fp32 atomics: the one reduction here whose order is not fixed, as in torch) */
 int prl_embed_scatter_add(float* dtable, const int64_t* ids, const void* dh, int64_t T, int64_t H, prl_stream_t stream);
 
+/* Same kernel with either operand stored MN-major: a_mn_major -> A is given as [K, M] row-major (row stride lda >= M),
+ * b_mn_major -> B as [K, N] row-major.  dgrad (dX = dY W, B = W as stored) and wgrad (dW += dY^T X, both operands as
+ * stored) need no transposed copies this way. */
+int prl_gemm_ex(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb, int32_t b_mn_major,
+                int64_t M, int64_t N, int64_t K, void* C, int64_t ldc, int32_t c_is_f32, int32_t accumulate,
+                const void* bias, const void* residual, int64_t ldr, float alpha, prl_stream_t stream);
 /* bf16 [rows, cols] (row stride ld_in) -> [cols, rows] (row stride ld_out): stages the K-major operands of wgrad. */
 int prl_transpose_bf16(const void* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
                        prl_stream_t stream);

@@ -29,6 +29,7 @@ constexpr int kHalf = 128;      // operand rows staged per CTA
 constexpr int kBK = 64;         // bf16 per k-block row = one 128-B swizzle atom
 constexpr int kStages = 6;
 constexpr int kStageBytes = 2 * kHalf * kBK * 2;  // 32 KB
+constexpr int kMnChunkBytes = 64 * kBK * 2;        // one 64(MN) x 64(k) box of an MN-major operand: 8 KB
 constexpr int kThreadsTN = 192;
 constexpr int kGroupM = 8;      // row tiles per raster super-group
 
@@ -36,6 +37,7 @@ struct TnParams {
   int64_t M, N, K;
   int kblocks;
   int m_tiles, n_tiles;
+  int a_mn, b_mn;    // operand stored MN-major: A as [K, M] / B as [K, N] row-major (no transposed copy needed)
   void* C;
   int64_t ldc;
   int c_f32;         // 1: fp32 output, 0: bf16 output
@@ -118,15 +120,27 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(s), 2u * (uint32_t)kStageBytes);
           else ptx::mbar_arrive_remote(full_bar(s), 0);
           const uint32_t a_dst = smem_base + (uint32_t)(s * kStageBytes);
-          ptx::tma_load_2d_2sm(a_dst, &tm_a, kb * kBK, a_row, full_bar(s), ptx::kEvictNormal);
-          ptx::tma_load_2d_2sm(a_dst + kHalf * kBK * 2, &tm_b, kb * kBK, b_row, full_bar(s), ptx::kEvictNormal);
+          const uint32_t b_dst = a_dst + kHalf * kBK * 2;
+          if (!p.a_mn) {
+            ptx::tma_load_2d_2sm(a_dst, &tm_a, kb * kBK, a_row, full_bar(s), ptx::kEvictNormal);
+          } else {  // two 64(MN) x 64(k) boxes: inner coordinate = MN index, outer = k
+            ptx::tma_load_2d_2sm(a_dst, &tm_a, a_row, kb * kBK, full_bar(s), ptx::kEvictNormal);
+            ptx::tma_load_2d_2sm(a_dst + kMnChunkBytes, &tm_a, a_row + 64, kb * kBK, full_bar(s), ptx::kEvictNormal);
+          }
+          if (!p.b_mn) {
+            ptx::tma_load_2d_2sm(b_dst, &tm_b, kb * kBK, b_row, full_bar(s), ptx::kEvictNormal);
+          } else {
+            ptx::tma_load_2d_2sm(b_dst, &tm_b, b_row, kb * kBK, full_bar(s), ptx::kEvictNormal);
+            ptx::tma_load_2d_2sm(b_dst + kMnChunkBytes, &tm_b, b_row + 64, kb * kBK, full_bar(s), ptx::kEvictNormal);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(kTile, kTile);
+      const uint32_t idesc = ptx::make_idesc_bf16_f32(kTile, kTile) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16);
+      const uint64_t a_step = p.a_mn ? 128u : 2u, b_step = p.b_mn ? 128u : 2u;  // K += 16 in (addr >> 4) units
       int it = 0, local = 0;
       for (int t = cluster; t < total_tiles; t += n_clusters, ++local) {
         const int acc = local & 1;
@@ -140,11 +154,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           ptx::mbar_wait(full_bar(s), ph);
           ptx::tc_fence_after_sync();
           const uint32_t a_addr = smem_base + (uint32_t)(s * kStageBytes);
-          const uint64_t a_desc = ptx::make_kmajor_sw128_desc(a_addr);
-          const uint64_t b_desc = ptx::make_kmajor_sw128_desc(a_addr + kHalf * kBK * 2);
+          const uint32_t b_addr = a_addr + kHalf * kBK * 2;
+          const uint64_t a_desc = p.a_mn ? ptx::make_mnmajor_sw128_desc(a_addr, kMnChunkBytes) : ptx::make_kmajor_sw128_desc(a_addr);
+          const uint64_t b_desc = p.b_mn ? ptx::make_mnmajor_sw128_desc(b_addr, kMnChunkBytes) : ptx::make_kmajor_sw128_desc(b_addr);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
-            ptx::mma_bf16_ss_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+            ptx::mma_bf16_ss_2sm(d_tmem, a_desc + a_step * (uint64_t)k, b_desc + b_step * (uint64_t)k, idesc,
                                  (kb > 0 || k > 0) ? 1u : 0u);
           ptx::tc_commit_2sm(empty_bar(s), 3);
         }
@@ -383,11 +398,18 @@ using namespace prl;
 extern "C" int prl_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
                            void* C, int64_t ldc, int32_t c_is_f32, int32_t accumulate, const void* bias,
                            const void* residual, int64_t ldr, float alpha, prl_stream_t stream_) {
+  return prl_gemm_ex(A, lda, 0, B, ldb, 0, M, N, K, C, ldc, c_is_f32, accumulate, bias, residual, ldr, alpha, stream_);
+}
+
+extern "C" int prl_gemm_ex(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb,
+                           int32_t b_mn_major, int64_t M, int64_t N, int64_t K, void* C, int64_t ldc, int32_t c_is_f32,
+                           int32_t accumulate, const void* bias, const void* residual, int64_t ldr, float alpha,
+                           prl_stream_t stream_) {
   PRL_CHECK_ARG(A && B && C, "prl_gemm_tn: NULL argument");
   PRL_CHECK_ARG(M >= 1 && N >= 1 && K >= 8, "prl_gemm_tn: need M, N >= 1 and K >= 8 (M=%lld N=%lld K=%lld)", (long long)M,
                 (long long)N, (long long)K);
-  PRL_CHECK_ARG(lda >= K && ldb >= K && lda % 8 == 0 && ldb % 8 == 0,
-                "prl_gemm_tn: operand row strides must be >= K and multiples of 8 elements (lda=%lld ldb=%lld K=%lld)",
+  PRL_CHECK_ARG(lda >= (a_mn_major ? M : K) && ldb >= (b_mn_major ? N : K) && lda % 8 == 0 && ldb % 8 == 0,
+                "prl_gemm_tn: operand row strides must cover a row and be multiples of 8 elements (lda=%lld ldb=%lld K=%lld)",
                 (long long)lda, (long long)ldb, (long long)K);
   PRL_CHECK_ARG(ldc >= N, "prl_gemm_tn: ldc %lld < N %lld", (long long)ldc, (long long)N);
   PRL_CHECK_ARG(!accumulate || c_is_f32, "prl_gemm_tn: accumulate needs an fp32 output");
@@ -402,10 +424,14 @@ extern "C" int prl_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ld
   p.residual = (const __nv_bfloat16*)residual;
   p.ldr = ldr;
   p.alpha = alpha;
+  p.a_mn = a_mn_major ? 1 : 0;
+  p.b_mn = b_mn_major ? 1 : 0;
   CUtensorMap ta, tb;
-  int rc = make_tmap_2d_bf16(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBK, kHalf);
+  int rc = a_mn_major ? make_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, kBK)
+                      : make_tmap_2d_bf16(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBK, kHalf);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBK, kHalf);
+  rc = b_mn_major ? make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, kBK)
+                  : make_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBK, kHalf);
   if (rc) return rc;
   const int smem = kStages * kStageBytes + 1024 + 8 * (2 * kStages + 4) + 16;
   static bool configured = false;

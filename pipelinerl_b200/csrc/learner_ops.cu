@@ -11,7 +11,7 @@ namespace {
 
 constexpr int kRowThreads = 256;
 constexpr int kMaxVec = 4;          // 8-element vectors per thread -> rows of up to 8192 elements
-constexpr int kPartialBlocks = 296; // 2 per SM: grid of the persistent row kernels = rows of the partial workspace
+constexpr int kPartialBlocks = 592; // 4 per SM: grid of the persistent row kernels = rows of the partial workspace
 
 struct Vec8 { float v[8]; };
 
@@ -48,6 +48,7 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
 }
 
 // y = bf16(x * rstd) * gamma  (the rounding order of HF's Qwen2RMSNorm); rstd kept for the backward
+template <int kVec>
 __global__ void __launch_bounds__(kRowThreads) rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                                   const __nv_bfloat16* __restrict__ gamma, int64_t T,
                                                                   int H, float eps, __nv_bfloat16* __restrict__ y,
@@ -55,10 +56,10 @@ __global__ void __launch_bounds__(kRowThreads) rmsnorm_fwd_kernel(const __nv_bfl
   __shared__ float s_red[kRowThreads / 32];
   const int nvec = H >> 3;
   for (int64_t row = blockIdx.x; row < T; row += gridDim.x) {
-    Vec8 xv[kMaxVec];
+    Vec8 xv[kVec];
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < kVec; ++i) {
       const int v = threadIdx.x + i * kRowThreads;
       if (v < nvec) {
         xv[i] = load8(x + row * H + v * 8);
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(kRowThreads) rmsnorm_fwd_kernel(const __nv_bfl
     const float r = rsqrtf(block_sum(ss, s_red) / (float)H + eps);
     if (threadIdx.x == 0) rstd[row] = r;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < kVec; ++i) {
       const int v = threadIdx.x + i * kRowThreads;
       if (v < nvec) {
         const Vec8 g = load8(gamma + v * 8);
@@ -83,7 +84,8 @@ __global__ void __launch_bounds__(kRowThreads) rmsnorm_fwd_kernel(const __nv_bfl
 }
 
 // dx = dres + rstd * (dy*gamma - xhat * mean(dy*gamma*xhat));  partial[block][c] = sum over this block's rows of dy*xhat
-__global__ void __launch_bounds__(kRowThreads) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+template <int kVec>
+__global__ void __launch_bounds__(kRowThreads, kVec <= 2 ? 3 : 1) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                                   const __nv_bfloat16* __restrict__ gamma,
                                                                   const float* __restrict__ rstd,
                                                                   const __nv_bfloat16* __restrict__ dy,
@@ -92,9 +94,9 @@ __global__ void __launch_bounds__(kRowThreads) rmsnorm_bwd_kernel(const __nv_bfl
                                                                   float* __restrict__ partial) {
   __shared__ float s_red[kRowThreads / 32];
   const int nvec = H >> 3;
-  Vec8 gv[kMaxVec], acc[kMaxVec];
+  Vec8 gv[kVec], acc[kVec];
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < kVec; ++i) {
     const int v = threadIdx.x + i * kRowThreads;
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[i].v[e] = 0.f;
@@ -102,10 +104,10 @@ __global__ void __launch_bounds__(kRowThreads) rmsnorm_bwd_kernel(const __nv_bfl
   }
   for (int64_t row = blockIdx.x; row < T; row += gridDim.x) {
     const float r = rstd[row];
-    Vec8 xh[kMaxVec], dxh[kMaxVec];
+    Vec8 xh[kVec], dxh[kVec];
     float dot = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < kVec; ++i) {
       const int v = threadIdx.x + i * kRowThreads;
       if (v < nvec) {
         xh[i] = load8(x + row * H + v * 8);
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(kRowThreads) rmsnorm_bwd_kernel(const __nv_bfl
     }
     const float m = block_sum(dot, s_red) / (float)H;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < kVec; ++i) {
       const int v = threadIdx.x + i * kRowThreads;
       if (v < nvec) {
         Vec8 o;
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(kRowThreads) rmsnorm_bwd_kernel(const __nv_bfl
     }
   }
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < kVec; ++i) {
     const int v = threadIdx.x + i * kRowThreads;
     if (v < nvec) {
       float* pp = partial + (int64_t)blockIdx.x * H + v * 8;
@@ -147,17 +149,18 @@ __global__ void __launch_bounds__(kRowThreads) rmsnorm_bwd_kernel(const __nv_bfl
   }
 }
 
+template <int kVec>
 __global__ void __launch_bounds__(kRowThreads) colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int64_t T,
                                                              int Cc, float* __restrict__ partial) {
   const int nvec = Cc >> 3;
-  Vec8 acc[kMaxVec];
+  Vec8 acc[kVec];
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i)
+  for (int i = 0; i < kVec; ++i)
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[i].v[e] = 0.f;
   for (int64_t row = blockIdx.x; row < T; row += gridDim.x) {
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < kVec; ++i) {
       const int v = threadIdx.x + i * kRowThreads;
       if (v < nvec) {
         const Vec8 d = load8(x + row * ld + v * 8);
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(kRowThreads) colsum_kernel(const __nv_bfloat16
     }
   }
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < kVec; ++i) {
     const int v = threadIdx.x + i * kRowThreads;
     if (v < nvec) {
       float* pp = partial + (int64_t)blockIdx.x * Cc + v * 8;
@@ -297,8 +300,11 @@ extern "C" int prl_rmsnorm_fwd(const void* x, const void* gamma, int64_t T, int6
                                prl_stream_t stream) {
   PRL_CHECK_ARG(x && gamma && y && rstd && T >= 1, "prl_rmsnorm_fwd: bad argument");
   PRL_ROW_ARGS("prl_rmsnorm_fwd", H);
-  rmsnorm_fwd_kernel<<<(unsigned)(T < 4 * kPartialBlocks ? T : 4 * kPartialBlocks), kRowThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, T, (int)H, eps, (__nv_bfloat16*)y, rstd);
+  const unsigned grid = (unsigned)(T < 4 * kPartialBlocks ? T : 4 * kPartialBlocks);
+#define PRL_FWD(V) rmsnorm_fwd_kernel<V><<<grid, kRowThreads, 0, (cudaStream_t)stream>>>( \
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, T, (int)H, eps, (__nv_bfloat16*)y, rstd)
+  if (H <= 2048) PRL_FWD(1); else if (H <= 4096) PRL_FWD(2); else PRL_FWD(4);
+#undef PRL_FWD
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }
@@ -310,9 +316,11 @@ extern "C" int prl_rmsnorm_bwd(const void* x, const void* gamma, const float* rs
   PRL_ROW_ARGS("prl_rmsnorm_bwd", H);
   PRL_CHECK_ARG(workspace_bytes >= prl_rowops_workspace_bytes(H), "prl_rmsnorm_bwd: workspace too small");
   const int g = row_grid(T);
-  rmsnorm_bwd_kernel<<<g, kRowThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, rstd, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dres, T,
-      (int)H, (__nv_bfloat16*)dx, (float*)workspace);
+#define PRL_BWD(V) rmsnorm_bwd_kernel<V><<<g, kRowThreads, 0, (cudaStream_t)stream>>>( \
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, rstd, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dres, T, \
+      (int)H, (__nv_bfloat16*)dx, (float*)workspace)
+  if (H <= 2048) PRL_BWD(1); else if (H <= 4096) PRL_BWD(2); else PRL_BWD(4);
+#undef PRL_BWD
   PRL_LAUNCH_CHECK();
   partial_reduce_kernel<<<(unsigned)((H + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, g, (int)H,
                                                                                        dgamma);
@@ -326,7 +334,10 @@ extern "C" int prl_colsum_bf16(const void* x, int64_t ld, int64_t T, int64_t col
   PRL_ROW_ARGS("prl_colsum_bf16", cols);
   PRL_CHECK_ARG(workspace_bytes >= prl_rowops_workspace_bytes(cols), "prl_colsum_bf16: workspace too small");
   const int g = row_grid(T);
-  colsum_kernel<<<g, kRowThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, T, (int)cols, (float*)workspace);
+#define PRL_CS(V) colsum_kernel<V><<<g, kRowThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, T, (int)cols, \
+                                                                            (float*)workspace)
+  if (cols <= 2048) PRL_CS(1); else if (cols <= 4096) PRL_CS(2); else PRL_CS(4);
+#undef PRL_CS
   PRL_LAUNCH_CHECK();
   partial_reduce_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, g,
                                                                                           (int)cols, out);

@@ -219,6 +219,19 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major operand (the MN index is the contiguous one in memory), 128-byte swizzle: the tile is staged as
+// 64-element (128-B) MN chunks x k rows; a k row of one chunk is one 128-B line, 8 k rows form the 1024-B swizzle
+// atom (SBO = 1024 B between k groups), and the next 64-element MN chunk starts `mn_chunk_bytes` later (LBO).
+// Advancing K by 16 = 16 lines = 2048 B: +128 in the (addr >> 4) field.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t mn_chunk_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((mn_chunk_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16 with BF16 A/B, FP32 accumulate, both operands K-major.
 //   [4,6) D format: 1 = F32   [7,10) A format: 1 = BF16   [10,13) B format: 1 = BF16
 //   [15] A major (0 = K)  [16] B major (0 = K)  [17,23) N >> 3   [24,29) M >> 4

@@ -6,12 +6,12 @@ conf/finetune/base.yaml:47-50 checkpointing).  Here there is no autograd inside 
 
   forward   per layer: RMSNorm -> qkv GEMM(+bias) -> RoPE -> causal block-diagonal attention -> o GEMM(+residual)
             -> RMSNorm -> gate_up GEMM -> SiLU*up -> down GEMM(+residual); only each layer's INPUT is kept
-  backward  per layer (reverse): recompute the layer, then dgrad GEMMs against transposed weight copies and wgrad
-            GEMMs that ACCUMULATE IN FP32 straight into the optimizer's gradient arena (no .grad tensors, no
-            autograd accumulation kernels, no per-parameter allocation)
+  backward  per layer (reverse): recompute the MLP half (and the attention half where it was not kept), then dgrad
+            GEMMs that read the weights as stored and wgrad GEMMs that read both activations as stored (MN-major
+            UMMA operands: no transposed copies) and ACCUMULATE IN FP32 straight into the optimizer's gradient
+            arena (no .grad tensors, no autograd accumulation kernels, no per-parameter allocation)
 
-Every GEMM is `prl_gemm_tn` (csrc/gemm_tn.cu, persistent CTA-pair tcgen05 kernel); the K-major operands of wgrad
-are staged by `prl_transpose_bf16`.  The row-wise pieces (RMSNorm, RoPE, SiLU*up, bias / gain reductions, embedding
+Every GEMM is `prl_gemm_ex` (csrc/gemm_tn.cu, persistent CTA-pair tcgen05 kernel).  The row-wise pieces (RMSNorm, RoPE, SiLU*up, bias / gain reductions, embedding
 scatter) are the kernels of csrc/learner_ops.cu.  Attention inside the learner is the one library call left
 (torch SDPA = a flash-attention library kernel): its sm_100a replacement is the next kernel on this path.
 """
@@ -36,21 +36,30 @@ class Ops:
     def __init__(self):
         self.lib = _lib.load()
 
-    # C[M,N] (=|+=) A[M,K] B[N,K]^T (+bias) (+residual)
-    def gemm(self, A, B, out=None, out_dtype=torch.bfloat16, bias=None, residual=None, accumulate=False, alpha=1.0):
-        M, K = A.shape
-        N = B.shape[0]
-        assert B.shape[1] == K and A.stride(1) == 1 and B.stride(1) == 1
+    # C[M,N] (=|+=) A[M,K] B[N,K]^T (+bias) (+residual); a_mn / b_mn: that operand is passed as stored [K, M] / [K, N]
+    def gemm(self, A, B, out=None, out_dtype=torch.bfloat16, bias=None, residual=None, accumulate=False, alpha=1.0,
+             a_mn=False, b_mn=False):
+        (K, M) = A.shape if a_mn else A.shape[::-1]
+        (Kb, N) = B.shape if b_mn else B.shape[::-1]
+        assert K == Kb and A.stride(1) == 1 and B.stride(1) == 1
         if out is None:
             out = torch.empty(M, N, dtype=out_dtype, device=A.device)
         assert out.shape == (M, N) and out.stride(1) == 1
-        _lib.check(self.lib.prl_gemm_tn(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, out.data_ptr(),
-                                        out.stride(0), int(out.dtype == torch.float32), int(accumulate),
+        _lib.check(self.lib.prl_gemm_ex(A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(), B.stride(0), int(b_mn), M, N, K,
+                                        out.data_ptr(), out.stride(0), int(out.dtype == torch.float32), int(accumulate),
                                         bias.data_ptr() if bias is not None else None,
                                         residual.data_ptr() if residual is not None else None,
                                         residual.stride(0) if residual is not None else 0, float(alpha),
                                         _lib.stream_ptr()))
         return out
+
+    def dgrad(self, dY, W):
+        """dX[T, in] = dY[T, out] W[out, in]: the weight is read as stored (MN-major B operand)"""
+        return self.gemm(dY, W, b_mn=True)
+
+    def wgrad(self, G, dY, X):
+        """G[out, in] (fp32) += dY[T, out]^T X[T, in]: both activations read as stored (MN-major operands, K = tokens)"""
+        self.gemm(dY, X, out=G, accumulate=True, a_mn=True, b_mn=True)
 
     def transpose(self, x, out=None):
         R, Cc = x.shape
@@ -61,10 +70,6 @@ class Ops:
         _lib.check(self.lib.prl_transpose_bf16(x.data_ptr(), R, Cc, x.stride(0), out.data_ptr(), out.stride(0),
                                                _lib.stream_ptr()))
         return out
-
-    def wgrad(self, G, dY, X):
-        """G[out, in] (fp32) += dY[T, out]^T X[T, in]"""
-        self.gemm(self.transpose(dY), self.transpose(X), out=G, accumulate=True)
 
     def rmsnorm(self, x, gamma, eps):
         T, H = x.shape
@@ -124,8 +129,7 @@ class Ops:
 
 class NativeBody:
     """weights: fused name -> bf16 tensor (views of the parameter arena); grads: fused name -> fp32 tensor
-    (views of the optimizer's gradient arena).  `refresh()` must be called after every optimizer step: it rebuilds
-    the transposed weight copies the dgrad GEMMs read."""
+    (views of the optimizer's gradient arena)."""
 
     def __init__(self, cfg: ModelConfig, weights: dict[str, torch.Tensor], grads: dict[str, torch.Tensor]):
         self.cfg, self.w, self.g = cfg, weights, grads
@@ -133,28 +137,11 @@ class NativeBody:
         dev = next(iter(weights.values())).device
         d = cfg.head_dim
         self.inv_freq = (1.0 / (cfg.rope_theta ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))).to(dev)
-        self.wt: dict[str, torch.Tensor] = {}
-        self.refresh()
         self._saved = None
         self.keep_attention_layers = cfg.num_layers   # lower it when activation memory is short (0 = full recompute)
 
-    def _gemm_names(self):
-        for l in range(self.cfg.num_layers):
-            for k in ("qkv_proj", "o_proj", "gate_up_proj", "down_proj"):
-                yield f"layers.{l}.{k}.weight"
-        if "lm_head.weight" in self.w:
-            yield "lm_head.weight"
-
-    def head_t(self) -> torch.Tensor:
-        return self.wt["lm_head.weight"]
-
     def refresh(self) -> None:
-        for name in self._gemm_names():
-            w = self.w[name]
-            if name not in self.wt:
-                buf = torch.empty(w.shape[1], _ru(w.shape[0], 8), dtype=torch.bfloat16, device=w.device)
-                self.wt[name] = buf[:, : w.shape[0]]
-            self.ops.transpose(w, out=self.wt[name])
+        """Hook called after every optimizer step.  Nothing to rebuild: dgrad reads the weights as stored."""
 
     # ---- attention (library call for now): q, k roped; block-diagonal causal over the packed segments ----
     def _attention(self, qkv, bounds, need_grad):
@@ -205,44 +192,44 @@ class NativeBody:
         h2 = o.gemm(attn, w[p + "o_proj.weight"], residual=h)
         return x1, rstd1, attn, graph, h2
 
-    def _mlp_half(self, l, h2):
+    def _mlp_half(self, l, h2, need_out=True):
         c, o, w = self.cfg, self.ops, self.w
         p = f"layers.{l}."
         x2, rstd2 = o.rmsnorm(h2, w[p + "post_attention_layernorm.weight"], c.rms_eps)
         gu = o.gemm(x2, w[p + "gate_up_proj.weight"])
         act = o.silu_mul(gu)
-        h3 = o.gemm(act, w[p + "down_proj.weight"], residual=h2)
+        h3 = o.gemm(act, w[p + "down_proj.weight"], residual=h2) if need_out else None  # the backward only needs act
         return x2, rstd2, gu, act, h3
 
     def _layer_bwd(self, l, h, saved, pos, bounds, dh3):
-        c, o, w, g, wt = self.cfg, self.ops, self.w, self.g, self.wt
+        c, o, w, g = self.cfg, self.ops, self.w, self.g
         p = f"layers.{l}."
         if saved is None:   # full recompute of the layer from its input
             x1, rstd1, attn, graph, h2 = self._attn_half(l, h, pos, bounds, need_grad=True)
         else:               # attention half was kept by the forward: only the (cheap) norm is redone
             attn, graph, h2 = saved
             x1, rstd1 = o.rmsnorm(h, w[p + "input_layernorm.weight"], c.rms_eps)
-        x2, rstd2, gu, act, _ = self._mlp_half(l, h2)
+        x2, rstd2, gu, act, _ = self._mlp_half(l, h2, need_out=False)
         T = h.shape[0]
-        d_act = o.gemm(dh3, wt[p + "down_proj.weight"])
+        d_act = o.dgrad(dh3, w[p + "down_proj.weight"])
         o.wgrad(g[p + "down_proj.weight"], dh3, act)
         del act
         d_gu = o.silu_mul_bwd(gu, d_act)
         del gu, d_act
-        dx2 = o.gemm(d_gu, wt[p + "gate_up_proj.weight"])
+        dx2 = o.dgrad(d_gu, w[p + "gate_up_proj.weight"])
         o.wgrad(g[p + "gate_up_proj.weight"], d_gu, x2)
         del d_gu, x2
         dh2 = o.rmsnorm_bwd(h2, w[p + "post_attention_layernorm.weight"], rstd2, dx2, dh3,
                             g[p + "post_attention_layernorm.weight"])
         del dx2, h2
-        d_attn = o.gemm(dh2, wt[p + "o_proj.weight"])
+        d_attn = o.dgrad(dh2, w[p + "o_proj.weight"])
         o.wgrad(g[p + "o_proj.weight"], dh2, attn)
         dqkv = self._attention_bwd(graph, bounds, d_attn, T)
         del graph, attn, d_attn
         o.rope_(dqkv, pos, self.inv_freq, c.num_q_heads + c.num_kv_heads, c.head_dim, -1.0)
         if c.qkv_bias:
             o.colsum_acc(dqkv, g[p + "qkv_proj.bias"])
-        dx1 = o.gemm(dqkv, wt[p + "qkv_proj.weight"])
+        dx1 = o.dgrad(dqkv, w[p + "qkv_proj.weight"])
         o.wgrad(g[p + "qkv_proj.weight"], dqkv, x1)
         del dqkv, x1
         return o.rmsnorm_bwd(h, w[p + "input_layernorm.weight"], rstd1, dx1, dh2, g[p + "input_layernorm.weight"])

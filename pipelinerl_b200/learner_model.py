@@ -115,8 +115,8 @@ class TorchQwen2(torch.nn.Module):
 class _NativeHead(torch.autograd.Function):
     """Final projection + log-softmax statistics of the native learner.  Forward: one tcgen05 GEMM whose epilogue
     reduces logits in TMEM (prl_head_logprob).  Backward: per chunk of rows, logits recomputed by the same kernel,
-    d logits formed in one pass (prl_logprob_rows_bwd), then dX = dZ W (prl_gemm_tn against the transposed head) and
-    dW += dZ^T X accumulated in fp32 in the optimizer's gradient arena."""
+    d logits formed in one pass (prl_logprob_rows_bwd), then dX = dZ W and dW += dZ^T X (prl_gemm_ex, operands read as
+    stored), the latter accumulated in fp32 in the optimizer's gradient arena."""
 
     @staticmethod
     def forward(ctx, hidden, model, targets, temperature: float, chunk_rows: int):
@@ -142,7 +142,7 @@ class _NativeHead(torch.autograd.Function):
         model, lib = ctx.model, _lib.load()
         body = model.body
         ops = body.ops
-        W, Wt, gW = model.p("lm_head.weight").data, body.head_t(), body.g["lm_head.weight"]
+        W, gW = model.p("lm_head.weight").data, body.g["lm_head.weight"]
         M, K = x.shape
         V = W.shape[0]
         dev = x.device
@@ -164,7 +164,7 @@ class _NativeHead(torch.autograd.Function):
                                                 g_ent[r0:r0 + n].data_ptr() if use_ent else None,
                                                 dlogits.data_ptr(), V, st))
             dz = dlogits.to(torch.bfloat16)
-            ops.gemm(dz, Wt, out=dx[r0:r0 + n])
+            ops.gemm(dz, W, out=dx[r0:r0 + n], b_mn=True)
             ops.wgrad(gW, dz, xs)
         return dx, None, None, None, None
 
@@ -172,8 +172,7 @@ class _NativeHead(torch.autograd.Function):
 class NativeQwen2(torch.nn.Module):
     """Learner model whose body is learner_body.NativeBody (hand-scheduled tcgen05 GEMMs + row kernels, fp32
     gradient accumulation in the optimizer arena).  bf16 parameters in the fused arena order; must be bound to a
-    FusedAdamW(grad_dtype=torch.float32) with `bind(optimizer)` before the first step, and
-    `after_optimizer_step()` must follow every optimizer step (refreshes the transposed weight copies)."""
+    FusedAdamW(grad_dtype=torch.float32) with `bind(optimizer)` before the first step."""
 
     use_fused_head = True
 

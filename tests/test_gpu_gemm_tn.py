@@ -97,3 +97,30 @@ def test_gemm_tn_rejects_bad_arguments(cuda_device):
     rc = lib.prl_gemm_tn(A.data_ptr(), 24, A.data_ptr(), 24, 16, 16, 16, C.data_ptr(), 16, 0, 1, None, None, 0, 1.0,
                          _lib.stream_ptr())
     assert rc != 0 and b"accumulate" in lib.prl_last_error()
+
+
+def gemm_ex(A, a_mn, B, b_mn, M, N, K, out_dtype=torch.float32, acc_into=None):
+    """A given as [K, M] when a_mn else [M, K]; B as [K, N] when b_mn else [N, K]."""
+    from pipelinerl_b200 import _lib
+    lib = _lib.load()
+    C = acc_into if acc_into is not None else torch.full((M, N), float("nan"), dtype=out_dtype, device=A.device)
+    _lib.check(lib.prl_gemm_ex(A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(), B.stride(0), int(b_mn), M, N, K,
+                               C.data_ptr(), C.stride(0), int(C.dtype == torch.float32), int(acc_into is not None), None,
+                               None, 0, 1.0, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    return C
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (304, 776, 200), (1000, 520, 1288), (4608, 3584, 2048), (24, 72, 136)])
+def test_gemm_mn_major_operands(cuda_device, M, N, K, a_mn, b_mn):
+    """dgrad reads W as stored (B MN-major), wgrad reads dY and X as stored (both MN-major): no transposed copies."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
+    B = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).to(cuda_device)
+    want = A.float() @ B.float().t()
+    got = gemm_ex(A.t().contiguous() if a_mn else A, a_mn, B.t().contiguous() if b_mn else B, b_mn, M, N, K)
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item() + 1e-6
+    ref = gemm_ex(A, False, B, False, M, N, K)
+    assert torch.equal(got, ref)    # same products, same k order: bitwise equal to the K-major path

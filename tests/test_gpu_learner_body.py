@@ -167,8 +167,7 @@ def test_native_body_matches_fp32_autograd(cuda_device, kind, lens):
 
 
 def test_native_model_trains_through_rl_step(cuda_device):
-    """rl_step + FusedAdamW on the native learner: loss/grad-norm agree with the fp32 torch learner on the same batch,
-    and after the optimizer step the transposed weight copies follow the parameters."""
+    """rl_step + FusedAdamW on the native learner: loss/grad-norm agree with the fp32 torch learner on the same batch."""
     from pipelinerl_b200.finetune.optim import FusedAdamW
     from pipelinerl_b200.finetune.rl import RLConfig, rl_step
     from pipelinerl_b200.learner_model import NativeQwen2, TorchQwen2
@@ -198,8 +197,6 @@ def test_native_model_trains_through_rl_step(cuda_device):
         out[kind] = (loss.item(), norm)
         if kind == "native":
             model.after_optimizer_step()
-            name = "layers.1.gate_up_proj.weight"
-            assert torch.equal(model.body.wt[name], model.p(name).data.t())
     (l_n, g_n), (l_f, g_f) = out["native"], out["fp32"]
     assert abs(l_n - l_f) <= 2e-2 * max(1.0, abs(l_f)), (l_n, l_f)
     assert abs(g_n - g_f) <= 5e-2 * g_f, (g_n, g_f)

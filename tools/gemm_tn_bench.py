@@ -50,6 +50,30 @@ def main():
                      "cublas_ms": round(t_c, 4), "cublas_TFLOPs": round(fl / t_c / 1e9, 1)}
         print(name, out[name], flush=True)
         del A, B, C
+    # operands as stored (MN-major): dgrad reads W [out, in] as B[K=out, N=in]; wgrad reads dY [T, out], X [T, in]
+    mn = {"down dgrad (B mn)": (T, 18944, 3584, False, True), "gate_up dgrad (B mn)": (T, 3584, 37888, False, True),
+          "gate_up wgrad (A,B mn)": (37888, 3584, T, True, True), "down wgrad (A,B mn)": (3584, 18944, T, True, True),
+          "qkv wgrad (A,B mn)": (4608, 3584, T, True, True)}
+    for name, (M, N, K, a_mn, b_mn) in mn.items():
+        A = (torch.randn((K, M) if a_mn else (M, K), device=dev) * 0.1).to(torch.bfloat16)
+        B = (torch.randn((K, N) if b_mn else (N, K), device=dev) * 0.1).to(torch.bfloat16)
+        f32 = "wgrad" in name
+        C = torch.zeros(M, N, dtype=torch.float32 if f32 else torch.bfloat16, device=dev)
+        st = _lib.stream_ptr()
+
+        def ours():
+            _lib.check(lib.prl_gemm_ex(A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(), B.stride(0), int(b_mn), M, N, K,
+                                       C.data_ptr(), N, int(f32), int(f32), None, None, 0, 1.0, st))
+        Am, Bm = (A.t() if a_mn else A), (B if b_mn else B.t())
+
+        def cublas():
+            torch.mm(Am, Bm)
+        t_o, t_c = time_ms(ours), time_ms(cublas)
+        fl = 2.0 * M * N * K
+        out[name] = {"M": M, "N": N, "K": K, "ours_ms": round(t_o, 4), "ours_TFLOPs": round(fl / t_o / 1e9, 1),
+                     "cublas_ms": round(t_c, 4), "cublas_TFLOPs": round(fl / t_c / 1e9, 1)}
+        print(name, out[name], flush=True)
+        del A, B, C
     x = torch.randn(T, 18944, device=dev).to(torch.bfloat16)
     y = torch.empty(18944, T, dtype=torch.bfloat16, device=dev)
     t = time_ms(lambda: _lib.check(lib.prl_transpose_bf16(x.data_ptr(), T, 18944, 18944, y.data_ptr(), T, _lib.stream_ptr())))

@@ -44,43 +44,42 @@ def synthetic_batch(cfg, T, n_samples, dev, seed):
     return b.to_device(dev)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--model", default="7b")
-    ap.add_argument("--tokens", type=int, default=16384)
-    ap.add_argument("--samples-per-row", type=int, default=1)
-    ap.add_argument("--micro", type=int, default=2, help="micro-batches per optimizer step")
-    ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--warmup", type=int, default=1)
-    ap.add_argument("--layers", type=int, default=0, help="override the layer count (debug)")
-    ap.add_argument("--keep-attn", type=int, default=-1, help="layers whose attention half is kept for backward (-1 = all)")
-    ap.add_argument("--profile", action="store_true", help="after the timed steps, print the per-kernel CUDA time of one step")
-    a = ap.parse_args()
-    dev = torch.device("cuda:0")
+def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, warmup=1, layers=0, keep_attn=-1,
+            profile=False, dev=None, log=True):
+    """Run the trainer step and return the result dict (also used by bench.py's `components.trainer_step`)."""
+    dev = dev or torch.device("cuda:0")
     torch.cuda.set_device(dev)
-    cfg = ModelConfig.qwen2_5_7b() if a.model == "7b" else ModelConfig.tiny()
-    if a.layers:
+    try:  # ~170 GB of the 192 GB are live at the peak: growable segments keep the caching allocator from fragmenting
+        torch.cuda.memory._set_allocator_settings("expandable_segments:True")
+    except Exception:  # noqa: BLE001
+        pass
+    cfg = ModelConfig.qwen2_5_7b() if model_name == "7b" else ModelConfig.tiny()
+    if layers:
         from dataclasses import replace
-        cfg = replace(cfg, num_layers=a.layers)
+        cfg = replace(cfg, num_layers=layers)
+
+    def say(msg):
+        if log:
+            print(f"[train_bench] {msg}", file=sys.stderr, flush=True)
     t0 = time.time()
     model = NativeQwen2(cfg, dev)
     opt = FusedAdamW(model.named_parameters(), lr=1e-6, weight_decay=0.01, max_grad_norm=0.3, grad_dtype=torch.float32)
     model.bind(opt)
-    if a.keep_attn >= 0:
-        model.body.keep_attention_layers = a.keep_attn
+    if keep_attn >= 0:
+        model.body.keep_attention_layers = keep_attn
     torch.cuda.synchronize()
-    print(f"[train_bench] model + optimizer state resident: {torch.cuda.memory_allocated() / 1e9:.1f} GB "
-          f"({time.time() - t0:.1f} s)", file=sys.stderr, flush=True)
-    n_samples_step = a.micro * a.samples_per_row
+    say(f"model + optimizer state resident: {torch.cuda.memory_allocated() / 1e9:.1f} GB ({time.time() - t0:.1f} s)")
+    n_samples_step = micro * samples_per_row
     rcfg = RLConfig(batch_size=n_samples_step)   # reference defaults: ppo, kl_coef 0.1, temperature 1.0
-    batches = [synthetic_batch(cfg, a.tokens, a.samples_per_row, dev, 100 + i) for i in range(a.micro)]
+    batches = [synthetic_batch(cfg, tokens, samples_per_row, dev, 100 + i) for i in range(micro)]
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     launches0 = None
     rec = []
-    for step in range(a.warmup + a.steps):
-        if step == a.warmup:
+    torch.cuda.reset_peak_memory_stats()
+    for step in range(warmup + steps):
+        if step == warmup:
             launches0 = _lib.launch_count()
-        e = [ev() for _ in range(2 * a.micro + 3)]
+        e = [ev() for _ in range(2 * micro + 3)]
         opt.zero_grad()
         e[0].record()
         losses = []
@@ -94,16 +93,16 @@ def main():
         model.after_optimizer_step()
         e[-1].record()
         torch.cuda.synchronize()
-        fwd = sum(e[2 * i].elapsed_time(e[2 * i + 1]) for i in range(a.micro))
-        bwd = sum(e[2 * i + 1].elapsed_time(e[2 * i + 2]) for i in range(a.micro))
-        optm = e[2 * a.micro].elapsed_time(e[-1])
+        fwd = sum(e[2 * i].elapsed_time(e[2 * i + 1]) for i in range(micro))
+        bwd = sum(e[2 * i + 1].elapsed_time(e[2 * i + 2]) for i in range(micro))
+        optm = e[2 * micro].elapsed_time(e[-1])
         total = e[0].elapsed_time(e[-1])
         rec.append((total, fwd, bwd, optm, float(sum(losses)), float(gn)))
-        print(f"[train_bench] step {step}: {total:.1f} ms (fwd {fwd:.1f} bwd {bwd:.1f} opt {optm:.1f}) loss {rec[-1][4]:.5f} "
-              f"grad_norm {rec[-1][5]:.4f} peak {torch.cuda.max_memory_allocated() / 1e9:.1f} GB", file=sys.stderr, flush=True)
-    if a.profile:
-        from torch.profiler import ProfilerActivity, profile
-        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        say(f"step {step}: {total:.1f} ms (fwd {fwd:.1f} bwd {bwd:.1f} opt {optm:.1f}) loss {rec[-1][4]:.5f} "
+            f"grad_norm {rec[-1][5]:.4f} peak {torch.cuda.max_memory_allocated() / 1e9:.1f} GB")
+    if profile:
+        from torch.profiler import ProfilerActivity, profile as tprofile
+        with tprofile(activities=[ProfilerActivity.CUDA]) as prof:
             opt.zero_grad()
             for b in batches:
                 loss, _ = rl_step(model, b, 0, 1000, rcfg)
@@ -113,32 +112,52 @@ def main():
             torch.cuda.synchronize()
         print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=70),
               file=sys.stderr, flush=True)
-    timed = rec[a.warmup:]
+    timed = rec[warmup:]
     ms = sum(r[0] for r in timed) / len(timed)
-    tokens = a.micro * a.tokens
+    total_tokens = micro * tokens
     c = cfg
     body_params = c.num_layers * (c.qkv_size * c.hidden_size + c.hidden_size * c.q_size + 3 * c.hidden_size * c.intermediate_size)
     head_params = c.vocab_size * c.hidden_size
-    per_seg = a.tokens // a.samples_per_row
-    attn_fwd = 4.0 * c.num_layers * c.num_q_heads * c.head_dim * (per_seg * (per_seg + 1) / 2) * a.samples_per_row
-    # model FLOPs (no recompute counted): 6 N per token + attention fwd (1x) + bwd (2.5x)... standard 3x convention
-    model_flops = a.micro * (6.0 * (body_params + head_params) * a.tokens + 3.0 * attn_fwd)
-    hw_flops = a.micro * (8.0 * body_params * a.tokens + 8.0 * head_params * a.tokens + 4.5 * attn_fwd)  # + recompute
+    per_seg = tokens // samples_per_row
+    attn_fwd = 4.0 * c.num_layers * c.num_q_heads * c.head_dim * (per_seg * (per_seg + 1) / 2) * samples_per_row
+    # model FLOPs: 6 N per token + causal attention (forward 1x + backward 2x); recompute is NOT counted
+    model_flops = micro * (6.0 * (body_params + head_params) * tokens + 3.0 * attn_fwd)
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     peak = peaks.get("bf16_tflops_sustained", 1459.7)
-    out = {"bench": "trainer_step", "model": "Qwen2.5-7B" if a.model == "7b" else "tiny", "layers": c.num_layers,
-           "tokens_per_micro_batch": a.tokens, "samples_per_micro_batch": a.samples_per_row, "micro_batches_per_step": a.micro,
+    out = {"bench": "trainer_step", "model": "Qwen2.5-7B" if model_name == "7b" else "tiny", "layers": c.num_layers,
+           "tokens_per_micro_batch": tokens, "samples_per_micro_batch": samples_per_row, "micro_batches_per_step": micro,
            "samples_per_optimizer_step": n_samples_step, "ms_per_optimizer_step": round(ms, 2),
-           "optimizer_steps_per_s": round(1000.0 / ms, 5), "trainer_tokens_per_s": round(tokens / ms * 1000.0, 1),
+           "optimizer_steps_per_s": round(1000.0 / ms, 5), "trainer_tokens_per_s": round(total_tokens / ms * 1000.0, 1),
            "fwd_ms": round(sum(r[1] for r in timed) / len(timed), 2), "bwd_ms": round(sum(r[2] for r in timed) / len(timed), 2),
            "opt_ms": round(sum(r[3] for r in timed) / len(timed), 2),
-           "model_TFLOPs": round(model_flops / ms / 1e9, 1), "hardware_TFLOPs_with_recompute": round(hw_flops / ms / 1e9, 1),
+           "model_TFLOPs": round(model_flops / ms / 1e9, 1),
            "mfu_vs_measured_sustained_peak": round(model_flops / ms / 1e9 / peak, 4), "peak_TFLOPs": peak,
-           "libprl_launches_per_step": (_lib.launch_count() - launches0) // max(1, a.steps),
+           "libprl_launches_per_step": (_lib.launch_count() - launches0) // max(1, steps),
            "peak_memory_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1),
-           "loss": rec[-1][4], "grad_norm": rec[-1][5],
-           "attention": "torch SDPA (library)", "keep_attention_layers": model.body.keep_attention_layers, "gemm": "prl_gemm_tn (tcgen05 cta_group::2)"}
-    print(json.dumps(out))
+           "loss": rec[-1][4], "grad_norm": rec[-1][5], "grad_accumulation": "fp32 in the optimizer arena",
+           "attention": "torch SDPA (library)", "keep_attention_layers": model.body.keep_attention_layers,
+           "gemm": "prl_gemm_ex (tcgen05 cta_group::2, MN-major dgrad/wgrad operands)"}
+    del model, opt, batches
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="7b")
+    ap.add_argument("--tokens", type=int, default=16384)
+    ap.add_argument("--samples-per-row", type=int, default=1)
+    ap.add_argument("--micro", type=int, default=2, help="micro-batches per optimizer step")
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--layers", type=int, default=0, help="override the layer count (debug)")
+    ap.add_argument("--keep-attn", type=int, default=-1, help="layers whose attention half is kept for backward (-1 = all)")
+    ap.add_argument("--profile", action="store_true", help="after the timed steps, print the per-kernel CUDA time of one step")
+    a = ap.parse_args()
+    print(json.dumps(measure(a.model, a.tokens, a.samples_per_row, a.micro, a.steps, a.warmup, a.layers, a.keep_attn,
+                             a.profile)))
 
 
 if __name__ == "__main__":
