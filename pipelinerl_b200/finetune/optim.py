@@ -162,7 +162,8 @@ class ShardedFusedAdamW:
     """
 
     def __init__(self, named_params, lr: float, weight_decay: float = 0.01, betas=(0.9, 0.999), eps: float = 1e-8,
-                 max_grad_norm: float | None = None, no_decay: Iterable[str] = NO_DECAY_DEFAULT, group=None):
+                 max_grad_norm: float | None = None, no_decay: Iterable[str] = NO_DECAY_DEFAULT, group=None,
+                 grad_accum_fp32: bool = False):
         import torch.distributed as dist
         from ..weights import ipc_alloc, ipc_export, ipc_open
         if not (dist.is_available() and dist.is_initialized()):
@@ -197,6 +198,9 @@ class ShardedFusedAdamW:
         self.master = torch.zeros(shard, dtype=torch.float32, device=dev)
         self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.master), torch.zeros_like(self.master)
         self.gsum = torch.zeros_like(self.master)
+        # micro-batch accumulation in fp32 (learner_body.NativeBody writes here through grad_views()); the exchange
+        # itself stays bf16: one cast pass per optimizer step fills the IPC gradient arena
+        self.grad_f32 = torch.zeros(self.n, dtype=torch.float32, device=dev) if grad_accum_fp32 else None
         with torch.no_grad():
             for p, off in zip(self.params, offsets):
                 k = p.numel()
@@ -228,7 +232,11 @@ class ShardedFusedAdamW:
         self.last_phase_ms = (0.0, 0.0)
 
     def zero_grad(self, set_to_none: bool = False) -> None:
-        self.grad.zero_()
+        (self.grad_f32 if self.grad_f32 is not None else self.grad).zero_()
+
+    def grad_views(self) -> dict[str, torch.Tensor]:
+        src = self.grad_f32 if self.grad_f32 is not None else self.grad
+        return {n: src[o:o + p.numel()].view(p.shape) for n, p, o in zip(self.names, self.params, self.offsets)}
 
     def _args(self) -> _lib.AdamwShardArgs:
         a = _lib.AdamwShardArgs()
@@ -254,6 +262,8 @@ class ShardedFusedAdamW:
         a = self._args()
         a.grad_scale = grad_scale
         st = _lib.stream_ptr()
+        if self.grad_f32 is not None:
+            self.grad.copy_(self.grad_f32)
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         self._barrier()                                   # every rank's backward has written its gradient arena
         e[0].record()

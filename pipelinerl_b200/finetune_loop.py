@@ -54,10 +54,13 @@ def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding
     if sharded:
         # learner DP: P2P reduce-scatter + AdamW shard + P2P all-gather in one exchange step (optimizer state / Ng)
         from .finetune.optim import ShardedFusedAdamW
-        opt = ShardedFusedAdamW(model.named_parameters(), lr=cfg.learning_rate, weight_decay=cfg.weight_decay,
-                                max_grad_norm=cfg.gradient_clipping_threshold, group=dp_group)
-    else:
         native = hasattr(model, "bind")   # learner_model.NativeQwen2: fp32 gradient accumulation in the arena
+        opt = ShardedFusedAdamW(model.named_parameters(), lr=cfg.learning_rate, weight_decay=cfg.weight_decay,
+                                max_grad_norm=cfg.gradient_clipping_threshold, group=dp_group, grad_accum_fp32=native)
+        if native:
+            model.bind(opt)
+    else:
+        native = hasattr(model, "bind")
         opt = FusedAdamW(model.named_parameters(), lr=cfg.learning_rate, weight_decay=cfg.weight_decay,
                          max_grad_norm=cfg.gradient_clipping_threshold,
                          grad_dtype=torch.float32 if native else None)

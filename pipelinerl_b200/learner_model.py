@@ -205,10 +205,12 @@ class NativeQwen2(torch.nn.Module):
 
     def bind(self, optimizer) -> None:
         from .learner_body import NativeBody
-        if optimizer.grad.dtype != torch.float32:
-            raise ValueError("NativeQwen2 accumulates gradients in fp32: build FusedAdamW(grad_dtype=torch.float32)")
+        grads = optimizer.grad_views()
+        if any(g.dtype != torch.float32 for g in grads.values()):
+            raise ValueError("NativeQwen2 accumulates gradients in fp32: build FusedAdamW(grad_dtype=torch.float32) "
+                             "or ShardedFusedAdamW(grad_accum_fp32=True)")
         weights = {n: self.p(n).data for n in self.names}
-        self.body = NativeBody(self.cfg, weights, optimizer.grad_views())
+        self.body = NativeBody(self.cfg, weights, grads)
 
     def after_optimizer_step(self) -> None:
         self.body.refresh()

@@ -50,3 +50,17 @@ def test_two_gpu_tensor_parallel_engine_matches_oracle():
     assert res.returncode == 0, res.stderr[-3000:]
     out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
     assert out["ok"]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_native_learners_match_single_learner():
+    """Two data-parallel native learners (fp32 micro-batch accumulation, bf16 P2P exchange fused with AdamW) end with
+    bit-identical parameters on both ranks that equal the single-learner result on all micro-batches (to bf16
+    exchange rounding)."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29586")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29586", str(ROOT / "tools" / "train_bench.py"),
+                          "--check"], capture_output=True, text=True, env=env, timeout=900)
+    assert res.returncode == 0, res.stderr[-3000:]
+    outs = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
+    assert outs and all(o["ok"] for o in outs), outs

@@ -48,6 +48,14 @@ def main():
         fl = 2.0 * M * N * K
         out[name] = {"M": M, "N": N, "K": K, "ours_ms": round(t_o, 4), "ours_TFLOPs": round(fl / t_o / 1e9, 1),
                      "cublas_ms": round(t_c, 4), "cublas_TFLOPs": round(fl / t_c / 1e9, 1)}
+        if "fwd" in name:  # the prefill path: fp32 [1, M, N] output through either kernel
+            P = torch.zeros(1, M, N, dtype=torch.float32, device=dev)
+            t_sw = time_ms(lambda: _lib.check(lib.prl_gemm_bf16_splitk(B.data_ptr(), None, A.data_ptr(), M, N, K, 1,
+                                                                       P.data_ptr(), st)))
+            t_f32 = time_ms(lambda: _lib.check(lib.prl_gemm_tn(A.data_ptr(), K, B.data_ptr(), K, M, N, K, P.data_ptr(), N,
+                                                               1, 0, None, None, 0, 1.0, st)))
+            out[name].update({"swapab_pair_f32_ms": round(t_sw, 4), "tn_f32_ms": round(t_f32, 4)})
+            del P
         print(name, out[name], flush=True)
         del A, B, C
     # operands as stored (MN-major): dgrad reads W [out, in] as B[K=out, N=in]; wgrad reads dY [T, out], X [T, in]

@@ -56,6 +56,17 @@ def main():
            "group_prefix_hit_tokens": d["prefix_hit_tokens"],
            "group_effective_tokens_per_s": round(8 * (P - 1) / ms8 * 1e3)}
     print(json.dumps(out), flush=True)
+    if "--profile" in sys.argv:
+        from torch.profiler import ProfilerActivity, profile
+        eng._evict_prefixes(10 ** 9)
+        while eng.slot_req:
+            eng.step(); eng.harvest()
+        eng._evict_prefixes(10 ** 9)
+        eng.add_request(prompts[0], sp)
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            eng.run_prefill()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=12, max_name_column_width=60), file=sys.stderr)
 
 
 if __name__ == "__main__":

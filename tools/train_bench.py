@@ -46,7 +46,18 @@ def synthetic_batch(cfg, T, n_samples, dev, seed):
 
 def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, warmup=1, layers=0, keep_attn=-1,
             profile=False, dev=None, log=True):
-    """Run the trainer step and return the result dict (also used by bench.py's `components.trainer_step`)."""
+    """Run the trainer step and return the result dict (also used by bench.py's `components.trainer_step`).
+    Under torchrun (WORLD_SIZE > 1) every rank is a data-parallel learner with its own `micro` micro-batches and the
+    optimizer step is the ShardedFusedAdamW exchange (P2P reduce-scatter + AdamW shard + P2P all-gather)."""
+    import os
+    import torch.distributed as dist
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if world > 1:
+        dev = torch.device(f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}")
+        if not dist.is_initialized():
+            os.environ.setdefault("NCCL_DEBUG", "WARN")
+            dist.init_process_group("nccl", device_id=dev)
+        log = log and rank == 0
     dev = dev or torch.device("cuda:0")
     torch.cuda.set_device(dev)
     try:  # ~170 GB of the 192 GB are live at the peak: growable segments keep the caching allocator from fragmenting
@@ -63,15 +74,20 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
             print(f"[train_bench] {msg}", file=sys.stderr, flush=True)
     t0 = time.time()
     model = NativeQwen2(cfg, dev)
-    opt = FusedAdamW(model.named_parameters(), lr=1e-6, weight_decay=0.01, max_grad_norm=0.3, grad_dtype=torch.float32)
+    if world > 1:
+        from pipelinerl_b200.finetune.optim import ShardedFusedAdamW
+        opt = ShardedFusedAdamW(model.named_parameters(), lr=1e-6, weight_decay=0.01, max_grad_norm=0.3,
+                                grad_accum_fp32=True)
+    else:
+        opt = FusedAdamW(model.named_parameters(), lr=1e-6, weight_decay=0.01, max_grad_norm=0.3, grad_dtype=torch.float32)
     model.bind(opt)
     if keep_attn >= 0:
         model.body.keep_attention_layers = keep_attn
     torch.cuda.synchronize()
     say(f"model + optimizer state resident: {torch.cuda.memory_allocated() / 1e9:.1f} GB ({time.time() - t0:.1f} s)")
-    n_samples_step = micro * samples_per_row
+    n_samples_step = micro * samples_per_row * world
     rcfg = RLConfig(batch_size=n_samples_step)   # reference defaults: ppo, kl_coef 0.1, temperature 1.0
-    batches = [synthetic_batch(cfg, tokens, samples_per_row, dev, 100 + i) for i in range(micro)]
+    batches = [synthetic_batch(cfg, tokens, samples_per_row, dev, 100 + rank * micro + i) for i in range(micro)]
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     launches0 = None
     rec = []
@@ -97,6 +113,10 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
         bwd = sum(e[2 * i + 1].elapsed_time(e[2 * i + 2]) for i in range(micro))
         optm = e[2 * micro].elapsed_time(e[-1])
         total = e[0].elapsed_time(e[-1])
+        if world > 1:   # device-timed, max over ranks
+            tt = torch.tensor([total, fwd, bwd, optm], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            total, fwd, bwd, optm = tt.tolist()
         rec.append((total, fwd, bwd, optm, float(sum(losses)), float(gn)))
         say(f"step {step}: {total:.1f} ms (fwd {fwd:.1f} bwd {bwd:.1f} opt {optm:.1f}) loss {rec[-1][4]:.5f} "
             f"grad_norm {rec[-1][5]:.4f} peak {torch.cuda.max_memory_allocated() / 1e9:.1f} GB")
@@ -114,14 +134,14 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
               file=sys.stderr, flush=True)
     timed = rec[warmup:]
     ms = sum(r[0] for r in timed) / len(timed)
-    total_tokens = micro * tokens
+    total_tokens = micro * tokens * world
     c = cfg
     body_params = c.num_layers * (c.qkv_size * c.hidden_size + c.hidden_size * c.q_size + 3 * c.hidden_size * c.intermediate_size)
     head_params = c.vocab_size * c.hidden_size
     per_seg = tokens // samples_per_row
     attn_fwd = 4.0 * c.num_layers * c.num_q_heads * c.head_dim * (per_seg * (per_seg + 1) / 2) * samples_per_row
     # model FLOPs: 6 N per token + causal attention (forward 1x + backward 2x); recompute is NOT counted
-    model_flops = micro * (6.0 * (body_params + head_params) * tokens + 3.0 * attn_fwd)
+    model_flops = world * micro * (6.0 * (body_params + head_params) * tokens + 3.0 * attn_fwd)
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     peak = peaks.get("bf16_tflops_sustained", 1459.7)
     out = {"bench": "trainer_step", "model": "Qwen2.5-7B" if model_name == "7b" else "tiny", "layers": c.num_layers,
@@ -131,7 +151,9 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
            "fwd_ms": round(sum(r[1] for r in timed) / len(timed), 2), "bwd_ms": round(sum(r[2] for r in timed) / len(timed), 2),
            "opt_ms": round(sum(r[3] for r in timed) / len(timed), 2),
            "model_TFLOPs": round(model_flops / ms / 1e9, 1),
-           "mfu_vs_measured_sustained_peak": round(model_flops / ms / 1e9 / peak, 4), "peak_TFLOPs": peak,
+           "mfu_vs_measured_sustained_peak": round(model_flops / ms / 1e9 / peak / world, 4), "peak_TFLOPs": peak,
+           "n_gpus": world, "parallelism": f"dp{world} (ShardedFusedAdamW exchange over NVLink peer memory)" if world > 1 else "single GPU",
+           "exchange_phase_ms": [round(x, 2) for x in getattr(opt, "last_phase_ms", (0.0, 0.0))],
            "libprl_launches_per_step": (_lib.launch_count() - launches0) // max(1, steps),
            "peak_memory_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1),
            "loss": rec[-1][4], "grad_norm": rec[-1][5], "grad_accumulation": "fp32 in the optimizer arena",
@@ -155,9 +177,72 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="override the layer count (debug)")
     ap.add_argument("--keep-attn", type=int, default=-1, help="layers whose attention half is kept for backward (-1 = all)")
     ap.add_argument("--profile", action="store_true", help="after the timed steps, print the per-kernel CUDA time of one step")
+    ap.add_argument("--check", action="store_true", help="tiny model: DP result == single-learner result on all micro-batches")
     a = ap.parse_args()
-    print(json.dumps(measure(a.model, a.tokens, a.samples_per_row, a.micro, a.steps, a.warmup, a.layers, a.keep_attn,
-                             a.profile)))
+    import os
+    if a.check:
+        print(json.dumps(check_dp()))
+        return
+    res = measure(a.model, a.tokens, a.samples_per_row, a.micro, a.steps, a.warmup, a.layers, a.keep_attn, a.profile)
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(json.dumps(res))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def check_dp():
+    """world ranks x 2 micro-batches through the sharded exchange  ==  one learner running all of them."""
+    import os
+    import torch.distributed as dist
+    from pipelinerl_b200.finetune.optim import ShardedFusedAdamW
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    dev = torch.device(f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = ModelConfig(vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2, num_q_heads=4, num_kv_heads=2)
+    micro, T = 2, 384
+    rcfg = RLConfig(batch_size=micro * world * 2)
+    all_batches = [synthetic_batch(cfg, T, 2, dev, 7 + i) for i in range(micro * world)]
+    for b in all_batches:
+        b.input_ids %= cfg.vocab_size
+        b.labels = torch.where(b.labels >= 0, b.input_ids, b.labels)
+        b.old_logprobs.fill_(-6.9)
+        b.ref_logprobs.fill_(-6.9)
+
+    def run(opt_factory, batches):
+        model = NativeQwen2(cfg, dev, seed=5)
+        opt = opt_factory(model)
+        model.bind(opt)
+        opt.zero_grad()
+        for b in batches:
+            loss, _ = rl_step(model, b, 0, 10, rcfg)
+            loss.backward()
+        gn = float(opt.step())
+        torch.cuda.synchronize()
+        return opt.shadow_bf16.clone(), gn, opt
+    ref, gn_ref, _ = run(lambda m: FusedAdamW(m.named_parameters(), lr=1e-3, weight_decay=0.01, max_grad_norm=0.3,
+                                              grad_dtype=torch.float32), all_batches)
+    if world == 1:
+        return {"ok": True, "world": 1, "note": "single process: nothing to compare"}
+    got, gn, opt = run(lambda m: ShardedFusedAdamW(m.named_parameters(), lr=1e-3, weight_decay=0.01, max_grad_norm=0.3,
+                                                   grad_accum_fp32=True), all_batches[rank * micro:(rank + 1) * micro])
+    same = (got == ref).float().mean().item()
+    # one AdamW step moves a parameter by at most ~lr: a gradient whose sign flips under the bf16 exchange rounding
+    # (near-zero gradients of zero-initialised biases) may differ by 2 lr; nothing may differ by more
+    max_abs = (got.float() - ref.float()).abs().max().item()
+    gathered = [torch.empty_like(got) for _ in range(world)]
+    dist.all_gather(gathered, got)
+    identical = all(torch.equal(g, gathered[0]) for g in gathered)
+    ok = identical and same > 0.98 and max_abs <= 2.5e-3 + 2 ** -7 * ref.float().abs().max().item() and abs(gn - gn_ref) <= 1e-2 * gn_ref
+    out = {"ok": bool(ok), "world": world, "ranks_bit_identical": bool(identical), "params_equal_to_single_learner": round(same, 5),
+           "max_abs_diff": max_abs, "grad_norm": gn, "grad_norm_single": gn_ref}
+    dist.barrier()
+    opt.close()
+    dist.destroy_process_group()
+    return out if rank == 0 else {"ok": bool(ok), "world": world, "rank": rank, "max_abs_diff": max_abs, "grad_norm": gn}
 
 
 if __name__ == "__main__":
