@@ -343,6 +343,15 @@ int prl_paged_attn_prefill(const void* q_bf16 /*[rows,n_q,128]*/, const void* kv
                            const int32_t* seq_slot, int32_t n_seqs, int32_t max_q_len, int32_t n_q, int32_t n_kv,
                            int32_t head_dim, int32_t page_size, float sm_scale, void* out_bf16 /*[rows,n_q*128]*/,
                            prl_stream_t stream);
+/* Same contract on the tcgen05 path (csrc/attn_tc.cu): a query tile packs 128 / (n_q / n_kv) tokens x the GQA group's
+ * heads into one UMMA tile, S = Q K^T and P V run on the tensor core with TMEM accumulators, V is read as stored
+ * (MN-major operand).  q_rows = rows of the q buffer that hold this chunk (TMA bounds). */
+int prl_paged_attn_prefill_tc(const void* q_bf16 /*[q_rows,n_q,128]*/, int32_t q_rows, const void* kv_cache_bf16,
+                              int64_t n_pages, int32_t n_layers, int32_t layer, const int32_t* block_table,
+                              int32_t max_blocks, const int32_t* seq_q_start, const int32_t* seq_q_len,
+                              const int32_t* seq_pos0, const int32_t* seq_slot, int32_t n_seqs, int32_t max_q_len,
+                              int32_t n_q, int32_t n_kv, int32_t head_dim, int32_t page_size, float sm_scale,
+                              void* out_bf16 /*[rows,n_q*128]*/, prl_stream_t stream);
 /* Sampling with in-kernel logprob capture: id ~ softmax(logits/T) (Gumbel-max, counter-based RNG on
  * (seed, step, row, vocab id)) or argmax when greedy; logprob = log_softmax(logits/T)[id]. */
 size_t prl_sample_workspace_bytes(int32_t B);

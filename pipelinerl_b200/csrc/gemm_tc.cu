@@ -77,6 +77,30 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner_elems, 
   return PRL_OK;
 }
 
+// 3-D bf16 tensor map (innermost dimension contiguous), 128-byte swizzle: box_inner * 2 bytes must be 128
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return PRL_ERR_CUDA;
+  if ((uintptr_t)base % 16 != 0 || stride1_bytes % 16 != 0 || stride2_bytes % 16 != 0) {
+    set_error("TMA operand must be 16-byte aligned (base %p, strides %llu / %llu B)", base,
+              (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes);
+    return PRL_ERR_INVALID;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, box2};
+  cuuint32_t elem_strides[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, elem_strides,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+    return PRL_ERR_CUDA;
+  }
+  return PRL_OK;
+}
+
 namespace {
 
 constexpr int kBlockM = 128;  // output features per CTA (UMMA M)

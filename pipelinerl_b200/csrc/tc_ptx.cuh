@@ -244,5 +244,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
 // ---- host: tensor-map creation through the driver entry point (no -lcuda link) ------------
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t outer_rows,
                       uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows);
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
 
 }  // namespace prl

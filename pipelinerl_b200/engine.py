@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -121,6 +122,7 @@ class DecodeEngine:
         self._graphs: dict[int, torch.cuda.CUDAGraph] = {}
         # ---- chunked prefill + prefix sharing (GRPO attempts share their prompt) ----
         self.prefill_chunk = int(prefill_chunk)
+        self.prefill_attn_tc = os.environ.get("PRL_PREFILL_ATTN", "tc") != "mma"   # tcgen05 (default) | mma.sync kernel
         self.prefix_sharing = prefix_sharing
         self.page_ref = [0] * self.n_pages
         self._prefill_queue: list[Request] = []
@@ -315,29 +317,47 @@ class DecodeEngine:
                                          a.ptr("layers.0.input_layernorm.weight"), cfg.rms_eps, n, H, cfg.vocab_size,
                                          h.data_ptr(), x.data_ptr(), st))
         max_q = max(k for _, _, k in segs)
+        big = n > 128   # compute-bound chunk: persistent CTA-pair GEMM; o/down accumulate straight into the fp32 residual
+
+        def gemm(w_name, src, N, K, dst, accumulate=False):
+            if big:
+                _lib.check(lib.prl_gemm_tn(src.data_ptr(), K, a.ptr(w_name), K, n, N, K, dst.data_ptr(), N, 1,
+                                           int(accumulate), None, None, 0, 1.0, st))
+            else:
+                self._gemm(w_name, src, N, K, 1, dst, m=n)
+
+        def add_and_norm(gamma_name):
+            # big: the GEMM epilogue already added its tile to h -> only the norm is left (zero partial slices)
+            _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), 0 if big else 1, n, H, a.ptr(gamma_name), cfg.rms_eps,
+                                                h.data_ptr(), x.data_ptr(), None, 0, st))
         for l in range(cfg.num_layers):
             p = f"layers.{l}."
-            self._gemm(p + "qkv_proj.weight", x, cfg.qkv_size, H, 1, part, m=n)
+            gemm(p + "qkv_proj.weight", x, cfg.qkv_size, H, part)
             _lib.check(lib.prl_qkv_rope_cache(part.data_ptr(), 1, n, a.ptr(p + "qkv_proj.bias") if cfg.qkv_bias else None,
                                               cfg.num_q_heads, cfg.num_kv_heads, cfg.head_dim, pf["pos"].data_ptr(),
                                               self.block_table.data_ptr(), self.max_blocks, pf["slot"].data_ptr(),
                                               self.inv_freq.data_ptr(), pf["q"].data_ptr(), self.kv_cache.data_ptr(),
                                               self.n_pages, l, PAGE_SIZE, None, 0, st))
             seq = pf["seq"]
-            _lib.check(lib.prl_paged_attn_prefill(pf["q"].data_ptr(), self.kv_cache.data_ptr(), self.n_pages,
-                                                  cfg.num_layers, l, self.block_table.data_ptr(), self.max_blocks,
-                                                  seq[0].data_ptr(), seq[1].data_ptr(), seq[2].data_ptr(),
-                                                  seq[3].data_ptr(), ns, max_q, cfg.num_q_heads, cfg.num_kv_heads,
-                                                  cfg.head_dim, PAGE_SIZE, sm_scale, pf["attn"].data_ptr(), st))
-            self._gemm(p + "o_proj.weight", pf["attn"], H, cfg.q_size, 1, part, m=n)
-            _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), 1, n, H, a.ptr(p + "post_attention_layernorm.weight"),
-                                                cfg.rms_eps, h.data_ptr(), x.data_ptr(), None, 0, st))
-            self._gemm(p + "gate_up_proj.weight", x, 2 * I, H, 1, part, m=n)
+            if self.prefill_attn_tc:   # tcgen05 path (csrc/attn_tc.cu)
+                _lib.check(lib.prl_paged_attn_prefill_tc(pf["q"].data_ptr(), n, self.kv_cache.data_ptr(), self.n_pages,
+                                                         cfg.num_layers, l, self.block_table.data_ptr(), self.max_blocks,
+                                                         seq[0].data_ptr(), seq[1].data_ptr(), seq[2].data_ptr(),
+                                                         seq[3].data_ptr(), ns, max_q, cfg.num_q_heads,
+                                                         cfg.num_kv_heads, cfg.head_dim, PAGE_SIZE, sm_scale,
+                                                         pf["attn"].data_ptr(), st))
+            else:                      # mma.sync path (csrc/paged_attn.cu)
+                _lib.check(lib.prl_paged_attn_prefill(pf["q"].data_ptr(), self.kv_cache.data_ptr(), self.n_pages,
+                                                      cfg.num_layers, l, self.block_table.data_ptr(), self.max_blocks,
+                                                      seq[0].data_ptr(), seq[1].data_ptr(), seq[2].data_ptr(),
+                                                      seq[3].data_ptr(), ns, max_q, cfg.num_q_heads, cfg.num_kv_heads,
+                                                      cfg.head_dim, PAGE_SIZE, sm_scale, pf["attn"].data_ptr(), st))
+            gemm(p + "o_proj.weight", pf["attn"], H, cfg.q_size, h if big else part, accumulate=big)
+            add_and_norm(p + "post_attention_layernorm.weight")
+            gemm(p + "gate_up_proj.weight", x, 2 * I, H, part)
             _lib.check(lib.prl_silu_mul(part.data_ptr(), 1, n, I, pf["act"].data_ptr(), None, 0, st))
-            self._gemm(p + "down_proj.weight", pf["act"], H, I, 1, part, m=n)
-            nxt = f"layers.{l + 1}.input_layernorm.weight" if l + 1 < cfg.num_layers else "norm.weight"
-            _lib.check(lib.prl_residual_rmsnorm(part.data_ptr(), 1, n, H, a.ptr(nxt), cfg.rms_eps, h.data_ptr(),
-                                                x.data_ptr(), None, 0, st))
+            gemm(p + "down_proj.weight", pf["act"], H, I, h if big else part, accumulate=big)
+            add_and_norm(f"layers.{l + 1}.input_layernorm.weight" if l + 1 < cfg.num_layers else "norm.weight")
         self.stats["prefill_tokens"] += n
         if score_temperature is None:
             return None

@@ -187,14 +187,20 @@ def test_prefix_sharing_and_chunked_prefill(cuda_device):
         logits = orc.forward(torch.tensor([tok]))[-1]
 
 
-def test_prefill_attention_long_context_vs_fp32(cuda_device):
-    """Prefill attention alone: a 1000-row chunk at position 7000 of an 8000-token sequence (causal), plus a short
-    sequence packed in the same launch."""
+@pytest.mark.parametrize("kernel", ["tc", "mma"])
+@pytest.mark.parametrize("n_q,n_kv,seqs", [
+    (28, 4, [(7000, 1000), (0, 37)]),              # Qwen2.5-7B grouping (R = 7 -> 18 tokens x 7 heads per UMMA tile)
+    (4, 2, [(0, 300), (129, 70), (64, 1)]),        # R = 2; chunk starting mid-page; single-row chunk
+    (8, 8, [(500, 129), (0, 128)]),                # R = 1 (MHA): 128 tokens per tile
+    (8, 1, [(1000, 260)]),                         # R = 8
+])
+def test_prefill_attention_long_context_vs_fp32(cuda_device, kernel, n_q, n_kv, seqs):
+    """Prefill attention alone (both kernels: tcgen05 `tc`, mma.sync `mma`): chunks of queries at arbitrary positions
+    of longer sequences (causal), several sequences packed in one launch."""
     from pipelinerl_b200 import _lib
     lib = _lib.load()
     dev = cuda_device
-    n_q, n_kv, D, P = 28, 4, 128, 64
-    seqs = [(7000, 1000), (0, 37)]           # (pos0, q_len)
+    D, P = 128, 64
     max_blocks = 128
     n_pages = 1 + sum((p0 + ql + P - 1) // P for p0, ql in seqs) + 3
     g = torch.Generator().manual_seed(9)
@@ -211,13 +217,20 @@ def test_prefill_attention_long_context_vs_fp32(cuda_device):
     rows = sum(ql for _, ql in seqs)
     q = torch.randn(rows, n_q, D, generator=g).to(torch.bfloat16).to(dev)
     out = torch.zeros(rows, n_q * D, dtype=torch.bfloat16, device=dev)
-    starts = [0, seqs[0][1]]
+    starts = [sum(s[1] for s in seqs[:z]) for z in range(len(seqs))]
     i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
-    qs, ql_t, p0_t, sl = i32(starts), i32([s[1] for s in seqs]), i32([s[0] for s in seqs]), i32([0, 1])
+    qs, ql_t, p0_t, sl = i32(starts), i32([s[1] for s in seqs]), i32([s[0] for s in seqs]), i32(list(range(len(seqs))))
     bt_d = bt.to(dev)
-    _lib.check(lib.prl_paged_attn_prefill(q.data_ptr(), kv.data_ptr(), n_pages, L, layer, bt_d.data_ptr(), max_blocks,
-                                          qs.data_ptr(), ql_t.data_ptr(), p0_t.data_ptr(), sl.data_ptr(), len(seqs),
-                                          max(s[1] for s in seqs), n_q, n_kv, D, P, 1.0 / D ** 0.5, out.data_ptr(), None))
+    if kernel == "tc":
+        _lib.check(lib.prl_paged_attn_prefill_tc(q.data_ptr(), rows, kv.data_ptr(), n_pages, L, layer, bt_d.data_ptr(),
+                                                 max_blocks, qs.data_ptr(), ql_t.data_ptr(), p0_t.data_ptr(), sl.data_ptr(),
+                                                 len(seqs), max(s[1] for s in seqs), n_q, n_kv, D, P, 1.0 / D ** 0.5,
+                                                 out.data_ptr(), None))
+    else:
+        _lib.check(lib.prl_paged_attn_prefill(q.data_ptr(), kv.data_ptr(), n_pages, L, layer, bt_d.data_ptr(), max_blocks,
+                                              qs.data_ptr(), ql_t.data_ptr(), p0_t.data_ptr(), sl.data_ptr(), len(seqs),
+                                              max(s[1] for s in seqs), n_q, n_kv, D, P, 1.0 / D ** 0.5, out.data_ptr(),
+                                              None))
     torch.cuda.synchronize()
     for z, (p0, ql) in enumerate(seqs):
         S = p0 + ql

@@ -18,7 +18,8 @@ def main():
     cfg = ModelConfig.qwen2_5_7b()
     arena = ParamArena(cfg, dev).init_random(seed=42)
     P = 8192
-    eng = DecodeEngine(cfg, arena, max_batch=16, max_seq_len=P + 128, max_new_tokens=64, device=dev, prefill_chunk=1024)
+    chunk = int(next((a.split("=")[1] for a in sys.argv if a.startswith("--chunk=")), 1024))
+    eng = DecodeEngine(cfg, arena, max_batch=16, max_seq_len=P + 128, max_new_tokens=64, device=dev, prefill_chunk=chunk)
     g = torch.Generator().manual_seed(1)
     prompts = [torch.randint(8, 151643, (P,), generator=g).tolist() for _ in range(3)]
     sp = SamplingParams(max_tokens=4, greedy=True, ignore_eos=True)
@@ -49,7 +50,7 @@ def main():
     ms8 = timed(eng.run_prefill)
     d = {k: eng.stats[k] - before[k] for k in eng.stats}
     flops = 2 * (cfg.num_params() - 2 * cfg.vocab_size * cfg.hidden_size) * (P - 1) + 2 * (P - 1) ** 2 * cfg.hidden_size * cfg.num_layers
-    out = {"bench": "prefill", "model": "Qwen2.5-7B", "prompt_tokens": P, "chunk": 1024,
+    out = {"bench": "prefill", "model": "Qwen2.5-7B", "prompt_tokens": P, "chunk": chunk,
            "single_prompt_ms": round(ms1, 2), "single_prompt_tokens_per_s": round((P - 1) / ms1 * 1e3),
            "single_prompt_TFLOPs": round(flops / ms1 / 1e9, 1),
            "group_of_8_ms": round(ms8, 2), "group_prefill_tokens": d["prefill_tokens"],
