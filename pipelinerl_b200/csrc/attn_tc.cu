@@ -5,13 +5,14 @@
 // query heads of one GQA group into the 128 rows of a UMMA tile (row = token * R + head), so every K/V page staged
 // by TMA serves all R heads.  Per 128-key step:
 //     S[128 x 128]  = Q K^T      tcgen05.mma, both operands K-major (k = head dim), accumulator in TMEM
-//     P             = exp2(S * scale - rowmax)   four softmax warps, thread = row, straight out of TMEM;
+//     P             = exp2(S * scale - rowmax)   eight softmax warps, straight out of TMEM (one read);
 //                                                bf16 P goes to shared memory in the 128-byte-swizzled K-major layout
 //     Ot[128 x 128] = P V        tcgen05.mma, A = P (smem), B = V read AS STORED (MN-major operand: keys are rows)
 // and the softmax warps fold Ot into their fp32 register accumulator with the online-softmax rescale.  S and Ot are
-// double-buffered in the 512 TMEM columns: the tensor core runs Q K^T of step i+1 and P V of step i while the
-// softmax warps work on step i / fold step i-1.  Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner,
-// 2..5 = softmax / epilogue.
+// double-buffered in the 512 TMEM columns and P in shared memory: the tensor core runs Q K^T of step i+1 and P V of
+// step i while the softmax warps exponentiate step i+1 / fold step i-1 (the exp phase is MUFU-bound: 16 K exp2 per
+// step against 16 per clock and SM).  Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner,
+// 2..9 = softmax / epilogue (two warps per TMEM lane quarter, each owning half of the keys / head-dim columns).
 //
 // Tensor-bound: 4 * 128 * S^2 / 2 FLOP per head (causal); K/V bytes are re-read from L2 by the other query tiles.
 #include "prl_common.cuh"
@@ -25,7 +26,7 @@ constexpr int kDT = 128;
 constexpr int kKeys = 128;                 // keys per step = 2 pages
 constexpr int kTile16K = 16384;            // one [128 rows x 128 B] operand tile
 constexpr int kStageBytesT = 4 * kTile16K; // K lo/hi + V lo/hi
-constexpr int kThreadsT = 192;
+constexpr int kThreadsT = 320;           // TMA warp, MMA warp, 8 softmax warps
 
 struct TcPrefillParams {
   __nv_bfloat16* out;            // [rows, n_q*128]
@@ -53,33 +54,41 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreadsT, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                        TcPrefillParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_smem = base;                          // Q lo | Q hi
   const uint32_t kv_smem = base + 2 * kTile16K;          // 2 stages x (K lo | K hi | V lo | V hi)
-  const uint32_t p_smem = kv_smem + 2 * kStageBytesT;    // P keys 0..63 | keys 64..127
-  const uint32_t bar_base = p_smem + 2 * kTile16K;
+  const uint32_t p_smem = kv_smem + 2 * kStageBytesT;    // 2 buffers x (P keys 0..63 | keys 64..127)
+  const uint32_t bar_base = p_smem + 4 * kTile16K;
   auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
-  // 0 q_full | 1,2 kv_full | 3,4 kv_empty | 5,6 s_full | 7,8 s_empty | 9 p_full | 10,11 o_full | 12,13 o_empty
-  const uint32_t tmem_slot = bar(14);
+  // 0 q_full | 1,2 k_full | 3,4 k_empty | 5,6 s_full | 7,8 s_empty | 9,14 p_full | 10,11 o_full | 12,13 o_empty |
+  // 15,16 v_full | 17,18 v_empty.   K and V slots cycle independently: a K slot is free as soon as its Q K^T has run,
+  // so K of step i+2 streams in during the softmax of step i and S is always ready when the softmax warps want it.
+  const uint32_t tmem_slot = bar(19);
 
+  // The two CTAs of a cluster own ADJACENT query tiles of the same (sequence, kv head): they walk the same K/V pages,
+  // so each CTA fetches one of the two pages of a step and TMA-multicasts it into both CTAs' shared memory -- the
+  // kernel is bound by L2 -> SM bandwidth (64 KB of K/V per 8.4 MFLOP step and CTA), and this halves it.
   const int qtile = blockIdx.x, kvh = blockIdx.y, z = blockIdx.z;
+  const uint32_t rank = ptx::cluster_ctarank();
   const int q_len = p.seq_q_len[z];
+  if ((qtile & ~1) * p.nq >= q_len) return;              // uniform across the CLUSTER, before any barrier / TMEM use
   const int t0 = qtile * p.nq;
-  if (t0 >= q_len) return;                               // uniform across the CTA, before any barrier / TMEM use
   const int row0 = p.seq_q_start[z] + t0;
   const int pos_first = p.seq_pos0[z] + t0;
-  const int n_valid = (q_len - t0) < p.nq ? (q_len - t0) : p.nq;
-  const int kv_end = pos_first + n_valid;                // keys [0, kv_end) are visible to the last query of the tile
+  const int n_valid = t0 >= q_len ? 0 : ((q_len - t0) < p.nq ? (q_len - t0) : p.nq);  // 0: partner-only CTA
+  // both CTAs run the step count of the LATER tile (the earlier tile's extra step is fully masked)
+  const int pair_rows = ((qtile | 1) + 1) * p.nq;
+  const int kv_end = p.seq_pos0[z] + (pair_rows < q_len ? pair_rows : q_len);
   const int n_it = (kv_end + kKeys - 1) / kKeys;
   const int last_page = (kv_end - 1) / kPageT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 14; ++i) ptx::mbar_init(bar(i), 1);
+    for (int i = 0; i < 19; ++i) ptx::mbar_init(bar(i), (i == 3 || i == 4 || i == 17 || i == 18) ? 2 : 1);  // *_empty: both CTAs' MMA warps
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
     ptx::prefetch_tensormap(&tm_q);
@@ -90,7 +99,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before_sync();
-  __syncthreads();
+  ptx::cluster_sync();                                   // the partner's barriers exist before anything targets them
   ptx::tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -102,25 +111,24 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       ptx::tma_load_3d(q_smem, &tm_q, 0, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
       ptx::tma_load_3d(q_smem + kTile16K, &tm_q, 64, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
       const int32_t* bt = p.block_table + (int64_t)p.seq_slot[z] * p.max_blocks;
-      for (int it = 0; it < n_it; ++it) {
+      // this CTA fetches ONE of the two pages of a step (rank 0: keys 0..63, rank 1: keys 64..127) and multicasts it
+      auto load_page = [&](int it, int kv, uint32_t full_bar, uint32_t empty_bar) {
         const int s = it & 1;
         const uint32_t ph = (uint32_t)((it >> 1) & 1);
-        ptx::mbar_wait(bar(3 + s), ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(bar(1 + s), (uint32_t)kStageBytesT);
-        const uint32_t dst = kv_smem + (uint32_t)(s * kStageBytesT);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          int pg = 2 * it + half;
-          if (pg > last_page) pg = last_page;            // the tail step re-reads the last page; its keys are masked
-          const int page = bt[pg];
-          const int row_k = (int)(((((int64_t)p.layer * 2 + 0) * p.n_pages + page) * p.n_kv + kvh) * kPageT);
-          const int row_v = (int)(((((int64_t)p.layer * 2 + 1) * p.n_pages + page) * p.n_kv + kvh) * kPageT);
-          const uint32_t off = (uint32_t)(half * 8192);
-          ptx::tma_load_2d(dst + off, &tm_kv, 0, row_k, bar(1 + s), ptx::kEvictLast);
-          ptx::tma_load_2d(dst + kTile16K + off, &tm_kv, 64, row_k, bar(1 + s), ptx::kEvictLast);
-          ptx::tma_load_2d(dst + 2 * kTile16K + off, &tm_kv, 0, row_v, bar(1 + s), ptx::kEvictLast);
-          ptx::tma_load_2d(dst + 3 * kTile16K + off, &tm_kv, 64, row_v, bar(1 + s), ptx::kEvictLast);
-        }
+        ptx::mbar_wait(empty_bar + 8u * (uint32_t)s, ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(full_bar + 8u * (uint32_t)s, (uint32_t)(2 * kTile16K));
+        int pg = 2 * it + (int)rank;
+        if (pg > last_page) pg = last_page;              // the tail step re-reads the last page; its keys are masked
+        const int page = bt[pg];
+        const int row = (int)(((((int64_t)p.layer * 2 + kv) * p.n_pages + page) * p.n_kv + kvh) * kPageT);
+        const uint32_t dst = kv_smem + (uint32_t)(s * kStageBytesT + kv * 2 * kTile16K) + (uint32_t)(rank * 8192);
+        ptx::tma_load_2d_multicast(dst, &tm_kv, 0, row, full_bar + 8u * (uint32_t)s, 3, ptx::kEvictLast);
+        ptx::tma_load_2d_multicast(dst + kTile16K, &tm_kv, 64, row, full_bar + 8u * (uint32_t)s, 3, ptx::kEvictLast);
+      };
+      load_page(0, 0, bar(1), bar(3));
+      for (int it = 0; it < n_it; ++it) {                // same order as the MMA warp consumes: K(it+1), then V(it)
+        if (it + 1 < n_it) load_page(it + 1, 0, bar(1), bar(3));
+        load_page(it, 1, bar(15), bar(17));
       }
     }
   } else if (warp == 1) {
@@ -131,7 +139,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       auto issue_qk = [&](int j) {
         const int s = j & 1;
         const uint32_t ph = (uint32_t)((j >> 1) & 1);
-        ptx::mbar_wait(bar(1 + s), ph);          // K/V of step j landed
+        ptx::mbar_wait(bar(1 + s), ph);          // K of step j landed
         ptx::mbar_wait(bar(7 + s), ph ^ 1u);     // S[s] drained by the softmax warps (step j - 2)
         ptx::tc_fence_after_sync();
         const uint32_t k_addr = kv_smem + (uint32_t)(s * kStageBytesT);
@@ -142,6 +150,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 128), a, b, idesc_qk, ks > 0 ? 1u : 0u);
         }
         ptx::tc_commit(bar(5 + s));
+        ptx::tc_commit_multicast(bar(3 + s), 3);  // K slot consumed here: tell BOTH producers
       };
       ptx::mbar_wait(bar(0), 0);
       issue_qk(0);
@@ -149,48 +158,56 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         if (i + 1 < n_it) issue_qk(i + 1);
         const int s = i & 1;
         const uint32_t ph = (uint32_t)((i >> 1) & 1);
-        ptx::mbar_wait(bar(9), (uint32_t)(i & 1));   // P of step i is in shared memory
+        ptx::mbar_wait(bar(s ? 14 : 9), ph);         // P[s] of step i is in shared memory
         ptx::mbar_wait(bar(12 + s), ph ^ 1u);        // Ot[s] folded by the softmax warps (step i - 2)
+        ptx::mbar_wait(bar(15 + s), ph);             // V of step i landed
         ptx::tc_fence_after_sync();
         const uint32_t v_addr = kv_smem + (uint32_t)(s * kStageBytesT) + 2 * kTile16K;
+        const uint32_t p_addr = p_smem + (uint32_t)(s * 2 * kTile16K);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a = ptx::make_kmajor_sw128_desc(p_smem + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
+          const uint64_t a = ptx::make_kmajor_sw128_desc(p_addr + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
           const uint64_t b = ptx::make_mnmajor_sw128_desc(v_addr, kTile16K) + (uint64_t)(128 * ks);
           ptx::mma_bf16_ss(tmem_base + (uint32_t)(256 + s * 128), a, b, idesc_pv, ks > 0 ? 1u : 0u);
         }
-        ptx::tc_commit(bar(10 + s));   // Ot[s] complete (and P free again)
-        ptx::tc_commit(bar(3 + s));    // K/V stage free
+        ptx::tc_commit(bar(10 + s));   // Ot[s] complete (and P[s] free again)
+        ptx::tc_commit_multicast(bar(17 + s), 3);  // V slot consumed here: tell BOTH producers
       }
     }
     __syncwarp();
   } else {
-    // ===== softmax + epilogue: thread = one (token, head) row =====
+    // ===== softmax + epilogue: 8 warps; a PAIR of threads owns one (token, head) row =====
+    // warp w may only touch TMEM lanes 32 (w % 4) ..; the two warps of a lane quarter split the row: half h works on
+    // keys [64 h, 64 h + 64) of every step (S kept in registers: one TMEM read) and on head-dim columns
+    // [64 h, 64 h + 64) of the output accumulator.  The row maximum is exchanged through shared memory.
     const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
     const int m = q * 32 + lane;
     const int qi = m / p.R, r = m - qi * p.R;
     const int qpos = pos_first + qi;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t p_row = p_smem + (uint32_t)(m * 128);
+    const uint32_t p_row0 = p_smem + (uint32_t)(h * kTile16K + m * 128);
+    float* xchg = reinterpret_cast<float*>(smem_raw + (bar_base - ptx::smem_u32(smem_raw)) + 8 * 20);  // [2][128]
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-    float o[kDT];
+    float o[64];
 #pragma unroll
-    for (int d = 0; d < kDT; ++d) o[d] = 0.f;
+    for (int d = 0; d < 64; ++d) o[d] = 0.f;
 
-    auto fold = [&](int j) {   // o = o * alpha_j + Ot_j
+    auto fold = [&](int j) {   // o = o * alpha_j + Ot_j   (this thread's 64 head-dim columns)
       const int s = j & 1;
       ptx::mbar_wait(bar(10 + s), (uint32_t)((j >> 1) & 1));
       ptx::tc_fence_after_sync();
+      uint32_t v0[32], v1[32];
+      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(256 + s * 128 + h * 64), v0);
+      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(256 + s * 128 + h * 64 + 32), v1);
+      ptx::tmem_ld_wait();
 #pragma unroll
-      for (int c0 = 0; c0 < kDT; c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(256 + s * 128 + c0), v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) o[c0 + e] = fmaf(o[c0 + e], alpha_prev, __uint_as_float(v[e]));
+      for (int e = 0; e < 32; ++e) {
+        o[e] = fmaf(o[e], alpha_prev, __uint_as_float(v0[e]));
+        o[32 + e] = fmaf(o[32 + e], alpha_prev, __uint_as_float(v1[e]));
       }
       ptx::tc_fence_before_sync();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x == 64) ptx::mbar_arrive(bar(12 + s));
     };
 
@@ -198,65 +215,65 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       const int s = i & 1;
       ptx::mbar_wait(bar(5 + s), (uint32_t)((i >> 1) & 1));
       ptx::tc_fence_after_sync();
-      const int key0 = i * kKeys;
-      const bool diag = key0 + kKeys - 1 > pos_first;    // some (row, key) of this step is masked
-      // pass 1: row maximum
+      const int key0 = i * kKeys + h * 64;
+      const bool diag = i * kKeys + kKeys - 1 > pos_first;   // some (row, key) of this step is masked
+      float sv[64];
+      {
+        uint32_t v0[32], v1[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(s * 128 + h * 64), v0);
+        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(s * 128 + h * 64 + 32), v1);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) { sv[e] = __uint_as_float(v0[e]); sv[32 + e] = __uint_as_float(v1[e]); }
+      }
+      if (diag) {
+#pragma unroll
+        for (int e = 0; e < 64; ++e)
+          if (key0 + e > qpos) sv[e] = -INFINITY;
+      }
       float mx = -INFINITY;
 #pragma unroll
-      for (int c0 = 0; c0 < kKeys; c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(s * 128 + c0), v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float sc = __uint_as_float(v[e]);
-          if (!diag || key0 + c0 + e <= qpos) mx = fmaxf(mx, sc);
-        }
-      }
-      mx *= p.scale_log2;                                // scale > 0: max commutes with the scaling
+      for (int e = 0; e < 64; ++e) mx = fmaxf(mx, sv[e]);
+      xchg[h * 128 + m] = mx;
+      ptx::tc_fence_before_sync();
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // S[s] is in registers on every thread; maxima exchanged
+      if (threadIdx.x == 64) ptx::mbar_arrive(bar(7 + s));  // S[s] drained -> Q K^T of step i + 2 may overwrite it
+      mx = fmaxf(mx, xchg[(1 - h) * 128 + m]) * p.scale_log2;  // scale > 0: max commutes with the scaling
       const float m_new = fmaxf(m_run, mx);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = ex2(m_run - m_use);            // 0 on the first step
-      if (i > 0) fold(i - 1);                            // P V of the previous step (also frees the P buffer)
-      // pass 2: P = exp2(S * scale - max) -> bf16 -> swizzled shared memory; row sum in fp32
+      const float alpha = ex2(m_run - m_use);               // 0 on the first step
+      // P[s] is free: P V of step i - 2 completed before fold(i - 2) returned during step i - 1
+      const uint32_t p_row = p_row0 + (uint32_t)(s * 2 * kTile16K);
       float sum = 0.f;
 #pragma unroll
-      for (int c0 = 0; c0 < kKeys; c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(s * 128 + c0), v);
-        ptx::tmem_ld_wait();
-        float pv[32];
+      for (int j = 0; j < 64; j += 8) {
+        float pe[8];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float pe = ex2(fmaf(__uint_as_float(v[e]), p.scale_log2, -m_use));
-          pv[e] = (!diag || key0 + c0 + e <= qpos) ? pe : 0.f;
-          sum += pv[e];
+        for (int e = 0; e < 8; ++e) {
+          pe[e] = ex2(fmaf(sv[j + e], p.scale_log2, -m_use));   // masked entries: exp2(-inf) = 0
+          sum += pe[e];
         }
-        const uint32_t tile = p_row + (uint32_t)((c0 >> 6) * kTile16K);
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const uint32_t ch = (uint32_t)(((c0 & 63) + j) >> 3);
-          st_shared_v4(tile + ((ch ^ (uint32_t)(m & 7)) << 4), pack2(pv[j], pv[j + 1]), pack2(pv[j + 2], pv[j + 3]),
-                       pack2(pv[j + 4], pv[j + 5]), pack2(pv[j + 6], pv[j + 7]));
-        }
+        st_shared_v4(p_row + (((uint32_t)(j >> 3) ^ (uint32_t)(m & 7)) << 4), pack2(pe[0], pe[1]), pack2(pe[2], pe[3]),
+                     pack2(pe[4], pe[5]), pack2(pe[6], pe[7]));
       }
-      l_run = l_run * alpha + sum;
+      l_run = l_run * alpha + sum;                           // this half's share of the row sum
       m_run = m_new;
+      ptx::fence_proxy_async();                              // generic-proxy stores of P -> visible to the UMMA reads
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 64) ptx::mbar_arrive(bar(s ? 14 : 9));   // P[s] ready -> P V of step i starts
+      // fold the PREVIOUS step while the tensor core runs this step's P V (its own P V finished during the exp phase)
+      if (i > 0) fold(i - 1);
       alpha_prev = alpha;
-      ptx::tc_fence_before_sync();
-      ptx::fence_proxy_async();                          // generic-proxy stores of P -> visible to the UMMA reads
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) {
-        ptx::mbar_arrive(bar(7 + s));                    // S[s] drained
-        ptx::mbar_arrive(bar(9));                        // P ready
-      }
     }
     fold(n_it - 1);
+    xchg[h * 128 + m] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l_tot = l_run + xchg[(1 - h) * 128 + m];
     if (qi < n_valid && qi < p.nq) {
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      __nv_bfloat16* dst = p.out + ((int64_t)(row0 + qi) * p.n_q + (kvh * p.R + r)) * kDT;
+      const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+      __nv_bfloat16* dst = p.out + ((int64_t)(row0 + qi) * p.n_q + (kvh * p.R + r)) * kDT + h * 64;
 #pragma unroll
-      for (int d = 0; d < kDT; d += 8) {
+      for (int d = 0; d < 64; d += 8) {
         uint4 u;
         u.x = pack2(o[d] * inv, o[d + 1] * inv);
         u.y = pack2(o[d + 2] * inv, o[d + 3] * inv);
@@ -268,7 +285,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   }
 
   ptx::tc_fence_before_sync();
-  __syncthreads();
+  ptx::cluster_sync();   // the partner may still multicast into this CTA's shared memory / arrive on its barriers
   if (warp == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -306,13 +323,13 @@ extern "C" int prl_paged_attn_prefill_tc(const void* q, int32_t q_rows, const vo
   rc = make_tmap_3d_bf16(&tq, q, kDT, (uint64_t)n_q, (uint64_t)q_rows, kDT * 2, (uint64_t)n_q * kDT * 2, 64, (uint32_t)p.R,
                          (uint32_t)p.nq);
   if (rc) return rc;
-  const int smem = 2 * kTile16K + 2 * kStageBytesT + 2 * kTile16K + 1024 + 8 * 16 + 16;
+  const int smem = 2 * kTile16K + 2 * kStageBytesT + 4 * kTile16K + 1024 + 8 * 20 + 2 * 128 * 4 + 16;
   static bool configured = false;
   if (!configured) {
     PRL_CUDA(cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid((unsigned)((max_q_len + p.nq - 1) / p.nq), (unsigned)n_kv, (unsigned)n_seqs);
+  dim3 grid((unsigned)(((max_q_len + p.nq - 1) / p.nq + 1) & ~1), (unsigned)n_kv, (unsigned)n_seqs);  // pairs of q tiles
   attn_prefill_tc_kernel<<<grid, kThreadsT, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
   PRL_LAUNCH_CHECK();
   return PRL_OK;
