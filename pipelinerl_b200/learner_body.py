@@ -139,6 +139,8 @@ class NativeBody:
         self.inv_freq = (1.0 / (cfg.rope_theta ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))).to(dev)
         self._saved = None
         self.keep_attention_layers = cfg.num_layers   # lower it when activation memory is short (0 = full recompute)
+        self.keep_gate_up_layers = 0                  # layers that also keep gate_up's output (2 I bf16 per token):
+        #                                               their backward skips the largest recompute GEMM
 
     def refresh(self) -> None:
         """Hook called after every optimizer step.  Nothing to rebuild: dgrad reads the weights as stored."""
@@ -204,12 +206,17 @@ class NativeBody:
     def _layer_bwd(self, l, h, saved, pos, bounds, dh3):
         c, o, w, g = self.cfg, self.ops, self.w, self.g
         p = f"layers.{l}."
+        gu = None
         if saved is None:   # full recompute of the layer from its input
             x1, rstd1, attn, graph, h2 = self._attn_half(l, h, pos, bounds, need_grad=True)
         else:               # attention half was kept by the forward: only the (cheap) norm is redone
-            attn, graph, h2 = saved
+            attn, graph, h2, gu = saved
             x1, rstd1 = o.rmsnorm(h, w[p + "input_layernorm.weight"], c.rms_eps)
-        x2, rstd2, gu, act, _ = self._mlp_half(l, h2, need_out=False)
+        if gu is None:
+            x2, rstd2, gu, act, _ = self._mlp_half(l, h2, need_out=False)
+        else:               # gate_up output kept too: norm and SiLU*up are one pass each, no GEMM
+            x2, rstd2 = o.rmsnorm(h2, w[p + "post_attention_layernorm.weight"], c.rms_eps)
+            act = o.silu_mul(gu)
         T = h.shape[0]
         d_act = o.dgrad(dh3, w[p + "down_proj.weight"])
         o.wgrad(g[p + "down_proj.weight"], dh3, act)
@@ -258,10 +265,12 @@ class NativeBody:
         for l in range(c.num_layers):
             keep_attn = keep and l < self.keep_attention_layers
             _, _, attn, graph, h2 = self._attn_half(l, h, pos, bounds, need_grad=keep_attn)
+            _, _, gu, _, h3 = self._mlp_half(l, h2)
             if keep:
                 inputs.append(h)
-                kept.append((attn, graph, h2) if keep_attn else None)
-            h = self._mlp_half(l, h2)[-1]
+                kept.append((attn, graph, h2, gu if l < self.keep_gate_up_layers else None) if keep_attn else None)
+            h = h3
+            del gu
         y, rstd = o.rmsnorm(h, self.w["norm.weight"], c.rms_eps)
         if keep:
             self._saved = (ids, pos, bounds, inputs, kept, h, rstd)

@@ -144,6 +144,10 @@ def test_native_body_matches_fp32_autograd(cuda_device, kind, lens):
     nat = NativeQwen2(cfg, cuda_device, init=w)
     opt = FusedAdamW(nat.named_parameters(), lr=1e-3, grad_dtype=torch.float32)
     nat.bind(opt)
+    # layer 0: attention half and gate_up output kept; layer 1: attention kept, MLP recomputed (gqa2) /
+    # everything recomputed (gqa7) -> all three backward variants are exercised
+    nat.body.keep_gate_up_layers = 1
+    nat.body.keep_attention_layers = 2 if kind == "gqa2" else 1
     hid = nat.hidden_states(ids, pos)[0]
     assert _rel(hid, hid_ref) <= 2e-2
     lp, ent = nat.forward_logprobs(batch, 1.0)

@@ -45,7 +45,7 @@ def synthetic_batch(cfg, T, n_samples, dev, seed):
 
 
 def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, warmup=1, layers=0, keep_attn=-1,
-            profile=False, dev=None, log=True):
+            profile=False, dev=None, log=True, keep_gate_up=-1):
     """Run the trainer step and return the result dict (also used by bench.py's `components.trainer_step`).
     Under torchrun (WORLD_SIZE > 1) every rank is a data-parallel learner with its own `micro` micro-batches and the
     optimizer step is the ShardedFusedAdamW exchange (P2P reduce-scatter + AdamW shard + P2P all-gather)."""
@@ -84,6 +84,12 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
     if keep_attn >= 0:
         model.body.keep_attention_layers = keep_attn
     torch.cuda.synchronize()
+    if keep_gate_up < 0:   # auto: spend the HBM that is left after ~24 GB of working set on kept gate_up outputs
+        free = torch.cuda.mem_get_info(dev)[0]
+        kept_attn_bytes = model.body.keep_attention_layers * tokens * (cfg.qkv_size + cfg.q_size + 2 * cfg.hidden_size) * 2
+        per_layer = tokens * 2 * cfg.intermediate_size * 2
+        keep_gate_up = int(max(0, min(model.body.keep_attention_layers, (free - 24e9 - kept_attn_bytes) // per_layer)))
+    model.body.keep_gate_up_layers = keep_gate_up
     say(f"model + optimizer state resident: {torch.cuda.memory_allocated() / 1e9:.1f} GB ({time.time() - t0:.1f} s)")
     n_samples_step = micro * samples_per_row * world
     rcfg = RLConfig(batch_size=n_samples_step)   # reference defaults: ppo, kl_coef 0.1, temperature 1.0
@@ -158,6 +164,7 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
            "peak_memory_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1),
            "loss": rec[-1][4], "grad_norm": rec[-1][5], "grad_accumulation": "fp32 in the optimizer arena",
            "attention": "torch SDPA (library)", "keep_attention_layers": model.body.keep_attention_layers,
+           "keep_gate_up_layers": model.body.keep_gate_up_layers,
            "gemm": "prl_gemm_ex (tcgen05 cta_group::2, MN-major dgrad/wgrad operands)"}
     del model, opt, batches
     import gc
@@ -176,6 +183,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--layers", type=int, default=0, help="override the layer count (debug)")
     ap.add_argument("--keep-attn", type=int, default=-1, help="layers whose attention half is kept for backward (-1 = all)")
+    ap.add_argument("--keep-gate-up", type=int, default=-1, help="layers that keep gate_up's output (-1 = as many as fit)")
     ap.add_argument("--profile", action="store_true", help="after the timed steps, print the per-kernel CUDA time of one step")
     ap.add_argument("--check", action="store_true", help="tiny model: DP result == single-learner result on all micro-batches")
     a = ap.parse_args()
@@ -183,7 +191,8 @@ def main():
     if a.check:
         print(json.dumps(check_dp()))
         return
-    res = measure(a.model, a.tokens, a.samples_per_row, a.micro, a.steps, a.warmup, a.layers, a.keep_attn, a.profile)
+    res = measure(a.model, a.tokens, a.samples_per_row, a.micro, a.steps, a.warmup, a.layers, a.keep_attn, a.profile,
+                  keep_gate_up=a.keep_gate_up)
     if int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps(res))
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
