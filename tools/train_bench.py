@@ -84,11 +84,13 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
     if keep_attn >= 0:
         model.body.keep_attention_layers = keep_attn
     torch.cuda.synchronize()
-    if keep_gate_up < 0:   # auto: spend the HBM that is left after ~24 GB of working set on kept gate_up outputs
+    if keep_gate_up < 0:   # auto: spend the HBM left after the kept attention halves + 20 GB of headroom
+        torch.cuda.empty_cache()
         free = torch.cuda.mem_get_info(dev)[0]
-        kept_attn_bytes = model.body.keep_attention_layers * tokens * (cfg.qkv_size + cfg.q_size + 2 * cfg.hidden_size) * 2
+        kept_bytes = tokens * 2 * (model.body.keep_attention_layers * (cfg.qkv_size + cfg.q_size + cfg.hidden_size)
+                                   + cfg.num_layers * cfg.hidden_size)
         per_layer = tokens * 2 * cfg.intermediate_size * 2
-        keep_gate_up = int(max(0, min(model.body.keep_attention_layers, (free - 24e9 - kept_attn_bytes) // per_layer)))
+        keep_gate_up = int(max(0, min(model.body.keep_attention_layers, (free - 20e9 - kept_bytes) // per_layer)))
     model.body.keep_gate_up_layers = keep_gate_up
     say(f"model + optimizer state resident: {torch.cuda.memory_allocated() / 1e9:.1f} GB ({time.time() - t0:.1f} s)")
     n_samples_step = micro * samples_per_row * world
