@@ -204,3 +204,44 @@ def test_native_model_trains_through_rl_step(cuda_device):
     (l_n, g_n), (l_f, g_f) = out["native"], out["fp32"]
     assert abs(l_n - l_f) <= 2e-2 * max(1.0, abs(l_f)), (l_n, l_f)
     assert abs(g_n - g_f) <= 5e-2 * g_f, (g_n, g_f)
+
+
+def test_full_size_layer_recompute_modes_agree(cuda_device):
+    """One transformer layer at Qwen2.5-7B width (H 3584, I 18944, 28/4 heads), 2 packed samples of 1024 tokens: the
+    backward must not depend on WHAT the forward kept (everything recomputed / attention half kept / attention half and
+    gate_up output kept).  MLP gradients see bit-identical operands in all three modes -> bitwise equal; the others go
+    through the library attention backward (fp32 atomics) -> equal to 1e-3 relative."""
+    from dataclasses import replace
+    from pipelinerl_b200.finetune.optim import FusedAdamW
+    from pipelinerl_b200.learner_model import NativeQwen2
+    from pipelinerl_b200.model import ModelConfig
+    cfg = replace(ModelConfig.qwen2_5_7b(), num_layers=1, vocab_size=2048)
+    g = torch.Generator().manual_seed(4)
+    T = 2048
+    ids = torch.randint(0, cfg.vocab_size, (1, T), generator=g).to(cuda_device)
+    pos = torch.cat([torch.arange(1024), torch.arange(1024)])[None].to(cuda_device)
+    dh = (torch.randn(T, cfg.hidden_size, generator=g) * 1e-2).to(torch.bfloat16).to(cuda_device)
+    model = NativeQwen2(cfg, cuda_device, seed=3)
+    opt = FusedAdamW(model.named_parameters(), lr=1e-3, grad_dtype=torch.float32)
+    model.bind(opt)
+    results = {}
+    for mode, (ka, kg) in {"recompute": (0, 0), "keep_attn": (1, 0), "keep_attn_gu": (1, 1)}.items():
+        model.body.keep_attention_layers, model.body.keep_gate_up_layers = ka, kg
+        opt.zero_grad()
+        hid = model.body.forward(ids[0], pos[0], keep=True)
+        model.body.backward(dh)
+        torch.cuda.synchronize()
+        results[mode] = ({n: v.clone() for n, v in opt.grad_views().items()}, hid.clone())
+    ref_g, ref_h = results["recompute"]
+    assert torch.isfinite(ref_h.float()).all() and all(torch.isfinite(v).all() for v in ref_g.values())
+    assert ref_g["layers.0.down_proj.weight"].abs().max().item() > 0
+    for mode in ("keep_attn", "keep_attn_gu"):
+        gr, h = results[mode]
+        assert torch.equal(h, ref_h)
+        for name in ("layers.0.down_proj.weight", "layers.0.gate_up_proj.weight", "layers.0.post_attention_layernorm.weight",
+                     "norm.weight"):
+            assert torch.equal(gr[name], ref_g[name]), (mode, name)
+        for name, v in ref_g.items():
+            if name == "lm_head.weight":
+                continue
+            assert _rel(gr[name], v) <= 1e-3, (mode, name, _rel(gr[name], v))
