@@ -119,3 +119,14 @@ def test_empty_and_single_sample_groups():
     out = populate_rl_data([e], 7, cfg)[0]
     assert out["advantages"] == [0.0, 0.0, 0.0]  # single member: baseline = own reward, std NaN -> 0
     assert out["group_tokens"] == [3.0] * 3 and out["num_labels"] == [2] * 3 and out["overflow"] == [0.0] * 3
+
+
+def test_native_body_segment_bounds_from_position_ids():
+    """Packed rows: every restart of position_ids opens a new causal segment (collate_packed layout, data.py:215-283)."""
+    import torch
+    from pipelinerl_b200.learner_body import NativeBody
+    pos = torch.tensor([0, 1, 2, 0, 1, 0, 0, 1, 2, 3])
+    assert NativeBody.segment_bounds(pos) == [(0, 3), (3, 5), (5, 6), (6, 10)]
+    assert NativeBody.segment_bounds(torch.arange(7)) == [(0, 7)]
+    # a row that does not start at position 0 (sequence-parallel slice): the head of the row is its own segment
+    assert NativeBody.segment_bounds(torch.tensor([5, 6, 0, 1])) == [(0, 2), (2, 4)]
