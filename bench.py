@@ -146,7 +146,9 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL_DEBUG=VERSION prints a banner)
+        # keep stdout to the single JSON line: NCCL writes its version banner / warnings to stdout unless told otherwise
+        os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")

@@ -59,6 +59,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     os.environ.setdefault("NCCL_DEBUG", "WARN")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=dev)
     assert world >= 2, "needs one learner and at least one sampler"
     cfg = ModelConfig.qwen2_5_7b() if args.model == "7b" else ModelConfig(

@@ -56,6 +56,7 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
         dev = torch.device(f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}")
         if not dist.is_initialized():
             os.environ.setdefault("NCCL_DEBUG", "WARN")
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=dev)
         log = log and rank == 0
     dev = dev or torch.device("cuda:0")
