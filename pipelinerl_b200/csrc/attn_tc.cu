@@ -324,11 +324,8 @@ extern "C" int prl_paged_attn_prefill_tc(const void* q, int32_t q_rows, const vo
                          (uint32_t)p.nq);
   if (rc) return rc;
   const int smem = 2 * kTile16K + 2 * kStageBytesT + 4 * kTile16K + 1024 + 8 * 20 + 2 * 128 * 4 + 16;
-  static bool configured = false;
-  if (!configured) {
-    PRL_CUDA(cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static SmemAttr smem_attr = {};
+  PRL_CUDA(ensure_smem(attn_prefill_tc_kernel, smem, smem_attr));
   dim3 grid((unsigned)(((max_q_len + p.nq - 1) / p.nq + 1) & ~1), (unsigned)n_kv, (unsigned)n_seqs);  // pairs of q tiles
   attn_prefill_tc_kernel<<<grid, kThreadsT, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
   PRL_LAUNCH_CHECK();

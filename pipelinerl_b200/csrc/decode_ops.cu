@@ -455,11 +455,8 @@ extern "C" int prl_residual_rmsnorm(const float* partials, int32_t n_split, int3
   PRL_CHECK_ARG(partials && gamma && h && x_bf16 && B >= 1 && H >= 4 && n_split >= 0, "prl_residual_rmsnorm: bad argument");
   PRL_CHECK_ARG(H % 4 == 0, "prl_residual_rmsnorm: hidden size must be a multiple of 4 (got %d)", H);
   PRL_CHECK_ARG(H * 4 <= 96 * 1024, "prl_residual_rmsnorm: hidden size too large for the row buffer");
-  static bool configured = false;
-  if (!configured) {
-    PRL_CUDA(cudaFuncSetAttribute(residual_rmsnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    configured = true;
-  }
+  static SmemAttr smem_attr = {};
+  PRL_CUDA(ensure_smem(residual_rmsnorm_kernel, 96 * 1024, smem_attr));
   int threads = ((H / 4 + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
   const size_t smem = (H / 4 > threads) ? (size_t)H * 4 : 0;

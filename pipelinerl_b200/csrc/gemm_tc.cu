@@ -407,12 +407,9 @@ int launch_gemm(const CUtensorMap& tw, const CUtensorMap& twl, const CUtensorMap
     if (n_stages < 2) n_stages = 2;
   }
   const int smem = n_stages * L::stage_bytes(lo) + 1024 /*align slack*/ + 8 * (2 * n_stages + 2) + 16;
-  static int configured[2] = {0, 0};
   auto kernel = p.head ? gemm_swapab_kernel<kNTile, true> : gemm_swapab_kernel<kNTile, false>;
-  if (configured[p.head ? 1 : 0] < smem) {
-    PRL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured[p.head ? 1 : 0] = smem;
-  }
+  static SmemAttr smem_attr[2] = {};
+  PRL_CUDA(ensure_smem(kernel, smem, smem_attr[p.head ? 1 : 0]));
   dim3 grid((unsigned)(((p.N + kBlockM - 1) / kBlockM) * ((p.M + kNTile - 1) / kNTile)), (unsigned)p.split_k, 1);
   PRL_CUDA(launch_pdl(kernel, grid, dim3(kThreads), (size_t)smem, stream, tw, twl, tx, p, n_stages));
   PRL_LAUNCH_CHECK();
@@ -553,11 +550,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
 int launch_gemm_pair(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, cudaStream_t stream) {
   int n_stages = 6;
   const int smem = n_stages * k2StageBytes + 1024 + 8 * (2 * n_stages + 2) + 16;
-  static int configured = 0;
-  if (!configured) {
-    PRL_CUDA(cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = 1;
-  }
+  static SmemAttr smem_attr = {};
+  PRL_CUDA(ensure_smem(gemm_pair_kernel, smem, smem_attr));
   const int64_t pairs = ((p.N + 2 * kBlockM - 1) / (2 * kBlockM)) * ((p.M + k2TokTile - 1) / k2TokTile);
   dim3 grid((unsigned)(2 * pairs), (unsigned)p.split_k, 1);
   PRL_CUDA(launch_pdl(gemm_pair_kernel, grid, dim3(kThreads), (size_t)smem, stream, tw, tx, p, n_stages));

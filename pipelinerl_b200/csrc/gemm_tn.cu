@@ -434,11 +434,8 @@ extern "C" int prl_gemm_ex(const void* A, int64_t lda, int32_t a_mn_major, const
                   : make_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBK, kHalf);
   if (rc) return rc;
   const int smem = kStages * kStageBytes + 1024 + 8 * (2 * kStages + 4) + 16;
-  static bool configured = false;
-  if (!configured) {
-    PRL_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static SmemAttr smem_attr = {};
+  PRL_CUDA(ensure_smem(gemm_tn_kernel<false>, smem, smem_attr));
   const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = (int)tiles;
@@ -467,11 +464,8 @@ int head_logprob_tn(const void* W, const void* X, int64_t M, int64_t V, int64_t 
   rc = make_tmap_2d_bf16(&tb, W, (uint64_t)K, (uint64_t)V, (uint64_t)K * 2, kBK, kHalf);
   if (rc) return rc;
   const int smem = kStages * kStageBytes + 1024 + 8 * (2 * kStages + 4) + 16;
-  static bool configured = false;
-  if (!configured) {
-    PRL_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static SmemAttr smem_attr = {};
+  PRL_CUDA(ensure_smem(gemm_tn_kernel<true>, smem, smem_attr));
   const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = (int)tiles;

@@ -576,11 +576,8 @@ extern "C" int prl_paged_attn_decode(const void* q, const void* kv_cache, int64_
   p.tickets = g_fused_combine ? reinterpret_cast<unsigned int*>(p.ml_part + (size_t)B * n_q * n_splits * 2) : nullptr;
   p.out = (__nv_bfloat16*)out_bf16;
   const int smem = kStages * kStageBytes + 1024 + 8 * 2 * kStages + 4 * kMaxPagesPerSplit + 16;
-  static bool configured = false;
-  if (!configured) {
-    PRL_CUDA(cudaFuncSetAttribute(paged_attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static SmemAttr smem_attr = {};
+  PRL_CUDA(ensure_smem(paged_attn_decode_kernel, smem, smem_attr));
   cudaStream_t stream = (cudaStream_t)stream_;
   dim3 grid((unsigned)n_splits, (unsigned)n_kv, (unsigned)B);
   PRL_CUDA(launch_pdl(paged_attn_decode_kernel, grid, dim3(kThreads), (size_t)smem, stream, tm, p));
@@ -616,11 +613,8 @@ extern "C" int prl_paged_attn_prefill(const void* q, const void* kv_cache, int64
   p.seq_slot = seq_slot; p.max_blocks = max_blocks; p.n_q = n_q; p.n_kv = n_kv; p.R = n_q / n_kv;
   p.n_pages = n_pages; p.layer = layer; p.scale_log2 = sm_scale * 1.4426950408889634f;
   const int smem = kStages * kStageBytes + 1024 + 8 * 2 * kStages + 16;
-  static bool configured = false;
-  if (!configured) {
-    PRL_CUDA(cudaFuncSetAttribute(paged_attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static SmemAttr smem_attr = {};
+  PRL_CUDA(ensure_smem(paged_attn_prefill_kernel, smem, smem_attr));
   dim3 grid((unsigned)((max_q_len + 15) / 16), (unsigned)n_kv, (unsigned)n_seqs);
   PRL_CUDA(launch_pdl(paged_attn_prefill_kernel, grid, dim3((p.R + 1) * 32), (size_t)smem, (cudaStream_t)stream_, tm, p));
   PRL_LAUNCH_CHECK();

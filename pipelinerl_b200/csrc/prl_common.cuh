@@ -67,6 +67,24 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE function attribute: remember the largest size granted
+// on each device (one static SmemAttr per launch site) instead of a per-process flag.
+constexpr int kMaxDevices = 16;
+struct SmemAttr { int bytes[kMaxDevices]; };
+template <typename K>
+inline cudaError_t ensure_smem(K kernel, int smem, SmemAttr& st) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (st.bytes[dev] < smem) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    st.bytes[dev] = smem;
+  }
+  return cudaSuccess;
+}
+
 constexpr int kWarp = 32;
 
 // PDL device side: let the next kernel of the stream start its prologue / weight prefetch now ...
