@@ -14,6 +14,19 @@ class RetryableAbortedCompletionError(TimeoutError):
     """Abort-shaped completion that should be retried instead of treated as data."""
 
 
+def _field(obj, name):
+    """tool calls arrive as pydantic objects (litellm types in the reference) or as plain dicts"""
+    return obj[name] if isinstance(obj, dict) else getattr(obj, name)
+
+
+def _token_ids(encoded) -> list[int]:
+    """apply_chat_template(tokenize=True) returns a list of ids with the transformers the reference pins (4.57) and a
+    BatchEncoding with transformers >= 5: accept both."""
+    if hasattr(encoded, "keys") and "input_ids" in encoded.keys():
+        encoded = encoded["input_ids"]
+    return list(encoded)
+
+
 def _chat_kwargs(llm: TrainableLLM, prompt: Prompt) -> dict:
     kw = dict(llm.chat_template_kwargs or {})
     if prompt.tools:
@@ -27,8 +40,8 @@ async def llm_async_generate(llm: TrainableLLM, prompt: Prompt, session=None,
     engine is in-process.  Returns an LLMCall with .output.content, .logprobs[i].{token_id, logprob},
     .prompt_length_tokens, .output_length_tokens and .llm_info['finish_reason'] in {stop, length}."""
     tok = llm.load_tokenizer()
-    prompt_ids = prompt.token_ids or tok.apply_chat_template(prompt.messages, add_generation_prompt=True,
-                                                            **_chat_kwargs(llm, prompt))
+    prompt_ids = prompt.token_ids or _token_ids(tok.apply_chat_template(prompt.messages, add_generation_prompt=True,
+                                                                        **_chat_kwargs(llm, prompt)))
     params = llm.parameters
     max_tokens = int(max_tokens_override if max_tokens_override is not None else params.get("max_tokens", 16))
     temperature = float(params.get("temperature", 1.0))
@@ -58,9 +71,15 @@ def make_training_text(llm: TrainableLLM, llm_call: LLMCall) -> TrainingText:
     kw = _chat_kwargs(llm, llm_call.prompt)
     prompt_ids = llm_call.llm_info.get("prompt_token_ids")
     if prompt_ids is None:
-        prompt_ids = tok.apply_chat_template(llm_call.prompt.messages, add_generation_prompt=True, **kw)
+        prompt_ids = _token_ids(tok.apply_chat_template(llm_call.prompt.messages, add_generation_prompt=True, **kw))
     prompt_text = tok.apply_chat_template(llm_call.prompt.messages, tokenize=False, add_generation_prompt=True, **kw)
-    full = llm_call.prompt.messages + [{"role": "assistant", "content": llm_call.output.content or ""}]
+    assistant: dict = {"role": "assistant", "content": llm_call.output.content or ""}
+    if llm_call.output.tool_calls:   # rendered by the chat template exactly as the reference passes them (:227-238)
+        assistant["tool_calls"] = [{"id": _field(tc, "id"), "type": "function",
+                                    "function": {"name": _field(_field(tc, "function"), "name"),
+                                                 "arguments": _field(_field(tc, "function"), "arguments")}}
+                                   for tc in llm_call.output.tool_calls]
+    full = llm_call.prompt.messages + [assistant]
     text = tok.apply_chat_template(full, tokenize=False, **kw)
     output_text = text[len(prompt_text):]
     bos = getattr(tok, "bos_token", None)

@@ -130,3 +130,32 @@ def test_native_body_segment_bounds_from_position_ids():
     assert NativeBody.segment_bounds(torch.arange(7)) == [(0, 7)]
     # a row that does not start at position 0 (sequence-parallel slice): the head of the row is its own segment
     assert NativeBody.segment_bounds(torch.tensor([5, 6, 0, 1])) == [(0, 2), (2, 4)]
+
+
+def test_make_training_text_matches_reference():
+    """Row a2 (integer path, bit-exact): tests/golden/training_text_cases.json holds the outputs of the reference's
+    make_training_text (pipelinerl/async_llm.py:215-346) on a locally built chat tokenizer — stop / length / eos in the
+    content / chat-template kwargs / tools + tool calls / bos stripping.  Same inputs through this package's function."""
+    import json
+    from pipelinerl_b200.async_llm import make_training_text
+    from pipelinerl_b200.llm import LLMCall, LLMOutput, Prompt, TokenLogprob, TrainableLLM
+    from tests.helpers import GOLDEN, tiny_chat_tokenizer
+    tok = tiny_chat_tokenizer()
+    cases = json.loads((GOLDEN / "training_text_cases.json").read_text())
+    assert len(cases) >= 6
+    for item in cases:
+        c, want = item["case"], item["expected"]
+        llm = TrainableLLM(base_url="inproc://none", model_name="tiny", tokenizer_name="tiny",
+                           parameters={"max_tokens": 8}, collect_logprobs=True,
+                           chat_template_kwargs=c.get("chat_template_kwargs"))
+        llm.tokenizer = tok
+        tcs = [{"id": t["id"], "function": {"name": t["name"], "arguments": t["arguments"]}}
+               for t in c.get("tool_calls", [])] or None
+        call = LLMCall(prompt=Prompt(messages=c["messages"], tools=c.get("tools")),
+                       output=LLMOutput(content=c["content"], tool_calls=tcs),
+                       prompt_length_tokens=c["prompt_len"], output_length_tokens=c["out_len"],
+                       llm_info={"finish_reason": c["finish_reason"]} if c["finish_reason"] else {},
+                       logprobs=[TokenLogprob(logprob=-0.25 * (i + 1), token_id=t) for i, t in enumerate(c["gen"])])
+        got = make_training_text(llm, call)
+        for k, v in want.items():
+            assert getattr(got, k) == v, (c["name"], k, getattr(got, k), v)
