@@ -65,3 +65,29 @@ def test_ops_fail_loudly_without_cuda():
     p = torch.nn.Parameter(torch.zeros(4))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         FusedAdamW([("w", p)], lr=1e-3)
+
+
+def test_argument_validation_needs_no_gpu(built_lib):
+    """Every entry point validates its arguments BEFORE touching CUDA: bad shapes come back as a negative status with a
+    message (the C ABI never throws).  Dummy non-NULL pointers are never dereferenced on these paths."""
+    lib, P = built_lib, 0x1000
+    cases = [
+        (lambda: lib.prl_gemm_ex(P, 20, 0, P, 24, 0, 16, 16, 20, P, 16, 0, 0, None, None, 0, 1.0, None), b"multiples of 8"),
+        (lambda: lib.prl_gemm_ex(P, 24, 0, P, 24, 0, 16, 16, 24, P, 16, 0, 1, None, None, 0, 1.0, None), b"accumulate"),
+        (lambda: lib.prl_gemm_ex(P, 24, 0, P, 24, 0, 16, 16, 24, P, 8, 0, 0, None, None, 0, 1.0, None), b"ldc"),
+        (lambda: lib.prl_gemm_ex(None, 8, 0, P, 8, 0, 8, 8, 8, P, 8, 0, 0, None, None, 0, 1.0, None), b"NULL"),
+        (lambda: lib.prl_transpose_bf16(P, 8, 16, 8, P, 8, None), b"bad shape"),
+        (lambda: lib.prl_rmsnorm_fwd(P, P, 4, 12, 1e-6, P, P, None), b"multiple of 8"),
+        (lambda: lib.prl_rmsnorm_fwd(P, P, 4, 16384, 1e-6, P, P, None), b"8192"),
+        (lambda: lib.prl_rope_inplace(P, 256, 4, 2, 100, P, P, 1.0, None), b"head_dim"),
+        (lambda: lib.prl_silu_mul_fwd(P, 4, 12, P, None), b"I % 8"),
+        (lambda: lib.prl_paged_attn_prefill_tc(P, 8, P, 4, 1, 0, P, 4, P, P, P, P, 1, 8, 4, 2, 64, 64, 0.1, P, None),
+         b"head_dim"),
+        (lambda: lib.prl_paged_attn_prefill_tc(P, 8, P, 4, 1, 3, P, 4, P, P, P, P, 1, 8, 4, 2, 128, 64, 0.1, P, None),
+         b"bad layer"),
+        (lambda: lib.prl_head_logprob(P, None, P, 4, 16, 12, 1.0, None, 1, 0, 0, None, None, None, None, None, P, 1 << 20,
+                                      None), b"K % 8"),
+    ]
+    for call, needle in cases:
+        assert call() < 0
+        assert needle in lib.prl_last_error(), (needle, lib.prl_last_error())
