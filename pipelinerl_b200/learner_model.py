@@ -1,11 +1,18 @@
-"""Learner-side Qwen2 module whose parameters ARE views of one arena in the fused layout (model.py).
+"""Learner-side Qwen2 modules whose parameters live in the fused arena layout (model.py).
 
-The transformer BODY here is plain torch (F.linear / SDPA): the sm_100a trainer-body kernels
-(varlen attention fwd/bwd, fused blocks) are the next row of SURVEY §8(f) and are not built yet, so
-this module is plumbing that lets the full actor -> preprocess -> rl_step -> FusedAdamW -> weight
-push loop run end to end with the hot-path kernels that do exist (logprob tail, PG loss, AdamW, push).
-Because parameter order and alignment equal `fused_shapes`, FusedAdamW's bf16 shadow arena has exactly
-the sampler's arena layout and can be pushed as raw bytes.
+`NativeQwen2` (bottom of this file) is the B200 learner: its body is learner_body.NativeBody — hand-scheduled forward /
+backward on the persistent CTA-pair tcgen05 GEMM and the row kernels of csrc/learner_ops.cu, fp32 gradient accumulation
+in the optimizer arena, fused head without logits.  It is what `run_training`, tools/train_bench.py and
+tools/pipeline_bench.py use.
+
+`TorchQwen2` is the same architecture as a plain torch module (F.linear / SDPA under autograd, any dtype).  `rl_step`
+accepts ANY torch module whose output has `.logits` (the reference contract, rl/__init__.py:190-207), and this one is
+the stand-in for "some other HF-style model": the pipeline tests drive it end to end and the learner-body tests use its
+fp32 autograd as a second opinion next to oracle/learner_oracle.py.  It is not a fallback: nothing selects it
+automatically.
+
+Because parameter order and alignment equal `fused_shapes`, FusedAdamW's bf16 shadow arena has exactly the sampler's
+arena layout and can be pushed as raw bytes.
 """
 from __future__ import annotations
 
