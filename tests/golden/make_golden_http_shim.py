@@ -75,6 +75,16 @@ async def main_async():
                                                "finish_reason": call.llm_info.get("finish_reason")}})
                 print(c["name"], "->", call.output.content[:40].replace("\n", " "), call.llm_info.get("finish_reason"),
                       len(call.logprobs), "logprobs")
+        # the reference-logprob pass: TrainableLLM.get_batch_logprobs_token_ids (llm.py:606-648) is synchronous
+        # (requests.post) -> run it in a worker thread while this loop serves the shim
+        prompts, completions = [[5, 6, 7], [9, 10, 11, 12]], [[8, 3], [13]]
+        self_ns = types.SimpleNamespace(tokenizer=tok, load_tokenizer=lambda: None, api_token=None, model_name="tiny",
+                                        base_url=url)
+        scored = await asyncio.get_running_loop().run_in_executor(
+            None, lambda: ref_llm.TrainableLLM.get_batch_logprobs_token_ids(self_ns, prompts, completions))
+        out["score"] = {"prompt_token_ids": prompts, "completion_token_ids": completions,
+                        "request": captured["request"], "response": captured["response"], "parsed": scored}
+        print("score ->", [[(d["token_id"], round(d["logprob"], 3)) for d in s["content"]] for s in scored])
     finally:
         await shim.stop()
         server.stop()

@@ -89,6 +89,17 @@ def test_chat_completions_replays_what_the_reference_client_accepted():
                     assert got["usage"]["prompt_tokens"] == case["parsed"]["prompt_length_tokens"]
                     assert got["usage"]["completion_tokens"] == case["parsed"]["output_length_tokens"]
                     assert ch["finish_reason"] == case["parsed"]["finish_reason"]
+                # reference-logprob pass as TrainableLLM.get_batch_logprobs_token_ids sends and reads it (llm.py:606-648)
+                sc = rec["score"]
+                async with s.post(url + "/v1/completions", json=sc["request"]) as r:
+                    assert r.status == 200
+                    got = await r.json()
+                assert _strip(got) == _strip(sc["response"])
+                for i, comp in enumerate(sc["completion_token_ids"]):
+                    tail = got["choices"][i]["prompt_logprobs"][-len(comp):]
+                    parsed = [{**v, "generated": 0, "token_id": k} for lp in tail for k, v in lp.items()]
+                    assert parsed == sc["parsed"][i]["content"]
+                    assert [int(p["token_id"]) for p in parsed] == comp
                 async with s.get(url + "/health") as r:
                     assert r.status == 200 and (await r.text()) == "OK"
                 async with s.post(url + "/receive_weight_update", json={"version": 9}) as r:
