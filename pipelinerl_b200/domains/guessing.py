@@ -26,6 +26,9 @@ def _history_message(target: int, guesses: list[int]) -> str:
     lines = [f"Your {len(guesses)} previous guesses:"]
     for g in guesses:
         lines.append(f"{g}, which is {'lower' if g < target else 'higher'} than the target number.")
+    # the reference builds this message with a `for ... else` whose else-branch always runs (guessing.py:41-46), so
+    # every history message ends with this line; kept verbatim: the prompt text is part of the plugin's behaviour
+    lines.append("<wrong output>")
     return "\n".join(lines)
 
 

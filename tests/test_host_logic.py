@@ -159,3 +159,40 @@ def test_make_training_text_matches_reference():
         got = make_training_text(llm, call)
         for k, v in want.items():
             assert getattr(got, k) == v, (c["name"], k, getattr(got, k), v)
+
+
+def test_guessing_plugin_matches_reference_plugin():
+    """Plugin surface: tests/golden/plugin_guessing.json was recorded by running the REFERENCE's example plugin
+    (pipelinerl/domains/guessing/guessing.py, unmodified) on this package's TrainableLLM / llm_async_generate /
+    make_training_text / RolloutResult with a scripted sampler (make_golden_plugin.py).  This package's own port of the
+    plugin must send the same prompts turn by turn and return the same RolloutResult; load_problems must agree."""
+    import asyncio
+    import json
+    from pipelinerl_b200.domains.guessing import generate_guessing_rollout, load_problems
+    from pipelinerl_b200.llm import TrainableLLM
+    from tests.helpers import GOLDEN, ScriptedSampler, ScriptedTokenizer
+    rec = json.loads((GOLDEN / "plugin_guessing.json").read_text())
+    scenarios = [r for r in rec if "scenario" in r]
+    assert len(scenarios) >= 4
+    for r in scenarios:
+        sc = r["scenario"]
+        sampler = ScriptedSampler("replay", sc["script"])
+        llm = TrainableLLM(base_url=sampler.base_url, model_name="scripted", tokenizer_name="scripted",
+                           parameters={"max_tokens": 8, "temperature": 1.0}, collect_logprobs=True)
+        llm.tokenizer = ScriptedTokenizer()
+        try:
+            res = asyncio.new_event_loop().run_until_complete(
+                generate_guessing_rollout({}, llm, {"answer": sc["answer"], "dataset": "train", "domain": "guessing"}, None))
+        finally:
+            sampler.close()
+        assert sampler.prompts_seen == r["calls"], sc["name"]          # identical prompts, turn by turn
+        want = r["result"]
+        assert res.metrics.model_dump() == want["metrics"], sc["name"]
+        assert (res.dataset_name, res.domain) == (want["dataset_name"], want["domain"])
+        assert len(res.training_texts) == len(want["training_texts"])
+        for got, w in zip(res.training_texts, want["training_texts"]):
+            for k, v in w.items():
+                assert getattr(got, k) == v, (sc["name"], k)
+    lp = [r for r in rec if "load_problems" in r][0]["load_problems"]
+    assert load_problems(["train"])[:3] == lp["train_first"] and load_problems(["test"])[:3] == lp["test_first"]
+    assert len(load_problems(["train", "test"])) == lp["n"]
