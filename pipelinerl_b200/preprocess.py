@@ -31,7 +31,28 @@ def preprocess_dataset(samples: list[dict[str, Any]], tokenizer, seq_length: int
         enc["model_version"] = meta.get("model_version", 0)
         entries.append(enc)
     entries = populate_rl_data(entries, tokenizer.eos_token_id, rl_config)
-    return [e for e in entries if len(e["input_ids"]) <= seq_length]
+    entries = [e for e in entries if len(e["input_ids"]) <= seq_length]
+    if rl_config.filter_zero_advantage_groups:
+        entries, _ = filter_zero_advantage_groups(entries)
+    return entries
+
+
+def filter_zero_advantage_groups(entries: list[dict], epsilon: float = 1e-6) -> tuple[list[dict], int]:
+    """Drop every group none of whose samples carries an advantage with |a| > epsilon (all attempts got the same
+    reward: no learning signal).  Applied by the preprocessor when `RLConfig.filter_zero_advantage_groups` is set
+    (pipelinerl/preprocess.py:316-353, call site :548-552).  Groups keep their first-seen order, samples their order
+    inside the group; returns (kept entries, number of samples dropped)."""
+    by_group: dict[Any, list[dict]] = {}
+    for e in entries:
+        by_group.setdefault(e["group_id"], []).append(e)
+    kept: list[dict] = []
+    dropped = 0
+    for members in by_group.values():
+        if any(abs(a) > epsilon for m in members for a in m["advantages"]):
+            kept.extend(members)
+        else:
+            dropped += len(members)
+    return kept, dropped
 
 
 def pack_micro_batches(entries: list[dict], tokenizer, seq_length: int, seq_parallel: int = 1,

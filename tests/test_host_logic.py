@@ -196,3 +196,17 @@ def test_guessing_plugin_matches_reference_plugin():
     lp = [r for r in rec if "load_problems" in r][0]["load_problems"]
     assert load_problems(["train"])[:3] == lp["train_first"] and load_problems(["test"])[:3] == lp["test_first"]
     assert len(load_problems(["train", "test"])) == lp["n"]
+
+
+def test_filter_zero_advantage_groups_matches_reference():
+    """preprocess.filter_zero_advantage_groups against the reference function executed on the same entries
+    (tests/golden/filter_zero_advantage_cases.json, make_golden_filter.py): same samples kept, in the same order."""
+    import json
+    from pipelinerl_b200.preprocess import filter_zero_advantage_groups
+    from tests.helpers import GOLDEN
+    cases = json.loads((GOLDEN / "filter_zero_advantage_cases.json").read_text())
+    assert len(cases) == 4
+    for c in cases:
+        kept, dropped = filter_zero_advantage_groups([dict(e) for e in c["entries"]])
+        assert [e["uid"] for e in kept] == c["kept_uids"]
+        assert dropped == c["dropped"]
