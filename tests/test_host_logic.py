@@ -210,3 +210,45 @@ def test_filter_zero_advantage_groups_matches_reference():
         kept, dropped = filter_zero_advantage_groups([dict(e) for e in c["entries"]])
         assert [e["uid"] for e in kept] == c["kept_uids"]
         assert dropped == c["dropped"]
+
+
+def test_schedule_rollouts_matches_reference_scheduler():
+    """Row a3: tests/golden/scheduler_case.json was recorded by EXECUTING the reference's schedule_rollouts
+    (pipelinerl/actor.py:114-286) with a scripted policy (make_golden_scheduler.py).  Same script through this package's
+    scheduler: identical least-busy routing of every rollout, identical group ids and identical stamping of
+    model_version / rollout_index / step_index on every training text."""
+    import asyncio
+    import json
+    from pipelinerl_b200.actor import schedule_rollouts
+    from pipelinerl_b200.rollouts import BaseMetrics, RolloutResult, TrainingText
+    from tests.helpers import GOLDEN
+    rec = json.loads((GOLDEN / "scheduler_case.json").read_text())
+    sc = rec["scenario"]
+    launches, groups = [], []
+
+    async def policy(cfg, llm, problem, session):
+        launches.append({"answer": problem["answer"], "llm": llm.name})
+        await asyncio.sleep(0.05)
+        texts = [TrainingText(text=f"p{problem['answer']}t{t}", n_predicted=1, input_ids=[1, 2], labels=[-100, 2],
+                              logprobs=[-0.5], output_tokens=1, prompt_tokens=1) for t in range(sc["turns"])]
+        return RolloutResult(training_texts=texts, latency=0.05, dataset_name=problem["dataset"],
+                             metrics=BaseMetrics(reward=1.0, success=True, no_error=True, no_answer=False))
+
+    class L:
+        def __init__(self, name):
+            self.name = name
+    llms = [L(f"llm{i}") for i in range(sc["n_llms"])]
+    stats = asyncio.new_event_loop().run_until_complete(
+        schedule_rollouts({}, sc["attempts"], sc["problems"], llms, policy, groups.append,
+                          get_model_version=lambda: sc["model_version"], max_rollouts_per_llm=sc["llm_max_rollouts"],
+                          scheduler_name=sc["scheduler_name"]))
+    assert launches == rec["launches"]
+    assert stats["started"] == stats["finished"] == len(rec["launches"]) and stats["groups"] == len(rec["groups"])
+    got = []
+    for g in groups:
+        rolls = sorted(g, key=lambda r: r.training_texts[0].metadata["rollout_index"])
+        got.append({"group_id": rolls[0].group_id, "n": len(rolls),
+                    "rollouts": [{"model_version": r.model_version, "group_id": r.group_id,
+                                  "texts": [{"group_id": t.group_id, "metadata": dict(t.metadata), "text": t.text}
+                                            for t in r.training_texts]} for r in rolls]})
+    assert sorted(got, key=lambda d: d["group_id"]) == rec["groups"]
