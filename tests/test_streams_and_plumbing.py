@@ -145,3 +145,64 @@ def test_trainer_state_follows_topic(tmp_path):
         w.write(TrainingDone())
         assert st.wait_for_training_done(timeout=5) and st.training_done
         st.stop()
+
+
+def test_file_streams_interoperate_with_the_reference_backend(tmp_path):
+    """tests/golden/streams_tree.json = the tree the REFERENCE's file backend wrote (make_golden_streams.py).  (1) this
+    package's writer, given the same writes, produces the same files (same relative paths, JSON-equal lines in the same
+    order: round-robin and explicit partitions, pydantic models, numpy / tensor payloads); (2) this package's reader,
+    pointed at the reference-written tree, yields what the reference's own reader yielded."""
+    import json
+    import numpy as np
+    import torch
+    from pydantic import BaseModel
+    from pipelinerl_b200 import streams
+    from tests.helpers import GOLDEN
+    rec = json.loads((GOLDEN / "streams_tree.json").read_text())
+
+    class Success(BaseModel):
+        kind: str = "weight_update_success"
+        version: int
+        timestamp: float
+
+    class WithTensor(BaseModel):
+        model_config = {"arbitrary_types_allowed": True}
+        name: str
+        values: torch.Tensor
+    g1 = [{"text": "a b", "input_ids": [1, 2, 3], "logprobs": [-0.5, -0.25], "reward": 1.0, "group_id": "actor0_0",
+           "metadata": {"model_version": 7, "rollout_index": 0, "step_index": 0}, "finished": True}]
+    g2 = [{"text": "é ü", "input_ids": [4], "logprobs": [-1.5], "reward": 0.0, "group_id": "actor0_1",
+           "metadata": {"model_version": 7, "rollout_index": 1, "step_index": 0}, "finished": False}]
+    writes = [
+        ("actor", dict(instance=0, partition=0), [(g1, None), (g2, None)]),
+        ("training_data", dict(instance=0, partition_range=(0, 2)),
+         [({"i": i, "arr": (np.arange(3) + i)}, None) for i in range(5)] + [({"i": 99, "arr": np.zeros(2)}, 1)]),
+        ("weight_update_request", dict(instance=0, partition=0),
+         [(Success(version=3, timestamp=12.5), None), (WithTensor(name="t", values=torch.arange(4, dtype=torch.float32)), None)]),
+    ]
+    streams.reset_streams_backend()
+    streams.set_streams_backend("files")
+    try:
+        mine = tmp_path / "mine"
+        for topic, kw, items in writes:
+            spec = streams.StreamRangeSpec(exp_path=mine, topic=topic, **kw) if "partition_range" in kw \
+                else streams.SingleStreamSpec(exp_path=mine, topic=topic, **kw)
+            with streams.write_to_streams(spec) as w:
+                for payload, part in items:
+                    w.write(payload, partition=part) if part is not None else w.write(payload)
+        tree = {str(p.relative_to(mine)): p.read_text(encoding="utf-8") for p in sorted(mine.rglob("*.jsonl"))}
+        assert sorted(tree) == sorted(rec["tree"])
+        for rel, text in rec["tree"].items():
+            want = [json.loads(line) for line in text.splitlines()]
+            got = [json.loads(line) for line in tree[rel].splitlines()]
+            assert got == want, rel
+        # reference-written tree -> this package's reader
+        theirs = tmp_path / "theirs"
+        for rel, text in rec["tree"].items():
+            f = theirs / rel
+            f.parent.mkdir(parents=True, exist_ok=True)
+            f.write_text(text, encoding="utf-8")
+        with streams.read_stream(streams.SingleStreamSpec(exp_path=theirs, topic="actor")) as r:
+            assert r.read_available() == rec["actor_read_back"]
+    finally:
+        streams.reset_streams_backend()
