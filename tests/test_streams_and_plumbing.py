@@ -206,3 +206,23 @@ def test_file_streams_interoperate_with_the_reference_backend(tmp_path):
             assert r.read_available() == rec["actor_read_back"]
     finally:
         streams.reset_streams_backend()
+
+
+def test_trainer_messages_are_what_the_reference_parses():
+    """tests/golden/trainer_messages.json: dumps of this package's trainer messages that the REFERENCE's TrainerMessage
+    union (finetune_loop.py:138-171, as state.py:35-47 uses it) parsed into the class of the same name with the same
+    fields.  The dumps must stay what was recorded; the topic name must stay the reference's."""
+    import json
+    from pipelinerl_b200 import weights as w
+    from tests.helpers import GOLDEN
+    rec = json.loads((GOLDEN / "trainer_messages.json").read_text())
+    assert rec["topic"] == "weight_update_request"
+    mk = {"WeightUpdateSuccess": lambda: w.WeightUpdateSuccess(version=12, timestamp=3.5),
+          "SamplesProcessed": lambda: w.SamplesProcessed(samples_processed=640, timestamp=4.5),
+          "TrainingDone": lambda: w.TrainingDone(timestamp=5.5),
+          "WeightUpdateRequest": lambda: w.WeightUpdateRequest(
+              version=13, timestamp=6.5, parameters_info=[w.ParameterInfo(name="w", shape=[2, 3], dtype="bfloat16")])}
+    assert len(rec["messages"]) == 4
+    for m in rec["messages"]:
+        assert m["reference_class"] == m["ours"]
+        assert mk[m["ours"]]().model_dump() == m["dump"] == m["reference_fields"]
