@@ -151,6 +151,56 @@ def get_optimizer(name: str, model, learning_rate: float, weight_decay: float, *
     return FusedAdamW(model.named_parameters(), lr=learning_rate, weight_decay=weight_decay, **kw)
 
 
+class LRSchedule:
+    """Learning-rate schedule of the trainer: `get_scheduler(args.lr_scheduler_type, optimizer, args.num_warmup_steps,
+    args.max_train_steps)` at pipelinerl/finetune_loop.py:394-399, i.e. transformers' LambdaLR schedules (the reference's
+    defaults: cosine, 50 warm-up steps, conf/finetune/base.yaml:41-43).  The factor of step t (t = number of `step()`
+    calls so far) multiplies the base rate found in `optimizer.param_groups[*]["lr"]` at construction; the fused
+    optimizers read `param_groups[0]["lr"]` at every step, so no kernel argument changes."""
+
+    KINDS = ("constant", "constant_with_warmup", "linear", "cosine")
+
+    def __init__(self, kind: str, optimizer, num_warmup_steps: int = 0, num_training_steps: int | None = None):
+        if kind not in self.KINDS:
+            raise ValueError(f"Unknown lr_scheduler_type {kind!r} (supported: {', '.join(self.KINDS)})")
+        if kind in ("linear", "cosine") and num_training_steps is None:
+            raise ValueError(f"{kind} schedule needs num_training_steps")
+        self.kind, self.opt = kind, optimizer
+        self.warmup, self.total = int(num_warmup_steps), num_training_steps
+        self.base_lrs = [g["lr"] for g in optimizer.param_groups]
+        self.last_step = 0
+        self._apply()
+
+    def factor(self, t: int) -> float:
+        import math
+        if self.kind == "constant":
+            return 1.0
+        if t < self.warmup:
+            return t / max(1, self.warmup)
+        if self.kind == "constant_with_warmup":
+            return 1.0
+        if self.kind == "linear":
+            return max(0.0, (self.total - t) / max(1, self.total - self.warmup))
+        progress = (t - self.warmup) / max(1, self.total - self.warmup)
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * progress)))   # num_cycles = 0.5
+
+    def _apply(self) -> None:
+        f = self.factor(self.last_step)
+        for g, base in zip(self.opt.param_groups, self.base_lrs):
+            g["lr"] = base * f
+
+    def step(self) -> None:
+        self.last_step += 1
+        self._apply()
+
+    def get_last_lr(self) -> list[float]:
+        return [g["lr"] for g in self.opt.param_groups]
+
+
+def get_scheduler(name: str, optimizer, num_warmup_steps: int = 0, num_training_steps: int | None = None) -> LRSchedule:
+    return LRSchedule(name, optimizer, num_warmup_steps, num_training_steps)
+
+
 class ShardedFusedAdamW:
     """Data-parallel learners: gradient reduce-scatter + AdamW on a 1/Ng shard + bf16 parameter all-gather as one
     exchange step over NVLink peer memory (csrc/adamw.cu: shard_reduce / shard_update), with the fp32 optimizer

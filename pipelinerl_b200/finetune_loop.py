@@ -30,6 +30,11 @@ class TrainerConfig:
     weight_decay: float = 0.01
     gradient_clipping_threshold: float | None = 0.3
     max_train_steps: int = 10
+    # learning-rate schedule (finetune_loop.py:394-399).  The reference's production values are "cosine" with 50
+    # warm-up steps over max_train_steps = 100000 (conf/finetune/base.yaml:41-53); the default here is the constant rate
+    # because this dataclass's default max_train_steps is a 10-step smoke value
+    lr_scheduler_type: str = "constant"
+    num_warmup_steps: int = 0
     weight_update_interval: int = 1
     rl: RLConfig = field(default_factory=RLConfig)
 
@@ -68,6 +73,8 @@ def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding
             model.bind(opt)
     if weight_manager is not None:
         weight_manager.src = opt.shadow_bf16
+    from .finetune.optim import get_scheduler
+    lr_schedule = get_scheduler(cfg.lr_scheduler_type, opt, cfg.num_warmup_steps, cfg.max_train_steps)
     rl_cfg = cfg.rl.model_copy(update={"batch_size": cfg.samples_per_step})
     tm = TrainingMetrics()
     history: list[dict] = []
@@ -93,6 +100,8 @@ def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding
         if not sharded:
             allreduce_gradients(opt.grad, dp_group)   # fp32-parameter path: plain SUM all-reduce, full AdamW per rank
         grad_norm = opt.step()
+        tm.lr = float(opt.param_groups[0]["lr"])
+        lr_schedule.step()
         opt.zero_grad()
         if hasattr(model, "after_optimizer_step"):
             model.after_optimizer_step()

@@ -252,3 +252,30 @@ def test_schedule_rollouts_matches_reference_scheduler():
                                   "texts": [{"group_id": t.group_id, "metadata": dict(t.metadata), "text": t.text}
                                             for t in r.training_texts]} for r in rolls]})
     assert sorted(got, key=lambda d: d["group_id"]) == rec["groups"]
+
+
+@pytest.mark.parametrize("kind,warmup,total", [("cosine", 50, 1000), ("cosine", 0, 7), ("linear", 5, 40),
+                                               ("constant_with_warmup", 3, None), ("constant", 0, None)])
+def test_lr_schedule_matches_transformers_get_scheduler(kind, warmup, total):
+    """Row a7: the reference builds its schedule with transformers.get_scheduler (finetune_loop.py:394-399; cosine, 50
+    warm-up steps by default).  finetune.optim.get_scheduler must produce the same learning rate at every step."""
+    import torch
+    import transformers
+    from pipelinerl_b200.finetune.optim import get_scheduler
+
+    class Opt:
+        def __init__(self, lr):
+            self.param_groups = [{"lr": lr}, {"lr": lr * 0.5}]
+    mine_opt = Opt(1e-6)
+    mine = get_scheduler(kind, mine_opt, warmup, total)
+    p = torch.nn.Parameter(torch.zeros(1))
+    ref_opt = torch.optim.SGD([{"params": [p], "lr": 1e-6}, {"params": [torch.nn.Parameter(torch.zeros(1))], "lr": 5e-7}])
+    ref = transformers.get_scheduler(kind, ref_opt, num_warmup_steps=warmup, num_training_steps=total)
+    n = (total or 60) + 5
+    for step in range(n):
+        got = [g["lr"] for g in mine_opt.param_groups]
+        want = [g["lr"] for g in ref_opt.param_groups]
+        assert all(abs(a - b) <= 1e-12 * max(1.0, abs(b)) + 1e-18 for a, b in zip(got, want)), (step, got, want)
+        ref_opt.step()
+        ref.step()
+        mine.step()
