@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import asyncio
 import importlib
+import math
 import time
 from typing import Any, Callable, Iterable
 
@@ -26,10 +27,48 @@ def get_method(path: str | Callable) -> Callable:
     return getattr(importlib.import_module(module), name)
 
 
+class LagBudget:
+    """How many rollout GROUPS the actor may have submitted so far (the `max_lag` throttle of the training actor loop,
+    pipelinerl/actor.py:509-534 for the arithmetic, :551-577 for its use): initially `ceil(max_lag / attempts)` groups
+    of head start plus one update's worth, `ceil(total_update_size / attempts)` more every time a NEW weight version is
+    observed (once per observation, whatever the jump), where total_update_size is `weight_update_interval` rounded up
+    to whole optimizer batches (`train_batch_size * gradient_accumulation_passes`).  max_lag=None disables the throttle."""
+
+    def __init__(self, max_lag: int | None, attempts: int, train_batch_size: int, gradient_accumulation_passes: int,
+                 weight_update_interval: int, get_model_version: Callable[[], int]):
+        self.get_model_version = get_model_version
+        self.submitted = 0
+        self.last_version = get_model_version()
+        if max_lag is None:
+            self.groups_per_update, self.can_submit = None, math.inf
+            return
+        total_batch = train_batch_size * gradient_accumulation_passes
+        total_update = math.ceil(weight_update_interval / total_batch) * total_batch
+        self.groups_per_update = math.ceil(total_update / attempts)
+        self.lag_groups = math.ceil(max_lag / attempts)
+        self.can_submit = self.lag_groups + self.groups_per_update
+
+    def observe(self) -> None:
+        v = self.get_model_version()
+        if v > self.last_version:
+            if self.groups_per_update is not None:
+                self.can_submit += self.groups_per_update
+            self.last_version = v
+
+    def try_submit(self) -> bool:
+        """True (and counted) when one more group may be submitted now."""
+        self.observe()
+        if self.submitted >= self.can_submit:
+            return False
+        self.submitted += 1
+        return True
+
+
 async def schedule_rollouts(cfg: Any, attempts: int, problems: Iterable[dict], llms: list[TrainableLLM],
                             rollout_policy: str | Callable, on_group: Callable[[list[RolloutResult]], None],
                             get_model_version: Callable[[], int] = lambda: 0, max_rollouts_per_llm: int = 64,
-                            scheduler_name: str = "actor", max_retries: int = 3) -> dict:
+                            scheduler_name: str = "actor", max_retries: int = 3,
+                            lag_budget: "LagBudget | None" = None) -> dict:
     policy = get_method(rollout_policy)
     active = [0] * len(llms)
     groups: dict[int, list[RolloutResult]] = {}
@@ -66,6 +105,8 @@ async def schedule_rollouts(cfg: Any, attempts: int, problems: Iterable[dict], l
 
     gid = 0
     for problem in problems:
+        while lag_budget is not None and not lag_budget.try_submit():
+            await asyncio.sleep(0.01)        # throttled by max_lag: wait for the next weight version (actor.py:566)
         groups[gid] = []
         for r in range(attempts):
             while min(active) >= max_rollouts_per_llm:

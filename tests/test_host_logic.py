@@ -279,3 +279,45 @@ def test_lr_schedule_matches_transformers_get_scheduler(kind, warmup, total):
         ref_opt.step()
         ref.step()
         mine.step()
+
+
+def test_lag_budget_arithmetic_and_throttle():
+    """a3 lag budget (pipelinerl/actor.py:509-534, 551-577): max_lag 16 samples, 8 attempts, batches of 4 x 2 samples,
+    weight update every 8 samples -> 2 head-start groups + 1 group per update; one more group per OBSERVED new version."""
+    import asyncio
+    from pipelinerl_b200.actor import LagBudget, schedule_rollouts
+    from pipelinerl_b200.rollouts import BaseMetrics, RolloutResult, TrainingText
+    version = {"v": 0}
+    b = LagBudget(max_lag=16, attempts=8, train_batch_size=4, gradient_accumulation_passes=2, weight_update_interval=8,
+                  get_model_version=lambda: version["v"])
+    assert (b.lag_groups, b.groups_per_update, b.can_submit) == (2, 1, 3)
+    assert [b.try_submit() for _ in range(4)] == [True, True, True, False]
+    version["v"] = 5                      # a jump of several versions still adds ONE update's worth (actor.py:551-556)
+    assert [b.try_submit() for _ in range(2)] == [True, False]
+    # weight_update_interval is rounded up to whole optimizer batches: 9 samples -> 16 -> 2 groups of 8
+    b2 = LagBudget(8, 8, 4, 2, 9, lambda: 0)
+    assert (b2.lag_groups, b2.groups_per_update, b2.can_submit) == (1, 2, 3)
+    assert LagBudget(None, 8, 4, 2, 8, lambda: 0).try_submit()
+
+    # inside the scheduler: with a budget of 3 groups the 4th problem is only started after the version moved
+    version["v"] = 0
+    budget = LagBudget(16, 2, 1, 2, 2, lambda: version["v"])      # lag 8 groups?  ceil(16/2)=8 + 1
+    budget.can_submit = 3
+    started = []
+
+    async def policy(cfg, llm, problem, session):
+        started.append(problem["answer"])
+        await asyncio.sleep(0.01)
+        return RolloutResult(training_texts=[TrainingText(text="x", n_predicted=1)], latency=0.0,
+                             metrics=BaseMetrics(reward=0.0, success=False, no_error=True, no_answer=False))
+
+    async def go():
+        async def bump():
+            await asyncio.sleep(0.2)
+            assert sorted(set(started)) == [0, 1, 2]      # three groups ran, the fourth is being held back
+            version["v"] = 1
+        llm = type("L", (), {"name": "l"})()
+        await asyncio.gather(schedule_rollouts({}, 2, [{"answer": i} for i in range(4)], [llm], policy, lambda g: None,
+                                               get_model_version=lambda: version["v"], lag_budget=budget), bump())
+    asyncio.new_event_loop().run_until_complete(go())
+    assert sorted(set(started)) == [0, 1, 2, 3]
