@@ -258,7 +258,9 @@ def run_ours(args):
 
     if rank == 0 and not args.no_components:
         out["components"] = bench_components(dev, peak)
-        # hot path 2 end to end (rl_step -> backward -> fused AdamW) on the same model: needs the whole GPU
+    if rank == 0 and world == 1 and not args.no_components:
+        # hot path 2 end to end (rl_step -> backward -> fused AdamW) on the same model: needs the whole GPU.  Only in
+        # the single-GPU run: under torchrun the other ranks are already waiting in the final barrier
         import gc
         del eng, attn_all_layers
         gc.collect()
@@ -266,7 +268,9 @@ def run_ours(args):
         try:
             sys.path.insert(0, str(ROOT / "tools"))
             import train_bench
-            out["components"]["trainer_step"] = train_bench.measure(steps=2, warmup=1, dev=dev, log=False)
+            # distributed=False: under torchrun only rank 0 is here, so the trainer must not enter any collective
+            out["components"]["trainer_step"] = train_bench.measure(steps=2, warmup=1, dev=dev, log=False,
+                                                                    distributed=False)
         except Exception as e:  # noqa: BLE001  (informational component: the headline line must still print)
             out["components"]["trainer_step"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

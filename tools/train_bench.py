@@ -45,13 +45,16 @@ def synthetic_batch(cfg, T, n_samples, dev, seed):
 
 
 def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, warmup=1, layers=0, keep_attn=-1,
-            profile=False, dev=None, log=True, keep_gate_up=-1):
+            profile=False, dev=None, log=True, keep_gate_up=-1, distributed=None):
     """Run the trainer step and return the result dict (also used by bench.py's `components.trainer_step`).
     Under torchrun (WORLD_SIZE > 1) every rank is a data-parallel learner with its own `micro` micro-batches and the
-    optimizer step is the ShardedFusedAdamW exchange (P2P reduce-scatter + AdamW shard + P2P all-gather)."""
+    optimizer step is the ShardedFusedAdamW exchange (P2P reduce-scatter + AdamW shard + P2P all-gather);
+    `distributed=False` forces the single-learner path even when torchrun's environment variables are set."""
     import os
     import torch.distributed as dist
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if distributed is False:   # e.g. bench.py's rank 0 under torchrun: ONE learner on this GPU, no collective
+        world, rank = 1, 0
     if world > 1:
         dev = torch.device(f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}")
         if not dist.is_initialized():
