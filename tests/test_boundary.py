@@ -91,3 +91,15 @@ def test_argument_validation_needs_no_gpu(built_lib):
     for call, needle in cases:
         assert call() < 0
         assert needle in lib.prl_last_error(), (needle, lib.prl_last_error())
+
+
+def test_header_is_plain_c():
+    """include/prl.h is the drop-in boundary: it must compile as C99 (plain pointers and sizes, no C++/torch types)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    for std, lang in (("-std=c99", "c"), ("-std=c++17", "c++")):
+        r = subprocess.run(["gcc", std, "-fsyntax-only", "-Wall", "-x", lang, str(ROOT / "include" / "prl.h")],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
