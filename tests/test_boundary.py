@@ -103,3 +103,22 @@ def test_header_is_plain_c():
         r = subprocess.run(["gcc", std, "-fsyntax-only", "-Wall", "-x", lang, str(ROOT / "include" / "prl.h")],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_plain_c_client_links_and_calls(built_lib, tmp_path):
+    """tests/c_abi/client.c — a C program that knows only include/prl.h — links against libprl.so and runs."""
+    import os
+    import shutil
+    import subprocess
+    from pipelinerl_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    so = Path(_lib.lib_path())
+    exe = tmp_path / "client"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-I", str(ROOT / "include"), str(ROOT / "tests" / "c_abi" / "client.c"),
+                        "-L", str(so.parent), "-lprl", f"-Wl,-rpath,{so.parent}", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    env = dict(os.environ, LD_LIBRARY_PATH=f"{so.parent}:{os.environ.get('LD_LIBRARY_PATH', '')}")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, env=env, timeout=60)
+    assert r.returncode == 0 and r.stdout.startswith("ok version="), (r.returncode, r.stdout, r.stderr)
