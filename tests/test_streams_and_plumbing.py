@@ -226,3 +226,73 @@ def test_trainer_messages_are_what_the_reference_parses():
     for m in rec["messages"]:
         assert m["reference_class"] == m["ours"]
         assert mk[m["ours"]]().model_dump() == m["dump"] == m["reference_fields"]
+
+
+def test_config1_plumbing_end_to_end_on_cpu(tmp_path):
+    """BASELINE configs[0]-style plumbing run without a GPU: the guessing plugin on a scripted sampler -> scheduler with
+    groups of 4 -> `actor` topic on the file stream backend -> preprocess (RL columns, leave-one-out advantages) ->
+    packed micro-batches -> the ORACLE learner (oracle/learner_oracle + pg_oracle: the CPU stand-in for the CUDA hot
+    path) -> AdamW oracle.  Everything between the sampler and the loss is this package's host code."""
+    import asyncio
+    import numpy as np
+    import torch
+    from oracle import adamw_oracle, learner_oracle, pg_oracle
+    from pipelinerl_b200 import streams
+    from pipelinerl_b200.actor import publish_groups_to_stream, schedule_rollouts
+    from pipelinerl_b200.domains.guessing import generate_guessing_rollout, load_problems
+    from pipelinerl_b200.finetune.rl import RLConfig
+    from pipelinerl_b200.llm import TrainableLLM
+    from pipelinerl_b200.preprocess import pack_micro_batches, preprocess_dataset
+    from tests.helpers import ScriptedSampler, ScriptedTokenizer, tiny_cfg, tiny_weights
+
+    class Tok(ScriptedTokenizer):
+        eos_token_id = 2
+    streams.reset_streams_backend()
+    streams.set_streams_backend("files")
+    sampler = ScriptedSampler("cfg1", [512, 256, 128, None])     # three wrong guesses, then a malformed answer
+    try:
+        llm = TrainableLLM(base_url=sampler.base_url, model_name="scripted", tokenizer_name="scripted",
+                           parameters={"max_tokens": 8, "temperature": 1.0}, collect_logprobs=True)
+        llm.tokenizer = Tok()
+        writer, on_group = publish_groups_to_stream(tmp_path)
+        problems = load_problems(["train"])[:2]
+        stats = asyncio.new_event_loop().run_until_complete(
+            schedule_rollouts({}, 4, problems, [llm], generate_guessing_rollout, on_group, get_model_version=lambda: 3,
+                              scheduler_name="actor0"))
+        writer.__exit__(None, None, None)
+        assert stats["groups"] == 2 and stats["started"] == 8
+        with streams.read_stream(streams.SingleStreamSpec(exp_path=tmp_path, topic="actor")) as r:
+            groups = r.read_available()
+        assert len(groups) == 2 and all(g[0]["metadata"]["model_version"] == 3 for g in groups)
+        samples = [s for g in groups for s in g]
+        rcfg = RLConfig(policy_loss="ppo", kl_coef=0.0, final_kl_coef=0.0, batch_size=len(samples))
+        entries = preprocess_dataset(samples, Tok(), seq_length=4096, rl_config=rcfg)
+        assert len(entries) == len(samples) and all(len(e["advantages"]) == len(e["input_ids"]) for e in entries)
+        batches = pack_micro_batches(entries, Tok(), seq_length=1024)
+        assert batches and all(b.is_packed for b in batches)
+        # the oracle learner consumes the packed rows this package produced
+        cfg = tiny_cfg("gqa2")
+        w = {k: v.float() for k, v in tiny_weights(cfg).items()}
+        ocfg = pg_oracle.OracleRLConfig.from_dict(rcfg.model_dump())
+        total, grads = 0.0, None
+        for b in batches:
+            cols = {k: getattr(b, k)[0] for k in ("input_ids", "labels", "position_ids", "segment_ids", "rewards",
+                                                  "advantages", "ref_logprobs", "old_logprobs", "group_tokens",
+                                                  "num_labels", "overflow")}
+            cols["input_ids"] = cols["input_ids"] % cfg.vocab_size
+            cols["labels"] = torch.where(cols["labels"] >= 0, cols["input_ids"], cols["labels"])
+            loss, st, lp, g = learner_oracle.learner_step(cfg, w, cols, ocfg, 0, 10)
+            assert np.isfinite(loss) and all(torch.isfinite(v).all() for v in g.values())
+            total += loss
+            grads = g if grads is None else {k: grads[k] + v for k, v in g.items()}
+        names = sorted(grads)
+        p = [w[n].reshape(-1).numpy().copy() for n in names]
+        before = [x.copy() for x in p]
+        m, v = [np.zeros_like(x) for x in p], [np.zeros_like(x) for x in p]
+        norm = adamw_oracle.adamw_step(p, [grads[n].reshape(-1).numpy() for n in names], m, v, names, 1, 1e-3, 0.01,
+                                       max_grad_norm=0.3)
+        assert np.isfinite(norm) and norm > 0
+        assert any(np.abs(a - b).max() > 0 for a, b in zip(p, before))
+    finally:
+        sampler.close()
+        streams.reset_streams_backend()
