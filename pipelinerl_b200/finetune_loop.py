@@ -49,6 +49,37 @@ def allreduce_gradients(flat_grad: torch.Tensor, group=None) -> None:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
 
 
+def prefetch_batches(batches: Iterable, maxsize: int = 1, pin_memory: bool = False):
+    """The trainer's loader thread (pipelinerl/finetune_loop.py:494-505): a background thread pulls the next
+    micro-batch from the `training_data` stream (parsing / tensor construction / optional pinning happen there) while
+    the GPU works on the current one; `Queue(maxsize=1)` bounds the look-ahead exactly as the reference does.  An
+    exception raised by the source is re-raised in the consumer (the reference forwards it through the queue, :104,133).
+    Usage: `run_training(model, prefetch_batches(batches), cfg, ...)`."""
+    import queue
+    import threading
+    q: "queue.Queue" = queue.Queue(maxsize=maxsize)
+    done = object()
+
+    def work():
+        try:
+            for b in batches:
+                if pin_memory and hasattr(b, "pin_memory"):
+                    b = b.pin_memory()
+                q.put(b)
+            q.put(done)
+        except BaseException as e:  # noqa: BLE001  (forwarded to the consumer)
+            q.put(e)
+    t = threading.Thread(target=work, name="trainer-loader", daemon=True)
+    t.start()
+    while True:
+        item = q.get()
+        if item is done:
+            return
+        if isinstance(item, BaseException):
+            raise item
+        yield item
+
+
 def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding], cfg: TrainerConfig,
                  weight_manager: WeightUpdateManager | None = None, message_writer=None,
                  device: torch.device | str = "cuda:0", dp_group=None) -> tuple[TrainingMetrics, list[dict]]:

@@ -296,3 +296,30 @@ def test_config1_plumbing_end_to_end_on_cpu(tmp_path):
     finally:
         sampler.close()
         streams.reset_streams_backend()
+
+
+def test_prefetch_batches_bounds_lookahead_and_forwards_errors():
+    """Loader thread of the trainer (finetune_loop.py:494-505): at most `maxsize` finished batches wait in the queue (plus
+    the one the producer is blocked on), order is preserved, and a source exception reaches the consumer."""
+    import threading
+    import time
+    from pipelinerl_b200.finetune_loop import prefetch_batches
+    produced = []
+
+    def source(n, fail_at=None):
+        for i in range(n):
+            if i == fail_at:
+                raise RuntimeError("stream broke")
+            produced.append(i)
+            yield i
+    got = []
+    it = prefetch_batches(source(6), maxsize=1)
+    first = next(it)
+    time.sleep(0.2)                       # the loader may run ahead by the queue slot + the item it is blocked on
+    assert first == 0 and len(produced) <= 3
+    got = [first] + list(it)
+    assert got == list(range(6))
+    produced.clear()
+    with pytest.raises(RuntimeError, match="stream broke"):
+        list(prefetch_batches(source(5, fail_at=3)))
+    assert threading.active_count() < 50
