@@ -323,3 +323,30 @@ def test_prefetch_batches_bounds_lookahead_and_forwards_errors():
     with pytest.raises(RuntimeError, match="stream broke"):
         list(prefetch_batches(source(5, fail_at=3)))
     assert threading.active_count() < 50
+
+
+def test_trainer_state_listener_agrees_with_the_reference_listener(tmp_path):
+    """tests/golden/trainer_state_case.json: a `weight_update_request` topic written by this package's trainer-side code,
+    and the state the REFERENCE's TrainerState listener (pipelinerl/state.py:20-65) reached after tailing it
+    (make_golden_trainer_state.py).  This package's listener must reach the same state from the same file."""
+    import json
+    from pipelinerl_b200 import streams
+    from pipelinerl_b200.state import TrainerState
+    from tests.helpers import GOLDEN
+    rec = json.loads((GOLDEN / "trainer_state_case.json").read_text())
+    assert rec["topic_file"] == "streams/weight_update_request/0/0/0.jsonl"
+    f = tmp_path / rec["topic_file"]
+    f.parent.mkdir(parents=True)
+    f.write_text(rec["content"])
+    streams.reset_streams_backend()
+    streams.set_streams_backend("files")
+    try:
+        st = TrainerState(tmp_path)
+        st.start_listening()
+        assert st.wait_for_training_done(timeout=20)
+        got = {"propagated_weight_version": st.propagated_weight_version, "samples_processed": st.samples_processed,
+               "training_done": st.training_done}
+        assert got == rec["reference_state"]
+        st.stop()
+    finally:
+        streams.reset_streams_backend()
