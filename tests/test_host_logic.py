@@ -321,3 +321,28 @@ def test_lag_budget_arithmetic_and_throttle():
                                                get_model_version=lambda: version["v"], lag_budget=budget), bump())
     asyncio.new_event_loop().run_until_complete(go())
     assert sorted(set(started)) == [0, 1, 2, 3]
+
+
+def test_rollout_records_match_reference_classes():
+    """Row a2 record types: tests/golden/rollouts_cases.json was produced by the reference's own TrainingText /
+    RolloutResult / helpers (pipelinerl/rollouts.py:6-110, make_golden_rollouts.py).  Same inputs through
+    pipelinerl_b200.rollouts: identical dumps (field names, defaults), prompt/output text slicing incl. the n_predicted == 0
+    quirk, overflow rule, reward stamping, summary."""
+    import json
+    from pipelinerl_b200.rollouts import (BaseMetrics, RolloutResult, TrainingText, apply_rollout_reward,
+                                          rollout_has_overflow, summarize_training_texts)
+    from tests.helpers import GOLDEN
+    rec = json.loads((GOLDEN / "rollouts_cases.json").read_text())
+    texts = [TrainingText(**t) for t in rec["texts"]]
+    assert [t.model_dump() for t in texts] == rec["dumps"]
+    assert [t.prompt_text for t in texts] == rec["prompt_text"]
+    assert [t.output_text for t in texts] == rec["output_text"]
+    assert rollout_has_overflow(texts) == rec["has_overflow_all"]
+    assert rollout_has_overflow(texts[:1]) == rec["has_overflow_first"]
+    assert [t.reward for t in apply_rollout_reward([TrainingText(**t) for t in rec["texts"]], 1.25)] == rec["after_reward"]
+    s = summarize_training_texts(texts)
+    assert {"prompt_tokens": s.prompt_tokens, "output_tokens": s.output_tokens, "overflow": s.overflow,
+            "num_turns": s.num_turns} == rec["summary"]
+    rr = RolloutResult(training_texts=texts[:1], latency=0.5,
+                       metrics=BaseMetrics(reward=1.0, success=True, no_error=True, no_answer=False))
+    assert rr.model_dump() == rec["rollout_result_dump"]
