@@ -352,12 +352,36 @@ int prl_paged_attn_prefill_tc(const void* q_bf16 /*[q_rows,n_q,128]*/, int32_t q
                               const int32_t* seq_pos0, const int32_t* seq_slot, int32_t n_seqs, int32_t max_q_len,
                               int32_t n_q, int32_t n_kv, int32_t head_dim, int32_t page_size, float sm_scale,
                               void* out_bf16 /*[rows,n_q*128]*/, prl_stream_t stream);
+/* Learner attention (hot path 2): block-diagonal causal attention over ONE packed row and its backward -- the
+ * flash-attn varlen call the reference makes through HF with packed position_ids
+ * (pipelinerl/finetune/rl/__init__.py:204 forward, finetune_loop.py:716-725 backward; conf/finetune/base.yaml:12-13,64).
+ * qkv: [T, qkv_stride] bf16 rows = [n_q q heads | n_kv k heads | n_kv v heads] x 128, q / k already roped.
+ * Segment z = rows [seg_start[z], seg_start[z] + seg_len[z]); head_dim must be 128, n_q / n_kv <= 64.
+ * fwd: out [T, n_q*128] bf16, lse [T, n_q] fp32 (log2 domain of the scaled scores; NULL = not needed).
+ * bwd: dqkv [T, dqkv_stride] bf16 in the layout of qkv (every segment row is written); dK / dV are reduced over
+ * the GQA group inside the tensor core in a fixed order (deterministic, no atomics).
+ * csrc/attn_tc.cu (forward) and csrc/attn_train.cu (backward): tcgen05 MMAs, TMEM accumulators, TMA operands. */
+int prl_attn_varlen_fwd(const void* qkv_bf16, int64_t qkv_stride, int32_t T, const int32_t* seg_start,
+                        const int32_t* seg_len, int32_t n_seg, int32_t max_seg_len, int32_t n_q, int32_t n_kv,
+                        int32_t head_dim, float sm_scale, void* out_bf16, float* lse, prl_stream_t stream);
+size_t prl_attn_varlen_bwd_workspace_bytes(int32_t T, int32_t n_q);
+int prl_attn_varlen_bwd(const void* qkv_bf16, int64_t qkv_stride, int32_t T, const int32_t* seg_start,
+                        const int32_t* seg_len, int32_t n_seg, int32_t max_seg_len, int32_t n_q, int32_t n_kv,
+                        int32_t head_dim, float sm_scale, const void* out_bf16, const void* d_out_bf16,
+                        const float* lse, void* dqkv_bf16, int64_t dqkv_stride, void* workspace,
+                        size_t workspace_bytes, prl_stream_t stream);
 /* Sampling with in-kernel logprob capture: id ~ softmax(logits/T) (Gumbel-max, counter-based RNG on
  * (seed, step, row, vocab id)) or argmax when greedy; logprob = log_softmax(logits/T)[id]. */
 size_t prl_sample_workspace_bytes(int32_t B);
 int prl_sample_logprob(const float* logits /*[B,V]*/, int32_t B, int32_t V, float temperature, int32_t greedy,
                        uint64_t seed, uint32_t step, int32_t* out_ids, float* out_logprobs,
                        void* workspace, size_t workspace_bytes, prl_stream_t stream);
+/* Same with PER-SEQUENCE sampling parameters (inv_temperature_rows[b] = 1 / T_b, greedy_rows[b]): requests admitted with
+ * different `llm.parameters` (train handle at T = 1, eval handle greedy ...) share one engine batch, and every sequence's
+ * logprobs stay those of ITS OWN distribution (what rl_step assumes via RLConfig.temperature). */
+int prl_sample_logprob_rows(const float* logits /*[B,V]*/, int32_t B, int32_t V, const float* inv_temperature_rows,
+                            const uint8_t* greedy_rows, uint64_t seed, uint32_t step, int32_t* out_ids,
+                            float* out_logprobs, void* workspace, size_t workspace_bytes, prl_stream_t stream);
 /* Device-resident scheduler state of one sampler (all pointers device, one entry per slot).
  * prl_advance_state moves every active slot one token forward without a host round trip:
  * feeds the next prompt token while inside the prompt, else appends (sampled id, logprob) to the
@@ -381,7 +405,8 @@ typedef struct {
   const int32_t* max_new;          /* [B] */
   uint8_t* finished;               /* [B] 0 running, 1 stop, 2 length */
   int32_t eos_id;
-  int32_t ignore_eos;
+  int32_t ignore_eos;              /* engine-wide: never stop on eos */
+  const uint8_t* ignore_eos_rows;  /* [B] per sequence (may be NULL) */
 } prl_engine_state;
 int prl_advance_state(const prl_engine_state* state, prl_stream_t stream);
 

@@ -75,7 +75,7 @@ class EngineState(C.Structure):
         ("positions", C.c_void_p), ("seq_lens", C.c_void_p), ("active", C.c_void_p), ("prompt_buf", C.c_void_p),
         ("prompt_stride", C.c_int32), ("prompt_len", C.c_void_p), ("out_ids", C.c_void_p),
         ("out_logprobs", C.c_void_p), ("out_stride", C.c_int32), ("gen_count", C.c_void_p), ("max_new", C.c_void_p),
-        ("finished", C.c_void_p), ("eos_id", C.c_int32), ("ignore_eos", C.c_int32),
+        ("finished", C.c_void_p), ("eos_id", C.c_int32), ("ignore_eos", C.c_int32), ("ignore_eos_rows", C.c_void_p),
     ]
 
 
@@ -147,6 +147,12 @@ _SIGNATURES = {
                                             C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                             C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                             C.c_void_p, C.c_void_p]),
+    "prl_attn_varlen_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "prl_attn_varlen_bwd_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "prl_attn_varlen_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "prl_paged_attn_prefill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
@@ -162,6 +168,8 @@ _SIGNATURES = {
     "prl_sample_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "prl_sample_logprob": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_uint64,
                                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "prl_sample_logprob_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64,
+                                          C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "prl_advance_state": (C.c_int, [C.POINTER(EngineState), C.c_void_p]),
     "prl_gemm_bf16_splitk_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                             C.c_void_p, C.c_void_p, C.c_void_p]),

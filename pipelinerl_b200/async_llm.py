@@ -34,6 +34,21 @@ def _chat_kwargs(llm: TrainableLLM, prompt: Prompt) -> dict:
     return kw
 
 
+def _reject_unsupported_sampling(params: dict) -> None:
+    """Sampling features the engine does not implement must fail loudly, exactly as http_shim.py answers 400 for them:
+    a silently ignored top_p / top_k / stop would make the recorded logprobs those of a different distribution than the
+    one the request asked for.  (The reference trains with top_p = 1, top_k = -1, no stop strings: conf/base.yaml:46-51.)"""
+    if float(params.get("top_p", 1.0)) < 1.0 or int(params.get("top_k", -1)) > 0:
+        raise ValueError("top_p / top_k sampling is not implemented by this engine")
+    if params.get("stop") or params.get("stop_token_ids"):
+        raise ValueError("stop strings / stop token ids are not implemented by this engine (eos only)")
+    if int(params.get("n", 1)) != 1:
+        raise ValueError("n > 1 completions per request is not implemented (the actor issues `attempts` requests)")
+    for name in ("presence_penalty", "frequency_penalty", "repetition_penalty", "min_p"):
+        if params.get(name) not in (None, 0, 0.0, 1, 1.0) or (name == "repetition_penalty" and params.get(name) not in (None, 1, 1.0)):
+            raise ValueError(f"sampling parameter {name} is not implemented by this engine")
+
+
 async def llm_async_generate(llm: TrainableLLM, prompt: Prompt, session=None,
                              max_tokens_override: int | None = None) -> LLMCall:
     """One completion.  `session` (an aiohttp.ClientSession in the reference) is accepted and unused: the
@@ -43,10 +58,11 @@ async def llm_async_generate(llm: TrainableLLM, prompt: Prompt, session=None,
     prompt_ids = prompt.token_ids or _token_ids(tok.apply_chat_template(prompt.messages, add_generation_prompt=True,
                                                                         **_chat_kwargs(llm, prompt)))
     params = llm.parameters
+    _reject_unsupported_sampling(params)
     max_tokens = int(max_tokens_override if max_tokens_override is not None else params.get("max_tokens", 16))
     temperature = float(params.get("temperature", 1.0))
     sp = SamplingParams(max_tokens=max_tokens, temperature=temperature if temperature > 0 else 1.0,
-                        greedy=temperature <= 0)
+                        greedy=temperature <= 0, ignore_eos=bool(params.get("ignore_eos", False)))
     req = await resolve(llm.base_url).generate(list(prompt_ids), sp)
     content = tok.decode(req.output_ids)
     call = llm.log_output(prompt, LLMOutput(content=content), count_tokens=False)

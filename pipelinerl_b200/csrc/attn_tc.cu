@@ -39,6 +39,10 @@ struct TcPrefillParams {
   int64_t n_pages;
   int layer;
   float scale_log2;
+  // kContig (learner, packed row): K / V are columns of the same [T, qkv] matrix Q lives in -- no block table;
+  // sequence z covers rows [seq_q_start[z], seq_q_start[z] + seq_q_len[z]) and its keys are those same rows
+  int col_k, col_v;              // element column of K / V head 0
+  float* lse;                    // [rows, n_q] log2-domain log-sum-exp of the scaled scores (may be NULL)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -54,6 +58,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+template <bool kContig>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                        TcPrefillParams p) {
@@ -72,17 +77,20 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   // The two CTAs of a cluster own ADJACENT query tiles of the same (sequence, kv head): they walk the same K/V pages,
   // so each CTA fetches one of the two pages of a step and TMA-multicasts it into both CTAs' shared memory -- the
   // kernel is bound by L2 -> SM bandwidth (64 KB of K/V per 8.4 MFLOP step and CTA), and this halves it.
-  const int qtile = blockIdx.x, kvh = blockIdx.y, z = blockIdx.z;
+  // packed training rows are long and causal: walk the query tiles heaviest-first (adjacent tiles stay a cluster pair)
+  const int qtile = kContig ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int kvh = blockIdx.y, z = blockIdx.z;
   const uint32_t rank = ptx::cluster_ctarank();
   const int q_len = p.seq_q_len[z];
+  const int pos0 = kContig ? 0 : p.seq_pos0[z];
   if ((qtile & ~1) * p.nq >= q_len) return;              // uniform across the CLUSTER, before any barrier / TMEM use
   const int t0 = qtile * p.nq;
   const int row0 = p.seq_q_start[z] + t0;
-  const int pos_first = p.seq_pos0[z] + t0;
+  const int pos_first = pos0 + t0;
   const int n_valid = t0 >= q_len ? 0 : ((q_len - t0) < p.nq ? (q_len - t0) : p.nq);  // 0: partner-only CTA
   // both CTAs run the step count of the LATER tile (the earlier tile's extra step is fully masked)
   const int pair_rows = ((qtile | 1) + 1) * p.nq;
-  const int kv_end = p.seq_pos0[z] + (pair_rows < q_len ? pair_rows : q_len);
+  const int kv_end = pos0 + (pair_rows < q_len ? pair_rows : q_len);
   const int n_it = (kv_end + kKeys - 1) / kKeys;
   const int last_page = (kv_end - 1) / kPageT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -110,7 +118,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       ptx::mbar_arrive_expect_tx(bar(0), (uint32_t)(2 * 128 * p.R * p.nq));
       ptx::tma_load_3d(q_smem, &tm_q, 0, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
       ptx::tma_load_3d(q_smem + kTile16K, &tm_q, 64, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
-      const int32_t* bt = p.block_table + (int64_t)p.seq_slot[z] * p.max_blocks;
+      const int32_t* bt = kContig ? nullptr : p.block_table + (int64_t)p.seq_slot[z] * p.max_blocks;
+      const int seq_row0 = p.seq_q_start[z];
       // this CTA fetches ONE of the two pages of a step (rank 0: keys 0..63, rank 1: keys 64..127) and multicasts it
       auto load_page = [&](int it, int kv, uint32_t full_bar, uint32_t empty_bar) {
         const int s = it & 1;
@@ -119,11 +128,18 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         ptx::mbar_arrive_expect_tx(full_bar + 8u * (uint32_t)s, (uint32_t)(2 * kTile16K));
         int pg = 2 * it + (int)rank;
         if (pg > last_page) pg = last_page;              // the tail step re-reads the last page; its keys are masked
-        const int page = bt[pg];
-        const int row = (int)(((((int64_t)p.layer * 2 + kv) * p.n_pages + page) * p.n_kv + kvh) * kPageT);
+        int row, c0;
+        if (kContig) {                                   // rows past the sequence / past T: masked keys (TMA zero-fills OOB)
+          row = seq_row0 + pg * kPageT;
+          c0 = (kv ? p.col_v : p.col_k) + kvh * kDT;
+        } else {
+          const int page = bt[pg];
+          row = (int)(((((int64_t)p.layer * 2 + kv) * p.n_pages + page) * p.n_kv + kvh) * kPageT);
+          c0 = 0;
+        }
         const uint32_t dst = kv_smem + (uint32_t)(s * kStageBytesT + kv * 2 * kTile16K) + (uint32_t)(rank * 8192);
-        ptx::tma_load_2d_multicast(dst, &tm_kv, 0, row, full_bar + 8u * (uint32_t)s, 3, ptx::kEvictLast);
-        ptx::tma_load_2d_multicast(dst + kTile16K, &tm_kv, 64, row, full_bar + 8u * (uint32_t)s, 3, ptx::kEvictLast);
+        ptx::tma_load_2d_multicast(dst, &tm_kv, c0, row, full_bar + 8u * (uint32_t)s, 3, ptx::kEvictLast);
+        ptx::tma_load_2d_multicast(dst + kTile16K, &tm_kv, c0 + 64, row, full_bar + 8u * (uint32_t)s, 3, ptx::kEvictLast);
       };
       load_page(0, 0, bar(1), bar(3));
       for (int it = 0; it < n_it; ++it) {                // same order as the MMA warp consumes: K(it+1), then V(it)
@@ -271,6 +287,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const float l_tot = l_run + xchg[(1 - h) * 128 + m];
     if (qi < n_valid && qi < p.nq) {
       const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+      if (kContig && p.lse != nullptr && h == 0)          // P = exp2(s * scale_log2 - lse) in the backward
+        p.lse[(int64_t)(row0 + qi) * p.n_q + (kvh * p.R + r)] = m_run + log2f(l_tot);
       __nv_bfloat16* dst = p.out + ((int64_t)(row0 + qi) * p.n_q + (kvh * p.R + r)) * kDT + h * 64;
 #pragma unroll
       for (int d = 0; d < 64; d += 8) {
@@ -317,6 +335,7 @@ extern "C" int prl_paged_attn_prefill_tc(const void* q, int32_t q_rows, const vo
   p.seq_slot = seq_slot; p.max_blocks = max_blocks; p.n_q = n_q; p.n_kv = n_kv; p.R = n_q / n_kv;
   p.nq = 128 / p.R;
   p.n_pages = n_pages; p.layer = layer; p.scale_log2 = sm_scale * 1.4426950408889634f;
+  p.col_k = p.col_v = 0; p.lse = nullptr;
   CUtensorMap tq, tkv;
   int rc = make_tmap_2d_bf16(&tkv, kv_cache, kDT, (uint64_t)total_rows, kDT * 2, 64, kPageT);
   if (rc) return rc;
@@ -325,9 +344,45 @@ extern "C" int prl_paged_attn_prefill_tc(const void* q, int32_t q_rows, const vo
   if (rc) return rc;
   const int smem = 2 * kTile16K + 2 * kStageBytesT + 4 * kTile16K + 1024 + 8 * 20 + 2 * 128 * 4 + 16;
   static SmemAttr smem_attr = {};
-  PRL_CUDA(ensure_smem(attn_prefill_tc_kernel, smem, smem_attr));
+  PRL_CUDA(ensure_smem(attn_prefill_tc_kernel<false>, smem, smem_attr));
   dim3 grid((unsigned)(((max_q_len + p.nq - 1) / p.nq + 1) & ~1), (unsigned)n_kv, (unsigned)n_seqs);  // pairs of q tiles
-  attn_prefill_tc_kernel<<<grid, kThreadsT, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
+  attn_prefill_tc_kernel<false><<<grid, kThreadsT, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
+
+// Learner forward (hot path 2): block-diagonal causal attention over ONE packed row, the varlen flash-attention call
+// the reference makes through HF (pipelinerl/finetune/rl/__init__.py:204 with packed position_ids,
+// conf/finetune/base.yaml:12-13,64).  qkv: [T, qkv_stride] bf16 = [q heads | k heads | v heads], q / k already roped.
+// Same kernel as chunked prefill, K / V tiles streamed from the packed matrix instead of KV pages; also writes the
+// log-sum-exp the backward needs.
+extern "C" int prl_attn_varlen_fwd(const void* qkv, int64_t qkv_stride, int32_t T, const int32_t* seg_start,
+                                   const int32_t* seg_len, int32_t n_seg, int32_t max_seg_len, int32_t n_q,
+                                   int32_t n_kv, int32_t head_dim, float sm_scale, void* out_bf16, float* lse,
+                                   prl_stream_t stream_) {
+  PRL_CHECK_ARG(qkv && seg_start && seg_len && out_bf16, "prl_attn_varlen_fwd: NULL argument");
+  PRL_CHECK_ARG(head_dim == kDT, "prl_attn_varlen_fwd: head_dim must be 128");
+  PRL_CHECK_ARG(T >= 1 && n_seg >= 1 && max_seg_len >= 1 && n_kv >= 1 && n_q % n_kv == 0 && n_q / n_kv <= 64,
+                "prl_attn_varlen_fwd: bad shape");
+  PRL_CHECK_ARG(qkv_stride >= (int64_t)(n_q + 2 * n_kv) * kDT && qkv_stride % 8 == 0, "prl_attn_varlen_fwd: bad row stride");
+  TcPrefillParams p;
+  p.out = (__nv_bfloat16*)out_bf16;
+  p.block_table = nullptr; p.seq_q_start = seg_start; p.seq_q_len = seg_len; p.seq_pos0 = nullptr; p.seq_slot = nullptr;
+  p.max_blocks = 0; p.n_q = n_q; p.n_kv = n_kv; p.R = n_q / n_kv; p.nq = 128 / p.R;
+  p.n_pages = 0; p.layer = 0; p.scale_log2 = sm_scale * 1.4426950408889634f;
+  p.col_k = n_q * kDT; p.col_v = (n_q + n_kv) * kDT; p.lse = lse;
+  CUtensorMap tq, tkv;
+  int rc = make_tmap_2d_bf16(&tkv, qkv, (uint64_t)(n_q + 2 * n_kv) * kDT, (uint64_t)T, (uint64_t)qkv_stride * 2, 64, kPageT);
+  if (rc) return rc;
+  rc = make_tmap_3d_bf16(&tq, qkv, kDT, (uint64_t)n_q, (uint64_t)T, kDT * 2, (uint64_t)qkv_stride * 2, 64, (uint32_t)p.R,
+                         (uint32_t)p.nq);
+  if (rc) return rc;
+  const int smem = 2 * kTile16K + 2 * kStageBytesT + 4 * kTile16K + 1024 + 8 * 20 + 2 * 128 * 4 + 16;
+  static SmemAttr smem_attr = {};
+  PRL_CUDA(ensure_smem(attn_prefill_tc_kernel<true>, smem, smem_attr));
+  dim3 grid((unsigned)(((max_seg_len + p.nq - 1) / p.nq + 1) & ~1), (unsigned)n_kv, (unsigned)n_seg);
+  attn_prefill_tc_kernel<true><<<grid, kThreadsT, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }

@@ -1,0 +1,644 @@
+// tcgen05 backward of the learner's block-diagonal causal attention over one packed row (hot path 2: what the
+// reference gets from flash-attn varlen through HF, pipelinerl/finetune/rl/__init__.py:204 + backward
+// finetune_loop.py:716-725; conf/finetune/base.yaml:12-13,64).  Forward: attn_tc.cu (prl_attn_varlen_fwd).
+//
+// Rows of every UMMA tile pack the R query heads of one GQA group: row = token * R + head.  With that packing the
+// contraction over query rows in dK = dS^T Q and dV = P^T dO sums over the R heads of the group inside the tensor core,
+// in a fixed order -- no atomics, no cross-head reduction pass, bitwise reproducible.
+//
+//     P  = exp2(S * scale_log2 - lse)         S = Q K^T        (lse saved by the forward, log2 domain)
+//     dP = dO V^T                              delta = rowsum(dO o O)
+//     dS = P o (dP - delta)
+//     dV = P^T dO        dK = scale * dS^T Q        dQ = scale * dS K
+//
+// Two kernels, each deterministic and each keeping every accumulator in TMEM:
+//   * attn_bwd_dkdv_kernel  (K/V stationary): one CTA per (128-key tile, kv head, sequence); streams 64-row query
+//     sub-tiles (Q, dO) through a 3-slot TMA ring.  It works on the TRANSPOSED scores, S^T = K Q^T and dP^T = V dO^T
+//     (UMMA 128 x 64, all operands K-major), so a softmax thread owns a KEY and writes P^T / dS^T rows straight into
+//     the K-major shared-memory layout that  dV += P^T dO  and  dK += dS^T Q  consume as operand A, while dO / Q are
+//     read AS STORED as MN-major operand B.  TMEM: S^T, dP^T double-buffered (4 x 64 columns) + dV + dK (2 x 128).
+//   * attn_bwd_dq_kernel    (Q stationary): the forward's structure (cluster pair of adjacent query tiles, K/V pages
+//     TMA-multicast to both CTAs, 128 keys per step) with  dP = dO V^T  as a third MMA and  dQ += dS K  in place of
+//     P V (K read as stored, MN-major).  TMEM: S double-buffered + dP + dQ.
+// Both: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = softmax (two warps per TMEM lane quarter).
+//
+// Tensor-bound.  Per (128 query rows x 128 keys) pair: 4 + 3 UMMAs of 4.2 MFLOP against 5 for the atomics-based
+// single-kernel formulation; 2 x 16 K exp2.
+#include "prl_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace prl {
+namespace {
+
+constexpr int kD = 128;
+constexpr int kT16 = 16384;   // [128 rows x 128 B] operand tile
+constexpr int kT8 = 8192;     // [64 rows x 128 B]
+constexpr int kThreadsB = 320;
+
+struct BwdParams {
+  const float* lse;              // [T, n_q]
+  const float* delta;            // [T, n_q]
+  __nv_bfloat16* dqkv;           // [T, dqkv_stride]: dQ | dK | dV in the layout of qkv
+  int64_t dqkv_stride;
+  const int32_t* seg_start;
+  const int32_t* seg_len;
+  int n_q, n_kv, R;
+  int nq;                        // query tokens per tile: 128 / R (dq kernel) or 64 / R (dkdv kernel)
+  int col_k, col_v;              // element column of K / V head 0 inside a qkv row
+  float scale_log2, sm_scale;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pk2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// =====================================================================================================
+// delta[t, h] = sum_d dO[t, h, d] * O[t, h, d]      one warp per (token, head)
+// =====================================================================================================
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                                  int64_t n_rows /* T * n_q */, float* __restrict__ delta) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const uint2 a = ld_stream_u2(reinterpret_cast<const uint2*>(o + row * kD) + lane);
+  const uint2 b = ld_stream_u2(reinterpret_cast<const uint2*>(d_o + row * kD) + lane);
+  float s = bf16_bits_to_float(a.x & 0xFFFFu) * bf16_bits_to_float(b.x & 0xFFFFu);
+  s = fmaf(bf16_bits_to_float(a.x >> 16), bf16_bits_to_float(b.x >> 16), s);
+  s = fmaf(bf16_bits_to_float(a.y & 0xFFFFu), bf16_bits_to_float(b.y & 0xFFFFu), s);
+  s = fmaf(bf16_bits_to_float(a.y >> 16), bf16_bits_to_float(b.y >> 16), s);
+  s = warp_sum(s);
+  if (lane == 0) delta[row] = s;
+}
+
+// =====================================================================================================
+// dK, dV: K/V-stationary
+// =====================================================================================================
+constexpr int kQStages = 3;
+constexpr int kQSlot = 4 * kT8;    // Q lo | Q hi | dO lo | dO hi   (64 query rows each)
+constexpr int kPdsSlot = 2 * kT16; // P^T | dS^T   ([128 keys x 64 query rows] each)
+constexpr int kKvBytes = 4 * kT16; // K lo | K hi | V lo | V hi
+constexpr int kMetaBytes = 2 * 3 * 64 * 4;   // [2 buffers][lse | delta | qpos][64 columns]
+constexpr int kSmemDkdv = 1024 + kKvBytes + kQStages * kQSlot + 2 * kPdsSlot + kMetaBytes + 8 * 18 + 16;
+static_assert(kSmemDkdv <= 232448, "dkdv kernel exceeds the 227 KB shared-memory limit");
+
+__global__ void __launch_bounds__(kThreadsB, 1)
+attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                     const __grid_constant__ CUtensorMap tm_kv, BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t kv_smem = base;                                   // K lo | K hi | V lo | V hi
+  const uint32_t q_ring = base + kKvBytes;
+  const uint32_t pds_smem = q_ring + kQStages * kQSlot;
+  const uint32_t meta_smem = pds_smem + 2 * kPdsSlot;
+  const uint32_t bar_base = meta_smem + kMetaBytes;
+  auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
+  // 0 kv_full | 1..3 q_full | 4..6 q_empty | 7,8 sdp_full | 9,10 sdp_empty | 11,12 pds_full | 13,14 pds_empty | 15 acc_done
+  const uint32_t tmem_slot = bar(16);
+  float* meta = reinterpret_cast<float*>(smem_raw + (meta_smem - ptx::smem_u32(smem_raw)));
+
+  const int jt = blockIdx.x, kvh = blockIdx.y, z = blockIdx.z;
+  const int q_len = p.seg_len[z];
+  const int key0 = jt * 128;
+  if (key0 >= q_len) return;                       // before any barrier / TMEM use
+  const int seg0 = p.seg_start[z];
+  const int nqa = p.nq;
+  const int u_first = key0 / nqa;                  // first 64-row query sub-tile holding a token >= key0
+  const int u_end = (q_len + nqa - 1) / nqa;
+  const int n_it = u_end - u_first;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // query rows R * nqa .. 63 of a sub-tile are never written by TMA: they must read as zeros (they are contracted over)
+  {
+    const uint32_t n16 = (uint32_t)(kQStages * kQSlot) / 16;
+    for (uint32_t i = threadIdx.x; i < n16; i += kThreadsB) sts_v4(q_ring + i * 16, 0u, 0u, 0u, 0u);
+    ptx::fence_proxy_async();
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 16; ++i) ptx::mbar_init(bar(i), 1);
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+    ptx::prefetch_tensormap(&tm_q);
+    ptx::prefetch_tensormap(&tm_do);
+    ptx::prefetch_tensormap(&tm_kv);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(bar(0), (uint32_t)kKvBytes);
+      const int krow = seg0 + key0;
+#pragma unroll
+      for (int kv = 0; kv < 2; ++kv) {
+        const int c0 = (kv ? p.col_v : p.col_k) + kvh * kD;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {       // d 0..63 | d 64..127
+          const uint32_t dst = kv_smem + (uint32_t)((kv * 2 + half) * kT16);
+          ptx::tma_load_2d(dst, &tm_kv, c0 + 64 * half, krow, bar(0), ptx::kEvictFirst);
+          ptx::tma_load_2d(dst + kT8, &tm_kv, c0 + 64 * half, krow + 64, bar(0), ptx::kEvictFirst);
+        }
+      }
+      const uint32_t q_bytes = (uint32_t)(4 * 128 * p.R * nqa);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it % kQStages;
+        const uint32_t ph = (uint32_t)((it / kQStages) & 1);
+        ptx::mbar_wait(bar(4 + st), ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(bar(1 + st), q_bytes);
+        const int row = seg0 + (u_first + it) * nqa;
+        const uint32_t dst = q_ring + (uint32_t)(st * kQSlot);
+        ptx::tma_load_3d(dst, &tm_q, 0, kvh * p.R, row, bar(1 + st), ptx::kEvictLast);
+        ptx::tma_load_3d(dst + kT8, &tm_q, 64, kvh * p.R, row, bar(1 + st), ptx::kEvictLast);
+        ptx::tma_load_3d(dst + 2 * kT8, &tm_do, 0, kvh * p.R, row, bar(1 + st), ptx::kEvictLast);
+        ptx::tma_load_3d(dst + 3 * kT8, &tm_do, 64, kvh * p.R, row, bar(1 + st), ptx::kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc_t = ptx::make_idesc_bf16_f32(128, 64);                 // S^T, dP^T: both operands K-major
+      constexpr uint32_t idesc_acc = ptx::make_idesc_bf16_f32(128, kD) | (1u << 16);  // dV, dK: B (dO / Q) MN-major
+      auto issue_sdp = [&](int it) {
+        const int st = it % kQStages, s = it & 1;
+        ptx::mbar_wait(bar(1 + st), (uint32_t)((it / kQStages) & 1));   // Q, dO of this sub-tile landed
+        ptx::mbar_wait(bar(9 + s), (uint32_t)(((it >> 1) & 1) ^ 1));    // S^T[s], dP^T[s] read by the softmax warps
+        ptx::tc_fence_after_sync();
+        const uint32_t q_addr = q_ring + (uint32_t)(st * kQSlot);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t a = ptx::make_kmajor_sw128_desc(kv_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+          const uint64_t b = ptx::make_kmajor_sw128_desc(q_addr + (uint32_t)((ks >> 2) * kT8)) + (uint64_t)(2 * (ks & 3));
+          ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 64), a, b, idesc_t, ks > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t a = ptx::make_kmajor_sw128_desc(kv_smem + (uint32_t)(2 * kT16 + (ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+          const uint64_t b = ptx::make_kmajor_sw128_desc(q_addr + (uint32_t)(2 * kT8 + (ks >> 2) * kT8)) + (uint64_t)(2 * (ks & 3));
+          ptx::mma_bf16_ss(tmem_base + (uint32_t)(128 + s * 64), a, b, idesc_t, ks > 0 ? 1u : 0u);
+        }
+        ptx::tc_commit(bar(7 + s));
+      };
+      ptx::mbar_wait(bar(0), 0);
+      issue_sdp(0);
+      for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) issue_sdp(it + 1);
+        const int st = it % kQStages, s = it & 1;
+        ptx::mbar_wait(bar(11 + s), (uint32_t)((it >> 1) & 1));         // P^T[s], dS^T[s] are in shared memory
+        ptx::tc_fence_after_sync();
+        const uint32_t q_addr = q_ring + (uint32_t)(st * kQSlot);
+        const uint32_t pt_addr = pds_smem + (uint32_t)(s * kPdsSlot);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {     // dV += P^T dO      (contraction over the 64 query rows)
+          const uint64_t a = ptx::make_kmajor_sw128_desc(pt_addr) + (uint64_t)(2 * ks);
+          const uint64_t b = ptx::make_mnmajor_sw128_desc(q_addr + 2 * kT8, kT8) + (uint64_t)(128 * ks);
+          ptx::mma_bf16_ss(tmem_base + 256u, a, b, idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {     // dK += dS^T Q
+          const uint64_t a = ptx::make_kmajor_sw128_desc(pt_addr + kT16) + (uint64_t)(2 * ks);
+          const uint64_t b = ptx::make_mnmajor_sw128_desc(q_addr, kT8) + (uint64_t)(128 * ks);
+          ptx::mma_bf16_ss(tmem_base + 384u, a, b, idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        ptx::tc_commit(bar(13 + s));     // P^T[s] / dS^T[s] may be rewritten
+        ptx::tc_commit(bar(4 + st));     // Q / dO slot may be refilled
+      }
+      ptx::tc_commit(bar(15));
+    }
+    __syncwarp();
+  } else {
+    // ===== softmax warps: a thread owns one KEY (TMEM lane) and half of the 64 query-row columns =====
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const int m = q * 32 + lane;                 // key row inside the tile
+    const int kpos = key0 + m;
+    const int ts = threadIdx.x - 64;             // 0..255
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int c0 = h * 32;
+    // per-column metadata of a sub-tile, staged one step ahead: lse (+inf on padding columns -> P = 0), delta, token
+    const int mc = ts & 63, mwhich = ts >> 6;    // 0 lse | 1 delta | 2 query position | 3 idle
+    const int mqi = mc / p.R, mr = mc - mqi * p.R;
+    auto fetch = [&](int u) -> float {
+      const int tok = u * nqa + mqi;
+      const bool valid = (mqi < nqa) && (tok < q_len);
+      if (mwhich == 2) return __int_as_float(valid ? tok : -1);
+      if (mwhich == 3) return 0.f;
+      if (!valid) return mwhich == 0 ? INFINITY : 0.f;
+      const float* src = mwhich == 0 ? p.lse : p.delta;
+      return __ldg(src + (int64_t)(seg0 + tok) * p.n_q + (kvh * p.R + mr));
+    };
+    if (mwhich < 3) meta[mwhich * 64 + mc] = fetch(u_first);
+
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1;
+      const int u = u_first + it;
+      float nxt = 0.f;
+      if (it + 1 < n_it) nxt = fetch(u + 1);     // global load in flight across the whole step
+      ptx::mbar_wait(bar(7 + s), (uint32_t)((it >> 1) & 1));
+      ptx::tc_fence_after_sync();
+      uint32_t sv[32], dv[32];
+      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(s * 64 + c0), sv);
+      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(128 + s * 64 + c0), dv);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before_sync();
+      softmax_bar();                                           // every thread holds its S^T / dP^T values
+      if (threadIdx.x == 64) ptx::mbar_arrive(bar(9 + s));    // -> S^T[s], dP^T[s] of step it + 2 may be issued
+      const float* mb = meta + (it & 1) * 192;
+      const bool diag = u * nqa < key0 + 127;                  // some (key, query) of this step is causally masked
+      ptx::mbar_wait(bar(13 + s), (uint32_t)(((it >> 1) & 1) ^ 1));   // dV / dK of step it - 2 consumed P^T[s], dS^T[s]
+      const uint32_t prow = pds_smem + (uint32_t)(s * kPdsSlot + m * 128);
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const float4 l0 = *reinterpret_cast<const float4*>(mb + c0 + j);
+        const float4 l1 = *reinterpret_cast<const float4*>(mb + c0 + j + 4);
+        const float4 d0 = *reinterpret_cast<const float4*>(mb + 64 + c0 + j);
+        const float4 d1 = *reinterpret_cast<const float4*>(mb + 64 + c0 + j + 4);
+        const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        float pe[8], de[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pe[e] = ex2f(fmaf(__uint_as_float(sv[j + e]), p.scale_log2, -ls[e]));
+        if (diag) {
+          const int4 q0 = *reinterpret_cast<const int4*>(mb + 128 + c0 + j);
+          const int4 q1 = *reinterpret_cast<const int4*>(mb + 128 + c0 + j + 4);
+          const int qp[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (kpos > qp[e]) pe[e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) de[e] = pe[e] * (__uint_as_float(dv[j + e]) - dl[e]);
+        const uint32_t off = (((uint32_t)((c0 + j) >> 3) ^ (uint32_t)(m & 7)) << 4);
+        sts_v4(prow + off, pk2(pe[0], pe[1]), pk2(pe[2], pe[3]), pk2(pe[4], pe[5]), pk2(pe[6], pe[7]));
+        sts_v4(prow + kT16 + off, pk2(de[0], de[1]), pk2(de[2], de[3]), pk2(de[4], de[5]), pk2(de[6], de[7]));
+      }
+      if (it + 1 < n_it && mwhich < 3) meta[((it + 1) & 1) * 192 + mwhich * 64 + mc] = nxt;
+      ptx::fence_proxy_async();                                // generic-proxy stores -> visible to the UMMA reads
+      softmax_bar();
+      if (threadIdx.x == 64) ptx::mbar_arrive(bar(11 + s));   // P^T[s], dS^T[s] ready
+    }
+
+    // ---- epilogue: dV, dK rows of this key ----
+    ptx::mbar_wait(bar(15), 0);
+    ptx::tc_fence_after_sync();
+    const bool valid = kpos < q_len;
+    __nv_bfloat16* drow = p.dqkv + (int64_t)(seg0 + kpos) * p.dqkv_stride + kvh * kD + h * 64;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {     // 0: dV (TMEM 256..383), 1: dK (384..511)
+      uint32_t v0[32], v1[32];
+      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(256 + which * 128 + h * 64), v0);
+      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(256 + which * 128 + h * 64 + 32), v1);
+      ptx::tmem_ld_wait();
+      const float sc = which ? p.sm_scale : 1.f;
+      if (valid) {
+        __nv_bfloat16* dst = drow + (which ? p.col_k : p.col_v);
+#pragma unroll
+        for (int d = 0; d < 32; d += 8) {
+          uint4 a, b;
+          a.x = pk2(__uint_as_float(v0[d]) * sc, __uint_as_float(v0[d + 1]) * sc);
+          a.y = pk2(__uint_as_float(v0[d + 2]) * sc, __uint_as_float(v0[d + 3]) * sc);
+          a.z = pk2(__uint_as_float(v0[d + 4]) * sc, __uint_as_float(v0[d + 5]) * sc);
+          a.w = pk2(__uint_as_float(v0[d + 6]) * sc, __uint_as_float(v0[d + 7]) * sc);
+          b.x = pk2(__uint_as_float(v1[d]) * sc, __uint_as_float(v1[d + 1]) * sc);
+          b.y = pk2(__uint_as_float(v1[d + 2]) * sc, __uint_as_float(v1[d + 3]) * sc);
+          b.z = pk2(__uint_as_float(v1[d + 4]) * sc, __uint_as_float(v1[d + 5]) * sc);
+          b.w = pk2(__uint_as_float(v1[d + 6]) * sc, __uint_as_float(v1[d + 7]) * sc);
+          *reinterpret_cast<uint4*>(dst + d) = a;
+          *reinterpret_cast<uint4*>(dst + 32 + d) = b;
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =====================================================================================================
+// dQ: Q-stationary (cluster pair of adjacent query tiles, K/V pages multicast)
+// =====================================================================================================
+constexpr int kStageKV = 4 * kT16;   // K lo | K hi | V lo | V hi   (128 keys)
+constexpr int kSmemDq = 1024 + 4 * kT16 + 2 * kStageKV + 2 * kT16 + 8 * 20 + 16;
+static_assert(kSmemDq <= 232448, "dq kernel exceeds the 227 KB shared-memory limit");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsB, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_kv, BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = base;                         // Q lo | Q hi
+  const uint32_t do_smem = base + 2 * kT16;             // dO lo | dO hi
+  const uint32_t kv_smem = base + 4 * kT16;             // 2 stages x (K lo | K hi | V lo | V hi)
+  const uint32_t ds_smem = kv_smem + 2 * kStageKV;      // dS keys 0..63 | keys 64..127
+  const uint32_t bar_base = ds_smem + 2 * kT16;
+  auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
+  // 0 q_full | 1,2 k_full | 3,4 k_empty | 5,6 s_full | 7,8 s_empty | 9 dp_full | 10 dp_empty | 11 ds_full | 12 ds_empty |
+  // 13,14 v_full | 15,16 v_empty | 17 dq_done
+  const uint32_t tmem_slot = bar(18);
+
+  const int qtile = (int)(gridDim.x - 1 - blockIdx.x);  // heaviest (latest) query tiles first; pairs stay adjacent
+  const int kvh = blockIdx.y, z = blockIdx.z;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int q_len = p.seg_len[z];
+  if ((qtile & ~1) * p.nq >= q_len) return;             // uniform across the cluster
+  const int seg0 = p.seg_start[z];
+  const int t0 = qtile * p.nq;
+  const int row0 = seg0 + t0;
+  const int n_valid = t0 >= q_len ? 0 : ((q_len - t0) < p.nq ? (q_len - t0) : p.nq);
+  const int pair_rows = ((qtile | 1) + 1) * p.nq;
+  const int kv_end = pair_rows < q_len ? pair_rows : q_len;
+  const int n_it = (kv_end + 127) / 128;
+  const int last_page = (kv_end - 1) / 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 18; ++i) ptx::mbar_init(bar(i), (i == 3 || i == 4 || i == 15 || i == 16) ? 2 : 1);
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+    ptx::prefetch_tensormap(&tm_q);
+    ptx::prefetch_tensormap(&tm_do);
+    ptx::prefetch_tensormap(&tm_kv);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync();
+  ptx::tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(bar(0), (uint32_t)(4 * 128 * p.R * p.nq));
+      ptx::tma_load_3d(q_smem, &tm_q, 0, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
+      ptx::tma_load_3d(q_smem + kT16, &tm_q, 64, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
+      ptx::tma_load_3d(do_smem, &tm_do, 0, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
+      ptx::tma_load_3d(do_smem + kT16, &tm_do, 64, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
+      // this CTA fetches ONE of the two 64-key pages of a step and multicasts it to both CTAs of the pair
+      auto load_page = [&](int it, int kv) {
+        const int s = it & 1;
+        const uint32_t ph = (uint32_t)((it >> 1) & 1);
+        const uint32_t full = bar((kv ? 13 : 1) + s), empty = bar((kv ? 15 : 3) + s);
+        ptx::mbar_wait(empty, ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(full, (uint32_t)(2 * kT16));
+        int pg = 2 * it + (int)rank;
+        if (pg > last_page) pg = last_page;            // tail: re-read the last page, its keys are causally masked
+        const int row = seg0 + pg * 64;
+        const int c0 = (kv ? p.col_v : p.col_k) + kvh * kD;
+        const uint32_t dst = kv_smem + (uint32_t)(s * kStageKV + kv * 2 * kT16) + (uint32_t)(rank * kT8);
+        ptx::tma_load_2d_multicast(dst, &tm_kv, c0, row, full, 3, ptx::kEvictLast);
+        ptx::tma_load_2d_multicast(dst + kT16, &tm_kv, c0 + 64, row, full, 3, ptx::kEvictLast);
+      };
+      for (int it = 0; it < n_it; ++it) {
+        load_page(it, 0);
+        load_page(it, 1);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc_kk = ptx::make_idesc_bf16_f32(128, 128);                 // S, dP: K-major x K-major
+      constexpr uint32_t idesc_dq = ptx::make_idesc_bf16_f32(128, kD) | (1u << 16);     // dQ: B (= K) MN-major
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        const uint32_t ph = (uint32_t)((j >> 1) & 1);
+        ptx::mbar_wait(bar(1 + s), ph);            // K of step j landed
+        ptx::mbar_wait(bar(7 + s), ph ^ 1u);       // S[s] drained (step j - 2)
+        ptx::tc_fence_after_sync();
+        const uint32_t k_addr = kv_smem + (uint32_t)(s * kStageKV);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t a = ptx::make_kmajor_sw128_desc(q_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+          const uint64_t b = ptx::make_kmajor_sw128_desc(k_addr + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+          ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 128), a, b, idesc_kk, ks > 0 ? 1u : 0u);
+        }
+        ptx::tc_commit(bar(5 + s));
+      };
+      auto issue_dp = [&](int j) {
+        const int s = j & 1;
+        ptx::mbar_wait(bar(13 + s), (uint32_t)((j >> 1) & 1));   // V of step j landed
+        ptx::mbar_wait(bar(10), (uint32_t)((j & 1) ^ 1));        // dP drained (step j - 1)
+        ptx::tc_fence_after_sync();
+        const uint32_t v_addr = kv_smem + (uint32_t)(s * kStageKV + 2 * kT16);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t a = ptx::make_kmajor_sw128_desc(do_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+          const uint64_t b = ptx::make_kmajor_sw128_desc(v_addr + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+          ptx::mma_bf16_ss(tmem_base + 256u, a, b, idesc_kk, ks > 0 ? 1u : 0u);
+        }
+        ptx::tc_commit(bar(9));
+        ptx::tc_commit_multicast(bar(15 + s), 3);  // V slot consumed: tell BOTH producers
+      };
+      ptx::mbar_wait(bar(0), 0);
+      issue_s(0);
+      issue_dp(0);
+      for (int i = 0; i < n_it; ++i) {
+        if (i + 1 < n_it) {
+          issue_s(i + 1);
+          issue_dp(i + 1);
+        }
+        const int s = i & 1;
+        ptx::mbar_wait(bar(11), (uint32_t)(i & 1));              // dS of step i is in shared memory
+        ptx::tc_fence_after_sync();
+        const uint32_t k_addr = kv_smem + (uint32_t)(s * kStageKV);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {           // dQ += dS K     (K read as stored: keys are the contraction rows)
+          const uint64_t a = ptx::make_kmajor_sw128_desc(ds_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+          const uint64_t b = ptx::make_mnmajor_sw128_desc(k_addr, kT16) + (uint64_t)(128 * ks);
+          ptx::mma_bf16_ss(tmem_base + 384u, a, b, idesc_dq, (i > 0 || ks > 0) ? 1u : 0u);
+        }
+        ptx::tc_commit(bar(12));                   // dS may be rewritten
+        ptx::tc_commit_multicast(bar(3 + s), 3);   // K slot consumed: tell BOTH producers
+      }
+      ptx::tc_commit(bar(17));
+    }
+    __syncwarp();
+  } else {
+    // ===== softmax warps: a PAIR of threads owns one (token, head) row; half h works on keys [64 h, 64 h + 64) =====
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const int m = q * 32 + lane;
+    const int qi = m / p.R, r = m - qi * p.R;
+    const int qpos = t0 + qi;
+    const bool valid = qi < n_valid && qi < p.nq;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int64_t stat = (int64_t)(row0 + qi) * p.n_q + (kvh * p.R + r);
+    const float lse_row = valid ? __ldg(p.lse + stat) : INFINITY;   // padding rows: P = 0
+    const float delta_row = valid ? __ldg(p.delta + stat) : 0.f;
+    const uint32_t ds_row = ds_smem + (uint32_t)(h * kT16 + m * 128);
+
+    for (int i = 0; i < n_it; ++i) {
+      const int s = i & 1;
+      ptx::mbar_wait(bar(5 + s), (uint32_t)((i >> 1) & 1));
+      ptx::tc_fence_after_sync();
+      float sv[64];
+      {
+        uint32_t v0[32], v1[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(s * 128 + h * 64), v0);
+        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(s * 128 + h * 64 + 32), v1);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) { sv[e] = __uint_as_float(v0[e]); sv[32 + e] = __uint_as_float(v1[e]); }
+      }
+      ptx::tc_fence_before_sync();
+      softmax_bar();
+      if (threadIdx.x == 64) ptx::mbar_arrive(bar(7 + s));   // S[s] drained -> Q K^T of step i + 2
+      const int key0 = i * 128 + h * 64;
+      const bool diag = i * 128 + 127 > t0;
+#pragma unroll
+      for (int e = 0; e < 64; ++e) sv[e] = ex2f(fmaf(sv[e], p.scale_log2, -lse_row));
+      if (diag) {
+#pragma unroll
+        for (int e = 0; e < 64; ++e)
+          if (key0 + e > qpos) sv[e] = 0.f;
+      }
+      ptx::mbar_wait(bar(9), (uint32_t)(i & 1));             // dP of step i
+      ptx::tc_fence_after_sync();
+      {
+        uint32_t v0[32], v1[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(256 + h * 64), v0);
+        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(256 + h * 64 + 32), v1);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          sv[e] *= (__uint_as_float(v0[e]) - delta_row);
+          sv[32 + e] *= (__uint_as_float(v1[e]) - delta_row);
+        }
+      }
+      ptx::tc_fence_before_sync();
+      softmax_bar();
+      if (threadIdx.x == 64) ptx::mbar_arrive(bar(10));      // dP drained -> dO V^T of step i + 1
+      ptx::mbar_wait(bar(12), (uint32_t)((i & 1) ^ 1));      // dQ MMA of step i - 1 has consumed the dS buffer
+#pragma unroll
+      for (int j = 0; j < 64; j += 8)
+        sts_v4(ds_row + (((uint32_t)(j >> 3) ^ (uint32_t)(m & 7)) << 4), pk2(sv[j], sv[j + 1]), pk2(sv[j + 2], sv[j + 3]),
+               pk2(sv[j + 4], sv[j + 5]), pk2(sv[j + 6], sv[j + 7]));
+      ptx::fence_proxy_async();
+      softmax_bar();
+      if (threadIdx.x == 64) ptx::mbar_arrive(bar(11));      // dS ready -> dQ += dS K
+    }
+
+    // ---- epilogue: this thread's 64 head-dim columns of its dQ row ----
+    ptx::mbar_wait(bar(17), 0);
+    ptx::tc_fence_after_sync();
+    uint32_t v0[32], v1[32];
+    ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(384 + h * 64), v0);
+    ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(384 + h * 64 + 32), v1);
+    ptx::tmem_ld_wait();
+    if (valid) {
+      __nv_bfloat16* dst = p.dqkv + (int64_t)(row0 + qi) * p.dqkv_stride + (kvh * p.R + r) * kD + h * 64;
+      const float sc = p.sm_scale;
+#pragma unroll
+      for (int d = 0; d < 32; d += 8) {
+        uint4 a, b;
+        a.x = pk2(__uint_as_float(v0[d]) * sc, __uint_as_float(v0[d + 1]) * sc);
+        a.y = pk2(__uint_as_float(v0[d + 2]) * sc, __uint_as_float(v0[d + 3]) * sc);
+        a.z = pk2(__uint_as_float(v0[d + 4]) * sc, __uint_as_float(v0[d + 5]) * sc);
+        a.w = pk2(__uint_as_float(v0[d + 6]) * sc, __uint_as_float(v0[d + 7]) * sc);
+        b.x = pk2(__uint_as_float(v1[d]) * sc, __uint_as_float(v1[d + 1]) * sc);
+        b.y = pk2(__uint_as_float(v1[d + 2]) * sc, __uint_as_float(v1[d + 3]) * sc);
+        b.z = pk2(__uint_as_float(v1[d + 4]) * sc, __uint_as_float(v1[d + 5]) * sc);
+        b.w = pk2(__uint_as_float(v1[d + 6]) * sc, __uint_as_float(v1[d + 7]) * sc);
+        *reinterpret_cast<uint4*>(dst + d) = a;
+        *reinterpret_cast<uint4*>(dst + 32 + d) = b;
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync();   // the partner may still multicast into this CTA's shared memory / arrive on its barriers
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+}  // namespace prl
+
+using namespace prl;
+
+extern "C" size_t prl_attn_varlen_bwd_workspace_bytes(int32_t T, int32_t n_q) { return (size_t)T * (size_t)n_q * sizeof(float); }
+
+// dqkv[T, dqkv_stride] <- gradients of the packed (roped) q | k | v given d_out; every row of every segment is written.
+extern "C" int prl_attn_varlen_bwd(const void* qkv, int64_t qkv_stride, int32_t T, const int32_t* seg_start,
+                                   const int32_t* seg_len, int32_t n_seg, int32_t max_seg_len, int32_t n_q,
+                                   int32_t n_kv, int32_t head_dim, float sm_scale, const void* out_bf16,
+                                   const void* d_out_bf16, const float* lse, void* dqkv, int64_t dqkv_stride,
+                                   void* workspace, size_t workspace_bytes, prl_stream_t stream_) {
+  PRL_CHECK_ARG(qkv && seg_start && seg_len && out_bf16 && d_out_bf16 && lse && dqkv && workspace,
+                "prl_attn_varlen_bwd: NULL argument");
+  PRL_CHECK_ARG(head_dim == kD, "prl_attn_varlen_bwd: head_dim must be 128");
+  PRL_CHECK_ARG(T >= 1 && n_seg >= 1 && max_seg_len >= 1 && n_kv >= 1 && n_q % n_kv == 0 && n_q / n_kv <= 64,
+                "prl_attn_varlen_bwd: bad shape (GQA group size must be <= 64)");
+  const int64_t width = (int64_t)(n_q + 2 * n_kv) * kD;
+  PRL_CHECK_ARG(qkv_stride >= width && qkv_stride % 8 == 0 && dqkv_stride >= width && dqkv_stride % 8 == 0,
+                "prl_attn_varlen_bwd: bad row stride");
+  PRL_CHECK_ARG(workspace_bytes >= prl_attn_varlen_bwd_workspace_bytes(T, n_q), "prl_attn_varlen_bwd: workspace too small");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float* delta = (float*)workspace;
+  {
+    const int64_t rows = (int64_t)T * n_q;
+    attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>((const __nv_bfloat16*)out_bf16,
+                                                                     (const __nv_bfloat16*)d_out_bf16, rows, delta);
+    PRL_LAUNCH_CHECK();
+  }
+  BwdParams p;
+  p.lse = lse; p.delta = delta; p.dqkv = (__nv_bfloat16*)dqkv; p.dqkv_stride = dqkv_stride;
+  p.seg_start = seg_start; p.seg_len = seg_len; p.n_q = n_q; p.n_kv = n_kv; p.R = n_q / n_kv;
+  p.col_k = n_q * kD; p.col_v = (n_q + n_kv) * kD;
+  p.scale_log2 = sm_scale * 1.4426950408889634f; p.sm_scale = sm_scale;
+  CUtensorMap tkv, tq, tdo;
+  int rc = make_tmap_2d_bf16(&tkv, qkv, (uint64_t)width, (uint64_t)T, (uint64_t)qkv_stride * 2, 64, 64);
+  if (rc) return rc;
+  {
+    // ---- dK, dV ----
+    p.nq = 64 / p.R;
+    rc = make_tmap_3d_bf16(&tq, qkv, kD, (uint64_t)n_q, (uint64_t)T, kD * 2, (uint64_t)qkv_stride * 2, 64, (uint32_t)p.R, (uint32_t)p.nq);
+    if (rc) return rc;
+    rc = make_tmap_3d_bf16(&tdo, d_out_bf16, kD, (uint64_t)n_q, (uint64_t)T, kD * 2, (uint64_t)n_q * kD * 2, 64, (uint32_t)p.R, (uint32_t)p.nq);
+    if (rc) return rc;
+    static SmemAttr attr = {};
+    PRL_CUDA(ensure_smem(attn_bwd_dkdv_kernel, kSmemDkdv, attr));
+    dim3 grid((unsigned)((max_seg_len + 127) / 128), (unsigned)n_kv, (unsigned)n_seg);
+    attn_bwd_dkdv_kernel<<<grid, kThreadsB, (size_t)kSmemDkdv, stream>>>(tq, tdo, tkv, p);
+    PRL_LAUNCH_CHECK();
+  }
+  {
+    // ---- dQ ----
+    p.nq = 128 / p.R;
+    rc = make_tmap_3d_bf16(&tq, qkv, kD, (uint64_t)n_q, (uint64_t)T, kD * 2, (uint64_t)qkv_stride * 2, 64, (uint32_t)p.R, (uint32_t)p.nq);
+    if (rc) return rc;
+    rc = make_tmap_3d_bf16(&tdo, d_out_bf16, kD, (uint64_t)n_q, (uint64_t)T, kD * 2, (uint64_t)n_q * kD * 2, 64, (uint32_t)p.R, (uint32_t)p.nq);
+    if (rc) return rc;
+    static SmemAttr attr = {};
+    PRL_CUDA(ensure_smem(attn_bwd_dq_kernel, kSmemDq, attr));
+    dim3 grid((unsigned)(((max_seg_len + p.nq - 1) / p.nq + 1) & ~1), (unsigned)n_kv, (unsigned)n_seg);
+    attn_bwd_dq_kernel<<<grid, kThreadsB, (size_t)kSmemDq, stream>>>(tq, tdo, tkv, p);
+    PRL_LAUNCH_CHECK();
+  }
+  return PRL_OK;
+}

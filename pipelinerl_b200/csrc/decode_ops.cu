@@ -291,10 +291,15 @@ struct SamplePartial { float m, s, v, z; int i; int pad[3]; };  // z = logit/T o
 __global__ void __launch_bounds__(kSampleThreads) sample_partial_kernel(const float* __restrict__ logits, int V,
                                                                        float inv_temp, int greedy, uint64_t seed,
                                                                        uint32_t step, int vocab_offset,
-                                                                       SamplePartial* __restrict__ part) {
+                                                                       SamplePartial* __restrict__ part,
+                                                                       const float* __restrict__ inv_temp_rows,
+                                                                       const uint8_t* __restrict__ greedy_rows) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x, pi = blockIdx.y;
+  // per-sequence sampling parameters (requests of different LLM handles share an engine: train T=1, eval greedy ...)
+  if (inv_temp_rows != nullptr) inv_temp = inv_temp_rows[b];
+  if (greedy_rows != nullptr) greedy = greedy_rows[b];
   const float* z = logits + (int64_t)b * V;
   const int per = (V + kSampleParts - 1) / kSampleParts;
   const int lo = pi * per, hi = (lo + per < V) ? lo + per : V;
@@ -422,7 +427,8 @@ __global__ void advance_kernel(prl_engine_state st) {
     st.out_logprobs[(int64_t)b * st.out_stride + n] = st.sampled_logprobs[b];
     st.gen_count[b] = n + 1;
     st.tokens[b] = id;
-    const bool eos = (id == st.eos_id) && !st.ignore_eos;
+    const bool ignore = st.ignore_eos || (st.ignore_eos_rows != nullptr && st.ignore_eos_rows[b]);
+    const bool eos = (id == st.eos_id) && !ignore;
     if (eos || n + 1 >= st.max_new[b]) {
       st.finished[b] = eos ? 1 : 2;  // 1 = stop, 2 = length
       st.active[b] = 0;
@@ -517,9 +523,23 @@ extern "C" int prl_sample_partials(const float* logits, int32_t B, int32_t V, fl
   PRL_CHECK_ARG(temperature > 0.f, "prl_sample_partials: temperature must be > 0 (use greedy=1 for argmax)");
   dim3 grid((unsigned)B, kSampleParts);
   PRL_CUDA(launch_pdl(sample_partial_kernel, grid, dim3(kSampleThreads), 0, (cudaStream_t)st, logits, (int)V,
-                      1.f / temperature, (int)greedy, seed, step, (int)vocab_offset, (SamplePartial*)partials));
+                      1.f / temperature, (int)greedy, seed, step, (int)vocab_offset, (SamplePartial*)partials,
+                      (const float*)nullptr, (const uint8_t*)nullptr));
   PRL_LAUNCH_CHECK();
   return PRL_OK;
+}
+
+extern "C" int prl_sample_logprob_rows(const float* logits, int32_t B, int32_t V, const float* inv_temperature_rows,
+                                       const uint8_t* greedy_rows, uint64_t seed, uint32_t step, int32_t* out_ids,
+                                       float* out_logprobs, void* workspace, size_t workspace_bytes, prl_stream_t st) {
+  PRL_CHECK_ARG(logits && inv_temperature_rows && greedy_rows && out_ids && out_logprobs && B >= 1 && V >= 1,
+                "prl_sample_logprob_rows: bad argument");
+  PRL_CHECK_ARG(workspace && workspace_bytes >= prl_sample_workspace_bytes(B), "prl_sample_logprob_rows: workspace too small");
+  dim3 grid((unsigned)B, kSampleParts);
+  PRL_CUDA(launch_pdl(sample_partial_kernel, grid, dim3(kSampleThreads), 0, (cudaStream_t)st, logits, (int)V, 1.f, 0, seed,
+                      step, 0, (SamplePartial*)workspace, inv_temperature_rows, greedy_rows));
+  PRL_LAUNCH_CHECK();
+  return prl_sample_finalize(workspace, B, 1, out_ids, out_logprobs, st);
 }
 
 // phase 2 only: merge n_groups x 16 partials per row ([group][B][16]) -> ids, logprobs

@@ -116,9 +116,13 @@ class DecodeEngine:
         self.free_slots = list(range(B - 1, -1, -1))
         self.slot_req: dict[int, Request] = {}
         self.step_count = 0
-        self.temperature = 1.0
-        self.greedy = False
-        self.ignore_eos = False
+        # sampling parameters are PER SLOT (device arrays read by the sampler / state-advance kernels): requests of
+        # different LLM handles (train T=1, eval greedy, ...) share the batch without touching each other's distribution.
+        # The engine-wide attributes below are the defaults of idle slots and what benches / tools set for all slots.
+        self.inv_temp_rows = torch.ones(B, dtype=torch.float32, device=d)
+        self.greedy_rows = torch.zeros(B, dtype=torch.uint8, device=d)
+        self.ignore_eos_rows = torch.zeros(B, dtype=torch.uint8, device=d)
+        self._temperature, self._greedy, self._ignore_eos = 1.0, False, False
         self._graphs: dict[int, torch.cuda.CUDAGraph] = {}
         # ---- chunked prefill + prefix sharing (GRPO attempts share their prompt) ----
         self.prefill_chunk = int(prefill_chunk)
@@ -129,11 +133,42 @@ class DecodeEngine:
         from collections import OrderedDict
         self._page_of_hash: "OrderedDict[int, int]" = OrderedDict()   # chained hash of a full 64-token page -> page id (LRU)
         self._hash_of_page: dict[int, int] = {}
+        self._tokens_of_page: dict[int, tuple] = {}                   # page -> its 64 tokens (verified on every hit)
         self._page_pending: dict[int, tuple[Request, int]] = {}       # page -> (request that fills it, tokens needed)
         self._pf = None                                # lazily allocated prefill buffers
         self.stats = {"prefill_tokens": 0, "prefix_hits": 0, "prefix_hit_tokens": 0}
         self._next_id = 0
         self._state = self._make_state()
+
+    # engine-wide sampling defaults: assigning one overwrites every slot (benches, tools, single-tenant tests)
+    @property
+    def temperature(self) -> float:
+        return self._temperature
+
+    @temperature.setter
+    def temperature(self, t: float) -> None:
+        if not t > 0:
+            raise ValueError("temperature must be > 0 (use greedy=True for argmax)")
+        self._temperature = float(t)
+        self.inv_temp_rows.fill_(1.0 / float(t))
+
+    @property
+    def greedy(self) -> bool:
+        return self._greedy
+
+    @greedy.setter
+    def greedy(self, g: bool) -> None:
+        self._greedy = bool(g)
+        self.greedy_rows.fill_(int(bool(g)))
+
+    @property
+    def ignore_eos(self) -> bool:
+        return self._ignore_eos
+
+    @ignore_eos.setter
+    def ignore_eos(self, v: bool) -> None:
+        self._ignore_eos = bool(v)
+        self.ignore_eos_rows.fill_(int(bool(v)))
 
     # ------------------------------------------------------------------------------------------
     def _plan_gemms(self) -> None:
@@ -156,6 +191,7 @@ class DecodeEngine:
         s.out_ids, s.out_logprobs, s.out_stride = self.out_ids.data_ptr(), self.out_logprobs.data_ptr(), self.max_new
         s.gen_count, s.max_new, s.finished = self.gen_count.data_ptr(), self.max_new_t.data_ptr(), self.finished.data_ptr()
         s.eos_id, s.ignore_eos = self.eos_id, 0
+        s.ignore_eos_rows = self.ignore_eos_rows.data_ptr()
         return s
 
     # ------------------------------------------------------------------------------------------
@@ -238,14 +274,12 @@ class DecodeEngine:
                                             float(self.temperature), None, int(self.greedy), self.seed, self.step_count,
                                             None, None, None, self.sampled.data_ptr(), self.sampled_lp.data_ptr(),
                                             self.head_ws.data_ptr(), self.head_ws.numel(), st))
-            self._state.ignore_eos = int(self.ignore_eos)
             _lib.check(lib.prl_advance_state(C.byref(self._state), st))
             return
-        _lib.check(lib.prl_sample_logprob(self.logits.data_ptr(), self.B, self.cfg.head_rows, float(self.temperature),
-                                          int(self.greedy), self.seed, self.step_count, self.sampled.data_ptr(),
-                                          self.sampled_lp.data_ptr(), self.sample_ws.data_ptr(),
-                                          self.sample_ws.numel(), st))
-        self._state.ignore_eos = int(self.ignore_eos)
+        _lib.check(lib.prl_sample_logprob_rows(self.logits.data_ptr(), self.B, self.cfg.head_rows,
+                                               self.inv_temp_rows.data_ptr(), self.greedy_rows.data_ptr(), self.seed,
+                                               self.step_count, self.sampled.data_ptr(), self.sampled_lp.data_ptr(),
+                                               self.sample_ws.data_ptr(), self.sample_ws.numel(), st))
         _lib.check(lib.prl_advance_state(C.byref(self._state), st))
 
     def step(self) -> None:
@@ -271,8 +305,32 @@ class DecodeEngine:
 
     def set_arena(self, arena: ParamArena) -> None:
         """Switch the parameter buffer between two token steps (weight update flip).  Graphs are cached per
-        buffer, so after the first use of each of the two buffers a flip costs one dictionary lookup."""
+        buffer, so after the first use of each of the two buffers a flip costs one dictionary lookup.
+        Prompt pages cached for prefix sharing hold KV computed under the OLD weights: they are dropped from the cache
+        (in-flight sequences keep their own references and finish on the KV they have, as in the reference, where
+        running requests survive `receive_weight_update`, vllm1.py:158-182), so a request stamped with the new
+        model_version never attends to stale prompt KV."""
+        if arena is not self.arena:
+            self.invalidate_prefix_cache()
         self.arena = arena
+
+    def invalidate_prefix_cache(self) -> None:
+        for h, pg in list(self._page_of_hash.items()):
+            self._drop_cached_page(h, pg)
+
+    def _drop_cached_page(self, h: int, pg: int) -> None:
+        self._page_of_hash.pop(h, None)
+        self._hash_of_page.pop(pg, None)
+        self._tokens_of_page.pop(pg, None)
+        self._page_pending.pop(pg, None)
+        self.page_ref[pg] -= 1                     # the cache's own reference
+        if self.page_ref[pg] == 0:
+            self.free_pages.append(pg)
+
+    def _check_token_ids(self, ids) -> None:
+        lo, hi = min(ids), max(ids)
+        if lo < 0 or hi >= self.cfg.vocab_size:
+            raise ValueError(f"token id out of range [0, {self.cfg.vocab_size}): min {lo}, max {hi}")
 
     # ---- chunked prefill ------------------------------------------------------------------------
     def _prefill_buffers(self):
@@ -463,9 +521,7 @@ class DecodeEngine:
                 break
             pg = self._page_of_hash[h]
             if self.page_ref[pg] == 1 and pg not in self._page_pending:
-                del self._page_of_hash[h]
-                del self._hash_of_page[pg]
-                self._release_pages([pg])
+                self._drop_cached_page(h, pg)
                 need -= 1
 
     def _evict_prefixes(self, need: int) -> None:  # kept name: tests / callers free the whole cache with a big `need`
@@ -491,6 +547,12 @@ class DecodeEngine:
             raise ValueError("empty prompt")
         if n + params.max_tokens > self.max_seq_len or params.max_tokens > self.max_new:
             raise ValueError(f"request of {n}+{params.max_tokens} tokens exceeds the engine limits")
+        self._check_token_ids(prompt_ids)
+        if not params.greedy and not params.temperature > 0:
+            raise ValueError("temperature must be > 0 (use greedy=True for argmax)")
+        if self.fused_head and (params.greedy != self._greedy or (not params.greedy and params.temperature != self._temperature)):
+            raise ValueError("the fused sampling head takes engine-wide sampling parameters: build the engine with "
+                             "fused_head=False to mix requests with different temperature / greedy settings")
         if not self.can_admit(n, params.max_tokens):
             raise RuntimeError("engine full")
         req = Request(self._next_id, list(prompt_ids), params, model_version=model_version)
@@ -504,10 +566,12 @@ class DecodeEngine:
             start = n - 1
             n_full = (n - 1) // PAGE_SIZE
             hashes = self._page_hashes(prompt_ids, n_full) if self.prefix_sharing else []
-            for h in hashes:                       # longest cached chain of full pages
+            for k, h in enumerate(hashes):         # longest cached chain of full pages
                 pg = self._page_of_hash.get(h)
                 if pg is None:
                     break
+                if self._tokens_of_page.get(pg) != tuple(prompt_ids[k * PAGE_SIZE:(k + 1) * PAGE_SIZE]):
+                    break                          # hash collision: the cached page holds other tokens
                 shared.append(pg)
                 self._page_of_hash.move_to_end(h)
             for pg in shared:
@@ -523,6 +587,7 @@ class DecodeEngine:
                 if h not in self._page_of_hash:
                     self._page_of_hash[h] = pg
                     self._hash_of_page[pg] = h
+                    self._tokens_of_page[pg] = tuple(prompt_ids[k * PAGE_SIZE:(k + 1) * PAGE_SIZE])
                     self.page_ref[pg] += 1               # the cache's own reference
                     self._page_pending[pg] = (req, (k + 1) * PAGE_SIZE)
             if shared:
@@ -538,6 +603,9 @@ class DecodeEngine:
         self.prompt_buf[slot, :n].copy_(torch.tensor(prompt_ids, dtype=torch.int32), non_blocking=True)
         self.prompt_len[slot] = n
         self.max_new_t[slot] = params.max_tokens
+        self.inv_temp_rows[slot] = 1.0 if params.greedy else 1.0 / float(params.temperature)
+        self.greedy_rows[slot] = int(bool(params.greedy))
+        self.ignore_eos_rows[slot] = int(bool(params.ignore_eos) or self._ignore_eos)
         self.tokens[slot] = prompt_ids[start]
         self.positions[slot] = start
         self.seq_lens[slot] = start + 1

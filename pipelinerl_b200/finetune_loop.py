@@ -49,6 +49,56 @@ def allreduce_gradients(flat_grad: torch.Tensor, group=None) -> None:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
 
 
+class StepAccountant:
+    """Sample accounting of one learner rank (pipelinerl/finetune_loop.py:626-646, 674-713).
+
+    `samples_per_step` is the GLOBAL batch of an optimizer step (and the loss normaliser, rl_config.batch_size);
+    every lead trainer owns `samples_per_step / world` of it.  After each micro-batch the cumulative local counts are
+    summed over the ranks (the reference all-gathers them, :707-709) and the optimizer step happens when the global
+    count EQUALS the target: the writer cuts micro-batches at that boundary (preprocess.py:620-622) and feeds sentinel
+    batches to ranks that already hold their share (:600-607, trainer side :674-676)."""
+
+    def __init__(self, samples_per_step: int, group=None, device=None, start_samples: int = 0):
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        if samples_per_step % self.world != 0:
+            raise ValueError(f"samples_per_step={samples_per_step} is not divisible by the {self.world} learner ranks")
+        self.samples_per_step = samples_per_step
+        self.samples_per_lead_per_step = samples_per_step // self.world
+        self.start_samples = start_samples
+        self.local_samples = 0
+        self.target_local = self.samples_per_lead_per_step
+        self.target_total = samples_per_step
+        self.device = device if (self.world > 1 and dist.get_backend(group) == "nccl") else "cpu"
+
+    def expects_sentinel(self) -> bool:
+        return self.local_samples == self.target_local
+
+    def observe(self, n_samples: int, sentinel: bool) -> tuple[int, bool]:
+        """account one micro-batch; returns (global samples so far incl. start_samples, do_optimizer_step)"""
+        if self.expects_sentinel() and not sentinel:
+            raise RuntimeError("this rank already holds its share of the optimizer step: expected a sentinel batch "
+                               "(the writer must cut micro-batches at the step boundary, MicroBatchDealer)")
+        if not sentinel:
+            self.local_samples += n_samples
+        total = self.local_samples
+        if self.world > 1:
+            import torch.distributed as dist
+            counts = torch.tensor([self.local_samples], dtype=torch.int64, device=self.device)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)
+            total = int(counts.item())
+        if total > self.target_total:
+            raise RuntimeError(f"micro-batch overshoots the optimizer step ({total} > {self.target_total} samples): "
+                               "pack with samples_per_step (pack_micro_batches / MicroBatchDealer)")
+        do_step = total == self.target_total
+        if do_step:
+            self.target_local += self.samples_per_lead_per_step
+            self.target_total += self.samples_per_step
+        return self.start_samples + total, do_step
+
+
 def prefetch_batches(batches: Iterable, maxsize: int = 1, pin_memory: bool = False):
     """The trainer's loader thread (pipelinerl/finetune_loop.py:494-505): a background thread pulls the next
     micro-batch from the `training_data` stream (parsing / tensor construction / optional pinning happen there) while
@@ -106,28 +156,31 @@ def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding
         weight_manager.src = opt.shadow_bf16
     from .finetune.optim import get_scheduler
     lr_schedule = get_scheduler(cfg.lr_scheduler_type, opt, cfg.num_warmup_steps, cfg.max_train_steps)
-    rl_cfg = cfg.rl.model_copy(update={"batch_size": cfg.samples_per_step})
+    rl_cfg = cfg.rl.model_copy(update={"batch_size": cfg.samples_per_step})   # GLOBAL batch normalises the loss
     tm = TrainingMetrics()
     history: list[dict] = []
-    samples_in_step, step_stats, t_step = 0, [], time.time()
+    acct = StepAccountant(cfg.samples_per_step, group=dp_group, device=dev, start_samples=tm.samples)
+    rank = acct.rank
+    step_stats, t_step = [], time.time()
     opt.zero_grad()
     for batch in batches:
         batch = batch.to_device(dev)
+        n_samples = 0 if batch.sentinel else (int(batch.seq_boundaries.numel()) - 1 - (1 if batch.padding else 0)
+                                               if batch.is_packed else batch.input_ids.shape[0])
+        samples_so_far, do_optimizer_step = acct.observe(n_samples, bool(batch.sentinel))
         loss, stats = rl_step(model, batch, tm.completed_steps, cfg.max_train_steps, rl_cfg)
         if batch.sentinel:
             loss = loss * 0.0
         loss.backward()
-        n_samples = 0 if batch.sentinel else (int(batch.seq_boundaries.numel()) - 1 - (1 if batch.padding else 0)
-                                               if batch.is_packed else batch.input_ids.shape[0])
-        samples_in_step += n_samples
-        tm.samples += n_samples
         tm.tokens += int(batch.input_ids.numel())
-        tm.passes += 1
-        step_stats.append(stats)
-        if message_writer is not None:
-            message_writer.write(SamplesProcessed(samples_processed=tm.samples, timestamp=time.time()))
-        if samples_in_step < cfg.samples_per_step:
+        if not batch.sentinel:
+            tm.passes += 1
+            step_stats.append(stats)
+        if message_writer is not None and rank == 0:
+            message_writer.write(SamplesProcessed(samples_processed=samples_so_far, timestamp=time.time()))
+        if not do_optimizer_step:
             continue
+        tm.samples = samples_so_far
         if not sharded:
             allreduce_gradients(opt.grad, dp_group)   # fp32-parameter path: plain SUM all-reduce, full AdamW per rank
         grad_norm = opt.step()
@@ -145,9 +198,9 @@ def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding
             tm.last_broadcasted_version = tm.samples
         history.append({"step": tm.completed_steps, "loss": tm.train_loss, "grad_norm": tm.grad_norm,
                         "samples": tm.samples, "sec_per_step": time.time() - t_step, "push_ms": pushed_ms})
-        samples_in_step, step_stats, t_step = 0, [], time.time()
+        step_stats, t_step = [], time.time()
         if tm.completed_steps >= cfg.max_train_steps:
             break
-    if message_writer is not None:
+    if message_writer is not None and rank == 0:
         message_writer.write(TrainingDone(timestamp=time.time()))
     return tm, history

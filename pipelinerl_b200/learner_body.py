@@ -12,15 +12,14 @@ conf/finetune/base.yaml:47-50 checkpointing).  Here there is no autograd inside 
             arena (no .grad tensors, no autograd accumulation kernels, no per-parameter allocation)
 
 Every GEMM is `prl_gemm_ex` (csrc/gemm_tn.cu, persistent CTA-pair tcgen05 kernel).  The row-wise pieces (RMSNorm, RoPE, SiLU*up, bias / gain reductions, embedding
-scatter) are the kernels of csrc/learner_ops.cu.  Attention inside the learner is the one library call left
-(torch SDPA = a flash-attention library kernel): its sm_100a replacement is the next kernel on this path.
+scatter) are the kernels of csrc/learner_ops.cu.  Attention (the flash-attn varlen call of the reference) is the
+tcgen05 forward of csrc/attn_tc.cu and the two-kernel deterministic backward of csrc/attn_train.cu.
 """
 from __future__ import annotations
 
 import math
 
 import torch
-import torch.nn.functional as F
 
 from . import _lib
 from .model import ModelConfig
@@ -115,6 +114,31 @@ class Ops:
         _lib.check(self.lib.prl_colsum_bf16(x.data_ptr(), x.stride(0), T, Cc, out_f32.data_ptr(), ws.data_ptr(),
                                             ws.numel(), _lib.stream_ptr()))
 
+    def attn_fwd(self, qkv, seg_start, seg_len, max_len, n_q, n_kv, head_dim, need_lse=True):
+        """block-diagonal causal attention over the packed row qkv [T, (n_q + 2 n_kv) d] (q, k roped)"""
+        T = qkv.shape[0]
+        assert qkv.dtype == torch.bfloat16 and qkv.stride(1) == 1
+        out = torch.empty(T, n_q * head_dim, dtype=torch.bfloat16, device=qkv.device)
+        lse = torch.empty(T, n_q, dtype=torch.float32, device=qkv.device) if need_lse else None
+        _lib.check(self.lib.prl_attn_varlen_fwd(qkv.data_ptr(), qkv.stride(0), T, seg_start.data_ptr(), seg_len.data_ptr(),
+                                                seg_start.numel(), int(max_len), n_q, n_kv, head_dim,
+                                                1.0 / math.sqrt(head_dim), out.data_ptr(),
+                                                lse.data_ptr() if lse is not None else None, _lib.stream_ptr()))
+        return out, lse
+
+    def attn_bwd(self, qkv, out, d_out, lse, seg_start, seg_len, max_len, n_q, n_kv, head_dim):
+        """dqkv [T, (n_q + 2 n_kv) d] bf16: gradients of the roped q | k | v"""
+        T = qkv.shape[0]
+        assert d_out.dtype == torch.bfloat16 and d_out.is_contiguous() and out.is_contiguous()
+        dqkv = torch.empty(T, (n_q + 2 * n_kv) * head_dim, dtype=torch.bfloat16, device=qkv.device)
+        ws = torch.empty(int(self.lib.prl_attn_varlen_bwd_workspace_bytes(T, n_q)), dtype=torch.uint8, device=qkv.device)
+        _lib.check(self.lib.prl_attn_varlen_bwd(qkv.data_ptr(), qkv.stride(0), T, seg_start.data_ptr(), seg_len.data_ptr(),
+                                                seg_start.numel(), int(max_len), n_q, n_kv, head_dim,
+                                                1.0 / math.sqrt(head_dim), out.data_ptr(), d_out.data_ptr(),
+                                                lse.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), ws.data_ptr(),
+                                                ws.numel(), _lib.stream_ptr()))
+        return dqkv
+
     def embed(self, table, ids):
         T, H = ids.numel(), table.shape[1]
         out = torch.empty(T, H, dtype=torch.bfloat16, device=table.device)
@@ -138,6 +162,7 @@ class NativeBody:
         d = cfg.head_dim
         self.inv_freq = (1.0 / (cfg.rope_theta ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))).to(dev)
         self._saved = None
+        self._seg_cache = None
         self.keep_attention_layers = cfg.num_layers   # lower it when activation memory is short (0 = full recompute)
         self.keep_gate_up_layers = 0                  # layers that also keep gate_up's output (2 I bf16 per token):
         #                                               their backward skips the largest recompute GEMM
@@ -145,43 +170,25 @@ class NativeBody:
     def refresh(self) -> None:
         """Hook called after every optimizer step.  Nothing to rebuild: dgrad reads the weights as stored."""
 
-    # ---- attention (library call for now): q, k roped; block-diagonal causal over the packed segments ----
-    def _attention(self, qkv, bounds, need_grad):
-        c = self.cfg
-        T = qkv.shape[0]
-        q = qkv[:, :c.q_size].view(T, c.num_q_heads, c.head_dim)
-        k = qkv[:, c.q_size:c.q_size + c.kv_size].view(T, c.num_kv_heads, c.head_dim)
-        v = qkv[:, c.q_size + c.kv_size:].view(T, c.num_kv_heads, c.head_dim)
-        out = None
-        graph = []
-        for s, e in bounds:
-            qs, ks, vs = (t[s:e].transpose(0, 1)[None] for t in (q, k, v))
-            if need_grad:
-                qs, ks, vs = (t.detach().requires_grad_(True) for t in (qs, ks, vs))
-            with torch.set_grad_enabled(need_grad):
-                o = F.scaled_dot_product_attention(qs, ks, vs, is_causal=True, enable_gqa=True,
-                                                   scale=1.0 / math.sqrt(c.head_dim))
-            flat = o.detach()[0].transpose(0, 1)
-            if len(bounds) == 1 and flat.is_contiguous():
-                out = flat.reshape(T, c.q_size)      # the library already wrote [T, heads, d]: no copy
-            else:
-                if out is None:
-                    out = torch.empty(T, c.q_size, dtype=torch.bfloat16, device=qkv.device)
-                out[s:e] = flat.reshape(e - s, c.q_size)
-            if need_grad:
-                graph.append((o, qs, ks, vs))
-        return out, graph
+    # ---- attention: q, k roped; block-diagonal causal over the packed segments (csrc/attn_tc.cu, attn_train.cu) ----
+    def _segments(self, bounds, dev):
+        key = tuple(bounds)
+        if self._seg_cache is None or self._seg_cache[0] != key or self._seg_cache[1].device != dev:
+            st = torch.tensor([s for s, _ in bounds], dtype=torch.int32, device=dev)
+            ln = torch.tensor([e - s for s, e in bounds], dtype=torch.int32, device=dev)
+            self._seg_cache = (key, st, ln, max(e - s for s, e in bounds))
+        return self._seg_cache[1:]
 
-    def _attention_bwd(self, graph, bounds, d_attn, T):
+    def _attention(self, qkv, bounds, need_grad):
+        """returns (attention output [T, q_size] bf16, log-sum-exp [T, n_q] fp32 or None)"""
         c = self.cfg
-        dqkv = torch.empty(T, c.qkv_size, dtype=torch.bfloat16, device=d_attn.device)
-        for (o, qs, ks, vs), (s, e) in zip(graph, bounds):
-            do = d_attn[s:e].view(e - s, c.num_q_heads, c.head_dim).transpose(0, 1)[None]
-            dq, dk, dv = torch.autograd.grad(o, (qs, ks, vs), do)
-            dqkv[s:e, :c.q_size] = dq[0].transpose(0, 1).reshape(e - s, c.q_size)
-            dqkv[s:e, c.q_size:c.q_size + c.kv_size] = dk[0].transpose(0, 1).reshape(e - s, c.kv_size)
-            dqkv[s:e, c.q_size + c.kv_size:] = dv[0].transpose(0, 1).reshape(e - s, c.kv_size)
-        return dqkv
+        st, ln, mx = self._segments(bounds, qkv.device)
+        return self.ops.attn_fwd(qkv, st, ln, mx, c.num_q_heads, c.num_kv_heads, c.head_dim, need_lse=need_grad)
+
+    def _attention_bwd(self, qkv, attn, lse, bounds, d_attn):
+        c = self.cfg
+        st, ln, mx = self._segments(bounds, qkv.device)
+        return self.ops.attn_bwd(qkv, attn, d_attn, lse, st, ln, mx, c.num_q_heads, c.num_kv_heads, c.head_dim)
 
     # ---- one layer, in two halves ----
     def _attn_half(self, l, h, pos, bounds, need_grad):
@@ -190,9 +197,9 @@ class NativeBody:
         x1, rstd1 = o.rmsnorm(h, w[p + "input_layernorm.weight"], c.rms_eps)
         qkv = o.gemm(x1, w[p + "qkv_proj.weight"], bias=w.get(p + "qkv_proj.bias"))
         o.rope_(qkv, pos, self.inv_freq, c.num_q_heads + c.num_kv_heads, c.head_dim, +1.0)
-        attn, graph = self._attention(qkv, bounds, need_grad=need_grad)
+        attn, lse = self._attention(qkv, bounds, need_grad=need_grad)
         h2 = o.gemm(attn, w[p + "o_proj.weight"], residual=h)
-        return x1, rstd1, attn, graph, h2
+        return x1, rstd1, attn, (qkv, lse) if need_grad else None, h2
 
     def _mlp_half(self, l, h2, need_out=True):
         c, o, w = self.cfg, self.ops, self.w
@@ -231,7 +238,7 @@ class NativeBody:
         del dx2, h2
         d_attn = o.dgrad(dh2, w[p + "o_proj.weight"])
         o.wgrad(g[p + "o_proj.weight"], dh2, attn)
-        dqkv = self._attention_bwd(graph, bounds, d_attn, T)
+        dqkv = self._attention_bwd(graph[0], attn, graph[1], bounds, d_attn)
         del graph, attn, d_attn
         o.rope_(dqkv, pos, self.inv_freq, c.num_q_heads + c.num_kv_heads, c.head_dim, -1.0)
         if c.qkv_bias:

@@ -114,12 +114,15 @@ class TrainableLLM:
         self._calls = 0
 
     def load_tokenizer(self):
+        """The model's tokenizer from the local HF cache (no network on the boxes this runs on).  The synthetic tokenizer
+        is used ONLY when asked for by name (`tokenizer_name="synthetic"`, benches / plumbing tests) or injected through
+        `tokenizer=`: a missing or misspelt real tokenizer raises instead of silently training on hashed word ids."""
         if self.tokenizer is None:
-            try:
+            if self.tokenizer_name in ("synthetic", "synthetic-tokenizer"):
+                self.tokenizer = SyntheticTokenizer()
+            else:
                 import transformers
                 self.tokenizer = transformers.AutoTokenizer.from_pretrained(self.tokenizer_name, local_files_only=True)
-            except Exception:
-                self.tokenizer = SyntheticTokenizer()
         return self.tokenizer
 
     def log_output(self, prompt: Prompt, output: LLMOutput, cached: bool = False, count_tokens: bool = True) -> LLMCall:

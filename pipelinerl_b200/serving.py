@@ -85,7 +85,6 @@ class EngineServer:
                 still = []
                 for p in self._waiting:
                     if eng.can_admit(len(p.prompt_ids), p.params.max_tokens):
-                        eng.temperature, eng.greedy = p.params.temperature, p.params.greedy
                         req = eng.add_request(p.prompt_ids, p.params, model_version=eng.arena.version)
                         self._futures[req.req_id] = p
                     else:

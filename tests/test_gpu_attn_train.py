@@ -1,0 +1,138 @@
+"""Learner attention on sm_100a (csrc/attn_tc.cu forward, csrc/attn_train.cu backward) against an fp32 reference.
+
+The op: block-diagonal causal attention over one packed row -- what the reference gets from flash-attn varlen
+through HF when `position_ids` restart per packed sample (pipelinerl/finetune/rl/__init__.py:204,
+conf/finetune/base.yaml:12-13,64).  Reference here: plain fp32 softmax(Q K^T / sqrt(d) + causal mask) V per segment and
+head with torch autograd, on the same bf16-representable inputs.  Bar: every output / gradient
+element within 2^-7 of the tensor's scale (bf16 P / dS operands + bf16 result rounding); the measured maxima are printed.
+The backward must also be bitwise reproducible (fixed-order GQA reduction, no atomics)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+D = 128
+
+
+def _ops():
+    from pipelinerl_b200.learner_body import Ops
+    return Ops()
+
+
+def _reference(qkv, d_out, bounds, n_q, n_kv):
+    """fp32 attention + autograd, one (segment, kv head) at a time to bound memory.  Returns out, dqkv (fp32)."""
+    T = qkv.shape[0]
+    R = n_q // n_kv
+    x = qkv.float()
+    out = torch.empty(T, n_q * D, device=qkv.device)
+    dqkv = torch.zeros_like(x)
+    scale = 1.0 / math.sqrt(D)
+    for s, e in bounds:
+        L = e - s
+        mask = torch.ones(L, L, dtype=torch.bool, device=qkv.device).tril()
+        for g in range(n_kv):
+            kc, vc = (n_q + g) * D, (n_q + n_kv + g) * D
+            k = x[s:e, kc:kc + D].clone().requires_grad_(True)
+            v = x[s:e, vc:vc + D].clone().requires_grad_(True)
+            for r in range(R):
+                hq = (g * R + r) * D
+                q = x[s:e, hq:hq + D].clone().requires_grad_(True)
+                sc = (q @ k.t()) * scale
+                p = torch.softmax(sc.masked_fill(~mask, float("-inf")), -1)
+                o = p @ v
+                out[s:e, hq:hq + D] = o.detach()
+                gq, gk, gv = torch.autograd.grad(o, (q, k, v), d_out[s:e, hq:hq + D].float())
+                dqkv[s:e, hq:hq + D] = gq
+                dqkv[s:e, kc:kc + D] += gk
+                dqkv[s:e, vc:vc + D] += gv
+                del sc, p, o, gq, gk, gv
+    return out, dqkv
+
+
+def _run(dev, n_q, n_kv, lens, seed=0, pad_cols=0):
+    o = _ops()
+    T = sum(lens)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    width = (n_q + 2 * n_kv) * D
+    buf = torch.randn(T, width + pad_cols, generator=g, device=dev).to(torch.bfloat16)
+    qkv = buf[:, :width]                                  # row stride may exceed the logical width
+    d_out = torch.randn(T, n_q * D, generator=g, device=dev).to(torch.bfloat16)
+    bounds, s = [], 0
+    for L in lens:
+        bounds.append((s, s + L))
+        s += L
+    st = torch.tensor([b[0] for b in bounds], dtype=torch.int32, device=dev)
+    ln = torch.tensor(lens, dtype=torch.int32, device=dev)
+    out, lse = o.attn_fwd(qkv, st, ln, max(lens), n_q, n_kv, D)
+    dqkv = o.attn_bwd(qkv, out, d_out, lse, st, ln, max(lens), n_q, n_kv, D)
+    dqkv2 = o.attn_bwd(qkv, out, d_out, lse, st, ln, max(lens), n_q, n_kv, D)
+    torch.cuda.synchronize()
+    assert torch.equal(dqkv, dqkv2), "attention backward is not bitwise reproducible"
+    want_out, want_d = _reference(qkv, d_out, bounds, n_q, n_kv)
+    res = {}
+    err = (out.float() - want_out).abs().max().item() / want_out.abs().max().item()
+    res["out"] = err
+    # log-sum-exp (log2 domain of the scaled scores) against fp32, spot-checked on the first kv group
+    qc, kc = 0, n_q * D
+    s0, e0 = bounds[-1]
+    sc = (qkv[s0:e0, qc:qc + D].float() @ qkv[s0:e0, kc:kc + D].float().t()) / math.sqrt(D)
+    sc = sc.masked_fill(~torch.ones(e0 - s0, e0 - s0, dtype=torch.bool, device=dev).tril(), float("-inf"))
+    want_lse = torch.logsumexp(sc, -1) / math.log(2.0)
+    res["lse"] = (lse[s0:e0, 0] - want_lse).abs().max().item()
+    qe, ke = n_q * D, (n_q + n_kv) * D
+    for name, a, b in (("dq", 0, qe), ("dk", qe, ke), ("dv", ke, width)):
+        res[name] = ((dqkv[:, a:b].float() - want_d[:, a:b]).abs().max().item() / want_d[:, a:b].abs().max().item())
+    print(f"[attn_train] n_q={n_q} n_kv={n_kv} lens={lens if len(lens) < 8 else str(lens[:6]) + '...'}: " +
+          " ".join(f"{k}={v:.2e}" for k, v in res.items()))
+    assert res["out"] <= 2 ** -7, res
+    assert res["lse"] <= 2e-3, res
+    for k in ("dq", "dk", "dv"):
+        assert res[k] <= 2 ** -7, res
+    assert torch.isfinite(dqkv.float()).all() and torch.isfinite(out.float()).all()
+    return res
+
+
+@pytest.mark.parametrize("n_q,n_kv,lens", [
+    (4, 2, [1]),                       # a single token
+    (4, 2, [5, 1, 3]),
+    (7, 1, [64]),
+    (7, 1, [130, 17, 300, 1, 64]),     # ragged: tiles straddle segment ends
+    (2, 2, [257]),                     # R = 1
+    (4, 1, [200, 56]),
+    (5, 1, [129, 383]),                # Qwen2.5-32B's 5:1 grouping
+    (16, 1, [96, 33]),
+    (28, 4, [511, 1, 700]),
+])
+def test_varlen_attention_small(cuda_device, n_q, n_kv, lens):
+    _run(cuda_device, n_q, n_kv, lens, seed=len(lens) * 131 + n_q)
+
+
+def test_varlen_attention_padded_row_stride(cuda_device):
+    _run(cuda_device, 7, 1, [100, 250], seed=3, pad_cols=64)
+
+
+@pytest.mark.parametrize("lens", [[2048, 2048], [4096], [3000, 5, 1091]])
+def test_varlen_attention_qwen7b_heads_medium(cuda_device, lens):
+    _run(cuda_device, 28, 4, lens, seed=11)
+
+
+@pytest.mark.parametrize("lens", [[16384], [8192, 8192], [5000, 11000, 384]])
+def test_varlen_attention_qwen7b_heads_16k(cuda_device, lens):
+    """the trainer's micro-batch size (16 384 packed tokens) at Qwen2.5-7B's 28 / 4 heads"""
+    _run(cuda_device, 28, 4, lens, seed=5)
+
+
+def test_attention_output_rows_outside_every_segment_are_untouched(cuda_device):
+    """rows not covered by a segment are never written (the body always covers the row; this pins the bounds logic)"""
+    o = _ops()
+    dev = cuda_device
+    n_q, n_kv, T = 4, 2, 300
+    width = (n_q + 2 * n_kv) * D
+    qkv = torch.randn(T, width, device=dev).to(torch.bfloat16)
+    st = torch.tensor([10], dtype=torch.int32, device=dev)
+    ln = torch.tensor([200], dtype=torch.int32, device=dev)
+    out, lse = o.attn_fwd(qkv, st, ln, 200, n_q, n_kv, D)
+    ref, _ = o.attn_fwd(qkv[10:210].contiguous(), torch.zeros(1, dtype=torch.int32, device=dev), ln, 200, n_q, n_kv, D)
+    assert torch.equal(out[10:210], ref)

@@ -1,5 +1,7 @@
 """Whole loop on one GPU with a tiny model: plugin rollouts through the in-process engine -> preprocess ->
-packed micro-batches -> rl_step (CUDA tail) -> FusedAdamW -> in-flight weight push -> sampler flip."""
+packed micro-batches (cut at the optimizer-step boundary) -> rl_step on the NATIVE learner (learner_model.NativeQwen2:
+tcgen05 GEMMs, tcgen05 attention forward / backward, fused head, fp32 gradient arena) -> FusedAdamW -> in-flight weight
+push -> sampler flip."""
 import asyncio
 
 import pytest
@@ -17,7 +19,7 @@ def test_actor_preprocess_finetune_push_loop(cuda_device, tmp_path):
     from pipelinerl_b200.engine import DecodeEngine
     from pipelinerl_b200.finetune.rl import RLConfig
     from pipelinerl_b200.finetune_loop import TrainerConfig, run_training
-    from pipelinerl_b200.learner_model import TorchQwen2
+    from pipelinerl_b200.learner_model import NativeQwen2
     from pipelinerl_b200.llm import SyntheticTokenizer, TrainableLLM
     from pipelinerl_b200.preprocess import pack_micro_batches, preprocess_dataset
     from pipelinerl_b200.serving import EngineServer
@@ -60,10 +62,10 @@ def test_actor_preprocess_finetune_push_loop(cuda_device, tmp_path):
                       divide_advantage_by_std=False)
         entries = preprocess_dataset([s for g in published for s in g], tok, seq_length=128, rl_config=rl)
         assert len(entries) == 16
-        batches = pack_micro_batches(entries, tok, seq_length=128)
+        batches = pack_micro_batches(entries, tok, seq_length=128, samples_per_step=8)
         assert sum(int(b.seq_boundaries.numel()) - 1 for b in batches) == 16
 
-        learner = TorchQwen2(cfg, cuda_device, dtype=torch.float32, init=w)
+        learner = NativeQwen2(cfg, cuda_device, init=w)
         mgr = WeightUpdateManager([recv], torch.zeros(recv.nbytes // 2, dtype=torch.bfloat16, device=cuda_device))
         tcfg = TrainerConfig(samples_per_step=8, learning_rate=1e-3, max_train_steps=2, rl=rl)
         before = recv.arena.data.clone()

@@ -346,3 +346,43 @@ def test_rollout_records_match_reference_classes():
     rr = RolloutResult(training_texts=texts[:1], latency=0.5,
                        metrics=BaseMetrics(reward=1.0, success=True, no_error=True, no_answer=False))
     assert rr.model_dump() == rec["rollout_result_dump"]
+
+
+# ---- a5 writer: dealing micro-batches to trainer ranks (reference loop executed: make_golden_dealer.py) ----
+@pytest.mark.parametrize("name", ["one_trainer", "two_trainers", "three_trainers_sentinels", "four_trainers_sp2"])
+def test_micro_batch_dealer_matches_reference_writer_loop(name):
+    from collections import deque
+
+    from pipelinerl_b200.preprocess import MicroBatchDealer
+    case = json.loads((GOLDEN / "dealer_cases.json").read_text())[name]
+    spec = case["spec"]
+    writes = []
+    dealer = MicroBatchDealer(Tok(), spec["seq_length"], spec["num_trainers"], spec["samples_per_lead_per_step"],
+                              write=lambda rank, b: writes.append((rank, b)), seq_parallel=spec["seq_parallel"])
+    queue, flags = deque(), []
+    for chunk in copy.deepcopy(case["arrivals"]):
+        queue.extend(chunk)
+        while queue:
+            before = (len(queue), len(writes))
+            flags.append(dealer.deal(queue))
+            if (len(queue), len(writes)) == before:
+                break
+    assert flags == case["batch_done_flags"]
+    assert len(writes) == len(case["writes"])
+    for (rank, b), want in zip(writes, case["writes"]):
+        assert rank == want["rank"]
+        for k, w in want["batch"].items():
+            g = getattr(b, k)
+            if isinstance(g, torch.Tensor):
+                assert torch.equal(g, torch.tensor(w, dtype=g.dtype)), (name, k)
+            else:
+                assert g == w, (name, k)
+    assert dealer.published_samples == case["published_samples"]
+    assert {str(k): v for k, v in dealer.samples_per_trainer.items()} == case["samples_per_trainer"]
+    assert len(dealer.current_batch) == case["left_in_current_batch"]
+    # every lead trainer got the same number of micro-batches per completed step (collectives stay aligned)
+    per_rank = {}
+    for rank, _ in writes:
+        per_rank[rank] = per_rank.get(rank, 0) + 1
+    if dealer.trainer_id == 0:
+        assert len(set(per_rank.values())) == 1

@@ -131,6 +131,63 @@ def test_dp_gradient_allreduce_gloo_world2(tmp_path):
     assert got == [3.0 * i for i in range(10)]
 
 
+def test_dealer_feeds_two_gloo_learner_ranks_in_lockstep(tmp_path):
+    """Writer + trainer accounting under torch.distributed gloo, world_size 2: MicroBatchDealer deals the golden
+    `two_trainers` arrivals through the file streams (topic training_data, partition = rank); each rank reads ITS
+    partition and runs StepAccountant.  Both ranks must take their optimizer steps at the same micro-batch index, on
+    exactly `samples_per_step` global samples, with sentinels only where the rank already holds its share."""
+    script = tmp_path / "deal.py"
+    script.write_text(
+        "import sys, json, copy, torch, torch.distributed as dist\n"
+        "from collections import deque\n"
+        f"sys.path.insert(0, {str(ROOT)!r})\n"
+        "from pipelinerl_b200 import streams\n"
+        "from pipelinerl_b200.preprocess import MicroBatchDealer\n"
+        "from pipelinerl_b200.finetune_loop import StepAccountant\n"
+        "from pipelinerl_b200.finetune.types import PipelineBatchEncoding\n"
+        "class Tok:\n    eos_token_id = 7\n    padding_side = 'right'\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        f"case = json.load(open({str(ROOT / 'tests' / 'golden' / 'dealer_cases.json')!r}))['two_trainers']\n"
+        "spec = case['spec']\n"
+        f"streams.set_streams_backend('files')\n"
+        f"exp = {str(tmp_path)!r}\n"
+        "if r == 0:\n"
+        "    out = streams.StreamRangeSpec(exp_path=exp, topic='training_data', partition_range=(0, w))\n"
+        "    with streams.write_to_streams(out) as wr:\n"
+        "        dealer = MicroBatchDealer(Tok(), spec['seq_length'], w, spec['samples_per_lead_per_step'],\n"
+        "                                  write=lambda rank, b: wr.write(b, rank))\n"
+        "        q = deque()\n"
+        "        for chunk in case['arrivals']:\n"
+        "            q.extend(copy.deepcopy(chunk))\n"
+        "            while q:\n"
+        "                before = (len(q), dealer.published_samples, dealer.trainer_id)\n"
+        "                dealer.deal(q)\n"
+        "                if (len(q), dealer.published_samples, dealer.trainer_id) == before: break\n"
+        "dist.barrier()\n"
+        "with streams.read_stream(streams.SingleStreamSpec(exp_path=exp, topic='training_data', partition=r)) as rd:\n"
+        "    mine = [PipelineBatchEncoding.from_dict(d) for d in rd.read_available()]\n"
+        "n_mb = torch.tensor([len(mine)]); dist.all_reduce(n_mb, op=dist.ReduceOp.MIN)\n"
+        "acct = StepAccountant(spec['samples_per_lead_per_step'] * w)\n"
+        "steps, sent = [], 0\n"
+        "for i, b in enumerate(mine[:int(n_mb)]):\n"
+        "    n = 0 if b.sentinel else int(b.seq_boundaries.numel()) - 1 - (1 if b.padding else 0)\n"
+        "    sent += int(bool(b.sentinel))\n"
+        "    total, do_step = acct.observe(n, bool(b.sentinel))\n"
+        "    if do_step: steps.append((i, total))\n"
+        "allsteps = [None] * w; dist.all_gather_object(allsteps, (steps, sent, len(mine)))\n"
+        "if r == 0: print(json.dumps(allsteps))\n"
+        "dist.destroy_process_group()\n")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29579", str(script)],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-3000:]
+    (s0, sent0, n0), (s1, sent1, n1) = json.loads([l for l in res.stdout.splitlines() if l.startswith("[")][-1])
+    assert s0 == s1 and len(s0) >= 2                      # same micro-batch index, same global sample count
+    assert [t for _, t in s0] == [6 * (k + 1) for k in range(len(s0))]
+    assert sent0 + sent1 >= 1 and abs(n0 - n1) <= 1
+
+
 def test_trainer_state_follows_topic(tmp_path):
     from pipelinerl_b200.state import TrainerState
     from pipelinerl_b200.weights import SamplesProcessed, TrainingDone, TRAINER_TOPIC
@@ -268,7 +325,7 @@ def test_config1_plumbing_end_to_end_on_cpu(tmp_path):
         rcfg = RLConfig(policy_loss="ppo", kl_coef=0.0, final_kl_coef=0.0, batch_size=len(samples))
         entries = preprocess_dataset(samples, Tok(), seq_length=4096, rl_config=rcfg)
         assert len(entries) == len(samples) and all(len(e["advantages"]) == len(e["input_ids"]) for e in entries)
-        batches = pack_micro_batches(entries, Tok(), seq_length=1024)
+        batches = pack_micro_batches(entries, Tok(), seq_length=1024, samples_per_step=len(samples))
         assert batches and all(b.is_packed for b in batches)
         # the oracle learner consumes the packed rows this package produced
         cfg = tiny_cfg("gqa2")
