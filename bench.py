@@ -9,6 +9,13 @@ conf/base.yaml:17,63), synthetic 8192-token prompts already in the paged KV cach
 A "step" = one token for each of the 64 sequences (one pass of hot path 1).  N > 1: one engine replica per
 GPU (the token step shards as replicas only, no data-path collective) -> weak scaling.
 
+Under torchrun (N >= 2) the same run then re-partitions the N GPUs into the actor-learner split of the north star
+(`components.pipeline`, tools/split_bench.py): 1+1 at N=2, 3+1 at N=4, 6+2 and 4+4 at N=8 -- samplers keep
+generating while data-parallel learners train and push weights after every optimizer step; rollout tokens/s while
+training, trainer tokens/s and steps/s, DP exchange ms, push ms, STALL ms, `bytes_identical`, `dp_equals_single`.
+At N=1, `components.vllm_baseline` runs the same workload on vLLM 0.22 + FlashInfer (the engine the reference serves
+rollouts with) in a subprocess on the same box.
+
 ONE JSON line on stdout (rank 0).  Extra keys: roofline (dominant kernel = paged decode attention),
 cpu_baseline (oracle port on the host cores, bounded sample), components (trainer side: fused AdamW and PG-loss
 tail on 7B-sized inputs, and `trainer_step` = hot path 2 end to end on Qwen2.5-7B: 2 x 16 384-token micro-batches
@@ -44,6 +51,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-components", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="N >= 2: skip the inference + learner split run")
+    ap.add_argument("--no-vllm", action="store_true", help="N = 1: skip the vLLM 0.22 A/B subprocess")
+    ap.add_argument("--splits", default="", help="learner counts of the split runs, e.g. '2,4' (default: by N)")
     return ap.parse_args()
 
 
@@ -51,7 +61,8 @@ def workload_config(args, n_gpus):
     return {"workload": f"Qwen2.5-7B random-init token step, {args.batch} seqs/GPU x {args.context}-token synthetic "
                         f"prompts in paged KV, temperature 1.0 (BASELINE.json configs[1], sampler side)",
             "batch_per_gpu": args.batch, "context": args.context, "parallelism": f"replicas x{n_gpus}",
-            "l2": "inputs_exceed_l2 (weights 15.2 GB + KV 30 GB read per step)", "cuda_graph": True}
+            "lm_head": "fp32-equivalent (bf16 hi + bf16 lo operand streams, vllm_quantization.py:266-278)",
+            "l2": "inputs_exceed_l2 (weights 16.3 GB + KV 30 GB read per step)", "cuda_graph": True}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -90,6 +101,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic_bytes(algorithmic_bytes: int):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r1_attn_full_raw.csv: dram__bytes_read.sum 1.08266 GB + dram__bytes_write.sum 0.9 MB at B=64, S=8240 -> ratio
+    to the algorithmic bytes 1.0004), scaled to the bytes of the launch timed here."""
+    f = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        ratio = float(json.loads(f.read_text())["paged_attn_decode_kernel"]["traffic_over_algorithmic"])
+    except Exception:  # noqa: BLE001
+        return None
+    return int(algorithmic_bytes * ratio)
+
+
 def measured_peaks():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -103,7 +126,7 @@ def build_engine(args, dev):
     import torch
     from pipelinerl_b200.engine import DecodeEngine, PAGE_SIZE
     from pipelinerl_b200.model import ModelConfig, ParamArena
-    cfg = ModelConfig.qwen2_5_7b()
+    cfg = ModelConfig.qwen2_5_7b(fp32_head=True)   # the reference computes lm_head in fp32 on the sampler
     arena = ParamArena(cfg, dev).init_random(seed=42)
     room = 256 + args.steps + args.warmup * 2 + 64
     eng = DecodeEngine(cfg, arena, max_batch=args.batch, max_seq_len=args.context + room, max_new_tokens=room,
@@ -133,7 +156,7 @@ def build_engine(args, dev):
 def algorithmic_bytes(cfg, B, S):
     w_body = 2 * sum(n for n in [cfg.num_layers * (cfg.qkv_size * cfg.hidden_size + cfg.hidden_size * cfg.q_size +
                                                    3 * cfg.intermediate_size * cfg.hidden_size)])
-    w_head = 2 * cfg.vocab_size * cfg.hidden_size
+    w_head = (4 if cfg.fp32_head else 2) * cfg.vocab_size * cfg.hidden_size   # hi + lo streams = an fp32 weight's bytes
     kv_per_layer = B * S * 2 * cfg.num_kv_heads * cfg.head_dim * 2
     return w_body + w_head, kv_per_layer
 
@@ -241,7 +264,9 @@ def run_ours(args):
     step_bytes = w_bytes + cfg.num_layers * kv_bytes
     roofline = {"kernel": "paged_attn_decode_kernel(+combine)", "bound": "hbm", "achieved": round(achieved, 1),
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "launch_ms": round(attn_ms, 4), "algorithmic_bytes_per_launch": kv_bytes,
+                "traffic": ncu_traffic_bytes(kv_bytes), "traffic_source": "ncu --set full dram__bytes_read.sum + "
+                "dram__bytes_write.sum of this kernel (profiles/r1_attn_full_raw.csv: read 1.0004 x, read+write 1.0046 x algorithmic), scaled to this launch",
+                "launch_ms": round(attn_ms, 4), "algorithmic_bytes_per_launch": kv_bytes,
                 "share_of_step": round(attn_ms * cfg.num_layers / (ms / args.steps), 4),
                 "whole_step": {"algorithmic_bytes": step_bytes,
                                "achieved_GBs": round(step_bytes / (ms / args.steps / 1e3) / 1e9, 1),
@@ -275,11 +300,94 @@ def run_ours(args):
             out["components"]["trainer_step"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, budget_s=25.0)
+    if rank == 0 and world == 1 and not args.no_components and not args.no_vllm:
+        out.setdefault("components", {})["vllm_baseline"] = vllm_baseline(args)
+    if world > 1 and not args.no_components and not args.no_pipeline:
+        # ---- the actor-learner split on the same N GPUs (north star: N inference + (8 - N) learner GPUs) ----
+        import gc
+        try:
+            del eng, attn_all_layers
+        except NameError:
+            pass
+        gc.collect()
+        torch.cuda.empty_cache()
+        out.setdefault("components", {})["pipeline"] = run_pipeline_splits(args, world, rank, out)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def default_splits(world: int) -> list[int]:
+    """learner counts per world size: 1+1 (N=2), 3+1 (N=4), 6+2 and 4+4 (N=8: BASELINE.json configs[1] and [2])"""
+    if world >= 8:
+        return [2, 4]
+    return [1]
+
+
+def run_pipeline_splits(args, world, rank, headline):
+    """All ranks.  A watchdog bounds the whole component: if a split hangs (a rank died inside a collective), rank 0
+    still prints the headline line with the error recorded and every rank exits 0."""
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT / "tools"))
+    import split_bench
+    splits = [int(x) for x in args.splits.split(",") if x] or default_splits(world)
+    splits = [m for m in splits if 1 <= m < world]
+    results = {"note": "samplers generate (64 seqs x 8192-token context each) WHILE the learners train 2 x 16384-token "
+                       "micro-batches per learner per optimizer step and push weights after every step; "
+                       "sampler lm_head bf16 in this component (arena layout shared with the learner)"}
+    deadline_s = 330.0 * len(splits)
+
+    def bail():
+        if rank == 0:
+            results["error"] = f"watchdog: split run exceeded {deadline_s:.0f} s"
+            headline.setdefault("components", {})["pipeline"] = results
+            print(json.dumps(headline), flush=True)
+        else:
+            time.sleep(3.0)
+        os._exit(0)
+    dog = threading.Timer(deadline_s, bail)
+    dog.daemon = True
+    dog.start()
+    for m in splits:
+        key = f"{world - m}+{m}"
+        ok = torch_ok_flag = 1
+        try:
+            res = split_bench.run_split(m, updates=3, context=args.context, batch=args.batch)
+        except Exception as e:  # noqa: BLE001
+            res = {"error": f"rank {rank}: {type(e).__name__}: {str(e)[:300]}"}
+            ok = 0
+        if rank == 0:
+            results[key] = res
+        if not ok:          # a failed rank cannot rejoin the collectives of the next split: stop here (watchdog covers peers)
+            break
+    dog.cancel()
+    return results if rank == 0 else None
+
+
+def vllm_baseline(args):
+    """Same workload on vLLM 0.22 + FlashInfer sm_100 (the engine family the reference serves rollouts with; it pins
+    0.18.1) on this box, in a subprocess (tools/vllm_baseline.py): a LIBRARY baseline for the A/B, not product code."""
+    import gc
+    import torch
+    gc.collect()
+    torch.cuda.empty_cache()
+    env = dict(os.environ, BATCH=str(args.batch), CTX=str(args.context))
+    t0 = time.time()
+    try:
+        res = subprocess.run([sys.executable, str(ROOT / "tools" / "vllm_baseline.py")], capture_output=True, text=True,
+                             timeout=420, env=env)
+        lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+        if res.returncode != 0 or not lines:
+            return {"error": f"rc={res.returncode}: {(res.stderr or res.stdout)[-300:]}", "wall_s": round(time.time() - t0, 1)}
+        out = json.loads(lines[-1])
+        out["wall_s"] = round(time.time() - t0, 1)
+        return out
+    except subprocess.TimeoutExpired:
+        return {"error": "timeout after 420 s", "wall_s": round(time.time() - t0, 1)}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
 
 def bench_components(dev, peak):

@@ -213,6 +213,43 @@ int prl_adamw_sharded_reduce(const prl_adamw_shard_args* args, void* workspace, 
 int prl_adamw_sharded_update(const prl_adamw_shard_args* args, float* grad_norm_out, prl_stream_t stream);
 
 /* ======================================================================= *
+ * Feeder of hot path (2), GPU-resident: one packed micro-batch row built on the learner's GPU from a
+ * compact binary record (pipelinerl_b200/records.py) -- replaces populate_rl_data's pandas pipeline
+ * (pipelinerl/finetune/rl/__init__.py:453-570), collate_packed's list -> tensor building (finetune/data.py:215-283)
+ * and the JSONL round trip of the twelve [1, T] columns (streams.py:269-277, finetune_loop.py:109).
+ * All pointers are DEVICE pointers into the uploaded record.  The `chunk` is the set of whole rollout groups the
+ * statistics are taken over (preprocess.py:145-189: chunk_n_groups groups); the `pack` is the subset of its samples
+ * that forms this micro-batch, in row order.  Float columns are double -> float roundings of exactly the doubles the
+ * reference computes (Kahan sum / Welford std of pandas' groupby, rows in dataset order).
+ * ======================================================================= */
+typedef struct {
+  int32_t n_chunk, n_pack, padding /* pad-to-seq_parallel sentinel tokens */, total_tok, total_lp;
+  int32_t n_stat_slots, n_rollout_slots, n_groups;
+  const double* reward;          /* [n_chunk] */
+  const int32_t* stat_slot;      /* [n_chunk] dense id of (group_id, step_index) */
+  const int32_t* rollout_slot;   /* [n_chunk] dense id of (group_id, rollout_index) */
+  const int32_t* group_slot;     /* [n_chunk] dense id of group_id */
+  const int32_t* n_tok_all;      /* [n_chunk] tokens of every chunk sample */
+  const int32_t* pack_idx;       /* [n_pack] chunk index of each packed sample */
+  const int32_t* pack_flags;     /* [n_pack] bit0 finished, bits1-2 finish_reason: 1 length, 2 stop|content_filter */
+  const int32_t* tok_off;        /* [n_pack+1] */
+  const int32_t* lp_off;         /* [n_pack+1] */
+  const int32_t* input_ids;      /* [total_tok] packed samples, row order */
+  const int32_t* labels;         /* [total_tok] */
+  const float* logprobs;         /* [total_lp] sampler logprobs of the labelled tokens */
+  const float* ref_logprobs;     /* [total_lp] or NULL (= logprobs: kl_coef == 0, preprocess.py:160-161) */
+} prl_mb_record;
+typedef struct {                 /* PipelineBatchEncoding columns, [1, total_tok + padding] each (types.py:46-180) */
+  int64_t* input_ids; int64_t* labels; int64_t* attention_mask; int64_t* position_ids; int64_t* segment_ids;
+  float* rewards; float* advantages; float* ref_logprobs; float* old_logprobs; float* group_tokens;
+  float* num_labels; float* overflow;
+  int32_t* seq_boundaries;       /* [n_pack + 1 (+1 with padding)] */
+} prl_mb_columns;
+size_t prl_preprocess_workspace_bytes(int32_t n_pack, int32_t n_stat_slots, int32_t n_rollout_slots, int32_t n_groups);
+int prl_preprocess_pack(const prl_mb_record* record, int32_t divide_advantage_by_std, int32_t eos_token_id,
+                        const prl_mb_columns* out, void* workspace, size_t workspace_bytes, prl_stream_t stream);
+
+/* ======================================================================= *
  * Hot path (1): tcgen05 weight-streaming GEMM of the token step
  *   Y[M, N] = X[M, K] * W[N, K]^T, bf16 operands (row-major, K contiguous),
  *   fp32 accumulation in TMEM.  Replaces the cuBLAS GEMMs the vLLM engine runs

@@ -79,6 +79,21 @@ class EngineState(C.Structure):
     ]
 
 
+class MbRecord(C.Structure):
+    _fields_ = [("n_chunk", C.c_int32), ("n_pack", C.c_int32), ("padding", C.c_int32), ("total_tok", C.c_int32),
+                ("total_lp", C.c_int32), ("n_stat_slots", C.c_int32), ("n_rollout_slots", C.c_int32), ("n_groups", C.c_int32),
+                ("reward", C.c_void_p), ("stat_slot", C.c_void_p), ("rollout_slot", C.c_void_p), ("group_slot", C.c_void_p),
+                ("n_tok_all", C.c_void_p), ("pack_idx", C.c_void_p), ("pack_flags", C.c_void_p), ("tok_off", C.c_void_p),
+                ("lp_off", C.c_void_p), ("input_ids", C.c_void_p), ("labels", C.c_void_p), ("logprobs", C.c_void_p),
+                ("ref_logprobs", C.c_void_p)]
+
+
+class MbColumns(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("input_ids", "labels", "attention_mask", "position_ids", "segment_ids", "rewards",
+                                          "advantages", "ref_logprobs", "old_logprobs", "group_tokens", "num_labels",
+                                          "overflow", "seq_boundaries")]
+
+
 PRL_NUM_STATS = 32
 LOSS_IDS = {"ppo": 0, "reinforce": 1, "gspo": 2}
 STAT_NAMES = [
@@ -168,6 +183,9 @@ _SIGNATURES = {
     "prl_sample_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "prl_sample_logprob": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_uint64,
                                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "prl_preprocess_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "prl_preprocess_pack": (C.c_int, [C.POINTER(MbRecord), C.c_int32, C.c_int32, C.POINTER(MbColumns), C.c_void_p,
+                                      C.c_size_t, C.c_void_p]),
     "prl_sample_logprob_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64,
                                           C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "prl_advance_state": (C.c_int, [C.POINTER(EngineState), C.c_void_p]),

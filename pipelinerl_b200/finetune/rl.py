@@ -341,15 +341,26 @@ def populate_rl_data(dataset: list[dict[str, Any]], eos_token_id: int, config: R
         g_sum[g] = g_sum.get(g, 0) + tok
         g_cnt[g] = g_cnt.get(g, 0) + 1
 
-    step_vals: dict[tuple, list[float]] = {}
+    # pandas' groupby kernels, restated: `sum` is Kahan-compensated, `std` is Welford's recurrence with ddof = 1, both over
+    # the rows in dataset order (bit-identical doubles for any group size, tests/test_oracle_golden.py)
+    acc: dict[tuple, list] = {}
     for e in dataset:
-        step_vals.setdefault((e["group_id"], e["step_index"]), []).append(e["rewards"][0])
+        v = float(e["rewards"][0])
+        a = acc.setdefault((e["group_id"], e["step_index"]), [0.0, 0.0, 0, 0.0, 0.0])   # sum, comp, n, mean, m2
+        y = v - a[1]
+        t = a[0] + y
+        a[1] = t - a[0] - y
+        if a[1] != a[1]:
+            a[1] = 0.0
+        a[0] = t
+        a[2] += 1
+        old = a[3]
+        a[3] += (v - old) / a[2]
+        a[4] += (v - a[3]) * (v - old)
     step_stat = {}
-    for key, vals in step_vals.items():
-        arr = np.asarray(vals, dtype=np.float64)
-        total = float(arr.sum())
-        std = float(arr.std(ddof=1)) if arr.size > 1 else 0.0  # pandas gives NaN -> nan_to_num -> 0
-        step_stat[key] = (total, arr.size, 0.0 if math.isnan(std) else std)
+    for key, (total, _comp, cnt, _mean, m2) in acc.items():
+        std = math.sqrt(m2 / (cnt - 1)) if cnt > 1 else 0.0     # pandas gives NaN for one member -> nan_to_num -> 0
+        step_stat[key] = (total, cnt, 0.0 if math.isnan(std) else std)
 
     for e, ln in zip(dataset, lengths):
         total, cnt, std = step_stat[(e["group_id"], e["step_index"])]

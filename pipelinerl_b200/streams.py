@@ -75,6 +75,13 @@ def stream_file(directory: Path, shard_id: int) -> Path:
     return directory / f"{shard_id}.jsonl"
 
 
+def binary_file(directory: Path, shard_id: int) -> Path:
+    return directory / f"{shard_id}.bin"
+
+
+BIN_KEY = "__bin__"
+
+
 def _plain(obj: Any) -> Any:
     if isinstance(obj, BaseModel):
         return _plain(obj.model_dump())
@@ -109,13 +116,30 @@ class FileStreamWriter:
 
     def __exit__(self, *exc):
         self._file.close()
+        if getattr(self, "_bin", None) is not None:
+            self._bin.close()
 
     def write(self, data: Any, partition: int | None = None) -> None:
         if partition is not None:
             raise ValueError("a single-partition writer takes no partition argument")
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            data = self._write_binary(data)
         self._file.write(json.dumps(_plain(data), separators=(",", ":")))
         self._file.write("\n")
         self._file.flush()
+
+    def _write_binary(self, payload) -> dict:
+        """Binary records (records.py: packed micro-batches at 12-16 B/token instead of ~170 B/token of JSON) keep the
+        topic protocol -- one JSON document per line, same files -- by travelling in a sibling `0.bin`: the line is a
+        pointer {"__bin__": [offset, nbytes]} that the reader resolves back to `bytes`."""
+        if getattr(self, "_bin", None) is None:
+            d = stream_dir(self.stream.exp_path, self.stream.topic, self.stream.instance, self.stream.partition)
+            self._bin = open(binary_file(d, 0), "ab" if self.mode == "a" else "wb")
+        self._bin.seek(0, os.SEEK_END)
+        off = self._bin.tell()
+        self._bin.write(payload)
+        self._bin.flush()          # payload is on disk before the pointer line becomes visible
+        return {BIN_KEY: [off, len(payload)]}
 
 
 class RoundRobinFileStreamWriter:
@@ -162,9 +186,23 @@ class FileStreamReader:
 
     def __exit__(self, *exc):
         self._file.close()
+        if getattr(self, "_bin", None) is not None:
+            self._bin.close()
 
     def close(self) -> None:
         self._stop = True
+
+    def _resolve(self, doc: Any) -> Any:
+        if isinstance(doc, dict) and len(doc) == 1 and BIN_KEY in doc:
+            off, n = doc[BIN_KEY]
+            if getattr(self, "_bin", None) is None:
+                self._bin = open(binary_file(self._path.parent, 0), "rb")
+            self._bin.seek(off)
+            payload = self._bin.read(n)
+            if len(payload) != n:
+                raise IOError(f"binary record truncated: wanted {n} bytes at {off}, got {len(payload)}")
+            return payload
+        return doc
 
     def read(self) -> Iterator[Any]:
         """Blocking tail; a partially written last line is re-read after a short delay."""
@@ -172,7 +210,7 @@ class FileStreamReader:
         while not self._stop:
             line = self._file.readline()
             if line.endswith("\n"):
-                yield json.loads(line)
+                yield self._resolve(json.loads(line))
                 pos = self._file.tell()
             else:
                 self._file.seek(pos)
@@ -187,7 +225,7 @@ class FileStreamReader:
             if not line.endswith("\n"):
                 self._file.seek(pos)
                 return out
-            out.append(json.loads(line))
+            out.append(self._resolve(json.loads(line)))
             pos = self._file.tell()
 
 

@@ -239,6 +239,48 @@ def gen_preprocess_cases(ref_rl, ref_data, ref_utils):
     print("preprocess cases:", list(out))
 
 
+def gen_preprocess_large_cases(ref_rl, ref_data, ref_utils):
+    """Big groups (64 attempts, BASELINE config 5), real-valued rewards, two steps per rollout (multi-turn: several
+    samples share a rollout_index) and unfinished samples without finish_reason: exercises pandas' Kahan sum / Welford std
+    beyond what 4-member groups can, and the "eos in input_ids" overflow rule."""
+    out = {}
+    for name, cfgd, sp, group_sizes in [
+        ("group64_std", dict(divide_advantage_by_std=True), 1, [64, 33]),
+        ("group64_nostd_sp4", dict(divide_advantage_by_std=False), 4, [64, 7, 1]),
+    ]:
+        rng = np.random.default_rng(zlib.crc32(name.encode()) % 100000)
+        cfg = ref_rl.RLConfig(**cfgd)
+        samples = []
+        for g, size in enumerate(group_sizes):
+            prompt = rng.integers(8, 97, size=int(rng.integers(3, 9))).tolist()
+            for a in range(size):
+                for step in range(2 if (a % 5 == 0) else 1):         # some rollouts have two turns
+                    n_gen = int(rng.integers(2, 12))
+                    gen = rng.integers(8, 97, size=n_gen).tolist()
+                    fin = bool(rng.random() < 0.6)
+                    if fin or rng.random() < 0.3:
+                        gen[-1] = _Tok.eos_token_id
+                    s = {"input_ids": prompt + gen, "labels": [-100] * len(prompt) + gen,
+                         "logprobs": (-rng.random(n_gen) * 3).tolist(), "ref_logprobs": (-rng.random(n_gen) * 3).tolist(),
+                         "reward": float(rng.random() * 3.7 - 1.1) * (1e3 if g == 1 else 1.0),
+                         "group_id": f"g{g}", "rollout_index": a, "step_index": step, "finished": fin,
+                         "metadata": {"model_version": 5 + (a % 3)}}
+                    if a % 4 == 1:
+                        s["finish_reason"] = "length" if not fin else "stop"
+                    samples.append(s)
+        raw = copy.deepcopy(samples)
+        entries = preprocess_like_reference(ref_rl, ref_data, samples, cfg)
+        batch = ref_data.collate_packed(copy.deepcopy(entries), _Tok(), seq_parallel=sp)
+        cols = ["rewards", "advantages", "overflow", "group_tokens", "num_labels"]
+        out[name] = {"config": cfg.model_dump(), "seq_parallel": sp, "eos_token_id": _Tok.eos_token_id, "raw_samples": raw,
+                     "entry_scalars": [{k: e[k][0] for k in cols} for e in entries],
+                     "batch": {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in batch_to_np(batch).items()}}
+    import gzip
+    with gzip.open(OUT / "preprocess_cases_large.json.gz", "wt", compresslevel=9) as f:
+        f.write(json.dumps(out))
+    print("large preprocess cases:", {k: len(v["raw_samples"]) for k, v in out.items()})
+
+
 def gen_adamw_case():
     """torch.optim.AdamW with the decay groups of finetune/optim.py:8-22, 3 steps with clipping (finetune_loop.py:739)."""
     torch.manual_seed(5)
@@ -272,4 +314,5 @@ if __name__ == "__main__":
     ref_rl, ref_data, ref_utils = _import_reference()
     gen_rl_step_cases(ref_rl, ref_data, ref_utils)
     gen_preprocess_cases(ref_rl, ref_data, ref_utils)
+    gen_preprocess_large_cases(ref_rl, ref_data, ref_utils)
     gen_adamw_case()

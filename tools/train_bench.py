@@ -169,7 +169,7 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
            "libprl_launches_per_step": (_lib.launch_count() - launches0) // max(1, steps),
            "peak_memory_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1),
            "loss": rec[-1][4], "grad_norm": rec[-1][5], "grad_accumulation": "fp32 in the optimizer arena",
-           "attention": "torch SDPA (library)", "keep_attention_layers": model.body.keep_attention_layers,
+           "attention": "prl_attn_varlen_fwd / prl_attn_varlen_bwd (tcgen05, csrc/attn_tc.cu + csrc/attn_train.cu)", "keep_attention_layers": model.body.keep_attention_layers,
            "keep_gate_up_layers": model.body.keep_gate_up_layers,
            "gemm": "prl_gemm_ex (tcgen05 cta_group::2, MN-major dgrad/wgrad operands)"}
     del model, opt, batches
@@ -207,16 +207,20 @@ def main():
         dist.destroy_process_group()
 
 
-def check_dp():
-    """world ranks x 2 micro-batches through the sharded exchange  ==  one learner running all of them."""
+def check_dp(group=None, own_process_group=True):
+    """world ranks x 2 micro-batches through the sharded exchange  ==  one learner running all of them.
+    `own_process_group=False`: run inside an already initialised job on the ranks of `group` (bench.py's split run)."""
     import os
     import torch.distributed as dist
     from pipelinerl_b200.finetune.optim import ShardedFusedAdamW
-    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     dev = torch.device(f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}")
     torch.cuda.set_device(dev)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    if own_process_group:
+        world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+        if world > 1:
+            dist.init_process_group("nccl", device_id=dev)
+    else:
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
     cfg = ModelConfig(vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2, num_q_heads=4, num_kv_heads=2)
     micro, T = 2, 384
     rcfg = RLConfig(batch_size=micro * world * 2)
@@ -243,20 +247,22 @@ def check_dp():
     if world == 1:
         return {"ok": True, "world": 1, "note": "single process: nothing to compare"}
     got, gn, opt = run(lambda m: ShardedFusedAdamW(m.named_parameters(), lr=1e-3, weight_decay=0.01, max_grad_norm=0.3,
-                                                   grad_accum_fp32=True), all_batches[rank * micro:(rank + 1) * micro])
+                                                   grad_accum_fp32=True, group=group),
+                       all_batches[rank * micro:(rank + 1) * micro])
     same = (got == ref).float().mean().item()
     # one AdamW step moves a parameter by at most ~lr: a gradient whose sign flips under the bf16 exchange rounding
     # (near-zero gradients of zero-initialised biases) may differ by 2 lr; nothing may differ by more
     max_abs = (got.float() - ref.float()).abs().max().item()
     gathered = [torch.empty_like(got) for _ in range(world)]
-    dist.all_gather(gathered, got)
+    dist.all_gather(gathered, got, group=group)
     identical = all(torch.equal(g, gathered[0]) for g in gathered)
     ok = identical and same > 0.98 and max_abs <= 2.5e-3 + 2 ** -7 * ref.float().abs().max().item() and abs(gn - gn_ref) <= 1e-2 * gn_ref
     out = {"ok": bool(ok), "world": world, "ranks_bit_identical": bool(identical), "params_equal_to_single_learner": round(same, 5),
            "max_abs_diff": max_abs, "grad_norm": gn, "grad_norm_single": gn_ref}
-    dist.barrier()
+    dist.barrier(group=group)
     opt.close()
-    dist.destroy_process_group()
+    if own_process_group:
+        dist.destroy_process_group()
     return out if rank == 0 else {"ok": bool(ok), "world": world, "rank": rank, "max_abs_diff": max_abs, "grad_norm": gn}
 
 
