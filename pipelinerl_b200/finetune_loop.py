@@ -36,6 +36,7 @@ class TrainerConfig:
     lr_scheduler_type: str = "constant"
     num_warmup_steps: int = 0
     weight_update_interval: int = 1
+    eos_token_id: int = 2                  # only used by the GPU-resident preprocess ("eos in input_ids" overflow rule)
     rl: RLConfig = field(default_factory=RLConfig)
 
 
@@ -163,7 +164,16 @@ def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding
     rank = acct.rank
     step_stats, t_step = [], time.time()
     opt.zero_grad()
+    gpu_pre = None
     for batch in batches:
+        if isinstance(batch, (bytes, bytearray, memoryview)):
+            # binary micro-batch record (records.py): RL columns and the packed row are built ON THIS GPU
+            if gpu_pre is None:
+                from .records import GpuPreprocessor
+                gpu_pre = GpuPreprocessor(dev, cfg.eos_token_id, divide_advantage_by_std=cfg.rl.divide_advantage_by_std)
+            batch = gpu_pre.pack(batch)
+        elif isinstance(batch, dict):
+            batch = PipelineBatchEncoding.from_dict(batch)        # JSON documents of the stream (sentinels, legacy rows)
         batch = batch.to_device(dev)
         n_samples = 0 if batch.sentinel else (int(batch.seq_boundaries.numel()) - 1 - (1 if batch.padding else 0)
                                                if batch.is_packed else batch.input_ids.shape[0])

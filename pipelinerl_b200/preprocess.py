@@ -122,7 +122,10 @@ class MicroBatchDealer:
         self.max_model_version = 0
         self.steps_dealt = 0
 
-    def _emit(self, batch: PipelineBatchEncoding) -> None:
+    def _collate(self, entries: list[dict]):
+        return collate_packed(entries, self.tokenizer, self.seq_parallel, pin_memory=self.pin_memory)
+
+    def _emit(self, batch) -> None:
         if self.seq_parallel > 1:
             for index, piece in enumerate(batch.make_slices(self.seq_parallel)):
                 self.write(self.trainer_id + index, piece)
@@ -156,7 +159,7 @@ class MicroBatchDealer:
                         break
                 if time_to_write:
                     assert self.current_batch, "a sample longer than seq_length reached the writer"
-                    batch = collate_packed(self.current_batch, self.tokenizer, self.seq_parallel, pin_memory=self.pin_memory)
+                    batch = self._collate(self.current_batch)
                     n_samples = len(self.current_batch)
                     self.current_batch, self.current_length = [], 0
                     self._emit(batch)
@@ -172,3 +175,58 @@ class MicroBatchDealer:
                 if keep_going and queue:
                     batch_done = False
         return batch_done
+
+
+def record_entries(samples: list[dict[str, Any]], seq_length: int) -> list[dict[str, Any]]:
+    """Entries for `RecordDealer` from the TrainingText dicts of WHOLE groups (one `actor`-topic chunk): no per-token host
+    work -- each entry keeps the sample's own arrays plus a reference to the chunk's scalar table (reward, group / rollout /
+    step ids and length of EVERY sample of the chunk), which is all the GPU needs for the leave-one-out statistics.
+    Samples longer than `seq_length` are dropped after the table is built, as the reference drops them after
+    populate_rl_data (preprocess.py:178-186)."""
+    table = []
+    for s in samples:
+        meta = s.get("metadata", {})
+        table.append({"reward": s["reward"], "group_id": s["group_id"], "rollout_index": meta.get("rollout_index", 0),
+                      "step_index": meta.get("step_index", 0), "n_tok": len(s["input_ids"])})
+    out = []
+    for pos, s in enumerate(samples):
+        if len(s["input_ids"]) > seq_length:
+            continue
+        e = {"input_ids": s["input_ids"], "labels": s["labels"], "logprobs": s["logprobs"],
+             "finished": s.get("finished", False), "model_version": s.get("metadata", {}).get("model_version", 0),
+             "_chunk": table, "_chunk_pos": pos}
+        if s.get("ref_logprobs"):
+            e["ref_logprobs"] = s["ref_logprobs"]
+        if "finish_reason" in s:
+            e["finish_reason"] = s["finish_reason"]
+        out.append(e)
+    return out
+
+
+class RecordDealer(MicroBatchDealer):
+    """MicroBatchDealer whose micro-batches are binary records (records.py) instead of host tensors: the same dealing
+    rules (they only look at sample LENGTHS), but what is written to `training_data` is 12-16 bytes per token and the RL
+    columns are produced on the learner's GPU (records.GpuPreprocessor / csrc/preprocess_pack.cu).  Sentinel batches stay
+    the small JSON objects they are.  A micro-batch may mix samples of several chunks: its scalar table is the union of
+    theirs (group ids are unique across chunks, so the statistics keys stay disjoint)."""
+
+    def __init__(self, *a, use_ref_logprobs: bool = True, **kw):
+        super().__init__(*a, **kw)
+        if self.seq_parallel != 1:
+            raise NotImplementedError("binary records are not sliced across sequence-parallel ranks")
+        self.use_ref_logprobs = use_ref_logprobs
+
+    def _collate(self, entries: list[dict]):
+        from .records import encode_micro_batch_record
+        chunk: list[dict] = []
+        base: dict[int, int] = {}
+        pack = []
+        for e in entries:
+            table = e["_chunk"]
+            if id(table) not in base:
+                base[id(table)] = len(chunk)
+                chunk.extend(dict(row) for row in table)
+            i = base[id(table)] + e["_chunk_pos"]
+            chunk[i].update({k: v for k, v in e.items() if not k.startswith("_")})
+            pack.append(i)
+        return encode_micro_batch_record(chunk, pack, seq_parallel=1, use_ref_logprobs=self.use_ref_logprobs)

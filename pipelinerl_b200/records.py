@@ -64,7 +64,7 @@ def encode_micro_batch_record(chunk: Sequence[dict[str, Any]], pack: Sequence[in
         group_slot[i] = groups.setdefault(g, len(groups))
         stat_slot[i] = stats.setdefault((g, e.get("step_index", 0)), len(stats))
         rollout_slot[i] = rollouts.setdefault((g, e.get("rollout_index", 0)), len(rollouts))
-        n_tok_all[i] = len(e["input_ids"])
+        n_tok_all[i] = e["n_tok"] if "n_tok" in e else len(e["input_ids"])
     ids_parts, lab_parts, lp_parts, ref_parts = [], [], [], []
     tok_off = np.zeros(n_pack + 1, dtype=np.int32)
     lp_off = np.zeros(n_pack + 1, dtype=np.int32)

@@ -82,3 +82,44 @@ def test_no_clip_and_grad_scale(cuda_device):
     assert abs(norm.item() - (1000 ** 0.5)) < 1e-3
     # first Adam step moves by lr regardless of scale
     assert torch.allclose(p.detach(), torch.full_like(p, 1.0 - 1e-2), rtol=1e-5)
+
+
+def test_training_state_checkpoint_resume_is_bit_exact(cuda_device, tmp_path):
+    """save_training_state -> fresh optimizer -> load_training_checkpoint: the resumed run takes bit-identical steps
+    (reference: finetune/checkpoints.py:225-329; here three fp32 arenas in safetensors + a JSON)."""
+    from pipelinerl_b200.finetune.checkpoints import load_training_checkpoint, save_training_state
+    from pipelinerl_b200.finetune.optim import FusedAdamW, get_scheduler
+
+    def build():
+        torch.manual_seed(3)
+        ps = [torch.nn.Parameter(torch.randn(s, device=cuda_device)) for s in ((37, 16), (16,), (5, 7))]
+        names = ["a.weight", "a.bias", "b.weight"]
+        opt = FusedAdamW(zip(names, ps), lr=1e-2, weight_decay=0.01, max_grad_norm=0.5)
+        return ps, opt, get_scheduler("cosine", opt, 2, 10)
+
+    def grads(ps, k):
+        g = torch.Generator(device=cuda_device).manual_seed(100 + k)
+        for p in ps:
+            p.grad.copy_(torch.randn(p.shape, generator=g, device=cuda_device))
+    ps, opt, sch = build()
+    for k in range(3):
+        grads(ps, k)
+        opt.step()
+        sch.step()
+    save_training_state(tmp_path / "state", None, opt, sch, {"completed_steps": 3, "samples": 24})
+    for k in range(3, 5):
+        grads(ps, k)
+        opt.step()
+        sch.step()
+    want = opt.master.clone()
+    ps2, opt2, sch2 = build()
+    extra = load_training_checkpoint(tmp_path / "state", None, opt2, sch2)
+    assert extra == {"completed_steps": 3, "samples": 24} and opt2.step_count == 3 and sch2.last_step == 3
+    assert opt2.param_groups[0]["lr"] == pytest.approx(sch.base_lrs[0] * sch2.factor(3))
+    for k in range(3, 5):
+        grads(ps2, k)
+        opt2.step()
+        sch2.step()
+    torch.cuda.synchronize()
+    assert torch.equal(opt2.master, want) and torch.equal(opt2.exp_avg, opt.exp_avg)
+    assert torch.equal(opt2.shadow_bf16, opt.shadow_bf16)

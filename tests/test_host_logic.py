@@ -386,3 +386,30 @@ def test_micro_batch_dealer_matches_reference_writer_loop(name):
         per_rank[rank] = per_rank.get(rank, 0) + 1
     if dealer.trainer_id == 0:
         assert len(set(per_rank.values())) == 1
+
+
+# ---- f4: checkpoint / resume in safetensors ----
+def test_model_checkpoint_roundtrip_hf_names(tmp_path):
+    from pipelinerl_b200.finetune.checkpoints import load_model_weights, save_model_only
+    from pipelinerl_b200.model import fused_shapes
+    from tests.helpers import tiny_cfg, tiny_weights
+    cfg = tiny_cfg("gqa2")
+    w = {k: v.to(torch.bfloat16) for k, v in tiny_weights(cfg).items()}
+    save_model_only(tmp_path / "ckpt", cfg, w.items())
+    assert (tmp_path / "ckpt" / "model.safetensors").exists() and not (tmp_path / "ckpt~temp").exists()
+    cfgj = json.loads((tmp_path / "ckpt" / "config.json").read_text())
+    assert cfgj["num_key_value_heads"] == cfg.num_kv_heads and cfgj["model_type"] == "qwen2"
+    from safetensors.torch import load_file
+    sd = load_file(str(tmp_path / "ckpt" / "model.safetensors"))
+    assert "model.layers.0.self_attn.k_proj.weight" in sd and "model.layers.1.mlp.up_proj.weight" in sd
+    assert sd["model.layers.0.self_attn.k_proj.weight"].shape == (cfg.kv_size, cfg.hidden_size)
+    back = load_model_weights(tmp_path / "ckpt", cfg)
+    for name, _ in fused_shapes(cfg):
+        assert torch.equal(back[name], w[name]), name
+    # a second save swaps directories atomically and leaves no temp / old siblings behind
+    save_model_only(tmp_path / "ckpt", cfg, w.items())
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["ckpt"]
+    # HF's own Qwen2ForCausalLM opens the directory (what the reference's load_model does, checkpoints.py:151-222)
+    from transformers import AutoModelForCausalLM
+    m = AutoModelForCausalLM.from_pretrained(str(tmp_path / "ckpt"), torch_dtype=torch.bfloat16)
+    assert torch.equal(m.model.layers[1].mlp.down_proj.weight.data, w["layers.1.down_proj.weight"])

@@ -155,3 +155,57 @@ def test_gpu_preprocess_subset_pack_equals_host_path(cuda_device):
               "old_logprobs", "group_tokens", "num_labels", "overflow", "seq_boundaries"):
         assert torch.equal(getattr(got, k).cpu(), getattr(want, k)), k
     assert got.model_version == want.model_version and got.padding == want.padding
+
+
+@pytest.mark.gpu
+def test_record_dealer_on_gpu_equals_tensor_dealer_on_host(cuda_device):
+    """The same dealing rules with two transports: MicroBatchDealer (host tensors: populate_rl_data + collate_packed) and
+    RecordDealer (binary records -> GPU pack).  Every micro-batch, to every rank, must be identical bit for bit."""
+    from collections import deque
+
+    from pipelinerl_b200.preprocess import MicroBatchDealer, RecordDealer, preprocess_dataset, record_entries
+    rng = np.random.default_rng(7)
+    samples = []
+    for g in range(6):
+        prompt = rng.integers(8, 97, size=int(rng.integers(3, 9))).tolist()
+        for a in range(5):
+            n_gen = int(rng.integers(2, 14))
+            gen = rng.integers(8, 97, size=n_gen).tolist()
+            fin = bool(rng.random() < 0.5)
+            if fin:
+                gen[-1] = Tok.eos_token_id
+            samples.append({"input_ids": prompt + gen, "labels": [-100] * len(prompt) + gen,
+                            "logprobs": (-rng.random(n_gen) * 3).tolist(), "ref_logprobs": (-rng.random(n_gen) * 3).tolist(),
+                            "reward": float(rng.random() * 2 - 0.5), "group_id": f"g{g}", "finished": fin,
+                            "metadata": {"model_version": 3 + a % 2, "rollout_index": a, "step_index": 0}})
+    chunks = [samples[:15], samples[15:]]          # two chunks of whole groups (chunk_n_groups = 3)
+    rl = RLConfig(divide_advantage_by_std=True)
+    host_writes, gpu_writes = [], []
+    host = MicroBatchDealer(Tok(), 40, 2, 4, write=lambda r, b: host_writes.append((r, b)))
+    gpu = RecordDealer(Tok(), 40, 2, 4, write=lambda r, b: gpu_writes.append((r, b)))
+    hq, gq = deque(), deque()
+    for ch in chunks:
+        hq.extend(preprocess_dataset(copy.deepcopy(ch), Tok(), seq_length=40, rl_config=rl))
+        gq.extend(record_entries(copy.deepcopy(ch), seq_length=40))
+        for dealer, q in ((host, hq), (gpu, gq)):
+            while q:
+                before = (len(q), dealer.published_samples, dealer.trainer_id)
+                dealer.deal(q)
+                if (len(q), dealer.published_samples, dealer.trainer_id) == before:
+                    break
+    assert len(host_writes) == len(gpu_writes) and len(host_writes) >= 4
+    pre = GpuPreprocessor(cuda_device, Tok.eos_token_id, divide_advantage_by_std=True)
+    n_records = 0
+    for (hr, hb), (gr, gb) in zip(host_writes, gpu_writes):
+        assert hr == gr
+        if hb.sentinel:
+            assert gb.sentinel
+            continue
+        assert isinstance(gb, bytes)
+        n_records += 1
+        got = pre.pack(gb)
+        for k in ("input_ids", "labels", "attention_mask", "position_ids", "segment_ids", "rewards", "advantages",
+                  "ref_logprobs", "old_logprobs", "group_tokens", "num_labels", "overflow", "seq_boundaries"):
+            assert torch.equal(getattr(got, k).cpu(), getattr(hb, k)), k
+        assert got.model_version == hb.model_version
+    assert n_records >= 4
