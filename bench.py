@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="N >= 2: skip the inference + learner split run")
     ap.add_argument("--no-vllm", action="store_true", help="N = 1: skip the vLLM 0.22 A/B subprocess")
+    ap.add_argument("--no-rollout", action="store_true", help="N = 1: skip the full-rollout run through the plugin API")
+    ap.add_argument("--rollout-tokens", type=int, default=8192, help="max_tokens of the full-rollout component")
     ap.add_argument("--splits", default="", help="learner counts of the split runs, e.g. '2,4' (default: by N)")
     return ap.parse_args()
 
@@ -300,6 +302,14 @@ def run_ours(args):
             out["components"]["trainer_step"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, budget_s=25.0)
+    if rank == 0 and world == 1 and not args.no_components and not args.no_rollout:
+        # whole rollouts through the plugin API: prefill + decode growing 8192 -> 16384 (not a static-state microbench)
+        try:
+            sys.path.insert(0, str(ROOT / "tools"))
+            import rollout_bench
+            out["components"]["rollout_full"] = rollout_bench.measure(dev=dev, max_tokens=args.rollout_tokens)
+        except Exception as e:  # noqa: BLE001
+            out["components"]["rollout_full"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     if rank == 0 and world == 1 and not args.no_components and not args.no_vllm:
         out.setdefault("components", {})["vllm_baseline"] = vllm_baseline(args)
     if world > 1 and not args.no_components and not args.no_pipeline:

@@ -401,12 +401,18 @@ int prl_paged_attn_prefill_tc(const void* q_bf16 /*[q_rows,n_q,128]*/, int32_t q
 int prl_attn_varlen_fwd(const void* qkv_bf16, int64_t qkv_stride, int32_t T, const int32_t* seg_start,
                         const int32_t* seg_len, int32_t n_seg, int32_t max_seg_len, int32_t n_q, int32_t n_kv,
                         int32_t head_dim, float sm_scale, void* out_bf16, float* lse, prl_stream_t stream);
+/* which forward kernel prl_attn_varlen_fwd launches: 2 (default) = two ping-pong softmax groups, O accumulated in TMEM
+ * with conditional rescale; 1 = the first-generation kernel shared with chunked prefill.  For A/B runs and tests. */
+int prl_attn_set_fwd_generation(int32_t generation);
 size_t prl_attn_varlen_bwd_workspace_bytes(int32_t T, int32_t n_q);
 int prl_attn_varlen_bwd(const void* qkv_bf16, int64_t qkv_stride, int32_t T, const int32_t* seg_start,
                         const int32_t* seg_len, int32_t n_seg, int32_t max_seg_len, int32_t n_q, int32_t n_kv,
                         int32_t head_dim, float sm_scale, const void* out_bf16, const void* d_out_bf16,
                         const float* lse, void* dqkv_bf16, int64_t dqkv_stride, void* workspace,
                         size_t workspace_bytes, prl_stream_t stream);
+/* Measurement helper (tools/attn_bench.py --tmem): cycles for `warps` warps of every SM to read iters x 4 KB out of
+ * TMEM with tcgen05.ld.32x32b.x32; out3 = {cycles, bytes per SM, -}. */
+int prl_debug_tmem_read_bench(int32_t iters, int32_t warps, int64_t* out3_device, prl_stream_t stream);
 /* Sampling with in-kernel logprob capture: id ~ softmax(logits/T) (Gumbel-max, counter-based RNG on
  * (seed, step, row, vocab id)) or argmax when greedy; logprob = log_softmax(logits/T)[id]. */
 size_t prl_sample_workspace_bytes(int32_t B);

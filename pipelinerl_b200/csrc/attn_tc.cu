@@ -15,6 +15,7 @@
 // 2..9 = softmax / epilogue (two warps per TMEM lane quarter, each owning half of the keys / head-dim columns).
 //
 // Tensor-bound: 4 * 128 * S^2 / 2 FLOP per head (causal); K/V bytes are re-read from L2 by the other query tiles.
+#include <stdlib.h>
 #include "prl_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -310,6 +311,290 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   }
 }
 
+
+// =====================================================================================================
+// Forward, second generation: two softmax groups in ping-pong, O accumulated in TMEM.
+//
+// The first-generation kernel above reads every P V product back out of TMEM (64 KB per step on top of the 64 KB of S)
+// and runs its eight softmax warps in lock-step through  load S -> max -> exp -> store P -> fold O,  so the MUFU pipe,
+// the tensor pipe and the TMEM read port take turns instead of overlapping.  Here:
+//   * softmax group g (4 warps, ONE THREAD PER ROW, all 128 keys of a step in registers) owns the steps i = g (mod 2)
+//     with its own online-softmax state (reference exponent m_ref, row sum l) and its own accumulator O_g in TMEM:
+//     while group 0 exponentiates step i, group 1 loads / maximises / stores step i + 1 and the tensor core runs the
+//     Q K^T of step i + 2 and the P V of step i - 1.  The two partial results are merged once, at the end
+//     (a log-sum-exp merge, as for split-KV decode).
+//   * O_g is NEVER read inside the loop: P V accumulates into it (tcgen05.mma accumulate), and a row is rescaled in TMEM
+//     (tcgen05.ld / scale / tcgen05.st) only when its running maximum grew by more than 2^8 since the reference was
+//     set -- P stays below 256, exact in bf16's range, and for trained or random scores the rescale branch is taken in
+//     the first steps of a row only.
+// TMEM: S_0 | S_1 | O_0 | O_1 (4 x 128 columns).  Shared memory and the K/V cluster multicast are those of generation 1.
+// =====================================================================================================
+__device__ __forceinline__ void group_bar(int g) {
+  if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
+
+template <bool kContig>
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(200)
+attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, TcPrefillParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = base;                          // Q lo | Q hi
+  const uint32_t kv_smem = base + 2 * kTile16K;          // 2 stages x (K lo | K hi | V lo | V hi)
+  const uint32_t p_smem = kv_smem + 2 * kStageBytesT;    // P of group 0 | P of group 1  (keys 0..63 | keys 64..127 each)
+  const uint32_t bar_base = p_smem + 4 * kTile16K;
+  auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
+  // 0 q_full | 1,2 k_full | 3,4 k_empty | 5,6 s_full | 7,8 s_empty | 9,10 p_full | 11,12 o_full | 13,14 v_full | 15,16 v_empty
+  const uint32_t tmem_slot = bar(17);
+
+  const int qtile = kContig ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int kvh = blockIdx.y, z = blockIdx.z;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int q_len = p.seq_q_len[z];
+  const int pos0 = kContig ? 0 : p.seq_pos0[z];
+  if ((qtile & ~1) * p.nq >= q_len) return;              // uniform across the CLUSTER, before any barrier / TMEM use
+  const int t0 = qtile * p.nq;
+  const int row0 = p.seq_q_start[z] + t0;
+  const int pos_first = pos0 + t0;
+  const int n_valid = t0 >= q_len ? 0 : ((q_len - t0) < p.nq ? (q_len - t0) : p.nq);
+  const int pair_rows = ((qtile | 1) + 1) * p.nq;
+  const int kv_end = pos0 + (pair_rows < q_len ? pair_rows : q_len);
+  const int n_it = (kv_end + kKeys - 1) / kKeys;
+  const int last_page = (kv_end - 1) / kPageT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 17; ++i) ptx::mbar_init(bar(i), (i == 3 || i == 4 || i == 15 || i == 16) ? 2 : 1);
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+    ptx::prefetch_tensormap(&tm_q);
+    ptx::prefetch_tensormap(&tm_kv);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync();
+  ptx::tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer (as generation 1) =====
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(bar(0), (uint32_t)(2 * 128 * p.R * p.nq));
+      ptx::tma_load_3d(q_smem, &tm_q, 0, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
+      ptx::tma_load_3d(q_smem + kTile16K, &tm_q, 64, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
+      const int32_t* bt = kContig ? nullptr : p.block_table + (int64_t)p.seq_slot[z] * p.max_blocks;
+      const int seq_row0 = p.seq_q_start[z];
+      auto load_page = [&](int it, int kv, uint32_t full_bar, uint32_t empty_bar) {
+        const int s = it & 1;
+        const uint32_t ph = (uint32_t)((it >> 1) & 1);
+        ptx::mbar_wait(empty_bar + 8u * (uint32_t)s, ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(full_bar + 8u * (uint32_t)s, (uint32_t)(2 * kTile16K));
+        int pg = 2 * it + (int)rank;
+        if (pg > last_page) pg = last_page;
+        int row, c0;
+        if (kContig) {
+          row = seq_row0 + pg * kPageT;
+          c0 = (kv ? p.col_v : p.col_k) + kvh * kDT;
+        } else {
+          const int page = bt[pg];
+          row = (int)(((((int64_t)p.layer * 2 + kv) * p.n_pages + page) * p.n_kv + kvh) * kPageT);
+          c0 = 0;
+        }
+        const uint32_t dst = kv_smem + (uint32_t)(s * kStageBytesT + kv * 2 * kTile16K) + (uint32_t)(rank * 8192);
+        ptx::tma_load_2d_multicast(dst, &tm_kv, c0, row, full_bar + 8u * (uint32_t)s, 3, ptx::kEvictLast);
+        ptx::tma_load_2d_multicast(dst + kTile16K, &tm_kv, c0 + 64, row, full_bar + 8u * (uint32_t)s, 3, ptx::kEvictLast);
+      };
+      load_page(0, 0, bar(1), bar(3));
+      for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) load_page(it + 1, 0, bar(1), bar(3));
+        load_page(it, 1, bar(13), bar(15));
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = ptx::make_idesc_bf16_f32(128, kKeys);
+      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16_f32(128, kDT) | (1u << 16);  // B (= V) is MN-major
+      auto issue_qk = [&](int j) {
+        const int s = j & 1;
+        const uint32_t ph = (uint32_t)((j >> 1) & 1);
+        ptx::mbar_wait(bar(1 + s), ph);          // K of step j landed
+        ptx::mbar_wait(bar(7 + s), ph ^ 1u);     // S_s drained by group s (step j - 2)
+        ptx::tc_fence_after_sync();
+        const uint32_t k_addr = kv_smem + (uint32_t)(s * kStageBytesT);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t a = ptx::make_kmajor_sw128_desc(q_smem + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
+          const uint64_t b = ptx::make_kmajor_sw128_desc(k_addr + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
+          ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 128), a, b, idesc_qk, ks > 0 ? 1u : 0u);
+        }
+        ptx::tc_commit(bar(5 + s));
+        ptx::tc_commit_multicast(bar(3 + s), 3);
+      };
+      ptx::mbar_wait(bar(0), 0);
+      issue_qk(0);
+      for (int i = 0; i < n_it; ++i) {
+        if (i + 1 < n_it) issue_qk(i + 1);
+        const int s = i & 1;
+        const uint32_t ph = (uint32_t)((i >> 1) & 1);
+        ptx::mbar_wait(bar(9 + s), ph);              // P_s of step i stored (and O_s rescaled if it had to be)
+        ptx::mbar_wait(bar(13 + s), ph);             // V of step i landed
+        ptx::tc_fence_after_sync();
+        const uint32_t v_addr = kv_smem + (uint32_t)(s * kStageBytesT) + 2 * kTile16K;
+        const uint32_t p_addr = p_smem + (uint32_t)(s * 2 * kTile16K);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t a = ptx::make_kmajor_sw128_desc(p_addr + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
+          const uint64_t b = ptx::make_mnmajor_sw128_desc(v_addr, kTile16K) + (uint64_t)(128 * ks);
+          ptx::mma_bf16_ss(tmem_base + (uint32_t)(256 + s * 128), a, b, idesc_pv, (i >= 2 || ks > 0) ? 1u : 0u);
+        }
+        ptx::tc_commit(bar(11 + s));                 // O_s updated, P_s free again
+        ptx::tc_commit_multicast(bar(15 + s), 3);    // V slot consumed: tell BOTH producers
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== softmax: group g = steps i = g (mod 2); one thread per (token, head) row =====
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int qi = m / p.R, r = m - qi * p.R;
+    const int qpos = pos_first + qi;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t s_addr = lane_addr + (uint32_t)(g * 128);
+    const uint32_t o_addr = lane_addr + (uint32_t)(256 + g * 128);
+    const uint32_t p_row = p_smem + (uint32_t)(g * 2 * kTile16K + m * 128);
+    const bool leader = (threadIdx.x == 64 + g * 128);
+    float2* xchg = reinterpret_cast<float2*>(smem_raw + (bar_base - ptx::smem_u32(smem_raw)) + 8 * 18);  // [128] (m_ref, l) of group 1
+    float m_ref = 0.f, l_run = 0.f;
+
+    for (int i = g; i < n_it; i += 2) {
+      const int j = i >> 1;
+      ptx::mbar_wait(bar(5 + g), (uint32_t)(j & 1));
+      ptx::tc_fence_after_sync();
+      float sv[128];
+      {
+        uint32_t su[128];                                   // four 32-column reads in flight, one wait
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          ptx::tmem_ld_32x32b_x32(s_addr + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&su[c * 32]));
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 128; ++e) sv[e] = __uint_as_float(su[e]);
+      }
+      ptx::tc_fence_before_sync();
+      group_bar(g);                                         // the whole S_g tile is in registers
+      if (leader) ptx::mbar_arrive(bar(7 + g));             // -> Q K^T of step i + 2 may overwrite S_g
+      if (i * kKeys + kKeys - 1 > pos_first) {              // some (row, key) of this step is causally masked
+        const int key0 = i * kKeys;
+#pragma unroll
+        for (int e = 0; e < 128; ++e)
+          if (key0 + e > qpos) sv[e] = -INFINITY;
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 128; ++e) mx = fmaxf(mx, sv[e]);
+      const float m_new = mx * p.scale_log2;                // scale > 0: max commutes with the scaling
+      if (j == 0) {
+        m_ref = (m_new == -INFINITY) ? 0.f : m_new;
+      } else {
+        ptx::mbar_wait(bar(11 + g), (uint32_t)((j - 1) & 1));   // P V of step i - 2 done: P_g free, O_g up to date
+        const bool need = m_new > m_ref + 8.f;              // rows of a warp decide together (TMEM ops are warp-wide)
+        if (__any_sync(0xffffffffu, need)) {
+          ptx::tc_fence_after_sync();
+          const float f = need ? ex2(m_ref - m_new) : 1.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(o_addr + (uint32_t)(c * 32), v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * f);
+            ptx::tmem_st_32x32b_x32(o_addr + (uint32_t)(c * 32), v);
+          }
+          ptx::tmem_st_wait();
+          l_run *= f;
+          if (need) m_ref = m_new;
+        }
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float pe[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          pe[e] = ex2(fmaf(sv[c * 8 + e], p.scale_log2, -m_ref));   // masked entries: exp2(-inf) = 0
+          sum += pe[e];
+        }
+        st_shared_v4(p_row + (uint32_t)((c >> 3) * kTile16K) + (((uint32_t)(c & 7) ^ (uint32_t)(m & 7)) << 4),
+                     pack2(pe[0], pe[1]), pack2(pe[2], pe[3]), pack2(pe[4], pe[5]), pack2(pe[6], pe[7]));
+      }
+      l_run += sum;
+      ptx::fence_proxy_async();                             // generic-proxy stores of P -> visible to the UMMA reads
+      ptx::tc_fence_before_sync();
+      group_bar(g);
+      if (leader) ptx::mbar_arrive(bar(9 + g));             // P_g ready -> P V of step i
+    }
+
+    // ---- merge the two groups' partial results and write the output rows (group 0) ----
+    const int n1 = n_it >> 1;                               // steps of group 1
+    if (g == 1) xchg[m] = make_float2(m_ref, l_run);
+    asm volatile("bar.sync 3, 256;" ::: "memory");
+    if (g == 0) {
+      const int n0 = (n_it + 1) >> 1;
+      ptx::mbar_wait(bar(11), (uint32_t)((n0 - 1) & 1));
+      if (n1 > 0) ptx::mbar_wait(bar(12), (uint32_t)((n1 - 1) & 1));
+      ptx::tc_fence_after_sync();
+      float m1 = 0.f, l1 = 0.f;
+      if (n1 > 0) { const float2 x = xchg[m]; m1 = x.x; l1 = x.y; }
+      const bool use1 = n1 > 0 && l1 > 0.f;
+      const bool use0 = l_run > 0.f;
+      const float m_all = use0 ? (use1 ? fmaxf(m_ref, m1) : m_ref) : m1;
+      const float f0 = use0 ? ex2(m_ref - m_all) : 0.f;
+      const float f1 = use1 ? ex2(m1 - m_all) : 0.f;
+      const float l_tot = f0 * l_run + f1 * l1;
+      const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+      const bool valid = qi < n_valid && qi < p.nq;
+      __nv_bfloat16* dst = p.out + ((int64_t)(row0 + qi) * p.n_q + (kvh * p.R + r)) * kDT;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t a[32], b[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(256 + c * 32), a);
+        if (n1 > 0) ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(384 + c * 32), b);
+        ptx::tmem_ld_wait();
+        if (valid) {
+          const float w0 = f0 * inv, w1 = f1 * inv;
+#pragma unroll
+          for (int d = 0; d < 32; d += 8) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              o[e] = __uint_as_float(a[d + e]) * w0;
+              if (n1 > 0) o[e] = fmaf(use1 ? __uint_as_float(b[d + e]) : 0.f, w1, o[e]);
+            }
+            uint4 u;
+            u.x = pack2(o[0], o[1]); u.y = pack2(o[2], o[3]); u.z = pack2(o[4], o[5]); u.w = pack2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(dst + c * 32 + d) = u;
+          }
+        }
+      }
+      if (kContig && valid && p.lse != nullptr)
+        p.lse[(int64_t)(row0 + qi) * p.n_q + (kvh * p.R + r)] = m_all + log2f(l_tot);
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 }  // namespace prl
 
@@ -352,6 +637,14 @@ extern "C" int prl_paged_attn_prefill_tc(const void* q, int32_t q_rows, const vo
 }
 
 
+namespace prl { namespace { int g_fwd_generation = [] { const char* e = getenv("PRL_ATTN_FWD"); return (e && e[0] == '1') ? 1 : 2; }(); } }
+
+extern "C" int prl_attn_set_fwd_generation(int32_t gen) {
+  PRL_CHECK_ARG(gen == 1 || gen == 2, "prl_attn_set_fwd_generation: 1 (lock-step softmax, O folded in registers) or 2 (ping-pong, O in TMEM)");
+  prl::g_fwd_generation = gen;
+  return PRL_OK;
+}
+
 // Learner forward (hot path 2): block-diagonal causal attention over ONE packed row, the varlen flash-attention call
 // the reference makes through HF (pipelinerl/finetune/rl/__init__.py:204 with packed position_ids,
 // conf/finetune/base.yaml:12-13,64).  qkv: [T, qkv_stride] bf16 = [q heads | k heads | v heads], q / k already roped.
@@ -379,10 +672,16 @@ extern "C" int prl_attn_varlen_fwd(const void* qkv, int64_t qkv_stride, int32_t 
                          (uint32_t)p.nq);
   if (rc) return rc;
   const int smem = 2 * kTile16K + 2 * kStageBytesT + 4 * kTile16K + 1024 + 8 * 20 + 2 * 128 * 4 + 16;
-  static SmemAttr smem_attr = {};
-  PRL_CUDA(ensure_smem(attn_prefill_tc_kernel<true>, smem, smem_attr));
   dim3 grid((unsigned)(((max_seg_len + p.nq - 1) / p.nq + 1) & ~1), (unsigned)n_kv, (unsigned)n_seg);
-  attn_prefill_tc_kernel<true><<<grid, kThreadsT, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
+  if (g_fwd_generation == 1) {      // A/B and tests only (prl_attn_set_fwd_generation)
+    static SmemAttr smem_attr = {};
+    PRL_CUDA(ensure_smem(attn_prefill_tc_kernel<true>, smem, smem_attr));
+    attn_prefill_tc_kernel<true><<<grid, kThreadsT, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
+  } else {
+    static SmemAttr smem_attr2 = {};
+    PRL_CUDA(ensure_smem(attn_fwd_v2_kernel<true>, smem, smem_attr2));
+    attn_fwd_v2_kernel<true><<<grid, kThreadsT, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
+  }
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }

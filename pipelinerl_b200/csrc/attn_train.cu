@@ -642,3 +642,49 @@ extern "C" int prl_attn_varlen_bwd(const void* qkv, int64_t qkv_stride, int32_t 
   }
   return PRL_OK;
 }
+
+// ---- measurement helper: TMEM read bandwidth of one SM (tcgen05.ld 32x32b.x32 from `warps` warps) -----------------
+// The attention kernels read every S / dP / O^T tile out of TMEM once per step; whether that costs 256 or 1024 cycles per
+// 64 KB tile decides their structure (profiles/r2_attention.md).  out[0] = cycles, out[1] = bytes read.
+namespace prl { namespace {
+__global__ void __launch_bounds__(256, 1) tmem_read_bench_kernel(int iters, int warps, long long* out) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) { ptx::tmem_alloc(ptx::smem_u32(&slot), 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t base = slot + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  if (warp < warps) {
+    for (int i = 0; i < iters; i += 4) {          // four 4 KB reads in flight per warp, one wait
+      uint32_t v0[32], v1[32], v2[32], v3[32];
+      const uint32_t c = (uint32_t)(((i >> 2) * 128) & 511);
+      ptx::tmem_ld_32x32b_x32(base + ((c + 0) & 511), v0);
+      ptx::tmem_ld_32x32b_x32(base + ((c + 32) & 511), v1);
+      ptx::tmem_ld_32x32b_x32(base + ((c + 64) & 511), v2);
+      ptx::tmem_ld_32x32b_x32(base + ((c + 96) & 511), v3);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) acc ^= v0[e] ^ v1[e] ^ v2[e] ^ v3[e];
+    }
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = t1 - t0; out[1] = (long long)iters * warps * 32 * 32 * 4; }
+  if (acc == 0x12345u) out[2] = acc;     // keep the loads alive
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) { ptx::tc_fence_after_sync(); ptx::tmem_dealloc(slot, 512); }
+}
+} }
+
+extern "C" int prl_debug_tmem_read_bench(int32_t iters, int32_t warps, int64_t* out3_device, prl_stream_t stream_) {
+  PRL_CHECK_ARG(out3_device && iters >= 1 && warps >= 1 && warps <= 8, "prl_debug_tmem_read_bench: bad argument");
+  prl::tmem_read_bench_kernel<<<(unsigned)prl::num_sms(), 256, 0, (cudaStream_t)stream_>>>((int)iters, (int)warps,
+                                                                                            (long long*)out3_device);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}

@@ -137,6 +137,7 @@ class DecodeEngine:
         self._page_pending: dict[int, tuple[Request, int]] = {}       # page -> (request that fills it, tokens needed)
         self._pf = None                                # lazily allocated prefill buffers
         self.stats = {"prefill_tokens": 0, "prefix_hits": 0, "prefix_hit_tokens": 0}
+        self.profile_timing = False                    # benches: wall time spent inside run_prefill (costs two syncs per call)
         self._next_id = 0
         self._state = self._make_state()
 
@@ -286,7 +287,15 @@ class DecodeEngine:
         """One token for every active slot.  The model part is replayed from a CUDA graph; sampling and
         state advance are launched per step (they take the step counter as an RNG argument)."""
         if self._prefill_queue:
-            self.run_prefill()
+            if self.profile_timing:
+                import time
+                torch.cuda.current_stream().synchronize()
+                t0 = time.perf_counter()
+                self.run_prefill()
+                torch.cuda.current_stream().synchronize()
+                self.stats["prefill_s"] = self.stats.get("prefill_s", 0.0) + time.perf_counter() - t0
+            else:
+                self.run_prefill()
         if self.use_graph:
             key = self.arena.data.data_ptr()
             g = self._graphs.get(key)

@@ -51,8 +51,10 @@ def _reference(qkv, d_out, bounds, n_q, n_kv):
     return out, dqkv
 
 
-def _run(dev, n_q, n_kv, lens, seed=0, pad_cols=0):
+def _run(dev, n_q, n_kv, lens, seed=0, pad_cols=0, fwd_gen=2):
+    from pipelinerl_b200 import _lib
     o = _ops()
+    _lib.check(o.lib.prl_attn_set_fwd_generation(fwd_gen))
     T = sum(lens)
     g = torch.Generator(device=dev).manual_seed(seed)
     width = (n_q + 2 * n_kv) * D
@@ -83,8 +85,10 @@ def _run(dev, n_q, n_kv, lens, seed=0, pad_cols=0):
     res["lse"] = (lse[s0:e0, 0] - want_lse).abs().max().item()
     qe, ke = n_q * D, (n_q + n_kv) * D
     for name, a, b in (("dq", 0, qe), ("dk", qe, ke), ("dv", ke, width)):
-        res[name] = ((dqkv[:, a:b].float() - want_d[:, a:b]).abs().max().item() / want_d[:, a:b].abs().max().item())
-    print(f"[attn_train] n_q={n_q} n_kv={n_kv} lens={lens if len(lens) < 8 else str(lens[:6]) + '...'}: " +
+        scale = max(want_d[:, a:b].abs().max().item(), 1e-3)      # a single-token segment has dq = dk = 0 exactly
+        res[name] = (dqkv[:, a:b].float() - want_d[:, a:b]).abs().max().item() / scale
+    _lib.check(o.lib.prl_attn_set_fwd_generation(2))
+    print(f"[attn_train gen{fwd_gen}] n_q={n_q} n_kv={n_kv} lens={lens if len(lens) < 8 else str(lens[:6]) + '...'}: " +
           " ".join(f"{k}={v:.2e}" for k, v in res.items()))
     assert res["out"] <= 2 ** -7, res
     assert res["lse"] <= 2e-3, res
@@ -105,8 +109,9 @@ def _run(dev, n_q, n_kv, lens, seed=0, pad_cols=0):
     (16, 1, [96, 33]),
     (28, 4, [511, 1, 700]),
 ])
-def test_varlen_attention_small(cuda_device, n_q, n_kv, lens):
-    _run(cuda_device, n_q, n_kv, lens, seed=len(lens) * 131 + n_q)
+@pytest.mark.parametrize("fwd_gen", [1, 2])
+def test_varlen_attention_small(cuda_device, n_q, n_kv, lens, fwd_gen):
+    _run(cuda_device, n_q, n_kv, lens, seed=len(lens) * 131 + n_q, fwd_gen=fwd_gen)
 
 
 def test_varlen_attention_padded_row_stride(cuda_device):
@@ -118,10 +123,10 @@ def test_varlen_attention_qwen7b_heads_medium(cuda_device, lens):
     _run(cuda_device, 28, 4, lens, seed=11)
 
 
-@pytest.mark.parametrize("lens", [[16384], [8192, 8192], [5000, 11000, 384]])
-def test_varlen_attention_qwen7b_heads_16k(cuda_device, lens):
+@pytest.mark.parametrize("lens,fwd_gen", [([16384], 2), ([8192, 8192], 2), ([5000, 11000, 384], 2), ([16384], 1)])
+def test_varlen_attention_qwen7b_heads_16k(cuda_device, lens, fwd_gen):
     """the trainer's micro-batch size (16 384 packed tokens) at Qwen2.5-7B's 28 / 4 heads"""
-    _run(cuda_device, 28, 4, lens, seed=5)
+    _run(cuda_device, 28, 4, lens, seed=5, fwd_gen=fwd_gen)
 
 
 def test_attention_output_rows_outside_every_segment_are_untouched(cuda_device):

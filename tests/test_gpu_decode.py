@@ -354,3 +354,29 @@ def test_engine_matches_vllm_golden(cuda_device, kind):
 
 # 1.5 x the measured difference to vLLM 0.22 bf16 (filled in when the golden was recorded; see the test's print)
 VLLM_BOUNDS = {"gqa2": (3e-2, 6e-3), "gqa7": (3e-2, 6e-3)}
+
+
+def test_one_layer_qwen7b_width_decode_step_vs_oracle(cuda_device):
+    """One transformer layer at Qwen2.5-7B's real widths (H 3584, I 18944, 28 q / 4 kv heads, qkv bias) through the
+    decode step (tcgen05 split-K GEMMs, RoPE + KV write, paged attention, residual RMSNorm, SiLU, fp32-equivalent head)
+    against the oracle on identical bf16-valued weights and the same rounding points: with a single layer there is no
+    chain of bf16 re-roundings to amplify summation-order noise, so the north star's 1e-3 relative bar applies."""
+    from dataclasses import replace
+    from pipelinerl_b200.engine import SamplingParams
+    from pipelinerl_b200.model import ModelConfig
+    cfg = replace(ModelConfig.qwen2_5_7b(), num_layers=1, vocab_size=4096)
+    w = tiny_weights(cfg, std=0.02, bias_std=0.1)
+    eng = make_engine(cfg, w, cuda_device, max_batch=4, max_seq_len=128, max_new_tokens=4, use_cuda_graph=False,
+                      prefill_chunk=0, fused_head=False)
+    g = torch.Generator().manual_seed(5)
+    tokens = torch.randint(0, cfg.vocab_size, (48,), generator=g).tolist()
+    eng.add_request(tokens, SamplingParams(max_tokens=2, temperature=1.0, greedy=True))
+    got = []
+    for t in range(len(tokens) - 1):
+        eng.step()
+        got.append(torch.log_softmax(eng.logits[0], -1)[tokens[t + 1]].item())
+    got = np.array(got)
+    want = OracleQwen2(cfg, w).score(tokens, 1.0).numpy()
+    rel = np.abs(got - want) / np.abs(want)
+    print(f"[7B-width one layer] max rel |dlogprob| {rel.max():.2e}  mean {rel.mean():.2e}  (|logprob| ~ {np.abs(want).mean():.2f})")
+    assert rel.max() <= 1e-3, (rel.max(), int(rel.argmax()))

@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--n-q", type=int, default=28)
     ap.add_argument("--n-kv", type=int, default=4)
     ap.add_argument("--no-library", action="store_true")
+    ap.add_argument("--tmem", action="store_true", help="TMEM read bandwidth microbenchmark")
+    ap.add_argument("--profile", action="store_true", help="per-kernel device time (torch profiler)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     o = Ops()
@@ -49,11 +51,17 @@ def main():
     d_out = torch.randn(T, n_q * D, generator=g, device=dev).to(torch.bfloat16)
     st = torch.arange(0, T, L, dtype=torch.int32, device=dev)
     ln = torch.tensor(lens, dtype=torch.int32, device=dev)
+    from pipelinerl_b200 import _lib as _l
+    _l.check(o.lib.prl_attn_set_fwd_generation(1))
+    out1, _ = o.attn_fwd(qkv, st, ln, L, n_q, n_kv, D)
+    fwd1_ms = timed(lambda: o.attn_fwd(qkv, st, ln, L, n_q, n_kv, D), a.reps)
+    _l.check(o.lib.prl_attn_set_fwd_generation(2))
     out, lse = o.attn_fwd(qkv, st, ln, L, n_q, n_kv, D)
     fwd_ms = timed(lambda: o.attn_fwd(qkv, st, ln, L, n_q, n_kv, D), a.reps)
     bwd_ms = timed(lambda: o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D), a.reps)
     flops_fwd = a.segments * n_q * 4 * D * L * L / 2
     res = {"bench": "learner_attention", "tokens": T, "segments": a.segments, "n_q": n_q, "n_kv": n_kv,
+           "fwd_gen1_ms": round(fwd1_ms, 3), "gen1_vs_gen2_max_abs_diff": (out1.float() - out.float()).abs().max().item(),
            "ours": {"fwd_ms": round(fwd_ms, 3), "bwd_ms": round(bwd_ms, 3),
                     "fwd_TFLOPs": round(flops_fwd / fwd_ms / 1e9, 1), "bwd_TFLOPs": round(2.5 * flops_fwd / bwd_ms / 1e9, 1)}}
     if not a.no_library:
@@ -72,6 +80,25 @@ def main():
                                "bwd_TFLOPs": round(2.5 * flops_fwd / lb / 1e9, 1)}
         err = (y.transpose(1, 2).reshape(T, n_q * D).float() - out.float()).abs().max().item()
         res["max_abs_diff_vs_library_out"] = err
+    if a.tmem:
+        from pipelinerl_b200 import _lib
+        lib = _lib.load()
+        o3 = torch.zeros(3, dtype=torch.int64, device=dev)
+        res["tmem_read_bytes_per_clk_per_sm"] = {}
+        for w in (1, 2, 4, 8):
+            _lib.check(lib.prl_debug_tmem_read_bench(4096, w, o3.data_ptr(), _lib.stream_ptr()))
+            torch.cuda.synchronize()
+            cyc, nbytes = int(o3[0]), int(o3[1])
+            res["tmem_read_bytes_per_clk_per_sm"][f"{w}_warps"] = round(nbytes / cyc, 1)
+    if a.profile:
+        from torch.profiler import ProfilerActivity, profile as tprofile
+        with tprofile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                o.attn_fwd(qkv, st, ln, L, n_q, n_kv, D)
+                o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D)
+            torch.cuda.synchronize()
+        res["kernels_us"] = {e.key.split("(")[0][-48:]: round(e.device_time_total / e.count, 1) for e in prof.key_averages()
+                             if e.device_time_total > 0}
     print(json.dumps(res), flush=True)
 
 
