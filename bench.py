@@ -346,7 +346,7 @@ def run_pipeline_splits(args, world, rank, headline):
     splits = [m for m in splits if 1 <= m < world]
     results = {"note": "samplers generate (64 seqs x 8192-token context each) WHILE the learners train 2 x 16384-token "
                        "micro-batches per learner per optimizer step and push weights after every step; "
-                       "sampler lm_head bf16 in this component (arena layout shared with the learner)"}
+                       "fp32-equivalent lm_head on samplers and learners"}
     deadline_s = 330.0 * len(splits)
 
     def bail():

@@ -184,6 +184,12 @@ size_t prl_adamw_workspace_bytes(void);
 int prl_adamw_step(const prl_adamw_args* args, float* grad_norm_out,
                    void* workspace, size_t workspace_bytes, prl_stream_t stream);
 
+/* lo = bf16(master - float(bf16(master))) for n elements, stored to n_dst (<= 8) destinations (own arena tail and, under
+ * data parallelism, the peers' over NVLink).  With hi = bf16(master) (the ordinary bf16 parameter) the pair is the
+ * fp32-equivalent lm_head the reference computes on both sides (vllm_quantization.py:266-278, checkpoints.py:44-105):
+ * prl_head_logprob / prl_gemm_bf16_splitk take (W, W_lo) as two bf16 operand streams into one fp32 accumulation. */
+int prl_bf16_residual(const float* master, int64_t n, void* const* lo_dsts, int32_t n_dst, prl_stream_t stream);
+
 /* Learner data parallelism as one fused exchange step over NVLink peer memory (replaces the gradient all-reduce
  * + per-rank full optimizer of finetune_loop.py:716-755): rank r owns elements [shard_begin, shard_end) of the
  * arena and ONLY that shard of fp32 master / exp_avg / exp_avg_sq (optimizer state sharded n_peers ways).

@@ -444,3 +444,48 @@ extern "C" int prl_adamw_sharded_update(const prl_adamw_shard_args* a, float* gr
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }
+
+
+// ---- bf16 residual of an fp32 master tensor: lo = bf16(master - float(bf16(master))) -------------------------------------
+// The lm_head is computed in fp32 on both sides of the reference (vllm_quantization.py:266-278, finetune/checkpoints.py:44-105).
+// Here the head weight travels as TWO bf16 operand streams, hi = bf16(master) (the ordinary bf16 parameter) and this
+// residual; hi + lo carries 16 mantissa bits, the tensor core accumulates both in fp32.  Written into up to 8 destinations
+// (every data-parallel learner's arena tail, over NVLink peer memory), 16-byte stores.
+namespace prl { namespace {
+struct ResidualDsts { __nv_bfloat16* p[8]; };
+__global__ void __launch_bounds__(256) bf16_residual_kernel(const float* __restrict__ master, int64_t n, ResidualDsts d, int n_dst) {
+  const int64_t i8 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i8 >= n) return;
+  if (i8 + 8 <= n) {
+    const float4 a = ld_stream_f4(reinterpret_cast<const float4*>(master + i8));
+    const float4 b = ld_stream_f4(reinterpret_cast<const float4*>(master + i8 + 4));
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float h0 = __bfloat162float(__float2bfloat16_rn(v[2 * k])), h1 = __bfloat162float(__float2bfloat16_rn(v[2 * k + 1]));
+      w[k] = float_to_bf16_bits(v[2 * k] - h0) | (float_to_bf16_bits(v[2 * k + 1] - h1) << 16);
+    }
+    for (int t = 0; t < n_dst; ++t) st_stream_u4(reinterpret_cast<uint4*>(d.p[t] + i8), make_uint4(w[0], w[1], w[2], w[3]));
+  } else {
+    for (int64_t i = i8; i < n; ++i) {
+      const float h = __bfloat162float(__float2bfloat16_rn(master[i]));
+      for (int t = 0; t < n_dst; ++t) d.p[t][i] = __float2bfloat16_rn(master[i] - h);
+    }
+  }
+}
+} }
+
+extern "C" int prl_bf16_residual(const float* master, int64_t n, void* const* lo_dsts, int32_t n_dst, prl_stream_t stream_) {
+  PRL_CHECK_ARG(master && lo_dsts && n >= 1 && n_dst >= 1 && n_dst <= 8, "prl_bf16_residual: bad argument");
+  PRL_CHECK_ARG((uintptr_t)master % 16 == 0, "prl_bf16_residual: master must be 16-byte aligned");
+  prl::ResidualDsts d = {};
+  for (int t = 0; t < n_dst; ++t) {
+    PRL_CHECK_ARG(lo_dsts[t] && (uintptr_t)lo_dsts[t] % 16 == 0, "prl_bf16_residual: destinations must be 16-byte aligned");
+    d.p[t] = (__nv_bfloat16*)lo_dsts[t];
+  }
+  const int64_t threads = (n + 7) / 8;
+  prl::bf16_residual_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(master, n, d, (int)n_dst);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}

@@ -335,7 +335,7 @@ __device__ __forceinline__ void group_bar(int g) {
 }
 
 template <bool kContig>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(200)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1)   // 10 warps: 3 share one SMSP -> 168 registers
 attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, TcPrefillParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -507,14 +507,14 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (__any_sync(0xffffffffu, need)) {
           ptx::tc_fence_after_sync();
           const float f = need ? ex2(m_ref - m_new) : 1.f;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            ptx::tmem_ld_32x32b_x32(o_addr + (uint32_t)(c * 32), v);
+#pragma unroll 1
+          for (int c = 0; c < 8; ++c) {                     // rare path: small chunks keep the S row in registers
+            uint32_t v[16];
+            ptx::tmem_ld_32x32b_x16(o_addr + (uint32_t)(c * 16), v);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * f);
-            ptx::tmem_st_32x32b_x32(o_addr + (uint32_t)(c * 32), v);
+            for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * f);
+            ptx::tmem_st_32x32b_x16(o_addr + (uint32_t)(c * 16), v);
           }
           ptx::tmem_st_wait();
           l_run *= f;

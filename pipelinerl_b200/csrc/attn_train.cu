@@ -254,38 +254,47 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       ptx::tc_fence_after_sync();
       uint32_t sv[32], dv[32];
       ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(s * 64 + c0), sv);
-      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(128 + s * 64 + c0), dv);
       ptx::tmem_ld_wait();
+      // the dP^T read is issued now and completes under the exponentials: the TMEM read port and the MUFU pipe are the
+      // two longest phases of a step and must not take turns
+      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(128 + s * 64 + c0), dv);
+      const float* mb = meta + (it & 1) * 192;
+      const bool diag = u * nqa < key0 + 127;                  // some (key, query) of this step is causally masked
+      float pe[32];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 l0 = *reinterpret_cast<const float4*>(mb + c0 + j);
+        pe[j + 0] = ex2f(fmaf(__uint_as_float(sv[j + 0]), p.scale_log2, -l0.x));
+        pe[j + 1] = ex2f(fmaf(__uint_as_float(sv[j + 1]), p.scale_log2, -l0.y));
+        pe[j + 2] = ex2f(fmaf(__uint_as_float(sv[j + 2]), p.scale_log2, -l0.z));
+        pe[j + 3] = ex2f(fmaf(__uint_as_float(sv[j + 3]), p.scale_log2, -l0.w));
+      }
+      if (diag) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int4 q0 = *reinterpret_cast<const int4*>(mb + 128 + c0 + j);
+          if (kpos > q0.x) pe[j + 0] = 0.f;
+          if (kpos > q0.y) pe[j + 1] = 0.f;
+          if (kpos > q0.z) pe[j + 2] = 0.f;
+          if (kpos > q0.w) pe[j + 3] = 0.f;
+        }
+      }
+      ptx::tmem_ld_wait();                                     // dP^T values are in registers
       ptx::tc_fence_before_sync();
       softmax_bar();                                           // every thread holds its S^T / dP^T values
       if (threadIdx.x == 64) ptx::mbar_arrive(bar(9 + s));    // -> S^T[s], dP^T[s] of step it + 2 may be issued
-      const float* mb = meta + (it & 1) * 192;
-      const bool diag = u * nqa < key0 + 127;                  // some (key, query) of this step is causally masked
       ptx::mbar_wait(bar(13 + s), (uint32_t)(((it >> 1) & 1) ^ 1));   // dV / dK of step it - 2 consumed P^T[s], dS^T[s]
       const uint32_t prow = pds_smem + (uint32_t)(s * kPdsSlot + m * 128);
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
-        const float4 l0 = *reinterpret_cast<const float4*>(mb + c0 + j);
-        const float4 l1 = *reinterpret_cast<const float4*>(mb + c0 + j + 4);
         const float4 d0 = *reinterpret_cast<const float4*>(mb + 64 + c0 + j);
         const float4 d1 = *reinterpret_cast<const float4*>(mb + 64 + c0 + j + 4);
-        const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
         const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-        float pe[8], de[8];
+        float de[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) pe[e] = ex2f(fmaf(__uint_as_float(sv[j + e]), p.scale_log2, -ls[e]));
-        if (diag) {
-          const int4 q0 = *reinterpret_cast<const int4*>(mb + 128 + c0 + j);
-          const int4 q1 = *reinterpret_cast<const int4*>(mb + 128 + c0 + j + 4);
-          const int qp[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (kpos > qp[e]) pe[e] = 0.f;
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) de[e] = pe[e] * (__uint_as_float(dv[j + e]) - dl[e]);
+        for (int e = 0; e < 8; ++e) de[e] = pe[j + e] * (__uint_as_float(dv[j + e]) - dl[e]);
         const uint32_t off = (((uint32_t)((c0 + j) >> 3) ^ (uint32_t)(m & 7)) << 4);
-        sts_v4(prow + off, pk2(pe[0], pe[1]), pk2(pe[2], pe[3]), pk2(pe[4], pe[5]), pk2(pe[6], pe[7]));
+        sts_v4(prow + off, pk2(pe[j], pe[j + 1]), pk2(pe[j + 2], pe[j + 3]), pk2(pe[j + 4], pe[j + 5]), pk2(pe[j + 6], pe[j + 7]));
         sts_v4(prow + kT16 + off, pk2(de[0], de[1]), pk2(de[2], de[3]), pk2(de[4], de[5]), pk2(de[6], de[7]));
       }
       if (it + 1 < n_it && mwhich < 3) meta[((it + 1) & 1) * 192 + mwhich * 64 + mc] = nxt;
@@ -508,6 +517,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (threadIdx.x == 64) ptx::mbar_arrive(bar(7 + s));   // S[s] drained -> Q K^T of step i + 2
       const int key0 = i * 128 + h * 64;
       const bool diag = i * 128 + 127 > t0;
+      // start the dP read now: it completes under the exponentials (TMEM read port and MUFU pipe overlap)
+      ptx::mbar_wait(bar(9), (uint32_t)(i & 1));             // dP of step i
+      ptx::tc_fence_after_sync();
+      uint32_t d0[32], d1[32];
+      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(256 + h * 64), d0);
+      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(256 + h * 64 + 32), d1);
 #pragma unroll
       for (int e = 0; e < 64; ++e) sv[e] = ex2f(fmaf(sv[e], p.scale_log2, -lse_row));
       if (diag) {
@@ -515,18 +530,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         for (int e = 0; e < 64; ++e)
           if (key0 + e > qpos) sv[e] = 0.f;
       }
-      ptx::mbar_wait(bar(9), (uint32_t)(i & 1));             // dP of step i
-      ptx::tc_fence_after_sync();
-      {
-        uint32_t v0[32], v1[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(256 + h * 64), v0);
-        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(256 + h * 64 + 32), v1);
-        ptx::tmem_ld_wait();
+      ptx::tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          sv[e] *= (__uint_as_float(v0[e]) - delta_row);
-          sv[32 + e] *= (__uint_as_float(v1[e]) - delta_row);
-        }
+      for (int e = 0; e < 32; ++e) {
+        sv[e] *= (__uint_as_float(d0[e]) - delta_row);
+        sv[32 + e] *= (__uint_as_float(d1[e]) - delta_row);
       }
       ptx::tc_fence_before_sync();
       softmax_bar();

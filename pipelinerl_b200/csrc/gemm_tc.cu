@@ -26,7 +26,7 @@
 
 namespace prl {
 
-int head_logprob_tn(const void* W, const void* X, int64_t M, int64_t V, int64_t K, float temperature,
+int head_logprob_tn(const void* W, const void* W_lo, const void* X, int64_t M, int64_t V, int64_t K, float temperature,
                     const int64_t* targets, float* logprob_target, float* entropy, float* lse, void* workspace,
                     cudaStream_t stream);  // gemm_tn.cu
 
@@ -683,10 +683,10 @@ extern "C" int prl_head_logprob(const void* W, const void* W_lo, const void* X, 
   PRL_CHECK_ARG(temperature > 0.f, "prl_head_logprob: temperature must be > 0");
   PRL_CHECK_ARG(!logprob_target || targets, "prl_head_logprob: logprob_target needs targets");
   PRL_CHECK_ARG(workspace_bytes >= prl_head_workspace_bytes(M, V), "prl_head_logprob: workspace too small");
-  if (M > kBlockM && !W_lo && !sampled_ids && !sampled_logprobs && g_use_2cta && !g_tiled_weights) {
+  if (M > kBlockM && !sampled_ids && !sampled_logprobs && g_use_2cta && !g_tiled_weights) {
     // many tokens, statistics only (learner forward, reference-logprob scoring): CTA-pair kernel, token-per-thread
     // epilogue (csrc/gemm_tn.cu)
-    return head_logprob_tn(W, X, M, V, K, temperature, targets, logprob_target, entropy, lse, workspace,
+    return head_logprob_tn(W, W_lo, X, M, V, K, temperature, targets, logprob_target, entropy, lse, workspace,
                            (cudaStream_t)stream_);
   }
   const int nt = pick_ntile(M);

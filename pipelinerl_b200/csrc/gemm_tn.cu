@@ -36,6 +36,8 @@ constexpr int kGroupM = 8;      // row tiles per raster super-group
 struct TnParams {
   int64_t M, N, K;
   int kblocks;
+  int k_wrap;        // k-blocks >= k_wrap read B from the SECOND tensor map and A from k-block (kb - k_wrap): C = A B^T + A B2^T
+                     // in one accumulation (fp32-equivalent lm_head: B = bf16 hi part, B2 = bf16 lo residual)
   int m_tiles, n_tiles;
   int a_mn, b_mn;    // operand stored MN-major: A as [K, M] / B as [K, N] row-major (no transposed copy needed)
   void* C;
@@ -63,7 +65,8 @@ __device__ __forceinline__ void tile_coords(int t, const TnParams& p, int& tm, i
 
 template <bool kHead>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTN, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, TnParams p) {
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+               const __grid_constant__ CUtensorMap tm_b2, TnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + (uint32_t)(kStages * kStageBytes);
@@ -121,17 +124,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           else ptx::mbar_arrive_remote(full_bar(s), 0);
           const uint32_t a_dst = smem_base + (uint32_t)(s * kStageBytes);
           const uint32_t b_dst = a_dst + kHalf * kBK * 2;
+          const bool second = kb >= p.k_wrap;                 // hi + lo operand streams (K-major operands only)
+          const int kk = (second ? kb - p.k_wrap : kb) * kBK;
+          const CUtensorMap* tb = second ? &tm_b2 : &tm_b;
           if (!p.a_mn) {
-            ptx::tma_load_2d_2sm(a_dst, &tm_a, kb * kBK, a_row, full_bar(s), ptx::kEvictNormal);
+            ptx::tma_load_2d_2sm(a_dst, &tm_a, kk, a_row, full_bar(s), ptx::kEvictNormal);
           } else {  // two 64(MN) x 64(k) boxes: inner coordinate = MN index, outer = k
-            ptx::tma_load_2d_2sm(a_dst, &tm_a, a_row, kb * kBK, full_bar(s), ptx::kEvictNormal);
-            ptx::tma_load_2d_2sm(a_dst + kMnChunkBytes, &tm_a, a_row + 64, kb * kBK, full_bar(s), ptx::kEvictNormal);
+            ptx::tma_load_2d_2sm(a_dst, &tm_a, a_row, kk, full_bar(s), ptx::kEvictNormal);
+            ptx::tma_load_2d_2sm(a_dst + kMnChunkBytes, &tm_a, a_row + 64, kk, full_bar(s), ptx::kEvictNormal);
           }
           if (!p.b_mn) {
-            ptx::tma_load_2d_2sm(b_dst, &tm_b, kb * kBK, b_row, full_bar(s), ptx::kEvictNormal);
+            ptx::tma_load_2d_2sm(b_dst, tb, kk, b_row, full_bar(s), ptx::kEvictNormal);
           } else {
-            ptx::tma_load_2d_2sm(b_dst, &tm_b, b_row, kb * kBK, full_bar(s), ptx::kEvictNormal);
-            ptx::tma_load_2d_2sm(b_dst + kMnChunkBytes, &tm_b, b_row + 64, kb * kBK, full_bar(s), ptx::kEvictNormal);
+            ptx::tma_load_2d_2sm(b_dst, tb, b_row, kk, full_bar(s), ptx::kEvictNormal);
+            ptx::tma_load_2d_2sm(b_dst + kMnChunkBytes, tb, b_row + 64, kk, full_bar(s), ptx::kEvictNormal);
           }
         }
       }
@@ -417,6 +423,7 @@ extern "C" int prl_gemm_ex(const void* A, int64_t lda, int32_t a_mn_major, const
   TnParams p = {};
   p.M = M; p.N = N; p.K = K;
   p.kblocks = (int)((K + kBK - 1) / kBK);
+  p.k_wrap = p.kblocks;
   p.m_tiles = (int)((M + kTile - 1) / kTile);
   p.n_tiles = (int)((N + kTile - 1) / kTile);
   p.C = C; p.ldc = ldc; p.c_f32 = c_is_f32; p.accumulate = accumulate;
@@ -439,7 +446,7 @@ extern "C" int prl_gemm_ex(const void* A, int64_t lda, int32_t a_mn_major, const
   const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = (int)tiles;
-  gemm_tn_kernel<false><<<dim3((unsigned)(2 * clusters)), dim3(kThreadsTN), (size_t)smem, (cudaStream_t)stream_>>>(ta, tb, p);
+  gemm_tn_kernel<false><<<dim3((unsigned)(2 * clusters)), dim3(kThreadsTN), (size_t)smem, (cudaStream_t)stream_>>>(ta, tb, tb, p);
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }
@@ -447,21 +454,25 @@ extern "C" int prl_gemm_ex(const void* A, int64_t lda, int32_t a_mn_major, const
 namespace prl {
 // fused output head for many tokens (M > 128): logprob of the target, entropy and logsumexp of softmax(X W^T / T)
 // without storing logits.  Called by prl_head_logprob (gemm_tc.cu).  workspace: ceil(V/256) * M float4.
-int head_logprob_tn(const void* W, const void* X, int64_t M, int64_t V, int64_t K, float temperature,
+int head_logprob_tn(const void* W, const void* W_lo, const void* X, int64_t M, int64_t V, int64_t K, float temperature,
                     const int64_t* targets, float* logprob_target, float* entropy, float* lse, void* workspace,
                     cudaStream_t stream) {
   TnParams p = {};
   p.M = M; p.N = V; p.K = K;
   p.kblocks = (int)((K + kBK - 1) / kBK);
+  p.k_wrap = p.kblocks;
+  if (W_lo) p.kblocks *= 2;          // logits = X W_hi^T + X W_lo^T accumulated in the same TMEM tile
   p.m_tiles = (int)((M + kTile - 1) / kTile);
   p.n_tiles = (int)((V + kTile - 1) / kTile);
   p.alpha = 1.f / temperature;
   p.targets = targets;
   p.head_part = (float4*)workspace;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tb2;
   int rc = make_tmap_2d_bf16(&ta, X, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kBK, kHalf);
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tb, W, (uint64_t)K, (uint64_t)V, (uint64_t)K * 2, kBK, kHalf);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tb2, W_lo ? W_lo : W, (uint64_t)K, (uint64_t)V, (uint64_t)K * 2, kBK, kHalf);
   if (rc) return rc;
   const int smem = kStages * kStageBytes + 1024 + 8 * (2 * kStages + 4) + 16;
   static SmemAttr smem_attr = {};
@@ -469,7 +480,7 @@ int head_logprob_tn(const void* W, const void* X, int64_t M, int64_t V, int64_t 
   const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = (int)tiles;
-  gemm_tn_kernel<true><<<dim3((unsigned)(2 * clusters)), dim3(kThreadsTN), (size_t)smem, stream>>>(ta, tb, p);
+  gemm_tn_kernel<true><<<dim3((unsigned)(2 * clusters)), dim3(kThreadsTN), (size_t)smem, stream>>>(ta, tb, tb2, p);
   PRL_LAUNCH_CHECK();
   head_tn_combine_kernel<<<(unsigned)((M + 3) / 4), 128, 0, stream>>>((const float4*)workspace, p.n_tiles, M,
                                                                       targets ? 1 : 0, logprob_target, entropy, lse);

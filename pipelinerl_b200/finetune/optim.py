@@ -45,7 +45,10 @@ class FusedAdamW:
 
     def __init__(self, named_params, lr: float, weight_decay: float = 0.01, betas=(0.9, 0.999), eps: float = 1e-8,
                  max_grad_norm: float | None = None, no_decay: Iterable[str] = NO_DECAY_DEFAULT,
-                 grad_dtype: torch.dtype | None = None, keep_lo_residual: bool = False):
+                 grad_dtype: torch.dtype | None = None, keep_lo_residual: bool = False, lo_tail_for: str | None = None):
+        """lo_tail_for: name of ONE parameter (the lm_head) whose bf16 residual lo = bf16(master - bf16(master)) is kept in a
+        tail of the bf16 arena, right where the sampler's arena layout has `<name>_lo` (model.fused_shapes with fp32_head):
+        the pushed bytes then carry the fp32-equivalent head, and the learner's own head reads the same pair."""
         named = [(n, p) for n, p in named_params if p.requires_grad]
         if not named:
             raise ValueError("FusedAdamW: no trainable parameters")
@@ -75,7 +78,9 @@ class FusedAdamW:
         self.exp_avg = torch.zeros_like(self.master)
         self.exp_avg_sq = torch.zeros_like(self.master)
         self.grad = torch.zeros(self.n, dtype=gdt, device=dev)
-        self.shadow_bf16 = torch.zeros(self.n, dtype=torch.bfloat16, device=dev)
+        self.lo_index = self.names.index(lo_tail_for) if lo_tail_for else None
+        tail = _align(self.params[self.lo_index].numel()) if self.lo_index is not None else 0
+        self.shadow_bf16 = torch.zeros(self.n + tail, dtype=torch.bfloat16, device=dev)   # [parameters | lo tail]
         self.shadow_lo = torch.zeros(self.n, dtype=torch.bfloat16, device=dev) if keep_lo_residual else None
         with torch.no_grad():
             for p, off in zip(self.params, offsets):
@@ -95,6 +100,18 @@ class FusedAdamW:
         self.workspace = torch.zeros(int(self.lib.prl_adamw_workspace_bytes()), dtype=torch.uint8, device=dev)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.param_groups = [{"lr": lr, "weight_decay": weight_decay, "params": self.params}]
+        self.lo_view = None
+        if self.lo_index is not None:
+            k = self.params[self.lo_index].numel()
+            self.lo_view = self.shadow_bf16[self.n:self.n + k].view(self.params[self.lo_index].shape)
+            self._refresh_lo()
+
+    def _refresh_lo(self) -> None:
+        if self.lo_index is None:
+            return
+        off, k = self.offsets[self.lo_index], self.params[self.lo_index].numel()
+        dst = (C.c_void_p * 1)(self.lo_view.data_ptr())
+        _lib.check(self.lib.prl_bf16_residual(self.master.data_ptr() + off * 4, k, dst, 1, _lib.stream_ptr()))
 
     def grad_view(self, name: str) -> torch.Tensor:
         i = self.names.index(name)
@@ -131,6 +148,7 @@ class FusedAdamW:
         a.grad_scale = grad_scale
         _lib.check(self.lib.prl_adamw_step(C.byref(a), self.grad_norm.data_ptr(), self.workspace.data_ptr(),
                                            self.workspace.numel(), _lib.stream_ptr()))
+        self._refresh_lo()
         return self.grad_norm
 
     def state_dict(self) -> dict:
@@ -142,7 +160,8 @@ class FusedAdamW:
         self.master.copy_(sd["master"])
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        self.shadow_bf16.copy_(self.master)
+        self.shadow_bf16[:self.n].copy_(self.master)
+        self._refresh_lo()
 
 
 def get_optimizer(name: str, model, learning_rate: float, weight_decay: float, **kw) -> FusedAdamW:
@@ -213,7 +232,7 @@ class ShardedFusedAdamW:
 
     def __init__(self, named_params, lr: float, weight_decay: float = 0.01, betas=(0.9, 0.999), eps: float = 1e-8,
                  max_grad_norm: float | None = None, no_decay: Iterable[str] = NO_DECAY_DEFAULT, group=None,
-                 grad_accum_fp32: bool = False):
+                 grad_accum_fp32: bool = False, lo_tail_for: str | None = None):
         import torch.distributed as dist
         from ..weights import ipc_alloc, ipc_export, ipc_open
         if not (dist.is_available() and dist.is_initialized()):
@@ -239,8 +258,10 @@ class ShardedFusedAdamW:
         self.n, self.offsets = at, offsets
         per = _align((self.n + self.world - 1) // self.world)
         self.lo, self.hi = min(self.n, per * self.rank), min(self.n, per * (self.rank + 1))
+        self.lo_index = self.names.index(lo_tail_for) if lo_tail_for else None
+        self.tail = _align(self.params[self.lo_index].numel()) if self.lo_index is not None else 0
         # IPC-shareable arenas of this rank
-        self._grad_buf, self._shadow_buf = ipc_alloc(self.n * 2), ipc_alloc(self.n * 2)
+        self._grad_buf, self._shadow_buf = ipc_alloc(self.n * 2), ipc_alloc((self.n + self.tail) * 2)
         self._norm_buf = ipc_alloc(8 * 8)
         self.grad = self._grad_buf.tensor(torch.bfloat16, dev)
         self.shadow_bf16 = self._shadow_buf.tensor(torch.bfloat16, dev)
@@ -275,11 +296,29 @@ class ShardedFusedAdamW:
             if r == self.rank:
                 self._grads.append(self._grad_buf.ptr); self._shadows.append(self._shadow_buf.ptr); self._norms.append(self._norm_buf.ptr)
             else:
-                g, s, nn = ipc_open(hg, self.n * 2), ipc_open(hs, self.n * 2), ipc_open(hn, 64)
+                g, s, nn = ipc_open(hg, self.n * 2), ipc_open(hs, (self.n + self.tail) * 2), ipc_open(hn, 64)
                 self._peer_bufs += [g, s, nn]
                 self._grads.append(g.ptr); self._shadows.append(s.ptr); self._norms.append(nn.ptr)
         self.param_groups = [{"lr": lr, "weight_decay": weight_decay, "params": self.params}]
         self.last_phase_ms = (0.0, 0.0)
+        self.lo_view = None
+        if self.lo_index is not None:
+            k = self.params[self.lo_index].numel()
+            self.lo_view = self.shadow_bf16[self.n:self.n + k].view(self.params[self.lo_index].shape)
+            self._refresh_lo()
+            self._barrier()
+
+    def _refresh_lo(self) -> None:
+        """this rank's part of the head's fp32 master -> bf16 residual in EVERY rank's arena tail (P2P stores)"""
+        if self.lo_index is None:
+            return
+        off, k = self.offsets[self.lo_index], self.params[self.lo_index].numel()
+        a, b = max(self.lo, off), min(self.hi, off + k)
+        if b <= a:
+            return
+        dsts = (C.c_void_p * self.world)(*[self._shadows[r] + (self.n + a - off) * 2 for r in range(self.world)])
+        _lib.check(self.lib.prl_bf16_residual(self.master.data_ptr() + (a - self.lo) * 4, b - a, dsts, self.world,
+                                              _lib.stream_ptr()))
 
     def zero_grad(self, set_to_none: bool = False) -> None:
         (self.grad_f32 if self.grad_f32 is not None else self.grad).zero_()
@@ -322,6 +361,7 @@ class ShardedFusedAdamW:
         self._barrier()                                   # every rank's norm partial is in every norm table
         e[2].record()
         _lib.check(self.lib.prl_adamw_sharded_update(C.byref(a), self.grad_norm.data_ptr(), st))
+        self._refresh_lo()
         e[3].record()
         self._barrier()                                   # every shard of every parameter arena is written
         self.last_phase_ms = (e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3]))

@@ -143,14 +143,16 @@ def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding
         from .finetune.optim import ShardedFusedAdamW
         native = hasattr(model, "bind")   # learner_model.NativeQwen2: fp32 gradient accumulation in the arena
         opt = ShardedFusedAdamW(model.named_parameters(), lr=cfg.learning_rate, weight_decay=cfg.weight_decay,
-                                max_grad_norm=cfg.gradient_clipping_threshold, group=dp_group, grad_accum_fp32=native)
+                                max_grad_norm=cfg.gradient_clipping_threshold, group=dp_group, grad_accum_fp32=native,
+                                **(model.optimizer_kwargs() if hasattr(model, "optimizer_kwargs") else {}))
         if native:
             model.bind(opt)
     else:
         native = hasattr(model, "bind")
         opt = FusedAdamW(model.named_parameters(), lr=cfg.learning_rate, weight_decay=cfg.weight_decay,
                          max_grad_norm=cfg.gradient_clipping_threshold,
-                         grad_dtype=torch.float32 if native else None)
+                         grad_dtype=torch.float32 if native else None,
+                         **(model.optimizer_kwargs() if hasattr(model, "optimizer_kwargs") else {}))
         if native:
             model.bind(opt)
     if weight_manager is not None:

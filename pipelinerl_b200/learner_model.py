@@ -136,7 +136,9 @@ class _NativeHead(torch.autograd.Function):
         lp = torch.empty(M, dtype=torch.float32, device=x.device)
         ent, lse = torch.empty_like(lp), torch.empty_like(lp)
         ws = torch.empty(int(lib.prl_head_workspace_bytes(M, V)), dtype=torch.uint8, device=x.device)
-        _lib.check(lib.prl_head_logprob(W.data_ptr(), None, x.data_ptr(), M, V, K, float(temperature), tg.data_ptr(), 1, 0,
+        W_lo = model.head_lo
+        _lib.check(lib.prl_head_logprob(W.data_ptr(), W_lo.data_ptr() if W_lo is not None else None, x.data_ptr(), M, V, K,
+                                        float(temperature), tg.data_ptr(), 1, 0,
                                         0, lp.data_ptr(), ent.data_ptr(), lse.data_ptr(), None, None, ws.data_ptr(),
                                         ws.numel(), _lib.stream_ptr()))
         ctx.save_for_backward(x, tg, lse, ent)
@@ -165,6 +167,8 @@ class _NativeHead(torch.autograd.Function):
             n = min(Cn, M - r0)
             xs, logits, dlogits = x[r0:r0 + n], logits_buf[:n], dlogits_buf[:n]
             ops.gemm(xs, W, out=logits)
+            if model.head_lo is not None:      # same fp32-equivalent logits as the forward: += X W_lo^T
+                ops.gemm(xs, model.head_lo, out=logits, accumulate=True)
             _lib.check(lib.prl_logprob_rows_bwd(logits.data_ptr(), n, V, V, tg[r0:r0 + n].data_ptr(), ctx.temperature,
                                                 lse[r0:r0 + n].data_ptr(), ent[r0:r0 + n].data_ptr(),
                                                 g_lp[r0:r0 + n].data_ptr(),
@@ -189,6 +193,8 @@ class NativeQwen2(torch.nn.Module):
         self.names = []
         g = torch.Generator(device=device).manual_seed(seed)
         for name, shape in fused_shapes(cfg):
+            if name.endswith("_lo"):
+                continue      # not a parameter: the bf16 residual of the head's fp32 master, kept by the optimizer (lo tail)
             if init is not None:
                 t = init[name].to(device=device, dtype=torch.bfloat16)
             elif name.endswith("layernorm.weight") or name == "norm.weight":
@@ -201,6 +207,7 @@ class NativeQwen2(torch.nn.Module):
             self.names.append(name)
         self.layout = ArenaLayout.build(cfg)
         self.body = None
+        self.head_lo = None
         self._hook = torch.zeros((), device=device, requires_grad=True)
 
     def p(self, name: str) -> torch.Tensor:
@@ -210,8 +217,18 @@ class NativeQwen2(torch.nn.Module):
         for name in self.names:
             yield name, self.p(name)
 
+    def optimizer_kwargs(self) -> dict:
+        """extra arguments FusedAdamW / ShardedFusedAdamW need for this model: with `cfg.fp32_head` the optimizer keeps
+        the lm_head's bf16 residual in the arena tail (= the sampler layout's `lm_head.weight_lo`), so that learner and
+        samplers both compute the head from the fp32 master's 16 mantissa bits (reference: fp32 lm_head on both sides,
+        vllm_quantization.py:266-278, finetune/checkpoints.py:44-105)."""
+        return {"lo_tail_for": "lm_head.weight"} if self.cfg.fp32_head else {}
+
     def bind(self, optimizer) -> None:
         from .learner_body import NativeBody
+        if self.cfg.fp32_head and getattr(optimizer, "lo_view", None) is None:
+            raise ValueError("cfg.fp32_head: build the optimizer with **model.optimizer_kwargs() (lo_tail_for='lm_head.weight')")
+        self.head_lo = optimizer.lo_view if self.cfg.fp32_head else None
         grads = optimizer.grad_views()
         if any(g.dtype != torch.float32 for g in grads.values()):
             raise ValueError("NativeQwen2 accumulates gradients in fp32: build FusedAdamW(grad_dtype=torch.float32) "

@@ -285,3 +285,51 @@ def test_native_learner_vs_reference_rl_step_on_hf(cuda_device, kind):
         got, want = flat[torch.from_numpy(idx)].numpy(), arrs["gsamp__" + key]
         rel = np.linalg.norm(got - want) / (np.linalg.norm(want) + 1e-12)
         assert rel <= 5e-2, (name, rel)
+
+
+def test_native_learner_fp32_equivalent_head(cuda_device):
+    """cfg.fp32_head: the learner's head reads (hi, lo) = the fp32 master split into two bf16 streams that the optimizer
+    maintains in the arena tail; logprobs match an fp32 head on the fp32 master to 1e-4 where a bf16 head is ~1e-2 off, the
+    arena (parameters | lo) has exactly the sampler's layout, and lo tracks the master across optimizer steps."""
+    from dataclasses import replace
+    from pipelinerl_b200 import _lib
+    from pipelinerl_b200.finetune.optim import FusedAdamW
+    from pipelinerl_b200.learner_model import NativeQwen2
+    from pipelinerl_b200.model import ArenaLayout
+    cfg = replace(tiny_cfg("gqa2"), fp32_head=True)
+    w = tiny_weights(cfg)
+    model = NativeQwen2(cfg, cuda_device, init=w)
+    assert "lm_head.weight_lo" not in dict(model.named_parameters())
+    opt = FusedAdamW(model.named_parameters(), lr=1e-2, weight_decay=0.0, grad_dtype=torch.float32, **model.optimizer_kwargs())
+    model.bind(opt)
+    lay = ArenaLayout.build(cfg)
+    assert opt.shadow_bf16.numel() == lay.total and lay.offsets["lm_head.weight_lo"] == opt.n
+    # make the master differ from its bf16 rounding, as it does after real optimizer steps
+    i = opt.names.index("lm_head.weight")
+    off, k = opt.offsets[i], opt.params[i].numel()
+    g = torch.Generator(device=cuda_device).manual_seed(1)
+    opt.master[off:off + k] += torch.randn(k, generator=g, device=cuda_device) * 1e-3
+    opt.grad.zero_()
+    opt.step()                                              # zero gradients, no decay: re-casts hi and refreshes lo
+    master = opt.master[off:off + k].view(cfg.vocab_size, cfg.hidden_size)
+    hi = model.p("lm_head.weight").data.float()
+    assert torch.equal(hi, master.to(torch.bfloat16).float())
+    assert torch.equal(model.head_lo.float(), (master - hi).to(torch.bfloat16).float())
+    T = 200
+    x = _bf(torch.randn(T, cfg.hidden_size, generator=g, device=cuda_device))
+    tg = torch.randint(0, cfg.vocab_size, (T,), generator=g, device=cuda_device)
+    lib = _lib.load()
+
+    def head(W_lo):
+        lp, ent, lse = (torch.empty(T, device=cuda_device) for _ in range(3))
+        ws = torch.empty(int(lib.prl_head_workspace_bytes(T, cfg.vocab_size)), dtype=torch.uint8, device=cuda_device)
+        _lib.check(lib.prl_head_logprob(model.p("lm_head.weight").data_ptr(), W_lo.data_ptr() if W_lo is not None else None,
+                                        x.data_ptr(), T, cfg.vocab_size, cfg.hidden_size, 1.0, tg.data_ptr(), 1, 0, 0,
+                                        lp.data_ptr(), ent.data_ptr(), lse.data_ptr(), None, None, ws.data_ptr(), ws.numel(),
+                                        _lib.stream_ptr()))
+        return lp
+    want = torch.log_softmax(x.float() @ master.t(), -1).gather(1, tg[:, None])[:, 0]
+    err_lo = (head(model.head_lo) - want).abs().max().item()
+    err_bf16 = (head(None) - want).abs().max().item()
+    print(f"[fp32-equivalent head] max |dlogprob| hi+lo {err_lo:.2e}   bf16 head {err_bf16:.2e}")
+    assert err_lo <= 2e-4 and err_lo < 0.2 * err_bf16

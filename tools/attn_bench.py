@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--n-q", type=int, default=28)
     ap.add_argument("--n-kv", type=int, default=4)
     ap.add_argument("--no-library", action="store_true")
+    ap.add_argument("--ours-only", action="store_true", help="one forward + one backward of our kernels, nothing else (ncu)")
     ap.add_argument("--tmem", action="store_true", help="TMEM read bandwidth microbenchmark")
     ap.add_argument("--profile", action="store_true", help="per-kernel device time (torch profiler)")
     a = ap.parse_args()
@@ -51,6 +52,12 @@ def main():
     d_out = torch.randn(T, n_q * D, generator=g, device=dev).to(torch.bfloat16)
     st = torch.arange(0, T, L, dtype=torch.int32, device=dev)
     ln = torch.tensor(lens, dtype=torch.int32, device=dev)
+    if a.ours_only:
+        for _ in range(2):
+            out, lse = o.attn_fwd(qkv, st, ln, L, n_q, n_kv, D)
+            o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D)
+        torch.cuda.synchronize()
+        return
     from pipelinerl_b200 import _lib as _l
     _l.check(o.lib.prl_attn_set_fwd_generation(1))
     out1, _ = o.attn_fwd(qkv, st, ln, L, n_q, n_kv, D)
@@ -97,8 +104,12 @@ def main():
                 o.attn_fwd(qkv, st, ln, L, n_q, n_kv, D)
                 o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D)
             torch.cuda.synchronize()
-        res["kernels_us"] = {e.key.split("(")[0][-48:]: round(e.device_time_total / e.count, 1) for e in prof.key_averages()
-                             if e.device_time_total > 0}
+        import re
+        res["kernels_us"] = {}
+        for e in prof.key_averages():
+            if e.device_time_total > 0:
+                mname = re.search(r"(\w+_kernel)(<[^>]*>)?", e.key)
+                res["kernels_us"][(mname.group(0) if mname else e.key[:40])] = round(e.device_time_total / e.count, 1)
     print(json.dumps(res), flush=True)
 
 

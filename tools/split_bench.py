@@ -53,8 +53,8 @@ def run_split(n_learners: int, updates: int = 2, context: int = 8192, batch: int
     torch.cuda.set_device(dev)
     n_samplers = world - n_learners
     assert n_learners >= 1 and n_samplers >= 1
-    cfg = ModelConfig.qwen2_5_7b() if model_name == "7b" else ModelConfig(
-        vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2, num_q_heads=4, num_kv_heads=2)
+    cfg = ModelConfig.qwen2_5_7b(fp32_head=True) if model_name == "7b" else ModelConfig(
+        vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2, num_q_heads=4, num_kv_heads=2, fp32_head=True)
     is_learner = rank < n_learners
     lgroup = dist.new_group(ranks=list(range(n_learners)))          # every rank must take part in group creation
     U = updates
@@ -79,9 +79,10 @@ def run_split(n_learners: int, updates: int = 2, context: int = 8192, batch: int
         model = NativeQwen2(cfg, dev)
         if n_learners > 1:
             opt = ShardedFusedAdamW(model.named_parameters(), lr=1e-6, weight_decay=0.01, max_grad_norm=0.3,
-                                    grad_accum_fp32=True, group=lgroup)
+                                    grad_accum_fp32=True, group=lgroup, **model.optimizer_kwargs())
         else:
-            opt = FusedAdamW(model.named_parameters(), lr=1e-6, weight_decay=0.01, max_grad_norm=0.3, grad_dtype=torch.float32)
+            opt = FusedAdamW(model.named_parameters(), lr=1e-6, weight_decay=0.01, max_grad_norm=0.3, grad_dtype=torch.float32,
+                         **model.optimizer_kwargs())
         model.bind(opt)
         rcfg = RLConfig(batch_size=micro * n_learners)
         batches = [train_bench.synthetic_batch(cfg, tokens, 1, dev, 100 + rank * micro + i) for i in range(micro)]
@@ -194,6 +195,7 @@ def run_split(n_learners: int, updates: int = 2, context: int = 8192, batch: int
                "bytes_identical": bool(all(s["checksum"] == L[0]["checksum"] for s in S)
                                        and all(l["checksum"] == L[0]["checksum"] for l in L)),
                "dp_equals_single": (bool(dpc["ok"]) if dpc is not None else None), "dp_check": dpc,
+               "lm_head": "fp32-equivalent on both sides (hi + lo bf16 streams; the push carries both)",
                "learner_peak_memory_GB": max(l["peak_memory_GB"] for l in L), "context": context, "batch_per_sampler": batch,
                "final_loss": L[0]["loss"]}
     # release IPC mappings / big buffers before the caller goes on

@@ -45,7 +45,7 @@ def synthetic_batch(cfg, T, n_samples, dev, seed):
 
 
 def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, warmup=1, layers=0, keep_attn=-1,
-            profile=False, dev=None, log=True, keep_gate_up=-1, distributed=None):
+            profile=False, dev=None, log=True, keep_gate_up=-1, distributed=None, fp32_head=True):
     """Run the trainer step and return the result dict (also used by bench.py's `components.trainer_step`).
     Under torchrun (WORLD_SIZE > 1) every rank is a data-parallel learner with its own `micro` micro-batches and the
     optimizer step is the ShardedFusedAdamW exchange (P2P reduce-scatter + AdamW shard + P2P all-gather);
@@ -68,7 +68,8 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
         torch.cuda.memory._set_allocator_settings("expandable_segments:True")
     except Exception:  # noqa: BLE001
         pass
-    cfg = ModelConfig.qwen2_5_7b() if model_name == "7b" else ModelConfig.tiny()
+    # fp32-equivalent lm_head (hi + lo bf16 operand streams), as the reference trains (finetune/checkpoints.py:44-105)
+    cfg = ModelConfig.qwen2_5_7b(fp32_head=fp32_head) if model_name == "7b" else ModelConfig.tiny(fp32_head=fp32_head)
     if layers:
         from dataclasses import replace
         cfg = replace(cfg, num_layers=layers)
@@ -81,9 +82,10 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
     if world > 1:
         from pipelinerl_b200.finetune.optim import ShardedFusedAdamW
         opt = ShardedFusedAdamW(model.named_parameters(), lr=1e-6, weight_decay=0.01, max_grad_norm=0.3,
-                                grad_accum_fp32=True)
+                                grad_accum_fp32=True, **model.optimizer_kwargs())
     else:
-        opt = FusedAdamW(model.named_parameters(), lr=1e-6, weight_decay=0.01, max_grad_norm=0.3, grad_dtype=torch.float32)
+        opt = FusedAdamW(model.named_parameters(), lr=1e-6, weight_decay=0.01, max_grad_norm=0.3, grad_dtype=torch.float32,
+                         **model.optimizer_kwargs())
     model.bind(opt)
     if keep_attn >= 0:
         model.body.keep_attention_layers = keep_attn
@@ -169,6 +171,7 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
            "libprl_launches_per_step": (_lib.launch_count() - launches0) // max(1, steps),
            "peak_memory_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1),
            "loss": rec[-1][4], "grad_norm": rec[-1][5], "grad_accumulation": "fp32 in the optimizer arena",
+           "lm_head": "fp32-equivalent (bf16 hi + lo streams from the fp32 master)" if cfg.fp32_head else "bf16",
            "attention": "prl_attn_varlen_fwd / prl_attn_varlen_bwd (tcgen05, csrc/attn_tc.cu + csrc/attn_train.cu)", "keep_attention_layers": model.body.keep_attention_layers,
            "keep_gate_up_layers": model.body.keep_gate_up_layers,
            "gemm": "prl_gemm_ex (tcgen05 cta_group::2, MN-major dgrad/wgrad operands)"}
