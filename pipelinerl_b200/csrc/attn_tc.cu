@@ -323,6 +323,11 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 //     while group 0 exponentiates step i, group 1 loads / maximises / stores step i + 1 and the tensor core runs the
 //     Q K^T of step i + 2 and the P V of step i - 1.  The two partial results are merged once, at the end
 //     (a log-sum-exp merge, as for split-KV decode).
+//   * P_g is handed to the tensor core THROUGH TMEM (tcgen05.mma with the A operand in tensor memory), written by each
+//     thread into its own row in place of the S values it has just consumed.  With both operands in shared memory a
+//     128 x 128 x 16 UMMA reads 8 KB per 64 cycles = all of an SM's shared-memory bandwidth; generation 1 moves 224 KB
+//     through shared memory per step (Q, K, P, V operand reads + the P store + the K/V TMA writes) = 1750 cycles against
+//     1024 of tensor work, which is exactly what it measures.  TMEM-resident P removes 64 KB of that.
 //   * O_g is NEVER read inside the loop: P V accumulates into it (tcgen05.mma accumulate), and a row is rescaled in TMEM
 //     (tcgen05.ld / scale / tcgen05.st) only when its running maximum grew by more than 2^8 since the reference was
 //     set -- P stays below 256, exact in bf16's range, and for trained or random scores the rescale branch is taken in
@@ -423,7 +428,8 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int s = j & 1;
         const uint32_t ph = (uint32_t)((j >> 1) & 1);
         ptx::mbar_wait(bar(1 + s), ph);          // K of step j landed
-        ptx::mbar_wait(bar(7 + s), ph ^ 1u);     // S_s drained by group s (step j - 2)
+        // S_s's columns held P_s of step j - 2: its P V was issued before this point and UMMAs of one thread execute in
+        // issue order, so this Q K^T cannot overtake it (and the softmax group finished reading S_s before it stored P_s)
         ptx::tc_fence_after_sync();
         const uint32_t k_addr = kv_smem + (uint32_t)(s * kStageBytesT);
 #pragma unroll
@@ -441,18 +447,17 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (i + 1 < n_it) issue_qk(i + 1);
         const int s = i & 1;
         const uint32_t ph = (uint32_t)((i >> 1) & 1);
-        ptx::mbar_wait(bar(9 + s), ph);              // P_s of step i stored (and O_s rescaled if it had to be)
+        ptx::mbar_wait(bar(9 + s), ph);              // P_s of step i is in TMEM (and O_s rescaled if it had to be)
         ptx::mbar_wait(bar(13 + s), ph);             // V of step i landed
         ptx::tc_fence_after_sync();
         const uint32_t v_addr = kv_smem + (uint32_t)(s * kStageBytesT) + 2 * kTile16K;
-        const uint32_t p_addr = p_smem + (uint32_t)(s * 2 * kTile16K);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a = ptx::make_kmajor_sw128_desc(p_addr + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
+        for (int ks = 0; ks < 8; ++ks) {             // A = P_s out of TMEM: 16 keys = 8 packed columns per UMMA
           const uint64_t b = ptx::make_mnmajor_sw128_desc(v_addr, kTile16K) + (uint64_t)(128 * ks);
-          ptx::mma_bf16_ss(tmem_base + (uint32_t)(256 + s * 128), a, b, idesc_pv, (i >= 2 || ks > 0) ? 1u : 0u);
+          ptx::mma_bf16_ts(tmem_base + (uint32_t)(256 + s * 128), tmem_base + (uint32_t)(s * 128 + ks * 8), b, idesc_pv,
+                           (i >= 2 || ks > 0) ? 1u : 0u);
         }
-        ptx::tc_commit(bar(11 + s));                 // O_s updated, P_s free again
+        ptx::tc_commit(bar(11 + s));                 // O_s updated
         ptx::tc_commit_multicast(bar(15 + s), 3);    // V slot consumed: tell BOTH producers
       }
     }
@@ -486,9 +491,6 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 #pragma unroll
         for (int e = 0; e < 128; ++e) sv[e] = __uint_as_float(su[e]);
       }
-      ptx::tc_fence_before_sync();
-      group_bar(g);                                         // the whole S_g tile is in registers
-      if (leader) ptx::mbar_arrive(bar(7 + g));             // -> Q K^T of step i + 2 may overwrite S_g
       if (i * kKeys + kKeys - 1 > pos_first) {              // some (row, key) of this step is causally masked
         const int key0 = i * kKeys;
 #pragma unroll
@@ -502,7 +504,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (j == 0) {
         m_ref = (m_new == -INFINITY) ? 0.f : m_new;
       } else {
-        ptx::mbar_wait(bar(11 + g), (uint32_t)((j - 1) & 1));   // P V of step i - 2 done: P_g free, O_g up to date
+        ptx::mbar_wait(bar(11 + g), (uint32_t)((j - 1) & 1));   // P V of step i - 2 done: O_g up to date
         const bool need = m_new > m_ref + 8.f;              // rows of a warp decide together (TMEM ops are warp-wide)
         if (__any_sync(0xffffffffu, need)) {
           ptx::tc_fence_after_sync();
@@ -521,20 +523,23 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           if (need) m_ref = m_new;
         }
       }
+      // P_g goes back into TMEM as the A operand of P V, in place of this row's own S values (lane = row; one 32-bit column
+      // = two adjacent keys): no shared-memory store, no shared-memory read by the tensor core
       float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        float pe[8];
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pp[16];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          pe[e] = ex2(fmaf(sv[c * 8 + e], p.scale_log2, -m_ref));   // masked entries: exp2(-inf) = 0
-          sum += pe[e];
+        for (int e = 0; e < 16; ++e) {
+          const float p0 = ex2(fmaf(sv[c * 32 + 2 * e], p.scale_log2, -m_ref));       // masked entries: exp2(-inf) = 0
+          const float p1 = ex2(fmaf(sv[c * 32 + 2 * e + 1], p.scale_log2, -m_ref));
+          sum += p0 + p1;
+          pp[e] = pack2(p0, p1);
         }
-        st_shared_v4(p_row + (uint32_t)((c >> 3) * kTile16K) + (((uint32_t)(c & 7) ^ (uint32_t)(m & 7)) << 4),
-                     pack2(pe[0], pe[1]), pack2(pe[2], pe[3]), pack2(pe[4], pe[5]), pack2(pe[6], pe[7]));
+        ptx::tmem_st_32x32b_x16(s_addr + (uint32_t)(c * 16), pp);
       }
       l_run += sum;
-      ptx::fence_proxy_async();                             // generic-proxy stores of P -> visible to the UMMA reads
+      ptx::tmem_st_wait();
       ptx::tc_fence_before_sync();
       group_bar(g);
       if (leader) ptx::mbar_arrive(bar(9 + g));             // P_g ready -> P V of step i

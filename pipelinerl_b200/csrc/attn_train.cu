@@ -24,6 +24,7 @@
 //
 // Tensor-bound.  Per (128 query rows x 128 keys) pair: 4 + 3 UMMAs of 4.2 MFLOP against 5 for the atomics-based
 // single-kernel formulation; 2 x 16 K exp2.
+#include <stdlib.h>
 #include "prl_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -91,6 +92,7 @@ constexpr int kMetaBytes = 2 * 3 * 64 * 4;   // [2 buffers][lse | delta | qpos][
 constexpr int kSmemDkdv = 1024 + kKvBytes + kQStages * kQSlot + 2 * kPdsSlot + kMetaBytes + 8 * 18 + 16;
 static_assert(kSmemDkdv <= 232448, "dkdv kernel exceeds the 227 KB shared-memory limit");
 
+template <bool kTS>   // kTS: P^T / dS^T reach the tensor core THROUGH TMEM (A operand in tensor memory, written in place of S^T / dP^T)
 __global__ void __launch_bounds__(kThreadsB, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                      const __grid_constant__ CUtensorMap tm_kv, BwdParams p) {
@@ -178,7 +180,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       auto issue_sdp = [&](int it) {
         const int st = it % kQStages, s = it & 1;
         ptx::mbar_wait(bar(1 + st), (uint32_t)((it / kQStages) & 1));   // Q, dO of this sub-tile landed
-        ptx::mbar_wait(bar(9 + s), (uint32_t)(((it >> 1) & 1) ^ 1));    // S^T[s], dP^T[s] read by the softmax warps
+        // kTS: S^T[s] / dP^T[s] hold P^T / dS^T of step it - 2 until its dV / dK UMMAs, issued earlier by this thread, have
+        // read them -- UMMAs of one thread execute in issue order, no barrier needed
+        if (!kTS) ptx::mbar_wait(bar(9 + s), (uint32_t)(((it >> 1) & 1) ^ 1));    // S^T[s], dP^T[s] read by the softmax warps
         ptx::tc_fence_after_sync();
         const uint32_t q_addr = q_ring + (uint32_t)(st * kQSlot);
 #pragma unroll
@@ -206,15 +210,17 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const uint32_t pt_addr = pds_smem + (uint32_t)(s * kPdsSlot);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {     // dV += P^T dO      (contraction over the 64 query rows)
-          const uint64_t a = ptx::make_kmajor_sw128_desc(pt_addr) + (uint64_t)(2 * ks);
           const uint64_t b = ptx::make_mnmajor_sw128_desc(q_addr + 2 * kT8, kT8) + (uint64_t)(128 * ks);
-          ptx::mma_bf16_ss(tmem_base + 256u, a, b, idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
+          if (kTS) ptx::mma_bf16_ts(tmem_base + 256u, tmem_base + (uint32_t)(s * 64 + ks * 8), b, idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
+          else ptx::mma_bf16_ss(tmem_base + 256u, ptx::make_kmajor_sw128_desc(pt_addr) + (uint64_t)(2 * ks), b, idesc_acc,
+                                (it > 0 || ks > 0) ? 1u : 0u);
         }
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {     // dK += dS^T Q
-          const uint64_t a = ptx::make_kmajor_sw128_desc(pt_addr + kT16) + (uint64_t)(2 * ks);
           const uint64_t b = ptx::make_mnmajor_sw128_desc(q_addr, kT8) + (uint64_t)(128 * ks);
-          ptx::mma_bf16_ss(tmem_base + 384u, a, b, idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
+          if (kTS) ptx::mma_bf16_ts(tmem_base + 384u, tmem_base + (uint32_t)(128 + s * 64 + ks * 8), b, idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
+          else ptx::mma_bf16_ss(tmem_base + 384u, ptx::make_kmajor_sw128_desc(pt_addr + kT16) + (uint64_t)(2 * ks), b, idesc_acc,
+                                (it > 0 || ks > 0) ? 1u : 0u);
         }
         ptx::tc_commit(bar(13 + s));     // P^T[s] / dS^T[s] may be rewritten
         ptx::tc_commit(bar(4 + st));     // Q / dO slot may be refilled
@@ -282,6 +288,22 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       ptx::tmem_ld_wait();                                     // dP^T values are in registers
       ptx::tc_fence_before_sync();
       softmax_bar();                                           // every thread holds its S^T / dP^T values
+      if (kTS) {
+        // P^T / dS^T rows go back into TMEM in place of S^T[s] / dP^T[s] (lane = key, one 32-bit column = two adjacent
+        // query rows; this thread owns packed columns [16 h, 16 h + 16)): no shared-memory store, no A-operand read
+        uint32_t pp[16], dd[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 d0 = *reinterpret_cast<const float4*>(mb + 64 + c0 + j);
+          pp[(j >> 1)] = pk2(pe[j], pe[j + 1]);
+          pp[(j >> 1) + 1] = pk2(pe[j + 2], pe[j + 3]);
+          dd[(j >> 1)] = pk2(pe[j] * (__uint_as_float(dv[j]) - d0.x), pe[j + 1] * (__uint_as_float(dv[j + 1]) - d0.y));
+          dd[(j >> 1) + 1] = pk2(pe[j + 2] * (__uint_as_float(dv[j + 2]) - d0.z), pe[j + 3] * (__uint_as_float(dv[j + 3]) - d0.w));
+        }
+        ptx::tmem_st_32x32b_x16(lane_addr + (uint32_t)(s * 64 + h * 16), pp);
+        ptx::tmem_st_32x32b_x16(lane_addr + (uint32_t)(128 + s * 64 + h * 16), dd);
+        ptx::tmem_st_wait();
+      } else {
       if (threadIdx.x == 64) ptx::mbar_arrive(bar(9 + s));    // -> S^T[s], dP^T[s] of step it + 2 may be issued
       ptx::mbar_wait(bar(13 + s), (uint32_t)(((it >> 1) & 1) ^ 1));   // dV / dK of step it - 2 consumed P^T[s], dS^T[s]
       const uint32_t prow = pds_smem + (uint32_t)(s * kPdsSlot + m * 128);
@@ -297,8 +319,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         sts_v4(prow + off, pk2(pe[j], pe[j + 1]), pk2(pe[j + 2], pe[j + 3]), pk2(pe[j + 4], pe[j + 5]), pk2(pe[j + 6], pe[j + 7]));
         sts_v4(prow + kT16 + off, pk2(de[0], de[1]), pk2(de[2], de[3]), pk2(de[4], de[5]), pk2(de[6], de[7]));
       }
+      }
       if (it + 1 < n_it && mwhich < 3) meta[((it + 1) & 1) * 192 + mwhich * 64 + mc] = nxt;
-      ptx::fence_proxy_async();                                // generic-proxy stores -> visible to the UMMA reads
+      if (kTS) ptx::tc_fence_before_sync();
+      else ptx::fence_proxy_async();                           // generic-proxy stores -> visible to the UMMA reads
       softmax_bar();
       if (threadIdx.x == 64) ptx::mbar_arrive(bar(11 + s));   // P^T[s], dS^T[s] ready
     }
@@ -350,6 +374,7 @@ constexpr int kStageKV = 4 * kT16;   // K lo | K hi | V lo | V hi   (128 keys)
 constexpr int kSmemDq = 1024 + 4 * kT16 + 2 * kStageKV + 2 * kT16 + 8 * 20 + 16;
 static_assert(kSmemDq <= 232448, "dq kernel exceeds the 227 KB shared-memory limit");
 
+template <bool kTS>   // kTS: dS reaches the tensor core through TMEM, written in place of dP
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsB, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                    const __grid_constant__ CUtensorMap tm_kv, BwdParams p) {
@@ -449,7 +474,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       auto issue_dp = [&](int j) {
         const int s = j & 1;
         ptx::mbar_wait(bar(13 + s), (uint32_t)((j >> 1) & 1));   // V of step j landed
-        ptx::mbar_wait(bar(10), (uint32_t)((j & 1) ^ 1));        // dP drained (step j - 1)
+        // kTS: dP's columns hold dS of step j - 1 until its dQ UMMAs -- issued BEFORE this call -- have read it (in order)
+        if (!kTS) ptx::mbar_wait(bar(10), (uint32_t)((j & 1) ^ 1));        // dP drained (step j - 1)
         ptx::tc_fence_after_sync();
         const uint32_t v_addr = kv_smem + (uint32_t)(s * kStageKV + 2 * kT16);
 #pragma unroll
@@ -467,20 +493,22 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       for (int i = 0; i < n_it; ++i) {
         if (i + 1 < n_it) {
           issue_s(i + 1);
-          issue_dp(i + 1);
+          if (!kTS) issue_dp(i + 1);
         }
         const int s = i & 1;
-        ptx::mbar_wait(bar(11), (uint32_t)(i & 1));              // dS of step i is in shared memory
+        ptx::mbar_wait(bar(11), (uint32_t)(i & 1));              // dS of step i is ready
         ptx::tc_fence_after_sync();
         const uint32_t k_addr = kv_smem + (uint32_t)(s * kStageKV);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {           // dQ += dS K     (K read as stored: keys are the contraction rows)
-          const uint64_t a = ptx::make_kmajor_sw128_desc(ds_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
           const uint64_t b = ptx::make_mnmajor_sw128_desc(k_addr, kT16) + (uint64_t)(128 * ks);
-          ptx::mma_bf16_ss(tmem_base + 384u, a, b, idesc_dq, (i > 0 || ks > 0) ? 1u : 0u);
+          if (kTS) ptx::mma_bf16_ts(tmem_base + 384u, tmem_base + (uint32_t)(256 + ks * 8), b, idesc_dq, (i > 0 || ks > 0) ? 1u : 0u);
+          else ptx::mma_bf16_ss(tmem_base + 384u, ptx::make_kmajor_sw128_desc(ds_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)),
+                                b, idesc_dq, (i > 0 || ks > 0) ? 1u : 0u);
         }
         ptx::tc_commit(bar(12));                   // dS may be rewritten
         ptx::tc_commit_multicast(bar(3 + s), 3);   // K slot consumed: tell BOTH producers
+        if (kTS && i + 1 < n_it) issue_dp(i + 1);  // dP of the next step goes where dS of this one was: after its dQ UMMAs
       }
       ptx::tc_commit(bar(17));
     }
@@ -537,7 +565,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         sv[32 + e] *= (__uint_as_float(d1[e]) - delta_row);
       }
       ptx::tc_fence_before_sync();
-      softmax_bar();
+      softmax_bar();                                         // every thread of the row pair has its dP values
+      if (kTS) {
+        // dS goes back into TMEM in place of dP (lane = row; one 32-bit column = two adjacent keys; this thread owns the
+        // packed columns [32 h, 32 h + 32) of the 64): the A operand of dQ += dS K costs no shared-memory traffic
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t pp[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pp[e] = pk2(sv[c * 32 + 2 * e], sv[c * 32 + 2 * e + 1]);
+          ptx::tmem_st_32x32b_x16(lane_addr + (uint32_t)(256 + h * 32 + c * 16), pp);
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
+      } else {
       if (threadIdx.x == 64) ptx::mbar_arrive(bar(10));      // dP drained -> dO V^T of step i + 1
       ptx::mbar_wait(bar(12), (uint32_t)((i & 1) ^ 1));      // dQ MMA of step i - 1 has consumed the dS buffer
 #pragma unroll
@@ -545,6 +586,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         sts_v4(ds_row + (((uint32_t)(j >> 3) ^ (uint32_t)(m & 7)) << 4), pk2(sv[j], sv[j + 1]), pk2(sv[j + 2], sv[j + 3]),
                pk2(sv[j + 4], sv[j + 5]), pk2(sv[j + 6], sv[j + 7]));
       ptx::fence_proxy_async();
+      }
       softmax_bar();
       if (threadIdx.x == 64) ptx::mbar_arrive(bar(11));      // dS ready -> dQ += dS K
     }
@@ -589,6 +631,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
 using namespace prl;
 
+namespace prl { namespace { int g_bwd_generation = [] { const char* e = getenv("PRL_ATTN_BWD"); return (e && e[0] == '1') ? 1 : 2; }(); } }
+
+extern "C" int prl_attn_set_bwd_generation(int32_t gen) {
+  PRL_CHECK_ARG(gen == 1 || gen == 2, "prl_attn_set_bwd_generation: 1 (P / dS operands through shared memory) or 2 (through TMEM)");
+  prl::g_bwd_generation = gen;
+  return PRL_OK;
+}
+
 extern "C" size_t prl_attn_varlen_bwd_workspace_bytes(int32_t T, int32_t n_q) { return (size_t)T * (size_t)n_q * sizeof(float); }
 
 // dqkv[T, dqkv_stride] <- gradients of the packed (roped) q | k | v given d_out; every row of every segment is written.
@@ -630,9 +680,15 @@ extern "C" int prl_attn_varlen_bwd(const void* qkv, int64_t qkv_stride, int32_t 
     rc = make_tmap_3d_bf16(&tdo, d_out_bf16, kD, (uint64_t)n_q, (uint64_t)T, kD * 2, (uint64_t)n_q * kD * 2, 64, (uint32_t)p.R, (uint32_t)p.nq);
     if (rc) return rc;
     static SmemAttr attr = {};
-    PRL_CUDA(ensure_smem(attn_bwd_dkdv_kernel, kSmemDkdv, attr));
     dim3 grid((unsigned)((max_seg_len + 127) / 128), (unsigned)n_kv, (unsigned)n_seg);
-    attn_bwd_dkdv_kernel<<<grid, kThreadsB, (size_t)kSmemDkdv, stream>>>(tq, tdo, tkv, p);
+    if (g_bwd_generation == 1) {
+      PRL_CUDA(ensure_smem(attn_bwd_dkdv_kernel<false>, kSmemDkdv, attr));
+      attn_bwd_dkdv_kernel<false><<<grid, kThreadsB, (size_t)kSmemDkdv, stream>>>(tq, tdo, tkv, p);
+    } else {
+      static SmemAttr attr2 = {};
+      PRL_CUDA(ensure_smem(attn_bwd_dkdv_kernel<true>, kSmemDkdv, attr2));
+      attn_bwd_dkdv_kernel<true><<<grid, kThreadsB, (size_t)kSmemDkdv, stream>>>(tq, tdo, tkv, p);
+    }
     PRL_LAUNCH_CHECK();
   }
   {
@@ -643,9 +699,15 @@ extern "C" int prl_attn_varlen_bwd(const void* qkv, int64_t qkv_stride, int32_t 
     rc = make_tmap_3d_bf16(&tdo, d_out_bf16, kD, (uint64_t)n_q, (uint64_t)T, kD * 2, (uint64_t)n_q * kD * 2, 64, (uint32_t)p.R, (uint32_t)p.nq);
     if (rc) return rc;
     static SmemAttr attr = {};
-    PRL_CUDA(ensure_smem(attn_bwd_dq_kernel, kSmemDq, attr));
     dim3 grid((unsigned)(((max_seg_len + p.nq - 1) / p.nq + 1) & ~1), (unsigned)n_kv, (unsigned)n_seg);
-    attn_bwd_dq_kernel<<<grid, kThreadsB, (size_t)kSmemDq, stream>>>(tq, tdo, tkv, p);
+    if (g_bwd_generation == 1) {
+      PRL_CUDA(ensure_smem(attn_bwd_dq_kernel<false>, kSmemDq, attr));
+      attn_bwd_dq_kernel<false><<<grid, kThreadsB, (size_t)kSmemDq, stream>>>(tq, tdo, tkv, p);
+    } else {
+      static SmemAttr attr2 = {};
+      PRL_CUDA(ensure_smem(attn_bwd_dq_kernel<true>, kSmemDq, attr2));
+      attn_bwd_dq_kernel<true><<<grid, kThreadsB, (size_t)kSmemDq, stream>>>(tq, tdo, tkv, p);
+    }
     PRL_LAUNCH_CHECK();
   }
   return PRL_OK;

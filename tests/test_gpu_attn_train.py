@@ -51,10 +51,13 @@ def _reference(qkv, d_out, bounds, n_q, n_kv):
     return out, dqkv
 
 
-def _run(dev, n_q, n_kv, lens, seed=0, pad_cols=0, fwd_gen=2):
+def _run(dev, n_q, n_kv, lens, seed=0, pad_cols=0, fwd_gen=2, bwd_gen=None):
+    """fwd_gen / bwd_gen: 1 = operands through shared memory, 2 = P / dS handed to the tensor core through TMEM (default)"""
     from pipelinerl_b200 import _lib
     o = _ops()
+    bwd_gen = fwd_gen if bwd_gen is None else bwd_gen
     _lib.check(o.lib.prl_attn_set_fwd_generation(fwd_gen))
+    _lib.check(o.lib.prl_attn_set_bwd_generation(bwd_gen))
     T = sum(lens)
     g = torch.Generator(device=dev).manual_seed(seed)
     width = (n_q + 2 * n_kv) * D
@@ -88,7 +91,8 @@ def _run(dev, n_q, n_kv, lens, seed=0, pad_cols=0, fwd_gen=2):
         scale = max(want_d[:, a:b].abs().max().item(), 1e-3)      # a single-token segment has dq = dk = 0 exactly
         res[name] = (dqkv[:, a:b].float() - want_d[:, a:b]).abs().max().item() / scale
     _lib.check(o.lib.prl_attn_set_fwd_generation(2))
-    print(f"[attn_train gen{fwd_gen}] n_q={n_q} n_kv={n_kv} lens={lens if len(lens) < 8 else str(lens[:6]) + '...'}: " +
+    _lib.check(o.lib.prl_attn_set_bwd_generation(2))
+    print(f"[attn_train fwd gen{fwd_gen} bwd gen{bwd_gen}] n_q={n_q} n_kv={n_kv} lens={lens if len(lens) < 8 else str(lens[:6]) + '...'}: " +
           " ".join(f"{k}={v:.2e}" for k, v in res.items()))
     assert res["out"] <= 2 ** -7, res
     assert res["lse"] <= 2e-3, res
@@ -123,10 +127,11 @@ def test_varlen_attention_qwen7b_heads_medium(cuda_device, lens):
     _run(cuda_device, 28, 4, lens, seed=11)
 
 
-@pytest.mark.parametrize("lens,fwd_gen", [([16384], 2), ([8192, 8192], 2), ([5000, 11000, 384], 2), ([16384], 1)])
-def test_varlen_attention_qwen7b_heads_16k(cuda_device, lens, fwd_gen):
+@pytest.mark.parametrize("lens,fwd_gen,bwd_gen", [([16384], 2, 2), ([8192, 8192], 2, 2), ([5000, 11000, 384], 2, 2),
+                                                  ([16384], 1, 1), ([16384], 2, 1), ([16384], 1, 2)])
+def test_varlen_attention_qwen7b_heads_16k(cuda_device, lens, fwd_gen, bwd_gen):
     """the trainer's micro-batch size (16 384 packed tokens) at Qwen2.5-7B's 28 / 4 heads"""
-    _run(cuda_device, 28, 4, lens, seed=5, fwd_gen=fwd_gen)
+    _run(cuda_device, 28, 4, lens, seed=5, fwd_gen=fwd_gen, bwd_gen=bwd_gen)
 
 
 def test_attention_output_rows_outside_every_segment_are_untouched(cuda_device):
