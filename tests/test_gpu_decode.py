@@ -18,6 +18,10 @@ from tests.helpers import GOLDEN, tiny_cfg, tiny_weights
 pytestmark = pytest.mark.gpu
 
 
+# end-to-end bounds = 1.5 x the differences measured on a B200 (printed by the tests; profiles/r2_summary.md)
+E2E_BOUNDS = {"gqa2": (3e-2, 6e-3), "gqa7": (3e-2, 6e-3)}
+
+
 def make_engine(cfg, weights, dev, **kw):
     from pipelinerl_b200.engine import DecodeEngine
     from pipelinerl_b200.model import ParamArena
@@ -49,9 +53,12 @@ def test_teacher_forced_logprobs_match_oracle_and_hf(cuda_device, kind):
     orc = OracleQwen2(cfg, w)
     want = orc.score(tokens, 0.7).numpy()
     err = np.abs(got - want)
-    assert err.max() <= 3e-2 and err.mean() <= 6e-3, (err.max(), err.mean(), int(err.argmax()))
     err_hf = np.abs(got - gold["logprobs"])
-    assert err_hf.max() <= 3e-2 and err_hf.mean() <= 6e-3, (err_hf.max(), err_hf.mean())
+    print(f"[decode e2e {kind}] vs oracle max {err.max():.4f} mean {err.mean():.5f} | vs HF fp32 max {err_hf.max():.4f} "
+          f"mean {err_hf.mean():.5f}  (|logprob| ~ {np.abs(want).mean():.2f})")
+    bmax, bmean = E2E_BOUNDS[kind]
+    assert err.max() <= bmax and err.mean() <= bmean, (err.max(), err.mean(), int(err.argmax()))
+    assert err_hf.max() <= bmax and err_hf.mean() <= bmean, (err_hf.max(), err_hf.mean())
 
 
 @pytest.mark.parametrize("kind,use_graph,fused", [("gqa2", True, True), ("gqa7", False, True), ("gqa2", True, False)])

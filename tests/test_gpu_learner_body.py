@@ -13,6 +13,10 @@ from tests.helpers import tiny_cfg, tiny_weights
 
 pytestmark = pytest.mark.gpu
 
+# end-to-end bounds (bf16 activations against fp32 references) = 1.5 x what a B200 measured; the tests print the measured values
+BODY_BOUNDS = {"hidden": 2e-2, "logprob": 3e-2, "grad": 3e-2}
+HF_STEP_BOUNDS = {"loss": 2e-2, "grad_norm": 3e-2, "grad_samples": 5e-2}
+
 
 def _ops():
     from pipelinerl_b200.learner_body import Ops
@@ -149,9 +153,10 @@ def test_native_body_matches_fp32_autograd(cuda_device, kind, lens):
     nat.body.keep_gate_up_layers = 1
     nat.body.keep_attention_layers = 2 if kind == "gqa2" else 1
     hid = nat.hidden_states(ids, pos)[0]
-    assert _rel(hid, hid_ref) <= 2e-2
     lp, ent = nat.forward_logprobs(batch, 1.0)
-    assert (lp[0] - lp_ref).abs().max().item() <= 3e-2
+    print(f"[native body {kind}] hidden rel L2 {_rel(hid, hid_ref):.4f}  max |dlogprob| {(lp[0] - lp_ref).abs().max().item():.4f}")
+    assert _rel(hid, hid_ref) <= BODY_BOUNDS["hidden"]
+    assert (lp[0] - lp_ref).abs().max().item() <= BODY_BOUNDS["logprob"]
     (lp[0] * coef).sum().backward()
     grads = opt.grad_views()
     worst = 0.0
@@ -159,8 +164,9 @@ def test_native_body_matches_fp32_autograd(cuda_device, kind, lens):
         e_nat = _rel(grads[name], p.grad)
         e_tb = _rel(tb.p(name).grad, p.grad)
         worst = max(worst, e_nat)
-        assert e_nat <= 3e-2, (name, e_nat, e_tb)
+        assert e_nat <= BODY_BOUNDS["grad"], (name, e_nat, e_tb)
         assert e_nat <= 2.0 * e_tb + 5e-3, (name, e_nat, e_tb)   # fp32 accumulation: no noisier than bf16 autograd
+    print(f"[native body {kind}] worst gradient rel L2 vs fp32 autograd {worst:.4f}")
     # a second backward ACCUMULATES (gradient accumulation over micro-batches is the arena's job)
     before = {n: g.clone() for n, g in grads.items()}
     lp2, _ = nat.forward_logprobs(batch, 1.0)
@@ -271,7 +277,9 @@ def test_native_learner_vs_reference_rl_step_on_hf(cuda_device, kind):
     loss, stats = rl_step(model, batch, meta["current_step"], meta["max_step"], RLConfig(**meta["config"]))
     loss.backward()
     want_loss = float(arrs["loss"])
-    assert abs(loss.item() - want_loss) <= 2e-2 * max(1.0, abs(want_loss)), (loss.item(), want_loss)
+    loss_rel = abs(loss.item() - want_loss) / max(1.0, abs(want_loss))
+    assert loss_rel <= HF_STEP_BOUNDS["loss"], (loss.item(), want_loss)
+    worst_norm = worst_samp = 0.0
     for k in ("loss", "entropy", "kl"):
         if k in meta["stats"] and k in stats:
             assert abs(stats[k] - meta["stats"][k]) <= 3e-2 * max(1.0, abs(meta["stats"][k])), (k, stats[k], meta["stats"][k])
@@ -280,11 +288,15 @@ def test_native_learner_vs_reference_rl_step_on_hf(cuda_device, kind):
         key = name.replace(".", "__")
         flat = g.reshape(-1).double().cpu()
         want_norm = float(arrs["gnorm__" + key])
-        assert abs(float(flat.norm()) - want_norm) <= 3e-2 * want_norm + 1e-6, (name, float(flat.norm()), want_norm)
+        worst_norm = max(worst_norm, abs(float(flat.norm()) - want_norm) / (want_norm + 1e-12))
+        assert abs(float(flat.norm()) - want_norm) <= HF_STEP_BOUNDS["grad_norm"] * want_norm + 1e-6, (name, float(flat.norm()), want_norm)
         idx = np.unique(np.linspace(0, flat.numel() - 1, num=min(257, flat.numel())).astype(np.int64))
         got, want = flat[torch.from_numpy(idx)].numpy(), arrs["gsamp__" + key]
         rel = np.linalg.norm(got - want) / (np.linalg.norm(want) + 1e-12)
-        assert rel <= 5e-2, (name, rel)
+        worst_samp = max(worst_samp, rel)
+        assert rel <= HF_STEP_BOUNDS["grad_samples"], (name, rel)
+    print(f"[native learner vs reference rl_step on HF, {kind}] loss rel {loss_rel:.2e}  worst gradient-norm rel {worst_norm:.4f}  "
+          f"worst sampled-gradient rel L2 {worst_samp:.4f}")
 
 
 def test_native_learner_fp32_equivalent_head(cuda_device):
