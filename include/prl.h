@@ -318,6 +318,13 @@ int prl_embed_scatter_add(float* dtable, const int64_t* ids, const void* dh, int
 int prl_gemm_ex(const void* A, int64_t lda, int32_t a_mn_major, const void* B, int64_t ldb, int32_t b_mn_major,
                 int64_t M, int64_t N, int64_t K, void* C, int64_t ldc, int32_t c_is_f32, int32_t accumulate,
                 const void* bias, const void* residual, int64_t ldr, float alpha, prl_stream_t stream);
+/* gate_up GEMM with SwiGLU in its epilogue (the MLP of the HF block the reference runs, rl/__init__.py:190-207):
+ * act[M, I] = silu(X Wg^T) * (X Wu^T) with W = [Wg; Wu] ([2 I, K], as gate_up_proj is stored); the two CTAs of a pair stage
+ * the gate rows and the up rows of the same 128 features, so one accumulator row holds both halves and the activation
+ * never makes a round trip through HBM.  gate_up ([M, 2 I] bf16) is written too when non-NULL (kept for the backward).
+ * Bit-identical to prl_gemm_ex + prl_silu_mul_fwd.  I must be a multiple of 128. */
+int prl_gemm_swiglu(const void* X, int64_t ldx, const void* W, int64_t ldw, int64_t M, int64_t I, int64_t K, void* act,
+                    int64_t ld_act, void* gate_up /*or NULL*/, int64_t ld_gate_up, prl_stream_t stream);
 /* bf16 [rows, cols] (row stride ld_in) -> [cols, rows] (row stride ld_out): stages the K-major operands of wgrad. */
 int prl_transpose_bf16(const void* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
                        prl_stream_t stream);

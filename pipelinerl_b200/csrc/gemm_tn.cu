@@ -48,6 +48,12 @@ struct TnParams {
   const __nv_bfloat16* residual;  // [M, ldr] or NULL
   int64_t ldr;
   float alpha;
+  // SwiGLU epilogue (swiglu_I > 0): B = [gate rows | up rows] of gate_up_proj; the pair's two CTAs stage the gate rows and
+  // the up rows of the SAME 128 features, so one accumulator row holds gate (columns 0..127) and up (128..255):
+  //   act[row, f] = silu(gate) * up   is written from the epilogue (bf16), gate_up itself to C only when C != NULL
+  int64_t swiglu_I;
+  __nv_bfloat16* act;      // [M, ld_act]
+  int64_t ld_act;
   // head epilogue (kHead): logits never leave TMEM/registers
   const int64_t* targets;  // [M] or NULL
   float4* head_part;       // [n_tiles, M]: (max, sum exp, sum exp*z, target logit or -inf) of one 256-column vocabulary tile
@@ -115,7 +121,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         int tm, tn;
         tile_coords(t, p, tm, tn);
         const int a_row = tm * kTile + (int)rank * kHalf;
-        const int b_row = tn * kTile + (int)rank * kHalf;
+        const int b_row = p.swiglu_I ? tn * kHalf + (int)rank * (int)p.swiglu_I : tn * kTile + (int)rank * kHalf;
         for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (uint32_t)((it / kStages) & 1);
@@ -227,6 +233,40 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           }
         }
         if (row_ok) p.head_part[(int64_t)tn * p.M + row] = make_float4(m, ssum, usum, zt);
+      } else if (p.swiglu_I) {
+        // columns 0..127 of the accumulator = gate, 128..255 = up of features [tn * 128, tn * 128 + 128)
+        const int64_t f0 = (int64_t)tn * kHalf;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kHalf; c0 += 32) {
+          uint32_t rg[32], ru[32];
+          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTile + c0), rg);
+          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTile + kHalf + c0), ru);
+          ptx::tmem_ld_wait();
+          if (!row_ok) continue;
+          __nv_bfloat16* ap = p.act + row * p.ld_act + f0 + c0;
+          __nv_bfloat16* gp = p.C ? reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + f0 + c0 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 ua, ug, uu;
+            __nv_bfloat162* ha = reinterpret_cast<__nv_bfloat162*>(&ua);
+            __nv_bfloat162* hg = reinterpret_cast<__nv_bfloat162*>(&ug);
+            __nv_bfloat162* hu = reinterpret_cast<__nv_bfloat162*>(&uu);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              // same rounding points as the two-kernel path: gate_up is rounded to bf16 first, SiLU * up is taken of the
+              // ROUNDED values (prl_silu_mul_fwd reads the bf16 tensor), so fused and unfused results are bit-identical
+              hg[e] = __floats2bfloat162_rn(__uint_as_float(rg[j + 2 * e]), __uint_as_float(rg[j + 2 * e + 1]));
+              hu[e] = __floats2bfloat162_rn(__uint_as_float(ru[j + 2 * e]), __uint_as_float(ru[j + 2 * e + 1]));
+              const float2 g = __bfloat1622float2(hg[e]), u = __bfloat1622float2(hu[e]);
+              ha[e] = __floats2bfloat162_rn(g.x / (1.f + __expf(-g.x)) * u.x, g.y / (1.f + __expf(-g.y)) * u.y);
+            }
+            *reinterpret_cast<uint4*>(ap + j) = ua;
+            if (gp) {
+              *reinterpret_cast<uint4*>(gp + j) = ug;
+              *reinterpret_cast<uint4*>(gp + p.swiglu_I + j) = uu;
+            }
+          }
+        }
       } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < kTile; c0 += 32) {
@@ -439,6 +479,40 @@ extern "C" int prl_gemm_ex(const void* A, int64_t lda, int32_t a_mn_major, const
   if (rc) return rc;
   rc = b_mn_major ? make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, kBK)
                   : make_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBK, kHalf);
+  if (rc) return rc;
+  const int smem = kStages * kStageBytes + 1024 + 8 * (2 * kStages + 4) + 16;
+  static SmemAttr smem_attr = {};
+  PRL_CUDA(ensure_smem(gemm_tn_kernel<false>, smem, smem_attr));
+  const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
+  int clusters = num_sms() / 2;
+  if (tiles < clusters) clusters = (int)tiles;
+  gemm_tn_kernel<false><<<dim3((unsigned)(2 * clusters)), dim3(kThreadsTN), (size_t)smem, (cudaStream_t)stream_>>>(ta, tb, tb, p);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
+// gate_up GEMM with the SwiGLU activation in its epilogue: act[M, I] = silu(X Wg^T) * (X Wu^T), W = [Wg; Wu] ([2 I, K]).
+// gate_up (bf16 [M, 2 I], may be NULL) is written as well when the backward will need it.
+extern "C" int prl_gemm_swiglu(const void* X, int64_t ldx, const void* W, int64_t ldw, int64_t M, int64_t I, int64_t K,
+                               void* act, int64_t ld_act, void* gate_up, int64_t ld_gu, prl_stream_t stream_) {
+  PRL_CHECK_ARG(X && W && act, "prl_gemm_swiglu: NULL argument");
+  PRL_CHECK_ARG(M >= 1 && I >= kHalf && I % kHalf == 0 && K >= 8, "prl_gemm_swiglu: need I %% 128 == 0 (M=%lld I=%lld K=%lld)",
+                (long long)M, (long long)I, (long long)K);
+  PRL_CHECK_ARG(ldx >= K && ldw >= K && ldx % 8 == 0 && ldw % 8 == 0 && ld_act >= I && ld_act % 8 == 0 &&
+                    (!gate_up || (ld_gu >= 2 * I && ld_gu % 8 == 0)),
+                "prl_gemm_swiglu: row strides must cover a row and be multiples of 8 elements");
+  TnParams p = {};
+  p.M = M; p.N = 2 * I; p.K = K;
+  p.kblocks = (int)((K + kBK - 1) / kBK);
+  p.k_wrap = p.kblocks;
+  p.m_tiles = (int)((M + kTile - 1) / kTile);
+  p.n_tiles = (int)(I / kHalf);
+  p.C = gate_up; p.ldc = ld_gu; p.alpha = 1.f;
+  p.swiglu_I = I; p.act = (__nv_bfloat16*)act; p.ld_act = ld_act;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d_bf16(&ta, X, (uint64_t)K, (uint64_t)M, (uint64_t)ldx * 2, kBK, kHalf);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tb, W, (uint64_t)K, (uint64_t)(2 * I), (uint64_t)ldw * 2, kBK, kHalf);
   if (rc) return rc;
   const int smem = kStages * kStageBytes + 1024 + 8 * (2 * kStages + 4) + 16;
   static SmemAttr smem_attr = {};

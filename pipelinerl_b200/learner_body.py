@@ -94,6 +94,16 @@ class Ops:
         _lib.check(self.lib.prl_rope_inplace(qkv.data_ptr(), qkv.stride(0), T, n_heads, head_dim, pos.data_ptr(),
                                              inv_freq.data_ptr(), float(sign), _lib.stream_ptr()))
 
+    def gemm_swiglu(self, x, W, need_gate_up=True):
+        """(gate_up [T, 2I] or None, act [T, I]) with SiLU(gate) * up computed in the GEMM epilogue"""
+        T, K = x.shape
+        I = W.shape[0] // 2
+        act = torch.empty(T, I, dtype=torch.bfloat16, device=x.device)
+        gu = torch.empty(T, 2 * I, dtype=torch.bfloat16, device=x.device) if need_gate_up else None
+        _lib.check(self.lib.prl_gemm_swiglu(x.data_ptr(), x.stride(0), W.data_ptr(), W.stride(0), T, I, K, act.data_ptr(), I,
+                                            gu.data_ptr() if gu is not None else None, 2 * I, _lib.stream_ptr()))
+        return gu, act
+
     def silu_mul(self, gu):
         T, two_i = gu.shape
         act = torch.empty(T, two_i // 2, dtype=torch.bfloat16, device=gu.device)
@@ -201,12 +211,15 @@ class NativeBody:
         h2 = o.gemm(attn, w[p + "o_proj.weight"], residual=h)
         return x1, rstd1, attn, (qkv, lse) if need_grad else None, h2
 
-    def _mlp_half(self, l, h2, need_out=True):
+    def _mlp_half(self, l, h2, need_out=True, need_gate_up=True):
         c, o, w = self.cfg, self.ops, self.w
         p = f"layers.{l}."
         x2, rstd2 = o.rmsnorm(h2, w[p + "post_attention_layernorm.weight"], c.rms_eps)
-        gu = o.gemm(x2, w[p + "gate_up_proj.weight"])
-        act = o.silu_mul(gu)
+        if c.intermediate_size % 128 == 0:      # SiLU * up in the gate_up GEMM's epilogue: no activation round trip
+            gu, act = o.gemm_swiglu(x2, w[p + "gate_up_proj.weight"], need_gate_up=need_gate_up)
+        else:
+            gu = o.gemm(x2, w[p + "gate_up_proj.weight"])
+            act = o.silu_mul(gu)
         h3 = o.gemm(act, w[p + "down_proj.weight"], residual=h2) if need_out else None  # the backward only needs act
         return x2, rstd2, gu, act, h3
 
@@ -272,7 +285,7 @@ class NativeBody:
         for l in range(c.num_layers):
             keep_attn = keep and l < self.keep_attention_layers
             _, _, attn, graph, h2 = self._attn_half(l, h, pos, bounds, need_grad=keep_attn)
-            _, _, gu, _, h3 = self._mlp_half(l, h2)
+            _, _, gu, _, h3 = self._mlp_half(l, h2, need_gate_up=keep and l < self.keep_gate_up_layers)
             if keep:
                 inputs.append(h)
                 kept.append((attn, graph, h2, gu if l < self.keep_gate_up_layers else None) if keep_attn else None)

@@ -124,3 +124,25 @@ def test_gemm_mn_major_operands(cuda_device, M, N, K, a_mn, b_mn):
     assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item() + 1e-6
     ref = gemm_ex(A, False, B, False, M, N, K)
     assert torch.equal(got, ref)    # same products, same k order: bitwise equal to the K-major path
+
+
+@pytest.mark.parametrize("T,K,I", [(300, 512, 1024), (257, 896, 1152), (1024, 3584, 18944), (5, 256, 128)])
+def test_gemm_swiglu_epilogue_is_bit_identical_to_gemm_plus_silu(cuda_device, T, K, I):
+    """gate_up GEMM with SiLU(gate) * up in its epilogue (prl_gemm_swiglu: the pair's two CTAs stage the gate rows and the up
+    rows of the same 128 features) == prl_gemm_ex followed by prl_silu_mul_fwd, bit for bit, for both outputs."""
+    from pipelinerl_b200.learner_body import Ops
+    o = Ops()
+    g = torch.Generator(device=cuda_device).manual_seed(T + K + I)
+    x = (torch.randn(T, K, generator=g, device=cuda_device) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(2 * I, K, generator=g, device=cuda_device) * K ** -0.5).to(torch.bfloat16)
+    gu_ref = o.gemm(x, W)
+    act_ref = o.silu_mul(gu_ref)
+    gu, act = o.gemm_swiglu(x, W, need_gate_up=True)
+    torch.cuda.synchronize()
+    assert torch.equal(gu, gu_ref) and torch.equal(act, act_ref)
+    none, act2 = o.gemm_swiglu(x, W, need_gate_up=False)
+    assert none is None and torch.equal(act2, act_ref)
+    # and against fp32 math
+    ref = x.float() @ W.float().t()
+    want = torch.nn.functional.silu(ref[:, :I]) * ref[:, I:]
+    assert (act.float() - want).abs().max().item() <= 2 ** -6 * want.abs().max().item()
