@@ -286,30 +286,18 @@ def run_ours(args):
     if rank == 0 and not args.no_components:
         out["components"] = bench_components(dev, peak)
     if rank == 0 and world == 1 and not args.no_components:
-        # hot path 2 end to end (rl_step -> backward -> fused AdamW) on the same model: needs the whole GPU.  Only in
-        # the single-GPU run: under torchrun the other ranks are already waiting in the final barrier
+        # hot path 2 end to end (rl_step -> backward -> fused AdamW) on the same model: needs the whole GPU, and runs in a
+        # CHILD process (tools/train_bench.py) so that nothing it does can cost the headline line
         import gc
         del eng, attn_all_layers
         gc.collect()
         torch.cuda.empty_cache()
-        try:
-            sys.path.insert(0, str(ROOT / "tools"))
-            import train_bench
-            # distributed=False: under torchrun only rank 0 is here, so the trainer must not enter any collective
-            out["components"]["trainer_step"] = train_bench.measure(steps=2, warmup=1, dev=dev, log=False,
-                                                                    distributed=False)
-        except Exception as e:  # noqa: BLE001  (informational component: the headline line must still print)
-            out["components"]["trainer_step"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        out["components"]["trainer_step"] = run_tool(["tools/train_bench.py", "--steps", "2", "--warmup", "1"], 600)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, budget_s=25.0)
     if rank == 0 and world == 1 and not args.no_components and not args.no_rollout:
         # whole rollouts through the plugin API: prefill + decode growing 8192 -> 16384 (not a static-state microbench)
-        try:
-            sys.path.insert(0, str(ROOT / "tools"))
-            import rollout_bench
-            out["components"]["rollout_full"] = rollout_bench.measure(dev=dev, max_tokens=args.rollout_tokens)
-        except Exception as e:  # noqa: BLE001
-            out["components"]["rollout_full"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        out["components"]["rollout_full"] = run_tool(["tools/rollout_bench.py", "--max-tokens", str(args.rollout_tokens)], 600)
     if rank == 0 and world == 1 and not args.no_components and not args.no_vllm:
         out.setdefault("components", {})["vllm_baseline"] = vllm_baseline(args)
     if world > 1 and not args.no_components and not args.no_pipeline:
@@ -337,43 +325,59 @@ def default_splits(world: int) -> list[int]:
 
 
 def run_pipeline_splits(args, world, rank, headline):
-    """All ranks.  A watchdog bounds the whole component: if a split hangs (a rank died inside a collective), rank 0
-    still prints the headline line with the error recorded and every rank exits 0."""
+    """All ranks.  Every rank runs its part of a split in a CHILD process (tools/split_bench.py with this rank's
+    RANK / LOCAL_RANK / WORLD_SIZE and a fresh rendezvous port): a crash, a CUDA error or a hang inside the split can only
+    cost the component -- the parent ranks keep their process group, time the child out, and rank 0 still prints the
+    headline line."""
     import torch.distributed as dist
-    sys.path.insert(0, str(ROOT / "tools"))
-    import split_bench
     splits = [int(x) for x in args.splits.split(",") if x] or default_splits(world)
     splits = [m for m in splits if 1 <= m < world]
     results = {"note": "samplers generate (64 seqs x 8192-token context each) WHILE the learners train 2 x 16384-token "
                        "micro-batches per learner per optimizer step and push weights after every step; "
-                       "fp32-equivalent lm_head on samplers and learners"}
-    deadline_s = 330.0 * len(splits)
-
-    def bail():
-        if rank == 0:
-            results["error"] = f"watchdog: split run exceeded {deadline_s:.0f} s"
-            headline.setdefault("components", {})["pipeline"] = results
-            print(json.dumps(headline), flush=True)
-        else:
-            time.sleep(3.0)
-        os._exit(0)
-    dog = threading.Timer(deadline_s, bail)
-    dog.daemon = True
-    dog.start()
-    for m in splits:
+                       "fp32-equivalent lm_head on samplers and learners; each split runs in child processes of the ranks"}
+    base_port = int(os.environ.get("MASTER_PORT", "29500"))
+    for k, m in enumerate(splits):
         key = f"{world - m}+{m}"
-        ok = torch_ok_flag = 1
+        env = dict(os.environ, MASTER_PORT=str(base_port + 101 + k), NCCL_DEBUG="WARN", NCCL_DEBUG_FILE="/dev/stderr")
+        cmd = [sys.executable, str(ROOT / "tools" / "split_bench.py"), "--learners", str(m), "--updates", "3",
+               "--context", str(args.context), "--batch", str(args.batch)]
+        t0 = time.time()
+        res = None
         try:
-            res = split_bench.run_split(m, updates=3, context=args.context, batch=args.batch)
+            done = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
+            lines = [l for l in done.stdout.splitlines() if l.startswith("{")]
+            if done.returncode == 0 and lines:
+                res = json.loads(lines[-1])
+            elif rank == 0 or done.returncode != 0:
+                res = {"error": f"rank {rank}: rc={done.returncode}: {(done.stderr or done.stdout)[-400:]}"}
+        except subprocess.TimeoutExpired:
+            res = {"error": f"rank {rank}: split timed out after 420 s"}
         except Exception as e:  # noqa: BLE001
             res = {"error": f"rank {rank}: {type(e).__name__}: {str(e)[:300]}"}
-            ok = 0
         if rank == 0:
+            if isinstance(res, dict):
+                res["wall_s"] = round(time.time() - t0, 1)
             results[key] = res
-        if not ok:          # a failed rank cannot rejoin the collectives of the next split: stop here (watchdog covers peers)
-            break
-    dog.cancel()
+        dist.barrier()          # the parents stay in step between splits
     return results if rank == 0 else None
+
+
+def run_tool(argv, timeout_s):
+    """one of tools/*.py in a child process -> its last JSON line (or an error record); the GPU must be free"""
+    t0 = time.time()
+    try:
+        res = subprocess.run([sys.executable, str(ROOT / argv[0]), *argv[1:]], capture_output=True, text=True, timeout=timeout_s,
+                             env=dict(os.environ, WORLD_SIZE="1", RANK="0", LOCAL_RANK=os.environ.get("LOCAL_RANK", "0")))
+        lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+        if res.returncode != 0 or not lines:
+            return {"error": f"rc={res.returncode}: {(res.stderr or res.stdout)[-400:]}", "wall_s": round(time.time() - t0, 1)}
+        out = json.loads(lines[-1])
+        out["wall_s"] = round(time.time() - t0, 1)
+        return out
+    except subprocess.TimeoutExpired:
+        return {"error": f"timeout after {timeout_s} s", "wall_s": round(time.time() - t0, 1)}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
 
 
 def vllm_baseline(args):
