@@ -47,6 +47,9 @@ struct BwdParams {
   int nq;                        // query tokens per tile: 128 / R (dq kernel) or 64 / R (dkdv kernel)
   int col_k, col_v;              // element column of K / V head 0 inside a qkv row
   float scale_log2, sm_scale;
+  const __nv_bfloat16* q_base;   // qkv (query heads first) and d_out, for the kernels that stage rows themselves
+  const __nv_bfloat16* do_base;
+  int64_t q_stride, do_stride;
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -374,7 +377,11 @@ constexpr int kStageKV = 4 * kT16;   // K lo | K hi | V lo | V hi   (128 keys)
 constexpr int kSmemDq = 1024 + 4 * kT16 + 2 * kStageKV + 2 * kT16 + 8 * 20 + 16;
 static_assert(kSmemDq <= 232448, "dq kernel exceeds the 227 KB shared-memory limit");
 
-template <bool kTS>   // kTS: dS reaches the tensor core through TMEM, written in place of dP
+// kGen 1: every operand through shared memory.  2: dS reaches the tensor core through TMEM, written in place of dP.
+// 3: additionally the STATIONARY operands Q and dO live in TMEM for the whole kernel (64 packed columns each, staged once
+//    by the softmax threads straight from global memory; S single-buffered to make room): the A operands of all three
+//    UMMAs of a step then cost no shared-memory bandwidth -- 288 -> 160 KB of shared-memory traffic per step.
+template <int kGen>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsB, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                    const __grid_constant__ CUtensorMap tm_kv, BwdParams p) {
@@ -389,6 +396,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   // 0 q_full | 1,2 k_full | 3,4 k_empty | 5,6 s_full | 7,8 s_empty | 9 dp_full | 10 dp_empty | 11 ds_full | 12 ds_empty |
   // 13,14 v_full | 15,16 v_empty | 17 dq_done
   const uint32_t tmem_slot = bar(18);
+  constexpr bool kTS = kGen >= 2;
+  constexpr bool kQT = kGen >= 3;
+  // TMEM columns: gen 1/2: S[2] 0,128 | dP 256 | dQ 384.   gen 3: S 0 | dP 128 | dQ 256 | Q 384 | dO 448
+  constexpr uint32_t cDP = kQT ? 128u : 256u, cDQ = kQT ? 256u : 384u, cQ = 384u, cDO = 448u;
 
   const int qtile = (int)(gridDim.x - 1 - blockIdx.x);  // heaviest (latest) query tiles first; pairs stay adjacent
   const int kvh = blockIdx.y, z = blockIdx.z;
@@ -426,11 +437,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(bar(0), (uint32_t)(4 * 128 * p.R * p.nq));
-      ptx::tma_load_3d(q_smem, &tm_q, 0, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
-      ptx::tma_load_3d(q_smem + kT16, &tm_q, 64, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
-      ptx::tma_load_3d(do_smem, &tm_do, 0, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
-      ptx::tma_load_3d(do_smem + kT16, &tm_do, 64, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
+      if (!kQT) {
+        ptx::mbar_arrive_expect_tx(bar(0), (uint32_t)(4 * 128 * p.R * p.nq));
+        ptx::tma_load_3d(q_smem, &tm_q, 0, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
+        ptx::tma_load_3d(q_smem + kT16, &tm_q, 64, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
+        ptx::tma_load_3d(do_smem, &tm_do, 0, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
+        ptx::tma_load_3d(do_smem + kT16, &tm_do, 64, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
+      }
       // this CTA fetches ONE of the two 64-key pages of a step and multicasts it to both CTAs of the pair
       auto load_page = [&](int it, int kv) {
         const int s = it & 1;
@@ -460,16 +473,19 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int s = j & 1;
         const uint32_t ph = (uint32_t)((j >> 1) & 1);
         ptx::mbar_wait(bar(1 + s), ph);            // K of step j landed
-        ptx::mbar_wait(bar(7 + s), ph ^ 1u);       // S[s] drained (step j - 2)
+        if (kQT) ptx::mbar_wait(bar(7), (uint32_t)((j & 1) ^ 1));   // the single S buffer was read (step j - 1)
+        else ptx::mbar_wait(bar(7 + s), ph ^ 1u);                   // S[s] drained (step j - 2)
         ptx::tc_fence_after_sync();
         const uint32_t k_addr = kv_smem + (uint32_t)(s * kStageKV);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a = ptx::make_kmajor_sw128_desc(q_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
           const uint64_t b = ptx::make_kmajor_sw128_desc(k_addr + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
-          ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 128), a, b, idesc_kk, ks > 0 ? 1u : 0u);
+          if (kQT) ptx::mma_bf16_ts(tmem_base, tmem_base + cQ + (uint32_t)(ks * 8), b, idesc_kk, ks > 0 ? 1u : 0u);
+          else ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 128),
+                                ptx::make_kmajor_sw128_desc(q_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)), b,
+                                idesc_kk, ks > 0 ? 1u : 0u);
         }
-        ptx::tc_commit(bar(5 + s));
+        ptx::tc_commit(bar(kQT ? 5 : 5 + s));
       };
       auto issue_dp = [&](int j) {
         const int s = j & 1;
@@ -480,9 +496,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const uint32_t v_addr = kv_smem + (uint32_t)(s * kStageKV + 2 * kT16);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a = ptx::make_kmajor_sw128_desc(do_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
           const uint64_t b = ptx::make_kmajor_sw128_desc(v_addr + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
-          ptx::mma_bf16_ss(tmem_base + 256u, a, b, idesc_kk, ks > 0 ? 1u : 0u);
+          if (kQT) ptx::mma_bf16_ts(tmem_base + cDP, tmem_base + cDO + (uint32_t)(ks * 8), b, idesc_kk, ks > 0 ? 1u : 0u);
+          else ptx::mma_bf16_ss(tmem_base + cDP,
+                                ptx::make_kmajor_sw128_desc(do_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)), b,
+                                idesc_kk, ks > 0 ? 1u : 0u);
         }
         ptx::tc_commit(bar(9));
         ptx::tc_commit_multicast(bar(15 + s), 3);  // V slot consumed: tell BOTH producers
@@ -502,8 +520,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {           // dQ += dS K     (K read as stored: keys are the contraction rows)
           const uint64_t b = ptx::make_mnmajor_sw128_desc(k_addr, kT16) + (uint64_t)(128 * ks);
-          if (kTS) ptx::mma_bf16_ts(tmem_base + 384u, tmem_base + (uint32_t)(256 + ks * 8), b, idesc_dq, (i > 0 || ks > 0) ? 1u : 0u);
-          else ptx::mma_bf16_ss(tmem_base + 384u, ptx::make_kmajor_sw128_desc(ds_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)),
+          if (kTS) ptx::mma_bf16_ts(tmem_base + cDQ, tmem_base + cDP + (uint32_t)(ks * 8), b, idesc_dq, (i > 0 || ks > 0) ? 1u : 0u);
+          else ptx::mma_bf16_ss(tmem_base + cDQ, ptx::make_kmajor_sw128_desc(ds_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)),
                                 b, idesc_dq, (i > 0 || ks > 0) ? 1u : 0u);
         }
         ptx::tc_commit(bar(12));                   // dS may be rewritten
@@ -526,31 +544,56 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const float lse_row = valid ? __ldg(p.lse + stat) : INFINITY;   // padding rows: P = 0
     const float delta_row = valid ? __ldg(p.delta + stat) : 0.f;
     const uint32_t ds_row = ds_smem + (uint32_t)(h * kT16 + m * 128);
+    if (kQT) {
+      // stage this row's half (64 head-dim elements = 32 packed columns) of Q and dO in TMEM, straight from global memory
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const __nv_bfloat16* src = which == 0
+            ? p.q_base + (int64_t)(row0 + qi) * p.q_stride + (kvh * p.R + r) * kD + h * 64
+            : p.do_base + (int64_t)(row0 + qi) * p.do_stride + (kvh * p.R + r) * kD + h * 64;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t w[16];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint4 u = valid ? ld_stream_u4(reinterpret_cast<const uint4*>(src + c * 32) + e) : make_uint4(0u, 0u, 0u, 0u);
+            w[4 * e] = u.x; w[4 * e + 1] = u.y; w[4 * e + 2] = u.z; w[4 * e + 3] = u.w;
+          }
+          ptx::tmem_st_32x32b_x16(lane_addr + (which == 0 ? cQ : cDO) + (uint32_t)(h * 32 + c * 16), w);
+        }
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before_sync();
+      softmax_bar();
+      if (threadIdx.x == 64) ptx::mbar_arrive(bar(0));       // Q, dO are resident -> the UMMAs may start
+    }
 
     for (int i = 0; i < n_it; ++i) {
       const int s = i & 1;
-      ptx::mbar_wait(bar(5 + s), (uint32_t)((i >> 1) & 1));
+      if (kQT) ptx::mbar_wait(bar(5), (uint32_t)(i & 1));
+      else ptx::mbar_wait(bar(5 + s), (uint32_t)((i >> 1) & 1));
       ptx::tc_fence_after_sync();
+      const uint32_t cS = kQT ? 0u : (uint32_t)(s * 128);
       float sv[64];
       {
         uint32_t v0[32], v1[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(s * 128 + h * 64), v0);
-        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(s * 128 + h * 64 + 32), v1);
+        ptx::tmem_ld_32x32b_x32(lane_addr + cS + (uint32_t)(h * 64), v0);
+        ptx::tmem_ld_32x32b_x32(lane_addr + cS + (uint32_t)(h * 64 + 32), v1);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 32; ++e) { sv[e] = __uint_as_float(v0[e]); sv[32 + e] = __uint_as_float(v1[e]); }
       }
       ptx::tc_fence_before_sync();
       softmax_bar();
-      if (threadIdx.x == 64) ptx::mbar_arrive(bar(7 + s));   // S[s] drained -> Q K^T of step i + 2
+      if (threadIdx.x == 64) ptx::mbar_arrive(bar(kQT ? 7 : 7 + s));   // S drained -> the next Q K^T into this buffer
       const int key0 = i * 128 + h * 64;
       const bool diag = i * 128 + 127 > t0;
       // start the dP read now: it completes under the exponentials (TMEM read port and MUFU pipe overlap)
       ptx::mbar_wait(bar(9), (uint32_t)(i & 1));             // dP of step i
       ptx::tc_fence_after_sync();
       uint32_t d0[32], d1[32];
-      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(256 + h * 64), d0);
-      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(256 + h * 64 + 32), d1);
+      ptx::tmem_ld_32x32b_x32(lane_addr + cDP + (uint32_t)(h * 64), d0);
+      ptx::tmem_ld_32x32b_x32(lane_addr + cDP + (uint32_t)(h * 64 + 32), d1);
 #pragma unroll
       for (int e = 0; e < 64; ++e) sv[e] = ex2f(fmaf(sv[e], p.scale_log2, -lse_row));
       if (diag) {
@@ -574,7 +617,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           uint32_t pp[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) pp[e] = pk2(sv[c * 32 + 2 * e], sv[c * 32 + 2 * e + 1]);
-          ptx::tmem_st_32x32b_x16(lane_addr + (uint32_t)(256 + h * 32 + c * 16), pp);
+          ptx::tmem_st_32x32b_x16(lane_addr + cDP + (uint32_t)(h * 32 + c * 16), pp);
         }
         ptx::tmem_st_wait();
         ptx::tc_fence_before_sync();
@@ -595,8 +638,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     ptx::mbar_wait(bar(17), 0);
     ptx::tc_fence_after_sync();
     uint32_t v0[32], v1[32];
-    ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(384 + h * 64), v0);
-    ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(384 + h * 64 + 32), v1);
+    ptx::tmem_ld_32x32b_x32(lane_addr + cDQ + (uint32_t)(h * 64), v0);
+    ptx::tmem_ld_32x32b_x32(lane_addr + cDQ + (uint32_t)(h * 64 + 32), v1);
     ptx::tmem_ld_wait();
     if (valid) {
       __nv_bfloat16* dst = p.dqkv + (int64_t)(row0 + qi) * p.dqkv_stride + (kvh * p.R + r) * kD + h * 64;
@@ -634,7 +677,8 @@ using namespace prl;
 namespace prl { namespace { int g_bwd_generation = [] { const char* e = getenv("PRL_ATTN_BWD"); return (e && e[0] == '1') ? 1 : 2; }(); } }
 
 extern "C" int prl_attn_set_bwd_generation(int32_t gen) {
-  PRL_CHECK_ARG(gen == 1 || gen == 2, "prl_attn_set_bwd_generation: 1 (P / dS operands through shared memory) or 2 (through TMEM)");
+  PRL_CHECK_ARG(gen >= 1 && gen <= 3, "prl_attn_set_bwd_generation: 1 (P / dS operands through shared memory), 2 (through TMEM) "
+                "or 3 (2 + the dQ kernel keeps Q and dO in TMEM)");
   prl::g_bwd_generation = gen;
   return PRL_OK;
 }
@@ -669,6 +713,8 @@ extern "C" int prl_attn_varlen_bwd(const void* qkv, int64_t qkv_stride, int32_t 
   p.seg_start = seg_start; p.seg_len = seg_len; p.n_q = n_q; p.n_kv = n_kv; p.R = n_q / n_kv;
   p.col_k = n_q * kD; p.col_v = (n_q + n_kv) * kD;
   p.scale_log2 = sm_scale * 1.4426950408889634f; p.sm_scale = sm_scale;
+  p.q_base = (const __nv_bfloat16*)qkv; p.q_stride = qkv_stride;
+  p.do_base = (const __nv_bfloat16*)d_out_bf16; p.do_stride = (int64_t)n_q * kD;
   CUtensorMap tkv, tq, tdo;
   int rc = make_tmap_2d_bf16(&tkv, qkv, (uint64_t)width, (uint64_t)T, (uint64_t)qkv_stride * 2, 64, 64);
   if (rc) return rc;
@@ -681,7 +727,7 @@ extern "C" int prl_attn_varlen_bwd(const void* qkv, int64_t qkv_stride, int32_t 
     if (rc) return rc;
     static SmemAttr attr = {};
     dim3 grid((unsigned)((max_seg_len + 127) / 128), (unsigned)n_kv, (unsigned)n_seg);
-    if (g_bwd_generation == 1) {
+    if (g_bwd_generation == 1) {   // generations 2 and 3 share the dK / dV kernel
       PRL_CUDA(ensure_smem(attn_bwd_dkdv_kernel<false>, kSmemDkdv, attr));
       attn_bwd_dkdv_kernel<false><<<grid, kThreadsB, (size_t)kSmemDkdv, stream>>>(tq, tdo, tkv, p);
     } else {
@@ -701,12 +747,16 @@ extern "C" int prl_attn_varlen_bwd(const void* qkv, int64_t qkv_stride, int32_t 
     static SmemAttr attr = {};
     dim3 grid((unsigned)(((max_seg_len + p.nq - 1) / p.nq + 1) & ~1), (unsigned)n_kv, (unsigned)n_seg);
     if (g_bwd_generation == 1) {
-      PRL_CUDA(ensure_smem(attn_bwd_dq_kernel<false>, kSmemDq, attr));
-      attn_bwd_dq_kernel<false><<<grid, kThreadsB, (size_t)kSmemDq, stream>>>(tq, tdo, tkv, p);
-    } else {
+      PRL_CUDA(ensure_smem(attn_bwd_dq_kernel<1>, kSmemDq, attr));
+      attn_bwd_dq_kernel<1><<<grid, kThreadsB, (size_t)kSmemDq, stream>>>(tq, tdo, tkv, p);
+    } else if (g_bwd_generation == 2) {
       static SmemAttr attr2 = {};
-      PRL_CUDA(ensure_smem(attn_bwd_dq_kernel<true>, kSmemDq, attr2));
-      attn_bwd_dq_kernel<true><<<grid, kThreadsB, (size_t)kSmemDq, stream>>>(tq, tdo, tkv, p);
+      PRL_CUDA(ensure_smem(attn_bwd_dq_kernel<2>, kSmemDq, attr2));
+      attn_bwd_dq_kernel<2><<<grid, kThreadsB, (size_t)kSmemDq, stream>>>(tq, tdo, tkv, p);
+    } else {
+      static SmemAttr attr3 = {};
+      PRL_CUDA(ensure_smem(attn_bwd_dq_kernel<3>, kSmemDq, attr3));
+      attn_bwd_dq_kernel<3><<<grid, kThreadsB, (size_t)kSmemDq, stream>>>(tq, tdo, tkv, p);
     }
     PRL_LAUNCH_CHECK();
   }

@@ -113,9 +113,9 @@ def _run(dev, n_q, n_kv, lens, seed=0, pad_cols=0, fwd_gen=2, bwd_gen=None):
     (16, 1, [96, 33]),
     (28, 4, [511, 1, 700]),
 ])
-@pytest.mark.parametrize("fwd_gen", [1, 2])
-def test_varlen_attention_small(cuda_device, n_q, n_kv, lens, fwd_gen):
-    _run(cuda_device, n_q, n_kv, lens, seed=len(lens) * 131 + n_q, fwd_gen=fwd_gen)
+@pytest.mark.parametrize("fwd_gen,bwd_gen", [(1, 1), (2, 2), (2, 3)])
+def test_varlen_attention_small(cuda_device, n_q, n_kv, lens, fwd_gen, bwd_gen):
+    _run(cuda_device, n_q, n_kv, lens, seed=len(lens) * 131 + n_q, fwd_gen=fwd_gen, bwd_gen=bwd_gen)
 
 
 def test_varlen_attention_padded_row_stride(cuda_device):
@@ -128,7 +128,8 @@ def test_varlen_attention_qwen7b_heads_medium(cuda_device, lens):
 
 
 @pytest.mark.parametrize("lens,fwd_gen,bwd_gen", [([16384], 2, 2), ([8192, 8192], 2, 2), ([5000, 11000, 384], 2, 2),
-                                                  ([16384], 1, 1), ([16384], 2, 1), ([16384], 1, 2)])
+                                                  ([16384], 1, 1), ([16384], 2, 1), ([16384], 1, 2), ([16384], 2, 3),
+                                                  ([5000, 11000, 384], 2, 3)])
 def test_varlen_attention_qwen7b_heads_16k(cuda_device, lens, fwd_gen, bwd_gen):
     """the trainer's micro-batch size (16 384 packed tokens) at Qwen2.5-7B's 28 / 4 heads"""
     _run(cuda_device, 28, 4, lens, seed=5, fwd_gen=fwd_gen, bwd_gen=bwd_gen)

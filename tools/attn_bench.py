@@ -68,11 +68,15 @@ def main():
     _l.check(o.lib.prl_attn_set_bwd_generation(1))
     dq1 = o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D)
     bwd1_ms = timed(lambda: o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D), a.reps)
+    _l.check(o.lib.prl_attn_set_bwd_generation(3))
+    dq3 = o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D)
+    bwd3_ms = timed(lambda: o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D), a.reps)
     _l.check(o.lib.prl_attn_set_bwd_generation(2))
     dq2 = o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D)
     bwd_ms = timed(lambda: o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D), a.reps)
     flops_fwd = a.segments * n_q * 4 * D * L * L / 2
     res = {"bench": "learner_attention", "tokens": T, "segments": a.segments, "n_q": n_q, "n_kv": n_kv,
+           "bwd_gen3_ms": round(bwd3_ms, 3), "bwd_gen3_vs_gen2_max_abs_diff": (dq3.float() - dq2.float()).abs().max().item(),
            "bwd_gen1_ms": round(bwd1_ms, 3), "bwd_gen1_vs_gen2_max_abs_diff": (dq1.float() - dq2.float()).abs().max().item(),
            "fwd_gen1_ms": round(fwd1_ms, 3), "gen1_vs_gen2_max_abs_diff": (out1.float() - out.float()).abs().max().item(),
            "ours": {"fwd_ms": round(fwd_ms, 3), "bwd_ms": round(bwd_ms, 3),
