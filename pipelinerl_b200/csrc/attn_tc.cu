@@ -605,6 +605,19 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
 using namespace prl;
 
+// which forward kernel the two entry points launch (A/B runs and tests): prefill defaults to generation 1 until generation 2
+// has been validated on the paged path (PRL_PREFILL_ATTN_GEN=2 / prl_attn_set_prefill_generation)
+namespace prl { namespace {
+int g_fwd_generation = [] { const char* e = getenv("PRL_ATTN_FWD"); return (e && e[0] == '1') ? 1 : 2; }();
+int g_prefill_generation = [] { const char* e = getenv("PRL_PREFILL_ATTN_GEN"); return (e && e[0] == '2') ? 2 : 1; }();
+} }
+
+extern "C" int prl_attn_set_prefill_generation(int32_t gen) {
+  PRL_CHECK_ARG(gen == 1 || gen == 2, "prl_attn_set_prefill_generation: 1 or 2");
+  prl::g_prefill_generation = gen;
+  return PRL_OK;
+}
+
 extern "C" int prl_paged_attn_prefill_tc(const void* q, int32_t q_rows, const void* kv_cache, int64_t n_pages,
                                          int32_t n_layers, int32_t layer, const int32_t* block_table,
                                          int32_t max_blocks, const int32_t* seq_q_start, const int32_t* seq_q_len,
@@ -634,15 +647,19 @@ extern "C" int prl_paged_attn_prefill_tc(const void* q, int32_t q_rows, const vo
   if (rc) return rc;
   const int smem = 2 * kTile16K + 2 * kStageBytesT + 4 * kTile16K + 1024 + 8 * 20 + 2 * 128 * 4 + 16;
   static SmemAttr smem_attr = {};
-  PRL_CUDA(ensure_smem(attn_prefill_tc_kernel<false>, smem, smem_attr));
   dim3 grid((unsigned)(((max_q_len + p.nq - 1) / p.nq + 1) & ~1), (unsigned)n_kv, (unsigned)n_seqs);  // pairs of q tiles
-  attn_prefill_tc_kernel<false><<<grid, kThreadsT, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
+  if (g_prefill_generation == 2) {      // ping-pong softmax groups, P and O in TMEM (see attn_fwd_v2_kernel)
+    static SmemAttr smem_attr2 = {};
+    PRL_CUDA(ensure_smem(attn_fwd_v2_kernel<false>, smem, smem_attr2));
+    attn_fwd_v2_kernel<false><<<grid, kThreadsT, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
+  } else {
+    PRL_CUDA(ensure_smem(attn_prefill_tc_kernel<false>, smem, smem_attr));
+    attn_prefill_tc_kernel<false><<<grid, kThreadsT, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
+  }
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }
 
-
-namespace prl { namespace { int g_fwd_generation = [] { const char* e = getenv("PRL_ATTN_FWD"); return (e && e[0] == '1') ? 1 : 2; }(); } }
 
 extern "C" int prl_attn_set_fwd_generation(int32_t gen) {
   PRL_CHECK_ARG(gen == 1 || gen == 2, "prl_attn_set_fwd_generation: 1 (lock-step softmax, O folded in registers) or 2 (ping-pong, O in TMEM)");

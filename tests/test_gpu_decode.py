@@ -194,7 +194,7 @@ def test_prefix_sharing_and_chunked_prefill(cuda_device):
         logits = orc.forward(torch.tensor([tok]))[-1]
 
 
-@pytest.mark.parametrize("kernel", ["tc", "mma"])
+@pytest.mark.parametrize("kernel", ["tc", "tc2", "mma"])
 @pytest.mark.parametrize("n_q,n_kv,seqs", [
     (28, 4, [(7000, 1000), (0, 37)]),              # Qwen2.5-7B grouping (R = 7 -> 18 tokens x 7 heads per UMMA tile)
     (4, 2, [(0, 300), (129, 70), (64, 1)]),        # R = 2; chunk starting mid-page; single-row chunk
@@ -228,7 +228,8 @@ def test_prefill_attention_long_context_vs_fp32(cuda_device, kernel, n_q, n_kv, 
     i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
     qs, ql_t, p0_t, sl = i32(starts), i32([s[1] for s in seqs]), i32([s[0] for s in seqs]), i32(list(range(len(seqs))))
     bt_d = bt.to(dev)
-    if kernel == "tc":
+    if kernel in ("tc", "tc2"):      # tc2: generation 2 (ping-pong softmax groups, P and O in TMEM) on the paged path
+        _lib.check(lib.prl_attn_set_prefill_generation(2 if kernel == "tc2" else 1))
         _lib.check(lib.prl_paged_attn_prefill_tc(q.data_ptr(), rows, kv.data_ptr(), n_pages, L, layer, bt_d.data_ptr(),
                                                  max_blocks, qs.data_ptr(), ql_t.data_ptr(), p0_t.data_ptr(), sl.data_ptr(),
                                                  len(seqs), max(s[1] for s in seqs), n_q, n_kv, D, P, 1.0 / D ** 0.5,
@@ -239,6 +240,7 @@ def test_prefill_attention_long_context_vs_fp32(cuda_device, kernel, n_q, n_kv, 
                                               max(s[1] for s in seqs), n_q, n_kv, D, P, 1.0 / D ** 0.5, out.data_ptr(),
                                               None))
     torch.cuda.synchronize()
+    _lib.check(lib.prl_attn_set_prefill_generation(1))
     for z, (p0, ql) in enumerate(seqs):
         S = p0 + ql
         k = (S + P - 1) // P
