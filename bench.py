@@ -338,7 +338,10 @@ def run_pipeline_splits(args, world, rank, headline):
     base_port = int(os.environ.get("MASTER_PORT", "29500"))
     for k, m in enumerate(splits):
         key = f"{world - m}+{m}"
-        env = dict(os.environ, MASTER_PORT=str(base_port + 101 + k), NCCL_DEBUG="WARN", NCCL_DEBUG_FILE="/dev/stderr")
+        # a fresh rendezvous for the children: rank 0's child hosts the store itself (the torchrun agent's store, which
+        # TORCHELASTIC_USE_AGENT_STORE points the parents at, listens on the parents' port only)
+        env = {k_: v for k_, v in os.environ.items() if not k_.startswith("TORCHELASTIC_")}
+        env.update(MASTER_PORT=str(base_port + 101 + k), NCCL_DEBUG="WARN", NCCL_DEBUG_FILE="/dev/stderr")
         cmd = [sys.executable, str(ROOT / "tools" / "split_bench.py"), "--learners", str(m), "--updates", "3",
                "--context", str(args.context), "--batch", str(args.batch)]
         t0 = time.time()
