@@ -345,12 +345,14 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_smem = base;                          // Q lo | Q hi
-  const uint32_t kv_smem = base + 2 * kTile16K;          // 2 stages x (K lo | K hi | V lo | V hi)
-  const uint32_t p_smem = kv_smem + 2 * kStageBytesT;    // P of group 0 | P of group 1  (keys 0..63 | keys 64..127 each)
-  const uint32_t bar_base = p_smem + 4 * kTile16K;
+  const uint32_t kv_smem = base + 2 * kTile16K;          // 3 stages x (K lo | K hi | V lo | V hi): P lives in TMEM, so the
+  //                                                        64 KB generation 1 spends on P buffers buy a third K/V stage --
+  //                                                        K / V of step i + 2 are requested as soon as step i - 1 is done
+  constexpr int kSt = 3;
+  const uint32_t bar_base = kv_smem + kSt * kStageBytesT;
   auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
-  // 0 q_full | 1,2 k_full | 3,4 k_empty | 5,6 s_full | 7,8 s_empty | 9,10 p_full | 11,12 o_full | 13,14 v_full | 15,16 v_empty
-  const uint32_t tmem_slot = bar(17);
+  // 0 q_full | 1..3 k_full | 4..6 k_empty | 7,8 s_full | 9,10 p_full | 11,12 o_full | 13..15 v_full | 16..18 v_empty
+  const uint32_t tmem_slot = bar(19);
 
   const int qtile = kContig ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int kvh = blockIdx.y, z = blockIdx.z;
@@ -369,7 +371,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 17; ++i) ptx::mbar_init(bar(i), (i == 3 || i == 4 || i == 15 || i == 16) ? 2 : 1);
+    for (int i = 0; i < 19; ++i) ptx::mbar_init(bar(i), ((i >= 4 && i <= 6) || (i >= 16 && i <= 18)) ? 2 : 1);   // *_empty: both CTAs
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
     ptx::prefetch_tensormap(&tm_q);
@@ -394,8 +396,8 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const int32_t* bt = kContig ? nullptr : p.block_table + (int64_t)p.seq_slot[z] * p.max_blocks;
       const int seq_row0 = p.seq_q_start[z];
       auto load_page = [&](int it, int kv, uint32_t full_bar, uint32_t empty_bar) {
-        const int s = it & 1;
-        const uint32_t ph = (uint32_t)((it >> 1) & 1);
+        const int s = it % kSt;
+        const uint32_t ph = (uint32_t)((it / kSt) & 1);
         ptx::mbar_wait(empty_bar + 8u * (uint32_t)s, ph ^ 1u);
         ptx::mbar_arrive_expect_tx(full_bar + 8u * (uint32_t)s, (uint32_t)(2 * kTile16K));
         int pg = 2 * it + (int)rank;
@@ -413,10 +415,10 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         ptx::tma_load_2d_multicast(dst, &tm_kv, c0, row, full_bar + 8u * (uint32_t)s, 3, ptx::kEvictLast);
         ptx::tma_load_2d_multicast(dst + kTile16K, &tm_kv, c0 + 64, row, full_bar + 8u * (uint32_t)s, 3, ptx::kEvictLast);
       };
-      load_page(0, 0, bar(1), bar(3));
+      load_page(0, 0, bar(1), bar(4));
       for (int it = 0; it < n_it; ++it) {
-        if (it + 1 < n_it) load_page(it + 1, 0, bar(1), bar(3));
-        load_page(it, 1, bar(13), bar(15));
+        if (it + 1 < n_it) load_page(it + 1, 0, bar(1), bar(4));
+        load_page(it, 1, bar(13), bar(16));
       }
     }
   } else if (warp == 1) {
@@ -425,21 +427,21 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       constexpr uint32_t idesc_qk = ptx::make_idesc_bf16_f32(128, kKeys);
       constexpr uint32_t idesc_pv = ptx::make_idesc_bf16_f32(128, kDT) | (1u << 16);  // B (= V) is MN-major
       auto issue_qk = [&](int j) {
-        const int s = j & 1;
-        const uint32_t ph = (uint32_t)((j >> 1) & 1);
-        ptx::mbar_wait(bar(1 + s), ph);          // K of step j landed
+        const int s = j & 1;                     // S buffer / softmax group
+        const int ks_ = j % kSt;                 // K/V stage
+        ptx::mbar_wait(bar(1 + ks_), (uint32_t)((j / kSt) & 1));   // K of step j landed
         // S_s's columns held P_s of step j - 2: its P V was issued before this point and UMMAs of one thread execute in
         // issue order, so this Q K^T cannot overtake it (and the softmax group finished reading S_s before it stored P_s)
         ptx::tc_fence_after_sync();
-        const uint32_t k_addr = kv_smem + (uint32_t)(s * kStageBytesT);
+        const uint32_t k_addr = kv_smem + (uint32_t)(ks_ * kStageBytesT);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           const uint64_t a = ptx::make_kmajor_sw128_desc(q_smem + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
           const uint64_t b = ptx::make_kmajor_sw128_desc(k_addr + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
           ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 128), a, b, idesc_qk, ks > 0 ? 1u : 0u);
         }
-        ptx::tc_commit(bar(5 + s));
-        ptx::tc_commit_multicast(bar(3 + s), 3);
+        ptx::tc_commit(bar(7 + s));
+        ptx::tc_commit_multicast(bar(4 + ks_), 3);
       };
       ptx::mbar_wait(bar(0), 0);
       issue_qk(0);
@@ -447,10 +449,11 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (i + 1 < n_it) issue_qk(i + 1);
         const int s = i & 1;
         const uint32_t ph = (uint32_t)((i >> 1) & 1);
+        const int vs_ = i % kSt;
         ptx::mbar_wait(bar(9 + s), ph);              // P_s of step i is in TMEM (and O_s rescaled if it had to be)
-        ptx::mbar_wait(bar(13 + s), ph);             // V of step i landed
+        ptx::mbar_wait(bar(13 + vs_), (uint32_t)((i / kSt) & 1));   // V of step i landed
         ptx::tc_fence_after_sync();
-        const uint32_t v_addr = kv_smem + (uint32_t)(s * kStageBytesT) + 2 * kTile16K;
+        const uint32_t v_addr = kv_smem + (uint32_t)(vs_ * kStageBytesT) + 2 * kTile16K;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {             // A = P_s out of TMEM: 16 keys = 8 packed columns per UMMA
           const uint64_t b = ptx::make_mnmajor_sw128_desc(v_addr, kTile16K) + (uint64_t)(128 * ks);
@@ -458,7 +461,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                            (i >= 2 || ks > 0) ? 1u : 0u);
         }
         ptx::tc_commit(bar(11 + s));                 // O_s updated
-        ptx::tc_commit_multicast(bar(15 + s), 3);    // V slot consumed: tell BOTH producers
+        ptx::tc_commit_multicast(bar(16 + vs_), 3);  // V slot consumed: tell BOTH producers
       }
     }
     __syncwarp();
@@ -472,14 +475,13 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t s_addr = lane_addr + (uint32_t)(g * 128);
     const uint32_t o_addr = lane_addr + (uint32_t)(256 + g * 128);
-    const uint32_t p_row = p_smem + (uint32_t)(g * 2 * kTile16K + m * 128);
     const bool leader = (threadIdx.x == 64 + g * 128);
-    float2* xchg = reinterpret_cast<float2*>(smem_raw + (bar_base - ptx::smem_u32(smem_raw)) + 8 * 18);  // [128] (m_ref, l) of group 1
+    float2* xchg = reinterpret_cast<float2*>(smem_raw + (bar_base - ptx::smem_u32(smem_raw)) + 8 * 20);  // [128] (m_ref, l) of group 1
     float m_ref = 0.f, l_run = 0.f;
 
     for (int i = g; i < n_it; i += 2) {
       const int j = i >> 1;
-      ptx::mbar_wait(bar(5 + g), (uint32_t)(j & 1));
+      ptx::mbar_wait(bar(7 + g), (uint32_t)(j & 1));
       ptx::tc_fence_after_sync();
       float sv[128];
       {

@@ -310,7 +310,7 @@ def test_per_request_sampling_parameters_share_one_batch(cuda_device):
               SamplingParams(max_tokens=8, temperature=2.0), SamplingParams(max_tokens=8, temperature=1.0)]
     reqs = [eng.add_request(prompt, p) for p in params]
     checked = 0
-    for _ in range(len(prompt) + 6):
+    for _ in range(len(prompt) + 8):      # 9 prompt tokens through the decode path, then 8 generated tokens
         eng.step()
         logits, ids, lps = eng.logits.clone(), eng.sampled.clone(), eng.sampled_lp.clone()
         for r, p in zip(reqs, params):
