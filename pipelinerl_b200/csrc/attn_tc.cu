@@ -315,19 +315,17 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 // =====================================================================================================
 // Forward, second generation: two softmax groups in ping-pong, O accumulated in TMEM.
 //
-// The first-generation kernel above reads every P V product back out of TMEM (64 KB per step on top of the 64 KB of S)
-// and runs its eight softmax warps in lock-step through  load S -> max -> exp -> store P -> fold O,  so the MUFU pipe,
-// the tensor pipe and the TMEM read port take turns instead of overlapping.  Here:
+// The first-generation kernel above runs its eight softmax warps in lock-step through  load S -> max -> exp -> store P ->
+// fold O:  the MUFU pipe and the tensor pipe take turns instead of overlapping, and the softmax warps' instruction stream
+// (not the tensor pipe, not TMEM, not shared memory: profiles/r2_attention.md) is what a step waits for.  Here:
 //   * softmax group g (4 warps, ONE THREAD PER ROW, all 128 keys of a step in registers) owns the steps i = g (mod 2)
 //     with its own online-softmax state (reference exponent m_ref, row sum l) and its own accumulator O_g in TMEM:
 //     while group 0 exponentiates step i, group 1 loads / maximises / stores step i + 1 and the tensor core runs the
 //     Q K^T of step i + 2 and the P V of step i - 1.  The two partial results are merged once, at the end
 //     (a log-sum-exp merge, as for split-KV decode).
 //   * P_g is handed to the tensor core THROUGH TMEM (tcgen05.mma with the A operand in tensor memory), written by each
-//     thread into its own row in place of the S values it has just consumed.  With both operands in shared memory a
-//     128 x 128 x 16 UMMA reads 8 KB per 64 cycles = all of an SM's shared-memory bandwidth; generation 1 moves 224 KB
-//     through shared memory per step (Q, K, P, V operand reads + the P store + the K/V TMA writes) = 1750 cycles against
-//     1024 of tensor work, which is exactly what it measures.  TMEM-resident P removes 64 KB of that.
+//     thread into its own row in place of the S values it has just consumed: no shared-memory store, no proxy fence, no
+//     A-operand fetch from shared memory, and the 64 KB generation 1 spends on P buffers become a third K/V stage.
 //   * O_g is NEVER read inside the loop: P V accumulates into it (tcgen05.mma accumulate), and a row is rescaled in TMEM
 //     (tcgen05.ld / scale / tcgen05.st) only when its running maximum grew by more than 2^8 since the reference was
 //     set -- P stays below 256, exact in bf16's range, and for trained or random scores the rescale branch is taken in

@@ -136,9 +136,9 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem]: A is read from tensor memory (lane = row, 32-bit column = two K-adjacent bf16), so the
-// A operand costs no shared-memory bandwidth -- with both operands in shared memory a 128 x 128 x 16 UMMA reads 8 KB per
-// 64 cycles, the whole 128 B/clk of an SM's shared memory.  A cannot be transposed (K-major only).
+// D[tmem] (+)= A[tmem] * B[smem]: A is read from tensor memory (lane = row, 32-bit column = two K-adjacent bf16) -- the
+// producer of A (a softmax thread) writes it with tcgen05.st instead of a swizzled shared-memory store + proxy fence.
+// A cannot be transposed (K-major only).
 __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
