@@ -497,9 +497,13 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         for (int e = 0; e < 128; ++e)
           if (key0 + e > qpos) sv[e] = -INFINITY;
       }
-      float mx = -INFINITY;
-#pragma unroll
-      for (int e = 0; e < 128; ++e) mx = fmaxf(mx, sv[e]);
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains: this warp is alone on its
+#pragma unroll                                                       // scheduler for most of the phase, latency is exposed
+      for (int e = 0; e < 128; e += 4) {
+        mx4[0] = fmaxf(mx4[0], sv[e]); mx4[1] = fmaxf(mx4[1], sv[e + 1]);
+        mx4[2] = fmaxf(mx4[2], sv[e + 2]); mx4[3] = fmaxf(mx4[3], sv[e + 3]);
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = mx * p.scale_log2;                // scale > 0: max commutes with the scaling
       if (j == 0) {
         m_ref = (m_new == -INFINITY) ? 0.f : m_new;
@@ -525,7 +529,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
       // P_g goes back into TMEM as the A operand of P V, in place of this row's own S values (lane = row; one 32-bit column
       // = two adjacent keys): no shared-memory store, no shared-memory read by the tensor core
-      float sum = 0.f;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};                 // independent partial row sums (fixed order: deterministic)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pp[16];
@@ -533,12 +537,12 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         for (int e = 0; e < 16; ++e) {
           const float p0 = ex2(fmaf(sv[c * 32 + 2 * e], p.scale_log2, -m_ref));       // masked entries: exp2(-inf) = 0
           const float p1 = ex2(fmaf(sv[c * 32 + 2 * e + 1], p.scale_log2, -m_ref));
-          sum += p0 + p1;
+          sum4[e & 3] += p0 + p1;
           pp[e] = pack2(p0, p1);
         }
         ptx::tmem_st_32x32b_x16(s_addr + (uint32_t)(c * 16), pp);
       }
-      l_run += sum;
+      l_run += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       ptx::tmem_st_wait();
       ptx::tc_fence_before_sync();
       group_bar(g);
