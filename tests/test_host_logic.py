@@ -413,3 +413,26 @@ def test_model_checkpoint_roundtrip_hf_names(tmp_path):
     from transformers import AutoModelForCausalLM
     m = AutoModelForCausalLM.from_pretrained(str(tmp_path / "ckpt"), torch_dtype=torch.bfloat16)
     assert torch.equal(m.model.layers[1].mlp.down_proj.weight.data, w["layers.1.down_proj.weight"])
+
+
+def test_tokenizer_is_never_silently_substituted():
+    """a missing / misspelt tokenizer must raise; the synthetic tokenizer is used only when asked for by name or
+    injected (the reference resolves `tokenizer_name` through AutoTokenizer, llm.py:366-374)."""
+    from pipelinerl_b200.llm import SyntheticTokenizer, TrainableLLM
+    assert isinstance(TrainableLLM("inproc://x", "m", tokenizer_name="synthetic").load_tokenizer(), SyntheticTokenizer)
+    tok = SyntheticTokenizer()
+    assert TrainableLLM("inproc://x", "m", tokenizer=tok).load_tokenizer() is tok
+    with pytest.raises(Exception):
+        TrainableLLM("inproc://x", "no-such-model-anywhere/at-all").load_tokenizer()
+
+
+def test_unsupported_sampling_parameters_fail_loudly_in_process():
+    """top_p / top_k / stop / n are rejected by the in-process client exactly as http_shim answers 400 for them"""
+    import asyncio
+
+    from pipelinerl_b200.async_llm import llm_async_generate
+    from pipelinerl_b200.llm import Prompt, SyntheticTokenizer, TrainableLLM
+    for bad in ({"top_p": 0.9}, {"top_k": 20}, {"stop": ["\n"]}, {"n": 2}, {"repetition_penalty": 1.2}):
+        llm = TrainableLLM("inproc://none", "m", parameters={"max_tokens": 4, **bad}, tokenizer=SyntheticTokenizer())
+        with pytest.raises(ValueError):
+            asyncio.run(llm_async_generate(llm, Prompt(messages=[{"role": "user", "content": "hi"}])))
