@@ -375,10 +375,10 @@ def run_tool(argv, timeout_s):
         if res.returncode != 0 or not lines:
             return {"error": f"rc={res.returncode}: {(res.stderr or res.stdout)[-400:]}", "wall_s": round(time.time() - t0, 1)}
         out = json.loads(lines[-1])
-        out["wall_s"] = round(time.time() - t0, 1)
+        out["child_process_wall_s"] = round(time.time() - t0, 1)     # incl. interpreter start-up and model initialisation
         return out
     except subprocess.TimeoutExpired:
-        return {"error": f"timeout after {timeout_s} s", "wall_s": round(time.time() - t0, 1)}
+        return {"error": f"timeout after {timeout_s} s", "child_process_wall_s": round(time.time() - t0, 1)}
     except Exception as e:  # noqa: BLE001
         return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
 
