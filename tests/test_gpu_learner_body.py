@@ -14,8 +14,10 @@ from tests.helpers import tiny_cfg, tiny_weights
 pytestmark = pytest.mark.gpu
 
 # end-to-end bounds (bf16 activations against fp32 references) = 1.5 x what a B200 measured; the tests print the measured values
-BODY_BOUNDS = {"hidden": 2e-2, "logprob": 3e-2, "grad": 3e-2}
-HF_STEP_BOUNDS = {"loss": 2e-2, "grad_norm": 3e-2, "grad_samples": 5e-2}
+# measured: hidden rel L2 0.0061 / 0.0068, max |dlogprob| 0.0118 / 0.0192, worst gradient rel L2 0.0086 / 0.0104 (gqa2 / gqa7)
+BODY_BOUNDS = {"hidden": 1.02e-2, "logprob": 2.9e-2, "grad": 1.56e-2}
+# measured vs the reference's rl_step on HF fp32: loss rel 3.6e-6 / 4.0e-3, gradient-norm rel 0.0013 / 0.0015, sampled gradients 0.0131 / 0.0117
+HF_STEP_BOUNDS = {"loss": 6e-3, "grad_norm": 2.3e-3, "grad_samples": 2e-2}
 
 
 def _ops():
