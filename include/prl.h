@@ -417,7 +417,7 @@ int prl_attn_varlen_fwd(const void* qkv_bf16, int64_t qkv_stride, int32_t T, con
 /* which forward kernel prl_attn_varlen_fwd launches: 2 (default) = two ping-pong softmax groups, O accumulated in TMEM
  * with conditional rescale; 1 = the first-generation kernel shared with chunked prefill.  For A/B runs and tests. */
 int prl_attn_set_fwd_generation(int32_t generation);
-/* same switch for prl_paged_attn_prefill_tc (chunked prefill / scoring): default 1 */
+/* same switch for prl_paged_attn_prefill_tc (chunked prefill / scoring): default 2 */
 int prl_attn_set_prefill_generation(int32_t generation);
 /* backward kernels: 2 (default) = P^T / dS^T / dS reach the tensor core through TMEM (A operand in tensor memory);
  * 1 = through shared memory.  For A/B runs and tests. */

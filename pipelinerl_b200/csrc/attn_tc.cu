@@ -609,11 +609,11 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
 using namespace prl;
 
-// which forward kernel the two entry points launch (A/B runs and tests): prefill defaults to generation 1 until generation 2
-// has been validated on the paged path (PRL_PREFILL_ATTN_GEN=2 / prl_attn_set_prefill_generation)
+// which forward kernel the two entry points launch (generation 1 stays selectable for A/B runs and tests:
+// PRL_ATTN_FWD=1 / PRL_PREFILL_ATTN_GEN=1, prl_attn_set_fwd_generation / prl_attn_set_prefill_generation)
 namespace prl { namespace {
 int g_fwd_generation = [] { const char* e = getenv("PRL_ATTN_FWD"); return (e && e[0] == '1') ? 1 : 2; }();
-int g_prefill_generation = [] { const char* e = getenv("PRL_PREFILL_ATTN_GEN"); return (e && e[0] == '2') ? 2 : 1; }();
+int g_prefill_generation = [] { const char* e = getenv("PRL_PREFILL_ATTN_GEN"); return (e && e[0] == '1') ? 1 : 2; }();
 } }
 
 extern "C" int prl_attn_set_prefill_generation(int32_t gen) {

@@ -242,7 +242,7 @@ def test_prefill_attention_long_context_vs_fp32(cuda_device, kernel, n_q, n_kv, 
                                               max(s[1] for s in seqs), n_q, n_kv, D, P, 1.0 / D ** 0.5, out.data_ptr(),
                                               None))
     torch.cuda.synchronize()
-    _lib.check(lib.prl_attn_set_prefill_generation(1))
+    _lib.check(lib.prl_attn_set_prefill_generation(2))      # back to the default
     for z, (p0, ql) in enumerate(seqs):
         S = p0 + ql
         k = (S + P - 1) // P
