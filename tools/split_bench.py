@@ -84,6 +84,14 @@ def run_split(n_learners: int, updates: int = 2, context: int = 8192, batch: int
             opt = FusedAdamW(model.named_parameters(), lr=1e-6, weight_decay=0.01, max_grad_norm=0.3, grad_dtype=torch.float32,
                          **model.optimizer_kwargs())
         model.bind(opt)
+        # spend the HBM left after parameters / optimizer state (sharded over the learners) on kept gate_up outputs: every kept
+        # layer skips the largest recompute GEMM of the backward (same rule as tools/train_bench.py, 20 GB of headroom)
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        free = torch.cuda.mem_get_info(dev)[0]
+        kept_bytes = tokens * 2 * (cfg.num_layers * (cfg.qkv_size + cfg.q_size + cfg.hidden_size) + cfg.num_layers * cfg.hidden_size)
+        per_layer = tokens * 2 * cfg.intermediate_size * 2
+        model.body.keep_gate_up_layers = int(max(0, min(cfg.num_layers, (free - 20e9 - kept_bytes) // per_layer)))
         rcfg = RLConfig(batch_size=micro * n_learners)
         batches = [train_bench.synthetic_batch(cfg, tokens, 1, dev, 100 + rank * micro + i) for i in range(micro)]
         for b in batches:
@@ -135,7 +143,8 @@ def run_split(n_learners: int, updates: int = 2, context: int = 8192, batch: int
         mine = {"role": "learner", "step_ms": steps, "push_ms": pushes, "exchange_ms": exch,
                 "checksum": checksum(opt.shadow_bf16), "arena_bytes": int(opt.shadow_bf16.numel() * 2),
                 "push_bytes": int(mgr.bytes) * n_samplers, "loss": float(loss), "dp_check": dp_check,
-                "peak_memory_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1)}
+                "peak_memory_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1),
+                "keep_gate_up_layers": model.body.keep_gate_up_layers}
     else:
         dist.barrier()
         times, flips_at = [], []
@@ -196,7 +205,8 @@ def run_split(n_learners: int, updates: int = 2, context: int = 8192, batch: int
                                        and all(l["checksum"] == L[0]["checksum"] for l in L)),
                "dp_equals_single": (bool(dpc["ok"]) if dpc is not None else None), "dp_check": dpc,
                "lm_head": "fp32-equivalent on both sides (hi + lo bf16 streams; the push carries both)",
-               "learner_peak_memory_GB": max(l["peak_memory_GB"] for l in L), "context": context, "batch_per_sampler": batch,
+               "learner_peak_memory_GB": max(l["peak_memory_GB"] for l in L),
+               "learner_keep_gate_up_layers": [l["keep_gate_up_layers"] for l in L], "context": context, "batch_per_sampler": batch,
                "final_loss": L[0]["loss"]}
     # release IPC mappings / big buffers before the caller goes on
     dist.barrier()
