@@ -669,16 +669,505 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   }
 }
 
+
+// =====================================================================================================
+// Generation 4 of both kernels: the softmax warps stop moving in lock-step.
+//
+// What generations 1-3 lose (profiles/r2_attention.md): eight softmax warps walk through  wait -> tcgen05.ld -> exp2 ->
+// pack -> tcgen05.st -> signal  TOGETHER, with three 256-thread barriers per step, so the TMEM read port, the MUFU pipe
+// and the tensor core take turns; and the dQ kernel does not start its exponentials before dP of the step has arrived.
+// Here: 16 softmax warps (4 per TMEM lane quarter, 32 score columns per thread, 112 registers), no CTA-wide barrier inside
+// the loop (a warp signals an mbarrier by itself; every thread writes its bf16 results over columns IT read, so nothing
+// is shared between threads), and
+//   * dK/dV: two groups of 8 warps own the two S^T / dP^T buffers and alternate steps (ping-pong), so one group's exp2 runs
+//     under the other group's TMEM traffic and under both groups' UMMAs;
+//   * dQ: P = exp2(S - lse) of step i is computed while the tensor core still runs  dQ(i-1)  and  dP(i) = dO V^T.
+// The UMMA A operands (P^T, dS^T, dS in TMEM) are addressed per 16-row k-step, so a thread's packed output may stay inside
+// its own 32 columns: k-step ks reads packed columns 32 (ks / 2) + 8 (ks % 2).
+// =====================================================================================================
+constexpr int kThreadsB4 = 576;
+constexpr int kQStages4 = 4;
+constexpr int kMeta4 = 2 * 2 * 192 * 4;      // [group][buffer][lse | delta | qpos][64 columns]
+constexpr int kSmemDkdv4 = 1024 + kKvBytes + kQStages4 * kQSlot + kMeta4 + 8 * 16 + 16;
+static_assert(kSmemDkdv4 <= 232448, "dkdv4 kernel exceeds the 227 KB shared-memory limit");
+
+__device__ __forceinline__ void group_bar256(int g) {
+  if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else asm volatile("bar.sync 2, 256;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kThreadsB4, 1)
+attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                      const __grid_constant__ CUtensorMap tm_kv, BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t kv_smem = base;                                   // K lo | K hi | V lo | V hi
+  const uint32_t q_ring = base + kKvBytes;
+  const uint32_t meta_smem = q_ring + kQStages4 * kQSlot;
+  const uint32_t bar_base = meta_smem + kMeta4;
+  auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
+  // 0 kv_full | 1..4 q_full | 5..8 q_empty | 9,10 sdp_full | 11,12 pds_full (one arrival per warp of the group) | 13 acc_done
+  const uint32_t tmem_slot = bar(14);
+  float* meta = reinterpret_cast<float*>(smem_raw + (meta_smem - ptx::smem_u32(smem_raw)));
+
+  const int jt = blockIdx.x, kvh = blockIdx.y, z = blockIdx.z;
+  const int q_len = p.seg_len[z];
+  const int key0 = jt * 128;
+  if (key0 >= q_len) return;                       // before any barrier / TMEM use
+  const int seg0 = p.seg_start[z];
+  const int nqa = p.nq;
+  const int u_first = key0 / nqa;
+  const int u_end = (q_len + nqa - 1) / nqa;
+  const int n_it = u_end - u_first;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  {
+    const uint32_t n16 = (uint32_t)(kQStages4 * kQSlot) / 16;     // rows R * nqa .. 63 of a sub-tile must read as zeros
+    for (uint32_t i = threadIdx.x; i < n16; i += kThreadsB4) sts_v4(q_ring + i * 16, 0u, 0u, 0u, 0u);
+    ptx::fence_proxy_async();
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 14; ++i) ptx::mbar_init(bar(i), (i == 11 || i == 12) ? 8 : 1);
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+    ptx::prefetch_tensormap(&tm_q);
+    ptx::prefetch_tensormap(&tm_do);
+    ptx::prefetch_tensormap(&tm_kv);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(bar(0), (uint32_t)kKvBytes);
+      const int krow = seg0 + key0;
+#pragma unroll
+      for (int kv = 0; kv < 2; ++kv) {
+        const int c0 = (kv ? p.col_v : p.col_k) + kvh * kD;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t dst = kv_smem + (uint32_t)((kv * 2 + half) * kT16);
+          ptx::tma_load_2d(dst, &tm_kv, c0 + 64 * half, krow, bar(0), ptx::kEvictFirst);
+          ptx::tma_load_2d(dst + kT8, &tm_kv, c0 + 64 * half, krow + 64, bar(0), ptx::kEvictFirst);
+        }
+      }
+      const uint32_t q_bytes = (uint32_t)(4 * 128 * p.R * nqa);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it % kQStages4;
+        const uint32_t ph = (uint32_t)((it / kQStages4) & 1);
+        ptx::mbar_wait(bar(5 + st), ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(bar(1 + st), q_bytes);
+        const int row = seg0 + (u_first + it) * nqa;
+        const uint32_t dst = q_ring + (uint32_t)(st * kQSlot);
+        ptx::tma_load_3d(dst, &tm_q, 0, kvh * p.R, row, bar(1 + st), ptx::kEvictLast);
+        ptx::tma_load_3d(dst + kT8, &tm_q, 64, kvh * p.R, row, bar(1 + st), ptx::kEvictLast);
+        ptx::tma_load_3d(dst + 2 * kT8, &tm_do, 0, kvh * p.R, row, bar(1 + st), ptx::kEvictLast);
+        ptx::tma_load_3d(dst + 3 * kT8, &tm_do, 64, kvh * p.R, row, bar(1 + st), ptx::kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc_t = ptx::make_idesc_bf16_f32(128, 64);
+      constexpr uint32_t idesc_acc = ptx::make_idesc_bf16_f32(128, kD) | (1u << 16);
+      auto issue_sdp = [&](int it) {
+        const int st = it % kQStages4, s = it & 1;
+        ptx::mbar_wait(bar(1 + st), (uint32_t)((it / kQStages4) & 1));
+        // S^T[s] / dP^T[s] hold P^T / dS^T of step it - 2 until its dV / dK UMMAs, issued earlier by this thread, have read
+        // them: UMMAs of one thread execute in issue order
+        ptx::tc_fence_after_sync();
+        const uint32_t q_addr = q_ring + (uint32_t)(st * kQSlot);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t a = ptx::make_kmajor_sw128_desc(kv_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+          const uint64_t b = ptx::make_kmajor_sw128_desc(q_addr + (uint32_t)((ks >> 2) * kT8)) + (uint64_t)(2 * (ks & 3));
+          ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 64), a, b, idesc_t, ks > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t a = ptx::make_kmajor_sw128_desc(kv_smem + (uint32_t)(2 * kT16 + (ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+          const uint64_t b = ptx::make_kmajor_sw128_desc(q_addr + (uint32_t)(2 * kT8 + (ks >> 2) * kT8)) + (uint64_t)(2 * (ks & 3));
+          ptx::mma_bf16_ss(tmem_base + (uint32_t)(128 + s * 64), a, b, idesc_t, ks > 0 ? 1u : 0u);
+        }
+        ptx::tc_commit(bar(9 + s));
+      };
+      ptx::mbar_wait(bar(0), 0);
+      issue_sdp(0);
+      for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) issue_sdp(it + 1);
+        const int st = it % kQStages4, s = it & 1;
+        ptx::mbar_wait(bar(11 + s), (uint32_t)((it >> 1) & 1));         // P^T[s], dS^T[s] are in TMEM
+        ptx::tc_fence_after_sync();
+        const uint32_t q_addr = q_ring + (uint32_t)(st * kQSlot);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {     // dV += P^T dO      (contraction over the 64 query rows, 16 per k-step)
+          const uint64_t b = ptx::make_mnmajor_sw128_desc(q_addr + 2 * kT8, kT8) + (uint64_t)(128 * ks);
+          ptx::mma_bf16_ts(tmem_base + 256u, tmem_base + (uint32_t)(s * 64 + (ks >> 1) * 32 + (ks & 1) * 8), b, idesc_acc,
+                           (it > 0 || ks > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {     // dK += dS^T Q
+          const uint64_t b = ptx::make_mnmajor_sw128_desc(q_addr, kT8) + (uint64_t)(128 * ks);
+          ptx::mma_bf16_ts(tmem_base + 384u, tmem_base + (uint32_t)(128 + s * 64 + (ks >> 1) * 32 + (ks & 1) * 8), b, idesc_acc,
+                           (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        ptx::tc_commit(bar(5 + st));     // Q / dO slot may be refilled
+      }
+      ptx::tc_commit(bar(13));
+    }
+    __syncwarp();
+  } else {
+    // ===== softmax warps: group g owns buffer g and the steps it = g (mod 2); a thread owns one KEY (TMEM lane) and 32 of
+    // the 64 query-row columns =====
+    const int q = warp & 3;
+    const int idx = (warp - 2) >> 2;             // 0..3
+    const int g = idx & 1, h = idx >> 1;
+    const int m = q * 32 + lane;                 // key row inside the tile
+    const int kpos = key0 + m;
+    const int tsg = h * 128 + m;                 // thread index inside the group, 0..255
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int c0 = h * 32;
+    const int mc = tsg & 63, mwhich = tsg >> 6;  // 0 lse | 1 delta | 2 query position | 3 idle
+    const int mqi = mc / p.R, mr = mc - mqi * p.R;
+    float* mg = meta + g * 384;
+    auto fetch = [&](int u) -> float {
+      const int tok = u * nqa + mqi;
+      const bool valid = (mqi < nqa) && (tok < q_len);
+      if (mwhich == 2) return __int_as_float(valid ? tok : -1);
+      if (mwhich == 3) return 0.f;
+      if (!valid) return mwhich == 0 ? INFINITY : 0.f;
+      const float* src = mwhich == 0 ? p.lse : p.delta;
+      return __ldg(src + (int64_t)(seg0 + tok) * p.n_q + (kvh * p.R + mr));
+    };
+    const int n_own = n_it > g ? (n_it - g + 1) >> 1 : 0;
+    if (n_own > 0 && mwhich < 3) mg[mwhich * 64 + mc] = fetch(u_first + g);
+    float nxt = (g + 2 < n_it) ? fetch(u_first + g + 2) : 0.f;
+
+    for (int j = 0; j < n_own; ++j) {
+      const int it = 2 * j + g;
+      const int u = u_first + it;
+      group_bar256(g);                           // the group is done with own step j - 1; metadata of step j is visible
+      const float* mb = mg + (j & 1) * 192;
+      if (it + 2 < n_it) {
+        if (mwhich < 3) mg[((j + 1) & 1) * 192 + mwhich * 64 + mc] = nxt;
+        nxt = (it + 4 < n_it) ? fetch(u + 4) : 0.f;            // global load in flight across a whole step
+      }
+      ptx::mbar_wait(bar(9 + g), (uint32_t)(j & 1));
+      ptx::tc_fence_after_sync();
+      uint32_t sv[32], dv[32];
+      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(g * 64 + c0), sv);
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(128 + g * 64 + c0), dv);   // completes under the exponentials
+      const bool diag = u * nqa < key0 + 127;
+      float pe[32];
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        const float4 l0 = *reinterpret_cast<const float4*>(mb + c0 + e);
+        pe[e + 0] = ex2f(fmaf(__uint_as_float(sv[e + 0]), p.scale_log2, -l0.x));
+        pe[e + 1] = ex2f(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, -l0.y));
+        pe[e + 2] = ex2f(fmaf(__uint_as_float(sv[e + 2]), p.scale_log2, -l0.z));
+        pe[e + 3] = ex2f(fmaf(__uint_as_float(sv[e + 3]), p.scale_log2, -l0.w));
+      }
+      if (diag) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const int4 q0 = *reinterpret_cast<const int4*>(mb + 128 + c0 + e);
+          if (kpos > q0.x) pe[e + 0] = 0.f;
+          if (kpos > q0.y) pe[e + 1] = 0.f;
+          if (kpos > q0.z) pe[e + 2] = 0.f;
+          if (kpos > q0.w) pe[e + 3] = 0.f;
+        }
+      }
+      ptx::tmem_ld_wait();
+      uint32_t pp[16], dd[16];
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        const float4 d0 = *reinterpret_cast<const float4*>(mb + 64 + c0 + e);
+        pp[(e >> 1)] = pk2(pe[e], pe[e + 1]);
+        pp[(e >> 1) + 1] = pk2(pe[e + 2], pe[e + 3]);
+        dd[(e >> 1)] = pk2(pe[e] * (__uint_as_float(dv[e]) - d0.x), pe[e + 1] * (__uint_as_float(dv[e + 1]) - d0.y));
+        dd[(e >> 1) + 1] = pk2(pe[e + 2] * (__uint_as_float(dv[e + 2]) - d0.z), pe[e + 3] * (__uint_as_float(dv[e + 3]) - d0.w));
+      }
+      // packed P^T / dS^T over the first 16 of this thread's own 32 columns of S^T[g] / dP^T[g]
+      ptx::tmem_st_32x32b_x16(lane_addr + (uint32_t)(g * 64 + c0), pp);
+      ptx::tmem_st_32x32b_x16(lane_addr + (uint32_t)(128 + g * 64 + c0), dd);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(11 + g));
+    }
+
+    // ---- epilogue: 32 head-dim columns of this key's dV and dK rows ----
+    ptx::mbar_wait(bar(13), 0);
+    ptx::tc_fence_after_sync();
+    const bool valid = kpos < q_len;
+    __nv_bfloat16* drow = p.dqkv + (int64_t)(seg0 + kpos) * p.dqkv_stride + kvh * kD + idx * 32;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {     // 0: dV (TMEM 256..383), 1: dK (384..511)
+      uint32_t v0[32];
+      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(256 + which * 128 + idx * 32), v0);
+      ptx::tmem_ld_wait();
+      const float sc = which ? p.sm_scale : 1.f;
+      if (valid) {
+        __nv_bfloat16* dst = drow + (which ? p.col_k : p.col_v);
+#pragma unroll
+        for (int d = 0; d < 32; d += 8) {
+          uint4 a;
+          a.x = pk2(__uint_as_float(v0[d]) * sc, __uint_as_float(v0[d + 1]) * sc);
+          a.y = pk2(__uint_as_float(v0[d + 2]) * sc, __uint_as_float(v0[d + 3]) * sc);
+          a.z = pk2(__uint_as_float(v0[d + 4]) * sc, __uint_as_float(v0[d + 5]) * sc);
+          a.w = pk2(__uint_as_float(v0[d + 6]) * sc, __uint_as_float(v0[d + 7]) * sc);
+          *reinterpret_cast<uint4*>(dst + d) = a;
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+constexpr int kSmemDq4 = 1024 + 4 * kT16 + 2 * kStageKV + 8 * 20 + 16;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsB4, 1)
+attn_bwd_dq4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
+                    const __grid_constant__ CUtensorMap tm_kv, BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = base;                         // Q lo | Q hi
+  const uint32_t do_smem = base + 2 * kT16;             // dO lo | dO hi
+  const uint32_t kv_smem = base + 4 * kT16;             // 2 stages x (K lo | K hi | V lo | V hi)
+  const uint32_t bar_base = kv_smem + 2 * kStageKV;
+  auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
+  // 0 q_full | 1,2 k_full | 3,4 k_empty | 5,6 s_full | 7,8 s_empty (16 warps) | 9 dp_full | 11 ds_full (16 warps) |
+  // 13,14 v_full | 15,16 v_empty | 17 dq_done
+  const uint32_t tmem_slot = bar(18);
+  constexpr uint32_t cDP = 256u, cDQ = 384u;            // TMEM columns: S[2] 0,128 | dP 256 | dQ 384
+
+  const int qtile = (int)(gridDim.x - 1 - blockIdx.x);
+  const int kvh = blockIdx.y, z = blockIdx.z;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int q_len = p.seg_len[z];
+  if ((qtile & ~1) * p.nq >= q_len) return;             // uniform across the cluster
+  const int seg0 = p.seg_start[z];
+  const int t0 = qtile * p.nq;
+  const int row0 = seg0 + t0;
+  const int n_valid = t0 >= q_len ? 0 : ((q_len - t0) < p.nq ? (q_len - t0) : p.nq);
+  const int pair_rows = ((qtile | 1) + 1) * p.nq;
+  const int kv_end = pair_rows < q_len ? pair_rows : q_len;
+  const int n_it = (kv_end + 127) / 128;
+  const int last_page = (kv_end - 1) / 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 18; ++i) {
+      int cnt = 1;
+      if (i == 3 || i == 4 || i == 15 || i == 16) cnt = 2;
+      if (i == 7 || i == 8 || i == 11) cnt = 16;
+      ptx::mbar_init(bar(i), cnt);
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+    ptx::prefetch_tensormap(&tm_q);
+    ptx::prefetch_tensormap(&tm_do);
+    ptx::prefetch_tensormap(&tm_kv);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync();
+  ptx::tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(bar(0), (uint32_t)(4 * 128 * p.R * p.nq));
+      ptx::tma_load_3d(q_smem, &tm_q, 0, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
+      ptx::tma_load_3d(q_smem + kT16, &tm_q, 64, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
+      ptx::tma_load_3d(do_smem, &tm_do, 0, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
+      ptx::tma_load_3d(do_smem + kT16, &tm_do, 64, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
+      auto load_page = [&](int it, int kv) {
+        const int s = it & 1;
+        const uint32_t ph = (uint32_t)((it >> 1) & 1);
+        const uint32_t full = bar((kv ? 13 : 1) + s), empty = bar((kv ? 15 : 3) + s);
+        ptx::mbar_wait(empty, ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(full, (uint32_t)(2 * kT16));
+        int pg = 2 * it + (int)rank;
+        if (pg > last_page) pg = last_page;            // tail: re-read the last page, its keys are causally masked
+        const int row = seg0 + pg * 64;
+        const int c0 = (kv ? p.col_v : p.col_k) + kvh * kD;
+        const uint32_t dst = kv_smem + (uint32_t)(s * kStageKV + kv * 2 * kT16) + (uint32_t)(rank * kT8);
+        ptx::tma_load_2d_multicast(dst, &tm_kv, c0, row, full, 3, ptx::kEvictLast);
+        ptx::tma_load_2d_multicast(dst + kT16, &tm_kv, c0 + 64, row, full, 3, ptx::kEvictLast);
+      };
+      for (int it = 0; it < n_it; ++it) {
+        load_page(it, 0);
+        load_page(it, 1);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: S(i+1) | dQ(i) | dP(i+1), in that order =====
+    if (lane == 0) {
+      constexpr uint32_t idesc_kk = ptx::make_idesc_bf16_f32(128, 128);
+      constexpr uint32_t idesc_dq = ptx::make_idesc_bf16_f32(128, kD) | (1u << 16);
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        const uint32_t ph = (uint32_t)((j >> 1) & 1);
+        ptx::mbar_wait(bar(1 + s), ph);            // K of step j landed
+        ptx::mbar_wait(bar(7 + s), ph ^ 1u);       // S[s] drained (step j - 2)
+        ptx::tc_fence_after_sync();
+        const uint32_t k_addr = kv_smem + (uint32_t)(s * kStageKV);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t b = ptx::make_kmajor_sw128_desc(k_addr + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+          ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 128),
+                           ptx::make_kmajor_sw128_desc(q_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)), b,
+                           idesc_kk, ks > 0 ? 1u : 0u);
+        }
+        ptx::tc_commit(bar(5 + s));
+      };
+      auto issue_dp = [&](int j) {
+        const int s = j & 1;
+        ptx::mbar_wait(bar(13 + s), (uint32_t)((j >> 1) & 1));   // V of step j landed
+        // dP's columns hold dS of step j - 1 until its dQ UMMAs -- issued BEFORE this call -- have read it (in order)
+        ptx::tc_fence_after_sync();
+        const uint32_t v_addr = kv_smem + (uint32_t)(s * kStageKV + 2 * kT16);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t b = ptx::make_kmajor_sw128_desc(v_addr + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+          ptx::mma_bf16_ss(tmem_base + cDP,
+                           ptx::make_kmajor_sw128_desc(do_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)), b,
+                           idesc_kk, ks > 0 ? 1u : 0u);
+        }
+        ptx::tc_commit(bar(9));
+        ptx::tc_commit_multicast(bar(15 + s), 3);  // V slot consumed: tell BOTH producers
+      };
+      ptx::mbar_wait(bar(0), 0);
+      issue_s(0);
+      issue_dp(0);
+      for (int i = 0; i < n_it; ++i) {
+        if (i + 1 < n_it) issue_s(i + 1);
+        const int s = i & 1;
+        ptx::mbar_wait(bar(11), (uint32_t)(i & 1));              // dS of step i is in TMEM
+        ptx::tc_fence_after_sync();
+        const uint32_t k_addr = kv_smem + (uint32_t)(s * kStageKV);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {           // dQ += dS K     (K read as stored: keys are the contraction rows)
+          const uint64_t b = ptx::make_mnmajor_sw128_desc(k_addr, kT16) + (uint64_t)(128 * ks);
+          ptx::mma_bf16_ts(tmem_base + cDQ, tmem_base + cDP + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8), b, idesc_dq,
+                           (i > 0 || ks > 0) ? 1u : 0u);
+        }
+        ptx::tc_commit_multicast(bar(3 + s), 3);   // K slot consumed: tell BOTH producers
+        if (i + 1 < n_it) issue_dp(i + 1);
+      }
+      ptx::tc_commit(bar(17));
+    }
+    __syncwarp();
+  } else {
+    // ===== softmax warps: four threads share one (token, head) row; thread k works on keys [32 k, 32 k + 32) of a step =====
+    const int q = warp & 3;
+    const int k = (warp - 2) >> 2;               // 0..3
+    const int m = q * 32 + lane;
+    const int qi = m / p.R, r = m - qi * p.R;
+    const int qpos = t0 + qi;
+    const bool valid = qi < n_valid && qi < p.nq;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int64_t stat = (int64_t)(row0 + qi) * p.n_q + (kvh * p.R + r);
+    const float lse_row = valid ? __ldg(p.lse + stat) : INFINITY;   // padding rows: P = 0
+    const float delta_row = valid ? __ldg(p.delta + stat) : 0.f;
+
+    for (int i = 0; i < n_it; ++i) {
+      const int s = i & 1;
+      ptx::mbar_wait(bar(5 + s), (uint32_t)((i >> 1) & 1));
+      ptx::tc_fence_after_sync();
+      uint32_t v0[32];
+      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(s * 128 + k * 32), v0);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(7 + s));           // this warp's part of S[s] is in registers
+      // P of this step: runs while the tensor core is still busy with dQ(i-1) and dP(i)
+      float sv[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) sv[e] = ex2f(fmaf(__uint_as_float(v0[e]), p.scale_log2, -lse_row));
+      if (i * 128 + 127 > t0) {
+        const int key0 = i * 128 + k * 32;
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (key0 + e > qpos) sv[e] = 0.f;
+      }
+      ptx::mbar_wait(bar(9), (uint32_t)(i & 1));             // dP of step i
+      ptx::tc_fence_after_sync();
+      uint32_t d0[32];
+      ptx::tmem_ld_32x32b_x32(lane_addr + cDP + (uint32_t)(k * 32), d0);
+      ptx::tmem_ld_wait();
+      uint32_t pp[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        pp[e] = pk2(sv[2 * e] * (__uint_as_float(d0[2 * e]) - delta_row), sv[2 * e + 1] * (__uint_as_float(d0[2 * e + 1]) - delta_row));
+      // packed dS over the first 16 of this thread's own 32 dP columns
+      ptx::tmem_st_32x32b_x16(lane_addr + cDP + (uint32_t)(k * 32), pp);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(11));              // -> dQ += dS K
+    }
+
+    // ---- epilogue: 32 head-dim columns of this row's dQ ----
+    ptx::mbar_wait(bar(17), 0);
+    ptx::tc_fence_after_sync();
+    uint32_t v0[32];
+    ptx::tmem_ld_32x32b_x32(lane_addr + cDQ + (uint32_t)(k * 32), v0);
+    ptx::tmem_ld_wait();
+    if (valid) {
+      __nv_bfloat16* dst = p.dqkv + (int64_t)(row0 + qi) * p.dqkv_stride + (kvh * p.R + r) * kD + k * 32;
+      const float sc = p.sm_scale;
+#pragma unroll
+      for (int d = 0; d < 32; d += 8) {
+        uint4 a;
+        a.x = pk2(__uint_as_float(v0[d]) * sc, __uint_as_float(v0[d + 1]) * sc);
+        a.y = pk2(__uint_as_float(v0[d + 2]) * sc, __uint_as_float(v0[d + 3]) * sc);
+        a.z = pk2(__uint_as_float(v0[d + 4]) * sc, __uint_as_float(v0[d + 5]) * sc);
+        a.w = pk2(__uint_as_float(v0[d + 6]) * sc, __uint_as_float(v0[d + 7]) * sc);
+        *reinterpret_cast<uint4*>(dst + d) = a;
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync();   // the partner may still multicast into this CTA's shared memory / arrive on its barriers
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 }  // namespace prl
 
 using namespace prl;
 
-namespace prl { namespace { int g_bwd_generation = [] { const char* e = getenv("PRL_ATTN_BWD"); return (e && e[0] == '1') ? 1 : 2; }(); } }
+namespace prl { namespace { int g_bwd_generation = [] { const char* e = getenv("PRL_ATTN_BWD"); return (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 2; }(); } }
 
 extern "C" int prl_attn_set_bwd_generation(int32_t gen) {
-  PRL_CHECK_ARG(gen >= 1 && gen <= 3, "prl_attn_set_bwd_generation: 1 (P / dS operands through shared memory), 2 (through TMEM) "
-                "or 3 (2 + the dQ kernel keeps Q and dO in TMEM)");
+  PRL_CHECK_ARG(gen >= 1 && gen <= 4, "prl_attn_set_bwd_generation: 1 (P / dS operands through shared memory), 2 (through TMEM), "
+                "3 (2 + the dQ kernel keeps Q and dO in TMEM) or 4 (16 decoupled softmax warps)");
   prl::g_bwd_generation = gen;
   return PRL_OK;
 }
@@ -727,7 +1216,11 @@ extern "C" int prl_attn_varlen_bwd(const void* qkv, int64_t qkv_stride, int32_t 
     if (rc) return rc;
     static SmemAttr attr = {};
     dim3 grid((unsigned)((max_seg_len + 127) / 128), (unsigned)n_kv, (unsigned)n_seg);
-    if (g_bwd_generation == 1) {   // generations 2 and 3 share the dK / dV kernel
+    if (g_bwd_generation == 4) {
+      static SmemAttr attr4 = {};
+      PRL_CUDA(ensure_smem(attn_bwd_dkdv4_kernel, kSmemDkdv4, attr4));
+      attn_bwd_dkdv4_kernel<<<grid, kThreadsB4, (size_t)kSmemDkdv4, stream>>>(tq, tdo, tkv, p);
+    } else if (g_bwd_generation == 1) {   // generations 2 and 3 share the dK / dV kernel
       PRL_CUDA(ensure_smem(attn_bwd_dkdv_kernel<false>, kSmemDkdv, attr));
       attn_bwd_dkdv_kernel<false><<<grid, kThreadsB, (size_t)kSmemDkdv, stream>>>(tq, tdo, tkv, p);
     } else {
@@ -746,7 +1239,11 @@ extern "C" int prl_attn_varlen_bwd(const void* qkv, int64_t qkv_stride, int32_t 
     if (rc) return rc;
     static SmemAttr attr = {};
     dim3 grid((unsigned)(((max_seg_len + p.nq - 1) / p.nq + 1) & ~1), (unsigned)n_kv, (unsigned)n_seg);
-    if (g_bwd_generation == 1) {
+    if (g_bwd_generation == 4) {
+      static SmemAttr attr4 = {};
+      PRL_CUDA(ensure_smem(attn_bwd_dq4_kernel, kSmemDq4, attr4));
+      attn_bwd_dq4_kernel<<<grid, kThreadsB4, (size_t)kSmemDq4, stream>>>(tq, tdo, tkv, p);
+    } else if (g_bwd_generation == 1) {
       PRL_CUDA(ensure_smem(attn_bwd_dq_kernel<1>, kSmemDq, attr));
       attn_bwd_dq_kernel<1><<<grid, kThreadsB, (size_t)kSmemDq, stream>>>(tq, tdo, tkv, p);
     } else if (g_bwd_generation == 2) {

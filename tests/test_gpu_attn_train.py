@@ -52,7 +52,8 @@ def _reference(qkv, d_out, bounds, n_q, n_kv):
 
 
 def _run(dev, n_q, n_kv, lens, seed=0, pad_cols=0, fwd_gen=2, bwd_gen=None):
-    """fwd_gen / bwd_gen: 1 = operands through shared memory, 2 = P / dS handed to the tensor core through TMEM (default)"""
+    """fwd_gen / bwd_gen: 1 = operands through shared memory, 2 = P / dS handed to the tensor core through TMEM (default);
+    fwd_gen 3 = 2 with two threads per row (16 softmax warps); bwd_gen 3 = 2 + Q / dO resident in TMEM, 4 = 16 decoupled softmax warps"""
     from pipelinerl_b200 import _lib
     o = _ops()
     bwd_gen = fwd_gen if bwd_gen is None else bwd_gen
@@ -113,7 +114,7 @@ def _run(dev, n_q, n_kv, lens, seed=0, pad_cols=0, fwd_gen=2, bwd_gen=None):
     (16, 1, [96, 33]),
     (28, 4, [511, 1, 700]),
 ])
-@pytest.mark.parametrize("fwd_gen,bwd_gen", [(1, 1), (2, 2), (2, 3)])
+@pytest.mark.parametrize("fwd_gen,bwd_gen", [(1, 1), (2, 2), (2, 3), (2, 4), (3, 4)])
 def test_varlen_attention_small(cuda_device, n_q, n_kv, lens, fwd_gen, bwd_gen):
     _run(cuda_device, n_q, n_kv, lens, seed=len(lens) * 131 + n_q, fwd_gen=fwd_gen, bwd_gen=bwd_gen)
 
@@ -129,7 +130,9 @@ def test_varlen_attention_qwen7b_heads_medium(cuda_device, lens):
 
 @pytest.mark.parametrize("lens,fwd_gen,bwd_gen", [([16384], 2, 2), ([8192, 8192], 2, 2), ([5000, 11000, 384], 2, 2),
                                                   ([16384], 1, 1), ([16384], 2, 1), ([16384], 1, 2), ([16384], 2, 3),
-                                                  ([5000, 11000, 384], 2, 3)])
+                                                  ([5000, 11000, 384], 2, 3), ([16384], 2, 4), ([8192, 8192], 2, 4),
+                                                  ([5000, 11000, 384], 2, 4), ([16384], 3, 4), ([8192, 8192], 3, 2),
+                                                  ([5000, 11000, 384], 3, 4)])
 def test_varlen_attention_qwen7b_heads_16k(cuda_device, lens, fwd_gen, bwd_gen):
     """the trainer's micro-batch size (16 384 packed tokens) at Qwen2.5-7B's 28 / 4 heads"""
     _run(cuda_device, 28, 4, lens, seed=5, fwd_gen=fwd_gen, bwd_gen=bwd_gen)

@@ -41,6 +41,8 @@ def main():
     ap.add_argument("--ours-only", action="store_true", help="one forward + one backward of our kernels, nothing else (ncu)")
     ap.add_argument("--tmem", action="store_true", help="TMEM read bandwidth microbenchmark")
     ap.add_argument("--profile", action="store_true", help="per-kernel device time (torch profiler)")
+    ap.add_argument("--fwd-gen", type=int, default=0, help="forward generation for --profile / --ours-only")
+    ap.add_argument("--bwd-gen", type=int, default=0, help="backward generation for --profile / --ours-only (0 = library default)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     o = Ops()
@@ -52,6 +54,11 @@ def main():
     d_out = torch.randn(T, n_q * D, generator=g, device=dev).to(torch.bfloat16)
     st = torch.arange(0, T, L, dtype=torch.int32, device=dev)
     ln = torch.tensor(lens, dtype=torch.int32, device=dev)
+    from pipelinerl_b200 import _lib as _l0
+    if a.bwd_gen:
+        _l0.check(o.lib.prl_attn_set_bwd_generation(a.bwd_gen))
+    if a.fwd_gen:
+        _l0.check(o.lib.prl_attn_set_fwd_generation(a.fwd_gen))
     if a.ours_only:
         for _ in range(2):
             out, lse = o.attn_fwd(qkv, st, ln, L, n_q, n_kv, D)
@@ -62,6 +69,9 @@ def main():
     _l.check(o.lib.prl_attn_set_fwd_generation(1))
     out1, _ = o.attn_fwd(qkv, st, ln, L, n_q, n_kv, D)
     fwd1_ms = timed(lambda: o.attn_fwd(qkv, st, ln, L, n_q, n_kv, D), a.reps)
+    _l.check(o.lib.prl_attn_set_fwd_generation(3))
+    out3, lse3 = o.attn_fwd(qkv, st, ln, L, n_q, n_kv, D)
+    fwd3_ms = timed(lambda: o.attn_fwd(qkv, st, ln, L, n_q, n_kv, D), a.reps)
     _l.check(o.lib.prl_attn_set_fwd_generation(2))
     out, lse = o.attn_fwd(qkv, st, ln, L, n_q, n_kv, D)
     fwd_ms = timed(lambda: o.attn_fwd(qkv, st, ln, L, n_q, n_kv, D), a.reps)
@@ -71,11 +81,17 @@ def main():
     _l.check(o.lib.prl_attn_set_bwd_generation(3))
     dq3 = o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D)
     bwd3_ms = timed(lambda: o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D), a.reps)
+    _l.check(o.lib.prl_attn_set_bwd_generation(4))
+    dq4 = o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D)
+    bwd4_ms = timed(lambda: o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D), a.reps)
     _l.check(o.lib.prl_attn_set_bwd_generation(2))
     dq2 = o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D)
     bwd_ms = timed(lambda: o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D), a.reps)
     flops_fwd = a.segments * n_q * 4 * D * L * L / 2
     res = {"bench": "learner_attention", "tokens": T, "segments": a.segments, "n_q": n_q, "n_kv": n_kv,
+           "fwd_gen3_ms": round(fwd3_ms, 3), "fwd_gen3_vs_gen2_max_abs_diff": (out3.float() - out.float()).abs().max().item(),
+           "fwd_gen3_lse_max_abs_diff": (lse3 - lse).abs().max().item(),
+           "bwd_gen4_ms": round(bwd4_ms, 3), "bwd_gen4_vs_gen2_max_abs_diff": (dq4.float() - dq2.float()).abs().max().item(),
            "bwd_gen3_ms": round(bwd3_ms, 3), "bwd_gen3_vs_gen2_max_abs_diff": (dq3.float() - dq2.float()).abs().max().item(),
            "bwd_gen1_ms": round(bwd1_ms, 3), "bwd_gen1_vs_gen2_max_abs_diff": (dq1.float() - dq2.float()).abs().max().item(),
            "fwd_gen1_ms": round(fwd1_ms, 3), "gen1_vs_gen2_max_abs_diff": (out1.float() - out.float()).abs().max().item(),
@@ -108,6 +124,10 @@ def main():
             cyc, nbytes = int(o3[0]), int(o3[1])
             res["tmem_read_bytes_per_clk_per_sm"][f"{w}_warps"] = round(nbytes / cyc, 1)
     if a.profile:
+        if a.bwd_gen:
+            _l.check(o.lib.prl_attn_set_bwd_generation(a.bwd_gen))
+        if a.fwd_gen:
+            _l.check(o.lib.prl_attn_set_fwd_generation(a.fwd_gen))
         from torch.profiler import ProfilerActivity, profile as tprofile
         with tprofile(activities=[ProfilerActivity.CUDA]) as prof:
             for _ in range(3):
