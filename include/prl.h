@@ -431,6 +431,14 @@ int prl_attn_varlen_bwd(const void* qkv_bf16, int64_t qkv_stride, int32_t T, con
 /* Measurement helper (tools/attn_bench.py --tmem): cycles for `warps` warps of every SM to read iters x 4 KB out of
  * TMEM with tcgen05.ld.32x32b.x32; out3 = {cycles, bytes per SM, -}. */
 int prl_debug_tmem_read_bench(int32_t iters, int32_t warps, int64_t* out3_device, prl_stream_t stream);
+/* measurement helper: tcgen05.mma throughput per operand configuration (modes 0-9, batches of 8 UMMAs under one lane
+ * election) and the softmax <-> tensor-core hand-off round trip (mode 10); out2_device[0] = cycles, [1] = UMMAs issued
+ * (profiles/r2_attention.md) */
+/* measurement helper: per-phase cycle sums of one CTA of the generation-2 learner attention forward (20 int64; NULL = off) */
+int prl_attn_debug_timing(int64_t* out20_device);
+/* likewise for the generation-4 dQ backward kernel (16 int64; NULL = off) */
+int prl_attn_debug_bwd_timing(int64_t* out16_device);
+int prl_debug_mma_bench(int32_t mode, int32_t iters, int64_t* out2_device, prl_stream_t stream);
 /* Sampling with in-kernel logprob capture: id ~ softmax(logits/T) (Gumbel-max, counter-based RNG on
  * (seed, step, row, vocab id)) or argmax when greedy; logprob = log_softmax(logits/T)[id]. */
 size_t prl_sample_workspace_bytes(int32_t B);

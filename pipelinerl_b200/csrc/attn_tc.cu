@@ -44,6 +44,7 @@ struct TcPrefillParams {
   // sequence z covers rows [seq_q_start[z], seq_q_start[z] + seq_q_len[z]) and its keys are those same rows
   int col_k, col_v;              // element column of K / V head 0
   float* lse;                    // [rows, n_q] log2-domain log-sum-exp of the scaled scores (may be NULL)
+  long long* timing;             // measurement only (prl_attn_debug_timing): per-phase cycle sums of one CTA, else NULL
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -82,11 +83,11 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   const int qtile = kContig ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int kvh = blockIdx.y, z = blockIdx.z;
   const uint32_t rank = ptx::cluster_ctarank();
-  const int q_len = p.seq_q_len[z];
-  const int pos0 = kContig ? 0 : p.seq_pos0[z];
+  const int q_len = ptx::warp_uniform(p.seq_q_len[z]);
+  const int pos0 = kContig ? 0 : ptx::warp_uniform(p.seq_pos0[z]);
   if ((qtile & ~1) * p.nq >= q_len) return;              // uniform across the CLUSTER, before any barrier / TMEM use
   const int t0 = qtile * p.nq;
-  const int row0 = p.seq_q_start[z] + t0;
+  const int row0 = ptx::warp_uniform(p.seq_q_start[z]) + t0;
   const int pos_first = pos0 + t0;
   const int n_valid = t0 >= q_len ? 0 : ((q_len - t0) < p.nq ? (q_len - t0) : p.nq);  // 0: partner-only CTA
   // both CTAs run the step count of the LATER tile (the earlier tile's extra step is fully masked)
@@ -112,6 +113,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   ptx::tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = ptx::warp_uniform(tmem_base);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -150,7 +152,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    {   // the whole warp, converged: one elected lane issues each tcgen05 instruction (ptx::elect_one)
       constexpr uint32_t idesc_qk = ptx::make_idesc_bf16_f32(128, kKeys);
       constexpr uint32_t idesc_pv = ptx::make_idesc_bf16_f32(128, kDT) | (1u << 16);  // B (= V) is MN-major
       auto issue_qk = [&](int j) {
@@ -160,14 +162,16 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         ptx::mbar_wait(bar(7 + s), ph ^ 1u);     // S[s] drained by the softmax warps (step j - 2)
         ptx::tc_fence_after_sync();
         const uint32_t k_addr = kv_smem + (uint32_t)(s * kStageBytesT);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a = ptx::make_kmajor_sw128_desc(q_smem + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
-          const uint64_t b = ptx::make_kmajor_sw128_desc(k_addr + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
-          ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 128), a, b, idesc_qk, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t a = ptx::make_kmajor_sw128_desc(q_smem + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
+            const uint64_t b = ptx::make_kmajor_sw128_desc(k_addr + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
+            ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 128), a, b, idesc_qk, ks > 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(bar(5 + s));
+          ptx::tc_commit_multicast(bar(3 + s), 3);  // K slot consumed here: tell BOTH producers
         }
-        ptx::tc_commit(bar(5 + s));
-        ptx::tc_commit_multicast(bar(3 + s), 3);  // K slot consumed here: tell BOTH producers
       };
       ptx::mbar_wait(bar(0), 0);
       issue_qk(0);
@@ -181,14 +185,16 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         ptx::tc_fence_after_sync();
         const uint32_t v_addr = kv_smem + (uint32_t)(s * kStageBytesT) + 2 * kTile16K;
         const uint32_t p_addr = p_smem + (uint32_t)(s * 2 * kTile16K);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a = ptx::make_kmajor_sw128_desc(p_addr + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
-          const uint64_t b = ptx::make_mnmajor_sw128_desc(v_addr, kTile16K) + (uint64_t)(128 * ks);
-          ptx::mma_bf16_ss(tmem_base + (uint32_t)(256 + s * 128), a, b, idesc_pv, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t a = ptx::make_kmajor_sw128_desc(p_addr + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
+            const uint64_t b = ptx::make_mnmajor_sw128_desc(v_addr, kTile16K) + (uint64_t)(128 * ks);
+            ptx::mma_bf16_ss(tmem_base + (uint32_t)(256 + s * 128), a, b, idesc_pv, ks > 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(bar(10 + s));   // Ot[s] complete (and P[s] free again)
+          ptx::tc_commit_multicast(bar(17 + s), 3);  // V slot consumed here: tell BOTH producers
         }
-        ptx::tc_commit(bar(10 + s));   // Ot[s] complete (and P[s] free again)
-        ptx::tc_commit_multicast(bar(17 + s), 3);  // V slot consumed here: tell BOTH producers
       }
     }
     __syncwarp();
@@ -337,7 +343,7 @@ __device__ __forceinline__ void group_bar(int g) {
   else asm volatile("bar.sync 2, 128;" ::: "memory");
 }
 
-template <bool kContig>
+template <bool kContig, bool kTimed = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1)   // 10 warps: 3 share one SMSP -> 168 registers
 attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, TcPrefillParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -355,11 +361,11 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const int qtile = kContig ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int kvh = blockIdx.y, z = blockIdx.z;
   const uint32_t rank = ptx::cluster_ctarank();
-  const int q_len = p.seq_q_len[z];
-  const int pos0 = kContig ? 0 : p.seq_pos0[z];
+  const int q_len = ptx::warp_uniform(p.seq_q_len[z]);
+  const int pos0 = kContig ? 0 : ptx::warp_uniform(p.seq_pos0[z]);
   if ((qtile & ~1) * p.nq >= q_len) return;              // uniform across the CLUSTER, before any barrier / TMEM use
   const int t0 = qtile * p.nq;
-  const int row0 = p.seq_q_start[z] + t0;
+  const int row0 = ptx::warp_uniform(p.seq_q_start[z]) + t0;
   const int pos_first = pos0 + t0;
   const int n_valid = t0 >= q_len ? 0 : ((q_len - t0) < p.nq ? (q_len - t0) : p.nq);
   const int pair_rows = ((qtile | 1) + 1) * p.nq;
@@ -384,6 +390,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   ptx::tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = ptx::warp_uniform(tmem_base);
 
   if (warp == 0) {
     // ===== TMA producer (as generation 1) =====
@@ -421,7 +428,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    {   // the whole warp, converged: one elected lane issues each tcgen05 instruction (ptx::elect_one)
       constexpr uint32_t idesc_qk = ptx::make_idesc_bf16_f32(128, kKeys);
       constexpr uint32_t idesc_pv = ptx::make_idesc_bf16_f32(128, kDT) | (1u << 16);  // B (= V) is MN-major
       auto issue_qk = [&](int j) {
@@ -432,15 +439,19 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         // issue order, so this Q K^T cannot overtake it (and the softmax group finished reading S_s before it stored P_s)
         ptx::tc_fence_after_sync();
         const uint32_t k_addr = kv_smem + (uint32_t)(ks_ * kStageBytesT);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a = ptx::make_kmajor_sw128_desc(q_smem + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
-          const uint64_t b = ptx::make_kmajor_sw128_desc(k_addr + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
-          ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 128), a, b, idesc_qk, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t a = ptx::make_kmajor_sw128_desc(q_smem + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
+            const uint64_t b = ptx::make_kmajor_sw128_desc(k_addr + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
+            ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 128), a, b, idesc_qk, ks > 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(bar(7 + s));
+          ptx::tc_commit_multicast(bar(4 + ks_), 3);
         }
-        ptx::tc_commit(bar(7 + s));
-        ptx::tc_commit_multicast(bar(4 + ks_), 3);
       };
+      const bool timed = kTimed && p.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      long long w_p = 0, w_v = 0, w_tot0 = clock64();
       ptx::mbar_wait(bar(0), 0);
       issue_qk(0);
       for (int i = 0; i < n_it; ++i) {
@@ -448,18 +459,23 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const int s = i & 1;
         const uint32_t ph = (uint32_t)((i >> 1) & 1);
         const int vs_ = i % kSt;
+        const long long c0 = clock64();
         ptx::mbar_wait(bar(9 + s), ph);              // P_s of step i is in TMEM (and O_s rescaled if it had to be)
+        const long long c1 = clock64();
         ptx::mbar_wait(bar(13 + vs_), (uint32_t)((i / kSt) & 1));   // V of step i landed
+        w_p += c1 - c0; w_v += clock64() - c1;
         ptx::tc_fence_after_sync();
         const uint32_t v_addr = kv_smem + (uint32_t)(vs_ * kStageBytesT) + 2 * kTile16K;
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {             // A = P_s out of TMEM: 16 keys = 8 packed columns per UMMA
-          const uint64_t b = ptx::make_mnmajor_sw128_desc(v_addr, kTile16K) + (uint64_t)(128 * ks);
-          ptx::mma_bf16_ts(tmem_base + (uint32_t)(256 + s * 128), tmem_base + (uint32_t)(s * 128 + ks * 8), b, idesc_pv,
-                           (i >= 2 || ks > 0) ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks) {             // A = P_s out of TMEM: 16 keys = 8 packed columns per UMMA
+            const uint64_t b = ptx::make_mnmajor_sw128_desc(v_addr, kTile16K) + (uint64_t)(128 * ks);
+            ptx::mma_bf16_ts(tmem_base + (uint32_t)(256 + s * 128), tmem_base + (uint32_t)(s * 128 + ks * 8), b, idesc_pv,
+                             (i >= 2 || ks > 0) ? 1u : 0u);
+          }
+          ptx::tc_commit(bar(11 + s));                 // O_s updated
+          ptx::tc_commit_multicast(bar(16 + vs_), 3);  // V slot consumed: tell BOTH producers
         }
-        ptx::tc_commit(bar(11 + s));                 // O_s updated
-        ptx::tc_commit_multicast(bar(16 + vs_), 3);  // V slot consumed: tell BOTH producers
       }
     }
     __syncwarp();
@@ -476,11 +492,15 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const bool leader = (threadIdx.x == 64 + g * 128);
     float2* xchg = reinterpret_cast<float2*>(smem_raw + (bar_base - ptx::smem_u32(smem_raw)) + 8 * 20);  // [128] (m_ref, l) of group 1
     float m_ref = 0.f, l_run = 0.f;
+    const bool timed = kTimed && p.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && q == 0 && lane == 0;
+    long long tph[6] = {0, 0, 0, 0, 0, 0};
 
     for (int i = g; i < n_it; i += 2) {
       const int j = i >> 1;
+      const long long c0 = clock64();
       ptx::mbar_wait(bar(7 + g), (uint32_t)(j & 1));
       ptx::tc_fence_after_sync();
+      const long long c1 = clock64();
       float sv[128];
       {
         uint32_t su[128];                                   // four 32-column reads in flight, one wait
@@ -491,6 +511,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 #pragma unroll
         for (int e = 0; e < 128; ++e) sv[e] = __uint_as_float(su[e]);
       }
+      const long long c2 = clock64();
       if (i * kKeys + kKeys - 1 > pos_first) {              // some (row, key) of this step is causally masked
         const int key0 = i * kKeys;
 #pragma unroll
@@ -505,6 +526,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = mx * p.scale_log2;                // scale > 0: max commutes with the scaling
+      const long long c3 = clock64();
       if (j == 0) {
         m_ref = (m_new == -INFINITY) ? 0.f : m_new;
       } else {
@@ -529,6 +551,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
       // P_g goes back into TMEM as the A operand of P V, in place of this row's own S values (lane = row; one 32-bit column
       // = two adjacent keys): no shared-memory store, no shared-memory read by the tensor core
+      const long long c4 = clock64();
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};                 // independent partial row sums (fixed order: deterministic)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -544,9 +567,18 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
       l_run += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       ptx::tmem_st_wait();
+      const long long c5 = clock64();
       ptx::tc_fence_before_sync();
       group_bar(g);
       if (leader) ptx::mbar_arrive(bar(9 + g));             // P_g ready -> P V of step i
+      if (timed) {
+        const long long c6 = clock64();
+        tph[0] += c1 - c0; tph[1] += c2 - c1; tph[2] += c3 - c2; tph[3] += c4 - c3; tph[4] += c5 - c4; tph[5] += c6 - c5;
+      }
+    }
+    if (timed) {
+#pragma unroll
+      for (int e = 0; e < 6; ++e) p.timing[g * 8 + e] = tph[e];
     }
 
     // ---- merge the two groups' partial results and write the output rows (group 0) ----
@@ -605,301 +637,6 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 }
 
 
-// =====================================================================================================
-// Forward, generation 3: generation 2 with the softmax row split over TWO threads (16 softmax warps, 4 per TMEM lane
-// quarter and per scheduler).  A group step of generation 2 is one long dependent chain per thread -- 128-column
-// tcgen05.ld, 128-deep max, 128 exp2, pack, tcgen05.st -- with one other warp on the scheduler to hide it
-// (profiles/r2_attention.md: tensor pipe 51 %, MUFU 51 %, and the two ADD).  Halving the chain and doubling the warps lets
-// one warp's exp2 run under its neighbours' TMEM traffic.  The two threads of a row agree on the step's reference maximum
-// through 2 bytes of shared memory (each rounds its half-row maximum to bf16 first, so both compute the identical value --
-// the reference only has to be close to the maximum, not equal to it), keep separate partial row sums, and write their
-// packed P over the first 32 of their own 64 S columns (UMMA k-step ks reads packed columns 64 (ks / 4) + 8 (ks % 4)).
-// =====================================================================================================
-constexpr int kThreadsT3 = 576;
-
-__device__ __forceinline__ void group_bar256_f(int g) {
-  if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-  else asm volatile("bar.sync 2, 256;" ::: "memory");
-}
-
-template <bool kContig>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT3, 1)
-attn_fwd_v3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, TcPrefillParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t q_smem = base;
-  const uint32_t kv_smem = base + 2 * kTile16K;
-  constexpr int kSt = 3;
-  const uint32_t bar_base = kv_smem + kSt * kStageBytesT;
-  auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
-  // 0 q_full | 1..3 k_full | 4..6 k_empty | 7,8 s_full | 9,10 p_full (8 warps) | 11,12 o_full | 13..15 v_full | 16..18 v_empty
-  const uint32_t tmem_slot = bar(19);
-
-  const int qtile = kContig ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
-  const int kvh = blockIdx.y, z = blockIdx.z;
-  const uint32_t rank = ptx::cluster_ctarank();
-  const int q_len = p.seq_q_len[z];
-  const int pos0 = kContig ? 0 : p.seq_pos0[z];
-  if ((qtile & ~1) * p.nq >= q_len) return;
-  const int t0 = qtile * p.nq;
-  const int row0 = p.seq_q_start[z] + t0;
-  const int pos_first = pos0 + t0;
-  const int n_valid = t0 >= q_len ? 0 : ((q_len - t0) < p.nq ? (q_len - t0) : p.nq);
-  const int pair_rows = ((qtile | 1) + 1) * p.nq;
-  const int kv_end = pos0 + (pair_rows < q_len ? pair_rows : q_len);
-  const int n_it = (kv_end + kKeys - 1) / kKeys;
-  const int last_page = (kv_end - 1) / kPageT;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 19; ++i) {
-      int cnt = 1;
-      if ((i >= 4 && i <= 6) || (i >= 16 && i <= 18)) cnt = 2;     // *_empty: both CTAs
-      if (i == 9 || i == 10) cnt = 8;                              // p_full: one arrival per warp of the group
-      ptx::mbar_init(bar(i), cnt);
-    }
-    ptx::fence_barrier_init();
-    ptx::fence_proxy_async();
-    ptx::prefetch_tensormap(&tm_q);
-    ptx::prefetch_tensormap(&tm_kv);
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before_sync();
-  ptx::cluster_sync();
-  ptx::tc_fence_after_sync();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  if (warp == 0) {
-    // ===== TMA producer (as generations 1 and 2) =====
-    if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(bar(0), (uint32_t)(2 * 128 * p.R * p.nq));
-      ptx::tma_load_3d(q_smem, &tm_q, 0, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
-      ptx::tma_load_3d(q_smem + kTile16K, &tm_q, 64, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
-      const int32_t* bt = kContig ? nullptr : p.block_table + (int64_t)p.seq_slot[z] * p.max_blocks;
-      const int seq_row0 = p.seq_q_start[z];
-      auto load_page = [&](int it, int kv, uint32_t full_bar, uint32_t empty_bar) {
-        const int s = it % kSt;
-        const uint32_t ph = (uint32_t)((it / kSt) & 1);
-        ptx::mbar_wait(empty_bar + 8u * (uint32_t)s, ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(full_bar + 8u * (uint32_t)s, (uint32_t)(2 * kTile16K));
-        int pg = 2 * it + (int)rank;
-        if (pg > last_page) pg = last_page;
-        int row, c0;
-        if (kContig) {
-          row = seq_row0 + pg * kPageT;
-          c0 = (kv ? p.col_v : p.col_k) + kvh * kDT;
-        } else {
-          const int page = bt[pg];
-          row = (int)(((((int64_t)p.layer * 2 + kv) * p.n_pages + page) * p.n_kv + kvh) * kPageT);
-          c0 = 0;
-        }
-        const uint32_t dst = kv_smem + (uint32_t)(s * kStageBytesT + kv * 2 * kTile16K) + (uint32_t)(rank * 8192);
-        ptx::tma_load_2d_multicast(dst, &tm_kv, c0, row, full_bar + 8u * (uint32_t)s, 3, ptx::kEvictLast);
-        ptx::tma_load_2d_multicast(dst + kTile16K, &tm_kv, c0 + 64, row, full_bar + 8u * (uint32_t)s, 3, ptx::kEvictLast);
-      };
-      load_page(0, 0, bar(1), bar(4));
-      for (int it = 0; it < n_it; ++it) {
-        if (it + 1 < n_it) load_page(it + 1, 0, bar(1), bar(4));
-        load_page(it, 1, bar(13), bar(16));
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = ptx::make_idesc_bf16_f32(128, kKeys);
-      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16_f32(128, kDT) | (1u << 16);
-      auto issue_qk = [&](int j) {
-        const int s = j & 1;
-        const int ks_ = j % kSt;
-        ptx::mbar_wait(bar(1 + ks_), (uint32_t)((j / kSt) & 1));
-        ptx::tc_fence_after_sync();
-        const uint32_t k_addr = kv_smem + (uint32_t)(ks_ * kStageBytesT);
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a = ptx::make_kmajor_sw128_desc(q_smem + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
-          const uint64_t b = ptx::make_kmajor_sw128_desc(k_addr + (uint32_t)((ks >> 2) * kTile16K)) + (uint64_t)(2 * (ks & 3));
-          ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 128), a, b, idesc_qk, ks > 0 ? 1u : 0u);
-        }
-        ptx::tc_commit(bar(7 + s));
-        ptx::tc_commit_multicast(bar(4 + ks_), 3);
-      };
-      ptx::mbar_wait(bar(0), 0);
-      issue_qk(0);
-      for (int i = 0; i < n_it; ++i) {
-        if (i + 1 < n_it) issue_qk(i + 1);
-        const int s = i & 1;
-        const uint32_t ph = (uint32_t)((i >> 1) & 1);
-        const int vs_ = i % kSt;
-        ptx::mbar_wait(bar(9 + s), ph);
-        ptx::mbar_wait(bar(13 + vs_), (uint32_t)((i / kSt) & 1));
-        ptx::tc_fence_after_sync();
-        const uint32_t v_addr = kv_smem + (uint32_t)(vs_ * kStageBytesT) + 2 * kTile16K;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {             // A = P_s out of TMEM: keys 16 ks .. 16 ks + 15 = 8 packed columns
-          const uint64_t b = ptx::make_mnmajor_sw128_desc(v_addr, kTile16K) + (uint64_t)(128 * ks);
-          ptx::mma_bf16_ts(tmem_base + (uint32_t)(256 + s * 128), tmem_base + (uint32_t)(s * 128 + (ks >> 2) * 64 + (ks & 3) * 8), b,
-                           idesc_pv, (i >= 2 || ks > 0) ? 1u : 0u);
-        }
-        ptx::tc_commit(bar(11 + s));
-        ptx::tc_commit_multicast(bar(16 + vs_), 3);
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===== softmax: group g = steps i = g (mod 2); threads (h = 0, 1) of a (token, head) row own keys [64 h, 64 h + 64) =====
-    const int q = warp & 3;
-    const int idx = (warp - 2) >> 2;            // 0..3
-    const int g = idx & 1, h = idx >> 1;
-    const int m = q * 32 + lane;
-    const int qi = m / p.R, r = m - qi * p.R;
-    const int qpos = pos_first + qi;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t s_addr = lane_addr + (uint32_t)(g * 128 + h * 64);
-    const uint32_t o_addr = lane_addr + (uint32_t)(256 + g * 128 + h * 64);
-    // [group][half][row] bf16 half-row maxima
-    unsigned short* xmax = reinterpret_cast<unsigned short*>(smem_raw + (bar_base - ptx::smem_u32(smem_raw)) + 8 * 20);
-    unsigned short* xm_own = xmax + (g * 2 + h) * 128 + m;
-    const unsigned short* xm_other = xmax + (g * 2 + (h ^ 1)) * 128 + m;
-    float m_ref = 0.f, l_run = 0.f;
-
-    for (int i = g; i < n_it; i += 2) {
-      const int j = i >> 1;
-      ptx::mbar_wait(bar(7 + g), (uint32_t)(j & 1));
-      ptx::tc_fence_after_sync();
-      float sv[64];
-      {
-        uint32_t su[64];
-        ptx::tmem_ld_32x32b_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&su[0]));
-        ptx::tmem_ld_32x32b_x32(s_addr + 32u, *reinterpret_cast<uint32_t(*)[32]>(&su[32]));
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 64; ++e) sv[e] = __uint_as_float(su[e]);
-      }
-      if (i * kKeys + kKeys - 1 > pos_first) {
-        const int key0 = i * kKeys + h * 64;
-#pragma unroll
-        for (int e = 0; e < 64; ++e)
-          if (key0 + e > qpos) sv[e] = -INFINITY;
-      }
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int e = 0; e < 64; e += 4) {
-        mx4[0] = fmaxf(mx4[0], sv[e]); mx4[1] = fmaxf(mx4[1], sv[e + 1]);
-        mx4[2] = fmaxf(mx4[2], sv[e + 2]); mx4[3] = fmaxf(mx4[3], sv[e + 3]);
-      }
-      const float mx_half = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;
-      const __nv_bfloat16 mxb = __float2bfloat16_rn(mx_half);
-      *xm_own = *reinterpret_cast<const unsigned short*>(&mxb);
-      group_bar256_f(g);        // the partner's next write waits for P V of this step, i.e. for this thread's p_full arrival
-      const unsigned short ob = *xm_other;
-      const float m_new = fmaxf(__bfloat162float(mxb), __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&ob)));
-      if (j == 0) {
-        m_ref = (m_new == -INFINITY) ? 0.f : m_new;
-      } else {
-        ptx::mbar_wait(bar(11 + g), (uint32_t)((j - 1) & 1));   // P V of step i - 2 done: O_g up to date
-        const bool need = m_new > m_ref + 8.f;
-        if (__any_sync(0xffffffffu, need)) {
-          ptx::tc_fence_after_sync();
-          const float f = need ? ex2(m_ref - m_new) : 1.f;
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {                     // this thread's 64 of the row's 128 head-dim columns
-            uint32_t v[16];
-            ptx::tmem_ld_32x32b_x16(o_addr + (uint32_t)(c * 16), v);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * f);
-            ptx::tmem_st_32x32b_x16(o_addr + (uint32_t)(c * 16), v);
-          }
-          ptx::tmem_st_wait();
-          l_run *= f;
-          if (need) m_ref = m_new;
-        }
-      }
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t pp[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float p0 = ex2(fmaf(sv[c * 32 + 2 * e], p.scale_log2, -m_ref));
-          const float p1 = ex2(fmaf(sv[c * 32 + 2 * e + 1], p.scale_log2, -m_ref));
-          sum4[e & 3] += p0 + p1;
-          pp[e] = pack2(p0, p1);
-        }
-        ptx::tmem_st_32x32b_x16(s_addr + (uint32_t)(c * 16), pp);
-      }
-      l_run += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar(9 + g));          // this warp's part of P_g is in TMEM
-    }
-
-    // ---- merge: four partial results per row (2 groups x 2 halves); every thread writes 32 head-dim columns ----
-    const int n0 = (n_it + 1) >> 1, n1 = n_it >> 1;
-    if (g == 0) {
-      ptx::mbar_wait(bar(11), (uint32_t)((n0 - 1) & 1));
-      if (n1 > 0) ptx::mbar_wait(bar(12), (uint32_t)((n1 - 1) & 1));
-    } else {
-      if (n1 > 0) ptx::mbar_wait(bar(12), (uint32_t)((n1 - 1) & 1));
-      ptx::mbar_wait(bar(11), (uint32_t)((n0 - 1) & 1));
-    }
-    ptx::tc_fence_after_sync();
-    // every UMMA and every TMA write of this CTA has completed: the K/V stages are free to carry the exchange
-    float* xl = reinterpret_cast<float*>(smem_raw + (kv_smem - ptx::smem_u32(smem_raw)));    // [group][half][row]
-    float* xmr = xl + 4 * 128;                                                               // [group][row]
-    xl[(g * 2 + h) * 128 + m] = l_run;
-    if (h == 0) xmr[g * 128 + m] = m_ref;
-    asm volatile("bar.sync 3, 512;" ::: "memory");
-    {
-      const float l0 = xl[m] + xl[128 + m], l1 = xl[256 + m] + xl[384 + m];
-      const float m0 = xmr[m], m1 = xmr[128 + m];
-      const bool use1 = n1 > 0 && l1 > 0.f;
-      const bool use0 = l0 > 0.f;
-      const float m_all = use0 ? (use1 ? fmaxf(m0, m1) : m0) : m1;
-      const float f0 = use0 ? ex2(m0 - m_all) : 0.f;
-      const float f1 = use1 ? ex2(m1 - m_all) : 0.f;
-      const float l_tot = f0 * l0 + f1 * l1;
-      const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
-      const bool valid = qi < n_valid && qi < p.nq;
-      const int c = h * 2 + g;                              // this thread's 32 head-dim columns
-      uint32_t a[32], b[32];
-      ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(256 + c * 32), a);
-      if (n1 > 0) ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(384 + c * 32), b);
-      ptx::tmem_ld_wait();
-      if (valid) {
-        __nv_bfloat16* dst = p.out + ((int64_t)(row0 + qi) * p.n_q + (kvh * p.R + r)) * kDT + c * 32;
-        const float w0 = f0 * inv, w1 = f1 * inv;
-#pragma unroll
-        for (int d = 0; d < 32; d += 8) {
-          float o[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            o[e] = __uint_as_float(a[d + e]) * w0;
-            if (n1 > 0) o[e] = fmaf(use1 ? __uint_as_float(b[d + e]) : 0.f, w1, o[e]);
-          }
-          uint4 u;
-          u.x = pack2(o[0], o[1]); u.y = pack2(o[2], o[3]); u.z = pack2(o[4], o[5]); u.w = pack2(o[6], o[7]);
-          *reinterpret_cast<uint4*>(dst + d) = u;
-        }
-        if (kContig && c == 0 && p.lse != nullptr)
-          p.lse[(int64_t)(row0 + qi) * p.n_q + (kvh * p.R + r)] = m_all + log2f(l_tot);
-      }
-    }
-  }
-
-  ptx::tc_fence_before_sync();
-  ptx::cluster_sync();
-  if (warp == 1) {
-    ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc(tmem_base, 512);
-  }
-}
-
 }  // namespace
 }  // namespace prl
 
@@ -908,12 +645,12 @@ using namespace prl;
 // which forward kernel the two entry points launch (generation 1 stays selectable for A/B runs and tests:
 // PRL_ATTN_FWD=1 / PRL_PREFILL_ATTN_GEN=1, prl_attn_set_fwd_generation / prl_attn_set_prefill_generation)
 namespace prl { namespace {
-int g_fwd_generation = [] { const char* e = getenv("PRL_ATTN_FWD"); return (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 2; }();
-int g_prefill_generation = [] { const char* e = getenv("PRL_PREFILL_ATTN_GEN"); return (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 2; }();
+int g_fwd_generation = [] { const char* e = getenv("PRL_ATTN_FWD"); return (e && e[0] == '1') ? 1 : 2; }();
+int g_prefill_generation = [] { const char* e = getenv("PRL_PREFILL_ATTN_GEN"); return (e && e[0] == '1') ? 1 : 2; }();
 } }
 
 extern "C" int prl_attn_set_prefill_generation(int32_t gen) {
-  PRL_CHECK_ARG(gen >= 1 && gen <= 3, "prl_attn_set_prefill_generation: 1, 2 or 3");
+  PRL_CHECK_ARG(gen == 1 || gen == 2, "prl_attn_set_prefill_generation: 1 or 2");
   prl::g_prefill_generation = gen;
   return PRL_OK;
 }
@@ -938,7 +675,7 @@ extern "C" int prl_paged_attn_prefill_tc(const void* q, int32_t q_rows, const vo
   p.seq_slot = seq_slot; p.max_blocks = max_blocks; p.n_q = n_q; p.n_kv = n_kv; p.R = n_q / n_kv;
   p.nq = 128 / p.R;
   p.n_pages = n_pages; p.layer = layer; p.scale_log2 = sm_scale * 1.4426950408889634f;
-  p.col_k = p.col_v = 0; p.lse = nullptr;
+  p.col_k = p.col_v = 0; p.lse = nullptr; p.timing = nullptr;
   CUtensorMap tq, tkv;
   int rc = make_tmap_2d_bf16(&tkv, kv_cache, kDT, (uint64_t)total_rows, kDT * 2, 64, kPageT);
   if (rc) return rc;
@@ -948,11 +685,7 @@ extern "C" int prl_paged_attn_prefill_tc(const void* q, int32_t q_rows, const vo
   const int smem = 2 * kTile16K + 2 * kStageBytesT + 4 * kTile16K + 1024 + 8 * 20 + 2 * 128 * 4 + 16;
   static SmemAttr smem_attr = {};
   dim3 grid((unsigned)(((max_q_len + p.nq - 1) / p.nq + 1) & ~1), (unsigned)n_kv, (unsigned)n_seqs);  // pairs of q tiles
-  if (g_prefill_generation == 3) {      // generation 2 with the row split over two threads (see attn_fwd_v3_kernel)
-    static SmemAttr smem_attr3 = {};
-    PRL_CUDA(ensure_smem(attn_fwd_v3_kernel<false>, smem, smem_attr3));
-    attn_fwd_v3_kernel<false><<<grid, kThreadsT3, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
-  } else if (g_prefill_generation == 2) {      // ping-pong softmax groups, P and O in TMEM (see attn_fwd_v2_kernel)
+  if (g_prefill_generation == 2) {      // ping-pong softmax groups, P and O in TMEM (see attn_fwd_v2_kernel)
     static SmemAttr smem_attr2 = {};
     PRL_CUDA(ensure_smem(attn_fwd_v2_kernel<false>, smem, smem_attr2));
     attn_fwd_v2_kernel<false><<<grid, kThreadsT, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
@@ -965,9 +698,17 @@ extern "C" int prl_paged_attn_prefill_tc(const void* q, int32_t q_rows, const vo
 }
 
 
+namespace prl { namespace { long long* g_fwd_timing = nullptr; } }
+// measurement only: per-phase cycle sums of CTA (0,0,0) of the next generation-2 learner forward launches
+// [0..5] group 0: wait S | tcgen05.ld | mask + max | wait O + rescale | exp2 + pack + tcgen05.st | barrier + arrive
+// [8..13] group 1 likewise; [16] MMA warp waiting for P, [17] for V, [18] MMA warp total, [19] steps.  NULL switches it off.
+extern "C" int prl_attn_debug_timing(int64_t* out20_device) {
+  prl::g_fwd_timing = (long long*)out20_device;
+  return PRL_OK;
+}
+
 extern "C" int prl_attn_set_fwd_generation(int32_t gen) {
-  PRL_CHECK_ARG(gen >= 1 && gen <= 3, "prl_attn_set_fwd_generation: 1 (lock-step softmax, O folded in registers), 2 (ping-pong, O in TMEM) "
-                "or 3 (2 with two threads per row)");
+  PRL_CHECK_ARG(gen == 1 || gen == 2, "prl_attn_set_fwd_generation: 1 (lock-step softmax, O folded in registers) or 2 (ping-pong, O in TMEM)");
   prl::g_fwd_generation = gen;
   return PRL_OK;
 }
@@ -991,7 +732,7 @@ extern "C" int prl_attn_varlen_fwd(const void* qkv, int64_t qkv_stride, int32_t 
   p.block_table = nullptr; p.seq_q_start = seg_start; p.seq_q_len = seg_len; p.seq_pos0 = nullptr; p.seq_slot = nullptr;
   p.max_blocks = 0; p.n_q = n_q; p.n_kv = n_kv; p.R = n_q / n_kv; p.nq = 128 / p.R;
   p.n_pages = 0; p.layer = 0; p.scale_log2 = sm_scale * 1.4426950408889634f;
-  p.col_k = n_q * kDT; p.col_v = (n_q + n_kv) * kDT; p.lse = lse;
+  p.col_k = n_q * kDT; p.col_v = (n_q + n_kv) * kDT; p.lse = lse; p.timing = g_fwd_timing;
   CUtensorMap tq, tkv;
   int rc = make_tmap_2d_bf16(&tkv, qkv, (uint64_t)(n_q + 2 * n_kv) * kDT, (uint64_t)T, (uint64_t)qkv_stride * 2, 64, kPageT);
   if (rc) return rc;
@@ -1004,10 +745,10 @@ extern "C" int prl_attn_varlen_fwd(const void* qkv, int64_t qkv_stride, int32_t 
     static SmemAttr smem_attr = {};
     PRL_CUDA(ensure_smem(attn_prefill_tc_kernel<true>, smem, smem_attr));
     attn_prefill_tc_kernel<true><<<grid, kThreadsT, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
-  } else if (g_fwd_generation == 3) {
-    static SmemAttr smem_attr3 = {};
-    PRL_CUDA(ensure_smem(attn_fwd_v3_kernel<true>, smem, smem_attr3));
-    attn_fwd_v3_kernel<true><<<grid, kThreadsT3, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
+  } else if (g_fwd_timing != nullptr) {
+    static SmemAttr smem_attr_t = {};
+    PRL_CUDA(ensure_smem(attn_fwd_v2_kernel<true, true>, smem, smem_attr_t));
+    attn_fwd_v2_kernel<true, true><<<grid, kThreadsT, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
   } else {
     static SmemAttr smem_attr2 = {};
     PRL_CUDA(ensure_smem(attn_fwd_v2_kernel<true>, smem, smem_attr2));

@@ -50,6 +50,7 @@ struct BwdParams {
   const __nv_bfloat16* q_base;   // qkv (query heads first) and d_out, for the kernels that stage rows themselves
   const __nv_bfloat16* do_base;
   int64_t q_stride, do_stride;
+  long long* timing;             // measurement only (prl_attn_debug_bwd_timing): per-phase cycle sums of one CTA, else NULL
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -112,10 +113,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   float* meta = reinterpret_cast<float*>(smem_raw + (meta_smem - ptx::smem_u32(smem_raw)));
 
   const int jt = blockIdx.x, kvh = blockIdx.y, z = blockIdx.z;
-  const int q_len = p.seg_len[z];
+  const int q_len = ptx::warp_uniform(p.seg_len[z]);
   const int key0 = jt * 128;
   if (key0 >= q_len) return;                       // before any barrier / TMEM use
-  const int seg0 = p.seg_start[z];
+  const int seg0 = ptx::warp_uniform(p.seg_start[z]);
   const int nqa = p.nq;
   const int u_first = key0 / nqa;                  // first 64-row query sub-tile holding a token >= key0
   const int u_end = (q_len + nqa - 1) / nqa;
@@ -145,6 +146,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   ptx::tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = ptx::warp_uniform(tmem_base);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -177,7 +179,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    {   // the whole warp, converged: one elected lane issues each tcgen05 instruction (ptx::elect_one)
       constexpr uint32_t idesc_t = ptx::make_idesc_bf16_f32(128, 64);                 // S^T, dP^T: both operands K-major
       constexpr uint32_t idesc_acc = ptx::make_idesc_bf16_f32(128, kD) | (1u << 16);  // dV, dK: B (dO / Q) MN-major
       auto issue_sdp = [&](int it) {
@@ -188,19 +190,21 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         if (!kTS) ptx::mbar_wait(bar(9 + s), (uint32_t)(((it >> 1) & 1) ^ 1));    // S^T[s], dP^T[s] read by the softmax warps
         ptx::tc_fence_after_sync();
         const uint32_t q_addr = q_ring + (uint32_t)(st * kQSlot);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a = ptx::make_kmajor_sw128_desc(kv_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
-          const uint64_t b = ptx::make_kmajor_sw128_desc(q_addr + (uint32_t)((ks >> 2) * kT8)) + (uint64_t)(2 * (ks & 3));
-          ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 64), a, b, idesc_t, ks > 0 ? 1u : 0u);
-        }
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t a = ptx::make_kmajor_sw128_desc(kv_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+            const uint64_t b = ptx::make_kmajor_sw128_desc(q_addr + (uint32_t)((ks >> 2) * kT8)) + (uint64_t)(2 * (ks & 3));
+            ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 64), a, b, idesc_t, ks > 0 ? 1u : 0u);
+          }
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a = ptx::make_kmajor_sw128_desc(kv_smem + (uint32_t)(2 * kT16 + (ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
-          const uint64_t b = ptx::make_kmajor_sw128_desc(q_addr + (uint32_t)(2 * kT8 + (ks >> 2) * kT8)) + (uint64_t)(2 * (ks & 3));
-          ptx::mma_bf16_ss(tmem_base + (uint32_t)(128 + s * 64), a, b, idesc_t, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t a = ptx::make_kmajor_sw128_desc(kv_smem + (uint32_t)(2 * kT16 + (ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+            const uint64_t b = ptx::make_kmajor_sw128_desc(q_addr + (uint32_t)(2 * kT8 + (ks >> 2) * kT8)) + (uint64_t)(2 * (ks & 3));
+            ptx::mma_bf16_ss(tmem_base + (uint32_t)(128 + s * 64), a, b, idesc_t, ks > 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(bar(7 + s));
         }
-        ptx::tc_commit(bar(7 + s));
       };
       ptx::mbar_wait(bar(0), 0);
       issue_sdp(0);
@@ -211,24 +215,28 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         ptx::tc_fence_after_sync();
         const uint32_t q_addr = q_ring + (uint32_t)(st * kQSlot);
         const uint32_t pt_addr = pds_smem + (uint32_t)(s * kPdsSlot);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {     // dV += P^T dO      (contraction over the 64 query rows)
-          const uint64_t b = ptx::make_mnmajor_sw128_desc(q_addr + 2 * kT8, kT8) + (uint64_t)(128 * ks);
-          if (kTS) ptx::mma_bf16_ts(tmem_base + 256u, tmem_base + (uint32_t)(s * 64 + ks * 8), b, idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
-          else ptx::mma_bf16_ss(tmem_base + 256u, ptx::make_kmajor_sw128_desc(pt_addr) + (uint64_t)(2 * ks), b, idesc_acc,
-                                (it > 0 || ks > 0) ? 1u : 0u);
-        }
+          for (int ks = 0; ks < 4; ++ks) {     // dV += P^T dO      (contraction over the 64 query rows)
+            const uint64_t b = ptx::make_mnmajor_sw128_desc(q_addr + 2 * kT8, kT8) + (uint64_t)(128 * ks);
+            if (kTS) ptx::mma_bf16_ts(tmem_base + 256u, tmem_base + (uint32_t)(s * 64 + ks * 8), b, idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
+            else ptx::mma_bf16_ss(tmem_base + 256u, ptx::make_kmajor_sw128_desc(pt_addr) + (uint64_t)(2 * ks), b, idesc_acc,
+                                  (it > 0 || ks > 0) ? 1u : 0u);
+          }
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {     // dK += dS^T Q
-          const uint64_t b = ptx::make_mnmajor_sw128_desc(q_addr, kT8) + (uint64_t)(128 * ks);
-          if (kTS) ptx::mma_bf16_ts(tmem_base + 384u, tmem_base + (uint32_t)(128 + s * 64 + ks * 8), b, idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
-          else ptx::mma_bf16_ss(tmem_base + 384u, ptx::make_kmajor_sw128_desc(pt_addr + kT16) + (uint64_t)(2 * ks), b, idesc_acc,
-                                (it > 0 || ks > 0) ? 1u : 0u);
+          for (int ks = 0; ks < 4; ++ks) {     // dK += dS^T Q
+            const uint64_t b = ptx::make_mnmajor_sw128_desc(q_addr, kT8) + (uint64_t)(128 * ks);
+            if (kTS) ptx::mma_bf16_ts(tmem_base + 384u, tmem_base + (uint32_t)(128 + s * 64 + ks * 8), b, idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
+            else ptx::mma_bf16_ss(tmem_base + 384u, ptx::make_kmajor_sw128_desc(pt_addr + kT16) + (uint64_t)(2 * ks), b, idesc_acc,
+                                  (it > 0 || ks > 0) ? 1u : 0u);
+          }
+          ptx::tc_commit(bar(13 + s));     // P^T[s] / dS^T[s] may be rewritten
+          ptx::tc_commit(bar(4 + st));     // Q / dO slot may be refilled
         }
-        ptx::tc_commit(bar(13 + s));     // P^T[s] / dS^T[s] may be rewritten
-        ptx::tc_commit(bar(4 + st));     // Q / dO slot may be refilled
       }
-      ptx::tc_commit(bar(15));
+      if (ptx::elect_one()) {
+        ptx::tc_commit(bar(15));
+      }
     }
     __syncwarp();
   } else {
@@ -404,9 +412,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const int qtile = (int)(gridDim.x - 1 - blockIdx.x);  // heaviest (latest) query tiles first; pairs stay adjacent
   const int kvh = blockIdx.y, z = blockIdx.z;
   const uint32_t rank = ptx::cluster_ctarank();
-  const int q_len = p.seg_len[z];
+  const int q_len = ptx::warp_uniform(p.seg_len[z]);
   if ((qtile & ~1) * p.nq >= q_len) return;             // uniform across the cluster
-  const int seg0 = p.seg_start[z];
+  const int seg0 = ptx::warp_uniform(p.seg_start[z]);
   const int t0 = qtile * p.nq;
   const int row0 = seg0 + t0;
   const int n_valid = t0 >= q_len ? 0 : ((q_len - t0) < p.nq ? (q_len - t0) : p.nq);
@@ -433,6 +441,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   ptx::tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = ptx::warp_uniform(tmem_base);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -466,7 +475,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    {   // the whole warp, converged: one elected lane issues each tcgen05 instruction (ptx::elect_one)
       constexpr uint32_t idesc_kk = ptx::make_idesc_bf16_f32(128, 128);                 // S, dP: K-major x K-major
       constexpr uint32_t idesc_dq = ptx::make_idesc_bf16_f32(128, kD) | (1u << 16);     // dQ: B (= K) MN-major
       auto issue_s = [&](int j) {
@@ -477,15 +486,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         else ptx::mbar_wait(bar(7 + s), ph ^ 1u);                   // S[s] drained (step j - 2)
         ptx::tc_fence_after_sync();
         const uint32_t k_addr = kv_smem + (uint32_t)(s * kStageKV);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t b = ptx::make_kmajor_sw128_desc(k_addr + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
-          if (kQT) ptx::mma_bf16_ts(tmem_base, tmem_base + cQ + (uint32_t)(ks * 8), b, idesc_kk, ks > 0 ? 1u : 0u);
-          else ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 128),
-                                ptx::make_kmajor_sw128_desc(q_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)), b,
-                                idesc_kk, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t b = ptx::make_kmajor_sw128_desc(k_addr + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+            if (kQT) ptx::mma_bf16_ts(tmem_base, tmem_base + cQ + (uint32_t)(ks * 8), b, idesc_kk, ks > 0 ? 1u : 0u);
+            else ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 128),
+                                  ptx::make_kmajor_sw128_desc(q_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)), b,
+                                  idesc_kk, ks > 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(bar(kQT ? 5 : 5 + s));
         }
-        ptx::tc_commit(bar(kQT ? 5 : 5 + s));
       };
       auto issue_dp = [&](int j) {
         const int s = j & 1;
@@ -494,16 +505,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (!kTS) ptx::mbar_wait(bar(10), (uint32_t)((j & 1) ^ 1));        // dP drained (step j - 1)
         ptx::tc_fence_after_sync();
         const uint32_t v_addr = kv_smem + (uint32_t)(s * kStageKV + 2 * kT16);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t b = ptx::make_kmajor_sw128_desc(v_addr + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
-          if (kQT) ptx::mma_bf16_ts(tmem_base + cDP, tmem_base + cDO + (uint32_t)(ks * 8), b, idesc_kk, ks > 0 ? 1u : 0u);
-          else ptx::mma_bf16_ss(tmem_base + cDP,
-                                ptx::make_kmajor_sw128_desc(do_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)), b,
-                                idesc_kk, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t b = ptx::make_kmajor_sw128_desc(v_addr + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+            if (kQT) ptx::mma_bf16_ts(tmem_base + cDP, tmem_base + cDO + (uint32_t)(ks * 8), b, idesc_kk, ks > 0 ? 1u : 0u);
+            else ptx::mma_bf16_ss(tmem_base + cDP,
+                                  ptx::make_kmajor_sw128_desc(do_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)), b,
+                                  idesc_kk, ks > 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(bar(9));
+          ptx::tc_commit_multicast(bar(15 + s), 3);  // V slot consumed: tell BOTH producers
         }
-        ptx::tc_commit(bar(9));
-        ptx::tc_commit_multicast(bar(15 + s), 3);  // V slot consumed: tell BOTH producers
       };
       ptx::mbar_wait(bar(0), 0);
       issue_s(0);
@@ -517,18 +530,22 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         ptx::mbar_wait(bar(11), (uint32_t)(i & 1));              // dS of step i is ready
         ptx::tc_fence_after_sync();
         const uint32_t k_addr = kv_smem + (uint32_t)(s * kStageKV);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {           // dQ += dS K     (K read as stored: keys are the contraction rows)
-          const uint64_t b = ptx::make_mnmajor_sw128_desc(k_addr, kT16) + (uint64_t)(128 * ks);
-          if (kTS) ptx::mma_bf16_ts(tmem_base + cDQ, tmem_base + cDP + (uint32_t)(ks * 8), b, idesc_dq, (i > 0 || ks > 0) ? 1u : 0u);
-          else ptx::mma_bf16_ss(tmem_base + cDQ, ptx::make_kmajor_sw128_desc(ds_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)),
-                                b, idesc_dq, (i > 0 || ks > 0) ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks) {           // dQ += dS K     (K read as stored: keys are the contraction rows)
+            const uint64_t b = ptx::make_mnmajor_sw128_desc(k_addr, kT16) + (uint64_t)(128 * ks);
+            if (kTS) ptx::mma_bf16_ts(tmem_base + cDQ, tmem_base + cDP + (uint32_t)(ks * 8), b, idesc_dq, (i > 0 || ks > 0) ? 1u : 0u);
+            else ptx::mma_bf16_ss(tmem_base + cDQ, ptx::make_kmajor_sw128_desc(ds_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)),
+                                  b, idesc_dq, (i > 0 || ks > 0) ? 1u : 0u);
+          }
+          ptx::tc_commit(bar(12));                   // dS may be rewritten
+          ptx::tc_commit_multicast(bar(3 + s), 3);   // K slot consumed: tell BOTH producers
         }
-        ptx::tc_commit(bar(12));                   // dS may be rewritten
-        ptx::tc_commit_multicast(bar(3 + s), 3);   // K slot consumed: tell BOTH producers
         if (kTS && i + 1 < n_it) issue_dp(i + 1);  // dP of the next step goes where dS of this one was: after its dQ UMMAs
       }
-      ptx::tc_commit(bar(17));
+      if (ptx::elect_one()) {
+        ptx::tc_commit(bar(17));
+      }
     }
     __syncwarp();
   } else {
@@ -711,10 +728,10 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   float* meta = reinterpret_cast<float*>(smem_raw + (meta_smem - ptx::smem_u32(smem_raw)));
 
   const int jt = blockIdx.x, kvh = blockIdx.y, z = blockIdx.z;
-  const int q_len = p.seg_len[z];
+  const int q_len = ptx::warp_uniform(p.seg_len[z]);
   const int key0 = jt * 128;
   if (key0 >= q_len) return;                       // before any barrier / TMEM use
-  const int seg0 = p.seg_start[z];
+  const int seg0 = ptx::warp_uniform(p.seg_start[z]);
   const int nqa = p.nq;
   const int u_first = key0 / nqa;
   const int u_end = (q_len + nqa - 1) / nqa;
@@ -743,6 +760,7 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   ptx::tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = ptx::warp_uniform(tmem_base);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -775,7 +793,7 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    {   // the whole warp, converged: one elected lane issues each tcgen05 instruction (ptx::elect_one)
       constexpr uint32_t idesc_t = ptx::make_idesc_bf16_f32(128, 64);
       constexpr uint32_t idesc_acc = ptx::make_idesc_bf16_f32(128, kD) | (1u << 16);
       auto issue_sdp = [&](int it) {
@@ -785,19 +803,21 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         // them: UMMAs of one thread execute in issue order
         ptx::tc_fence_after_sync();
         const uint32_t q_addr = q_ring + (uint32_t)(st * kQSlot);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a = ptx::make_kmajor_sw128_desc(kv_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
-          const uint64_t b = ptx::make_kmajor_sw128_desc(q_addr + (uint32_t)((ks >> 2) * kT8)) + (uint64_t)(2 * (ks & 3));
-          ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 64), a, b, idesc_t, ks > 0 ? 1u : 0u);
-        }
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t a = ptx::make_kmajor_sw128_desc(kv_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+            const uint64_t b = ptx::make_kmajor_sw128_desc(q_addr + (uint32_t)((ks >> 2) * kT8)) + (uint64_t)(2 * (ks & 3));
+            ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 64), a, b, idesc_t, ks > 0 ? 1u : 0u);
+          }
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a = ptx::make_kmajor_sw128_desc(kv_smem + (uint32_t)(2 * kT16 + (ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
-          const uint64_t b = ptx::make_kmajor_sw128_desc(q_addr + (uint32_t)(2 * kT8 + (ks >> 2) * kT8)) + (uint64_t)(2 * (ks & 3));
-          ptx::mma_bf16_ss(tmem_base + (uint32_t)(128 + s * 64), a, b, idesc_t, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t a = ptx::make_kmajor_sw128_desc(kv_smem + (uint32_t)(2 * kT16 + (ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+            const uint64_t b = ptx::make_kmajor_sw128_desc(q_addr + (uint32_t)(2 * kT8 + (ks >> 2) * kT8)) + (uint64_t)(2 * (ks & 3));
+            ptx::mma_bf16_ss(tmem_base + (uint32_t)(128 + s * 64), a, b, idesc_t, ks > 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(bar(9 + s));
         }
-        ptx::tc_commit(bar(9 + s));
       };
       ptx::mbar_wait(bar(0), 0);
       issue_sdp(0);
@@ -807,21 +827,25 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         ptx::mbar_wait(bar(11 + s), (uint32_t)((it >> 1) & 1));         // P^T[s], dS^T[s] are in TMEM
         ptx::tc_fence_after_sync();
         const uint32_t q_addr = q_ring + (uint32_t)(st * kQSlot);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {     // dV += P^T dO      (contraction over the 64 query rows, 16 per k-step)
-          const uint64_t b = ptx::make_mnmajor_sw128_desc(q_addr + 2 * kT8, kT8) + (uint64_t)(128 * ks);
-          ptx::mma_bf16_ts(tmem_base + 256u, tmem_base + (uint32_t)(s * 64 + (ks >> 1) * 32 + (ks & 1) * 8), b, idesc_acc,
-                           (it > 0 || ks > 0) ? 1u : 0u);
-        }
+          for (int ks = 0; ks < 4; ++ks) {     // dV += P^T dO      (contraction over the 64 query rows, 16 per k-step)
+            const uint64_t b = ptx::make_mnmajor_sw128_desc(q_addr + 2 * kT8, kT8) + (uint64_t)(128 * ks);
+            ptx::mma_bf16_ts(tmem_base + 256u, tmem_base + (uint32_t)(s * 64 + (ks >> 1) * 32 + (ks & 1) * 8), b, idesc_acc,
+                             (it > 0 || ks > 0) ? 1u : 0u);
+          }
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {     // dK += dS^T Q
-          const uint64_t b = ptx::make_mnmajor_sw128_desc(q_addr, kT8) + (uint64_t)(128 * ks);
-          ptx::mma_bf16_ts(tmem_base + 384u, tmem_base + (uint32_t)(128 + s * 64 + (ks >> 1) * 32 + (ks & 1) * 8), b, idesc_acc,
-                           (it > 0 || ks > 0) ? 1u : 0u);
+          for (int ks = 0; ks < 4; ++ks) {     // dK += dS^T Q
+            const uint64_t b = ptx::make_mnmajor_sw128_desc(q_addr, kT8) + (uint64_t)(128 * ks);
+            ptx::mma_bf16_ts(tmem_base + 384u, tmem_base + (uint32_t)(128 + s * 64 + (ks >> 1) * 32 + (ks & 1) * 8), b, idesc_acc,
+                             (it > 0 || ks > 0) ? 1u : 0u);
+          }
+          ptx::tc_commit(bar(5 + st));     // Q / dO slot may be refilled
         }
-        ptx::tc_commit(bar(5 + st));     // Q / dO slot may be refilled
       }
-      ptx::tc_commit(bar(13));
+      if (ptx::elect_one()) {
+        ptx::tc_commit(bar(13));
+      }
     }
     __syncwarp();
   } else {
@@ -939,8 +963,11 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   }
 }
 
-constexpr int kSmemDq4 = 1024 + 4 * kT16 + 2 * kStageKV + 8 * 20 + 16;
+constexpr int kKSlots4 = 3;          // K of step i serves S(i) (issued a step early) and dQ(i) (issued last): two slots leave no slack
+constexpr int kSmemDq4 = 1024 + 4 * kT16 + kKSlots4 * 2 * kT16 + 2 * 2 * kT16 + 8 * 24 + 16;
+static_assert(kSmemDq4 <= 232448, "dq4 kernel exceeds the 227 KB shared-memory limit");
 
+template <bool kTimed>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsB4, 1)
 attn_bwd_dq4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                     const __grid_constant__ CUtensorMap tm_kv, BwdParams p) {
@@ -948,10 +975,11 @@ attn_bwd_dq4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_smem = base;                         // Q lo | Q hi
   const uint32_t do_smem = base + 2 * kT16;             // dO lo | dO hi
-  const uint32_t kv_smem = base + 4 * kT16;             // 2 stages x (K lo | K hi | V lo | V hi)
-  const uint32_t bar_base = kv_smem + 2 * kStageKV;
+  const uint32_t k_smem = base + 4 * kT16;              // 3 slots x (K lo | K hi)
+  const uint32_t v_smem = k_smem + kKSlots4 * 2 * kT16; // 2 slots x (V lo | V hi)
+  const uint32_t bar_base = v_smem + 2 * 2 * kT16;
   auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
-  // 0 q_full | 1,2 k_full | 3,4 k_empty | 5,6 s_full | 7,8 s_empty (16 warps) | 9 dp_full | 11 ds_full (16 warps) |
+  // 0 q_full | 1..3 k_full | 4..6 k_empty | 7,8 s_full | 9,10 s_empty (16 warps) | 11 dp_full | 12 ds_full (16 warps) |
   // 13,14 v_full | 15,16 v_empty | 17 dq_done
   const uint32_t tmem_slot = bar(18);
   constexpr uint32_t cDP = 256u, cDQ = 384u;            // TMEM columns: S[2] 0,128 | dP 256 | dQ 384
@@ -959,9 +987,9 @@ attn_bwd_dq4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const int qtile = (int)(gridDim.x - 1 - blockIdx.x);
   const int kvh = blockIdx.y, z = blockIdx.z;
   const uint32_t rank = ptx::cluster_ctarank();
-  const int q_len = p.seg_len[z];
+  const int q_len = ptx::warp_uniform(p.seg_len[z]);
   if ((qtile & ~1) * p.nq >= q_len) return;             // uniform across the cluster
-  const int seg0 = p.seg_start[z];
+  const int seg0 = ptx::warp_uniform(p.seg_start[z]);
   const int t0 = qtile * p.nq;
   const int row0 = seg0 + t0;
   const int n_valid = t0 >= q_len ? 0 : ((q_len - t0) < p.nq ? (q_len - t0) : p.nq);
@@ -974,8 +1002,8 @@ attn_bwd_dq4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < 18; ++i) {
       int cnt = 1;
-      if (i == 3 || i == 4 || i == 15 || i == 16) cnt = 2;
-      if (i == 7 || i == 8 || i == 11) cnt = 16;
+      if ((i >= 4 && i <= 6) || i == 15 || i == 16) cnt = 2;
+      if (i == 9 || i == 10 || i == 12) cnt = 16;
       ptx::mbar_init(bar(i), cnt);
     }
     ptx::fence_barrier_init();
@@ -993,6 +1021,7 @@ attn_bwd_dq4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   ptx::tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = ptx::warp_uniform(tmem_base);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -1003,80 +1032,102 @@ attn_bwd_dq4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       ptx::tma_load_3d(do_smem, &tm_do, 0, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
       ptx::tma_load_3d(do_smem + kT16, &tm_do, 64, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
       auto load_page = [&](int it, int kv) {
-        const int s = it & 1;
-        const uint32_t ph = (uint32_t)((it >> 1) & 1);
-        const uint32_t full = bar((kv ? 13 : 1) + s), empty = bar((kv ? 15 : 3) + s);
+        const int s = kv ? (it & 1) : (it % kKSlots4);
+        const uint32_t ph = (uint32_t)((kv ? (it >> 1) : (it / kKSlots4)) & 1);
+        const uint32_t full = bar((kv ? 13 : 1) + s), empty = bar((kv ? 15 : 4) + s);
         ptx::mbar_wait(empty, ph ^ 1u);
         ptx::mbar_arrive_expect_tx(full, (uint32_t)(2 * kT16));
         int pg = 2 * it + (int)rank;
         if (pg > last_page) pg = last_page;            // tail: re-read the last page, its keys are causally masked
         const int row = seg0 + pg * 64;
         const int c0 = (kv ? p.col_v : p.col_k) + kvh * kD;
-        const uint32_t dst = kv_smem + (uint32_t)(s * kStageKV + kv * 2 * kT16) + (uint32_t)(rank * kT8);
+        const uint32_t dst = (kv ? v_smem : k_smem) + (uint32_t)(s * 2 * kT16) + (uint32_t)(rank * kT8);
         ptx::tma_load_2d_multicast(dst, &tm_kv, c0, row, full, 3, ptx::kEvictLast);
         ptx::tma_load_2d_multicast(dst + kT16, &tm_kv, c0 + 64, row, full, 3, ptx::kEvictLast);
       };
+      load_page(0, 0);
       for (int it = 0; it < n_it; ++it) {
-        load_page(it, 0);
+        if (it + 1 < n_it) load_page(it + 1, 0);     // K runs one step ahead of V: S(i+1) is issued during step i
         load_page(it, 1);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: S(i+1) | dQ(i) | dP(i+1), in that order =====
-    if (lane == 0) {
+    {   // the whole warp, converged: one elected lane issues each tcgen05 instruction (ptx::elect_one)
       constexpr uint32_t idesc_kk = ptx::make_idesc_bf16_f32(128, 128);
       constexpr uint32_t idesc_dq = ptx::make_idesc_bf16_f32(128, kD) | (1u << 16);
+      long long w_k = 0, w_sd = 0, w_ds = 0, w_v = 0;
+      const bool timed = kTimed && p.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      const long long w0 = clock64();
       auto issue_s = [&](int j) {
-        const int s = j & 1;
+        const int s = j & 1, ks_ = j % kKSlots4;
         const uint32_t ph = (uint32_t)((j >> 1) & 1);
-        ptx::mbar_wait(bar(1 + s), ph);            // K of step j landed
-        ptx::mbar_wait(bar(7 + s), ph ^ 1u);       // S[s] drained (step j - 2)
+        const long long c0 = clock64();
+        ptx::mbar_wait(bar(1 + ks_), (uint32_t)((j / kKSlots4) & 1));   // K of step j landed
+        const long long c1 = clock64();
+        ptx::mbar_wait(bar(9 + s), ph ^ 1u);       // S[s] drained (step j - 2)
+        if (kTimed) { w_k += c1 - c0; w_sd += clock64() - c1; }
         ptx::tc_fence_after_sync();
-        const uint32_t k_addr = kv_smem + (uint32_t)(s * kStageKV);
+        const uint32_t k_addr = k_smem + (uint32_t)(ks_ * 2 * kT16);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t b = ptx::make_kmajor_sw128_desc(k_addr + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
-          ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 128),
-                           ptx::make_kmajor_sw128_desc(q_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)), b,
-                           idesc_kk, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t b = ptx::make_kmajor_sw128_desc(k_addr + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+            ptx::mma_bf16_ss(tmem_base + (uint32_t)(s * 128),
+                             ptx::make_kmajor_sw128_desc(q_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)), b,
+                             idesc_kk, ks > 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(bar(7 + s));
         }
-        ptx::tc_commit(bar(5 + s));
       };
       auto issue_dp = [&](int j) {
         const int s = j & 1;
+        const long long c0 = clock64();
         ptx::mbar_wait(bar(13 + s), (uint32_t)((j >> 1) & 1));   // V of step j landed
+        if (kTimed) w_v += clock64() - c0;
         // dP's columns hold dS of step j - 1 until its dQ UMMAs -- issued BEFORE this call -- have read it (in order)
         ptx::tc_fence_after_sync();
-        const uint32_t v_addr = kv_smem + (uint32_t)(s * kStageKV + 2 * kT16);
+        const uint32_t v_addr = v_smem + (uint32_t)(s * 2 * kT16);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t b = ptx::make_kmajor_sw128_desc(v_addr + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
-          ptx::mma_bf16_ss(tmem_base + cDP,
-                           ptx::make_kmajor_sw128_desc(do_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)), b,
-                           idesc_kk, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t b = ptx::make_kmajor_sw128_desc(v_addr + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+            ptx::mma_bf16_ss(tmem_base + cDP,
+                             ptx::make_kmajor_sw128_desc(do_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3)), b,
+                             idesc_kk, ks > 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(bar(11));
+          ptx::tc_commit_multicast(bar(15 + s), 3);  // V slot consumed: tell BOTH producers
         }
-        ptx::tc_commit(bar(9));
-        ptx::tc_commit_multicast(bar(15 + s), 3);  // V slot consumed: tell BOTH producers
       };
       ptx::mbar_wait(bar(0), 0);
       issue_s(0);
       issue_dp(0);
       for (int i = 0; i < n_it; ++i) {
         if (i + 1 < n_it) issue_s(i + 1);
-        const int s = i & 1;
-        ptx::mbar_wait(bar(11), (uint32_t)(i & 1));              // dS of step i is in TMEM
+        const int ks_ = i % kKSlots4;
+        const long long c0 = clock64();
+        ptx::mbar_wait(bar(12), (uint32_t)(i & 1));              // dS of step i is in TMEM
+        if (kTimed) w_ds += clock64() - c0;
         ptx::tc_fence_after_sync();
-        const uint32_t k_addr = kv_smem + (uint32_t)(s * kStageKV);
+        const uint32_t k_addr = k_smem + (uint32_t)(ks_ * 2 * kT16);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {           // dQ += dS K     (K read as stored: keys are the contraction rows)
-          const uint64_t b = ptx::make_mnmajor_sw128_desc(k_addr, kT16) + (uint64_t)(128 * ks);
-          ptx::mma_bf16_ts(tmem_base + cDQ, tmem_base + cDP + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8), b, idesc_dq,
-                           (i > 0 || ks > 0) ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks) {           // dQ += dS K     (K read as stored: keys are the contraction rows)
+            const uint64_t b = ptx::make_mnmajor_sw128_desc(k_addr, kT16) + (uint64_t)(128 * ks);
+            ptx::mma_bf16_ts(tmem_base + cDQ, tmem_base + cDP + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8), b, idesc_dq,
+                             (i > 0 || ks > 0) ? 1u : 0u);
+          }
+          ptx::tc_commit_multicast(bar(4 + ks_), 3);   // K slot consumed: tell BOTH producers
         }
-        ptx::tc_commit_multicast(bar(3 + s), 3);   // K slot consumed: tell BOTH producers
         if (i + 1 < n_it) issue_dp(i + 1);
       }
-      ptx::tc_commit(bar(17));
+      if (ptx::elect_one()) {
+        ptx::tc_commit(bar(17));
+      }
+      if (timed && lane == 0) {
+        p.timing[8] = w_k; p.timing[9] = w_sd; p.timing[10] = w_ds; p.timing[11] = w_v; p.timing[12] = clock64() - w0; p.timing[13] = n_it;
+      }
     }
     __syncwarp();
   } else {
@@ -1092,16 +1143,20 @@ attn_bwd_dq4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const float lse_row = valid ? __ldg(p.lse + stat) : INFINITY;   // padding rows: P = 0
     const float delta_row = valid ? __ldg(p.delta + stat) : 0.f;
 
+    const bool timed = kTimed && p.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
+    long long tph[5] = {0, 0, 0, 0, 0};
     for (int i = 0; i < n_it; ++i) {
       const int s = i & 1;
-      ptx::mbar_wait(bar(5 + s), (uint32_t)((i >> 1) & 1));
+      const long long c0 = clock64();
+      ptx::mbar_wait(bar(7 + s), (uint32_t)((i >> 1) & 1));
       ptx::tc_fence_after_sync();
+      const long long c1 = clock64();
       uint32_t v0[32];
       ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(s * 128 + k * 32), v0);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar(7 + s));           // this warp's part of S[s] is in registers
+      if (lane == 0) ptx::mbar_arrive(bar(9 + s));           // this warp's part of S[s] is in registers
       // P of this step: runs while the tensor core is still busy with dQ(i-1) and dP(i)
       float sv[32];
 #pragma unroll
@@ -1112,8 +1167,10 @@ attn_bwd_dq4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         for (int e = 0; e < 32; ++e)
           if (key0 + e > qpos) sv[e] = 0.f;
       }
-      ptx::mbar_wait(bar(9), (uint32_t)(i & 1));             // dP of step i
+      const long long c2 = clock64();
+      ptx::mbar_wait(bar(11), (uint32_t)(i & 1));            // dP of step i
       ptx::tc_fence_after_sync();
+      const long long c3 = clock64();
       uint32_t d0[32];
       ptx::tmem_ld_32x32b_x32(lane_addr + cDP + (uint32_t)(k * 32), d0);
       ptx::tmem_ld_wait();
@@ -1126,7 +1183,15 @@ attn_bwd_dq4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       ptx::tmem_st_wait();
       ptx::tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar(11));              // -> dQ += dS K
+      if (lane == 0) ptx::mbar_arrive(bar(12));              // -> dQ += dS K
+      if (kTimed) {
+        const long long c4 = clock64();
+        tph[0] += c1 - c0; tph[1] += c2 - c1; tph[2] += c3 - c2; tph[3] += c4 - c3;
+      }
+    }
+    if (timed) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) p.timing[e] = tph[e];
     }
 
     // ---- epilogue: 32 head-dim columns of this row's dQ ----
@@ -1163,7 +1228,16 @@ attn_bwd_dq4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
 using namespace prl;
 
-namespace prl { namespace { int g_bwd_generation = [] { const char* e = getenv("PRL_ATTN_BWD"); return (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 2; }(); } }
+namespace prl { namespace { int g_bwd_generation = [] { const char* e = getenv("PRL_ATTN_BWD"); return (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 4; }(); } }
+
+namespace prl { namespace { long long* g_bwd_timing = nullptr; } }
+// measurement only: per-phase cycle sums of CTA (0,0,0) of the generation-4 dQ kernel.  [0..3] one softmax warp: wait S |
+// tcgen05.ld + exp2 | wait dP | tcgen05.ld + dS + tcgen05.st + arrive; [8..11] MMA warp waiting for K | S drained | dS | V,
+// [12] MMA warp total, [13] steps.  NULL switches it off.
+extern "C" int prl_attn_debug_bwd_timing(int64_t* out16_device) {
+  prl::g_bwd_timing = (long long*)out16_device;
+  return PRL_OK;
+}
 
 extern "C" int prl_attn_set_bwd_generation(int32_t gen) {
   PRL_CHECK_ARG(gen >= 1 && gen <= 4, "prl_attn_set_bwd_generation: 1 (P / dS operands through shared memory), 2 (through TMEM), "
@@ -1204,6 +1278,7 @@ extern "C" int prl_attn_varlen_bwd(const void* qkv, int64_t qkv_stride, int32_t 
   p.scale_log2 = sm_scale * 1.4426950408889634f; p.sm_scale = sm_scale;
   p.q_base = (const __nv_bfloat16*)qkv; p.q_stride = qkv_stride;
   p.do_base = (const __nv_bfloat16*)d_out_bf16; p.do_stride = (int64_t)n_q * kD;
+  p.timing = g_bwd_timing;
   CUtensorMap tkv, tq, tdo;
   int rc = make_tmap_2d_bf16(&tkv, qkv, (uint64_t)width, (uint64_t)T, (uint64_t)qkv_stride * 2, 64, 64);
   if (rc) return rc;
@@ -1241,8 +1316,14 @@ extern "C" int prl_attn_varlen_bwd(const void* qkv, int64_t qkv_stride, int32_t 
     dim3 grid((unsigned)(((max_seg_len + p.nq - 1) / p.nq + 1) & ~1), (unsigned)n_kv, (unsigned)n_seg);
     if (g_bwd_generation == 4) {
       static SmemAttr attr4 = {};
-      PRL_CUDA(ensure_smem(attn_bwd_dq4_kernel, kSmemDq4, attr4));
-      attn_bwd_dq4_kernel<<<grid, kThreadsB4, (size_t)kSmemDq4, stream>>>(tq, tdo, tkv, p);
+      if (g_bwd_timing != nullptr) {
+        static SmemAttr attr4t = {};
+        PRL_CUDA(ensure_smem(attn_bwd_dq4_kernel<true>, kSmemDq4, attr4t));
+        attn_bwd_dq4_kernel<true><<<grid, kThreadsB4, (size_t)kSmemDq4, stream>>>(tq, tdo, tkv, p);
+      } else {
+        PRL_CUDA(ensure_smem(attn_bwd_dq4_kernel<false>, kSmemDq4, attr4));
+        attn_bwd_dq4_kernel<false><<<grid, kThreadsB4, (size_t)kSmemDq4, stream>>>(tq, tdo, tkv, p);
+      }
     } else if (g_bwd_generation == 1) {
       PRL_CUDA(ensure_smem(attn_bwd_dq_kernel<1>, kSmemDq, attr));
       attn_bwd_dq_kernel<1><<<grid, kThreadsB, (size_t)kSmemDq, stream>>>(tq, tdo, tkv, p);
@@ -1304,4 +1385,134 @@ extern "C" int prl_debug_tmem_read_bench(int32_t iters, int32_t warps, int64_t* 
                                                                                             (long long*)out3_device);
   PRL_LAUNCH_CHECK();
   return PRL_OK;
+}
+
+// ---- measurement helper: tcgen05.mma throughput per operand configuration, and the softmax <-> tensor-core hand-off ------
+// One converged warp issues batches of 8 UMMAs (K = 128) under ONE lane election, the instruction stream between two
+// UMMAs is empty (the mode is a template parameter): what is measured is the tensor core, not the issuing thread.
+//   0  SS  A, B K-major      128 x 128      1  SS  128 x 64        2  SS  128 x 256       3  SS  B MN-major 128 x 128
+//   4  TS (A in TMEM) B K-major 128 x 128   5  TS  B MN-major 128 x 128   6  TS B K-major 128 x 256   7  TS 128 x 64
+//   8  SS 128 x 128, two accumulators interleaved       9  SS 128 x 128 batch, then TS MN-major batch (the forward's step)
+//   10 hand-off round trip: 1 UMMA -> commit -> 4 warps tcgen05.ld x32 + tcgen05.st x16 -> arrive -> next UMMA
+// out[0] = cycles, out[1] = UMMAs issued.
+namespace prl { namespace {
+template <int kMode>
+__global__ void __launch_bounds__(192, 1) mma_bench_kernel(int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_smem = base, b_smem = base + 2 * kT16;          // A: two [128 x 128 B] tiles, B: four
+  const uint32_t bar0 = base + 6 * kT16, bar1 = bar0 + 8, slot = bar0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t i = threadIdx.x; i < (uint32_t)(6 * kT16) / 16; i += blockDim.x) sts_v4(base + i * 16, 0u, 0u, 0u, 0u);
+  ptx::fence_proxy_async();
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar0, 1);
+    ptx::mbar_init(bar1, 4);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) { ptx::tmem_alloc(slot, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(slot));
+  if (warp == 1) {
+    constexpr uint32_t id128 = ptx::make_idesc_bf16_f32(128, 128), id64 = ptx::make_idesc_bf16_f32(128, 64);
+    constexpr uint32_t id256 = ptx::make_idesc_bf16_f32(128, 256), id128mn = id128 | (1u << 16);
+    const uint32_t tb = ptx::warp_uniform(tmem_base);
+    const long long t0 = clock64();
+    long long n = 0;
+    for (int it = 0; it < iters; ++it) {
+      if (kMode == 10) {
+        if (ptx::elect_one()) {
+          ptx::mma_bf16_ss(tb, ptx::make_kmajor_sw128_desc(a_smem), ptx::make_kmajor_sw128_desc(b_smem), id128, 0u);
+          ptx::tc_commit(bar0);
+        }
+        ptx::mbar_wait(bar1, (uint32_t)(it & 1));
+        ptx::tc_fence_after_sync();
+        ++n;
+        continue;
+      }
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ak = ptx::make_kmajor_sw128_desc(a_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+          const uint64_t bk = ptx::make_kmajor_sw128_desc(b_smem + (uint32_t)((ks >> 2) * kT16)) + (uint64_t)(2 * (ks & 3));
+          const uint64_t bmn = ptx::make_mnmajor_sw128_desc(b_smem, kT16) + (uint64_t)(128 * ks);
+          const uint32_t at = tb + 256u + (uint32_t)(ks * 8);
+          if (kMode == 0 || kMode == 9) ptx::mma_bf16_ss(tb, ak, bk, id128, ks > 0);
+          if (kMode == 1) ptx::mma_bf16_ss(tb, ak, bk, id64, ks > 0);
+          if (kMode == 2) ptx::mma_bf16_ss(tb, ak, bk, id256, ks > 0);
+          if (kMode == 3) ptx::mma_bf16_ss(tb, ak, bmn, id128mn, ks > 0);
+          if (kMode == 4) ptx::mma_bf16_ts(tb, at, bk, id128, ks > 0);
+          if (kMode == 5) ptx::mma_bf16_ts(tb, at, bmn, id128mn, ks > 0);
+          if (kMode == 6) ptx::mma_bf16_ts(tb, at, bk, id256, ks > 0);
+          if (kMode == 7) ptx::mma_bf16_ts(tb, at, bk, id64, ks > 0);
+          if (kMode == 8) ptx::mma_bf16_ss(tb + (uint32_t)((ks & 1) * 128), ak, bk, id128, ks > 1);
+        }
+        if (kMode == 9) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            ptx::mma_bf16_ts(tb + 128u, tb + 256u + (uint32_t)(ks * 8), ptx::make_mnmajor_sw128_desc(b_smem, kT16) + (uint64_t)(128 * ks),
+                             id128mn, ks > 0);
+        }
+      }
+      n += kMode == 9 ? 16 : 8;
+    }
+    if (kMode != 10) {
+      if (ptx::elect_one()) ptx::tc_commit(bar0);
+      ptx::mbar_wait(bar0, 0);
+    }
+    const long long t1 = clock64();
+    if (blockIdx.x == 0 && lane == 0) { out[0] = t1 - t0; out[1] = n; }
+  } else if (warp >= 2 && kMode == 10) {
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int it = 0; it < iters; ++it) {
+      ptx::mbar_wait(bar0, (uint32_t)(it & 1));
+      ptx::tc_fence_after_sync();
+      uint32_t v[32], w[16];
+      ptx::tmem_ld_32x32b_x32(lane_addr, v);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) w[e] = v[2 * e] ^ v[2 * e + 1];
+      ptx::tmem_st_32x32b_x16(lane_addr + 256u, w);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar1);
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after_sync(); ptx::tmem_dealloc(tmem_base, 512); }
+}
+
+template <int kMode>
+int launch_mma_bench(int iters, long long* out, cudaStream_t stream) {
+  const int smem = 6 * kT16 + 1024 + 64;
+  static SmemAttr attr = {};
+  PRL_CUDA(ensure_smem(mma_bench_kernel<kMode>, smem, attr));
+  mma_bench_kernel<kMode><<<(unsigned)num_sms(), 192, (size_t)smem, stream>>>(iters, out);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+} }
+
+extern "C" int prl_debug_mma_bench(int32_t mode, int32_t iters, int64_t* out2_device, prl_stream_t stream_) {
+  PRL_CHECK_ARG(out2_device && iters >= 1 && mode >= 0 && mode <= 10, "prl_debug_mma_bench: bad argument");
+  long long* out = (long long*)out2_device;
+  cudaStream_t st = (cudaStream_t)stream_;
+  switch (mode) {
+    case 0: return prl::launch_mma_bench<0>(iters, out, st);
+    case 1: return prl::launch_mma_bench<1>(iters, out, st);
+    case 2: return prl::launch_mma_bench<2>(iters, out, st);
+    case 3: return prl::launch_mma_bench<3>(iters, out, st);
+    case 4: return prl::launch_mma_bench<4>(iters, out, st);
+    case 5: return prl::launch_mma_bench<5>(iters, out, st);
+    case 6: return prl::launch_mma_bench<6>(iters, out, st);
+    case 7: return prl::launch_mma_bench<7>(iters, out, st);
+    case 8: return prl::launch_mma_bench<8>(iters, out, st);
+    case 9: return prl::launch_mma_bench<9>(iters, out, st);
+    default: return prl::launch_mma_bench<10>(iters, out, st);
+  }
 }

@@ -125,6 +125,24 @@ __device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_m
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(cta_mask) : "memory");
 }
+// One lane of a CONVERGED warp.  tcgen05.mma / commit take their operands from uniform registers: issued from inside an
+// `if (lane == 0)` region the compiler cannot prove the operands warp-uniform and wraps every UMMA in a
+// R2UR + ELECT "waterfall" loop (~180 cycles per instruction, measured with prl_debug_mma_bench) -- more than the 64 cycles
+// a 128 x 128 x 16 UMMA occupies the tensor core.  The MMA warp therefore runs its whole loop converged, computes the
+// descriptors on all lanes (uniform values), and elects one lane around each instruction only.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// a value every lane holds, marked warp-uniform for the compiler
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ int warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate; issued by ONE thread
 __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -288,6 +306,20 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
 //   [15] A major (0 = K)  [16] B major (0 = K)  [17,23) N >> 3   [24,29) M >> 4
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// warp-converged forms: every lane of the MMA warp calls them with warp-uniform operands, one elected lane issues
+__device__ __forceinline__ void mma_bf16_ss_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (elect_one()) mma_bf16_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+__device__ __forceinline__ void mma_bf16_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (elect_one()) mma_bf16_ts(d_tmem, a_tmem, b_desc, idesc, accumulate);
+}
+__device__ __forceinline__ void tc_commit_w(uint32_t bar) {
+  if (elect_one()) tc_commit(bar);
+}
+__device__ __forceinline__ void tc_commit_multicast_w(uint32_t bar, uint16_t cta_mask) {
+  if (elect_one()) tc_commit_multicast(bar, cta_mask);
 }
 
 }  // namespace ptx

@@ -53,7 +53,7 @@ def _reference(qkv, d_out, bounds, n_q, n_kv):
 
 def _run(dev, n_q, n_kv, lens, seed=0, pad_cols=0, fwd_gen=2, bwd_gen=None):
     """fwd_gen / bwd_gen: 1 = operands through shared memory, 2 = P / dS handed to the tensor core through TMEM (default);
-    fwd_gen 3 = 2 with two threads per row (16 softmax warps); bwd_gen 3 = 2 + Q / dO resident in TMEM, 4 = 16 decoupled softmax warps"""
+    bwd_gen 3 = 2 + Q / dO resident in TMEM, 4 = 16 decoupled softmax warps"""
     from pipelinerl_b200 import _lib
     o = _ops()
     bwd_gen = fwd_gen if bwd_gen is None else bwd_gen
@@ -92,7 +92,7 @@ def _run(dev, n_q, n_kv, lens, seed=0, pad_cols=0, fwd_gen=2, bwd_gen=None):
         scale = max(want_d[:, a:b].abs().max().item(), 1e-3)      # a single-token segment has dq = dk = 0 exactly
         res[name] = (dqkv[:, a:b].float() - want_d[:, a:b]).abs().max().item() / scale
     _lib.check(o.lib.prl_attn_set_fwd_generation(2))
-    _lib.check(o.lib.prl_attn_set_bwd_generation(2))
+    _lib.check(o.lib.prl_attn_set_bwd_generation(4))
     print(f"[attn_train fwd gen{fwd_gen} bwd gen{bwd_gen}] n_q={n_q} n_kv={n_kv} lens={lens if len(lens) < 8 else str(lens[:6]) + '...'}: " +
           " ".join(f"{k}={v:.2e}" for k, v in res.items()))
     assert res["out"] <= 2 ** -7, res
@@ -114,7 +114,7 @@ def _run(dev, n_q, n_kv, lens, seed=0, pad_cols=0, fwd_gen=2, bwd_gen=None):
     (16, 1, [96, 33]),
     (28, 4, [511, 1, 700]),
 ])
-@pytest.mark.parametrize("fwd_gen,bwd_gen", [(1, 1), (2, 2), (2, 3), (2, 4), (3, 4)])
+@pytest.mark.parametrize("fwd_gen,bwd_gen", [(1, 1), (2, 2), (2, 3), (2, 4)])
 def test_varlen_attention_small(cuda_device, n_q, n_kv, lens, fwd_gen, bwd_gen):
     _run(cuda_device, n_q, n_kv, lens, seed=len(lens) * 131 + n_q, fwd_gen=fwd_gen, bwd_gen=bwd_gen)
 
@@ -131,8 +131,7 @@ def test_varlen_attention_qwen7b_heads_medium(cuda_device, lens):
 @pytest.mark.parametrize("lens,fwd_gen,bwd_gen", [([16384], 2, 2), ([8192, 8192], 2, 2), ([5000, 11000, 384], 2, 2),
                                                   ([16384], 1, 1), ([16384], 2, 1), ([16384], 1, 2), ([16384], 2, 3),
                                                   ([5000, 11000, 384], 2, 3), ([16384], 2, 4), ([8192, 8192], 2, 4),
-                                                  ([5000, 11000, 384], 2, 4), ([16384], 3, 4), ([8192, 8192], 3, 2),
-                                                  ([5000, 11000, 384], 3, 4)])
+                                                  ([5000, 11000, 384], 2, 4)])
 def test_varlen_attention_qwen7b_heads_16k(cuda_device, lens, fwd_gen, bwd_gen):
     """the trainer's micro-batch size (16 384 packed tokens) at Qwen2.5-7B's 28 / 4 heads"""
     _run(cuda_device, 28, 4, lens, seed=5, fwd_gen=fwd_gen, bwd_gen=bwd_gen)
