@@ -428,6 +428,23 @@ int prl_attn_varlen_bwd(const void* qkv_bf16, int64_t qkv_stride, int32_t T, con
                         int32_t head_dim, float sm_scale, const void* out_bf16, const void* d_out_bf16,
                         const float* lse, void* dqkv_bf16, int64_t dqkv_stride, void* workspace,
                         size_t workspace_bytes, prl_stream_t stream);
+/* Sequence-parallel forms (the reference shards a packed row over `seq_parallel` ranks and runs ring attention:
+ * finetune_loop.py:507-517,757-759, finetune/types.py:145-180).  The queries are the LOCAL slice q[Tq, q_stride] (query heads
+ * in the first n_q * 128 columns -- the local qkv matrix qualifies), the keys / values the all-gathered
+ * kv[Tkv, kv_stride] = [k heads | v heads].  Local segment z = q rows [seg_q_start[z], + seg_q_len[z]); its first query
+ * sits at position seg_pos0[z] of its sequence, whose first key is kv row seg_kv_start[z].  The backward writes the local
+ * dq[Tq, dq_stride] and THIS RANK'S contribution dkv[Tkv, dkv_stride] = [dK | dV] to every key row (zero where no local
+ * query attends); the caller reduce-scatters dkv over the group. */
+int prl_attn_varlen_fwd_kv(const void* q_bf16, int64_t q_stride, int32_t Tq, const void* kv_bf16, int64_t kv_stride,
+                           int32_t Tkv, const int32_t* seg_q_start, const int32_t* seg_q_len, const int32_t* seg_pos0,
+                           const int32_t* seg_kv_start, int32_t n_seg, int32_t max_q_len, int32_t n_q, int32_t n_kv,
+                           int32_t head_dim, float sm_scale, void* out_bf16, float* lse, prl_stream_t stream);
+int prl_attn_varlen_bwd_kv(const void* q_bf16, int64_t q_stride, int32_t Tq, const void* kv_bf16, int64_t kv_stride,
+                           int32_t Tkv, const int32_t* seg_q_start, const int32_t* seg_q_len, const int32_t* seg_pos0,
+                           const int32_t* seg_kv_start, int32_t n_seg, int32_t max_q_len, int32_t max_kv_len,
+                           int32_t n_q, int32_t n_kv, int32_t head_dim, float sm_scale, const void* out_bf16,
+                           const void* d_out_bf16, const float* lse, void* dq_bf16, int64_t dq_stride, void* dkv_bf16,
+                           int64_t dkv_stride, void* workspace, size_t workspace_bytes, prl_stream_t stream);
 /* Measurement helper (tools/attn_bench.py --tmem): cycles for `warps` warps of every SM to read iters x 4 KB out of
  * TMEM with tcgen05.ld.32x32b.x32; out3 = {cycles, bytes per SM, -}. */
 int prl_debug_tmem_read_bench(int32_t iters, int32_t warps, int64_t* out3_device, prl_stream_t stream);

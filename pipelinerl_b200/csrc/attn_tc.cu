@@ -36,6 +36,8 @@ struct TcPrefillParams {
   const int32_t* seq_q_len;
   const int32_t* seq_pos0;
   const int32_t* seq_slot;
+  const int32_t* seq_kv_start;   // kContig only, may be NULL: row of the sequence's FIRST key in the K / V matrix when the queries
+                                 // are a slice of the sequence (sequence-parallel learner; seq_pos0 = position of the first query)
   int max_blocks, n_q, n_kv, R, nq;
   int64_t n_pages;
   int layer;
@@ -50,6 +52,11 @@ struct TcPrefillParams {
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float y;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
   return y;
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -362,7 +369,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const int kvh = blockIdx.y, z = blockIdx.z;
   const uint32_t rank = ptx::cluster_ctarank();
   const int q_len = ptx::warp_uniform(p.seq_q_len[z]);
-  const int pos0 = kContig ? 0 : ptx::warp_uniform(p.seq_pos0[z]);
+  const int pos0 = (kContig && p.seq_pos0 == nullptr) ? 0 : ptx::warp_uniform(p.seq_pos0[z]);
   if ((qtile & ~1) * p.nq >= q_len) return;              // uniform across the CLUSTER, before any barrier / TMEM use
   const int t0 = qtile * p.nq;
   const int row0 = ptx::warp_uniform(p.seq_q_start[z]) + t0;
@@ -399,7 +406,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       ptx::tma_load_3d(q_smem, &tm_q, 0, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
       ptx::tma_load_3d(q_smem + kTile16K, &tm_q, 64, kvh * p.R, row0, bar(0), ptx::kEvictFirst);
       const int32_t* bt = kContig ? nullptr : p.block_table + (int64_t)p.seq_slot[z] * p.max_blocks;
-      const int seq_row0 = p.seq_q_start[z];
+      const int seq_row0 = (kContig && p.seq_kv_start != nullptr) ? p.seq_kv_start[z] : p.seq_q_start[z];
       auto load_page = [&](int it, int kv, uint32_t full_bar, uint32_t empty_bar) {
         const int s = it % kSt;
         const uint32_t ph = (uint32_t)((it / kSt) & 1);
@@ -518,11 +525,11 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         for (int e = 0; e < 128; ++e)
           if (key0 + e > qpos) sv[e] = -INFINITY;
       }
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains: this warp is alone on its
-#pragma unroll                                                       // scheduler for most of the phase, latency is exposed
-      for (int e = 0; e < 128; e += 4) {
-        mx4[0] = fmaxf(mx4[0], sv[e]); mx4[1] = fmaxf(mx4[1], sv[e + 1]);
-        mx4[2] = fmaxf(mx4[2], sv[e + 2]); mx4[3] = fmaxf(mx4[3], sv[e + 3]);
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains of 3-input maxima (FMNMX3):
+#pragma unroll                                                       // 64 instructions for the 128 scores of a row
+      for (int e = 0; e < 128; e += 8) {
+        mx4[0] = max3(mx4[0], sv[e], sv[e + 1]); mx4[1] = max3(mx4[1], sv[e + 2], sv[e + 3]);
+        mx4[2] = max3(mx4[2], sv[e + 4], sv[e + 5]); mx4[3] = max3(mx4[3], sv[e + 6], sv[e + 7]);
       }
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = mx * p.scale_log2;                // scale > 0: max commutes with the scaling
@@ -530,9 +537,12 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (j == 0) {
         m_ref = (m_new == -INFINITY) ? 0.f : m_new;
       } else {
-        ptx::mbar_wait(bar(11 + g), (uint32_t)((j - 1) & 1));   // P V of step i - 2 done: O_g up to date
         const bool need = m_new > m_ref + 8.f;              // rows of a warp decide together (TMEM ops are warp-wide)
         if (__any_sync(0xffffffffu, need)) {
+          // O_g is touched only here: wait for P V of step i - 2.  Skipping the wait on the other steps is safe -- phase j of
+          // this barrier needs P of own step j, which this thread has not produced yet, so at own step j the barrier is
+          // either still in phase j - 1 or has just completed it: the parity test cannot alias an older phase.
+          ptx::mbar_wait(bar(11 + g), (uint32_t)((j - 1) & 1));
           ptx::tc_fence_after_sync();
           const float f = need ? ex2(m_ref - m_new) : 1.f;
 #pragma unroll 1
@@ -672,7 +682,7 @@ extern "C" int prl_paged_attn_prefill_tc(const void* q, int32_t q_rows, const vo
   TcPrefillParams p;
   p.out = (__nv_bfloat16*)out_bf16;
   p.block_table = block_table; p.seq_q_start = seq_q_start; p.seq_q_len = seq_q_len; p.seq_pos0 = seq_pos0;
-  p.seq_slot = seq_slot; p.max_blocks = max_blocks; p.n_q = n_q; p.n_kv = n_kv; p.R = n_q / n_kv;
+  p.seq_slot = seq_slot; p.seq_kv_start = nullptr; p.max_blocks = max_blocks; p.n_q = n_q; p.n_kv = n_kv; p.R = n_q / n_kv;
   p.nq = 128 / p.R;
   p.n_pages = n_pages; p.layer = layer; p.scale_log2 = sm_scale * 1.4426950408889634f;
   p.col_k = p.col_v = 0; p.lse = nullptr; p.timing = nullptr;
@@ -729,7 +739,7 @@ extern "C" int prl_attn_varlen_fwd(const void* qkv, int64_t qkv_stride, int32_t 
   PRL_CHECK_ARG(qkv_stride >= (int64_t)(n_q + 2 * n_kv) * kDT && qkv_stride % 8 == 0, "prl_attn_varlen_fwd: bad row stride");
   TcPrefillParams p;
   p.out = (__nv_bfloat16*)out_bf16;
-  p.block_table = nullptr; p.seq_q_start = seg_start; p.seq_q_len = seg_len; p.seq_pos0 = nullptr; p.seq_slot = nullptr;
+  p.block_table = nullptr; p.seq_q_start = seg_start; p.seq_q_len = seg_len; p.seq_pos0 = nullptr; p.seq_slot = nullptr; p.seq_kv_start = nullptr;
   p.max_blocks = 0; p.n_q = n_q; p.n_kv = n_kv; p.R = n_q / n_kv; p.nq = 128 / p.R;
   p.n_pages = 0; p.layer = 0; p.scale_log2 = sm_scale * 1.4426950408889634f;
   p.col_k = n_q * kDT; p.col_v = (n_q + n_kv) * kDT; p.lse = lse; p.timing = g_fwd_timing;
@@ -754,6 +764,43 @@ extern "C" int prl_attn_varlen_fwd(const void* qkv, int64_t qkv_stride, int32_t 
     PRL_CUDA(ensure_smem(attn_fwd_v2_kernel<true>, smem, smem_attr2));
     attn_fwd_v2_kernel<true><<<grid, kThreadsT, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
   }
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
+// Sequence-parallel form of prl_attn_varlen_fwd (the reference shards a packed row over `seq_parallel` ranks and runs
+// ring attention, finetune_loop.py:507-517, finetune/types.py:145-180): the queries are the LOCAL slice q[Tq, q_stride]
+// (query heads in the first n_q * 128 columns), the keys / values the all-gathered matrix kv[Tkv, kv_stride] =
+// [k heads | v heads].  Local segment z: queries q rows [seg_q_start[z], + seg_q_len[z]), the first of them at position
+// seg_pos0[z] of its sequence, whose first key is kv row seg_kv_start[z].
+extern "C" int prl_attn_varlen_fwd_kv(const void* q, int64_t q_stride, int32_t Tq, const void* kv, int64_t kv_stride,
+                                      int32_t Tkv, const int32_t* seg_q_start, const int32_t* seg_q_len,
+                                      const int32_t* seg_pos0, const int32_t* seg_kv_start, int32_t n_seg,
+                                      int32_t max_q_len, int32_t n_q, int32_t n_kv, int32_t head_dim, float sm_scale,
+                                      void* out_bf16, float* lse, prl_stream_t stream_) {
+  PRL_CHECK_ARG(q && kv && seg_q_start && seg_q_len && seg_pos0 && seg_kv_start && out_bf16, "prl_attn_varlen_fwd_kv: NULL argument");
+  PRL_CHECK_ARG(head_dim == kDT, "prl_attn_varlen_fwd_kv: head_dim must be 128");
+  PRL_CHECK_ARG(Tq >= 1 && Tkv >= 1 && n_seg >= 1 && max_q_len >= 1 && n_kv >= 1 && n_q % n_kv == 0 && n_q / n_kv <= 64,
+                "prl_attn_varlen_fwd_kv: bad shape");
+  PRL_CHECK_ARG(q_stride >= (int64_t)n_q * kDT && q_stride % 8 == 0 && kv_stride >= (int64_t)2 * n_kv * kDT && kv_stride % 8 == 0,
+                "prl_attn_varlen_fwd_kv: bad row stride");
+  TcPrefillParams p;
+  p.out = (__nv_bfloat16*)out_bf16;
+  p.block_table = nullptr; p.seq_q_start = seg_q_start; p.seq_q_len = seg_q_len; p.seq_pos0 = seg_pos0; p.seq_slot = nullptr;
+  p.seq_kv_start = seg_kv_start;
+  p.max_blocks = 0; p.n_q = n_q; p.n_kv = n_kv; p.R = n_q / n_kv; p.nq = 128 / p.R;
+  p.n_pages = 0; p.layer = 0; p.scale_log2 = sm_scale * 1.4426950408889634f;
+  p.col_k = 0; p.col_v = n_kv * kDT; p.lse = lse; p.timing = nullptr;
+  CUtensorMap tq, tkv;
+  int rc = make_tmap_2d_bf16(&tkv, kv, (uint64_t)(2 * n_kv) * kDT, (uint64_t)Tkv, (uint64_t)kv_stride * 2, 64, kPageT);
+  if (rc) return rc;
+  rc = make_tmap_3d_bf16(&tq, q, kDT, (uint64_t)n_q, (uint64_t)Tq, kDT * 2, (uint64_t)q_stride * 2, 64, (uint32_t)p.R, (uint32_t)p.nq);
+  if (rc) return rc;
+  const int smem = 2 * kTile16K + 2 * kStageBytesT + 4 * kTile16K + 1024 + 8 * 20 + 2 * 128 * 4 + 16;
+  dim3 grid((unsigned)(((max_q_len + p.nq - 1) / p.nq + 1) & ~1), (unsigned)n_kv, (unsigned)n_seg);
+  static SmemAttr smem_attr = {};
+  PRL_CUDA(ensure_smem(attn_fwd_v2_kernel<true>, smem, smem_attr));
+  attn_fwd_v2_kernel<true><<<grid, kThreadsT, (size_t)smem, (cudaStream_t)stream_>>>(tq, tkv, p);
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }

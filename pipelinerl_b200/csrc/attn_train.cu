@@ -51,6 +51,12 @@ struct BwdParams {
   const __nv_bfloat16* do_base;
   int64_t q_stride, do_stride;
   long long* timing;             // measurement only (prl_attn_debug_bwd_timing): per-phase cycle sums of one CTA, else NULL
+  // sequence-parallel form (generation 4 only; NULL / dqkv values otherwise): the queries are a slice of their sequences
+  const int32_t* seg_pos0;       // position of a segment's first LOCAL query inside its sequence
+  const int32_t* seg_kv_start;   // row of the sequence's first key in the K / V matrix
+  __nv_bfloat16* dkv;            // where dK / dV rows go: [kv rows, dkv_stride], columns dkv_col_k / dkv_col_v (+ head * 128)
+  int64_t dkv_stride;
+  int dkv_col_k, dkv_col_v;
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -730,10 +736,12 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const int jt = blockIdx.x, kvh = blockIdx.y, z = blockIdx.z;
   const int q_len = ptx::warp_uniform(p.seg_len[z]);
   const int key0 = jt * 128;
-  if (key0 >= q_len) return;                       // before any barrier / TMEM use
+  const int pos0 = p.seg_pos0 ? ptx::warp_uniform(p.seg_pos0[z]) : 0;   // position of local query 0 (sequence-parallel slice)
+  if (key0 >= pos0 + q_len) return;                // before any barrier / TMEM use
   const int seg0 = ptx::warp_uniform(p.seg_start[z]);
+  const int kv0 = p.seg_kv_start ? ptx::warp_uniform(p.seg_kv_start[z]) : seg0;
   const int nqa = p.nq;
-  const int u_first = key0 / nqa;
+  const int u_first = (key0 > pos0 ? key0 - pos0 : 0) / nqa;   // first 64-row query sub-tile holding a position >= key0
   const int u_end = (q_len + nqa - 1) / nqa;
   const int n_it = u_end - u_first;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -766,7 +774,7 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     // ===== TMA producer =====
     if (lane == 0) {
       ptx::mbar_arrive_expect_tx(bar(0), (uint32_t)kKvBytes);
-      const int krow = seg0 + key0;
+      const int krow = kv0 + key0;
 #pragma unroll
       for (int kv = 0; kv < 2; ++kv) {
         const int c0 = (kv ? p.col_v : p.col_k) + kvh * kD;
@@ -865,7 +873,7 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     auto fetch = [&](int u) -> float {
       const int tok = u * nqa + mqi;
       const bool valid = (mqi < nqa) && (tok < q_len);
-      if (mwhich == 2) return __int_as_float(valid ? tok : -1);
+      if (mwhich == 2) return __int_as_float(valid ? pos0 + tok : -1);
       if (mwhich == 3) return 0.f;
       if (!valid) return mwhich == 0 ? INFINITY : 0.f;
       const float* src = mwhich == 0 ? p.lse : p.delta;
@@ -890,7 +898,7 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(g * 64 + c0), sv);
       ptx::tmem_ld_wait();
       ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(128 + g * 64 + c0), dv);   // completes under the exponentials
-      const bool diag = u * nqa < key0 + 127;
+      const bool diag = pos0 + u * nqa < key0 + 127;
       float pe[32];
 #pragma unroll
       for (int e = 0; e < 32; e += 4) {
@@ -932,8 +940,8 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     // ---- epilogue: 32 head-dim columns of this key's dV and dK rows ----
     ptx::mbar_wait(bar(13), 0);
     ptx::tc_fence_after_sync();
-    const bool valid = kpos < q_len;
-    __nv_bfloat16* drow = p.dqkv + (int64_t)(seg0 + kpos) * p.dqkv_stride + kvh * kD + idx * 32;
+    const bool valid = kpos < pos0 + q_len;
+    __nv_bfloat16* drow = p.dkv + (int64_t)(kv0 + kpos) * p.dkv_stride + kvh * kD + idx * 32;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {     // 0: dV (TMEM 256..383), 1: dK (384..511)
       uint32_t v0[32];
@@ -941,7 +949,7 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       ptx::tmem_ld_wait();
       const float sc = which ? p.sm_scale : 1.f;
       if (valid) {
-        __nv_bfloat16* dst = drow + (which ? p.col_k : p.col_v);
+        __nv_bfloat16* dst = drow + (which ? p.dkv_col_k : p.dkv_col_v);
 #pragma unroll
         for (int d = 0; d < 32; d += 8) {
           uint4 a;
@@ -990,11 +998,13 @@ attn_bwd_dq4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const int q_len = ptx::warp_uniform(p.seg_len[z]);
   if ((qtile & ~1) * p.nq >= q_len) return;             // uniform across the cluster
   const int seg0 = ptx::warp_uniform(p.seg_start[z]);
+  const int pos0 = p.seg_pos0 ? ptx::warp_uniform(p.seg_pos0[z]) : 0;
+  const int kv0 = p.seg_kv_start ? ptx::warp_uniform(p.seg_kv_start[z]) : seg0;
   const int t0 = qtile * p.nq;
   const int row0 = seg0 + t0;
   const int n_valid = t0 >= q_len ? 0 : ((q_len - t0) < p.nq ? (q_len - t0) : p.nq);
   const int pair_rows = ((qtile | 1) + 1) * p.nq;
-  const int kv_end = pair_rows < q_len ? pair_rows : q_len;
+  const int kv_end = pos0 + (pair_rows < q_len ? pair_rows : q_len);
   const int n_it = (kv_end + 127) / 128;
   const int last_page = (kv_end - 1) / 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1039,7 +1049,7 @@ attn_bwd_dq4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         ptx::mbar_arrive_expect_tx(full, (uint32_t)(2 * kT16));
         int pg = 2 * it + (int)rank;
         if (pg > last_page) pg = last_page;            // tail: re-read the last page, its keys are causally masked
-        const int row = seg0 + pg * 64;
+        const int row = kv0 + pg * 64;
         const int c0 = (kv ? p.col_v : p.col_k) + kvh * kD;
         const uint32_t dst = (kv ? v_smem : k_smem) + (uint32_t)(s * 2 * kT16) + (uint32_t)(rank * kT8);
         ptx::tma_load_2d_multicast(dst, &tm_kv, c0, row, full, 3, ptx::kEvictLast);
@@ -1136,7 +1146,7 @@ attn_bwd_dq4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int k = (warp - 2) >> 2;               // 0..3
     const int m = q * 32 + lane;
     const int qi = m / p.R, r = m - qi * p.R;
-    const int qpos = t0 + qi;
+    const int qpos = pos0 + t0 + qi;
     const bool valid = qi < n_valid && qi < p.nq;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int64_t stat = (int64_t)(row0 + qi) * p.n_q + (kvh * p.R + r);
@@ -1161,7 +1171,7 @@ attn_bwd_dq4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       float sv[32];
 #pragma unroll
       for (int e = 0; e < 32; ++e) sv[e] = ex2f(fmaf(__uint_as_float(v0[e]), p.scale_log2, -lse_row));
-      if (i * 128 + 127 > t0) {
+      if (i * 128 + 127 > pos0 + t0) {
         const int key0 = i * 128 + k * 32;
 #pragma unroll
         for (int e = 0; e < 32; ++e)
@@ -1279,6 +1289,8 @@ extern "C" int prl_attn_varlen_bwd(const void* qkv, int64_t qkv_stride, int32_t 
   p.q_base = (const __nv_bfloat16*)qkv; p.q_stride = qkv_stride;
   p.do_base = (const __nv_bfloat16*)d_out_bf16; p.do_stride = (int64_t)n_q * kD;
   p.timing = g_bwd_timing;
+  p.seg_pos0 = nullptr; p.seg_kv_start = nullptr; p.dkv = (__nv_bfloat16*)dqkv; p.dkv_stride = dqkv_stride;
+  p.dkv_col_k = p.col_k; p.dkv_col_v = p.col_v;
   CUtensorMap tkv, tq, tdo;
   int rc = make_tmap_2d_bf16(&tkv, qkv, (uint64_t)width, (uint64_t)T, (uint64_t)qkv_stride * 2, 64, 64);
   if (rc) return rc;
@@ -1336,6 +1348,74 @@ extern "C" int prl_attn_varlen_bwd(const void* qkv, int64_t qkv_stride, int32_t 
       PRL_CUDA(ensure_smem(attn_bwd_dq_kernel<3>, kSmemDq, attr3));
       attn_bwd_dq_kernel<3><<<grid, kThreadsB, (size_t)kSmemDq, stream>>>(tq, tdo, tkv, p);
     }
+    PRL_LAUNCH_CHECK();
+  }
+  return PRL_OK;
+}
+
+// Sequence-parallel form of prl_attn_varlen_bwd (see prl_attn_varlen_fwd_kv for the segment description).  dq[Tq, dq_stride]
+// receives the query-head gradients of the LOCAL queries; dkv[Tkv, dkv_stride] = [dK heads | dV heads] receives THIS RANK'S
+// contribution to every key row (zero where no local query attends) -- the caller reduce-scatters it over the group.
+extern "C" int prl_attn_varlen_bwd_kv(const void* q, int64_t q_stride, int32_t Tq, const void* kv, int64_t kv_stride,
+                                      int32_t Tkv, const int32_t* seg_q_start, const int32_t* seg_q_len,
+                                      const int32_t* seg_pos0, const int32_t* seg_kv_start, int32_t n_seg,
+                                      int32_t max_q_len, int32_t max_kv_len, int32_t n_q, int32_t n_kv, int32_t head_dim,
+                                      float sm_scale, const void* out_bf16, const void* d_out_bf16, const float* lse,
+                                      void* dq, int64_t dq_stride, void* dkv, int64_t dkv_stride, void* workspace,
+                                      size_t workspace_bytes, prl_stream_t stream_) {
+  PRL_CHECK_ARG(q && kv && seg_q_start && seg_q_len && seg_pos0 && seg_kv_start && out_bf16 && d_out_bf16 && lse && dq && dkv && workspace,
+                "prl_attn_varlen_bwd_kv: NULL argument");
+  PRL_CHECK_ARG(head_dim == kD, "prl_attn_varlen_bwd_kv: head_dim must be 128");
+  PRL_CHECK_ARG(Tq >= 1 && Tkv >= 1 && n_seg >= 1 && max_q_len >= 1 && max_kv_len >= max_q_len && n_kv >= 1 && n_q % n_kv == 0 &&
+                n_q / n_kv <= 64, "prl_attn_varlen_bwd_kv: bad shape (GQA group size must be <= 64)");
+  const int64_t kvw = (int64_t)2 * n_kv * kD;
+  PRL_CHECK_ARG(q_stride >= (int64_t)n_q * kD && q_stride % 8 == 0 && dq_stride >= (int64_t)n_q * kD && dq_stride % 8 == 0 &&
+                kv_stride >= kvw && kv_stride % 8 == 0 && dkv_stride >= kvw && dkv_stride % 8 == 0, "prl_attn_varlen_bwd_kv: bad row stride");
+  PRL_CHECK_ARG(workspace_bytes >= prl_attn_varlen_bwd_workspace_bytes(Tq, n_q), "prl_attn_varlen_bwd_kv: workspace too small");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float* delta = (float*)workspace;
+  {
+    const int64_t rows = (int64_t)Tq * n_q;
+    attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>((const __nv_bfloat16*)out_bf16,
+                                                                     (const __nv_bfloat16*)d_out_bf16, rows, delta);
+    PRL_LAUNCH_CHECK();
+  }
+  PRL_CUDA(cudaMemset2DAsync(dkv, (size_t)dkv_stride * 2, 0, (size_t)kvw * 2, (size_t)Tkv, stream));
+  BwdParams p;
+  p.lse = lse; p.delta = delta; p.dqkv = (__nv_bfloat16*)dq; p.dqkv_stride = dq_stride;
+  p.seg_start = seg_q_start; p.seg_len = seg_q_len; p.n_q = n_q; p.n_kv = n_kv; p.R = n_q / n_kv;
+  p.col_k = 0; p.col_v = n_kv * kD;
+  p.scale_log2 = sm_scale * 1.4426950408889634f; p.sm_scale = sm_scale;
+  p.q_base = (const __nv_bfloat16*)q; p.q_stride = q_stride;
+  p.do_base = (const __nv_bfloat16*)d_out_bf16; p.do_stride = (int64_t)n_q * kD;
+  p.timing = nullptr;
+  p.seg_pos0 = seg_pos0; p.seg_kv_start = seg_kv_start; p.dkv = (__nv_bfloat16*)dkv; p.dkv_stride = dkv_stride;
+  p.dkv_col_k = 0; p.dkv_col_v = n_kv * kD;
+  CUtensorMap tkv, tq, tdo;
+  int rc = make_tmap_2d_bf16(&tkv, kv, (uint64_t)kvw, (uint64_t)Tkv, (uint64_t)kv_stride * 2, 64, 64);
+  if (rc) return rc;
+  {
+    p.nq = 64 / p.R;
+    rc = make_tmap_3d_bf16(&tq, q, kD, (uint64_t)n_q, (uint64_t)Tq, kD * 2, (uint64_t)q_stride * 2, 64, (uint32_t)p.R, (uint32_t)p.nq);
+    if (rc) return rc;
+    rc = make_tmap_3d_bf16(&tdo, d_out_bf16, kD, (uint64_t)n_q, (uint64_t)Tq, kD * 2, (uint64_t)n_q * kD * 2, 64, (uint32_t)p.R, (uint32_t)p.nq);
+    if (rc) return rc;
+    dim3 grid((unsigned)((max_kv_len + 127) / 128), (unsigned)n_kv, (unsigned)n_seg);
+    static SmemAttr attr = {};
+    PRL_CUDA(ensure_smem(attn_bwd_dkdv4_kernel, kSmemDkdv4, attr));
+    attn_bwd_dkdv4_kernel<<<grid, kThreadsB4, (size_t)kSmemDkdv4, stream>>>(tq, tdo, tkv, p);
+    PRL_LAUNCH_CHECK();
+  }
+  {
+    p.nq = 128 / p.R;
+    rc = make_tmap_3d_bf16(&tq, q, kD, (uint64_t)n_q, (uint64_t)Tq, kD * 2, (uint64_t)q_stride * 2, 64, (uint32_t)p.R, (uint32_t)p.nq);
+    if (rc) return rc;
+    rc = make_tmap_3d_bf16(&tdo, d_out_bf16, kD, (uint64_t)n_q, (uint64_t)Tq, kD * 2, (uint64_t)n_q * kD * 2, 64, (uint32_t)p.R, (uint32_t)p.nq);
+    if (rc) return rc;
+    dim3 grid((unsigned)(((max_q_len + p.nq - 1) / p.nq + 1) & ~1), (unsigned)n_kv, (unsigned)n_seg);
+    static SmemAttr attr = {};
+    PRL_CUDA(ensure_smem(attn_bwd_dq4_kernel<false>, kSmemDq4, attr));
+    attn_bwd_dq4_kernel<false><<<grid, kThreadsB4, (size_t)kSmemDq4, stream>>>(tq, tdo, tkv, p);
     PRL_LAUNCH_CHECK();
   }
   return PRL_OK;

@@ -204,7 +204,18 @@ def rl_step(model, batch: PipelineBatchEncoding, current_step: int, max_step: in
     full-vocabulary logits never reach HBM.
     """
     if seq_parallel_group is not None:
-        raise NotImplementedError("sequence-parallel rl_step is out of scope for v1 (SURVEY.md §8e)")
+        # The batch is this rank's slice of a packed row (PipelineBatchEncoding.make_slices); like the reference, logits
+        # and labels are shifted INSIDE the slice (rl/__init__.py:207-212 on the sliced batch), so the last token of a
+        # slice predicts nothing.  Everything but attention is token-local; the model exchanges K / V itself.
+        if config.policy_loss == "gspo":
+            raise NotImplementedError("gspo with seq_parallel_group: the per-segment sums would have to be all-reduced "
+                                      "inside the fused loss tail (reference rl/utils.py:194-206); use ppo / reinforce")
+        if not hasattr(model, "set_sequence_parallel"):
+            raise NotImplementedError("seq_parallel_group needs a model that exchanges K / V over the group "
+                                      "(pipelinerl_b200.learner_model.NativeQwen2)")
+        if not batch.is_packed:
+            raise ValueError("sequence parallelism slices PACKED rows")
+        model.set_sequence_parallel(seq_parallel_group)
     if hasattr(model, "value_head"):
         raise NotImplementedError("value-head models are out of scope (GRPO path has no critic)")
     _require_cuda(batch.input_ids, "batch")

@@ -36,6 +36,7 @@ class TrainerConfig:
     lr_scheduler_type: str = "constant"
     num_warmup_steps: int = 0
     weight_update_interval: int = 1
+    seq_parallel: int = 1                  # consecutive learner ranks sharing one packed row (finetune_loop.py:507-517)
     eos_token_id: int = 2                  # only used by the GPU-resident preprocess ("eos in input_ids" overflow rule)
     rl: RLConfig = field(default_factory=RLConfig)
 
@@ -50,6 +51,23 @@ def allreduce_gradients(flat_grad: torch.Tensor, group=None) -> None:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
 
 
+def build_seq_parallel_group(dp_group, seq_parallel: int):
+    """Groups of `seq_parallel` CONSECUTIVE learner ranks (the reference's loop, finetune_loop.py:508-516); every learner
+    rank calls this and gets the group it belongs to."""
+    import torch.distributed as dist
+    world = dist.get_world_size(dp_group)
+    if world % seq_parallel != 0:
+        raise ValueError(f"{world} learner ranks are not a multiple of seq_parallel={seq_parallel}")
+    global_ranks = dist.get_process_group_ranks(dp_group) if dp_group is not None else list(range(world))
+    me, mine = dist.get_rank(), None
+    for leader in range(0, world, seq_parallel):
+        ranks = [global_ranks[leader + i] for i in range(seq_parallel)]
+        if me in ranks:      # only the members create their group (use_local_synchronization): samplers need not join
+            mine = dist.new_group(ranks=ranks, use_local_synchronization=True)
+    assert mine is not None
+    return mine
+
+
 class StepAccountant:
     """Sample accounting of one learner rank (pipelinerl/finetune_loop.py:626-646, 674-713).
 
@@ -59,15 +77,21 @@ class StepAccountant:
     count EQUALS the target: the writer cuts micro-batches at that boundary (preprocess.py:620-622) and feeds sentinel
     batches to ranks that already hold their share (:600-607, trainer side :674-676)."""
 
-    def __init__(self, samples_per_step: int, group=None, device=None, start_samples: int = 0):
+    def __init__(self, samples_per_step: int, group=None, device=None, start_samples: int = 0, seq_parallel: int = 1):
         import torch.distributed as dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
-        if samples_per_step % self.world != 0:
-            raise ValueError(f"samples_per_step={samples_per_step} is not divisible by the {self.world} learner ranks")
+        # sequence parallelism: `seq_parallel` consecutive ranks hold slices of the SAME micro-batch and each counts its
+        # samples, so the summed count is `seq_parallel` times the truth (reference finetune_loop.py:628,709-712)
+        self.seq_parallel = seq_parallel
+        if self.world % seq_parallel != 0:
+            raise ValueError(f"{self.world} learner ranks are not a multiple of seq_parallel={seq_parallel}")
+        leads = self.world // seq_parallel
+        if samples_per_step % leads != 0:
+            raise ValueError(f"samples_per_step={samples_per_step} is not divisible by the {leads} lead learner ranks")
         self.samples_per_step = samples_per_step
-        self.samples_per_lead_per_step = samples_per_step // self.world
+        self.samples_per_lead_per_step = samples_per_step // leads
         self.start_samples = start_samples
         self.local_samples = 0
         self.target_local = self.samples_per_lead_per_step
@@ -90,6 +114,9 @@ class StepAccountant:
             counts = torch.tensor([self.local_samples], dtype=torch.int64, device=self.device)
             dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)
             total = int(counts.item())
+            if total % self.seq_parallel != 0:
+                raise RuntimeError("sample counts of a sequence-parallel group disagree (finetune_loop.py:711)")
+            total //= self.seq_parallel
         if total > self.target_total:
             raise RuntimeError(f"micro-batch overshoots the optimizer step ({total} > {self.target_total} samples): "
                                "pack with samples_per_step (pack_micro_batches / MicroBatchDealer)")
@@ -162,7 +189,9 @@ def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding
     rl_cfg = cfg.rl.model_copy(update={"batch_size": cfg.samples_per_step})   # GLOBAL batch normalises the loss
     tm = TrainingMetrics()
     history: list[dict] = []
-    acct = StepAccountant(cfg.samples_per_step, group=dp_group, device=dev, start_samples=tm.samples)
+    sp_group = build_seq_parallel_group(dp_group, cfg.seq_parallel) if cfg.seq_parallel > 1 else None
+    acct = StepAccountant(cfg.samples_per_step, group=dp_group, device=dev, start_samples=tm.samples,
+                          seq_parallel=cfg.seq_parallel)
     rank = acct.rank
     step_stats, t_step = [], time.time()
     opt.zero_grad()
@@ -180,7 +209,7 @@ def run_training(model: torch.nn.Module, batches: Iterable[PipelineBatchEncoding
         n_samples = 0 if batch.sentinel else (int(batch.seq_boundaries.numel()) - 1 - (1 if batch.padding else 0)
                                                if batch.is_packed else batch.input_ids.shape[0])
         samples_so_far, do_optimizer_step = acct.observe(n_samples, bool(batch.sentinel))
-        loss, stats = rl_step(model, batch, tm.completed_steps, cfg.max_train_steps, rl_cfg)
+        loss, stats = rl_step(model, batch, tm.completed_steps, cfg.max_train_steps, rl_cfg, seq_parallel_group=sp_group)
         if batch.sentinel:
             loss = loss * 0.0
         loss.backward()

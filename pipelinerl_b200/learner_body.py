@@ -149,6 +149,37 @@ class Ops:
                                                 ws.numel(), _lib.stream_ptr()))
         return dqkv
 
+    def attn_fwd_kv(self, q, kv, segs, n_q, n_kv, head_dim, need_lse=True):
+        """sequence-parallel slice: local queries q [Tq, >= n_q d] against the gathered kv [Tkv, 2 n_kv d];
+        segs = (q_start, q_len, pos0, kv_start) int32 device tensors + max_q_len, max_kv_len (sp_segments)"""
+        q_start, q_len, pos0, kv_start, max_q, _ = segs
+        Tq = q.shape[0]
+        assert q.dtype == torch.bfloat16 and kv.dtype == torch.bfloat16 and q.stride(1) == 1 and kv.stride(1) == 1
+        out = torch.empty(Tq, n_q * head_dim, dtype=torch.bfloat16, device=q.device)
+        lse = torch.empty(Tq, n_q, dtype=torch.float32, device=q.device) if need_lse else None
+        _lib.check(self.lib.prl_attn_varlen_fwd_kv(q.data_ptr(), q.stride(0), Tq, kv.data_ptr(), kv.stride(0), kv.shape[0],
+                                                   q_start.data_ptr(), q_len.data_ptr(), pos0.data_ptr(), kv_start.data_ptr(),
+                                                   q_start.numel(), int(max_q), n_q, n_kv, head_dim,
+                                                   1.0 / math.sqrt(head_dim), out.data_ptr(),
+                                                   lse.data_ptr() if lse is not None else None, _lib.stream_ptr()))
+        return out, lse
+
+    def attn_bwd_kv(self, q, kv, out, d_out, lse, segs, n_q, n_kv, head_dim, dq):
+        """writes dq (a [Tq, n_q d] view, e.g. the query columns of the local dqkv) and returns this rank's contribution
+        dkv [Tkv, 2 n_kv d] to every key row"""
+        q_start, q_len, pos0, kv_start, max_q, max_kv = segs
+        Tq = q.shape[0]
+        assert d_out.dtype == torch.bfloat16 and d_out.is_contiguous() and out.is_contiguous() and dq.stride(1) == 1
+        dkv = torch.empty(kv.shape[0], 2 * n_kv * head_dim, dtype=torch.bfloat16, device=q.device)
+        ws = torch.empty(int(self.lib.prl_attn_varlen_bwd_workspace_bytes(Tq, n_q)), dtype=torch.uint8, device=q.device)
+        _lib.check(self.lib.prl_attn_varlen_bwd_kv(q.data_ptr(), q.stride(0), Tq, kv.data_ptr(), kv.stride(0), kv.shape[0],
+                                                   q_start.data_ptr(), q_len.data_ptr(), pos0.data_ptr(), kv_start.data_ptr(),
+                                                   q_start.numel(), int(max_q), int(max_kv), n_q, n_kv, head_dim,
+                                                   1.0 / math.sqrt(head_dim), out.data_ptr(), d_out.data_ptr(), lse.data_ptr(),
+                                                   dq.data_ptr(), dq.stride(0), dkv.data_ptr(), dkv.stride(0), ws.data_ptr(),
+                                                   ws.numel(), _lib.stream_ptr()))
+        return dkv
+
     def embed(self, table, ids):
         T, H = ids.numel(), table.shape[1]
         out = torch.empty(T, H, dtype=torch.bfloat16, device=table.device)
@@ -176,6 +207,18 @@ class NativeBody:
         self.keep_attention_layers = cfg.num_layers   # lower it when activation memory is short (0 = full recompute)
         self.keep_gate_up_layers = 0                  # layers that also keep gate_up's output (2 I bf16 per token):
         #                                               their backward skips the largest recompute GEMM
+        self.sp_group = None                          # sequence parallelism: see set_sequence_parallel
+        self._sp_segs = None
+
+    def set_sequence_parallel(self, group) -> None:
+        """Sequence parallelism (reference: `seq_parallel` ranks share one packed row, finetune_loop.py:507-517, through
+        ring attention).  Here every rank runs the token-local work (norms, GEMMs, MLP, head) on its slice and attention
+        is the only exchange: K / V of a GQA model are 2 n_kv / (n_q + 2 n_kv) of the qkv row (1/4.5 for Qwen2.5-7B), so
+        each layer ALL-GATHERS the K | V columns over the group (NCCL, 32 MB per layer at 16 K tokens), runs its local
+        queries against the gathered keys (prl_attn_varlen_fwd_kv), and in the backward REDUCE-SCATTERS the ranks'
+        dK / dV contributions.  `group` = None switches it off."""
+        import torch.distributed as dist
+        self.sp_group = group if (group is not None and dist.get_world_size(group) > 1) else None
 
     def refresh(self) -> None:
         """Hook called after every optimizer step.  Nothing to rebuild: dgrad reads the weights as stored."""
@@ -190,13 +233,34 @@ class NativeBody:
         return self._seg_cache[1:]
 
     def _attention(self, qkv, bounds, need_grad):
-        """returns (attention output [T, q_size] bf16, log-sum-exp [T, n_q] fp32 or None)"""
+        """returns (attention output [T, q_size] bf16, statistics for the backward or None)"""
         c = self.cfg
+        if self.sp_group is not None:
+            import torch.distributed as dist
+            qe = c.num_q_heads * c.head_dim
+            kv_local = qkv[:, qe:].contiguous()
+            kv = torch.empty(kv_local.shape[0] * dist.get_world_size(self.sp_group), kv_local.shape[1],
+                             dtype=kv_local.dtype, device=kv_local.device)
+            dist.all_gather_into_tensor(kv, kv_local, group=self.sp_group)
+            out, lse = self.ops.attn_fwd_kv(qkv, kv, self._sp_segs, c.num_q_heads, c.num_kv_heads, c.head_dim,
+                                            need_lse=need_grad)
+            return out, ((lse, kv) if need_grad else None)
         st, ln, mx = self._segments(bounds, qkv.device)
         return self.ops.attn_fwd(qkv, st, ln, mx, c.num_q_heads, c.num_kv_heads, c.head_dim, need_lse=need_grad)
 
     def _attention_bwd(self, qkv, attn, lse, bounds, d_attn):
         c = self.cfg
+        if self.sp_group is not None:
+            import torch.distributed as dist
+            lse, kv = lse
+            qe = c.num_q_heads * c.head_dim
+            dqkv = torch.empty_like(qkv)
+            dkv_all = self.ops.attn_bwd_kv(qkv, kv, attn, d_attn, lse, self._sp_segs, c.num_q_heads, c.num_kv_heads,
+                                           c.head_dim, dqkv[:, :qe])
+            dkv = torch.empty(qkv.shape[0], dkv_all.shape[1], dtype=dkv_all.dtype, device=dkv_all.device)
+            dist.reduce_scatter_tensor(dkv, dkv_all, op=dist.ReduceOp.SUM, group=self.sp_group)
+            dqkv[:, qe:] = dkv
+            return dqkv
         st, ln, mx = self._segments(bounds, qkv.device)
         return self.ops.attn_bwd(qkv, attn, d_attn, lse, st, ln, mx, c.num_q_heads, c.num_kv_heads, c.head_dim)
 
@@ -263,6 +327,27 @@ class NativeBody:
 
     # ---- whole body ----
     @staticmethod
+    def sp_segments(position_ids: torch.Tensor, offset: int, device):
+        """Segment description of a sequence-parallel slice: `position_ids` are those of the LOCAL tokens (a contiguous
+        slice, starting at global row `offset`, of a packed row whose position ids restart at 0 for every sample -- the
+        reference's make_slices, finetune/types.py:145-180).  A local segment starts at every local 0 and at local row 0;
+        its first query sits at position position_ids[start], and its sequence's first key is global row
+        offset + start - position_ids[start]."""
+        pos = position_ids.to("cpu", torch.int64)
+        T = pos.numel()
+        starts = torch.nonzero(pos == 0).flatten().tolist()
+        if not starts or starts[0] != 0:
+            starts = [0] + starts
+        ends = starts[1:] + [T]
+        q_start = torch.tensor(starts, dtype=torch.int32)
+        q_len = torch.tensor([e - s for s, e in zip(starts, ends)], dtype=torch.int32)
+        pos0 = pos[starts].to(torch.int32)
+        kv_start = (q_start + int(offset) - pos0).to(torch.int32)
+        max_q = int(q_len.max())
+        max_kv = int((pos0 + q_len).max())
+        return (q_start.to(device), q_len.to(device), pos0.to(device), kv_start.to(device), max_q, max_kv)
+
+    @staticmethod
     def segment_bounds(position_ids: torch.Tensor) -> list[tuple[int, int]]:
         starts = torch.nonzero(position_ids == 0).flatten().tolist()
         T = position_ids.numel()
@@ -280,6 +365,10 @@ class NativeBody:
         ids = input_ids.to(torch.int64).contiguous()
         pos = position_ids.to(torch.int32).contiguous()
         bounds = self.segment_bounds(position_ids)
+        if self.sp_group is not None:
+            import torch.distributed as dist
+            # this rank holds rows [rank * T, (rank + 1) * T) of the packed row (make_slices, finetune/types.py:145-180)
+            self._sp_segs = self.sp_segments(position_ids, dist.get_rank(self.sp_group) * position_ids.numel(), ids.device)
         h = o.embed(self.w["embed_tokens.weight"], ids)
         inputs, kept = [], []
         for l in range(c.num_layers):

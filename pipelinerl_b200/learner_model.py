@@ -239,6 +239,12 @@ class NativeQwen2(torch.nn.Module):
     def after_optimizer_step(self) -> None:
         self.body.refresh()
 
+    def set_sequence_parallel(self, group) -> None:
+        """every rank of `group` feeds its slice of the same packed row (rl_step's seq_parallel_group; NativeBody)"""
+        if self.body is None:
+            raise RuntimeError("NativeQwen2.bind(optimizer) must be called first")
+        self.body.set_sequence_parallel(group)
+
     def hidden_states(self, input_ids, position_ids=None):
         if self.body is None:
             raise RuntimeError("NativeQwen2.bind(optimizer) must be called first")

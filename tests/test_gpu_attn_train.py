@@ -149,3 +149,51 @@ def test_attention_output_rows_outside_every_segment_are_untouched(cuda_device):
     out, lse = o.attn_fwd(qkv, st, ln, 200, n_q, n_kv, D)
     ref, _ = o.attn_fwd(qkv[10:210].contiguous(), torch.zeros(1, dtype=torch.int32, device=dev), ln, 200, n_q, n_kv, D)
     assert torch.equal(out[10:210], ref)
+
+
+@pytest.mark.parametrize("n_q,n_kv,lens,sp", [
+    (4, 2, [5, 1, 3, 7], 2),
+    (7, 1, [130, 17, 300, 1, 64], 2),          # slices start in the middle of a sample
+    (28, 4, [511, 1, 700, 836], 4),
+    (5, 1, [129, 383], 4),
+    (28, 4, [16384], 2),                        # one 16 384-token sample over two ranks
+    (28, 4, [5000, 11000, 384], 4),
+])
+def test_sequence_parallel_slices_match_full_attention(cuda_device, n_q, n_kv, lens, sp):
+    """prl_attn_varlen_fwd_kv / _bwd_kv (the sequence-parallel learner, reference finetune_loop.py:507-517 + make_slices
+    finetune/types.py:145-180): every rank's slice of queries against the gathered K / V reproduces its rows of the
+    single-rank result bit for bit (out, lse, dQ), and the ranks' dK / dV contributions sum to the single-rank dK / dV."""
+    from pipelinerl_b200.learner_body import NativeBody
+    o = _ops()
+    dev = cuda_device
+    D = 128
+    T = sum(lens)
+    assert T % sp == 0
+    g = torch.Generator(device=dev).manual_seed(7 + T)
+    qkv = torch.randn(T, (n_q + 2 * n_kv) * D, generator=g, device=dev).to(torch.bfloat16)
+    d_out = torch.randn(T, n_q * D, generator=g, device=dev).to(torch.bfloat16)
+    st = torch.tensor([sum(lens[:i]) for i in range(len(lens))], dtype=torch.int32, device=dev)
+    ln = torch.tensor(lens, dtype=torch.int32, device=dev)
+    out, lse = o.attn_fwd(qkv, st, ln, max(lens), n_q, n_kv, D)
+    dqkv = o.attn_bwd(qkv, out, d_out, lse, st, ln, max(lens), n_q, n_kv, D)
+    qe = n_q * D
+    kv = qkv[:, qe:].contiguous()
+    pos = torch.cat([torch.arange(l) for l in lens])
+    dkv_sum = torch.zeros(T, 2 * n_kv * D, dtype=torch.float32, device=dev)
+    Tl = T // sp
+    for r in range(sp):
+        a, b = r * Tl, (r + 1) * Tl
+        segs = NativeBody.sp_segments(pos[a:b], a, dev)
+        out_r, lse_r = o.attn_fwd_kv(qkv[a:b], kv, segs, n_q, n_kv, D)
+        assert torch.equal(out_r, out[a:b]), f"rank {r}: forward rows differ from the single-rank result"
+        assert torch.equal(lse_r, lse[a:b])
+        dq_r = torch.empty(Tl, qe, dtype=torch.bfloat16, device=dev)
+        dkv_r = o.attn_bwd_kv(qkv[a:b], kv, out_r, d_out[a:b].contiguous(), lse_r, segs, n_q, n_kv, D, dq_r)
+        assert torch.equal(dq_r, dqkv[a:b, :qe]), f"rank {r}: dQ rows differ from the single-rank result"
+        assert torch.all(dkv_r[b:] == 0), "keys after the slice's last query must receive no gradient"
+        dkv_sum += dkv_r.float()
+    want = dqkv[:, qe:].float()
+    scale = max(want.abs().max().item(), 1e-3)
+    err = (dkv_sum - want).abs().max().item() / scale
+    print(f"[attn sp={sp}] n_q={n_q} n_kv={n_kv} lens={lens}: sum of rank dK/dV vs single rank rel {err:.2e}")
+    assert err <= 2 ** -7, err

@@ -188,6 +188,57 @@ def test_dealer_feeds_two_gloo_learner_ranks_in_lockstep(tmp_path):
     assert sent0 + sent1 >= 1 and abs(n0 - n1) <= 1
 
 
+def test_sequence_parallel_ranks_share_one_sample_count(tmp_path):
+    """seq_parallel = 2 on a gloo world of 2: both ranks hold slices of the SAME micro-batch and each counts its samples;
+    the accountant divides the summed count by seq_parallel (reference finetune_loop.py:628,709-712) and both ranks step at
+    the same micro-batch.  The dealer cuts a micro-batch into `seq_parallel` slices for ranks lead .. lead + sp - 1."""
+    script = tmp_path / "sp.py"
+    script.write_text(
+        "import sys, json, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {str(ROOT)!r})\n"
+        "from pipelinerl_b200.finetune_loop import StepAccountant, build_seq_parallel_group\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "g = build_seq_parallel_group(None, 2)\n"
+        "assert dist.get_world_size(g) == 2\n"
+        "acct = StepAccountant(6, seq_parallel=2)\n"
+        "assert acct.samples_per_lead_per_step == 6\n"
+        "steps = []\n"
+        "for i, n in enumerate([2, 3, 1, 4, 2]):\n"
+        "    total, do_step = acct.observe(n, False)\n"
+        "    if do_step: steps.append((i, total))\n"
+        "out = [None] * w; dist.all_gather_object(out, steps)\n"
+        "if r == 0: print(json.dumps(out))\n"
+        "dist.destroy_process_group()\n")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29581", str(script)],
+                         capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stderr[-3000:]
+    s0, s1 = json.loads([l for l in res.stdout.splitlines() if l.startswith("[")][-1])
+    assert s0 == s1 == [[2, 6], [4, 12]]
+
+
+def test_sequence_parallel_segment_description():
+    """NativeBody.sp_segments: a slice of a packed row -> (local start, length, position of the first local query, global
+    row of the sequence's first key) per local segment, checked against the row's own sample boundaries"""
+    import torch
+    from pipelinerl_b200.learner_body import NativeBody
+    lens = [130, 17, 300, 1, 64]
+    pos = torch.cat([torch.arange(l) for l in lens])
+    T = pos.numel()
+    starts = [sum(lens[:i]) for i in range(len(lens))]
+    for sp in (1, 2, 4):
+        Tl = T // sp
+        for r in range(sp):
+            a = r * Tl
+            qs, ql, p0, kvs, mq, mkv = NativeBody.sp_segments(pos[a:a + Tl], a, "cpu")
+            assert int(ql.sum()) == Tl and mq == int(ql.max()) and mkv == int((p0 + ql).max())
+            for s, l, p, k in zip(qs.tolist(), ql.tolist(), p0.tolist(), kvs.tolist()):
+                first = max(x for x in starts if x <= a + s)
+                assert p == a + s - first and k == first
+                assert pos[a + s:a + s + l].tolist() == list(range(p, p + l))
+
+
 def test_trainer_state_follows_topic(tmp_path):
     from pipelinerl_b200.state import TrainerState
     from pipelinerl_b200.weights import SamplesProcessed, TrainingDone, TRAINER_TOPIC

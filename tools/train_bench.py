@@ -195,8 +195,12 @@ def main():
     ap.add_argument("--keep-gate-up", type=int, default=-1, help="layers that keep gate_up's output (-1 = as many as fit)")
     ap.add_argument("--profile", action="store_true", help="after the timed steps, print the per-kernel CUDA time of one step")
     ap.add_argument("--check", action="store_true", help="tiny model: DP result == single-learner result on all micro-batches")
+    ap.add_argument("--check-sp", action="store_true", help="tiny model: sequence-parallel ranks == single learner on the whole rows")
     a = ap.parse_args()
     import os
+    if a.check_sp:
+        print(json.dumps(check_sp()))
+        return
     if a.check:
         print(json.dumps(check_dp()))
         return
@@ -266,6 +270,74 @@ def check_dp(group=None, own_process_group=True):
     opt.close()
     if own_process_group:
         dist.destroy_process_group()
+    return out if rank == 0 else {"ok": bool(ok), "world": world, "rank": rank, "max_abs_diff": max_abs, "grad_norm": gn}
+
+
+def check_sp():
+    """`seq_parallel` = world ranks share every packed row (slices of the same micro-batch, all-gathered K / V, local loss
+    shift)  ==  one learner running the whole rows with the slice-leading labels masked (a slice's first token has no
+    predecessor on its rank, so sequence parallelism never scores it -- reference rl/__init__.py:207-212 on make_slices)."""
+    import os
+    import torch.distributed as dist
+    from pipelinerl_b200.finetune.optim import ShardedFusedAdamW
+    dev = torch.device(f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}")
+    torch.cuda.set_device(dev)
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = ModelConfig(vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2, num_q_heads=4, num_kv_heads=2)
+    micro, T = 2, 768
+    rcfg = RLConfig(batch_size=micro * 3)
+    batches = [synthetic_batch(cfg, T, 3, dev, 17 + i) for i in range(micro)]
+    for b in batches:
+        b.input_ids %= cfg.vocab_size
+        b.labels = torch.where(b.labels >= 0, b.input_ids, b.labels)
+        b.old_logprobs.fill_(-6.9)
+        b.ref_logprobs.fill_(-6.9)
+
+    def run(opt_factory, items, group=None):
+        model = NativeQwen2(cfg, dev, seed=5)
+        opt = opt_factory(model)
+        model.bind(opt)
+        opt.zero_grad()
+        losses = []
+        for b in items:
+            loss, _ = rl_step(model, b, 0, 10, rcfg, seq_parallel_group=group)
+            loss.backward()
+            losses.append(float(loss))
+        gn = float(opt.step())
+        torch.cuda.synchronize()
+        return opt.shadow_bf16.clone(), gn, opt, sum(losses)
+    n_slices = max(world, 2)
+    masked = []
+    for b in batches:
+        m = b.make_slices(1)[0]
+        m.labels = b.labels.clone()
+        for r in range(1, n_slices):
+            m.labels[:, r * (T // n_slices)] = -100
+        masked.append(m)
+    ref, gn_ref, _, loss_ref = run(lambda m: FusedAdamW(m.named_parameters(), lr=1e-3, weight_decay=0.01, max_grad_norm=0.3,
+                                                        grad_dtype=torch.float32), masked)
+    if world == 1:
+        return {"ok": True, "world": 1, "note": "single process: nothing to compare"}
+    slices = [b.make_slices(world)[rank] for b in batches]
+    got, gn, opt, loss_part = run(lambda m: ShardedFusedAdamW(m.named_parameters(), lr=1e-3, weight_decay=0.01, max_grad_norm=0.3,
+                                                              grad_accum_fp32=True), slices, group=dist.group.WORLD)
+    lt = torch.tensor([loss_part], dtype=torch.float64, device=dev)
+    dist.all_reduce(lt)
+    same = (got == ref).float().mean().item()
+    max_abs = (got.float() - ref.float()).abs().max().item()
+    gathered = [torch.empty_like(got) for _ in range(world)]
+    dist.all_gather(gathered, got)
+    identical = all(torch.equal(g, gathered[0]) for g in gathered)
+    loss_ok = abs(float(lt) - loss_ref) <= 2e-3 * max(1.0, abs(loss_ref))
+    ok = identical and loss_ok and same > 0.98 and max_abs <= 2.5e-3 + 2 ** -7 * ref.float().abs().max().item() and abs(gn - gn_ref) <= 1e-2 * gn_ref
+    out = {"ok": bool(ok), "check": "sequence_parallel", "world": world, "ranks_bit_identical": bool(identical),
+           "params_equal_to_single_learner": round(same, 5), "max_abs_diff": max_abs, "grad_norm": gn, "grad_norm_single": gn_ref,
+           "loss_sum_over_ranks": float(lt), "loss_single": loss_ref}
+    dist.barrier()
+    opt.close()
+    dist.destroy_process_group()
     return out if rank == 0 else {"ok": bool(ok), "world": world, "rank": rank, "max_abs_diff": max_abs, "grad_norm": gn}
 
 
