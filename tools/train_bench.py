@@ -45,7 +45,7 @@ def synthetic_batch(cfg, T, n_samples, dev, seed):
 
 
 def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, warmup=1, layers=0, keep_attn=-1,
-            profile=False, dev=None, log=True, keep_gate_up=-1, distributed=None, fp32_head=True):
+            profile=False, dev=None, log=True, keep_gate_up=-1, distributed=None, fp32_head=True, seq_parallel=1):
     """Run the trainer step and return the result dict (also used by bench.py's `components.trainer_step`).
     Under torchrun (WORLD_SIZE > 1) every rank is a data-parallel learner with its own `micro` micro-batches and the
     optimizer step is the ShardedFusedAdamW exchange (P2P reduce-scatter + AdamW shard + P2P all-gather);
@@ -90,18 +90,28 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
     if keep_attn >= 0:
         model.body.keep_attention_layers = keep_attn
     torch.cuda.synchronize()
+    sp = seq_parallel if world > 1 else 1
+    if sp > 1 and sp != world:
+        raise ValueError("--seq-parallel must equal the number of ranks (one sequence-parallel group)")
+    local_tokens = tokens // sp
     if keep_gate_up < 0:   # auto: spend the HBM left after the kept attention halves + 20 GB of headroom
         torch.cuda.empty_cache()
         free = torch.cuda.mem_get_info(dev)[0]
-        kept_bytes = tokens * 2 * (model.body.keep_attention_layers * (cfg.qkv_size + cfg.q_size + cfg.hidden_size)
+        kept_bytes = local_tokens * 2 * (model.body.keep_attention_layers * (cfg.qkv_size + cfg.q_size + cfg.hidden_size)
                                    + cfg.num_layers * cfg.hidden_size)
-        per_layer = tokens * 2 * cfg.intermediate_size * 2
+        per_layer = local_tokens * 2 * cfg.intermediate_size * 2
         keep_gate_up = int(max(0, min(model.body.keep_attention_layers, (free - 20e9 - kept_bytes) // per_layer)))
     model.body.keep_gate_up_layers = keep_gate_up
     say(f"model + optimizer state resident: {torch.cuda.memory_allocated() / 1e9:.1f} GB ({time.time() - t0:.1f} s)")
-    n_samples_step = micro * samples_per_row * world
+    dp = world // sp
+    n_samples_step = micro * samples_per_row * dp
     rcfg = RLConfig(batch_size=n_samples_step)   # reference defaults: ppo, kl_coef 0.1, temperature 1.0
-    batches = [synthetic_batch(cfg, tokens, samples_per_row, dev, 100 + rank * micro + i) for i in range(micro)]
+    if sp > 1:   # every rank of the group holds its slice of the SAME rows (PipelineBatchEncoding.make_slices)
+        batches = [synthetic_batch(cfg, tokens, samples_per_row, dev, 100 + i).make_slices(sp)[rank] for i in range(micro)]
+        sp_group = dist.group.WORLD
+    else:
+        batches = [synthetic_batch(cfg, tokens, samples_per_row, dev, 100 + rank * micro + i) for i in range(micro)]
+        sp_group = None
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     launches0 = None
     rec = []
@@ -114,7 +124,7 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
         e[0].record()
         losses = []
         for i, b in enumerate(batches):
-            loss, stats = rl_step(model, b, step, 1000, rcfg)
+            loss, stats = rl_step(model, b, step, 1000, rcfg, seq_parallel_group=sp_group)
             e[2 * i + 1].record()
             loss.backward()
             e[2 * i + 2].record()
@@ -127,11 +137,15 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
         bwd = sum(e[2 * i + 1].elapsed_time(e[2 * i + 2]) for i in range(micro))
         optm = e[2 * micro].elapsed_time(e[-1])
         total = e[0].elapsed_time(e[-1])
-        if world > 1:   # device-timed, max over ranks
+        loss_sum = float(sum(losses))
+        if world > 1:   # device-timed, max over ranks; the loss is the sum of the ranks' parts
             tt = torch.tensor([total, fwd, bwd, optm], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             total, fwd, bwd, optm = tt.tolist()
-        rec.append((total, fwd, bwd, optm, float(sum(losses)), float(gn)))
+            ls = torch.tensor([loss_sum], dtype=torch.float64, device=dev)
+            dist.all_reduce(ls)
+            loss_sum = float(ls)
+        rec.append((total, fwd, bwd, optm, loss_sum, float(gn)))
         say(f"step {step}: {total:.1f} ms (fwd {fwd:.1f} bwd {bwd:.1f} opt {optm:.1f}) loss {rec[-1][4]:.5f} "
             f"grad_norm {rec[-1][5]:.4f} peak {torch.cuda.max_memory_allocated() / 1e9:.1f} GB")
     if profile:
@@ -139,7 +153,7 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
         with tprofile(activities=[ProfilerActivity.CUDA]) as prof:
             opt.zero_grad()
             for b in batches:
-                loss, _ = rl_step(model, b, 0, 1000, rcfg)
+                loss, _ = rl_step(model, b, 0, 1000, rcfg, seq_parallel_group=sp_group)
                 loss.backward()
             opt.step()
             model.after_optimizer_step()
@@ -148,14 +162,14 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
               file=sys.stderr, flush=True)
     timed = rec[warmup:]
     ms = sum(r[0] for r in timed) / len(timed)
-    total_tokens = micro * tokens * world
+    total_tokens = micro * tokens * dp
     c = cfg
     body_params = c.num_layers * (c.qkv_size * c.hidden_size + c.hidden_size * c.q_size + 3 * c.hidden_size * c.intermediate_size)
     head_params = c.vocab_size * c.hidden_size
     per_seg = tokens // samples_per_row
     attn_fwd = 4.0 * c.num_layers * c.num_q_heads * c.head_dim * (per_seg * (per_seg + 1) / 2) * samples_per_row
     # model FLOPs: 6 N per token + causal attention (forward 1x + backward 2x); recompute is NOT counted
-    model_flops = world * micro * (6.0 * (body_params + head_params) * tokens + 3.0 * attn_fwd)
+    model_flops = dp * micro * (6.0 * (body_params + head_params) * tokens + 3.0 * attn_fwd)
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     peak = peaks.get("bf16_tflops_sustained", 1459.7)
     out = {"bench": "trainer_step", "model": "Qwen2.5-7B" if model_name == "7b" else "tiny", "layers": c.num_layers,
@@ -166,7 +180,8 @@ def measure(model_name="7b", tokens=16384, samples_per_row=1, micro=2, steps=2, 
            "opt_ms": round(sum(r[3] for r in timed) / len(timed), 2),
            "model_TFLOPs": round(model_flops / ms / 1e9, 1),
            "mfu_vs_measured_sustained_peak": round(model_flops / ms / 1e9 / peak / world, 4), "peak_TFLOPs": peak,
-           "n_gpus": world, "parallelism": f"dp{world} (ShardedFusedAdamW exchange over NVLink peer memory)" if world > 1 else "single GPU",
+           "n_gpus": world, "parallelism": (f"sp{sp}: the ranks share every packed row (K / V all-gather + dK / dV reduce-scatter per layer), gradients through the ShardedFusedAdamW exchange" if sp > 1 else
+                           f"dp{world} (ShardedFusedAdamW exchange over NVLink peer memory)") if world > 1 else "single GPU",
            "exchange_phase_ms": [round(x, 2) for x in getattr(opt, "last_phase_ms", (0.0, 0.0))],
            "libprl_launches_per_step": (_lib.launch_count() - launches0) // max(1, steps),
            "peak_memory_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1),
@@ -194,6 +209,7 @@ def main():
     ap.add_argument("--keep-attn", type=int, default=-1, help="layers whose attention half is kept for backward (-1 = all)")
     ap.add_argument("--keep-gate-up", type=int, default=-1, help="layers that keep gate_up's output (-1 = as many as fit)")
     ap.add_argument("--profile", action="store_true", help="after the timed steps, print the per-kernel CUDA time of one step")
+    ap.add_argument("--seq-parallel", type=int, default=1, help="all ranks share every packed row (must equal the rank count)")
     ap.add_argument("--check", action="store_true", help="tiny model: DP result == single-learner result on all micro-batches")
     ap.add_argument("--check-sp", action="store_true", help="tiny model: sequence-parallel ranks == single learner on the whole rows")
     a = ap.parse_args()
@@ -205,7 +221,7 @@ def main():
         print(json.dumps(check_dp()))
         return
     res = measure(a.model, a.tokens, a.samples_per_row, a.micro, a.steps, a.warmup, a.layers, a.keep_attn, a.profile,
-                  keep_gate_up=a.keep_gate_up)
+                  keep_gate_up=a.keep_gate_up, seq_parallel=a.seq_parallel)
     if int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps(res))
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
