@@ -455,6 +455,7 @@ int prl_debug_tmem_read_bench(int32_t iters, int32_t warps, int64_t* out3_device
 int prl_attn_debug_timing(int64_t* out20_device);
 /* likewise for the generation-4 dQ backward kernel (16 int64; NULL = off) */
 int prl_attn_debug_bwd_timing(int64_t* out16_device);
+int prl_attn_debug_bwd_timing_dkdv(int64_t* out16_device);
 int prl_debug_mma_bench(int32_t mode, int32_t iters, int64_t* out2_device, prl_stream_t stream);
 /* Sampling with in-kernel logprob capture: id ~ softmax(logits/T) (Gumbel-max, counter-based RNG on
  * (seed, step, row, vocab id)) or argmax when greedy; logprob = log_softmax(logits/T)[id]. */

@@ -170,6 +170,7 @@ _SIGNATURES = {
     "prl_debug_tmem_read_bench": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "prl_attn_debug_timing": (C.c_int, [C.c_void_p]),
     "prl_attn_debug_bwd_timing": (C.c_int, [C.c_void_p]),
+    "prl_attn_debug_bwd_timing_dkdv": (C.c_int, [C.c_void_p]),
     "prl_debug_mma_bench": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "prl_attn_varlen_bwd_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "prl_attn_varlen_fwd_kv": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,

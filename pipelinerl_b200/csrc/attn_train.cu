@@ -719,6 +719,7 @@ __device__ __forceinline__ void group_bar256(int g) {
   else asm volatile("bar.sync 2, 256;" ::: "memory");
 }
 
+template <bool kTimed>
 __global__ void __launch_bounds__(kThreadsB4, 1)
 attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                       const __grid_constant__ CUtensorMap tm_kv, BwdParams p) {
@@ -804,9 +805,12 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     {   // the whole warp, converged: one elected lane issues each tcgen05 instruction (ptx::elect_one)
       constexpr uint32_t idesc_t = ptx::make_idesc_bf16_f32(128, 64);
       constexpr uint32_t idesc_acc = ptx::make_idesc_bf16_f32(128, kD) | (1u << 16);
+      long long w_q = 0;
       auto issue_sdp = [&](int it) {
         const int st = it % kQStages4, s = it & 1;
+        const long long cq = clock64();
         ptx::mbar_wait(bar(1 + st), (uint32_t)((it / kQStages4) & 1));
+        if (kTimed) w_q += clock64() - cq;
         // S^T[s] / dP^T[s] hold P^T / dS^T of step it - 2 until its dV / dK UMMAs, issued earlier by this thread, have read
         // them: UMMAs of one thread execute in issue order
         ptx::tc_fence_after_sync();
@@ -827,12 +831,17 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           ptx::tc_commit(bar(9 + s));
         }
       };
+      const bool timed = kTimed && p.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      long long w_pds = 0;
+      const long long w0 = clock64();
       ptx::mbar_wait(bar(0), 0);
       issue_sdp(0);
       for (int it = 0; it < n_it; ++it) {
         if (it + 1 < n_it) issue_sdp(it + 1);
         const int st = it % kQStages4, s = it & 1;
+        const long long c0 = clock64();
         ptx::mbar_wait(bar(11 + s), (uint32_t)((it >> 1) & 1));         // P^T[s], dS^T[s] are in TMEM
+        if (kTimed) w_pds += clock64() - c0;
         ptx::tc_fence_after_sync();
         const uint32_t q_addr = q_ring + (uint32_t)(st * kQSlot);
         if (ptx::elect_one()) {
@@ -854,6 +863,7 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       if (ptx::elect_one()) {
         ptx::tc_commit(bar(13));
       }
+      if (timed && lane == 0) { p.timing[8] = w_q; p.timing[9] = w_pds; p.timing[12] = clock64() - w0; p.timing[13] = n_it; }
     }
     __syncwarp();
   } else {
@@ -882,18 +892,27 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const int n_own = n_it > g ? (n_it - g + 1) >> 1 : 0;
     if (n_own > 0 && mwhich < 3) mg[mwhich * 64 + mc] = fetch(u_first + g);
     float nxt = (g + 2 < n_it) ? fetch(u_first + g + 2) : 0.f;
+    group_bar256(g);                             // metadata of own step 0 is visible to the whole group
 
+    const bool timed = kTimed && p.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
+    long long tph[5] = {0, 0, 0, 0, 0};
     for (int j = 0; j < n_own; ++j) {
       const int it = 2 * j + g;
       const int u = u_first + it;
-      group_bar256(g);                           // the group is done with own step j - 1; metadata of step j is visible
+      const long long tk0 = clock64();
       const float* mb = mg + (j & 1) * 192;
+      const long long tk1 = clock64();
+      ptx::mbar_wait(bar(9 + g), (uint32_t)(j & 1));
+      ptx::tc_fence_after_sync();
+      // No barrier inside the loop.  S^T / dP^T of own step j exist only after dV / dK of own step j - 1 were issued, i.e. after
+      // EVERY warp of the group arrived at the end of step j - 1: (a) nobody reads the metadata buffer of step j - 1 any more,
+      // so it may be overwritten with step j + 1's now; (b) the writes made during step j - 1 for step j happened before those
+      // arrivals (release) and this wait (acquire) -- they are visible.
       if (it + 2 < n_it) {
         if (mwhich < 3) mg[((j + 1) & 1) * 192 + mwhich * 64 + mc] = nxt;
         nxt = (it + 4 < n_it) ? fetch(u + 4) : 0.f;            // global load in flight across a whole step
       }
-      ptx::mbar_wait(bar(9 + g), (uint32_t)(j & 1));
-      ptx::tc_fence_after_sync();
+      const long long tk2 = clock64();
       uint32_t sv[32], dv[32];
       ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(g * 64 + c0), sv);
       ptx::tmem_ld_wait();
@@ -918,6 +937,7 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           if (kpos > q0.w) pe[e + 3] = 0.f;
         }
       }
+      const long long tk3 = clock64();
       ptx::tmem_ld_wait();
       uint32_t pp[16], dd[16];
 #pragma unroll
@@ -935,6 +955,14 @@ attn_bwd_dkdv4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar(11 + g));
+      if (kTimed) {
+        const long long tk4 = clock64();
+        tph[0] += tk1 - tk0; tph[1] += tk2 - tk1; tph[2] += tk3 - tk2; tph[3] += tk4 - tk3;
+      }
+    }
+    if (timed) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) p.timing[e] = tph[e];
     }
 
     // ---- epilogue: 32 head-dim columns of this key's dV and dK rows ----
@@ -1240,12 +1268,20 @@ using namespace prl;
 
 namespace prl { namespace { int g_bwd_generation = [] { const char* e = getenv("PRL_ATTN_BWD"); return (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 4; }(); } }
 
-namespace prl { namespace { long long* g_bwd_timing = nullptr; } }
+namespace prl { namespace { long long* g_bwd_timing = nullptr; int g_bwd_timing_kernel = 1; } }
 // measurement only: per-phase cycle sums of CTA (0,0,0) of the generation-4 dQ kernel.  [0..3] one softmax warp: wait S |
 // tcgen05.ld + exp2 | wait dP | tcgen05.ld + dS + tcgen05.st + arrive; [8..11] MMA warp waiting for K | S drained | dS | V,
 // [12] MMA warp total, [13] steps.  NULL switches it off.
 extern "C" int prl_attn_debug_bwd_timing(int64_t* out16_device) {
   prl::g_bwd_timing = (long long*)out16_device;
+  prl::g_bwd_timing_kernel = 1;
+  return PRL_OK;
+}
+// same for the dK/dV kernel: [0..3] one softmax warp: group barrier | wait S^T, dP^T | tcgen05.ld + exp2 | dS + tcgen05.st +
+// arrive; [8] MMA warp waiting for Q / dO, [9] for P^T / dS^T, [12] MMA warp total, [13] sub-steps
+extern "C" int prl_attn_debug_bwd_timing_dkdv(int64_t* out16_device) {
+  prl::g_bwd_timing = (long long*)out16_device;
+  prl::g_bwd_timing_kernel = 0;
   return PRL_OK;
 }
 
@@ -1305,8 +1341,14 @@ extern "C" int prl_attn_varlen_bwd(const void* qkv, int64_t qkv_stride, int32_t 
     dim3 grid((unsigned)((max_seg_len + 127) / 128), (unsigned)n_kv, (unsigned)n_seg);
     if (g_bwd_generation == 4) {
       static SmemAttr attr4 = {};
-      PRL_CUDA(ensure_smem(attn_bwd_dkdv4_kernel, kSmemDkdv4, attr4));
-      attn_bwd_dkdv4_kernel<<<grid, kThreadsB4, (size_t)kSmemDkdv4, stream>>>(tq, tdo, tkv, p);
+      if (g_bwd_timing != nullptr && g_bwd_timing_kernel == 0) {
+        static SmemAttr attr4t = {};
+        PRL_CUDA(ensure_smem(attn_bwd_dkdv4_kernel<true>, kSmemDkdv4, attr4t));
+        attn_bwd_dkdv4_kernel<true><<<grid, kThreadsB4, (size_t)kSmemDkdv4, stream>>>(tq, tdo, tkv, p);
+      } else {
+        PRL_CUDA(ensure_smem(attn_bwd_dkdv4_kernel<false>, kSmemDkdv4, attr4));
+        attn_bwd_dkdv4_kernel<false><<<grid, kThreadsB4, (size_t)kSmemDkdv4, stream>>>(tq, tdo, tkv, p);
+      }
     } else if (g_bwd_generation == 1) {   // generations 2 and 3 share the dK / dV kernel
       PRL_CUDA(ensure_smem(attn_bwd_dkdv_kernel<false>, kSmemDkdv, attr));
       attn_bwd_dkdv_kernel<false><<<grid, kThreadsB, (size_t)kSmemDkdv, stream>>>(tq, tdo, tkv, p);
@@ -1328,7 +1370,7 @@ extern "C" int prl_attn_varlen_bwd(const void* qkv, int64_t qkv_stride, int32_t 
     dim3 grid((unsigned)(((max_seg_len + p.nq - 1) / p.nq + 1) & ~1), (unsigned)n_kv, (unsigned)n_seg);
     if (g_bwd_generation == 4) {
       static SmemAttr attr4 = {};
-      if (g_bwd_timing != nullptr) {
+      if (g_bwd_timing != nullptr && g_bwd_timing_kernel == 1) {
         static SmemAttr attr4t = {};
         PRL_CUDA(ensure_smem(attn_bwd_dq4_kernel<true>, kSmemDq4, attr4t));
         attn_bwd_dq4_kernel<true><<<grid, kThreadsB4, (size_t)kSmemDq4, stream>>>(tq, tdo, tkv, p);
@@ -1402,8 +1444,8 @@ extern "C" int prl_attn_varlen_bwd_kv(const void* q, int64_t q_stride, int32_t T
     if (rc) return rc;
     dim3 grid((unsigned)((max_kv_len + 127) / 128), (unsigned)n_kv, (unsigned)n_seg);
     static SmemAttr attr = {};
-    PRL_CUDA(ensure_smem(attn_bwd_dkdv4_kernel, kSmemDkdv4, attr));
-    attn_bwd_dkdv4_kernel<<<grid, kThreadsB4, (size_t)kSmemDkdv4, stream>>>(tq, tdo, tkv, p);
+    PRL_CUDA(ensure_smem(attn_bwd_dkdv4_kernel<false>, kSmemDkdv4, attr));
+    attn_bwd_dkdv4_kernel<false><<<grid, kThreadsB4, (size_t)kSmemDkdv4, stream>>>(tq, tdo, tkv, p);
     PRL_LAUNCH_CHECK();
   }
   {

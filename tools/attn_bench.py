@@ -108,6 +108,19 @@ def main():
                                                            enumerate(["wait_S", "ld_exp", "wait_dP", "ld_dS_st_arrive"])},
                           "mma_warp_cycles_per_step": {n: round(v[8 + i] / steps, 1) for i, n in
                                                        enumerate(["wait_K", "wait_S_drained", "wait_dS", "wait_V", "total"])}}), flush=True)
+        t16.zero_()
+        _l0.check(lib.prl_attn_debug_bwd_timing_dkdv(t16.data_ptr()))
+        o.attn_bwd(qkv, out, d_out, lse, st, ln, L, n_q, n_kv, D)
+        torch.cuda.synchronize()
+        _l0.check(lib.prl_attn_debug_bwd_timing(None))
+        v = t16.tolist()
+        steps = max(v[13], 1)
+        own = max((steps + 1) // 2, 1)
+        print(json.dumps({"bench": "attn_bwd_dkdv4_phases", "sub_steps_of_cta0": v[13],
+                          "softmax_warp_cycles_per_own_step": {n: round(v[i] / own, 1) for i, n in
+                                                               enumerate(["group_barrier", "wait_ST_dPT", "ld_exp", "dS_st_arrive"])},
+                          "mma_warp_cycles_per_sub_step": {"wait_Q_dO": round(v[8] / steps, 1), "wait_PT_dST": round(v[9] / steps, 1),
+                                                           "total": round(v[12] / steps, 1)}}), flush=True)
         return
     if a.ours_only:
         for _ in range(2):
