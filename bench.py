@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="N >= 2: skip the inference + learner split run")
     ap.add_argument("--no-vllm", action="store_true", help="N = 1: skip the vLLM 0.22 A/B subprocess")
+    ap.add_argument("--no-seq-parallel", action="store_true", help="N = 2: skip the sequence-parallel trainer step")
     ap.add_argument("--no-rollout", action="store_true", help="N = 1: skip the full-rollout run through the plugin API")
     ap.add_argument("--rollout-tokens", type=int, default=8192, help="max_tokens of the full-rollout component")
     ap.add_argument("--splits", default="", help="learner counts of the split runs, e.g. '2,4' (default: by N)")
@@ -310,6 +311,11 @@ def run_ours(args):
         gc.collect()
         torch.cuda.empty_cache()
         out.setdefault("components", {})["pipeline"] = run_pipeline_splits(args, world, rank, out)
+        if world == 2 and not args.no_seq_parallel:
+            # the sequence-parallel learner on the same two GPUs: both ranks share every 16384-token row
+            sp = run_seq_parallel_trainer(world, rank)
+            if rank == 0:
+                out["components"]["trainer_step_seq_parallel_2"] = sp
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -363,6 +369,32 @@ def run_pipeline_splits(args, world, rank, headline):
             results[key] = res
         dist.barrier()          # the parents stay in step between splits
     return results if rank == 0 else None
+
+
+def run_seq_parallel_trainer(world, rank):
+    """All ranks (N = 2).  tools/train_bench.py --seq-parallel 2 in child processes with a fresh rendezvous, like the splits:
+    the 7B trainer step of `components.trainer_step` (2 x 16384-token rows per optimizer step) with the two ranks holding
+    half of every row each (K / V all-gather + dK / dV reduce-scatter per layer, sharded AdamW exchange)."""
+    import torch.distributed as dist
+    env = {k_: v for k_, v in os.environ.items() if not k_.startswith("TORCHELASTIC_")}
+    env.update(MASTER_PORT=str(int(os.environ.get("MASTER_PORT", "29500")) + 171), NCCL_DEBUG="WARN", NCCL_DEBUG_FILE="/dev/stderr")
+    cmd = [sys.executable, str(ROOT / "tools" / "train_bench.py"), "--seq-parallel", str(world), "--steps", "2", "--warmup", "1"]
+    t0 = time.time()
+    try:
+        done = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
+        lines = [l for l in done.stdout.splitlines() if l.startswith("{")]
+        if done.returncode == 0 and (lines or rank != 0):
+            res = json.loads(lines[-1]) if lines else {}
+        else:
+            res = {"error": f"rank {rank}: rc={done.returncode}: {(done.stderr or done.stdout)[-400:]}"}
+    except subprocess.TimeoutExpired:
+        res = {"error": f"rank {rank}: timed out after 420 s"}
+    except Exception as e:  # noqa: BLE001
+        res = {"error": f"rank {rank}: {type(e).__name__}: {str(e)[:300]}"}
+    if isinstance(res, dict):
+        res["child_process_wall_s"] = round(time.time() - t0, 1)
+    dist.barrier()
+    return res if rank == 0 else None
 
 
 def run_tool(argv, timeout_s):
