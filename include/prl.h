@@ -130,6 +130,17 @@ int prl_pg_loss_fwd_bwd(const prl_pg_batch* batch, const prl_pg_config* cfg,
                         double* stats, int32_t* nonfinite,
                         void* workspace, size_t workspace_bytes, prl_stream_t stream);
 
+/* GSPO under sequence parallelism (rl/utils.py:194-206: the per-segment sums are all-reduced over the group).
+ * Step 1 writes this rank's sums over its slice, seg_sums[n_segments][4] doubles = (sum log-ratio new/old, sum advantage,
+ * token count, sum token weight); the caller SUM-all-reduces the array over the group.  Step 2 is prl_pg_loss_fwd_bwd with
+ * those totals given; seg_local_count[n_segments] (this rank's token counts, or NULL) scales every segment's loss term to
+ * this rank's share so that the ranks' losses add up to the loss of the whole row. */
+int prl_pg_gspo_segment_sums(const prl_pg_batch* batch, const prl_pg_config* cfg, double* seg_sums, prl_stream_t stream);
+int prl_pg_loss_fwd_bwd_seg(const prl_pg_batch* batch, const prl_pg_config* cfg, float* loss, float* dloss_dlogprob,
+                            float* dloss_dentropy, double* stats, int32_t* nonfinite, void* workspace,
+                            size_t workspace_bytes, const double* seg_sums, const double* seg_local_count,
+                            prl_stream_t stream);
+
 /* ======================================================================= *
  * Hot path (2b, generic-model variant): logprob tail from materialised logits
  *   replaces pipelinerl/finetune/rl/__init__.py:207-233 (logits/T, gather,

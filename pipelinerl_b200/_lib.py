@@ -116,6 +116,9 @@ _SIGNATURES = {
     "prl_pg_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "prl_pg_loss_fwd_bwd": (C.c_int, [C.POINTER(PgBatch), C.POINTER(PgConfig), C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "prl_pg_gspo_segment_sums": (C.c_int, [C.POINTER(PgBatch), C.POINTER(PgConfig), C.c_void_p, C.c_void_p]),
+    "prl_pg_loss_fwd_bwd_seg": (C.c_int, [C.POINTER(PgBatch), C.POINTER(PgConfig), C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "prl_logprob_tail_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "prl_logprob_tail_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_float,

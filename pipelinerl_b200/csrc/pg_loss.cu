@@ -97,7 +97,8 @@ __device__ __forceinline__ void gspo_segment_terms(const SegSums& ss, const prl_
 __global__ void __launch_bounds__(kThreads) pg_loss_kernel(prl_pg_batch b, prl_pg_config c, float* __restrict__ loss_out,
                                                           float* __restrict__ dlp, float* __restrict__ dent,
                                                           double* __restrict__ stats, int* __restrict__ nonfinite,
-                                                          Workspace* ws, Partial* partials, const SegSums* seg) {
+                                                          Workspace* ws, Partial* partials, const SegSums* seg,
+                                                          const double* __restrict__ seg_local_count) {
   const int64_t n = b.T - 1;
   float acc[A_NSUM];
   float mx[M_NMM], mn[M_NMM];
@@ -264,7 +265,11 @@ __global__ void __launch_bounds__(kThreads) pg_loss_kernel(prl_pg_batch b, prl_p
       for (int s = 0; s < b.n_segments; ++s) {
         float lt, gc, si;
         gspo_segment_terms(seg[s], c, lt, gc, si);
-        tot += (double)lt;
+        // sequence parallelism: `seg` holds the sums over ALL ranks; this rank reports the share of a segment's loss that
+        // its own tokens carry, so that the ranks' losses add up to the loss of the whole row
+        double share = 1.0;
+        if (seg_local_count != nullptr) share = seg[s].tok_count > 0 ? seg_local_count[s] / seg[s].tok_count : 0.0;
+        tot += (double)lt * share;
       }
     }
     f_gspo = tot;
@@ -363,7 +368,56 @@ extern "C" int prl_pg_loss_fwd_bwd(const prl_pg_batch* batch, const prl_pg_confi
     }
   }
   pg_loss_kernel<<<blocks, kThreads, 0, stream>>>(*batch, *cfg, loss, dloss_dlogprob, dloss_dentropy, stats,
-                                                 nonfinite, ws, partials, seg);
+                                                 nonfinite, ws, partials, seg, nullptr);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
+// ---- GSPO under sequence parallelism (reference rl/utils.py:194-206: the per-segment sums are all-reduced over the group) ----
+// Step 1: this rank's per-segment sums of its slice, seg_sums[n_segments][4] = (sum log-ratio, sum advantage, token count,
+// sum token weight) as doubles.  The caller all-reduces (SUM) the array over the group and keeps a copy of column 2.
+extern "C" int prl_pg_gspo_segment_sums(const prl_pg_batch* batch, const prl_pg_config* cfg, double* seg_sums,
+                                        prl_stream_t stream_) {
+  PRL_CHECK_ARG(batch && cfg && seg_sums, "prl_pg_gspo_segment_sums: NULL argument");
+  PRL_CHECK_ARG(cfg->policy_loss == PRL_LOSS_GSPO && batch->segment_ids != nullptr && batch->n_segments >= 1,
+                "prl_pg_gspo_segment_sums: needs the GSPO loss, segment_ids and n_segments >= 1");
+  static_assert(sizeof(SegSums) == 4 * sizeof(double), "SegSums is the 4-double row the ABI documents");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PRL_CUDA(cudaMemsetAsync(seg_sums, 0, sizeof(SegSums) * (size_t)batch->n_segments, stream));
+  const int64_t n = batch->T - 1;
+  if (n > 0) {
+    int blocks = (int)((n + kThreads - 1) / kThreads);
+    const int cap = num_sms() * 8 < kMaxBlocks ? num_sms() * 8 : kMaxBlocks;
+    if (blocks > cap) blocks = cap;
+    gspo_segment_kernel<<<blocks, kThreads, 0, stream>>>(*batch, *cfg, (SegSums*)seg_sums);
+    PRL_LAUNCH_CHECK();
+  }
+  return PRL_OK;
+}
+
+// Step 2: prl_pg_loss_fwd_bwd with the segment sums GIVEN (the group's totals) instead of computed; `seg_local_count`
+// (this rank's token counts, [n_segments] doubles) scales each segment's loss term to this rank's share.
+extern "C" int prl_pg_loss_fwd_bwd_seg(const prl_pg_batch* batch, const prl_pg_config* cfg, float* loss,
+                                       float* dloss_dlogprob, float* dloss_dentropy, double* stats, int32_t* nonfinite,
+                                       void* workspace, size_t workspace_bytes, const double* seg_sums,
+                                       const double* seg_local_count, prl_stream_t stream_) {
+  PRL_CHECK_ARG(batch && cfg && loss && stats && nonfinite && workspace && seg_sums, "prl_pg_loss_fwd_bwd_seg: NULL argument");
+  PRL_CHECK_ARG(cfg->policy_loss == PRL_LOSS_GSPO && batch->segment_ids != nullptr && batch->n_segments >= 1,
+                "prl_pg_loss_fwd_bwd_seg: needs the GSPO loss, segment_ids and n_segments >= 1");
+  PRL_CHECK_ARG(batch->T >= 1, "prl_pg_loss_fwd_bwd_seg: T must be >= 1");
+  PRL_CHECK_ARG(cfg->group_normalization || cfg->batch_size > 0.f, "prl_pg_loss_fwd_bwd_seg: batch_size must be > 0 unless group_normalization");
+  PRL_CHECK_ARG(workspace_bytes >= prl_pg_workspace_bytes(0), "prl_pg_loss_fwd_bwd_seg: workspace too small");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  Workspace* ws = (Workspace*)workspace;
+  Partial* partials = (Partial*)((char*)workspace + sizeof(Workspace));
+  const int64_t n = batch->T - 1;
+  int blocks = (int)((n + kThreads - 1) / kThreads);
+  if (blocks < 1) blocks = 1;
+  const int cap = num_sms() * 8 < kMaxBlocks ? num_sms() * 8 : kMaxBlocks;
+  if (blocks > cap) blocks = cap;
+  PRL_CUDA(cudaMemsetAsync(ws, 0, sizeof(Workspace), stream));
+  pg_loss_kernel<<<blocks, kThreads, 0, stream>>>(*batch, *cfg, loss, dloss_dlogprob, dloss_dentropy, stats, nonfinite, ws,
+                                                 partials, (const SegSums*)seg_sums, seg_local_count);
   PRL_LAUNCH_CHECK();
   return PRL_OK;
 }

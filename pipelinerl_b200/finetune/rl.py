@@ -151,9 +151,22 @@ class _PgLoss(torch.autograd.Function):
         b.num_sequences = int(meta["num_sequences"])
         b.sentinel = int(bool(meta["sentinel"]))
         ws = _pg_workspace(dev, b.n_segments)
-        _lib.check(lib.prl_pg_loss_fwd_bwd(C.byref(b), C.byref(cfg_struct), loss.data_ptr(), dlp.data_ptr(),
-                                           dent.data_ptr(), stats.data_ptr(), flags.data_ptr(), ws.data_ptr(),
-                                           ws.numel(), _lib.stream_ptr()))
+        sp_group = meta.get("seq_parallel_group")
+        if sp_group is not None and cfg_struct.policy_loss == _lib.LOSS_IDS["gspo"] and b.n_segments > 0:
+            # GSPO is a per-SEQUENCE objective and the sequence is spread over the group: all-reduce the per-segment sums
+            # (reference rl/utils.py:194-206), then every rank differentiates the whole-sequence terms w.r.t. ITS tokens
+            import torch.distributed as dist
+            seg = torch.empty(b.n_segments, 4, dtype=torch.float64, device=dev)
+            _lib.check(lib.prl_pg_gspo_segment_sums(C.byref(b), C.byref(cfg_struct), seg.data_ptr(), _lib.stream_ptr()))
+            local_count = seg[:, 2].contiguous()
+            dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=sp_group)
+            _lib.check(lib.prl_pg_loss_fwd_bwd_seg(C.byref(b), C.byref(cfg_struct), loss.data_ptr(), dlp.data_ptr(),
+                                                   dent.data_ptr(), stats.data_ptr(), flags.data_ptr(), ws.data_ptr(),
+                                                   ws.numel(), seg.data_ptr(), local_count.data_ptr(), _lib.stream_ptr()))
+        else:
+            _lib.check(lib.prl_pg_loss_fwd_bwd(C.byref(b), C.byref(cfg_struct), loss.data_ptr(), dlp.data_ptr(),
+                                               dent.data_ptr(), stats.data_ptr(), flags.data_ptr(), ws.data_ptr(),
+                                               ws.numel(), _lib.stream_ptr()))
         ctx.save_for_backward(dlp, dent)
         ctx.has_entropy = entropy is not None
         ctx.mark_non_differentiable(stats, flags)
@@ -207,9 +220,6 @@ def rl_step(model, batch: PipelineBatchEncoding, current_step: int, max_step: in
         # The batch is this rank's slice of a packed row (PipelineBatchEncoding.make_slices); like the reference, logits
         # and labels are shifted INSIDE the slice (rl/__init__.py:207-212 on the sliced batch), so the last token of a
         # slice predicts nothing.  Everything but attention is token-local; the model exchanges K / V itself.
-        if config.policy_loss == "gspo":
-            raise NotImplementedError("gspo with seq_parallel_group: the per-segment sums would have to be all-reduced "
-                                      "inside the fused loss tail (reference rl/utils.py:194-206); use ppo / reinforce")
         if not hasattr(model, "set_sequence_parallel"):
             raise NotImplementedError("seq_parallel_group needs a model that exchanges K / V over the group "
                                       "(pipelinerl_b200.learner_model.NativeQwen2)")
@@ -262,7 +272,8 @@ def rl_step(model, batch: PipelineBatchEncoding, current_step: int, max_step: in
                 row["segment_ids"] = batch.segment_ids[r].contiguous()
                 # shape-only upper bound on max(segment_ids)+1: no device sync (empty segments are inert)
                 n_seg = int(batch.seq_boundaries.numel()) - 1 if batch.seq_boundaries is not None else L
-        meta = {"T": L, "n_segments": n_seg, "num_sequences": B, "sentinel": batch.sentinel}
+        meta = {"T": L, "n_segments": n_seg, "num_sequences": B, "sentinel": batch.sentinel,
+                "seq_parallel_group": seq_parallel_group}
         loss_r, stats_r, flags_r = _PgLoss.apply(new_lp, ent, row, cfg_struct, meta)
         total = loss_r if total is None else total + loss_r
         stat_parts.append(stats_r)

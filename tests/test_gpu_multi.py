@@ -66,15 +66,17 @@ def test_two_gpu_native_learners_match_single_learner():
     assert outs and all(o["ok"] for o in outs), outs
 
 
+@pytest.mark.parametrize("policy_loss", ["ppo", "gspo"])
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_sequence_parallel_learner_matches_single_learner():
+def test_two_gpu_sequence_parallel_learner_matches_single_learner(policy_loss):
     """Two ranks share every packed row (rl_step(seq_parallel_group=...): slices of the same micro-batch, K / V
     all-gathered per layer, dK / dV reduce-scattered): summed loss, gradient norm and updated parameters equal one learner
-    running the whole rows (reference: finetune_loop.py:507-517 ring attention over make_slices)."""
+    running the whole rows (reference: finetune_loop.py:507-517 ring attention over make_slices); with GSPO the per-segment
+    sums are all-reduced inside the loss tail (rl/utils.py:194-206)."""
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29587")
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29587", str(ROOT / "tools" / "train_bench.py"),
-                          "--check-sp"], capture_output=True, text=True, env=env, timeout=900)
+                          "--check-sp", "--policy-loss", policy_loss], capture_output=True, text=True, env=env, timeout=900)
     assert res.returncode == 0, res.stderr[-3000:]
     outs = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
     assert outs and all(o["ok"] for o in outs), outs

@@ -208,3 +208,85 @@ def test_rl_step_fused_head_matches_logits_path(cuda_device):
     for n in g0:
         scale = g0[n].abs().max().item() + 1e-12
         assert (g1[n] - g0[n]).abs().max().item() <= 3e-2 * scale, n
+
+
+@pytest.mark.parametrize("sp", [2, 4])
+def test_gspo_under_sequence_parallelism_matches_the_whole_row(cuda_device, sp):
+    """GSPO is a per-sequence objective; with seq_parallel the sequence is spread over the group and the reference
+    all-reduces the per-segment sums (rl/utils.py:194-206).  Here: every slice's prl_pg_gspo_segment_sums, their sum (the
+    all-reduce), then prl_pg_loss_fwd_bwd_seg per slice  ==  prl_pg_loss_fwd_bwd on the whole row with the slice-leading
+    labels masked (a slice's first token has no predecessor on its rank): the slices' losses add up to the row's loss and
+    their gradients are the row's gradient, element for element."""
+    import ctypes as C
+    from pipelinerl_b200 import _lib
+    lib = _lib.load()
+    dev = cuda_device
+    T = 4096
+    g = torch.Generator().manual_seed(11 + sp)
+    cuts = sorted(set([0, T] + torch.randint(1, T, (12,), generator=g).tolist()))
+    seg_ids = torch.cat([torch.full((b - a,), i) for i, (a, b) in enumerate(zip(cuts[:-1], cuts[1:]))]).to(dev)
+    pos = torch.cat([torch.arange(b - a) for a, b in zip(cuts[:-1], cuts[1:])])
+    labels = torch.where(torch.rand(T, generator=g) < 0.6, torch.randint(0, 1000, (T,), generator=g), torch.full((T,), -100))
+    labels[pos == 0] = -100
+    Tl = T // sp
+    for r in range(1, sp):
+        labels[r * Tl] = -100
+    labels = labels.to(dev)
+    new_lp = (-torch.rand(T - 1, generator=g) * 3).to(dev)
+    cols = {"rewards": torch.rand(T, generator=g).round(), "advantages": torch.randn(T, generator=g),
+            "ref_logprobs": -torch.rand(T, generator=g) * 3, "old_logprobs": torch.zeros(T),
+            "group_tokens": torch.full((T,), 37.5), "num_labels": torch.full((T,), 9.0),
+            "overflow": (torch.rand(T, generator=g) < 0.2).float()}
+    cols["old_logprobs"][1:] = new_lp.cpu() + 0.05 * torch.randn(T - 1, generator=g)
+    cols = {k: v.to(dev) for k, v in cols.items()}
+    n_seg = len(cuts) - 1
+    c = _lib.PgConfig()
+    c.policy_loss = _lib.LOSS_IDS["gspo"]
+    c.use_advantages = 1
+    c.overlong_filtering = 1
+    c.epsilon_low, c.epsilon_high = 0.03, 0.04
+    c.clamp_log_ratio_ref_new_value = 1.0
+    c.kl_coef = 0.07
+    c.batch_size = 11.0
+
+    def pg_batch(a, b):
+        pb = _lib.PgBatch()
+        pb.T = b - a
+        keep = [new_lp[a:b - 1].contiguous(), labels[a:b].contiguous(), seg_ids[a:b].contiguous()]
+        pb.new_logprobs, pb.labels, pb.segment_ids = keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr()
+        for k, v in cols.items():
+            keep.append(v[a:b].contiguous())
+            setattr(pb, k, keep[-1].data_ptr())
+        pb.n_segments = n_seg
+        pb.num_sequences = 1
+        return pb, keep
+
+    def outputs(n):
+        return (torch.zeros(1, device=dev), torch.zeros(max(n - 1, 0), device=dev), torch.zeros(32, dtype=torch.float64, device=dev),
+                torch.zeros(1, dtype=torch.int32, device=dev))
+    ws = torch.zeros(int(lib.prl_pg_workspace_bytes(n_seg)), dtype=torch.uint8, device=dev)
+    full, keep_full = pg_batch(0, T)
+    loss_f, dlp_f, stats_f, flags_f = outputs(T)
+    _lib.check(lib.prl_pg_loss_fwd_bwd(C.byref(full), C.byref(c), loss_f.data_ptr(), dlp_f.data_ptr(), None, stats_f.data_ptr(),
+                                       flags_f.data_ptr(), ws.data_ptr(), ws.numel(), None))
+    slices = [pg_batch(r * Tl, (r + 1) * Tl) for r in range(sp)]
+    sums = []
+    for pb, _ in slices:
+        s = torch.empty(n_seg, 4, dtype=torch.float64, device=dev)
+        _lib.check(lib.prl_pg_gspo_segment_sums(C.byref(pb), C.byref(c), s.data_ptr(), None))
+        sums.append(s)
+    total = torch.stack(sums).sum(0)
+    loss_sum = 0.0
+    for r, (pb, _) in enumerate(slices):
+        loss_r, dlp_r, stats_r, flags_r = outputs(Tl)
+        local = sums[r][:, 2].contiguous()
+        _lib.check(lib.prl_pg_loss_fwd_bwd_seg(C.byref(pb), C.byref(c), loss_r.data_ptr(), dlp_r.data_ptr(), None, stats_r.data_ptr(),
+                                               flags_r.data_ptr(), ws.data_ptr(), ws.numel(), total.data_ptr(), local.data_ptr(), None))
+        torch.cuda.synchronize()
+        loss_sum += loss_r.item()
+        a = r * Tl
+        assert torch.allclose(dlp_r, dlp_f[a:a + Tl - 1], rtol=1e-6, atol=1e-12), f"slice {r}: gradient differs from the whole row's"
+        if r + 1 < sp:
+            assert dlp_f[a + Tl - 1].item() == 0.0        # the position that would score the next slice's first token
+    assert abs(loss_sum - loss_f.item()) <= 1e-5 * max(1.0, abs(loss_f.item())), (loss_sum, loss_f.item())
+    assert abs(loss_f.item()) > 1e-3                      # the case is not degenerate

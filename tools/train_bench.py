@@ -211,11 +211,12 @@ def main():
     ap.add_argument("--profile", action="store_true", help="after the timed steps, print the per-kernel CUDA time of one step")
     ap.add_argument("--seq-parallel", type=int, default=1, help="all ranks share every packed row (must equal the rank count)")
     ap.add_argument("--check", action="store_true", help="tiny model: DP result == single-learner result on all micro-batches")
+    ap.add_argument("--policy-loss", default="ppo", help="--check-sp: ppo / reinforce / gspo")
     ap.add_argument("--check-sp", action="store_true", help="tiny model: sequence-parallel ranks == single learner on the whole rows")
     a = ap.parse_args()
     import os
     if a.check_sp:
-        print(json.dumps(check_sp()))
+        print(json.dumps(check_sp(a.policy_loss)))
         return
     if a.check:
         print(json.dumps(check_dp()))
@@ -289,7 +290,7 @@ def check_dp(group=None, own_process_group=True):
     return out if rank == 0 else {"ok": bool(ok), "world": world, "rank": rank, "max_abs_diff": max_abs, "grad_norm": gn}
 
 
-def check_sp():
+def check_sp(policy_loss="ppo"):
     """`seq_parallel` = world ranks share every packed row (slices of the same micro-batch, all-gathered K / V, local loss
     shift)  ==  one learner running the whole rows with the slice-leading labels masked (a slice's first token has no
     predecessor on its rank, so sequence parallelism never scores it -- reference rl/__init__.py:207-212 on make_slices)."""
@@ -303,7 +304,7 @@ def check_sp():
         dist.init_process_group("nccl", device_id=dev)
     cfg = ModelConfig(vocab_size=1024, hidden_size=512, intermediate_size=1024, num_layers=2, num_q_heads=4, num_kv_heads=2)
     micro, T = 2, 768
-    rcfg = RLConfig(batch_size=micro * 3)
+    rcfg = RLConfig(batch_size=micro * 3, policy_loss=policy_loss)
     batches = [synthetic_batch(cfg, T, 3, dev, 17 + i) for i in range(micro)]
     for b in batches:
         b.input_ids %= cfg.vocab_size
@@ -348,7 +349,7 @@ def check_sp():
     identical = all(torch.equal(g, gathered[0]) for g in gathered)
     loss_ok = abs(float(lt) - loss_ref) <= 2e-3 * max(1.0, abs(loss_ref))
     ok = identical and loss_ok and same > 0.98 and max_abs <= 2.5e-3 + 2 ** -7 * ref.float().abs().max().item() and abs(gn - gn_ref) <= 1e-2 * gn_ref
-    out = {"ok": bool(ok), "check": "sequence_parallel", "world": world, "ranks_bit_identical": bool(identical),
+    out = {"ok": bool(ok), "check": "sequence_parallel", "policy_loss": policy_loss, "world": world, "ranks_bit_identical": bool(identical),
            "params_equal_to_single_learner": round(same, 5), "max_abs_diff": max_abs, "grad_norm": gn, "grad_norm_single": gn_ref,
            "loss_sum_over_ranks": float(lt), "loss_single": loss_ref}
     dist.barrier()
