@@ -470,7 +470,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         ptx::mbar_wait(bar(9 + s), ph);              // P_s of step i is in TMEM (and O_s rescaled if it had to be)
         const long long c1 = clock64();
         ptx::mbar_wait(bar(13 + vs_), (uint32_t)((i / kSt) & 1));   // V of step i landed
-        w_p += c1 - c0; w_v += clock64() - c1;
+        if (kTimed) { w_p += c1 - c0; w_v += clock64() - c1; }
         ptx::tc_fence_after_sync();
         const uint32_t v_addr = kv_smem + (uint32_t)(vs_ * kStageBytesT) + 2 * kTile16K;
         if (ptx::elect_one()) {
@@ -484,6 +484,7 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           ptx::tc_commit_multicast(bar(16 + vs_), 3);  // V slot consumed: tell BOTH producers
         }
       }
+      if (timed && lane == 0) { p.timing[16] = w_p; p.timing[17] = w_v; p.timing[18] = clock64() - w_tot0; p.timing[19] = n_it; }
     }
     __syncwarp();
   } else {
