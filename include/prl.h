@@ -336,6 +336,10 @@ int prl_gemm_ex(const void* A, int64_t lda, int32_t a_mn_major, const void* B, i
  * Bit-identical to prl_gemm_ex + prl_silu_mul_fwd.  I must be a multiple of 128. */
 int prl_gemm_swiglu(const void* X, int64_t ldx, const void* W, int64_t ldw, int64_t M, int64_t I, int64_t K, void* act,
                     int64_t ld_act, void* gate_up /*or NULL*/, int64_t ld_gate_up, prl_stream_t stream);
+/* sampler form (chunked prefill): act = bf16(SiLU(gate) * up) of the fp32 accumulators, i.e. the bits of
+ * prl_gemm_tn(fp32 out) + prl_silu_mul without the [M, 2I] fp32 round trip through HBM */
+int prl_gemm_swiglu_f32(const void* X_bf16, int64_t ldx, const void* W_gate_up_bf16, int64_t ldw, int64_t M, int64_t I,
+                        int64_t K, void* act_bf16, int64_t ld_act, prl_stream_t stream);
 /* bf16 [rows, cols] (row stride ld_in) -> [cols, rows] (row stride ld_out): stages the K-major operands of wgrad. */
 int prl_transpose_bf16(const void* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
                        prl_stream_t stream);

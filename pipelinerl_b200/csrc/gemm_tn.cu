@@ -52,6 +52,7 @@ struct TnParams {
   // the up rows of the SAME 128 features, so one accumulator row holds gate (columns 0..127) and up (128..255):
   //   act[row, f] = silu(gate) * up   is written from the epilogue (bf16), gate_up itself to C only when C != NULL
   int64_t swiglu_I;
+  int swiglu_fp32;      // 1: SiLU(gate) * up of the fp32 ACCUMULATORS (the sampler's rounding points, decode_ops.cu silu_mul_kernel)
   __nv_bfloat16* act;      // [M, ld_act]
   int64_t ld_act;
   // head epilogue (kHead): logits never leave TMEM/registers
@@ -255,6 +256,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             for (int e = 0; e < 4; ++e) {
               // same rounding points as the two-kernel path: gate_up is rounded to bf16 first, SiLU * up is taken of the
               // ROUNDED values (prl_silu_mul_fwd reads the bf16 tensor), so fused and unfused results are bit-identical
+              if (p.swiglu_fp32) {   // sampler prefill: identical bits to the fp32 GEMM output + silu_mul_kernel pair
+                const float g0 = __uint_as_float(rg[j + 2 * e]), g1 = __uint_as_float(rg[j + 2 * e + 1]);
+                const float u0 = __uint_as_float(ru[j + 2 * e]), u1 = __uint_as_float(ru[j + 2 * e + 1]);
+                ha[e] = __floats2bfloat162_rn((g0 / (1.f + __expf(-g0))) * u0, (g1 / (1.f + __expf(-g1))) * u1);
+                continue;
+              }
               hg[e] = __floats2bfloat162_rn(__uint_as_float(rg[j + 2 * e]), __uint_as_float(rg[j + 2 * e + 1]));
               hu[e] = __floats2bfloat162_rn(__uint_as_float(ru[j + 2 * e]), __uint_as_float(ru[j + 2 * e + 1]));
               const float2 g = __bfloat1622float2(hg[e]), u = __bfloat1622float2(hu[e]);
@@ -493,8 +500,24 @@ extern "C" int prl_gemm_ex(const void* A, int64_t lda, int32_t a_mn_major, const
 
 // gate_up GEMM with the SwiGLU activation in its epilogue: act[M, I] = silu(X Wg^T) * (X Wu^T), W = [Wg; Wu] ([2 I, K]).
 // gate_up (bf16 [M, 2 I], may be NULL) is written as well when the backward will need it.
+static int gemm_swiglu_impl(const void* X, int64_t ldx, const void* W, int64_t ldw, int64_t M, int64_t I, int64_t K,
+                            void* act, int64_t ld_act, void* gate_up, int64_t ld_gu, int fp32_act, prl_stream_t stream_);
+
 extern "C" int prl_gemm_swiglu(const void* X, int64_t ldx, const void* W, int64_t ldw, int64_t M, int64_t I, int64_t K,
                                void* act, int64_t ld_act, void* gate_up, int64_t ld_gu, prl_stream_t stream_) {
+  return gemm_swiglu_impl(X, ldx, W, ldw, M, I, K, act, ld_act, gate_up, ld_gu, 0, stream_);
+}
+
+// Sampler form (chunked prefill / scoring): act = bf16(SiLU(gate) * up) taken of the fp32 accumulators -- the rounding points
+// of the token step's GEMM + silu_mul_kernel pair, so a prompt prefilled in chunks and a prompt decoded token by token see
+// the same MLP arithmetic; gate_up itself is never written.
+extern "C" int prl_gemm_swiglu_f32(const void* X, int64_t ldx, const void* W, int64_t ldw, int64_t M, int64_t I, int64_t K,
+                                   void* act, int64_t ld_act, prl_stream_t stream_) {
+  return gemm_swiglu_impl(X, ldx, W, ldw, M, I, K, act, ld_act, nullptr, 0, 1, stream_);
+}
+
+static int gemm_swiglu_impl(const void* X, int64_t ldx, const void* W, int64_t ldw, int64_t M, int64_t I, int64_t K,
+                            void* act, int64_t ld_act, void* gate_up, int64_t ld_gu, int fp32_act, prl_stream_t stream_) {
   PRL_CHECK_ARG(X && W && act, "prl_gemm_swiglu: NULL argument");
   PRL_CHECK_ARG(M >= 1 && I >= kHalf && I % kHalf == 0 && K >= 8, "prl_gemm_swiglu: need I %% 128 == 0 (M=%lld I=%lld K=%lld)",
                 (long long)M, (long long)I, (long long)K);
@@ -508,7 +531,7 @@ extern "C" int prl_gemm_swiglu(const void* X, int64_t ldx, const void* W, int64_
   p.m_tiles = (int)((M + kTile - 1) / kTile);
   p.n_tiles = (int)(I / kHalf);
   p.C = gate_up; p.ldc = ld_gu; p.alpha = 1.f;
-  p.swiglu_I = I; p.act = (__nv_bfloat16*)act; p.ld_act = ld_act;
+  p.swiglu_I = I; p.swiglu_fp32 = fp32_act; p.act = (__nv_bfloat16*)act; p.ld_act = ld_act;
   CUtensorMap ta, tb;
   int rc = make_tmap_2d_bf16(&ta, X, (uint64_t)K, (uint64_t)M, (uint64_t)ldx * 2, kBK, kHalf);
   if (rc) return rc;

@@ -146,3 +146,28 @@ def test_gemm_swiglu_epilogue_is_bit_identical_to_gemm_plus_silu(cuda_device, T,
     ref = x.float() @ W.float().t()
     want = torch.nn.functional.silu(ref[:, :I]) * ref[:, I:]
     assert (act.float() - want).abs().max().item() <= 2 ** -6 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("T,K,I", [(1024, 512, 256), (1000, 896, 1152), (130, 256, 128)])
+def test_gemm_swiglu_f32_is_bit_identical_to_fp32_gemm_plus_sampler_silu(cuda_device, T, K, I):
+    """The sampler's chunked prefill (engine.py): prl_gemm_swiglu_f32 == prl_gemm_tn with an fp32 output followed by
+    prl_silu_mul (the token step's own SiLU(gate) * up of fp32 values), bit for bit -- the fusion removes the [T, 2I] fp32
+    round trip, not a rounding point."""
+    from pipelinerl_b200 import _lib
+    lib = _lib.load()
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(T + K + I)
+    x = (torch.randn(T, K, generator=g, device=dev) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(2 * I, K, generator=g, device=dev) * K ** -0.5).to(torch.bfloat16)
+    part = torch.empty(T, 2 * I, dtype=torch.float32, device=dev)
+    _lib.check(lib.prl_gemm_tn(x.data_ptr(), K, W.data_ptr(), K, T, 2 * I, K, part.data_ptr(), 2 * I, 1, 0, None, None, 0, 1.0,
+                               _lib.stream_ptr()))
+    act_ref = torch.empty(T, I, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.prl_silu_mul(part.data_ptr(), 1, T, I, act_ref.data_ptr(), None, 0, _lib.stream_ptr()))
+    act = torch.empty(T, I, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.prl_gemm_swiglu_f32(x.data_ptr(), K, W.data_ptr(), K, T, I, K, act.data_ptr(), I, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(act, act_ref)
+    ref = x.float() @ W.float().t()
+    want = torch.nn.functional.silu(ref[:, :I]) * ref[:, I:]
+    assert (act.float() - want).abs().max().item() <= 2 ** -7 * want.abs().max().item()
