@@ -346,6 +346,11 @@ int prl_transpose_bf16(const void* in, int64_t rows, int64_t cols, int64_t ld_in
 int prl_gemm_bf16_splitk(const void* W, const void* W_lo /*or NULL*/, const void* X,
                          int64_t M, int64_t N, int64_t K, int32_t split_k /*0 = auto*/,
                          float* partials, prl_stream_t stream);
+/* Token-step gate_up GEMM with SiLU(gate) * up in its epilogue (M <= 128 tokens, split_k = 1): act[M, I] bf16 = the bits
+ * of prl_gemm_bf16_splitk(split_k = 1) followed by prl_silu_mul, in one launch (vLLM: fused SiluAndMul after the
+ * gate_up_proj GEMM).  W = gate_up_proj.weight [2 I, K] as stored, gate rows first. */
+int prl_gemm_swiglu_decode(const void* W_bf16, const void* X_bf16, int64_t M, int64_t I, int64_t K, void* act_bf16,
+                           prl_stream_t stream);
 
 /* Fused output head with IN-KERNEL logprob capture: logits = X W^T (+ W_lo) are produced tile by tile in
  * TMEM and reduced on the spot — per token logsumexp, exact entropy, the log-probability of a given target

@@ -129,6 +129,11 @@ struct GemmParams {
   unsigned long long seed;
   unsigned int step;
   HeadPart* head_part;      // [n_tiles, M]
+  // SwiGLU epilogue of the token step's gate_up GEMM (split_k == 1): the CTA's 128 weight rows are 64 GATE rows
+  // [64 t, 64 t + 64) and the 64 UP rows of the same features (I rows further down), and the epilogue writes
+  // act[token, feature] = bf16(SiLU(gate) * up) -- the bits of the partial tile + silu_mul_kernel pair, without the pair
+  int64_t swiglu_I;         // 0 = off
+  __nv_bfloat16* act;       // [M, swiglu_I]
 };
 
 template <int kNTile>
@@ -189,7 +194,12 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
       const int kcoord = (kb_begin + i) * kBlockK;
       const int wc0 = p.tiled ? 0 : kcoord;
       const int wc1 = p.tiled ? (n_tile * p.kblocks + kb_begin + i) * kBlockM : n0;
-      ptx::tma_load_2d(a_dst, &tm_w, wc0, wc1, full_bar(i), ptx::kEvictFirst);
+      if (p.swiglu_I) {   // tm_w boxes are 64 rows here: gate half, then up half of the same 64 features
+        ptx::tma_load_2d(a_dst, &tm_w, wc0, n_tile * 64, full_bar(i), ptx::kEvictFirst);
+        ptx::tma_load_2d(a_dst + L::kABytes / 2, &tm_w, wc0, (int)p.swiglu_I + n_tile * 64, full_bar(i), ptx::kEvictFirst);
+      } else {
+        ptx::tma_load_2d(a_dst, &tm_w, wc0, wc1, full_bar(i), ptx::kEvictFirst);
+      }
       if (lo) ptx::tma_load_2d(a_dst + L::kABytes, &tm_wlo, wc0, wc1, full_bar(i), ptx::kEvictFirst);
     }
     ptx::prefetch_tensormap(&tm_x);
@@ -222,7 +232,12 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
         const int kcoord = (kb_begin + i) * kBlockK;
         const int wc0 = p.tiled ? 0 : kcoord;
         const int wc1 = p.tiled ? (n_tile * p.kblocks + kb_begin + i) * kBlockM : n0;
-        ptx::tma_load_2d(a_dst, &tm_w, wc0, wc1, full_bar(s), ptx::kEvictFirst);
+        if (p.swiglu_I) {
+          ptx::tma_load_2d(a_dst, &tm_w, wc0, n_tile * 64, full_bar(s), ptx::kEvictFirst);
+          ptx::tma_load_2d(a_dst + L::kABytes / 2, &tm_w, wc0, (int)p.swiglu_I + n_tile * 64, full_bar(s), ptx::kEvictFirst);
+        } else {
+          ptx::tma_load_2d(a_dst, &tm_w, wc0, wc1, full_bar(s), ptx::kEvictFirst);
+        }
         uint32_t b_dst = a_dst + L::kABytes;
         if (lo) {
           ptx::tma_load_2d(a_dst + L::kABytes, &tm_wlo, wc0, wc1, full_bar(s), ptx::kEvictFirst);
@@ -272,6 +287,37 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
     const bool feat_ok = feat < p.N;
     constexpr int kChunk = kNTile < 32 ? 16 : 32;
     if constexpr (!kHead) {
+      if (p.swiglu_I) {
+        // ---- SwiGLU: accumulator rows 0..63 = gate, 64..127 = up of features [64 t, 64 t + 64); columns = tokens.  The up
+        //      half crosses to the gate half's threads through shared memory (the tile ring is drained), token-major so
+        //      that both the stores and the loads are conflict-free ----
+        float* xch = reinterpret_cast<float*>(smem_raw + (smem_base - ptx::smem_u32(smem_raw)));   // [kNTile][64]
+        const int r = (q & 1) * 32 + lane;             // feature inside the 64
+#pragma unroll 1
+        for (int c0 = 0; c0 < kNTile; c0 += kChunk) {
+          uint32_t v[kChunk];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+          if constexpr (kChunk == 32) ptx::tmem_ld_32x32b_x32(taddr, v);
+          else ptx::tmem_ld_32x32b_x16(taddr, v);
+          ptx::tmem_ld_wait();
+          if (q >= 2) {
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) xch[(c0 + j) * 64 + r] = __uint_as_float(v[j]);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (q < 2) {
+            const int64_t f = (int64_t)n_tile * 64 + r;
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+              if (c0 + j < m_valid) {
+                const float gg = __uint_as_float(v[j]), uu = xch[(c0 + j) * 64 + r];
+                p.act[(int64_t)(m0 + c0 + j) * p.swiglu_I + f] = __float2bfloat16_rn((gg / (1.f + __expf(-gg))) * uu);
+              }
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");   // xch is rewritten by the next chunk
+        }
+      } else {
       // ---- TMEM -> registers -> fp32 partial tile ----
       float* out = p.partials + ((int64_t)split * p.M + m0) * p.N + feat;
       // tensor-parallel row-parallel GEMM: the partial sums are ALSO stored straight into the peer GPU's reduction
@@ -298,6 +344,7 @@ gemm_swapab_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_consta
               if (c0 + j < m_valid) out_peer[(int64_t)(c0 + j) * p.N] = __uint_as_float(r[j]);
           }
         }
+      }
       }
     } else {
       // ---- fused output head: per token, online-softmax statistics over this tile's 128 vocabulary rows,
@@ -410,7 +457,8 @@ int launch_gemm(const CUtensorMap& tw, const CUtensorMap& twl, const CUtensorMap
   auto kernel = p.head ? gemm_swapab_kernel<kNTile, true> : gemm_swapab_kernel<kNTile, false>;
   static SmemAttr smem_attr[2] = {};
   PRL_CUDA(ensure_smem(kernel, smem, smem_attr[p.head ? 1 : 0]));
-  dim3 grid((unsigned)(((p.N + kBlockM - 1) / kBlockM) * ((p.M + kNTile - 1) / kNTile)), (unsigned)p.split_k, 1);
+  const int64_t feat_tiles = p.swiglu_I ? p.swiglu_I / 64 : (p.N + kBlockM - 1) / kBlockM;
+  dim3 grid((unsigned)(feat_tiles * ((p.M + kNTile - 1) / kNTile)), (unsigned)p.split_k, 1);
   PRL_CUDA(launch_pdl(kernel, grid, dim3(kThreads), (size_t)smem, stream, tw, twl, tx, p, n_stages));
   PRL_LAUNCH_CHECK();
   return PRL_OK;
@@ -620,6 +668,34 @@ extern "C" int prl_gemm_auto_split_k(int64_t M, int64_t N, int64_t K) {
 
 static int gemm_splitk_impl(const void* W, const void* W_lo, const void* X, int64_t M, int64_t N, int64_t K,
                             int32_t split_k, float* partials, float* peer_partials, prl_stream_t stream_);
+
+// Token-step gate_up GEMM with SiLU(gate) * up in its epilogue (sampler side, M <= 128 tokens, no split-K: 2 I / 128 tiles
+// already fill the SMs): act[M, I] bf16 = the bits prl_gemm_bf16_splitk(split_k = 1) + prl_silu_mul produce, one launch and
+// no [M, 2 I] fp32 tile in between.  W = gate_up_proj [2 I, K] as stored (gate rows first).
+extern "C" int prl_gemm_swiglu_decode(const void* W, const void* X, int64_t M, int64_t I, int64_t K, void* act_bf16,
+                                      prl_stream_t stream_) {
+  PRL_CHECK_ARG(W && X && act_bf16, "prl_gemm_swiglu_decode: NULL argument");
+  PRL_CHECK_ARG(M >= 1 && M <= 128 && I >= 64 && I % 64 == 0 && K >= 8 && K % 8 == 0,
+                "prl_gemm_swiglu_decode: need 1 <= M <= 128, I %% 64 == 0, K %% 8 == 0 (M=%lld I=%lld K=%lld)", (long long)M,
+                (long long)I, (long long)K);
+  PRL_CHECK_ARG(!g_tiled_weights, "prl_gemm_swiglu_decode: not available with pre-tiled weights");
+  const int nt = pick_ntile(M);
+  GemmParams p = {};
+  p.M = M; p.N = 2 * I; p.K = K; p.kblocks = (int)((K + kBlockK - 1) / kBlockK); p.split_k = 1;
+  p.swiglu_I = I; p.act = (__nv_bfloat16*)act_bf16;
+  CUtensorMap tw, tx;
+  int rc = make_tmap_2d_bf16(&tw, W, (uint64_t)K, (uint64_t)(2 * I), (uint64_t)K * 2, kBlockK, 64);   // 64-row boxes
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tx, X, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kBlockK, (uint32_t)nt);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  switch (nt) {
+    case 16: return launch_gemm<16>(tw, tw, tx, p, stream);
+    case 32: return launch_gemm<32>(tw, tw, tx, p, stream);
+    case 64: return launch_gemm<64>(tw, tw, tx, p, stream);
+    default: return launch_gemm<128>(tw, tw, tx, p, stream);
+  }
+}
 
 extern "C" int prl_gemm_bf16_splitk(const void* W, const void* W_lo, const void* X, int64_t M, int64_t N, int64_t K,
                                     int32_t split_k, float* partials, prl_stream_t stream_) {

@@ -77,6 +77,8 @@ class DecodeEngine:
         self.l2_prefetch_bytes = 0          # cross-kernel L2 prefetch budget per site; measured to HURT (+0.19 ms/step,
                                             # profiles/r1_ablation.jsonl: HBM is already saturated), so off
         self._skip: set[str] = set()        # timing ablations only (tools/step_ablation.py)
+        # SiLU(gate) * up in the gate_up GEMM's epilogue (prl_gemm_swiglu_decode); PRL_FUSE_SWIGLU=0 keeps the two-kernel pair
+        self.fuse_swiglu = os.environ.get("PRL_FUSE_SWIGLU", "1") != "0"
         d, B, H, I = self.dev, self.B, cfg.hidden_size, cfg.intermediate_size
         kv_elems = cfg.num_layers * 2 * self.n_pages * cfg.num_kv_heads * PAGE_SIZE * cfg.head_dim
         self.kv_cache = torch.zeros(kv_elems, dtype=torch.bfloat16, device=d)
@@ -211,6 +213,7 @@ class DecodeEngine:
         part = self.partials
         skip = self._skip
         pf = self.l2_prefetch_bytes  # cross-kernel L2 prefetch budget per site (0 disables)
+        fuse_swiglu = (self.fuse_swiglu and not skip and not pf and self.split_k["gate_up"] == 1 and I % 64 == 0 and B <= 128)
 
         def wbytes(name):  # whole weight tensor, capped by the budget
             shape = a.layout.shapes[name]
@@ -248,14 +251,20 @@ class DecodeEngine:
                                                     self.h.data_ptr(), self.x.data_ptr(),
                                                     a.ptr(p + "down_proj.weight") if pf else None,
                                                     wbytes(p + "down_proj.weight"), st))
-            if "gemm" not in skip:
-                self._gemm(p + "gate_up_proj.weight", self.x, 2 * I, H, self.split_k["gate_up"], part)
             nxt_qkv = f"layers.{l + 1}.qkv_proj.weight" if l + 1 < cfg.num_layers else None
-            if "small" not in skip:
-                # while down streams, L2 fetches the next layer's qkv_proj
-                _lib.check(lib.prl_silu_mul(part.data_ptr(), self.split_k["gate_up"], B, I, self.act.data_ptr(),
-                                            a.ptr(nxt_qkv) if (pf and nxt_qkv) else None,
-                                            wbytes(nxt_qkv) if nxt_qkv else 0, st))
+            if fuse_swiglu:
+                # SiLU(gate) * up in the gate_up GEMM's epilogue (no split-K here: 2 I / 128 tiles fill the SMs): one launch
+                # less per layer and no [B, 2 I] fp32 tile between the two; same bits as the pair below
+                _lib.check(lib.prl_gemm_swiglu_decode(a.ptr(p + "gate_up_proj.weight"), self.x.data_ptr(), B, I, H,
+                                                      self.act.data_ptr(), st))
+            else:
+                if "gemm" not in skip:
+                    self._gemm(p + "gate_up_proj.weight", self.x, 2 * I, H, self.split_k["gate_up"], part)
+                if "small" not in skip:
+                    # while down streams, L2 fetches the next layer's qkv_proj
+                    _lib.check(lib.prl_silu_mul(part.data_ptr(), self.split_k["gate_up"], B, I, self.act.data_ptr(),
+                                                a.ptr(nxt_qkv) if (pf and nxt_qkv) else None,
+                                                wbytes(nxt_qkv) if nxt_qkv else 0, st))
             if "gemm" not in skip:
                 self._gemm(p + "down_proj.weight", self.act, H, I, self.split_k["down"], part)
             nxt = f"layers.{l + 1}.input_layernorm.weight" if l + 1 < cfg.num_layers else "norm.weight"

@@ -154,3 +154,26 @@ def test_fused_head_many_tokens_statistics_only(cuda_device, M, V, K, with_targe
     assert torch.allclose(ent, -(ref.exp() * ref).sum(-1), atol=3e-4, rtol=1e-4)
     if with_targets:
         assert torch.allclose(lp_t, ref.gather(1, targets[:, None])[:, 0], atol=3e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("B,I,K", [(4, 128, 256), (16, 1152, 896), (64, 18944, 3584), (100, 256, 512), (33, 192, 64)])
+def test_token_step_swiglu_epilogue_is_bit_identical_to_gemm_plus_silu(cuda_device, B, I, K):
+    """prl_gemm_swiglu_decode (the CTA's 128 weight rows = 64 gate rows + the 64 up rows of the same features; the up half
+    crosses to the gate half's threads through shared memory) == prl_gemm_bf16_splitk(split_k = 1) + prl_silu_mul, bit for bit."""
+    from pipelinerl_b200 import _lib
+    lib = _lib.load()
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(B * 7 + I + K)
+    x = (torch.randn(B, K, generator=g, device=dev) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(2 * I, K, generator=g, device=dev) * K ** -0.5).to(torch.bfloat16)
+    part = torch.empty(1, B, 2 * I, dtype=torch.float32, device=dev)
+    _lib.check(lib.prl_gemm_bf16_splitk(W.data_ptr(), None, x.data_ptr(), B, 2 * I, K, 1, part.data_ptr(), _lib.stream_ptr()))
+    want = torch.empty(B, I, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.prl_silu_mul(part.data_ptr(), 1, B, I, want.data_ptr(), None, 0, _lib.stream_ptr()))
+    got = torch.full((B, I), float("nan"), dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.prl_gemm_swiglu_decode(W.data_ptr(), x.data_ptr(), B, I, K, got.data_ptr(), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    ref = x.float() @ W.float().t()
+    fp32 = torch.nn.functional.silu(ref[:, :I]) * ref[:, I:]
+    assert (got.float() - fp32).abs().max().item() <= 2 ** -7 * fp32.abs().max().item() + 1e-6
