@@ -394,3 +394,30 @@ def test_one_layer_qwen7b_width_decode_step_vs_oracle(cuda_device):
     rel = np.abs(got - want) / np.abs(want)
     print(f"[7B-width one layer] max rel |dlogprob| {rel.max():.2e}  mean {rel.mean():.2e}  (|logprob| ~ {np.abs(want).mean():.2f})")
     assert rel.mean() <= 1e-3 and rel.max() <= 2.1e-3, (rel.max(), rel.mean(), int(rel.argmax()))
+
+
+def test_token_step_with_and_without_the_swiglu_epilogue_is_bit_identical(cuda_device):
+    """The token step's gate_up GEMM carries SiLU(gate) * up in its epilogue when it runs without split-K
+    (prl_gemm_swiglu_decode; Qwen2.5-7B widths do).  Same one-layer 7B-width model, same tokens: the logits of every step are
+    bitwise those of the GEMM + prl_silu_mul pair (engine.fuse_swiglu = False)."""
+    from dataclasses import replace
+    from pipelinerl_b200.engine import SamplingParams
+    from pipelinerl_b200.model import ModelConfig
+    cfg = replace(ModelConfig.qwen2_5_7b(), num_layers=1, vocab_size=4096)
+    w = tiny_weights(cfg, std=0.02, bias_std=0.1)
+    g = torch.Generator().manual_seed(6)
+    tokens = torch.randint(0, cfg.vocab_size, (12,), generator=g).tolist()
+    logits = {}
+    for fuse in (True, False):
+        eng = make_engine(cfg, w, cuda_device, max_batch=4, max_seq_len=128, max_new_tokens=4, use_cuda_graph=False,
+                          prefill_chunk=0, fused_head=False)
+        eng.fuse_swiglu = fuse
+        assert eng.split_k["gate_up"] == 1     # otherwise the fused path is not taken and the test proves nothing
+        eng.add_request(tokens, SamplingParams(max_tokens=2, temperature=1.0, greedy=True))
+        rows = []
+        for _ in range(len(tokens) - 1):
+            eng.step()
+            rows.append(eng.logits[0].clone())
+        logits[fuse] = torch.stack(rows)
+        del eng
+    assert torch.equal(logits[True], logits[False])
