@@ -164,6 +164,13 @@ int prl_logprob_rows_bwd(const float* logits, int64_t n_rows, int64_t V, int64_t
                          const int64_t* targets /*[n_rows]*/, float temperature, const float* lse,
                          const float* entropy, const float* g_logprobs, const float* g_entropy,
                          float* dlogits, int64_t dlogits_stride, prl_stream_t stream);
+/* Backward of the fused head WITHOUT materialised logits: one GEMM (X W_hi^T + X W_lo^T in TMEM, as prl_head_logprob) whose
+ * epilogue writes dz[M, ld_dz] bf16 = inv_T * (g_lp * (onehot(target) - p) - g_ent * p * (log p + H)), p = exp(z / T - lse):
+ * the operand of the dX / dW GEMMs.  Replaces logits GEMM(s) -> prl_logprob_rows_bwd -> bf16 cast (autograd through
+ * rl/__init__.py:207-233).  lse / entropy: the forward's outputs; g_logprobs / g_entropy may be NULL. */
+int prl_head_dlogits(const void* W_bf16, const void* W_lo_bf16, const void* X_bf16, int64_t M, int64_t V, int64_t K,
+                     float temperature, const int64_t* targets, const float* lse, const float* entropy,
+                     const float* g_logprobs, const float* g_entropy, void* dz_bf16, int64_t ld_dz, prl_stream_t stream);
 
 /* ======================================================================= *
  * Hot path (2c): fused AdamW over a flat parameter arena

@@ -233,6 +233,8 @@ _SIGNATURES = {
     "prl_logprob_rows_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_void_p]),
+    "prl_head_dlogits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "prl_adamw_sharded_reduce": (C.c_int, [C.POINTER(AdamwShardArgs), C.c_void_p, C.c_size_t, C.c_void_p]),
     "prl_adamw_sharded_update": (C.c_int, [C.POINTER(AdamwShardArgs), C.c_void_p, C.c_void_p]),
     "prl_adamw_workspace_bytes": (C.c_size_t, []),

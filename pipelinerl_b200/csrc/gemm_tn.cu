@@ -58,6 +58,14 @@ struct TnParams {
   // head epilogue (kHead): logits never leave TMEM/registers
   const int64_t* targets;  // [M] or NULL
   float4* head_part;       // [n_tiles, M]: (max, sum exp, sum exp*z, target logit or -inf) of one 256-column vocabulary tile
+  // head BACKWARD epilogue (kHead, dz != NULL): the logits tile is turned into d loss / d logits in registers and only its
+  // bf16 value reaches HBM -- dz[row, col] = inv_T * (g_lp * ([col == target] - p) - g_ent * p * (log p + H))
+  __nv_bfloat16* dz;       // [M, ld_dz]
+  int64_t ld_dz;
+  const float* bwd_lse;    // [M] natural-log logsumexp of the scaled logits (forward)
+  const float* bwd_ent;    // [M] entropy (forward) or NULL
+  const float* bwd_g_lp;   // [M] d loss / d logprob, or NULL (treated as 0)
+  const float* bwd_g_ent;  // [M] d loss / d entropy, or NULL
 };
 
 __device__ __forceinline__ void tile_coords(int t, const TnParams& p, int& tm, int& tn) {
@@ -198,6 +206,48 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         // thread = one token; online softmax statistics over this tile's 256 vocabulary columns, all thread-local
         constexpr float kLog2e = 1.4426950408889634f;
         const int64_t tgt = (p.targets && row_ok) ? p.targets[row] : -1;
+        if (p.dz != nullptr) {
+          // ---- backward: logits -> d logits (same formula as tail_bwd_kernel, logprob_tail.cu), written as bf16 ----
+          const float lse = row_ok ? p.bwd_lse[row] : 0.f;
+          const float gl = (p.bwd_g_lp && row_ok) ? p.bwd_g_lp[row] : 0.f;
+          const float ge = (p.bwd_g_ent && row_ok) ? p.bwd_g_ent[row] : 0.f;
+          const float H = (p.bwd_g_ent && p.bwd_ent && row_ok) ? p.bwd_ent[row] : 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < kTile; c0 += 32) {
+            if (col0 + c0 >= p.N) break;
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTile + c0), r);
+            ptx::tmem_ld_wait();
+            if (!row_ok) continue;
+            const int64_t col = col0 + c0;
+            const int n_ok = (int)((p.N - col) < 32 ? (p.N - col) : 32);
+            __nv_bfloat16* dst = p.dz + row * p.ld_dz + col;
+            const uint64_t rel = (uint64_t)(tgt - col);
+            float g[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float lp = __uint_as_float(r[j]) * p.alpha - lse;
+              const float pr = __expf(lp);
+              float v = -gl * pr - ge * pr * (lp + H);
+              if (rel == (uint64_t)j) v += gl;
+              g[j] = v * p.alpha;
+            }
+            if (n_ok == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 u;
+                __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) hb[e] = __floats2bfloat162_rn(g[j + 2 * e], g[j + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(dst + j) = u;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < n_ok) dst[j] = __float2bfloat16_rn(g[j]);
+            }
+          }
+        } else {
         float m = -INFINITY, ssum = 0.f, usum = 0.f, zt = -INFINITY;
 #pragma unroll 1
         for (int c0 = 0; c0 < kTile; c0 += 32) {
@@ -234,6 +284,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           }
         }
         if (row_ok) p.head_part[(int64_t)tn * p.M + row] = make_float4(m, ssum, usum, zt);
+        }   // forward statistics
       } else if (p.swiglu_I) {
         // columns 0..127 of the accumulator = gate, 128..255 = up of features [tn * 128, tn * 128 + 128)
         const int64_t f0 = (int64_t)tn * kHalf;
@@ -585,6 +636,50 @@ int head_logprob_tn(const void* W, const void* W_lo, const void* X, int64_t M, i
   return PRL_OK;
 }
 }  // namespace prl
+
+// Backward of the fused output head without materialised logits: dz[M, ld_dz] (bf16) = d loss / d logits for every row, from
+// ONE GEMM (X W_hi^T + X W_lo^T accumulated in TMEM, as the forward) whose epilogue applies
+//   dz = inv_T * (g_lp * (onehot(target) - p) - g_ent * p * (log p + H)),   p = exp(z * inv_T - lse)
+// in registers (reference: autograd through logits/T -> log_softmax / entropy, rl/__init__.py:207-233).  dz is the operand of
+// the dX and dW GEMMs that follow; fp32 logits, fp32 d logits and the cast pass never exist.
+extern "C" int prl_head_dlogits(const void* W, const void* W_lo, const void* X, int64_t M, int64_t V, int64_t K,
+                                float temperature, const int64_t* targets, const float* lse, const float* entropy,
+                                const float* g_logprobs, const float* g_entropy, void* dz_bf16, int64_t ld_dz,
+                                prl_stream_t stream_) {
+  using namespace prl;
+  PRL_CHECK_ARG(W && X && targets && lse && dz_bf16, "prl_head_dlogits: NULL argument");
+  PRL_CHECK_ARG(M >= 1 && V >= 1 && K >= 8 && K % 8 == 0 && ld_dz >= V && ld_dz % 8 == 0 && temperature > 0.f,
+                "prl_head_dlogits: bad shape (M=%lld V=%lld K=%lld ld_dz=%lld)", (long long)M, (long long)V, (long long)K,
+                (long long)ld_dz);
+  PRL_CHECK_ARG(!g_entropy || entropy, "prl_head_dlogits: g_entropy needs the forward entropy");
+  TnParams p = {};
+  p.M = M; p.N = V; p.K = K;
+  p.kblocks = (int)((K + kBK - 1) / kBK);
+  p.k_wrap = p.kblocks;
+  if (W_lo) p.kblocks *= 2;
+  p.m_tiles = (int)((M + kTile - 1) / kTile);
+  p.n_tiles = (int)((V + kTile - 1) / kTile);
+  p.alpha = 1.f / temperature;
+  p.targets = targets;
+  p.dz = (__nv_bfloat16*)dz_bf16; p.ld_dz = ld_dz;
+  p.bwd_lse = lse; p.bwd_ent = entropy; p.bwd_g_lp = g_logprobs; p.bwd_g_ent = g_entropy;
+  CUtensorMap ta, tb, tb2;
+  int rc = make_tmap_2d_bf16(&ta, X, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kBK, kHalf);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tb, W, (uint64_t)K, (uint64_t)V, (uint64_t)K * 2, kBK, kHalf);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tb2, W_lo ? W_lo : W, (uint64_t)K, (uint64_t)V, (uint64_t)K * 2, kBK, kHalf);
+  if (rc) return rc;
+  const int smem = kStages * kStageBytes + 1024 + 8 * (2 * kStages + 4) + 16;
+  static SmemAttr smem_attr = {};
+  PRL_CUDA(ensure_smem(gemm_tn_kernel<true>, smem, smem_attr));
+  const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
+  int clusters = num_sms() / 2;
+  if (tiles < clusters) clusters = (int)tiles;
+  gemm_tn_kernel<true><<<dim3((unsigned)(2 * clusters)), dim3(kThreadsTN), (size_t)smem, (cudaStream_t)stream_>>>(ta, tb, tb2, p);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
 
 extern "C" int prl_transpose_bf16(const void* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
                                   prl_stream_t stream_) {

@@ -121,9 +121,9 @@ class TorchQwen2(torch.nn.Module):
 
 class _NativeHead(torch.autograd.Function):
     """Final projection + log-softmax statistics of the native learner.  Forward: one tcgen05 GEMM whose epilogue
-    reduces logits in TMEM (prl_head_logprob).  Backward: per chunk of rows, logits recomputed by the same kernel,
-    d logits formed in one pass (prl_logprob_rows_bwd), then dX = dZ W and dW += dZ^T X (prl_gemm_ex, operands read as
-    stored), the latter accumulated in fp32 in the optimizer's gradient arena."""
+    reduces logits in TMEM (prl_head_logprob).  Backward: per chunk of rows, the same GEMM again with an epilogue that turns
+    the logits tile into d logits in registers and stores it as bf16 (prl_head_dlogits), then dX = dZ W and dW += dZ^T X
+    (prl_gemm_ex, operands read as stored), the latter accumulated in fp32 in the optimizer's gradient arena."""
 
     @staticmethod
     def forward(ctx, hidden, model, targets, temperature: float, chunk_rows: int):
@@ -160,21 +160,18 @@ class _NativeHead(torch.autograd.Function):
         g_ent = g_ent.contiguous() if use_ent else None
         dx = torch.empty(M, K, dtype=torch.bfloat16, device=dev)
         Cn = min(ctx.chunk_rows, M)
-        logits_buf = torch.empty(Cn, V, dtype=torch.float32, device=dev)
-        dlogits_buf = torch.empty(Cn, V, dtype=torch.float32, device=dev)
+        # d logits of a chunk of rows, bf16, straight out of the GEMM that recomputes the logits (prl_head_dlogits): fp32
+        # logits / d logits never reach HBM (the reference's autograd keeps 608 KB of fp32 logits per token alive)
+        dz_buf = torch.empty(Cn, V, dtype=torch.bfloat16, device=dev)
         st = _lib.stream_ptr()
+        W_lo = model.head_lo
         for r0 in range(0, M, Cn):
             n = min(Cn, M - r0)
-            xs, logits, dlogits = x[r0:r0 + n], logits_buf[:n], dlogits_buf[:n]
-            ops.gemm(xs, W, out=logits)
-            if model.head_lo is not None:      # same fp32-equivalent logits as the forward: += X W_lo^T
-                ops.gemm(xs, model.head_lo, out=logits, accumulate=True)
-            _lib.check(lib.prl_logprob_rows_bwd(logits.data_ptr(), n, V, V, tg[r0:r0 + n].data_ptr(), ctx.temperature,
-                                                lse[r0:r0 + n].data_ptr(), ent[r0:r0 + n].data_ptr(),
-                                                g_lp[r0:r0 + n].data_ptr(),
-                                                g_ent[r0:r0 + n].data_ptr() if use_ent else None,
-                                                dlogits.data_ptr(), V, st))
-            dz = dlogits.to(torch.bfloat16)
+            xs, dz = x[r0:r0 + n], dz_buf[:n]
+            _lib.check(lib.prl_head_dlogits(W.data_ptr(), W_lo.data_ptr() if W_lo is not None else None, xs.data_ptr(), n, V, K,
+                                            ctx.temperature, tg[r0:r0 + n].data_ptr(), lse[r0:r0 + n].data_ptr(),
+                                            ent[r0:r0 + n].data_ptr(), g_lp[r0:r0 + n].data_ptr(),
+                                            g_ent[r0:r0 + n].data_ptr() if use_ent else None, dz.data_ptr(), V, st))
             ops.gemm(dz, W, out=dx[r0:r0 + n], b_mn=True)
             ops.wgrad(gW, dz, xs)
         return dx, None, None, None, None

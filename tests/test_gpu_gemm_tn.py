@@ -171,3 +171,48 @@ def test_gemm_swiglu_f32_is_bit_identical_to_fp32_gemm_plus_sampler_silu(cuda_de
     ref = x.float() @ W.float().t()
     want = torch.nn.functional.silu(ref[:, :I]) * ref[:, I:]
     assert (act.float() - want).abs().max().item() <= 2 ** -7 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("M,V,K,with_lo,with_ent", [(300, 1031, 256, True, True), (2048, 4096, 512, True, False),
+                                                     (130, 777, 128, False, True), (1, 520, 64, True, True)])
+def test_head_dlogits_without_materialised_logits(cuda_device, M, V, K, with_lo, with_ent):
+    """prl_head_dlogits: the head GEMM (hi + lo weight streams in one TMEM accumulation) with the backward of
+    log-softmax / entropy in its epilogue, bf16 d logits out.  Against fp32 torch autograd through logits / T ->
+    log_softmax -> (target logprob, entropy) on the same bf16 inputs, and the statistics of prl_head_logprob as inputs."""
+    from pipelinerl_b200 import _lib
+    lib = _lib.load()
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(M + V + K)
+    T = 0.7
+    x = (torch.randn(M, K, generator=g, device=dev) * 0.7).to(torch.bfloat16)
+    Wf = torch.randn(V, K, generator=g, device=dev) * K ** -0.5
+    W = Wf.to(torch.bfloat16)
+    W_lo = (Wf - W.float()).to(torch.bfloat16) if with_lo else None
+    tg = torch.randint(0, V, (M,), generator=g, device=dev)
+    g_lp = torch.randn(M, generator=g, device=dev)
+    g_ent = torch.randn(M, generator=g, device=dev) * 0.3 if with_ent else None
+    lp = torch.empty(M, device=dev)
+    ent, lse = torch.empty_like(lp), torch.empty_like(lp)
+    ws = torch.empty(int(lib.prl_head_workspace_bytes(M, V)), dtype=torch.uint8, device=dev)
+    _lib.check(lib.prl_head_logprob(W.data_ptr(), W_lo.data_ptr() if with_lo else None, x.data_ptr(), M, V, K, T, tg.data_ptr(),
+                                    1, 0, 0, lp.data_ptr(), ent.data_ptr(), lse.data_ptr(), None, None, ws.data_ptr(), ws.numel(),
+                                    _lib.stream_ptr()))
+    ld = (V + 7) // 8 * 8
+    dz = torch.zeros(M, ld, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.prl_head_dlogits(W.data_ptr(), W_lo.data_ptr() if with_lo else None, x.data_ptr(), M, V, K, T, tg.data_ptr(),
+                                    lse.data_ptr(), ent.data_ptr(), g_lp.data_ptr(), g_ent.data_ptr() if with_ent else None,
+                                    dz.data_ptr(), ld, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    Wsum = W.float() + (W_lo.float() if with_lo else 0.0)
+    z = (x.float() @ Wsum.t()).requires_grad_(True)
+    ls = torch.log_softmax(z / T, -1)
+    obj = (ls.gather(1, tg[:, None])[:, 0] * g_lp).sum()
+    if with_ent:
+        obj = obj + ((-(ls.exp() * ls).sum(-1)) * g_ent).sum()
+    obj.backward()
+    want = z.grad
+    err = (dz[:, :V].float() - want).abs().max().item() / want.abs().max().item()
+    print(f"[head dlogits M={M} V={V} K={K} lo={with_lo} ent={with_ent}] rel max err {err:.2e}")
+    assert err <= 2 ** -7
+    if ld > V:
+        assert torch.count_nonzero(dz[:, V:]) == 0      # padding columns are not touched
