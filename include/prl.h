@@ -347,6 +347,11 @@ int prl_gemm_swiglu(const void* X, int64_t ldx, const void* W, int64_t ldw, int6
  * prl_gemm_tn(fp32 out) + prl_silu_mul without the [M, 2I] fp32 round trip through HBM */
 int prl_gemm_swiglu_f32(const void* X_bf16, int64_t ldx, const void* W_gate_up_bf16, int64_t ldw, int64_t M, int64_t I,
                         int64_t K, void* act_bf16, int64_t ld_act, prl_stream_t stream);
+/* down_proj dgrad with the backward of SiLU(gate) * up in its epilogue: d_gate_up[M, 2 I] (= d gate | d up) from dY[M, H],
+ * W_down[H, I] as stored and the forward's gate_up[M, 2 I]; d act is never written.  Bit-identical to
+ * prl_gemm_ex(dY, W_down as MN-major B) followed by prl_silu_mul_bwd.  Needs I % 32 == 0. */
+int prl_gemm_dgrad_swiglu(const void* dY_bf16, int64_t ldy, const void* W_down_bf16, int64_t ldw, int64_t M, int64_t I, int64_t H,
+                          const void* gate_up_bf16, void* d_gate_up_bf16, int64_t ld_gu, prl_stream_t stream);
 /* bf16 [rows, cols] (row stride ld_in) -> [cols, rows] (row stride ld_out): stages the K-major operands of wgrad. */
 int prl_transpose_bf16(const void* in, int64_t rows, int64_t cols, int64_t ld_in, void* out, int64_t ld_out,
                        prl_stream_t stream);

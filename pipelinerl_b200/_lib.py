@@ -204,6 +204,8 @@ _SIGNATURES = {
     "prl_gemm_swiglu": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                   C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "prl_gemm_swiglu_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "prl_gemm_dgrad_swiglu": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "prl_gemm_swiglu_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                       C.c_void_p, C.c_int64, C.c_void_p]),
     "prl_bf16_residual": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -66,6 +66,11 @@ struct TnParams {
   const float* bwd_ent;    // [M] entropy (forward) or NULL
   const float* bwd_g_lp;   // [M] d loss / d logprob, or NULL (treated as 0)
   const float* bwd_g_ent;  // [M] d loss / d entropy, or NULL
+  // SiLU * up BACKWARD epilogue (dgu != NULL; N = I, requires I % 32 == 0): this GEMM's output tile IS d act; the epilogue
+  // reads gate / up of the forward and writes d gate | d up -- d act never reaches HBM
+  const __nv_bfloat16* bwd_gu;   // [M, ld_gu] gate | up of the forward
+  __nv_bfloat16* dgu;            // [M, ld_gu] d gate | d up
+  int64_t ld_gu;
 };
 
 __device__ __forceinline__ void tile_coords(int t, const TnParams& p, int& tm, int& tn) {
@@ -363,6 +368,34 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               if (col + j < p.N) v[j] += __bfloat162float(rp[j]);
           }
         }
+        if (p.dgu != nullptr) {
+          // d act tile -> (d gate, d up): same rounding points as the two-kernel path (d act rounded to bf16, then
+          // silu_mul_bwd_kernel's arithmetic, learner_ops.cu), so fused and unfused results are bit-identical
+          const __nv_bfloat16* gp = p.bwd_gu + row * p.ld_gu + col;
+          __nv_bfloat16* dp = p.dgu + row * p.ld_gu + col;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 ug = *reinterpret_cast<const uint4*>(gp + j);
+            const uint4 uu = *reinterpret_cast<const uint4*>(gp + p.N + j);
+            const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&ug);
+            const __nv_bfloat162* hu = reinterpret_cast<const __nv_bfloat162*>(&uu);
+            uint4 og, ou;
+            __nv_bfloat162* dg = reinterpret_cast<__nv_bfloat162*>(&og);
+            __nv_bfloat162* du = reinterpret_cast<__nv_bfloat162*>(&ou);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 g = __bfloat1622float2(hg[e]), u = __bfloat1622float2(hu[e]);
+              const float2 d = __bfloat1622float2(__floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]));
+              const float s0 = 1.f / (1.f + __expf(-g.x)), s1 = 1.f / (1.f + __expf(-g.y));
+              const float l0 = g.x * s0, l1 = g.y * s1;
+              du[e] = __floats2bfloat162_rn(d.x * l0, d.y * l1);
+              dg[e] = __floats2bfloat162_rn(d.x * u.x * (s0 + l0 * (1.f - s0)), d.y * u.y * (s1 + l1 * (1.f - s1)));
+            }
+            *reinterpret_cast<uint4*>(dp + j) = og;
+            *reinterpret_cast<uint4*>(dp + p.N + j) = ou;
+          }
+          continue;
+        }
         if (p.c_f32) {
           float* cp = reinterpret_cast<float*>(p.C) + row * p.ldc + col;
           if (full && ((p.ldc & 3) == 0)) {
@@ -537,6 +570,40 @@ extern "C" int prl_gemm_ex(const void* A, int64_t lda, int32_t a_mn_major, const
   if (rc) return rc;
   rc = b_mn_major ? make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, kBK)
                   : make_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBK, kHalf);
+  if (rc) return rc;
+  const int smem = kStages * kStageBytes + 1024 + 8 * (2 * kStages + 4) + 16;
+  static SmemAttr smem_attr = {};
+  PRL_CUDA(ensure_smem(gemm_tn_kernel<false>, smem, smem_attr));
+  const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
+  int clusters = num_sms() / 2;
+  if (tiles < clusters) clusters = (int)tiles;
+  gemm_tn_kernel<false><<<dim3((unsigned)(2 * clusters)), dim3(kThreadsTN), (size_t)smem, (cudaStream_t)stream_>>>(ta, tb, tb, p);
+  PRL_LAUNCH_CHECK();
+  return PRL_OK;
+}
+
+// down_proj dgrad with the backward of SiLU(gate) * up in its epilogue: d gate_up[M, 2 I] from dY[M, H], W_down[H, I] (read as
+// stored: MN-major B) and the forward's gate_up[M, 2 I]; d act = dY W_down is never written.  Bit-identical to
+// prl_gemm_ex(dY, W_down, b_mn) -> prl_silu_mul_bwd.
+extern "C" int prl_gemm_dgrad_swiglu(const void* dY, int64_t ldy, const void* W_down, int64_t ldw, int64_t M, int64_t I,
+                                     int64_t H, const void* gate_up, void* d_gate_up, int64_t ld_gu, prl_stream_t stream_) {
+  PRL_CHECK_ARG(dY && W_down && gate_up && d_gate_up, "prl_gemm_dgrad_swiglu: NULL argument");
+  PRL_CHECK_ARG(M >= 1 && I >= 32 && I % 32 == 0 && H >= 8 && ldy >= H && ldy % 8 == 0 && ldw >= I && ldw % 8 == 0 &&
+                ld_gu >= 2 * I && ld_gu % 8 == 0, "prl_gemm_dgrad_swiglu: bad shape (M=%lld I=%lld H=%lld)", (long long)M,
+                (long long)I, (long long)H);
+  TnParams p = {};
+  p.M = M; p.N = I; p.K = H;
+  p.kblocks = (int)((H + kBK - 1) / kBK);
+  p.k_wrap = p.kblocks;
+  p.m_tiles = (int)((M + kTile - 1) / kTile);
+  p.n_tiles = (int)((I + kTile - 1) / kTile);
+  p.alpha = 1.f;
+  p.b_mn = 1;
+  p.bwd_gu = (const __nv_bfloat16*)gate_up; p.dgu = (__nv_bfloat16*)d_gate_up; p.ld_gu = ld_gu;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d_bf16(&ta, dY, (uint64_t)H, (uint64_t)M, (uint64_t)ldy * 2, kBK, kHalf);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tb, W_down, (uint64_t)I, (uint64_t)H, (uint64_t)ldw * 2, 64, kBK);
   if (rc) return rc;
   const int smem = kStages * kStageBytes + 1024 + 8 * (2 * kStages + 4) + 16;
   static SmemAttr smem_attr = {};

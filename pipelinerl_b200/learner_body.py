@@ -104,6 +104,15 @@ class Ops:
                                             gu.data_ptr() if gu is not None else None, 2 * I, _lib.stream_ptr()))
         return gu, act
 
+    def dgrad_swiglu(self, dY, W_down, gu):
+        """d gate_up [T, 2I] = silu_mul_bwd(gu, dY W_down) with d act kept inside the GEMM (prl_gemm_dgrad_swiglu)"""
+        T, H = dY.shape
+        I = W_down.shape[1]
+        dgu = torch.empty_like(gu)
+        _lib.check(self.lib.prl_gemm_dgrad_swiglu(dY.data_ptr(), dY.stride(0), W_down.data_ptr(), W_down.stride(0), T, I, H,
+                                                  gu.data_ptr(), dgu.data_ptr(), gu.stride(0), _lib.stream_ptr()))
+        return dgu
+
     def silu_mul(self, gu):
         T, two_i = gu.shape
         act = torch.empty(T, two_i // 2, dtype=torch.bfloat16, device=gu.device)
@@ -207,6 +216,11 @@ class NativeBody:
         self.keep_attention_layers = cfg.num_layers   # lower it when activation memory is short (0 = full recompute)
         self.keep_gate_up_layers = 0                  # layers that also keep gate_up's output (2 I bf16 per token):
         #                                               their backward skips the largest recompute GEMM
+        import os
+        # SiLU * up backward inside the down_proj dgrad epilogue (prl_gemm_dgrad_swiglu, bit-identical): measured SLOWER on the 7B
+        # step (1 926 / 1 942 ms vs 1 898 / 1 904 ms, same box, alternating runs): the epilogue's strided gate / up reads and its
+        # 2 x 256 exp / rcp per thread outlast the short K = 3584 main loop, so the tile pipeline waits for it.  Off by default.
+        self.fuse_silu_bwd = os.environ.get("PRL_FUSE_SILU_BWD", "0") == "1"
         self.sp_group = None                          # sequence parallelism: see set_sequence_parallel
         self._sp_segs = None
 
@@ -302,11 +316,13 @@ class NativeBody:
             x2, rstd2 = o.rmsnorm(h2, w[p + "post_attention_layernorm.weight"], c.rms_eps)
             act = o.silu_mul(gu)
         T = h.shape[0]
-        d_act = o.dgrad(dh3, w[p + "down_proj.weight"])
         o.wgrad(g[p + "down_proj.weight"], dh3, act)
         del act
-        d_gu = o.silu_mul_bwd(gu, d_act)
-        del gu, d_act
+        if c.intermediate_size % 32 == 0 and self.fuse_silu_bwd:     # SiLU * up backward in the dgrad GEMM's epilogue: d act never reaches HBM
+            d_gu = o.dgrad_swiglu(dh3, w[p + "down_proj.weight"], gu)
+        else:
+            d_gu = o.silu_mul_bwd(gu, o.dgrad(dh3, w[p + "down_proj.weight"]))
+        del gu
         dx2 = o.dgrad(d_gu, w[p + "gate_up_proj.weight"])
         o.wgrad(g[p + "gate_up_proj.weight"], d_gu, x2)
         del d_gu, x2

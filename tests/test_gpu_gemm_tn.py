@@ -216,3 +216,19 @@ def test_head_dlogits_without_materialised_logits(cuda_device, M, V, K, with_lo,
     assert err <= 2 ** -7
     if ld > V:
         assert torch.count_nonzero(dz[:, V:]) == 0      # padding columns are not touched
+
+
+@pytest.mark.parametrize("T,H,I", [(300, 512, 1024), (257, 896, 1152), (1024, 3584, 18944), (5, 256, 160)])
+def test_dgrad_with_silu_backward_epilogue_is_bit_identical(cuda_device, T, H, I):
+    """prl_gemm_dgrad_swiglu (down_proj dgrad whose epilogue applies the backward of SiLU(gate) * up) == prl_gemm_ex with the
+    weight read as stored followed by prl_silu_mul_bwd, bit for bit."""
+    from pipelinerl_b200.learner_body import Ops
+    o = Ops()
+    g = torch.Generator(device=cuda_device).manual_seed(T + H + I)
+    dY = (torch.randn(T, H, generator=g, device=cuda_device) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(H, I, generator=g, device=cuda_device) * H ** -0.5).to(torch.bfloat16)
+    gu = torch.randn(T, 2 * I, generator=g, device=cuda_device).to(torch.bfloat16)
+    want = o.silu_mul_bwd(gu, o.dgrad(dY, W))
+    got = o.dgrad_swiglu(dY, W, gu)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
