@@ -17,6 +17,7 @@ arena layout and can be pushed as raw bytes.
 from __future__ import annotations
 
 import math
+import os
 import types
 
 import torch
@@ -162,9 +163,28 @@ class _NativeHead(torch.autograd.Function):
         Cn = min(ctx.chunk_rows, M)
         # d logits of a chunk of rows, bf16, straight out of the GEMM that recomputes the logits (prl_head_dlogits): fp32
         # logits / d logits never reach HBM (the reference's autograd keeps 608 KB of fp32 logits per token alive)
-        dz_buf = torch.empty(Cn, V, dtype=torch.bfloat16, device=dev)
         st = _lib.stream_ptr()
         W_lo = model.head_lo
+        if os.environ.get("PRL_HEAD_BWD_FUSED", "1") == "0":
+            # A/B only: the previous formulation -- logits recomputed (hi GEMM, lo GEMM accumulating), one row kernel, a cast
+            logits_buf = torch.empty(Cn, V, dtype=torch.float32, device=dev)
+            dlogits_buf = torch.empty(Cn, V, dtype=torch.float32, device=dev)
+            for r0 in range(0, M, Cn):
+                n = min(Cn, M - r0)
+                xs, logits, dlogits = x[r0:r0 + n], logits_buf[:n], dlogits_buf[:n]
+                ops.gemm(xs, W, out=logits)
+                if W_lo is not None:
+                    ops.gemm(xs, W_lo, out=logits, accumulate=True)
+                _lib.check(lib.prl_logprob_rows_bwd(logits.data_ptr(), n, V, V, tg[r0:r0 + n].data_ptr(), ctx.temperature,
+                                                    lse[r0:r0 + n].data_ptr(), ent[r0:r0 + n].data_ptr(),
+                                                    g_lp[r0:r0 + n].data_ptr(),
+                                                    g_ent[r0:r0 + n].data_ptr() if use_ent else None,
+                                                    dlogits.data_ptr(), V, st))
+                dz = dlogits.to(torch.bfloat16)
+                ops.gemm(dz, W, out=dx[r0:r0 + n], b_mn=True)
+                ops.wgrad(gW, dz, xs)
+            return dx, None, None, None, None
+        dz_buf = torch.empty(Cn, V, dtype=torch.bfloat16, device=dev)
         for r0 in range(0, M, Cn):
             n = min(Cn, M - r0)
             xs, dz = x[r0:r0 + n], dz_buf[:n]
