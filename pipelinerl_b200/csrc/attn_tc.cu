@@ -14,6 +14,10 @@
 // step against 16 per clock and SM).  Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner,
 // 2..9 = softmax / epilogue (two warps per TMEM lane quarter, each owning half of the keys / head-dim columns).
 //
+// That is GENERATION 1 (attn_prefill_tc_kernel).  The default for both entry points is generation 2 (attn_fwd_v2_kernel,
+// further down): two softmax groups in ping-pong, P and O in TMEM.  In both, the MMA warp runs converged and elects one lane
+// per batch of UMMAs (tc_ptx.cuh: elect_one).
+//
 // Tensor-bound: 4 * 128 * S^2 / 2 FLOP per head (causal); K/V bytes are re-read from L2 by the other query tiles.
 #include <stdlib.h>
 #include "prl_common.cuh"

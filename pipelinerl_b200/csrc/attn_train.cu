@@ -20,10 +20,13 @@
 //   * attn_bwd_dq_kernel    (Q stationary): the forward's structure (cluster pair of adjacent query tiles, K/V pages
 //     TMA-multicast to both CTAs, 128 keys per step) with  dP = dO V^T  as a third MMA and  dQ += dS K  in place of
 //     P V (K read as stored, MN-major).  TMEM: S double-buffered + dP + dQ.
-// Both: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = softmax (two warps per TMEM lane quarter).
+// Both: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner (the WHOLE warp runs converged and elects one lane per batch of
+// UMMAs: issued from `if (lane == 0)` every UMMA costs ~180 cycles of R2UR + ELECT waterfall, tc_ptx.cuh: elect_one), the other
+// warps = softmax: 8 in lock-step in generations 1-3, 16 that never meet in generation 4 (the default; further down).
+// All four generations produce the same bits.
 //
-// Tensor-bound.  Per (128 query rows x 128 keys) pair: 4 + 3 UMMAs of 4.2 MFLOP against 5 for the atomics-based
-// single-kernel formulation; 2 x 16 K exp2.
+// Tensor-bound (profiles/r2_attention.md: the MMA warps sit in UMMA issue back-pressure).  Per (128 query rows x 128 keys)
+// pair: 4 + 3 UMMA products of 4.2 MFLOP against 5 for the atomics-based single-kernel formulation; 2 x 16 K exp2.
 #include <stdlib.h>
 #include "prl_common.cuh"
 #include "tc_ptx.cuh"
