@@ -436,3 +436,33 @@ def test_unsupported_sampling_parameters_fail_loudly_in_process():
         llm = TrainableLLM("inproc://none", "m", parameters={"max_tokens": 4, **bad}, tokenizer=SyntheticTokenizer())
         with pytest.raises(ValueError):
             asyncio.run(llm_async_generate(llm, Prompt(messages=[{"role": "user", "content": "hi"}])))
+
+
+def test_lag_budget_matches_the_reference_actor_loop():
+    """tests/golden/lag_budget_cases.json = the reference's own statements (the `max_lag` arithmetic of pipelinerl/actor.py:509-534,
+    the weight-version block and the `blocked_by_lag` test of its loop, :551-577) executed on scripted ticks
+    (make_golden_lag_budget.py).  LagBudget must allow exactly the same submissions and hold the same budget after every tick."""
+    import json
+    import math
+    from pathlib import Path
+    from pipelinerl_b200.actor import LagBudget
+    doc = json.loads((Path(__file__).parent / "golden" / "lag_budget_cases.json").read_text())
+    assert len(doc["cases"]) >= 5
+    for name, case in doc["cases"].items():
+        version = {"v": 0}
+        lb = LagBudget(case["config"]["max_lag"], case["config"]["attempts"], case["config"]["train_batch_size"],
+                       case["config"]["gradient_accumulation_passes"], case["config"]["weight_update_interval"],
+                       lambda: version["v"])
+        assert lb.groups_per_update == case["groups_per_update"], name
+        total = 0
+        for (v, available), want in zip(case["ticks"], case["after_tick"]):
+            version["v"] = v
+            lb.observe()
+            n = 0
+            for _ in range(available):
+                if not lb.try_submit():
+                    break
+                n += 1
+            total += n
+            assert (n, total) == (want["submitted_in_tick"], want["submitted_total"]), (name, v, available, n, want)
+            assert (None if lb.can_submit == math.inf else lb.can_submit) == want["can_submit_before_update"], name
